@@ -1,0 +1,279 @@
+"""Parity cases shared by oracle/gen_golden.py (reference side, build container only) and tests/ (oracle and
+CUDA side).  TEST INFRASTRUCTURE.
+
+A case = (operation, per-activity UCI tables, time base, forcing recipe).  `run_segment` walks the activities
+of one segment exactly like the reference's dispatcher does (main.py:123-146, 249-250): registry order,
+skip when the ACTIVITY flag is 0, CSNOFG -> SEDMNT/PWTGAS and AIRTFG -> PSTEMP injections.
+"""
+import copy
+import os
+
+import numpy as np
+
+from hspsquared_b200 import test10
+from hspsquared_b200.test10 import monthly
+
+ORDER = {
+    "PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"),  # configuration.py:48-50
+    "IMPLND": ("ATEMP", "SNOW", "IWATER"),  # configuration.py:51-52 (SOLIDS/IWTGAS/IQUAL out of scope)
+}
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hspsquared_b200", "data")
+
+
+def run_segment(operation, tables, ts, siminfo, activities, io_manager=None):
+    """-> {activity: errors}; outputs land in ts.  `activities`: {name: callable(io, siminfo, uci, ts)}."""
+    flags = tables["ACTIVITY"]
+    errs = {}
+    for act in ORDER[operation]:
+        if act not in activities or not flags.get(act, 0):
+            continue
+        ui = tables[act]
+        if operation == "PERLND" and act in ("SEDMNT", "PWTGAS"):
+            ui["PARAMETERS"]["CSNOFG"] = tables["PWATER"]["PARAMETERS"]["CSNOFG"]
+        if operation == "PERLND" and act == "PSTEMP":
+            ui["PARAMETERS"]["AIRTFG"] = flags["ATEMP"]
+        e, _msgs = activities[act](io_manager, siminfo, ui, ts)
+        errs[act] = np.asarray(e, dtype=np.int64)
+    return errs
+
+
+# ---------------------------------------------------------------------------------------------------
+# forcing recipes (deterministic numpy, from the committed 1976 test10 met decoded by gen_golden.py)
+# ---------------------------------------------------------------------------------------------------
+_met_cache = {}
+
+
+def load_met():
+    if "met" not in _met_cache:
+        z = np.load(os.path.join(DATA, "test10_met_1976.npz"))
+        _met_cache["met"] = {k: z[k] for k in z.files}
+    return _met_cache["met"]
+
+
+FLOWS = ("PREC", "PETINP", "WINMOV", "SOLRAD")  # amounts per interval: split / summed on resampling
+
+
+def forcings(case):
+    """Hourly 1976 series -> the case's window and step.  Returns dict name -> float64[steps]."""
+    met = load_met()
+    pre = "P_" if case["met"] == "perlnd" else "I_"
+    names = ["PREC", "AIRTMP", "PETINP", "WINMOV", "SOLRAD", "DTMPG", "CLOUD"]
+    hourly = {n: met[pre + n].copy() for n in names}
+    if case["met"] == "flowtest":
+        hourly = {"PREC": met["F_PREC"].copy(), "PETINP": met["F_PETINP"].copy()}
+    h0 = case.get("hour0", 0)  # first hour of 1976 used
+    delt = case["delt"]
+    steps = case["steps"]
+    out = {}
+    for n, a in hourly.items():
+        if delt == 60:
+            v = a[h0:h0 + steps]
+        elif delt < 60:
+            k = 60 // delt
+            nh = (steps + k - 1) // k
+            v = np.repeat(a[h0:h0 + nh], k)[:steps]
+            if n in FLOWS:
+                v = v / k
+        else:
+            k = delt // 60
+            blk = a[h0:h0 + steps * k].reshape(steps, k)
+            v = blk.sum(axis=1) if n in FLOWS else blk[:, 0].copy()
+        out[n] = np.ascontiguousarray(v, dtype=np.float64)
+    for n in case.get("drop", ()):
+        out.pop(n, None)
+    rng = np.random.default_rng(case.get("seed", 7))
+    if case.get("rain_mult"):
+        out["PREC"] = out["PREC"] * case["rain_mult"]
+    if "gatmp" in case:  # ATEMP active: gauge temperature in, AIRTMP computed
+        out["GATMP"] = out.pop("AIRTMP") + case["gatmp"]
+    for n in case.get("lateral", ()):  # sparse positive lateral inflow series
+        a = rng.random(steps)
+        out[n] = np.where(a > 0.97, 0.02 * rng.random(steps), 0.0)
+    for n, (lo, hi) in case.get("lateral_conc", {}).items():
+        out[n] = lo + (hi - lo) * rng.random(steps)
+    return out
+
+
+def siminfo_for(case):
+    start = np.datetime64("%04d-01-01T00:00" % case.get("year", 1976)) + np.timedelta64(case.get("hour0", 0), "h")
+    stop = start + np.timedelta64(case["steps"] * case["delt"], "m")
+    return {"start": start, "stop": stop, "delt": case["delt"], "units": 1, "steps": case["steps"]}
+
+
+# ---------------------------------------------------------------------------------------------------
+# table variants
+# ---------------------------------------------------------------------------------------------------
+def _cbp_tables():
+    """Full chain, Chesapeake-Bay style land segment (tests/land_spec/hwmA51800.uci:73-262)."""
+    t = test10.perlnd()
+    t["ACTIVITY"] = {"ATEMP": 1, "SNOW": 1, "PWATER": 1, "SEDMNT": 1, "PSTEMP": 1, "PWTGAS": 1}
+    t["ATEMP"] = {"PARAMETERS": {"ELDAT": 150.0, "AIRTMP": 23.1476}}
+    t["SNOW"]["PARAMETERS"].update({"LAT": 36.69108, "MELEV": 55.78, "SHADE": 0.05, "SNOWCF": 1.3, "COVIND": 1.08,
+                                    "SNOEVP": 0.13, "MWATER": 0.03, "MGMELT": 0.03})
+    t["SNOW"]["STATES"].update({"PACKF": 0.0, "PACKI": 0.0, "PACKW": 0.0, "RDENPF": 0.15, "DULL": 100.0,
+                                "PAKTMP": 30.0, "COVINX": 1.08, "SKYCLR": 0.9})
+    p = t["PWATER"]["PARAMETERS"]
+    p.update({"RTOPFG": 1, "FOREST": 0.0, "INFILT": 0.017857, "LSUR": 461.0, "SLSUR": 0.014, "KVARY": 0.10E-05,
+              "AGWRC": 0.92, "DEEPFR": 0.0, "AGWETP": 0.05, "UZSN": 0.7, "INTFW": 2.0, "IRC": 0.435477})
+    t["PWATER"]["STATES"].update({"CEPS": 0.0, "UZS": 0.7, "LZS": 5.0, "AGWS": 1.0, "GWVS": 0.0})
+    t["PWATER"]["MONTHLY_CEPSC"] = monthly([.067, .065, .062, .06, .064, .085, .138, .15, .146, .109, .087, .077])
+    t["PWATER"]["MONTHLY_UZSN"] = monthly([.672, .672, .672, .672, .672, .784, 1.064, 1.12, 1.12, .896, .784, .728])
+    t["PWATER"]["MONTHLY_NSUR"] = monthly([.2028, .2028, .1971, .2103, .2804, .3505, .3692, .3594, .3262, .2283, .2085, .2028])
+    t["PWATER"]["MONTHLY_LZETP"] = monthly([.232, .221, .208, .2, .218, .312, .547, .6, .582, .416, .322, .276])
+    t["SEDMNT"] = {
+        "PARAMETERS": {"CRVFG": 1, "VSIVFG": 0, "SDOPFG": 1, "SMPF": 1.0, "KRER": 1.394872, "JRER": 2.0,
+                       "AFFIX": 0.07675, "COVER": 0.0, "NVSI": 30.57534, "KSER": 6.974359, "JSER": 2.0,
+                       "KGER": 0.0, "JGER": 4.0, "DETS": 0.0},
+        "MONTHLY_COVER": monthly([.0618, .0618, .0557, .1392, .2285, .3906, .6657, .7618, .8416, .7424, .6945, .0618]),
+        "MONTHLY_NVSI": monthly([.1] * 12),
+    }
+    t["PSTEMP"] = {
+        "PARAMETERS": {"SLTVFG": 1, "ULTVFG": 1, "LGTVFG": 1, "TSOPFG": 1, "ASLT": 0.0, "BSLT": 1.0, "ULTP1": 0.0,
+                       "ULTP2": 0.0, "LGTP1": 0.0, "LGTP2": 0.0, "AIRTC": 32.0, "SLTMP": 32.0, "ULTMP": 32.0,
+                       "LGTMP": 50.0},
+        "MONTHLY_ASLT": monthly([35.58, 37.14, 40.49, 45.09, 49.46, 53.62, 55.76, 54.6, 51.54, 46.08, 41.55, 36.97]),
+        "MONTHLY_BSLT": monthly([.5] * 12),
+        "MONTHLY_ULTP1": monthly([38.45, 41.25, 47.27, 55.57, 63.43, 70.92, 74.77, 72.67, 67.17, 57.34, 49.19, 40.94]),
+        "MONTHLY_ULTP2": monthly([.1] * 12),
+        "MONTHLY_LGTP1": monthly([46.51, 45.41, 46.57, 49.09, 52.79, 56.03, 59.01, 60.41, 59.74, 57.2, 53.27, 49.9]),
+        "MONTHLY_LGTP2": monthly([0.0] * 12),
+    }
+    t["PWTGAS"] = {
+        "PARAMETERS": {"IDVFG": 1, "ICVFG": 0, "GDVFG": 1, "GCVFG": 0, "ELEV": 55.78, "IDOXP": 0.0, "ICO2P": 0.0,
+                       "ADOXP": 0.0, "ACO2P": 0.0, "SDLFAC": 0.0, "SLIFAC": 0.0, "ILIFAC": 0.0, "ALIFAC": 0.0,
+                       "SOTMP": 33.0, "IOTMP": 40.0, "AOTMP": 55.0, "SODOX": 0.0, "SOCO2": 0.0, "IODOX": 0.0,
+                       "IOCO2": 0.0, "AODOX": 0.0, "AOCO2": 0.0},
+        "MONTHLY_IDOXP": monthly([12.7, 12.7, 11.2, 9.7, 7.4, 6.6, 6.2, 6.2, 7.5, 8.4, 9.4, 11.6]),
+        "MONTHLY_ADOXP": monthly([10., 10., 10., 10., 7.5, 5.5, 5., 5., 6.5, 7.5, 9., 10.]),
+    }
+    return t
+
+
+def _set(tables, act, table, **kv):
+    tables[act].setdefault(table, {}).update(kv)
+    return tables
+
+
+def build_cases():
+    """name -> case dict (tables + recipe).  Everything is deterministic."""
+    C = {}
+    Y = 8784  # hourly steps in 1976
+
+    def add(name, op, tables, met, steps=Y, delt=60, **kw):
+        C[name] = dict(name=name, operation=op, tables=tables, met=met, steps=steps, delt=delt, **kw)
+
+    # -- the two test10 land segments as shipped (CLOUD present) ---------------------------------
+    add("p001_test10", "PERLND", test10.perlnd(), "perlnd")
+    add("i001_test10", "IMPLND", test10.implnd(), "implnd")
+
+    # -- BASELINE config 2 base: SNOW+PWATER only, 6 forcings (no CLOUD) -------------------------
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    add("p001_snow_pwater", "PERLND", t, "perlnd", drop=("CLOUD",))
+
+    # -- full chain, CBP-style (ATEMP on, RTOPFG=1, SDOPFG=1, TSOPFG=1, monthly everything) -------
+    add("cbp_fullchain", "PERLND", _cbp_tables(), "perlnd", drop=("CLOUD",), gatmp=2.0)
+
+    # -- full chain variants: UZFG=1 + Newton routing + method-2 washoff + TSOPFG=0 + VSIVFG=2 ----
+    t = _cbp_tables()
+    t["PWATER"]["PARAMETERS"].update({"RTOPFG": 0, "UZFG": 1, "VLEFG": 2, "KVARY": 0.0, "BASETP": 0.15})
+    t["SEDMNT"]["PARAMETERS"].update({"SDOPFG": 0, "VSIVFG": 2, "KGER": 0.3, "JGER": 1.5})
+    t["PSTEMP"]["PARAMETERS"].update({"TSOPFG": 0, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5,
+                                      "BSLT": 0.365, "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0})
+    t["PWTGAS"]["PARAMETERS"].update({"IDVFG": 0, "GDVFG": 0, "ICVFG": 1, "GCVFG": 1, "IDOXP": 6.0, "ADOXP": 5.0})
+    t["PWTGAS"]["MONTHLY_ICO2P"] = monthly([.05, .05, .06, .07, .08, .1, .12, .12, .1, .08, .06, .05])
+    t["PWTGAS"]["MONTHLY_ACO2P"] = monthly([.04, .04, .05, .05, .06, .07, .08, .08, .07, .06, .05, .04])
+    add("chain_uzfg_newton", "PERLND", t, "perlnd", drop=("CLOUD",), gatmp=-1.5, rain_mult=3.0)
+
+    # -- TSOPFG=2, VSIVFG=1, ICEFG=0, IFRDFG=1, VLEFG=3 ------------------------------------------
+    t = _cbp_tables()
+    t["ACTIVITY"]["ATEMP"] = 0
+    t["SNOW"]["FLAGS"]["ICEFG"] = 0
+    t["PWATER"]["PARAMETERS"].update({"IFRDFG": 1, "VLEFG": 3, "VIFWFG": 1, "VIRCFG": 1})
+    t["PWATER"]["MONTHLY_INTFW"] = monthly([2., 2., 2.2, 2.5, 2.5, 2.2, 2., 1.8, 1.8, 2., 2., 2.])
+    t["PWATER"]["MONTHLY_IRC"] = monthly([.45, .45, .5, .55, .6, .6, .55, .5, .5, .45, .45, .45])
+    t["SEDMNT"]["PARAMETERS"].update({"VSIVFG": 1})
+    t["PSTEMP"]["PARAMETERS"].update({"TSOPFG": 2, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5,
+                                      "BSLT": 0.365, "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0})
+    add("chain_tsop2_ifrd", "PERLND", t, "perlnd")
+
+    # -- degree-day snow (SNOPFG=1) with monthly KMELT ------------------------------------------
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    t["SNOW"]["FLAGS"].update({"SNOPFG": 1, "VKMFG": 1, "ICEFG": 0})
+    t["SNOW"]["PARAMETERS"]["KMELT"] = 0.05
+    t["SNOW"]["MONTHLY_KMELT"] = monthly([.03, .03, .05, .08, .1, .1, .1, .1, .08, .06, .04, .03])
+    add("p_degday", "PERLND", t, "perlnd", drop=("CLOUD",))
+
+    # -- no SNOW at all: CSNOFG=0, IFFCFG=2 quirk, SEDMNT sees NaN RAINF -------------
+    t = _cbp_tables()
+    t["ACTIVITY"].update({"ATEMP": 0, "SNOW": 0})
+    t["PWATER"]["PARAMETERS"].update({"CSNOFG": 0, "IFFCFG": 2})
+    add("p_nosnow_iffc2", "PERLND", t, "perlnd")
+
+    # -- sub-hourly and super-hourly steps ------------------------------------------------------
+    t = test10.perlnd()
+    add("p001_delt30", "PERLND", t, "perlnd", steps=2 * 24 * 120, delt=30)
+    add("cbp_delt15", "PERLND", _cbp_tables(), "perlnd", steps=4 * 24 * 75, delt=15, gatmp=1.0, hour0=24 * 40)
+    t = test10.perlnd()
+    add("p001_delt120", "PERLND", t, "perlnd", steps=12 * 200, delt=120)
+
+    # -- run starting mid-year, not on a day boundary (calendar dofirst quirk) -------------------
+    add("p001_midyear", "PERLND", test10.perlnd(), "perlnd", steps=24 * 150 + 7, hour0=24 * 74 + 6)
+
+    # -- stress: 8x rain, tiny UZSN (table-bounds errors), thin soil ------------------------------
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    t["PWATER"]["PARAMETERS"].update({"VUZFG": 0, "UZSN": 0.02, "INFILT": 0.01, "LZSN": 2.0, "AGWRC": 0.999,
+                                      "KVARY": 3.0, "NSUR": 0.4})
+    t["PWATER"]["STATES"].update({"UZS": 0.5, "AGWS": 0.0, "GWVS": 0.0})
+    add("p_stress_wet", "PERLND", t, "perlnd", rain_mult=8.0)
+
+    # -- lateral inflows + lateral concentrations -------------------------------------------------
+    t = _cbp_tables()
+    t["PWTGAS"]["PARAMETERS"].update({"SLIFAC": 0.5, "ILIFAC": 0.3, "ALIFAC": 0.2})
+    add("cbp_lateral", "PERLND", t, "perlnd", gatmp=0.5, steps=24 * 200,
+        lateral=("SURLI", "UZLI", "IFWLI", "LZLI", "AGWLI", "SLSED"),
+        lateral_conc={"SLITMP": (35., 70.), "SLIDOX": (4., 12.), "SLICO2": (0., .2), "ILITMP": (35., 70.),
+                      "ILIDOX": (4., 12.), "ILICO2": (0., .2), "ALITMP": (40., 60.), "ALIDOX": (3., 9.),
+                      "ALICO2": (0., .2)})
+
+    # -- IMPLND variants --------------------------------------------------------------------------
+    t = test10.implnd()
+    t["ACTIVITY"]["SNOW"] = 0
+    t["IWATER"]["PARAMETERS"].update({"CSNOFG": 0, "RTOPFG": 1, "VRSFG": 1, "VNNFG": 1, "RTLIFG": 0})
+    t["IWATER"]["MONTHLY_RETSC"] = monthly([.01, .01, .02, .03, .05, .06, .06, .05, .04, .02, .01, .01])
+    t["IWATER"]["MONTHLY_NSUR"] = monthly([.01, .01, .012, .015, .02, .02, .02, .02, .015, .012, .01, .01])
+    add("i_rtop_monthly", "IMPLND", t, "implnd", lateral=("SURLI",))
+    add("i001_delt15", "IMPLND", test10.implnd(), "implnd", steps=4 * 24 * 60, delt=15, hour0=24 * 20)
+    t = test10.implnd()
+    t["ACTIVITY"]["ATEMP"] = 1
+    t["ATEMP"] = {"PARAMETERS": {"ELDAT": -300.0, "AIRTMP": 30.0}}
+    add("i_atemp_snow", "IMPLND", t, "implnd", gatmp=0.0, drop=("CLOUD",), rain_mult=2.0)
+
+    # -- the reference's own unit-test cases (tests/ipwater/test_ipwater.py:43-84) ----------------
+    fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}
+    add("flowtest_pwater", "PERLND", fp, "flowtest", steps=8760, year=2018)
+    fi = {"ACTIVITY": {"IWATER": 1}, "IWATER": copy.deepcopy(FLOWTEST_IMPLND)}
+    add("flowtest_iwater", "IMPLND", fi, "flowtest", steps=8760, year=2018)
+    return C
+
+
+# tests/ipwater/data/uci_data.json (numeric entries the kernels read; the rest of that file is unused by them)
+FLOWTEST_IMPLND = {
+    "PARAMETERS": {"CSNOFG": 0, "RTOPFG": 0, "VRSFG": 0, "VNNFG": 0, "RTLIFG": 0, "LSUR": 100.0, "SLSUR": 0.02,
+                   "NSUR": 0.05, "RETSC": 0.15, "PETMAX": 40.0, "PETMIN": 35.0},
+    "STATES": {"RETS": 0.01, "SURS": 0.01},
+}
+FLOWTEST_PERLND = {
+    "PARAMETERS": {"CSNOFG": 0, "RTOPFG": 1, "UZFG": 1, "VCSFG": 1, "VUZFG": 0, "VNNFG": 0, "VIFWFG": 0, "VIRCFG": 0,
+                   "VLEFG": 0, "IFFCFG": 1, "HWTFG": 0, "IRRGFG": 0, "IFRDFG": 0, "FOREST": 0.0, "LZSN": 7.35,
+                   "INFILT": 0.079, "LSUR": 50.0, "SLSUR": 0.1548, "KVARY": 1.0, "AGWRC": 0.993, "PETMAX": 40.0,
+                   "PETMIN": 35.0, "INFEXP": 2.0, "INFILD": 2.0, "DEEPFR": 0.02, "BASETP": 0.22, "AGWETP": 0.0,
+                   "CEPSC": 0.01, "UZSN": 0.85, "NSUR": 0.4, "INTFW": 3.0, "IRC": 0.7, "LZETP": 0.73, "FZG": 1.0,
+                   "FZGL": 0.1},
+    "STATES": {"CEPS": 0.0462, "SURS": 0.0, "UZS": 1.6075, "IFWS": 0.0996, "LZS": 8.9629, "AGWS": 2.8649,
+               "GWVS": 1.9555},
+    "MONTHLY_CEPSC": monthly([0.09, 0.1, 0.1, 0.14, 0.17, 0.18, 0.18, 0.18, 0.17, 0.15, 0.12, 0.1]),
+}

@@ -1,0 +1,185 @@
+"""CPU-oracle activities with the reference's module contract.  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+`atemp/snow/pwater/iwater/sedmnt/pstemp/pwtgas(io_manager, siminfo, uci, ts) -> (errors, errmsgs)` restate the
+Python wrappers of the reference (ATEMP.py:16-30, SNOW.py:27-88, PWATER.py:27-99, IWATER.py:19-72,
+SEDMNT.py:21-49, PSTEMP.py:23-59, PWTGAS.py:28-62) on top of the C cores in hsp2_oracle.c.  The calendar
+series come from hspsquared_b200.calendar (numpy), which tests/test_calendar.py pins against series produced
+by the reference's own pandas code.  `ts` is a plain dict of float64 arrays and is filled exactly like the
+reference fills its typed Dict (every output name, helper arrays, NaN / zero fills) because later activities
+of the same segment read them (SURVEY.md 8b "side effects to preserve").
+"""
+import numpy as np
+
+from hspsquared_b200.calendar import SEASONS, Calendar
+
+from . import oracle as O
+
+ERRMSGS_SNOW = ("Snow simulation cannot function properly with delt> 360",)
+ERRMSGS_PWATER = (
+    "PWATER: Sum of irrtgt in not one", "PWATER: UZRAA exceeds UZRA array bounds",
+    "PWATER: INTGB exceeds INTGRL array bounds", "PWATER: Reduced AGWO value to available",
+    "PWATER: Reduced GVWS to AGWS", "PWATER: GWVS < -0.02, set to zero",
+    "PWATER: Proute runoff did not converge", "PWATER: UZI highly negative", "PWATER: Reset AGWS to zero",
+    "PWATER: High Water Table code not implemented")
+ERRMSGS_IWATER = ("IWATER: IROUTE Newton Method did not converge",)
+ERRMSGS_PSTEMP = ["SLTMP temperature less than -100C", "ULTMP temperature less than -100C",
+                  "LGTMP temperature less than -100C", "SLTMP temperature greater than 100C",
+                  "ULTMP temperature greater than 100C", "LGTMP temperature greater than 100C"]
+
+
+def make_ui(uci):
+    """utilities.py:58-79: flatten FLAGS/PARAMETERS/STATES, keeping exact Python int/float values only."""
+    ui = {}
+    for name in set(uci.keys()) & {"FLAGS", "PARAMETERS", "STATES"}:
+        for key, value in uci[name].items():
+            if type(value) in {int, float}:
+                ui[key] = float(value)
+    return ui
+
+
+def _cal(siminfo):
+    if "_calendar" not in siminfo:
+        siminfo["_calendar"] = Calendar.from_siminfo(siminfo, siminfo.get("time_unit"))
+    return siminfo["_calendar"]
+
+
+def _english(siminfo):
+    if siminfo.get("units", 1) != 1:
+        raise NotImplementedError("oracle restates English units only (uunits == 1)")
+
+
+def atemp(io_manager, siminfo, uci, ts):
+    cal = _cal(siminfo)
+    ts["LAPSE"] = cal.lapse()
+    ui = make_ui(uci)
+    ui["k"] = siminfo["delt"] * 0.000833
+    ui["steps"] = siminfo["steps"]
+    return O._atemp_(ui, ts), ()
+
+
+def snow(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    steps = siminfo["steps"]
+    ts["SEASONS"] = cal.monthval(SEASONS)
+    cloudfg = "CLOUD" in ts
+    for name in ["AIRTMP", "CLOUD", "DTMPG", "PREC", "SOLRAD", "WINMOV"]:
+        if name not in ts:
+            ts[name] = np.full(steps, np.nan)
+    for name in ["CCFACT", "COVIND", "MGMELT", "MWATER", "SHADE", "SNOEVP", "SNOWCF", "KMELT"]:
+        if name not in ts and name in uci["PARAMETERS"]:
+            ts[name] = np.full(steps, uci["PARAMETERS"][name])
+    ts["HR6IND"] = cal.hour6flag(dofirst=True)
+    ts["HRFG"] = cal.hoursval(np.ones(24), dofirst=True)
+    siminfo["ICEFG"] = 0
+    if "FLAGS" in uci and "ICEFG" in uci["FLAGS"]:
+        siminfo["ICEFG"] = uci["FLAGS"]["ICEFG"]
+    ui = make_ui(uci)
+    ui.update(steps=steps, delt=siminfo["delt"], cloudfg=cloudfg)
+    vkmfg = uci.get("FLAGS", {}).get("VKMFG", 0)
+    ts["KMELT"] = cal.initm(uci, vkmfg, "MONTHLY_KMELT", uci["PARAMETERS"]["KMELT"])
+    errors = O._snow_(ui, ts)
+    if siminfo["delt"] > 360:
+        raise KeyError("ICEFLG")  # the reference raises here (SNOW.py:85 typo); mirrored, not fixed
+    return errors, ERRMSGS_SNOW
+
+
+def pwater(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    steps = siminfo["steps"]
+    for name in ("AGWLI", "IFWLI", "LGTMP", "LZLI", "PETINP", "PREC", "SURLI", "UZLI"):
+        if name not in ts:
+            ts[name] = np.zeros(steps)
+    for name in ("AIRTMP", "PACKI", "PETINP", "PREC", "RAINF", "SNOCOV", "WYIELD"):
+        if name not in ts:
+            ts[name] = np.full(steps, np.nan)
+    u = uci["PARAMETERS"]
+    for name in ("AGWRC", "DEEPFR", "INFILT", "KVARY", "LZSN", "PETMIN", "PETMAX"):
+        if name not in ts and name in u:
+            ts[name] = np.full(steps, u[name])
+    if "VLEFG" in u:
+        flag = (u["VLEFG"] == 1) or (u["VLEFG"] == 3)
+        ts["LZETP"] = cal.initm(uci, flag, "MONTHLY_LZETP", u["LZETP"])
+        ts["CEPSC"] = cal.initm(uci, u["VCSFG"], "MONTHLY_CEPSC", u["CEPSC"])
+        ts["INTFW"] = cal.initm(uci, u["VIFWFG"], "MONTHLY_INTFW", u["INTFW"])
+        ts["IRC"] = cal.initm(uci, u["VIRCFG"], "MONTHLY_IRC", u["IRC"])
+        ts["NSUR"] = cal.initm(uci, u["VNNFG"], "MONTHLY_NSUR", u["NSUR"])
+        ts["UZSN"] = cal.initm(uci, u["VUZFG"], "MONTHLY_UZSN", u["UZSN"])
+    else:
+        for n in ("LZETP", "CEPSC", "INTFW", "IRC", "NSUR", "UZSN"):
+            ts[n] = np.full(steps, u[n])
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    ts["HRFG"] = cal.hoursval(np.ones(24), dofirst=True)
+    ui = make_ui(uci)
+    ui.update(steps=steps, delt=siminfo["delt"])
+    ui["ICEFG"] = siminfo["ICEFG"] if "ICEFG" in siminfo else 0.0
+    u["CSNOFG"] = int(ui["CSNOFG"]) if "CSNOFG" in ui else 0
+    errors = O._pwater_(ui, ts)
+    return errors, ERRMSGS_PWATER
+
+
+def iwater(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    steps = siminfo["steps"]
+    for name in ("AIRTMP", "PETINP", "PREC", "RAINF", "SNOCOV", "WYIELD"):
+        if name not in ts:
+            ts[name] = np.full(steps, np.nan)
+    if "SURLI" not in ts:
+        ts["SURLI"] = np.zeros(steps)
+    u = uci["PARAMETERS"]
+    for name in ["PETMAX", "PETMIN"]:
+        if name not in ts:
+            ts[name] = np.full(steps, u[name], dtype=np.float64)
+    if "VRSFG" in u:
+        ts["RETSC"] = cal.initm(uci, u["VRSFG"], "MONTHLY_RETSC", u["RETSC"])
+        ts["NSUR"] = cal.initm(uci, u["VNNFG"], "MONTHLY_NSUR", u["NSUR"])
+    else:
+        ts["RETSC"] = np.full(steps, u["RETSC"])
+        ts["NSUR"] = np.full(steps, u["NSUR"])
+    ts["HR1FG"] = cal.hourflag(1, dofirst=True)
+    ts["HRFG"] = cal.hoursval(np.ones(24), dofirst=True)
+    ui = make_ui(uci)
+    ui.update(steps=steps, delt=siminfo["delt"])
+    return O._iwater_(ui, ts), ERRMSGS_IWATER
+
+
+def sedmnt(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    ui = make_ui(uci)
+    ui.update(simlen=n, delt=siminfo["delt"])
+    u = uci["PARAMETERS"]
+    ts["COVERI"] = cal.initm(uci, u["CRVFG"], "MONTHLY_COVER", u["COVER"]) if "CRVFG" in u else np.full(n, u["COVER"])
+    ts["NVSI"] = cal.initm(uci, u["VSIVFG"], "MONTHLY_NVSI", u["NVSI"]) if "VSIVFG" in u else np.full(n, u["NVSI"])
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return O._sedmnt_(ui, ts), []
+
+
+def pstemp(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    ui = make_ui(uci)
+    ui.update(simlen=n, delt=siminfo["delt"])
+    u = uci["PARAMETERS"]
+    for flag, names in (("SLTVFG", ("ASLT", "BSLT")), ("ULTVFG", ("ULTP1", "ULTP2")), ("LGTVFG", ("LGTP1", "LGTP2"))):
+        for nm in names:
+            ts[nm] = cal.initm(uci, u[flag], "MONTHLY_" + nm, u[nm]) if flag in u else np.full(n, u[nm])
+    ts["HRFG"] = cal.hoursval(np.ones(24), dofirst=True)
+    return O._pstemp_(ui, ts), ERRMSGS_PSTEMP
+
+
+def pwtgas(io_manager, siminfo, uci, ts):
+    _english(siminfo)
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    ui = make_ui(uci)
+    ui.update(simlen=n)
+    u = uci["PARAMETERS"]
+    for flag, nm in (("IDVFG", "IDOXP"), ("ICVFG", "ICO2P"), ("GDVFG", "ADOXP"), ("GCVFG", "ACO2P")):
+        ts[nm] = cal.initm(uci, u[flag], "MONTHLY_" + nm, u[nm]) if flag in u else np.full(n, u[nm])
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return O._pwtgas_(ui, ts), []
