@@ -1,0 +1,105 @@
+"""ctypes binding of libhsp2g.so (include/hsp2g.h).  There is no CPU fallback: if the shared object is missing or no
+CUDA device is present, the engine fails loudly.
+
+The id spaces (parameters, monthly tables, flag bits, states, forcings, outputs, error counters) are read back from the
+library itself (hsp2g_names), so host code can never drift from the kernels.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsp2g.so")
+
+PERLND, IMPLND = 0, 1
+ACT_BITS = {"ATEMP": 1, "SNOW": 2, "PWATER": 4, "SEDMNT": 8, "PSTEMP": 16, "PWTGAS": 32, "IWATER": 64}
+OPT_SED_RAIN_IS_PREC = 1
+CAL_HRFG, CAL_DAYFG, CAL_HR1FG, CAL_HR6IND, CAL_SEASON, CAL_NEWDAY = 1, 2, 4, 8, 16, 32
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
+_h = C.c_void_p
+
+_PROTOS = {
+    "hsp2g_abi_version": (C.c_int, []),
+    "hsp2g_last_error": (C.c_char_p, []),
+    "hsp2g_names": (C.c_char_p, [C.c_char_p]),
+    "hsp2g_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "hsp2g_batch_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_uint32, C.c_double, C.POINTER(_h)]),
+    "hsp2g_batch_destroy": (C.c_int, [_h]),
+    "hsp2g_batch_npad": (C.c_int64, [_h]),
+    "hsp2g_set_params": (C.c_int, [_h, _dp, C.c_int64]),
+    "hsp2g_set_flags": (C.c_int, [_h, _u64p]),
+    "hsp2g_set_monthly": (C.c_int, [_h, C.c_int, _dp, C.c_int64]),
+    "hsp2g_set_state": (C.c_int, [_h, _dp, C.c_int64]),
+    "hsp2g_get_state": (C.c_int, [_h, _dp, C.c_int64]),
+    "hsp2g_set_calendar": (C.c_int, [_h, C.c_int64, _u8p, _u8p, _u8p, _dp, _dp, _dp]),
+    "hsp2g_set_forcing_layout": (C.c_int, [_h, C.c_int, _i32p, _dp, C.c_uint32]),
+    "hsp2g_set_save": (C.c_int, [_h, C.c_int, _i32p]),
+    "hsp2g_run_device": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "hsp2g_sync": (C.c_int, [_h]),
+    "hsp2g_get_errors": (C.c_int, [_h, _i64p, C.c_int64]),
+    "hsp2g_reset_errors": (C.c_int, [_h]),
+    "hsp2g_set_timing": (C.c_int, [_h, C.c_int]),
+    "hsp2g_kernel_stats": (C.c_int, [_h, _i64p, _dp]),
+    "hsp2g_kernel_name": (C.c_char_p, [_h]),
+    "hsp2g_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "hsp2g_host_free": (C.c_int, [C.c_void_p]),
+    "hsp2g_device_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
+    "hsp2g_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "hsp2g_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hsp2g_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+}
+EXPORTS = tuple(_PROTOS)
+
+_lib = None
+_names = {}
+
+
+class Hsp2gError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libhsp2g.so; raises if it has not been built (python -m hspsquared_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Hsp2gError("%s is missing: build it with `python -m hspsquared_b200.build` (nvcc, sm_100a). "
+                         "There is no CPU fallback for the land-segment hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError here = ABI mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hsp2g_abi_version() != 1:
+        raise Hsp2gError("libhsp2g ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Hsp2gError(load().hsp2g_last_error().decode())
+
+
+def names(table):
+    """Ordered id list of one identifier space, straight from the library."""
+    if table not in _names:
+        s = load().hsp2g_names(table.encode()).decode()
+        _names[table] = tuple(x for x in s.split(",") if x)
+    return _names[table]
+
+
+def index(table):
+    return {n: i for i, n in enumerate(names(table))}
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().hsp2g_device_count(C.byref(n))
+    return n.value if rc == 0 else 0

@@ -1,0 +1,564 @@
+// hsp2g_api.cu -- C ABI of libhsp2g (include/hsp2g.h): batch handle, segment store in HBM, chunked runs.
+//
+// Streams: `comp` runs the kernels (state dependencies serialise there); `h2d` and `d2h` move host chunks through two
+// device slots so that copy-in of chunk k+1, the kernel of chunk k and copy-out of chunk k-1 overlap (SURVEY 8b
+// "Threading": one handle per GPU, internal streams).
+#include "cuda_rt.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hsp2g.h"
+#include "land_common.cuh"
+#include "launch.h"
+
+static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && HSP2G_PWATER == HSP2G_ACT_PWATER &&
+                  HSP2G_SEDMNT == HSP2G_ACT_SEDMNT && HSP2G_PSTEMP == HSP2G_ACT_PSTEMP &&
+                  HSP2G_PWTGAS == HSP2G_ACT_PWTGAS && HSP2G_IWATER == HSP2G_ACT_IWATER,
+              "public activity bits must match the kernel's");
+static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
+static_assert(sizeof(CalStep) == 32, "CalStep layout");
+
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Slot {
+    double *forc = nullptr, *out = nullptr;
+    size_t cap_f = 0, cap_o = 0;
+    cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+};
+
+struct hsp2g_batch {
+    int device = 0, op = 0;
+    int64_t n_seg = 0, n_pad = 0;
+    unsigned act = 0, opts = 0;
+    double delt = 60.0;
+    double *par = nullptr, *mon = nullptr, *state = nullptr;
+    unsigned long long *flags = nullptr;
+    long long *err = nullptr;
+    CalStep *cal = nullptr;
+    int64_t ncal = 0;
+    int nmon_slots = 0;
+    short mslot[HSP2G_NMON];
+    short frow[HSP2G_NFORC];
+    double ffill[HSP2G_NFORC];
+    short srow[HSP2G_NOUT];
+    int nf = -1, ns = -1;
+    bool have_par = false, have_flags = false, have_state = false;
+    cudaStream_t comp = nullptr, h2d = nullptr, d2h = nullptr;
+    Slot slot[2];
+    int next_slot = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    double kernel_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    const char *kname = "";
+};
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define NAME_ITEM(n) #n ","
+const char *k_params = HSP2G_PARAMS(NAME_ITEM);
+const char *k_monthly = HSP2G_MONTHLY(NAME_ITEM);
+const char *k_flags = HSP2G_FLAGS(NAME_ITEM);
+const char *k_states = HSP2G_STATES(NAME_ITEM);
+const char *k_forcings = HSP2G_FORCINGS(NAME_ITEM);
+const char *k_errors = HSP2G_ERRORS(NAME_ITEM);
+#define OA(n) "ATEMP_" #n ","
+#define OS(n) "SNOW_" #n ","
+#define OP(n) "PWATER_" #n ","
+#define OD(n) "SEDMNT_" #n ","
+#define OT(n) "PSTEMP_" #n ","
+#define OG(n) "PWTGAS_" #n ","
+#define OI(n) "IWATER_" #n ","
+const char *k_outputs = HSP2G_OUT_ATEMP(OA) HSP2G_OUT_SNOW(OS) HSP2G_OUT_PWATER(OP) HSP2G_OUT_SEDMNT(OD)
+    HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI);
+
+int upload2d(void *dst, int64_t n_pad, const void *src, int64_t ld, int64_t n_seg, int64_t rows, size_t elt) {
+    CU(cudaMemcpy2D(dst, (size_t)n_pad * elt, src, (size_t)ld * elt, (size_t)n_seg * elt, (size_t)rows,
+                    cudaMemcpyHostToDevice));
+    return 0;
+}
+int download2d(void *dst, int64_t ld, const void *src, int64_t n_pad, int64_t n_seg, int64_t rows, size_t elt) {
+    CU(cudaMemcpy2D(dst, (size_t)ld * elt, src, (size_t)n_pad * elt, (size_t)n_seg * elt, (size_t)rows,
+                    cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int check_ready(const hsp2g_batch *b, int64_t t0, int32_t nsteps) {
+    if (!b) return fail("null batch");
+    if (!b->have_par) return fail("hsp2g_set_params has not been called");
+    if (!b->have_flags) return fail("hsp2g_set_flags has not been called");
+    if (!b->have_state) return fail("hsp2g_set_state has not been called");
+    if (!b->cal) return fail("hsp2g_set_calendar has not been called");
+    if (b->nf < 0) return fail("hsp2g_set_forcing_layout has not been called");
+    if (b->ns < 0) return fail("hsp2g_set_save has not been called");
+    if (nsteps <= 0) return fail("nsteps must be positive");
+    if (t0 < 0 || t0 + nsteps > b->ncal) return fail("intervals [%lld, %lld) outside the calendar (%lld records)",
+                                                   (long long)t0, (long long)(t0 + nsteps), (long long)b->ncal);
+    return 0;
+}
+
+cudaEvent_t get_event(hsp2g_batch *b) {
+    if (!b->ev_pool.empty()) {
+        cudaEvent_t e = b->ev_pool.back();
+        b->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+int drain_timing(hsp2g_batch *b) {
+    for (auto &p : b->pending) {
+        CU(cudaEventSynchronize(p.second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p.first, p.second));
+        b->kernel_ms += ms;
+        b->ev_pool.push_back(p.first);
+        b->ev_pool.push_back(p.second);
+    }
+    b->pending.clear();
+    return 0;
+}
+
+int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, cudaStream_t st) {
+    LandLaunch L;
+    memset(&L, 0, sizeof L);
+    L.par = b->par;
+    L.mon = b->mon;
+    L.flags = b->flags;
+    L.state = b->state;
+    L.err = b->err;
+    L.forc = d_forc;
+    L.out = d_out;
+    L.cal = b->cal + t0;
+    L.n_pad = b->n_pad;
+    L.n_seg = (int)b->n_seg;
+    L.nsteps = nsteps;
+    L.first_chunk = t0 == 0;
+    L.nf = b->nf;
+    L.ns = b->ns;
+    L.act = b->act;
+    L.opts = b->opts;
+    L.delt = b->delt;
+    L.delt60 = b->delt / 60.0;
+    memcpy(L.frow, b->frow, sizeof L.frow);
+    memcpy(L.ffill, b->ffill, sizeof L.ffill);
+    memcpy(L.srow, b->srow, sizeof L.srow);
+    memcpy(L.mslot, b->mslot, sizeof L.mslot);
+    const bool hourly = b->delt >= 60.0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (b->timing) {
+        e0 = get_event(b);
+        e1 = get_event(b);
+        CU(cudaEventRecord(e0, st));
+    }
+    cudaError_t e = b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, st, &b->kname)
+                                          : hsp2g_launch_implnd(L, hourly, st, &b->kname);
+    if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+    if (b->timing) {
+        CU(cudaEventRecord(e1, st));
+        b->pending.emplace_back(e0, e1);
+    }
+    b->launches += 1;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int hsp2g_abi_version(void) { return HSP2G_ABI_VERSION; }
+const char *hsp2g_last_error(void) { return g_err.c_str(); }
+
+const char *hsp2g_names(const char *t) {
+    if (!t) return "";
+    if (!strcmp(t, "params")) return k_params;
+    if (!strcmp(t, "monthly")) return k_monthly;
+    if (!strcmp(t, "flags")) return k_flags;
+    if (!strcmp(t, "states")) return k_states;
+    if (!strcmp(t, "forcings")) return k_forcings;
+    if (!strcmp(t, "outputs")) return k_outputs;
+    if (!strcmp(t, "errors")) return k_errors;
+    return "";
+}
+
+int hsp2g_device_count(int *count) {
+    if (!count) return fail("null count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, double delt, hsp2g_batch **out) {
+    if (!out) return fail("null out");
+    *out = nullptr;
+    if (operation != HSP2G_PERLND && operation != HSP2G_IMPLND) return fail("operation must be PERLND(0) or IMPLND(1)");
+    if (n_seg <= 0 || n_seg > 2000000000LL) return fail("n_seg out of range");
+    if (!(delt > 0.0) || delt > 1440.0) return fail("delt must be in (0, 1440] minutes");
+    if (delt > 360.0 && (act & HSP2G_SNOW))
+        return fail("SNOW with delt > 360: the reference raises KeyError('ICEFLG') (SNOW.py:85); refused");
+    const unsigned perl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_PWATER | HSP2G_SEDMNT | HSP2G_PSTEMP | HSP2G_PWTGAS;
+    const unsigned impl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_IWATER;
+    if (act == 0 || (act & ~(operation == HSP2G_PERLND ? perl : impl)))
+        return fail("activity mask 0x%x is not valid for this operation", act);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device (%s): libhsp2g has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail("cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    hsp2g_batch *b = new hsp2g_batch();
+    b->device = device;
+    b->op = operation;
+    b->n_seg = n_seg;
+    b->n_pad = (n_seg + LAND_BLOCK - 1) / LAND_BLOCK * LAND_BLOCK;
+    b->act = act;
+    b->delt = delt;
+    for (int i = 0; i < HSP2G_NMON; ++i) b->mslot[i] = -1;
+    for (int i = 0; i < HSP2G_NFORC; ++i) {
+        b->frow[i] = -1;
+        b->ffill[i] = 0.0;
+    }
+    for (int i = 0; i < HSP2G_NOUT; ++i) b->srow[i] = -1;
+    const size_t np = (size_t)b->n_pad;
+    cudaError_t ce;
+#define ALLOC(ptr, bytes)                                                          \
+    if ((ce = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) {              \
+        hsp2g_batch_destroy(b);                                                    \
+        return fail("cudaMalloc(%zu bytes): %s", (size_t)(bytes), cudaGetErrorString(ce)); \
+    }                                                                              \
+    cudaMemset((ptr), 0, (bytes));
+    ALLOC(b->par, np * HSP2G_NPAR * sizeof(double));
+    ALLOC(b->state, np * HSP2G_NSTATE * sizeof(double));
+    ALLOC(b->flags, np * sizeof(unsigned long long));
+    ALLOC(b->err, np * HSP2G_NERR * sizeof(long long));
+#undef ALLOC
+    CU(cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking));
+    for (auto &s : b->slot) {
+        CU(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+    }
+    *out = b;
+    return 0;
+}
+
+int hsp2g_batch_destroy(hsp2g_batch *b) {
+    if (!b) return 0;
+    DeviceGuard g(b->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->par);
+    cudaFree(b->mon);
+    cudaFree(b->state);
+    cudaFree(b->flags);
+    cudaFree(b->err);
+    cudaFree(b->cal);
+    for (auto &s : b->slot) {
+        cudaFree(s.forc);
+        cudaFree(s.out);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.k_done) cudaEventDestroy(s.k_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+    }
+    for (auto &p : b->pending) {
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    for (auto e : b->ev_pool) cudaEventDestroy(e);
+    if (b->comp) cudaStreamDestroy(b->comp);
+    if (b->h2d) cudaStreamDestroy(b->h2d);
+    if (b->d2h) cudaStreamDestroy(b->d2h);
+    delete b;
+    return 0;
+}
+
+int64_t hsp2g_batch_npad(const hsp2g_batch *b) { return b ? b->n_pad : 0; }
+
+int hsp2g_set_params(hsp2g_batch *b, const double *par, int64_t ld) {
+    if (!b || !par) return fail("null argument");
+    if (ld < b->n_seg) return fail("ld < n_seg");
+    DeviceGuard g(b->device);
+    if (upload2d(b->par, b->n_pad, par, ld, b->n_seg, HSP2G_NPAR, sizeof(double))) return 1;
+    b->have_par = true;
+    return 0;
+}
+
+int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags) {
+    if (!b || !flags) return fail("null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpy(b->flags, flags, (size_t)b->n_seg * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    b->have_flags = true;
+    return 0;
+}
+
+int hsp2g_set_monthly(hsp2g_batch *b, int id, const double *tab, int64_t ld) {
+    if (!b || !tab) return fail("null argument");
+    if (id < 0 || id >= HSP2G_NMON) return fail("monthly table id %d out of range", id);
+    if (ld < b->n_seg) return fail("ld < n_seg");
+    DeviceGuard g(b->device);
+    if (b->mslot[id] < 0) {  // grow the slot array by one table
+        const size_t one = (size_t)12 * b->n_pad * sizeof(double);
+        double *nm = nullptr;
+        CU(cudaMalloc((void **)&nm, one * (b->nmon_slots + 1)));
+        CU(cudaMemset(nm, 0, one * (b->nmon_slots + 1)));
+        if (b->mon) {
+            CU(cudaDeviceSynchronize());
+            CU(cudaMemcpy(nm, b->mon, one * b->nmon_slots, cudaMemcpyDeviceToDevice));
+            cudaFree(b->mon);
+        }
+        b->mon = nm;
+        b->mslot[id] = (short)b->nmon_slots++;
+    }
+    return upload2d(b->mon + (size_t)b->mslot[id] * 12 * b->n_pad, b->n_pad, tab, ld, b->n_seg, 12, sizeof(double));
+}
+
+int hsp2g_set_state(hsp2g_batch *b, const double *st, int64_t ld) {
+    if (!b || !st) return fail("null argument");
+    if (ld < b->n_seg) return fail("ld < n_seg");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->comp));
+    if (upload2d(b->state, b->n_pad, st, ld, b->n_seg, HSP2G_NSTATE, sizeof(double))) return 1;
+    b->have_state = true;
+    return 0;
+}
+
+int hsp2g_get_state(hsp2g_batch *b, double *st, int64_t ld) {
+    if (!b || !st) return fail("null argument");
+    if (ld < b->n_seg) return fail("ld < n_seg");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->comp));
+    return download2d(st, ld, b->state, b->n_pad, b->n_seg, HSP2G_NSTATE, sizeof(double));
+}
+
+int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const uint8_t *m0, const uint8_t *m1,
+                       const double *xm, const double *dxm, const double *lapse) {
+    if (!b || !flags || !m0 || !m1 || !xm || !dxm || !lapse) return fail("null argument");
+    if (n <= 0) return fail("empty calendar");
+    std::vector<CalStep> h((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (m0[i] > 11 || m1[i] > 11) return fail("calendar month index out of range at record %lld", (long long)i);
+        CalStep c;
+        memset(&c, 0, sizeof c);
+        c.xm = xm[i];
+        c.dxm = dxm[i];
+        c.lapse = lapse[i];
+        c.flags = flags[i];
+        c.m0 = m0[i];
+        c.m1 = m1[i];
+        h[(size_t)i] = c;
+    }
+    DeviceGuard g(b->device);
+    CU(cudaDeviceSynchronize());
+    cudaFree(b->cal);
+    b->cal = nullptr;
+    CU(cudaMalloc((void **)&b->cal, (size_t)n * sizeof(CalStep)));
+    CU(cudaMemcpy(b->cal, h.data(), (size_t)n * sizeof(CalStep), cudaMemcpyHostToDevice));
+    b->ncal = n;
+    return 0;
+}
+
+int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *ids, const double *fill, uint32_t opts) {
+    if (!b || !fill || (n_rows > 0 && !ids)) return fail("null argument");
+    if (n_rows < 0 || n_rows > HSP2G_NFORC) return fail("n_rows out of range");
+    short row[HSP2G_NFORC];
+    for (int i = 0; i < HSP2G_NFORC; ++i) row[i] = -1;
+    for (int r = 0; r < n_rows; ++r) {
+        if (ids[r] < 0 || ids[r] >= HSP2G_NFORC) return fail("forcing id %d out of range", ids[r]);
+        if (row[ids[r]] >= 0) return fail("forcing id %d listed twice", ids[r]);
+        row[ids[r]] = (short)r;
+    }
+    memcpy(b->frow, row, sizeof row);
+    memcpy(b->ffill, fill, sizeof(double) * HSP2G_NFORC);
+    b->nf = n_rows;
+    b->opts = opts;
+    return 0;
+}
+
+int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *ids) {
+    if (!b || (n_rows > 0 && !ids)) return fail("null argument");
+    if (n_rows < 0 || n_rows > HSP2G_NOUT) return fail("n_rows out of range");
+    short row[HSP2G_NOUT];
+    for (int i = 0; i < HSP2G_NOUT; ++i) row[i] = -1;
+    for (int r = 0; r < n_rows; ++r) {
+        if (ids[r] < 0 || ids[r] >= HSP2G_NOUT) return fail("output id %d out of range", ids[r]);
+        if (row[ids[r]] >= 0) return fail("output id %d listed twice", ids[r]);
+        row[ids[r]] = (short)r;
+    }
+    memcpy(b->srow, row, sizeof row);
+    b->ns = n_rows;
+    return 0;
+}
+
+int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, void *stream) {
+    if (check_ready(b, t0, nsteps)) return 1;
+    if (b->nf > 0 && !d_forc) return fail("null forcing pointer");
+    if (b->ns > 0 && !d_out) return fail("null output pointer");
+    DeviceGuard g(b->device);
+    return launch(b, t0, nsteps, d_forc, d_out, stream ? (cudaStream_t)stream : b->comp);
+}
+
+int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, int64_t ldf, double *h_out,
+                   int64_t ldo) {
+    if (check_ready(b, t0, nsteps)) return 1;
+    if (b->nf > 0 && (!h_forc || ldf < b->n_seg)) return fail("bad forcing buffer / ld");
+    if (b->ns > 0 && (!h_out || ldo < b->n_seg)) return fail("bad output buffer / ld");
+    DeviceGuard g(b->device);
+    Slot &s = b->slot[b->next_slot];
+    b->next_slot ^= 1;
+    const size_t row = (size_t)b->n_pad * sizeof(double);
+    const size_t need_f = row * (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0);
+    const size_t need_o = row * (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0);
+    if (need_f > s.cap_f || need_o > s.cap_o) {
+        CU(cudaEventSynchronize(s.d2h_done));
+        if (need_f > s.cap_f) {
+            cudaFree(s.forc);
+            s.forc = nullptr;
+            CU(cudaMalloc((void **)&s.forc, need_f));
+            s.cap_f = need_f;
+        }
+        if (need_o > s.cap_o) {
+            cudaFree(s.out);
+            s.out = nullptr;
+            CU(cudaMalloc((void **)&s.out, need_o));
+            s.cap_o = need_o;
+        }
+    }
+    // the slot is free once its previous outputs have left the device
+    CU(cudaStreamWaitEvent(b->h2d, s.d2h_done, 0));
+    if (b->nf > 0)
+        CU(cudaMemcpy2DAsync(s.forc, row, h_forc, (size_t)ldf * sizeof(double), (size_t)b->n_seg * sizeof(double),
+                             (size_t)nsteps * b->nf, cudaMemcpyHostToDevice, b->h2d));
+    CU(cudaEventRecord(s.h2d_done, b->h2d));
+    CU(cudaStreamWaitEvent(b->comp, s.h2d_done, 0));
+    if (launch(b, t0, nsteps, s.forc, s.out, b->comp)) return 1;
+    CU(cudaEventRecord(s.k_done, b->comp));
+    CU(cudaStreamWaitEvent(b->d2h, s.k_done, 0));
+    if (b->ns > 0)
+        CU(cudaMemcpy2DAsync(h_out, (size_t)ldo * sizeof(double), s.out, row, (size_t)b->n_seg * sizeof(double),
+                             (size_t)nsteps * b->ns, cudaMemcpyDeviceToHost, b->d2h));
+    CU(cudaEventRecord(s.d2h_done, b->d2h));
+    return 0;
+}
+
+int hsp2g_sync(hsp2g_batch *b) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->h2d));
+    CU(cudaStreamSynchronize(b->comp));
+    CU(cudaStreamSynchronize(b->d2h));
+    return drain_timing(b);
+}
+
+int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld) {
+    if (!b || !err) return fail("null argument");
+    if (ld < b->n_seg) return fail("ld < n_seg");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->comp));
+    return download2d(err, ld, b->err, b->n_pad, b->n_seg, HSP2G_NERR, sizeof(long long));
+}
+
+int hsp2g_reset_errors(hsp2g_batch *b) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->comp));
+    CU(cudaMemset(b->err, 0, (size_t)b->n_pad * HSP2G_NERR * sizeof(long long)));
+    return 0;
+}
+
+int hsp2g_set_timing(hsp2g_batch *b, int on) {
+    if (!b) return fail("null batch");
+    b->timing = on != 0;
+    return 0;
+}
+
+int hsp2g_kernel_stats(hsp2g_batch *b, int64_t *launches, double *kernel_ms) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    if (drain_timing(b)) return 1;
+    if (launches) *launches = b->launches;
+    if (kernel_ms) *kernel_ms = b->kernel_ms;
+    return 0;
+}
+
+const char *hsp2g_kernel_name(const hsp2g_batch *b) { return b ? b->kname : ""; }
+
+void *hsp2g_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fail("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int hsp2g_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+void *hsp2g_device_alloc(int device, size_t bytes) {
+    DeviceGuard g(device);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        fail("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int hsp2g_device_free(int device, void *p) {
+    DeviceGuard g(device);
+    if (p) CU(cudaFree(p));
+    return 0;
+}
+int hsp2g_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
+    DeviceGuard g(device);
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int hsp2g_memcpy_d2h(int device, void *dst, const void *src, size_t bytes) {
+    DeviceGuard g(device);
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // extern "C"

@@ -1,0 +1,193 @@
+/*
+ * hsp2g_ids.h -- identifier spaces of the land-segment engine (shared by the CUDA kernels and the C ABI).
+ *
+ * Every list is an X-macro so that the library can export its own name tables (hsp2g_names()), from which the
+ * Python host code builds its index maps: one source of truth, no hand-mirrored enums.
+ *
+ * Names follow the HSPF/HSP2 domain: the parameter / state / flux names are the reference's `ui` / `ts` keys
+ * (src/hsp2/hsp2/{ATEMP,SNOW,PWATER,IWATER,SEDMNT,PSTEMP,PWTGAS}.py; tables in hsp2tools/data/ParseTable.csv).
+ */
+#ifndef HSP2G_IDS_H
+#define HSP2G_IDS_H
+
+/* ---- operations and activities ------------------------------------------------------------------ */
+#define HSP2G_OP_PERLND 0
+#define HSP2G_OP_IMPLND 1
+
+/* activity mask bits, registry order of configuration.py:48-52 */
+#define HSP2G_ACT_ATEMP 1u
+#define HSP2G_ACT_SNOW 2u
+#define HSP2G_ACT_PWATER 4u
+#define HSP2G_ACT_SEDMNT 8u
+#define HSP2G_ACT_PSTEMP 16u
+#define HSP2G_ACT_PWTGAS 32u
+#define HSP2G_ACT_IWATER 64u
+
+/* ---- per-segment scalar parameters: par[P_x][segment], fp64 -------------------------------------- */
+/* derived columns (computed by the host with the reference's own expression order):
+ *   MGMELT_IVL = MGMELT*delt/1440 (SNOW.py:146)   INFILT_IVL = INFILT*delt60 (PWATER.py:215)
+ *   KGW = 1 - AGWRC**(delt60/24) (PWATER.py:247)   ELEVGC = ((288-0.00198*ELEV)/288)**5.256 (PWTGAS.py:95) */
+#define HSP2G_PARAMS(X)                                                                                   \
+    X(ELDAT)                                                                                              \
+    X(MELEV) X(SHADE) X(SNOWCF) X(COVIND) X(KMELT) X(TBASE) X(RDCSN) X(TSNOW) X(SNOEVP) X(CCFACT)         \
+    X(MWATER) X(MGMELT_IVL)                                                                               \
+    X(FOREST) X(LZSN) X(INFILT_IVL) X(LSUR) X(SLSUR) X(KVARY) X(KGW) X(PETMAX) X(PETMIN) X(INFEXP)        \
+    X(INFILD) X(DEEPFR) X(BASETP) X(AGWETP) X(CEPSC) X(UZSN) X(NSUR) X(INTFW) X(IRC) X(LZETP) X(FZG)      \
+    X(FZGL)                                                                                               \
+    X(SMPF) X(KRER) X(JRER) X(AFFIX) X(COVER) X(NVSI) X(KSER) X(JSER) X(KGER) X(JGER)                     \
+    X(ASLT) X(BSLT) X(ULTP1) X(ULTP2) X(LGTP1) X(LGTP2)                                                   \
+    X(ELEVGC) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(SLIFAC) X(ILIFAC) X(ALIFAC)                           \
+    X(RETSC)
+
+/* ---- monthly tables: mon[slot][12][segment]; a parameter follows its table only where the segment's
+ *      M_<name> flag bit is set (utilities.py:205-211 initm: flag truthy AND table present) -------------- */
+#define HSP2G_MONTHLY(X)                                                                                  \
+    X(KMELT) X(LZETP) X(CEPSC) X(INTFW) X(IRC) X(NSUR) X(UZSN) X(COVER) X(NVSI) X(ASLT) X(BSLT) X(ULTP1)  \
+    X(ULTP2) X(LGTP1) X(LGTP2) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(RETSC)
+
+/* ---- per-segment option flags: one 64-bit word per segment ---------------------------------------- */
+#define HSP2G_FLAGS(X)                                                                                    \
+    X(ICEFG)      /* SNOW ICEFG (SNOW.py:105-107) */                                                      \
+    X(SNOPFG)     /* degree-day snowmelt (SNOW.py:125-127) */                                             \
+    X(CSNOFG)     /* PWATER / IWATER consider snow (PWATER.py:170, IWATER.py:91) */                        \
+    X(PW_ICEFG)   /* ICEFG as PWATER sees it through siminfo (SNOW.py:60-63, PWATER.py:87) */             \
+    X(RTOP1)      /* RTOPFG == 1: ARM/NPS routing (PWATER.py:701); IWATER: RTOPFG truthy (IWATER.py:202) */ \
+    X(UZFG) X(IFRDFG)                                                                                     \
+    X(IFFCFG2)    /* IFFCFG == 2 (PWATER.py:302) */                                                       \
+    X(VLE_GE2)    /* VLEFG >= 2 (PWATER.py:615-620) */                                                    \
+    X(RTLIFG)     /* IWATER lateral inflow subject to retention (IWATER.py:174) */                         \
+    X(SED_CSNO1)  /* SEDMNT: CSNOFG == 1 (SEDMNT.py:164) */                                               \
+    X(SDOPFG) X(VSIV_EQ2) X(VSIV_LE2)                                                                     \
+    X(TSOP1) X(TSOP0) X(AIRTFG)                                                                           \
+    X(PWG_CSNO)   /* PWTGAS: CSNOFG truthy (PWTGAS.py:203) */                                              \
+    X(GDVFG)                                                                                              \
+    X(M_KMELT) X(M_LZETP) X(M_CEPSC) X(M_INTFW) X(M_IRC) X(M_NSUR) X(M_UZSN) X(M_COVER) X(M_NVSI)         \
+    X(M_ASLT) X(M_BSLT) X(M_ULTP1) X(M_ULTP2) X(M_LGTP1) X(M_LGTP2) X(M_IDOXP) X(M_ICO2P) X(M_ADOXP)      \
+    X(M_ACO2P) X(M_RETSC)
+
+/* ---- carried state: state[S_x][segment], fp64.  Named states (restart.py:9-14) AND the hidden scalars the
+ *      reference carries across steps, so a run split into time chunks is bit-identical
+ *      to a single pass.  Integer latches are stored as 0.0/1.0. ------------------------------------------ */
+#define HSP2G_STATES(X)                                                                                   \
+    /* SNOW */                                                                                            \
+    X(COVINX) X(DULL) X(PACKF) X(PACKI) X(PACKW) X(PAKTMP) X(RDENPF) X(SKYCLR) X(XLNMLT) X(PDEPTH)        \
+    X(SNOCOV) X(NEGHTS) X(OLDPREC) X(SNOTMP) X(DEWTMP) X(MNEGHS) X(PACKWC) X(COMPCT) X(GMELTR) X(MOSTHT)  \
+    X(NEGHT) X(RDNSN) X(SNOWEP) X(VAP) X(ALBEDO) X(HR6FG)                                                 \
+    /* PWATER */                                                                                          \
+    X(CEPS) X(SURS) X(UZS) X(IFWS) X(LZS) X(AGWS) X(GWVS) X(MSUPY) X(DEC) X(SRC) X(IFWK1) X(IFWK2)        \
+    X(RLZRAT) X(LZFRAC) X(RPARM) X(PETADJ)                                                                \
+    /* SEDMNT */                                                                                          \
+    X(DETS) X(SED_COVER) X(SED_NVSI) X(DRYDFG)                                                            \
+    /* PSTEMP (deg C internally) */                                                                       \
+    X(SLTMP) X(ULTMP) X(LGTMP) X(AIRTS)                                                                   \
+    /* IWATER (SURS, MSUPY, DEC, SRC, PETADJ shared with the PWATER slots: a batch is one operation) */    \
+    X(RETS)
+
+/* ---- forcing / input series ids: forc[t][row][segment]; absent ids read a per-batch fill value that the
+ *      host derives by replaying the reference wrappers' NaN / zero / -1e30 fills (SNOW.py:44-46,
+ *      PWATER.py:41-48, IWATER.py:35-42, SEDMNT.py:94-96, PWTGAS.py:106-140) ---------------------------- */
+#define HSP2G_FORCINGS(X)                                                                                 \
+    X(GATMP) X(PREC) X(PETINP) X(AIRTMP) X(WINMOV) X(SOLRAD) X(DTMPG) X(CLOUD)                            \
+    X(SURLI) X(UZLI) X(IFWLI) X(LZLI) X(AGWLI) X(LGTMP)                                                   \
+    X(RAINF) X(SNOCOV) X(WYIELD) X(PACKI)                                                                 \
+    X(SLSED) X(SURO) X(SURS) X(IFWO) X(AGWO) X(SLTMP) X(ULTMP)                                            \
+    X(SLITMP) X(SLIDOX) X(SLICO2) X(ILITMP) X(ILIDOX) X(ILICO2) X(ALITMP) X(ALIDOX) X(ALICO2)
+
+/* ---- output series ids (the reference's ts[...] outputs; SAVE selects the rows that are written) ------ */
+#define HSP2G_OUT_ATEMP(X) X(AIRTMP)
+#define HSP2G_OUT_SNOW(X)                                                                                 \
+    X(ALBEDO) X(COVINX) X(DEWTMP) X(DULL) X(MELT) X(NEGHTS) X(PACKF) X(PACKI) X(PACKW) X(PACK) X(PAKTMP)  \
+    X(PDEPTH) X(PRAIN) X(RAINF) X(RDENPF) X(SKYCLR) X(SNOCOV) X(SNOTMP) X(SNOWE) X(SNOWF) X(WYIELD)       \
+    X(XLNMLT)
+#define HSP2G_OUT_PWATER(X)                                                                               \
+    X(AGWET) X(AGWI) X(AGWO) X(AGWS) X(BASET) X(CEPE) X(CEPS) X(GWVS) X(IFWI) X(IFWO) X(IFWS) X(IGWI)     \
+    X(INFIL) X(LZET) X(LZI) X(LZS) X(PERC) X(PERO) X(PERS) X(PET) X(PETADJ) X(SUPY) X(SURI) X(SURO)       \
+    X(SURS) X(TAET) X(TGWS) X(UZET) X(UZI) X(UZS) X(INFFAC)
+#define HSP2G_OUT_SEDMNT(X) X(DETS) X(WSSD) X(SCRSD) X(SOSED) X(COVER)
+#define HSP2G_OUT_PSTEMP(X) X(AIRTC) X(SLTMP) X(ULTMP) X(LGTMP)
+#define HSP2G_OUT_PWTGAS(X)                                                                               \
+    X(SOTMP) X(IOTMP) X(AOTMP) X(SODOX) X(SOCO2) X(IODOX) X(IOCO2) X(AODOX) X(AOCO2) X(SOHT) X(IOHT)      \
+    X(AOHT) X(POHT) X(SODOXM) X(SOCO2M) X(IODOXM) X(IOCO2M) X(AODOXM) X(AOCO2M) X(PODOXM) X(POCO2M)
+/* IWATER outputs: IMPEV PET PETADJ RETS SUPY SURI SURO SURS (IWATER.py:119-126) */
+#define HSP2G_OUT_IWATER(X) X(IMPEV) X(PET) X(PETADJ) X(RETS) X(SUPY) X(SURI) X(SURO) X(SURS)
+
+/* ---- error counters: err[E_x][segment], int64 (ERRMSGS tuples of the reference) ---------------------- */
+#define HSP2G_ERRORS(X)                                                                                   \
+    X(SNOW0)                                                                                              \
+    X(PWATER0) X(PWATER1) X(PWATER2) X(PWATER3) X(PWATER4) X(PWATER5) X(PWATER6) X(PWATER7) X(PWATER8)    \
+    X(PWATER9)                                                                                            \
+    X(PSTEMP0) X(PSTEMP1) X(PSTEMP2) X(PSTEMP3) X(PSTEMP4) X(PSTEMP5)                                     \
+    X(IWATER0)
+
+/* per-step shared calendar flag bits (hspsquared_b200/calendar.py) */
+#define HSP2G_CAL_HRFG 1u
+#define HSP2G_CAL_DAYFG 2u
+#define HSP2G_CAL_HR1FG 4u
+#define HSP2G_CAL_HR6IND 8u
+#define HSP2G_CAL_SEASON 16u
+#define HSP2G_CAL_NEWDAY 32u
+
+enum {
+#define X(n) P_##n,
+    HSP2G_PARAMS(X)
+#undef X
+        HSP2G_NPAR
+};
+enum {
+#define X(n) M_##n,
+    HSP2G_MONTHLY(X)
+#undef X
+        HSP2G_NMON
+};
+enum {
+#define X(n) FB_##n,
+    HSP2G_FLAGS(X)
+#undef X
+        HSP2G_NFLAG
+};
+enum {
+#define X(n) S_##n,
+    HSP2G_STATES(X)
+#undef X
+        HSP2G_NSTATE
+};
+enum {
+#define X(n) F_##n,
+    HSP2G_FORCINGS(X)
+#undef X
+        HSP2G_NFORC
+};
+enum {
+#define X(n) O_ATEMP_##n,
+    HSP2G_OUT_ATEMP(X)
+#undef X
+#define X(n) O_SNOW_##n,
+        HSP2G_OUT_SNOW(X)
+#undef X
+#define X(n) O_PWATER_##n,
+            HSP2G_OUT_PWATER(X)
+#undef X
+#define X(n) O_SEDMNT_##n,
+                HSP2G_OUT_SEDMNT(X)
+#undef X
+#define X(n) O_PSTEMP_##n,
+                    HSP2G_OUT_PSTEMP(X)
+#undef X
+#define X(n) O_PWTGAS_##n,
+                        HSP2G_OUT_PWTGAS(X)
+#undef X
+#define X(n) O_IWATER_##n,
+                            HSP2G_OUT_IWATER(X)
+#undef X
+                                HSP2G_NOUT
+};
+enum {
+#define X(n) E_##n,
+    HSP2G_ERRORS(X)
+#undef X
+        HSP2G_NERR
+};
+
+#define FLAG(n) (1ull << FB_##n)
+
+#endif

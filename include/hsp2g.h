@@ -1,0 +1,122 @@
+/*
+ * hsp2g.h -- C ABI of libhsp2g: the B200-native (sm_100a CUDA) implementation of HSP2's land-segment hot path.
+ *
+ * What it replaces.  In respec/HSPsquared every land segment is advanced by Numba loops called one segment and
+ * one activity at a time:
+ *     errors, errmsgs = function(io_manager, siminfo, ui, ts)          src/hsp2/hsp2/main.py:249-250
+ * with `function` one of atemp/snow/pwater/sedmnt/pstemp/pwtgas (PERLND) or atemp/snow/iwater (IMPLND) from the
+ * registry at src/hsp2/hsp2/configuration.py:45-55, each of which ends in an @njit core:
+ *     _atemp_  ATEMP.py:33    _snow_   SNOW.py:91     _pwater_ PWATER.py:102 (+ proute :696)
+ *     _iwater_ IWATER.py:75   _sedmnt_ SEDMNT.py:52   _pstemp_ PSTEMP.py:62  _pwtgas_ PWTGAS.py:65
+ * This library runs the same arithmetic for a BATCH of independent segments of one operation,
+ * all active sections fused into one pass per interval, in time chunks.  The reference has no FFI of its own (it is
+ * pure Python); the binding a maintainer adds is the ctypes stub of hspsquared_b200/_lib.py, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns host buffers, the library owns device memory behind the handle;
+ *   - every function returns 0 on success, non-zero on failure with a message in hsp2g_last_error() (thread local);
+ *   - there is NO CPU fallback: without a CUDA device hsp2g_batch_create fails;
+ *   - identifier spaces (parameter / monthly-table / flag-bit / state / forcing / output / error ids) are the
+ *     positions in the comma separated lists returned by hsp2g_names(); hspsquared_b200/csrc/hsp2g_ids.h is the
+ *     single definition;
+ *   - 2-D host arrays are row-major [row][segment] with leading dimension `ld` >= n_seg (elements);
+ *     device-resident arrays use ld = hsp2g_batch_npad() (segment count rounded up to 128);
+ *   - time-major series are [interval][row][segment].
+ * A handle is not thread-safe; use one handle per GPU per thread (the reference kernels hold the GIL anyway).
+ */
+#ifndef HSP2G_H
+#define HSP2G_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSP2G_ABI_VERSION 1
+
+#define HSP2G_PERLND 0 /* configuration.py:48-50 */
+#define HSP2G_IMPLND 1 /* configuration.py:51-52 */
+
+/* activity mask bits, registry order */
+#define HSP2G_ATEMP 1u
+#define HSP2G_SNOW 2u
+#define HSP2G_PWATER 4u
+#define HSP2G_SEDMNT 8u
+#define HSP2G_PSTEMP 16u
+#define HSP2G_PWTGAS 32u
+#define HSP2G_IWATER 64u
+
+/* hsp2g_set_forcing_layout opts */
+#define HSP2G_OPT_SED_RAIN_IS_PREC 1u /* SEDMNT.py:86-89: no RAINF in ts -> RAIN = PREC */
+
+typedef struct hsp2g_batch hsp2g_batch;
+
+int hsp2g_abi_version(void);
+const char *hsp2g_last_error(void);
+/* table in {"params","monthly","flags","states","forcings","outputs","errors"}; comma separated ids in order.
+ * Output ids are prefixed with their section, e.g. "SNOW_PACKF", "PWATER_SURO", "IWATER_SURO". */
+const char *hsp2g_names(const char *table);
+int hsp2g_device_count(int *count);
+
+/* One batch = n_seg segments of one operation sharing one activity mask and one time base.
+ * Replaces the per-segment dispatch loop of main.py:91-275 for land operations. */
+int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t activity_mask, double delt_minutes,
+                       hsp2g_batch **out);
+int hsp2g_batch_destroy(hsp2g_batch *b);
+int64_t hsp2g_batch_npad(const hsp2g_batch *b);
+
+/* Segment store (replaces make_numba_dict, utilities.py:58-79, and the per-step broadcast of constants,
+ * SNOW.py:49-51 / PWATER.py:51-53): structure-of-arrays fp64 parameters, one 64-bit option word per segment. */
+int hsp2g_set_params(hsp2g_batch *b, const double *par /*[n_params][ld]*/, int64_t ld);
+int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags /*[n_seg]*/);
+/* 12 monthly values per segment for one table (utilities.py:205-211 initm / :186-202 dayval). */
+int hsp2g_set_monthly(hsp2g_batch *b, int table_id, const double *tab /*[12][ld]*/, int64_t ld);
+/* Full carried state, named and hidden (hsp2tools/restart.py:9-14 plus SURVEY.md A.2-A.5). */
+int hsp2g_set_state(hsp2g_batch *b, const double *state /*[n_states][ld]*/, int64_t ld);
+int hsp2g_get_state(hsp2g_batch *b, double *state /*[n_states][ld]*/, int64_t ld);
+
+/* Shared time base (replaces hoursval/hourflag/monthval/dayval per-step arrays, utilities.py:136-202):
+ * n = steps+1 records keyed by interval start.  flags = HRFG|DAYFG<<1|HR1FG<<2|HR6IND<<3|SEASONS<<4|NEWDAY<<5. */
+int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const uint8_t *m0, const uint8_t *m1,
+                       const double *xm, const double *dxm, const double *lapse);
+
+/* Which forcing ids the [interval][row][segment] forcing arrays carry (row order = ids order), and the value every
+ * absent id reads (the reference wrappers' NaN / zero / -1e30 fills; get_timeseries utilities.py:274-290). */
+int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *forcing_ids,
+                             const double *fill /*[n_forcings]*/, uint32_t opts);
+/* Which output ids are written (the SAVE table, utilities.py:292-333), row order = ids order. */
+int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *output_ids);
+
+/* Advance all segments over intervals [t0, t0+nsteps).  State is read at the start and written at the end, so
+ * consecutive chunks are bit-identical to one pass.
+ * _device: forcings and outputs already in HBM (ld = npad); `stream` is a cudaStream_t (NULL = the batch's own).
+ * _host:   host buffers; H2D, kernel and D2H are pipelined on three streams over two device slots; buffers must stay
+ *          valid until hsp2g_sync.  Pinned host memory (hsp2g_host_alloc) is needed for real overlap. */
+int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forcing, double *d_out, void *stream);
+int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, int64_t ld_forcing,
+                   double *h_out, int64_t ld_out);
+int hsp2g_sync(hsp2g_batch *b);
+
+/* Error counters (the `errors` vectors returned beside ERRMSGS, main.py:255-257), int64 [n_errors][ld]. */
+int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld);
+int hsp2g_reset_errors(hsp2g_batch *b);
+
+/* Instrumentation: kernels launched so far and, when timing is on, the summed CUDA-event duration of those kernels
+ * (events on the launching stream). */
+int hsp2g_set_timing(hsp2g_batch *b, int on);
+int hsp2g_kernel_stats(hsp2g_batch *b, int64_t *launches, double *kernel_ms);
+const char *hsp2g_kernel_name(const hsp2g_batch *b);
+
+/* Pinned host memory / raw device memory helpers for callers without a CUDA runtime of their own. */
+void *hsp2g_host_alloc(size_t bytes);
+int hsp2g_host_free(void *p);
+void *hsp2g_device_alloc(int device, size_t bytes);
+int hsp2g_device_free(int device, void *p);
+int hsp2g_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int hsp2g_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

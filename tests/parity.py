@@ -1,0 +1,107 @@
+"""Shared parity harness: run a case of oracle/cases.py through (a) the CPU oracle, (b) the fused LandBatch path,
+(c) the drop-in activities, and compare.  Used by the CPU suite (against the host-compiled test double, bit-exact) and
+by the `-m gpu` suite (against the CUDA library through the C ABI, <= 1e-9 relative, integers exact)."""
+import copy
+
+import numpy as np
+
+from hspsquared_b200 import _lib, activities
+from hspsquared_b200.calendar import Calendar
+from hspsquared_b200.engine import ERRORS_OF, LandBatch, pack_forcings
+from hspsquared_b200.segstore import SegmentStore
+from oracle import cases as CASES
+from oracle import wrappers as W
+
+ORACLE_ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt,
+               "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas}
+RTOL = 1e-9  # BASELINE.json north_star: max relative error <= 1e-9 on all saved flows and storages
+
+
+def run_oracle(case, time_unit="us"):
+    si = CASES.siminfo_for(case)
+    si["time_unit"] = time_unit
+    ts = dict(CASES.forcings(case))
+    errs = CASES.run_segment(case["operation"], copy.deepcopy(case["tables"]), ts, si, ORACLE_ACTS)
+    return ts, errs
+
+
+def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0):
+    """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block)."""
+    si = CASES.siminfo_for(case)
+    cal = Calendar(si["start"], si["stop"], si["delt"], time_unit)
+    forc = CASES.forcings(case)
+    F = _lib.index("forcings")
+    names = [n for n in forc if n in F]
+    tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
+    store = SegmentStore.from_tables(case["operation"], tables, cal)
+    with LandBatch(store, cal, names, "all", device=device) as b:
+        out = b.run(pack_forcings(forc, names, replicate), chunk=chunk)
+        e = b.errors()
+        kname = b.kernel_name()
+        save = b.save
+    order = CASES.ORDER[case["operation"]]
+    errs = {}
+    for a in order:
+        if store.act & _lib.ACT_BITS[a]:
+            errs[a] = np.stack([e[k] for k in ERRORS_OF[a]]) if ERRORS_OF[a] else np.zeros((0, replicate), dtype=np.int64)
+    ts = {full.split("_", 1)[1]: out[:, r, :] for r, full in enumerate(save)}
+    return ts, errs, kname
+
+
+def run_dropin(case, time_unit="us", device=0):
+    """The reference's dispatch order through the drop-in activities, one section per call."""
+    si = CASES.siminfo_for(case)
+    si["time_unit"] = time_unit
+    ts = dict(CASES.forcings(case))
+    activities.DEVICE = device
+    acts = dict(activities.ACTIVITIES[case["operation"]])
+    errs = CASES.run_segment(case["operation"], copy.deepcopy(case["tables"]), ts, si, acts)
+    return ts, errs
+
+
+def rel_err(got, ref):
+    """max elementwise |got-ref| / max(|ref|, 1e-3*max|ref|, tiny), with NaN==NaN and +-1e30 sentinels exact."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if got.shape != ref.shape:
+        return np.inf
+    nan_r, nan_g = np.isnan(ref), np.isnan(got)
+    if not np.array_equal(nan_r, nan_g):
+        return np.inf
+    sent = np.abs(ref) > 1e29
+    if not np.array_equal(got[sent], ref[sent]):
+        return np.inf
+    ok = ~(nan_r | sent)
+    if not ok.any():
+        return 0.0
+    scale = np.abs(ref[ok]).max()
+    den = np.maximum(np.abs(ref[ok]), max(1e-3 * scale, 1e-300))
+    return float((np.abs(got[ok] - ref[ok]) / den).max())
+
+
+def compare(ts_ref, ts_got, exact, seg=None):
+    """-> list of (name, error) violations over the series present in ts_got that the oracle also produced."""
+    bad = []
+    for k, g in ts_got.items():
+        if k not in ts_ref:
+            bad.append((k, "not produced by the oracle"))
+            continue
+        r = ts_ref[k]
+        g = np.asarray(g)
+        if g.ndim == 2:
+            cols = range(g.shape[1]) if seg is None else [seg]
+        else:
+            cols = [None]
+        for c in cols:
+            gc = g if c is None else g[:, c]
+            n = min(len(r), len(gc))
+            if exact:
+                if not np.array_equal(gc[:n], r[:n], equal_nan=True):
+                    bad.append((k, "bits differ (max rel %.3g)" % rel_err(gc[:n], r[:n])))
+                    break
+            else:
+                e = rel_err(gc[:n], r[:n])
+                if not e <= RTOL:
+                    bad.append((k, e))
+                    break
+    return bad

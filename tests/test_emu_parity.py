@@ -1,0 +1,60 @@
+"""CPU suite: the real host stack (segment store, calendar, C ABI, chunking, drop-in activities) and the kernels'
+control flow, executed through the host-compiled TEST DOUBLE of libhsp2g (tests/emu/README.md) and compared with the
+CPU oracle BIT FOR BIT (same glibc libm, no FMA contraction).  The CUDA library itself is exercised by the `-m gpu`
+suite (tests/test_gpu_parity.py) through the same harness."""
+import numpy as np
+import pytest
+
+from oracle import cases as CASES
+
+from . import parity
+
+ALL = CASES.build_cases()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_library(oracle_lib):
+    from hspsquared_b200 import _lib
+    from tests.emu import build_emu
+
+    path = build_emu.build()
+    saved = (_lib.LIB_PATH, _lib._lib, dict(_lib._names))
+    _lib.LIB_PATH, _lib._lib = path, None
+    _lib._names.clear()
+    yield path
+    _lib.LIB_PATH, _lib._lib = saved[0], saved[1]
+    _lib._names.clear()
+    _lib._names.update(saved[2])
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+def test_fused_bit_exact(name):
+    case = ALL[name]
+    ref, ref_err = parity.run_oracle(case)
+    got, got_err, _ = parity.run_fused(case, replicate=3)
+    assert not parity.compare(ref, got, exact=True)
+    for a, e in ref_err.items():
+        assert np.array_equal(got_err[a], np.repeat(e[:, None], 3, axis=1)), a
+
+
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear"])
+def test_chunked_equals_single_pass(name):
+    """State (named + hidden) carried through the per-segment state record makes chunked runs bit-identical."""
+    case = ALL[name]
+    a, ea, _ = parity.run_fused(case)
+    b, eb, _ = parity.run_fused(case, chunk=97)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    for k in ea:
+        assert np.array_equal(ea[k], eb[k])
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+def test_dropin_bit_exact(name):
+    case = ALL[name]
+    ref, ref_err = parity.run_oracle(case)
+    got, got_err = parity.run_dropin(case)
+    assert set(ref) == set(got), "the drop-in must leave the same set of ts names as the reference wrappers"
+    assert not parity.compare(ref, got, exact=True)
+    for a, e in ref_err.items():
+        assert np.array_equal(got_err[a], e), a
