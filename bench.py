@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- segment-timesteps/s of the fused PERLND SNOW+PWATER kernel (fp64) on B200, with roofline and CPU baseline.
+
+Workload (BASELINE.json configs[1]): test10 PERLND 1, SNOW+PWATER, replicated to 100,000 segments per GPU with jittered
+parameters, 10-year hourly synthetic met, default SAVE set (13 SNOW + 11 PWATER series).
+One "step" = one time chunk of `--chunk` intervals over all segments of the rank; steps walk forward through simulated
+time, state carried.  Forcings of every timed step are resident in HBM before the timed region (each chunk is ~2.5 GB,
+far larger than the 126 MB L2, so nothing is served from cache between steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, segments sharded, no collective)
+
+`--impl reference` times the CPU oracle port (oracle/hsp2_oracle.c, OpenMP over segments) on the host cores: the
+reference itself is pure Python + Numba and cannot travel to the GPU box.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_SEGSTEP = 8 * (6 + 24)  # 6 forcings read + 24 default-SAVE series written, fp64
+N_SEG_PER_GPU = 100_000
+RUN_START, RUN_STOP = "1976-01-01", "1986-01-01"  # 87,672 hourly intervals
+
+
+def default_save():
+    from hspsquared_b200 import test10
+
+    return ["SNOW_" + n for n in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + n for n in test10.SAVE_DEFAULT["PWATER"]]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_sample(nseg, nsteps, seed=1234):
+    """Inputs of the CPU baseline in the oracle's segment-major layout, from the same synthetic generator."""
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import SEASONS, Calendar
+    from oracle import oracle
+
+    cal = Calendar(np.datetime64(RUN_START), np.datetime64(RUN_START) + np.timedelta64(nsteps, "h"), 60, "ns")
+    ens = synth.Ensemble("PERLND", nseg, seed=seed, sections=("SNOW", "PWATER"))
+    f = synth.forcing_chunk(ens, cal, 0, nsteps)  # [t][6][n]
+    forc = np.ascontiguousarray(f.transpose(2, 1, 0))  # [n][6][t]
+    names = oracle.fields("batch_par")
+    par = np.zeros((nseg, len(names)))
+    m0, m1, xm, dxm, _ = cal.day_interp()
+    mon = np.zeros((nseg, 4, nsteps + 1))
+    for i in range(nseg):
+        t = ens.tables_of(i)
+        flat = {}
+        for sec in ("SNOW", "PWATER"):
+            for grp in ("FLAGS", "PARAMETERS", "STATES"):
+                flat.update(t[sec].get(grp, {}))
+        for j, nm in enumerate(names):
+            par[i, j] = float(flat[nm])
+        for r, nm in enumerate(("CEPSC", "UZSN", "NSUR", "LZETP")):
+            tab = np.array(list(t["PWATER"]["MONTHLY_" + nm].values()))
+            v = ((tab[m1] - tab[m0]) / dxm) * xm + tab[m0]
+            mon[i, r] = np.where(xm == 0, tab[m0], v)
+    calarr = np.stack([cal.hoursval(np.ones(24), dofirst=True), cal.hourflag(0, dofirst=True),
+                       cal.hour6flag(dofirst=True), cal.monthval(SEASONS)])
+    return forc, par, mon, calarr
+
+
+def time_cpu(nthreads, nseg, nsteps, min_seconds, max_reps=50):
+    from oracle import oracle
+
+    forc, par, mon, cal = cpu_sample(nseg, nsteps)
+    oracle.perlnd_batch(nsteps, 60.0, forc[: max(1, nseg // 8)], par[: max(1, nseg // 8)], mon[: max(1, nseg // 8)], cal,
+                        nthreads)  # warm-up
+    reps, t_total, used = 0, 0.0, nthreads
+    while reps < max_reps and (t_total < min_seconds or reps < 1):
+        t0 = time.perf_counter()
+        sums, errs, used = oracle.perlnd_batch(nsteps, 60.0, forc, par, mon, cal, nthreads)
+        t_total += time.perf_counter() - t0
+        reps += 1
+    assert np.isfinite(sums[:, 13:]).all()
+    return nseg * nsteps * reps / t_total, used, reps, t_total
+
+
+def cpu_baseline(budget_s=12.0):
+    from oracle import oracle
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    nsteps = 8784
+    nseg = min(4096, 32 * cores)
+    v, used, reps, tt = time_cpu(0, nseg, nsteps, budget_s)
+    vs, _, _, _ = time_cpu(1, 48, nsteps, 3.0)
+    return {"value": v, "unit": "segment-timesteps/s", "cores": used, "kind": "port",
+            "sample": "%d segments x %d hourly intervals (1976), SNOW+PWATER, x%d repeats, %.1f s; OpenMP over segments"
+                      % (nseg, nsteps, reps, tt),
+            "serial_value": vs, "serial_cores": 1, "host_cpus": cores}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path on the host cores (oracle port; see module docstring)."""
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    nsteps, nseg = 8784, min(4096, 32 * cores)
+    forc, par, mon, cal = cpu_sample(nseg, nsteps)
+    for _ in range(max(1, args.warmup)):
+        oracle.perlnd_batch(nsteps, 60.0, forc, par, mon, cal, 0)
+    t0 = time.perf_counter()
+    used = 0
+    for _ in range(args.steps):
+        _s, _e, used = oracle.perlnd_batch(nsteps, 60.0, forc, par, mon, cal, 0)
+    dt = time.perf_counter() - t0
+    v = nseg * nsteps * args.steps / dt
+    sample = "%d segments x %d hourly intervals per step, SNOW+PWATER, default SAVE set computed" % (nseg, nsteps)
+    line = {
+        "impl": "reference", "metric": "segment-timesteps/sec PERLND SNOW+PWATER fp64", "value": v,
+        "unit": "segment-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "test10 PERLND SNOW+PWATER replicated, jittered params, hourly synthetic met "
+                               "(CPU sample of the 100k-segment x 10-yr job)", "segments_per_step": nseg,
+                   "intervals_per_step": nsteps},
+        "cpu_baseline": {"value": v, "unit": "segment-timesteps/s", "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "segment-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def device_forcing(torch, ens, cal, t0, nsteps, npad, dev):
+    """[nsteps][6][npad] fp64 forcings generated ON the device with the same elementwise expressions as
+    synth.forcing_chunk (separate mul / add kernels: no FMA), so the oracle spot-check sees identical bits."""
+    from hspsquared_b200 import synth
+
+    s = synth.shared_series("PERLND", cal, t0, nsteps)
+    n = ens.n
+    f = torch.zeros((nsteps, 6, npad), dtype=torch.float64, device=dev)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    airt = T(s["AIRTMP"])[:, None] + T(3.0 * ens.u_airt)[None, :]
+    for r, nm in enumerate(synth.PERLND_FORCINGS):
+        if nm == "PREC":
+            f[:, r, :n] = T(s["PREC"])[:, None] * T(1.0 + 0.2 * ens.u_prec)[None, :]
+        elif nm == "PETINP":
+            f[:, r, :n] = T(s["PETINP"])[:, None] * T(1.0 + 0.1 * ens.u_pet)[None, :]
+        elif nm == "AIRTMP":
+            f[:, r, :n] = airt
+        elif nm == "DTMPG":
+            f[:, r, :n] = airt - 5.0
+        else:
+            f[:, r, :n] = T(s[nm])[:, None]
+    return f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--segments", type=int, default=N_SEG_PER_GPU, help="segments per GPU")
+    ap.add_argument("--chunk", type=int, default=512, help="intervals per step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the land-segment path has no CPU fallback (use --impl reference for the CPU port)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    from hspsquared_b200 import _lib, synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    _lib.load()
+    n, Tc, K, W = args.segments, args.chunk, args.steps, args.warmup
+    cal = Calendar(RUN_START, RUN_STOP, 60, "ns")
+    total_chunks = K + W
+    if total_chunks * Tc > cal.steps:
+        sys.exit("steps*chunk exceeds the 10-year run (%d intervals)" % cal.steps)
+    ens = synth.Ensemble("PERLND", n, seed=1234 + rank, sections=("SNOW", "PWATER"))
+    store = ens.store(cal)
+    save = default_save()
+    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank)
+    npad, nf, ns = batch.npad, batch.nf, batch.ns
+    assert nf == 6 and ns == 24
+
+    # ---- device-resident inputs for every step of the run, two output slots
+    free, _tot = torch.cuda.mem_get_info(dev)
+    per_f = Tc * nf * npad * 8
+    ring = max(2, min(total_chunks, int((free * 0.6 - 2 * Tc * ns * npad * 8) // per_f)))
+    forc = [device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev) for c in range(min(ring, total_chunks))]
+    outs = [torch.empty((Tc, ns, npad), dtype=torch.float64, device=dev) for _ in range(2)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(c):
+        batch.run_device(c * Tc, Tc, forc[c % len(forc)].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for c in range(W):
+        step(c)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, _ = batch.kernel_stats()
+    e0.record(stream)
+    for c in range(W, W + K):
+        step(c)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    l1, _ = batch.kernel_stats()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    seg_steps = n * Tc * K * world
+    value = seg_steps / (ms * 1e-3)
+
+    # ---- parity spot-check of the timed run against the CPU oracle (rank 0): last chunk, three segments
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import cases as CASES
+            from oracle import wrappers as Wr
+
+            last = W + K - 1
+            got = outs[last % 2].cpu().numpy()
+            nst = (last + 1) * Tc
+            acts = {"SNOW": Wr.snow, "PWATER": Wr.pwater}
+            worst = 0.0
+            for i in (0, n // 2, n - 1):
+                si = {"start": cal.start, "stop": cal.start + np.timedelta64(nst, "h"), "delt": 60, "units": 1,
+                      "steps": nst, "time_unit": "ns"}
+                ts = synth.forcing_of(ens, cal, i, 0, nst)
+                CASES.run_segment("PERLND", ens.tables_of(i), ts, si, acts)
+                for r, full in enumerate(save):
+                    ref = ts[full.split("_", 1)[1]][last * Tc:]
+                    g = got[:, r, i]
+                    ok = ~np.isnan(ref)
+                    assert np.array_equal(np.isnan(g), ~ok)
+                    den = np.maximum(np.abs(ref[ok]), max(1e-3 * np.abs(ref[ok]).max(), 1e-300)) if ok.any() else 1.0
+                    if ok.any():
+                        worst = max(worst, float((np.abs(g[ok] - ref[ok]) / den).max()))
+            parity = {"max_rel_err_vs_oracle": worst, "segments_checked": 3, "intervals": nst, "tolerance": 1e-9}
+        except Exception as ex:  # the number stands; say that the check could not run
+            parity = {"error": repr(ex)}
+
+    # ---- end-to-end through the C ABI with HOST buffers (H2D and D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier)
+
+    peak, peak_src = measured_peak()
+    avg_launch_s = ms * 1e-3 / K
+    achieved = BYTES_PER_SEGSTEP * n * Tc / avg_launch_s / 1e9
+    line = {
+        "metric": "segment-timesteps/sec PERLND SNOW+PWATER fp64", "value": value, "unit": "segment-timesteps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "test10 PERLND SNOW+PWATER replicated to %d segments/GPU, jittered params, 10-yr hourly "
+                               "synthetic met, default SAVE (13 SNOW + 11 PWATER)" % n,
+                   "segments_per_gpu": n, "intervals_per_step": Tc, "forcings": 6, "saved_series": 24,
+                   "cache": "inputs of every step (%.2f GB) and outputs (%.2f GB) are far larger than L2; %d distinct "
+                            "forcing chunks resident" % (per_f / 1e9, Tc * ns * npad * 8 / 1e9, len(forc)),
+                   "kernel": batch.kernel_name(), "parallelism": "segments sharded over %d GPU(s), no collective" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_SEGSTEP * n * Tc,
+                     "avg_launch_ms": avg_launch_s * 1e3},
+        "gpu_launches": int(l1 - l0),
+        "clocks": clocks,
+        "parity": parity,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)}
+    batch.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier):
+    """Same metric through hsp2g_run_host: pinned host forcings in, pinned host outputs back, every step."""
+    from hspsquared_b200 import _lib, synth
+
+    lib = _lib.load()
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    Te = Tc
+    while Te > 32 and 2 * Te * (nf + ns) * n * 8 > 0.35 * avail:
+        Te //= 2
+    fb, ob = Te * nf * n * 8, Te * ns * n * 8
+    bufs = []
+    try:
+        hf, ho = [], []
+        for _ in range(2):
+            p = lib.hsp2g_host_alloc(fb)
+            q = lib.hsp2g_host_alloc(ob)
+            if not p or not q:
+                raise MemoryError(lib.hsp2g_last_error().decode())
+            bufs += [p, q]
+            hf.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(Te, nf, n)))
+            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_double)), shape=(Te, ns, n)))
+        # continue the simulation where the device-resident run stopped: keeps state and calendar consistent
+        base = (W + K) * Tc
+        for j in range(2):
+            synth.forcing_chunk(ens, cal, base + j * Te, Te, out=hf[j])
+        nwarm = 2
+        if base + (nwarm + K) * Te > cal.steps:
+            base = 0
+            batch.set_state(store.state)
+        for c in range(nwarm):
+            batch.run_host_ptr(base + c * Te, Te, hf[c % 2].ctypes.data, ho[c % 2].ctypes.data)
+        batch.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(nwarm, nwarm + K):
+            batch.run_host_ptr(base + c * Te, Te, hf[c % 2].ctypes.data, ho[c % 2].ctypes.data)
+        batch.sync()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        chk = float(np.nansum(ho[(nwarm + K - 1) % 2][-1, 13:, :]))  # device->host read of the step's result
+        return {"value": n * Te * K * world / dt, "unit": "segment-timesteps/s", "h2d_bytes_per_step": fb,
+                "d2h_bytes_per_step": ob, "intervals_per_step": Te, "steps": K, "ms_per_step": 1e3 * dt / K,
+                "pcie_gbs": (fb + ob) * K / dt / 1e9, "result_checksum": chk,
+                "note": "pinned host buffers -> hsp2g_run_host (H2D, kernel, D2H pipelined over 3 streams, 2 slots)"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+    finally:
+        for p in bufs:
+            lib.hsp2g_host_free(p)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+"""Synthetic replicated-segment workloads of BASELINE.json (definitions: SURVEY.md 8d "Synthetic inputs").
+
+Base segment = test10 PERLND 1 / IMPLND 1 (hspsquared_b200/test10.py).  Segment i gets multiplicative jitter
+p*(1+0.1*u_i), u_i ~ U(-1,1) from numpy.random.default_rng(seed) on the continuous parameters and the initial
+storages (flags unchanged); AGWRC is clipped below 0.999, IRC to (0.3, 0.85), SHADE to [0, 0.8].  Met = test10's 1976
+hourly series (hspsquared_b200/data/test10_met_1976.npz) tiled over the run with Feb-29 dropped in non-leap years,
+CLOUD omitted, and per-segment forcing jitter PREC*(1+0.2u), AIRTMP+3u degF, PETINP*(1+0.1u), DTMPG = AIRTMP-5.
+Everything is fp64 and deterministic in (seed, n_seg).
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+
+from . import test10
+from .segstore import SegmentStore, broadcast, effective
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "test10_met_1976.npz")
+PERLND_FORCINGS = ("PREC", "PETINP", "AIRTMP", "WINMOV", "SOLRAD", "DTMPG")  # north_star list, 48 B / interval
+IMPLND_FORCINGS = PERLND_FORCINGS
+
+JITTER = {
+    "PERLND": {
+        "SNOW": {"PARAMETERS": ("SNOWCF", "COVIND", "MELEV", "SHADE", "CCFACT", "MWATER", "MGMELT"),
+                 "STATES": ("PACKF", "PACKI", "PACKW")},
+        "PWATER": {"PARAMETERS": ("LZSN", "INFILT", "LSUR", "SLSUR", "AGWRC", "UZSN", "CEPSC", "NSUR", "INTFW", "IRC",
+                                  "LZETP", "DEEPFR", "AGWETP"),
+                   "STATES": ("CEPS", "SURS", "UZS", "IFWS", "LZS", "AGWS", "GWVS")},
+    },
+    "IMPLND": {
+        "SNOW": {"PARAMETERS": ("SNOWCF", "COVIND", "MELEV", "SHADE", "CCFACT", "MWATER", "MGMELT"),
+                 "STATES": ("PACKF", "PACKI", "PACKW")},
+        "IWATER": {"PARAMETERS": ("LSUR", "SLSUR", "NSUR", "RETSC"), "STATES": ("RETS", "SURS")},
+    },
+}
+CLIP = {"AGWRC": (None, 0.999), "IRC": (0.3, 0.85), "SHADE": (0.0, 0.8)}
+
+
+def base_tables(operation, sections=None):
+    t = test10.perlnd() if operation == "PERLND" else test10.implnd()
+    if sections is not None:
+        for a in t["ACTIVITY"]:
+            t["ACTIVITY"][a] = int(a in sections)
+    return t
+
+
+def _clip(name, v):
+    lo, hi = CLIP.get(name, (None, None))
+    if lo is not None or hi is not None:
+        v = np.clip(v, lo, hi)
+    return v
+
+
+class Ensemble:
+    """n jittered replicas of a base segment; `tables_of(i)` gives segment i back as UCI tables for the oracle."""
+
+    def __init__(self, operation, n, seed=1234, sections=None):
+        self.operation, self.n, self.seed = operation, int(n), seed
+        self.base = base_tables(operation, sections)
+        rng = np.random.default_rng(seed)
+        self.factor = {}
+        for sec, groups in JITTER[operation].items():
+            if not self.base["ACTIVITY"].get(sec, 0):
+                continue
+            for grp, names in groups.items():
+                for nm in names:
+                    self.factor[(sec, grp, nm)] = 1.0 + 0.1 * rng.uniform(-1.0, 1.0, self.n)
+        self.u_prec = rng.uniform(-1.0, 1.0, self.n)
+        self.u_airt = rng.uniform(-1.0, 1.0, self.n)
+        self.u_pet = rng.uniform(-1.0, 1.0, self.n)
+
+    def tables_of(self, i):
+        t = copy.deepcopy(self.base)
+        for (sec, grp, nm), f in self.factor.items():
+            t[sec][grp][nm] = float(_clip(nm, t[sec][grp][nm] * f[i]))
+            key = "MONTHLY_" + nm
+            if key in t[sec]:
+                t[sec][key] = {m: float(_clip(nm, v * f[i])) for m, v in t[sec][key].items()}
+        return t
+
+    def store(self, calendar):
+        """Vectorised build: effective values of the base, broadcast, jittered column-wise."""
+        eff = effective(self.operation, copy.deepcopy(self.base))
+        arrs = broadcast(eff, self.n)
+        for (sec, grp, nm), f in self.factor.items():
+            base = self.base[sec][grp][nm]
+            col = _clip(nm, base * f)
+            if grp == "PARAMETERS":
+                arrs["raw"][nm] = col
+            else:
+                arrs["init"][nm] = col
+            if nm in arrs["mon"]:
+                tab = np.array(list(self.base[sec]["MONTHLY_" + nm].values()), dtype=np.float64)
+                arrs["mon"][nm] = _clip(nm, tab[:, None] * f[None, :])
+        return SegmentStore.build(self.operation, arrs, calendar)
+
+
+_met = {}
+
+
+def met_1976(operation):
+    if not _met:
+        z = np.load(DATA)
+        _met.update({k: z[k] for k in z.files})
+    pre = "P_" if operation == "PERLND" else "I_"
+    return {n: _met[pre + n] for n in ("PREC", "PETINP", "AIRTMP", "WINMOV", "SOLRAD", "DTMPG")}
+
+
+def met_index(calendar):
+    """interval i of the run -> hour index into the (leap) 1976 series; Feb-29 dropped in non-leap years."""
+    t = calendar.times[: calendar.steps]
+    year = t.astype("datetime64[Y]")
+    hour_of_year = ((t - year) / np.timedelta64(1, "h")).astype(np.int64)
+    y = year.astype(np.int64) + 1970
+    leap = ((y % 4 == 0) & (y % 100 != 0)) | (y % 400 == 0)
+    feb29 = 59 * 24
+    return np.where(leap | (hour_of_year < feb29), hour_of_year, hour_of_year + 24)
+
+
+def shared_series(operation, calendar, t0, nsteps):
+    """{name: float64[nsteps]} un-jittered series of intervals [t0, t0+nsteps) (hourly runs)."""
+    if calendar.delt != 60:
+        raise ValueError("synthetic met is hourly")
+    idx = met_index(calendar)[t0:t0 + nsteps]
+    m = met_1976(operation)
+    return {k: np.ascontiguousarray(v[idx]) for k, v in m.items()}
+
+
+def forcing_chunk(ens, calendar, t0, nsteps, names=PERLND_FORCINGS, out=None):
+    """[nsteps][len(names)][n] float64 jittered forcings on the host."""
+    s = shared_series(ens.operation, calendar, t0, nsteps)
+    n = ens.n
+    if out is None:
+        out = np.empty((nsteps, len(names), n), dtype=np.float64)
+    airt = s["AIRTMP"][:, None] + 3.0 * ens.u_airt[None, :]
+    for r, nm in enumerate(names):
+        if nm == "PREC":
+            out[:, r, :] = s["PREC"][:, None] * (1.0 + 0.2 * ens.u_prec)[None, :]
+        elif nm == "PETINP":
+            out[:, r, :] = s["PETINP"][:, None] * (1.0 + 0.1 * ens.u_pet)[None, :]
+        elif nm == "AIRTMP":
+            out[:, r, :] = airt
+        elif nm == "DTMPG":
+            out[:, r, :] = airt - 5.0
+        else:
+            out[:, r, :] = s[nm][:, None]
+    return out
+
+
+def forcing_of(ens, calendar, i, t0, nsteps):
+    """{name: float64[nsteps]} forcings of segment i (what forcing_chunk puts in column i), for the oracle."""
+    s = shared_series(ens.operation, calendar, t0, nsteps)
+    airt = s["AIRTMP"] + 3.0 * ens.u_airt[i]
+    return {"PREC": s["PREC"] * (1.0 + 0.2 * ens.u_prec[i]), "PETINP": s["PETINP"] * (1.0 + 0.1 * ens.u_pet[i]),
+            "AIRTMP": airt, "DTMPG": airt - 5.0, "WINMOV": s["WINMOV"].copy(), "SOLRAD": s["SOLRAD"].copy()}

@@ -24,3 +24,19 @@ def oracle_lib():
 
     oracle.build()
     return oracle.lib()
+
+
+@pytest.fixture(scope="module")
+def emu_library(oracle_lib):
+    """Point the loader at the host-compiled TEST DOUBLE of libhsp2g for this module (tests/emu/README.md)."""
+    from hspsquared_b200 import _lib
+    from tests.emu import build_emu
+
+    path = build_emu.build()
+    saved = (_lib.LIB_PATH, _lib._lib, dict(_lib._names))
+    _lib.LIB_PATH, _lib._lib = path, None
+    _lib._names.clear()
+    yield path
+    _lib.LIB_PATH, _lib._lib = saved[0], saved[1]
+    _lib._names.clear()
+    _lib._names.update(saved[2])

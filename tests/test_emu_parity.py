@@ -13,18 +13,8 @@ ALL = CASES.build_cases()
 
 
 @pytest.fixture(scope="module", autouse=True)
-def emu_library(oracle_lib):
-    from hspsquared_b200 import _lib
-    from tests.emu import build_emu
-
-    path = build_emu.build()
-    saved = (_lib.LIB_PATH, _lib._lib, dict(_lib._names))
-    _lib.LIB_PATH, _lib._lib = path, None
-    _lib._names.clear()
-    yield path
-    _lib.LIB_PATH, _lib._lib = saved[0], saved[1]
-    _lib._names.clear()
-    _lib._names.update(saved[2])
+def _use_emu(emu_library):
+    yield
 
 
 @pytest.mark.parametrize("name", sorted(ALL))

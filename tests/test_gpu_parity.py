@@ -1,0 +1,99 @@
+"""`-m gpu`: the CUDA library (libhsp2g.so, sm_100a) through its C ABI against the CPU oracle on the same seeded
+inputs.  Bar (BASELINE.json north_star): max relative error <= 1e-9 on every saved fp64 series (NaN == NaN, -1e30
+sentinels equal), error-count vectors exactly equal.  The only arithmetic difference from the oracle is CUDA's libm
+(pow <= 2 ulp, exp/exp2/log <= 1 ulp) -- the device code is compiled with -fmad=false."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cases as CASES
+
+from . import parity
+
+pytestmark = pytest.mark.gpu
+ALL = CASES.build_cases()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_library(oracle_lib):
+    import torch
+
+    from hspsquared_b200 import _lib
+
+    assert torch.cuda.is_available(), "the -m gpu suite needs a CUDA device"
+    lib = _lib.load()
+    assert _lib.LIB_PATH.endswith(os.path.join("hspsquared_b200", "libhsp2g.so"))
+    assert _lib.device_count() >= 1
+    return lib
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+def test_fused_vs_oracle(name):
+    case = ALL[name]
+    ref, ref_err = parity.run_oracle(case)
+    got, got_err, kname = parity.run_fused(case, replicate=2)
+    bad = parity.compare(ref, got, exact=False)
+    assert not bad, "%s via %s: %s" % (name, kname, bad[:8])
+    for a, e in ref_err.items():
+        assert np.array_equal(got_err[a], np.repeat(e[:, None], 2, axis=1)), (a, got_err[a][:, 0], e)
+
+
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear"])
+def test_chunked_equals_single_pass_bitwise(name):
+    case = ALL[name]
+    a, ea, _ = parity.run_fused(case)
+    b, eb, _ = parity.run_fused(case, chunk=97)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    for k in ea:
+        assert np.array_equal(ea[k], eb[k])
+
+
+@pytest.mark.parametrize("name", ["p001_test10", "i001_test10", "cbp_fullchain", "p_nosnow_iffc2", "flowtest_pwater",
+                                  "flowtest_iwater", "i_atemp_snow"])
+def test_dropin_vs_oracle(name):
+    case = ALL[name]
+    ref, ref_err = parity.run_oracle(case)
+    got, got_err = parity.run_dropin(case)
+    assert set(ref) == set(got)
+    bad = parity.compare(ref, got, exact=False)
+    assert not bad, bad[:8]
+    for a, e in ref_err.items():
+        assert np.array_equal(got_err[a], e), a
+
+
+def test_golden_reference_arrays(golden_dir):
+    """Directly against the committed fp64 outputs of the reference's Numba kernels (tests/golden/ref_*.npz)."""
+    for name in ("p001_test10", "i001_test10", "cbp_fullchain", "p001_snow_pwater"):
+        ref = np.load(os.path.join(golden_dir, "ref_%s.npz" % name))
+        got, _, _ = parity.run_fused(ALL[name])
+        for k, g in got.items():
+            if k in ref.files:
+                e = parity.rel_err(g[:, 0], ref[k])
+                assert e <= parity.RTOL, (name, k, e)
+
+
+def test_many_segments_padding_and_blocks():
+    """333 jitter-free replicas (not a multiple of 128): every column equals column 0 bit for bit."""
+    case = ALL["p001_snow_pwater"]
+    got, errs, kname = parity.run_fused(case, replicate=333, chunk=1000)
+    assert "SNOW|PWATER" in kname
+    for k, g in got.items():
+        assert np.array_equal(g, np.repeat(g[:, :1], 333, axis=1), equal_nan=True), k
+
+
+def test_hspf_known_answers(golden_dir):
+    """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
+    hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))
+    got, errs, _ = parity.run_fused(ALL["flowtest_pwater"])
+    assert not errs["PWATER"].any()
+    for v in ("SURO", "IFWO", "AGWO"):
+        assert abs((got[v][:, 0] - hspf["PERLND1_" + v]).sum()) < 1e-3
+    got, errs, _ = parity.run_fused(ALL["flowtest_iwater"])
+    assert not errs["IWATER"].any()
+    assert abs((got["SURO"][:, 0] - hspf["IMPLND1_SURO"]).sum()) < 1e-3
+    h10 = np.load(os.path.join(golden_dir, "hspf_test10I.npz"))
+    got, _, _ = parity.run_fused(ALL["i001_test10"])
+    for v, t in {"SUPY": 2e-6, "SURO": 2e-6, "SURS": 1e-6, "RETS": 1e-6, "PET": 1e-7, "IMPEV": 1e-7}.items():
+        assert np.abs(got[v][:, 0] - h10[v]).max() < t, v
