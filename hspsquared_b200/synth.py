@@ -71,6 +71,14 @@ class Ensemble:
         self.u_airt = rng.uniform(-1.0, 1.0, self.n)
         self.u_pet = rng.uniform(-1.0, 1.0, self.n)
 
+    def shard(self, lo, hi):
+        """Segments [lo, hi) of this ensemble as an ensemble of their own (multi-GPU sharding)."""
+        e = copy.copy(self)
+        e.n = hi - lo
+        e.factor = {k: v[lo:hi] for k, v in self.factor.items()}
+        e.u_prec, e.u_airt, e.u_pet = self.u_prec[lo:hi], self.u_airt[lo:hi], self.u_pet[lo:hi]
+        return e
+
     def tables_of(self, i):
         t = copy.deepcopy(self.base)
         for (sec, grp, nm), f in self.factor.items():
