@@ -194,9 +194,10 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def device_forcing(torch, ens, cal, t0, nsteps, npad, dev):
-    """[nsteps][6][npad] fp64 forcings generated ON the device with the same elementwise expressions as
-    synth.forcing_chunk (separate mul / add kernels: no FMA), so the oracle spot-check sees identical bits."""
+def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
+    """Tile-major [ntiles][nsteps][6][32] fp64 forcings (include/hsp2g.h) generated ON the device with the same
+    elementwise expressions as synth.forcing_chunk (separate mul / add kernels: no FMA), so the oracle spot-check
+    sees identical bits.  Lanes past n in the last tile copy the last segment."""
     from hspsquared_b200 import synth
 
     s = synth.shared_series("PERLND", cal, t0, nsteps)
@@ -204,7 +205,7 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev):
     f = torch.zeros((nsteps, 6, npad), dtype=torch.float64, device=dev)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     airt = T(s["AIRTMP"])[:, None] + T(3.0 * ens.u_airt)[None, :]
-    for r, nm in enumerate(synth.PERLND_FORCINGS):
+    for r, nm in enumerate(rows):
         if nm == "PREC":
             f[:, r, :n] = T(s["PREC"])[:, None] * T(1.0 + 0.2 * ens.u_prec)[None, :]
         elif nm == "PETINP":
@@ -215,7 +216,9 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev):
             f[:, r, :n] = airt - 5.0
         else:
             f[:, r, :n] = T(s[nm])[:, None]
-    return f
+    if npad > n:
+        f[:, :, n:] = f[:, :, n - 1:n]
+    return f.view(nsteps, 6, npad // 32, 32).permute(2, 0, 1, 3).contiguous()
 
 
 def main():
@@ -274,8 +277,8 @@ def main():
     free, _tot = torch.cuda.mem_get_info(dev)
     per_f = Tc * nf * npad * 8
     ring = max(2, min(total_chunks, int((free * 0.6 - 2 * Tc * ns * npad * 8) // per_f)))
-    forc = [device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev) for c in range(min(ring, total_chunks))]
-    outs = [torch.empty((Tc, ns, npad), dtype=torch.float64, device=dev) for _ in range(2)]
+    forc = [device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(min(ring, total_chunks))]
+    outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
     torch.cuda.synchronize(dev)
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the kernels, and the events that time them, live here
     assert stream.cuda_stream != 0
@@ -327,9 +330,9 @@ def main():
                       "steps": nst, "time_unit": "ns"}
                 ts = synth.forcing_of(ens, cal, i, 0, nst)
                 CASES.run_segment("PERLND", ens.tables_of(i), ts, si, acts)
-                for r, full in enumerate(save):
+                for r, full in enumerate(batch.save_rows):
                     ref = ts[full.split("_", 1)[1]][last * Tc:]
-                    g = got[:, r, i]
+                    g = got[i // 32, :, r, i % 32]
                     ok = ~np.isnan(ref)
                     assert np.array_equal(np.isnan(g), ~ok)
                     den = np.maximum(np.abs(ref[ok]), max(1e-3 * np.abs(ref[ok]).max(), 1e-300)) if ok.any() else 1.0
@@ -383,6 +386,7 @@ def main():
 def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier):
     """Same metric through hsp2g_run_host: pinned host forcings in, pinned host outputs back, every step."""
     from hspsquared_b200 import _lib, synth
+    from hspsquared_b200.engine import tile_series
 
     lib = _lib.load()
     try:
@@ -392,9 +396,11 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
     except Exception:
         avail = 64 << 30
     Te = Tc
-    while Te > 32 and 2 * Te * (nf + ns) * n * 8 > 0.35 * avail:
+    while Te > 32 and 2 * Te * (nf + ns) * batch.npad * 8 > 0.35 * avail:
         Te //= 2
-    fb, ob = Te * nf * n * 8, Te * ns * n * 8
+    npad = batch.npad
+    nt = npad // 32
+    fb, ob = Te * nf * npad * 8, Te * ns * npad * 8
     bufs = []
     try:
         hf, ho = [], []
@@ -404,12 +410,12 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             if not p or not q:
                 raise MemoryError(lib.hsp2g_last_error().decode())
             bufs += [p, q]
-            hf.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(Te, nf, n)))
-            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_double)), shape=(Te, ns, n)))
+            hf.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(nt, Te, nf, 32)))
+            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_double)), shape=(nt, Te, ns, 32)))
         # continue the simulation where the device-resident run stopped: keeps state and calendar consistent
         base = (W + K) * Tc
         for j in range(2):
-            synth.forcing_chunk(ens, cal, base + j * Te, Te, out=hf[j])
+            hf[j][...] = tile_series(synth.forcing_chunk(ens, cal, base + j * Te, Te, names=batch.forcing_rows))
         nwarm = 2
         if base + (nwarm + K) * Te > cal.steps:
             base = 0
@@ -428,11 +434,11 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        chk = float(np.nansum(ho[(nwarm + K - 1) % 2][-1, 13:, :]))  # device->host read of the step's result
+        chk = float(np.nansum(ho[(nwarm + K - 1) % 2][:, -1, 13:, :]))  # device->host read of the step's result
         return {"value": n * Te * K * world / dt, "unit": "segment-timesteps/s", "h2d_bytes_per_step": fb,
                 "d2h_bytes_per_step": ob, "intervals_per_step": Te, "steps": K, "ms_per_step": 1e3 * dt / K,
                 "pcie_gbs": (fb + ob) * K / dt / 1e9, "result_checksum": chk,
-                "note": "pinned host buffers -> hsp2g_run_host (H2D, kernel, D2H pipelined over 3 streams, 2 slots)"}
+                "note": "pinned tile-major host buffers -> hsp2g_run_host (one contiguous H2D, kernel, one contiguous D2H per step, pipelined over 3 streams / 2 device slots)"}
     except Exception as ex:
         return {"error": repr(ex)}
     finally:

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhsp2g.so")
 
 PERLND, IMPLND = 0, 1
+ABI_VERSION = 2
+TILE = 32  # segments per tile of the series layout [tile][interval][row][32] (include/hsp2g.h)
 ACT_BITS = {"ATEMP": 1, "SNOW": 2, "PWATER": 4, "SEDMNT": 8, "PSTEMP": 16, "PWTGAS": 32, "IWATER": 64}
 OPT_SED_RAIN_IS_PREC = 1
 CAL_HRFG, CAL_DAYFG, CAL_HR1FG, CAL_HR6IND, CAL_SEASON, CAL_NEWDAY = 1, 2, 4, 8, 16, 32
@@ -39,7 +41,9 @@ _PROTOS = {
     "hsp2g_set_forcing_layout": (C.c_int, [_h, C.c_int, _i32p, _dp, C.c_uint32]),
     "hsp2g_set_save": (C.c_int, [_h, C.c_int, _i32p]),
     "hsp2g_run_device": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "hsp2g_pack_series": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hsp2g_unpack_series": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "hsp2g_sync": (C.c_int, [_h]),
     "hsp2g_get_errors": (C.c_int, [_h, _i64p, C.c_int64]),
     "hsp2g_reset_errors": (C.c_int, [_h]),
@@ -76,7 +80,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.hsp2g_abi_version() != 1:
+    if lib.hsp2g_abi_version() != ABI_VERSION:
         raise Hsp2gError("libhsp2g ABI version mismatch")
     _lib = lib
     return lib

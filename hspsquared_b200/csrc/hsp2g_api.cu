@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,6 +21,7 @@ static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && 
                   HSP2G_SEDMNT == HSP2G_ACT_SEDMNT && HSP2G_PSTEMP == HSP2G_ACT_PSTEMP &&
                   HSP2G_PWTGAS == HSP2G_ACT_PWTGAS && HSP2G_IWATER == HSP2G_ACT_IWATER,
               "public activity bits must match the kernel's");
+static_assert(HSP2G_ABI_VERSION == 2, "bump _lib.py with the header");
 static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
 static_assert(sizeof(CalStep) == 32, "CalStep layout");
 
@@ -47,12 +50,12 @@ struct Slot {
 
 struct hsp2g_batch {
     int device = 0, op = 0;
-    int64_t n_seg = 0, n_pad = 0;
+    int64_t n_seg = 0, n_pad = 0, ntiles = 0;
     unsigned act = 0, opts = 0;
     double delt = 60.0;
-    double *par = nullptr, *mon = nullptr, *state = nullptr;
-    unsigned long long *flags = nullptr;
-    long long *err = nullptr;
+    double *segblk = nullptr;  // [tile][SB_ROWS][32]: option word, parameters, states, error counters
+    double *mon = nullptr;     // [tile][slot*12 + month][32]
+    std::vector<double> h_mon; // host copy [slot][12][n_seg] (tables arrive one at a time)
     CalStep *cal = nullptr;
     int64_t ncal = 0;
     int nmon_slots = 0;
@@ -103,14 +106,37 @@ const char *k_errors = HSP2G_ERRORS(NAME_ITEM);
 const char *k_outputs = HSP2G_OUT_ATEMP(OA) HSP2G_OUT_SNOW(OS) HSP2G_OUT_PWATER(OP) HSP2G_OUT_SEDMNT(OD)
     HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI);
 
-int upload2d(void *dst, int64_t n_pad, const void *src, int64_t ld, int64_t n_seg, int64_t rows, size_t elt) {
-    CU(cudaMemcpy2D(dst, (size_t)n_pad * elt, src, (size_t)ld * elt, (size_t)n_seg * elt, (size_t)rows,
+// host [rows][ld] (segment-minor) <-> device tile-major rows [tile][row0 + r][32] of a block with `blk_rows` rows per
+// tile.  Padded lanes of the last tile receive copies of the last real segment (land_common.cuh).
+int upload_rows(double *blk, int blk_rows, int row0, const void *src, int64_t ld, int64_t n_seg, int64_t ntiles,
+                int rows) {
+    std::vector<uint64_t> pk((size_t)ntiles * rows * LAND_TILE);
+    const uint64_t *in = (const uint64_t *)src;
+    for (int64_t t = 0; t < ntiles; ++t)
+        for (int r = 0; r < rows; ++r)
+            for (int l = 0; l < LAND_TILE; ++l) {
+                int64_t seg = t * LAND_TILE + l;
+                if (seg >= n_seg) seg = n_seg - 1;
+                pk[((size_t)t * rows + r) * LAND_TILE + l] = in[(size_t)r * ld + seg];
+            }
+    const size_t w = (size_t)rows * LAND_TILE * 8;
+    CU(cudaMemcpy2D(blk + (size_t)row0 * LAND_TILE, (size_t)blk_rows * LAND_TILE * 8, pk.data(), w, w, (size_t)ntiles,
                     cudaMemcpyHostToDevice));
     return 0;
 }
-int download2d(void *dst, int64_t ld, const void *src, int64_t n_pad, int64_t n_seg, int64_t rows, size_t elt) {
-    CU(cudaMemcpy2D(dst, (size_t)ld * elt, src, (size_t)n_pad * elt, (size_t)n_seg * elt, (size_t)rows,
+int download_rows(void *dst, int64_t ld, const double *blk, int blk_rows, int row0, int64_t n_seg, int64_t ntiles,
+                  int rows) {
+    std::vector<uint64_t> pk((size_t)ntiles * rows * LAND_TILE);
+    const size_t w = (size_t)rows * LAND_TILE * 8;
+    CU(cudaMemcpy2D(pk.data(), w, blk + (size_t)row0 * LAND_TILE, (size_t)blk_rows * LAND_TILE * 8, w, (size_t)ntiles,
                     cudaMemcpyDeviceToHost));
+    uint64_t *out = (uint64_t *)dst;
+    for (int64_t t = 0; t < ntiles; ++t)
+        for (int r = 0; r < rows; ++r)
+            for (int l = 0; l < LAND_TILE; ++l) {
+                const int64_t seg = t * LAND_TILE + l;
+                if (seg < n_seg) out[(size_t)r * ld + seg] = pk[((size_t)t * rows + r) * LAND_TILE + l];
+            }
     return 0;
 }
 
@@ -155,16 +181,13 @@ int drain_timing(hsp2g_batch *b) {
 int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, cudaStream_t st) {
     LandLaunch L;
     memset(&L, 0, sizeof L);
-    L.par = b->par;
+    L.segblk = b->segblk;
     L.mon = b->mon;
-    L.flags = b->flags;
-    L.state = b->state;
-    L.err = b->err;
     L.forc = d_forc;
     L.out = d_out;
     L.cal = b->cal + t0;
-    L.n_pad = b->n_pad;
-    L.n_seg = (int)b->n_seg;
+    L.ntiles = (int)b->ntiles;
+    L.mon_rows = 12 * b->nmon_slots;
     L.nsteps = nsteps;
     L.first_chunk = t0 == 0;
     L.nf = b->nf;
@@ -195,6 +218,23 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     return 0;
 }
 }  // namespace
+
+// Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
+// forcing rows are present) and ask for a carve-out that leaves the rest of the 256 KB to L1, where the parameter
+// rows of the resident tiles live.
+cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes) {
+    static std::mutex mu;
+    static std::map<const void *, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && it->second >= smem_bytes) return cudaSuccess;
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    done[kernel] = smem_bytes;
+    return cudaSuccess;
+}
 
 extern "C" {
 
@@ -250,7 +290,8 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
     b->device = device;
     b->op = operation;
     b->n_seg = n_seg;
-    b->n_pad = (n_seg + LAND_BLOCK - 1) / LAND_BLOCK * LAND_BLOCK;
+    b->ntiles = (n_seg + LAND_TILE - 1) / LAND_TILE;
+    b->n_pad = b->ntiles * LAND_TILE;
     b->act = act;
     b->delt = delt;
     for (int i = 0; i < HSP2G_NMON; ++i) b->mslot[i] = -1;
@@ -267,10 +308,7 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
         return fail("cudaMalloc(%zu bytes): %s", (size_t)(bytes), cudaGetErrorString(ce)); \
     }                                                                              \
     cudaMemset((ptr), 0, (bytes));
-    ALLOC(b->par, np * HSP2G_NPAR * sizeof(double));
-    ALLOC(b->state, np * HSP2G_NSTATE * sizeof(double));
-    ALLOC(b->flags, np * sizeof(unsigned long long));
-    ALLOC(b->err, np * HSP2G_NERR * sizeof(long long));
+    ALLOC(b->segblk, np * SB_ROWS * sizeof(double));
 #undef ALLOC
     CU(cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
@@ -288,11 +326,8 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     if (!b) return 0;
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
-    cudaFree(b->par);
+    cudaFree(b->segblk);
     cudaFree(b->mon);
-    cudaFree(b->state);
-    cudaFree(b->flags);
-    cudaFree(b->err);
     cudaFree(b->cal);
     for (auto &s : b->slot) {
         cudaFree(s.forc);
@@ -319,7 +354,7 @@ int hsp2g_set_params(hsp2g_batch *b, const double *par, int64_t ld) {
     if (!b || !par) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
-    if (upload2d(b->par, b->n_pad, par, ld, b->n_seg, HSP2G_NPAR, sizeof(double))) return 1;
+    if (upload_rows(b->segblk, SB_ROWS, SB_PAR, par, ld, b->n_seg, b->ntiles, HSP2G_NPAR)) return 1;
     b->have_par = true;
     return 0;
 }
@@ -327,7 +362,7 @@ int hsp2g_set_params(hsp2g_batch *b, const double *par, int64_t ld) {
 int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags) {
     if (!b || !flags) return fail("null argument");
     DeviceGuard g(b->device);
-    CU(cudaMemcpy(b->flags, flags, (size_t)b->n_seg * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (upload_rows(b->segblk, SB_ROWS, SB_FLAGS, flags, b->n_seg, b->n_seg, b->ntiles, 1)) return 1;
     b->have_flags = true;
     return 0;
 }
@@ -337,20 +372,18 @@ int hsp2g_set_monthly(hsp2g_batch *b, int id, const double *tab, int64_t ld) {
     if (id < 0 || id >= HSP2G_NMON) return fail("monthly table id %d out of range", id);
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
-    if (b->mslot[id] < 0) {  // grow the slot array by one table
-        const size_t one = (size_t)12 * b->n_pad * sizeof(double);
-        double *nm = nullptr;
-        CU(cudaMalloc((void **)&nm, one * (b->nmon_slots + 1)));
-        CU(cudaMemset(nm, 0, one * (b->nmon_slots + 1)));
-        if (b->mon) {
-            CU(cudaDeviceSynchronize());
-            CU(cudaMemcpy(nm, b->mon, one * b->nmon_slots, cudaMemcpyDeviceToDevice));
-            cudaFree(b->mon);
-        }
-        b->mon = nm;
+    const size_t one = (size_t)12 * b->n_seg;
+    if (b->mslot[id] < 0) {  // a new table: grow the host copy and the tile-major device block by one slot
         b->mslot[id] = (short)b->nmon_slots++;
+        b->h_mon.resize(one * b->nmon_slots);
+        CU(cudaDeviceSynchronize());
+        cudaFree(b->mon);
+        b->mon = nullptr;
+        CU(cudaMalloc((void **)&b->mon, (size_t)b->ntiles * 12 * b->nmon_slots * LAND_TILE * sizeof(double)));
     }
-    return upload2d(b->mon + (size_t)b->mslot[id] * 12 * b->n_pad, b->n_pad, tab, ld, b->n_seg, 12, sizeof(double));
+    for (int m = 0; m < 12; ++m)
+        memcpy(&b->h_mon[one * b->mslot[id] + (size_t)m * b->n_seg], tab + (size_t)m * ld, (size_t)b->n_seg * sizeof(double));
+    return upload_rows(b->mon, 12 * b->nmon_slots, 0, b->h_mon.data(), b->n_seg, b->n_seg, b->ntiles, 12 * b->nmon_slots);
 }
 
 int hsp2g_set_state(hsp2g_batch *b, const double *st, int64_t ld) {
@@ -358,7 +391,7 @@ int hsp2g_set_state(hsp2g_batch *b, const double *st, int64_t ld) {
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
     CU(cudaStreamSynchronize(b->comp));
-    if (upload2d(b->state, b->n_pad, st, ld, b->n_seg, HSP2G_NSTATE, sizeof(double))) return 1;
+    if (upload_rows(b->segblk, SB_ROWS, SB_STATE, st, ld, b->n_seg, b->ntiles, HSP2G_NSTATE)) return 1;
     b->have_state = true;
     return 0;
 }
@@ -368,7 +401,7 @@ int hsp2g_get_state(hsp2g_batch *b, double *st, int64_t ld) {
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
     CU(cudaStreamSynchronize(b->comp));
-    return download2d(st, ld, b->state, b->n_pad, b->n_seg, HSP2G_NSTATE, sizeof(double));
+    return download_rows(st, ld, b->segblk, SB_ROWS, SB_STATE, b->n_seg, b->ntiles, HSP2G_NSTATE);
 }
 
 int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const uint8_t *m0, const uint8_t *m1,
@@ -434,15 +467,15 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
     if (check_ready(b, t0, nsteps)) return 1;
     if (b->nf > 0 && !d_forc) return fail("null forcing pointer");
     if (b->ns > 0 && !d_out) return fail("null output pointer");
+    if (((uintptr_t)d_forc | (uintptr_t)d_out) & 15) return fail("device series must be 16-byte aligned (TMA bulk copies)");
     DeviceGuard g(b->device);
     return launch(b, t0, nsteps, d_forc, d_out, stream ? (cudaStream_t)stream : b->comp);
 }
 
-int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, int64_t ldf, double *h_out,
-                   int64_t ldo) {
+int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, double *h_out) {
     if (check_ready(b, t0, nsteps)) return 1;
-    if (b->nf > 0 && (!h_forc || ldf < b->n_seg)) return fail("bad forcing buffer / ld");
-    if (b->ns > 0 && (!h_out || ldo < b->n_seg)) return fail("bad output buffer / ld");
+    if (b->nf > 0 && !h_forc) return fail("null forcing buffer");
+    if (b->ns > 0 && !h_out) return fail("null output buffer");
     DeviceGuard g(b->device);
     Slot &s = b->slot[b->next_slot];
     b->next_slot ^= 1;
@@ -464,20 +497,48 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
             s.cap_o = need_o;
         }
     }
-    // the slot is free once its previous outputs have left the device
+    // the slot is free once its previous outputs have left the device; host and device share the tile-major
+    // layout, so each direction is ONE contiguous copy
     CU(cudaStreamWaitEvent(b->h2d, s.d2h_done, 0));
-    if (b->nf > 0)
-        CU(cudaMemcpy2DAsync(s.forc, row, h_forc, (size_t)ldf * sizeof(double), (size_t)b->n_seg * sizeof(double),
-                             (size_t)nsteps * b->nf, cudaMemcpyHostToDevice, b->h2d));
+    if (need_f) CU(cudaMemcpyAsync(s.forc, h_forc, need_f, cudaMemcpyHostToDevice, b->h2d));
     CU(cudaEventRecord(s.h2d_done, b->h2d));
     CU(cudaStreamWaitEvent(b->comp, s.h2d_done, 0));
     if (launch(b, t0, nsteps, s.forc, s.out, b->comp)) return 1;
     CU(cudaEventRecord(s.k_done, b->comp));
     CU(cudaStreamWaitEvent(b->d2h, s.k_done, 0));
-    if (b->ns > 0)
-        CU(cudaMemcpy2DAsync(h_out, (size_t)ldo * sizeof(double), s.out, row, (size_t)b->n_seg * sizeof(double),
-                             (size_t)nsteps * b->ns, cudaMemcpyDeviceToHost, b->d2h));
+    if (need_o) CU(cudaMemcpyAsync(h_out, s.out, need_o, cudaMemcpyDeviceToHost, b->d2h));
     CU(cudaEventRecord(s.d2h_done, b->d2h));
+    return 0;
+}
+
+int hsp2g_pack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, int64_t ld, double *dst) {
+    if (!src || !dst) return fail("null argument");
+    if (n_seg <= 0 || nsteps < 0 || nrows < 0 || ld < n_seg) return fail("bad series shape");
+    const int64_t ntiles = (n_seg + LAND_TILE - 1) / LAND_TILE;
+    for (int64_t tl = 0; tl < ntiles; ++tl)
+        for (int64_t t = 0; t < nsteps; ++t)
+            for (int r = 0; r < nrows; ++r) {
+                const double *in = src + ((size_t)t * nrows + r) * ld;
+                double *o = dst + (((size_t)tl * nsteps + t) * nrows + r) * LAND_TILE;
+                for (int l = 0; l < LAND_TILE; ++l) {
+                    int64_t seg = tl * LAND_TILE + l;
+                    o[l] = in[seg < n_seg ? seg : n_seg - 1];
+                }
+            }
+    return 0;
+}
+
+int hsp2g_unpack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, double *dst, int64_t ld) {
+    if (!src || !dst) return fail("null argument");
+    if (n_seg <= 0 || nsteps < 0 || nrows < 0 || ld < n_seg) return fail("bad series shape");
+    const int64_t ntiles = (n_seg + LAND_TILE - 1) / LAND_TILE;
+    for (int64_t tl = 0; tl < ntiles; ++tl) {
+        const int64_t n = n_seg - tl * LAND_TILE < LAND_TILE ? n_seg - tl * LAND_TILE : LAND_TILE;
+        for (int64_t t = 0; t < nsteps; ++t)
+            for (int r = 0; r < nrows; ++r)
+                memcpy(dst + ((size_t)t * nrows + r) * ld + tl * LAND_TILE,
+                       src + (((size_t)tl * nsteps + t) * nrows + r) * LAND_TILE, (size_t)n * sizeof(double));
+    }
     return 0;
 }
 
@@ -495,14 +556,15 @@ int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld) {
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
     CU(cudaStreamSynchronize(b->comp));
-    return download2d(err, ld, b->err, b->n_pad, b->n_seg, HSP2G_NERR, sizeof(long long));
+    return download_rows(err, ld, b->segblk, SB_ROWS, SB_ERR, b->n_seg, b->ntiles, HSP2G_NERR);
 }
 
 int hsp2g_reset_errors(hsp2g_batch *b) {
     if (!b) return fail("null batch");
     DeviceGuard g(b->device);
     CU(cudaStreamSynchronize(b->comp));
-    CU(cudaMemset(b->err, 0, (size_t)b->n_pad * HSP2G_NERR * sizeof(long long)));
+    CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
+                    (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
     return 0;
 }
 

@@ -1,0 +1,67 @@
+// io_configs.h -- the compile-time I/O configurations (StaticIO) the library ships besides the run-time one.
+// A batch whose forcing rows and SAVE rows are in ascending id order and equal one of these sets runs the
+// specialised kernel; anything else runs the DynIO kernel (same arithmetic, row tables read at run time).
+#pragma once
+#include "land_common.cuh"
+
+constexpr unsigned long long fbit(int id) { return 1ull << id; }
+constexpr unsigned long long olo(int oid) { return oid < 64 ? 1ull << oid : 0ull; }
+constexpr unsigned long long ohi(int oid) { return oid >= 64 ? 1ull << (oid - 64) : 0ull; }
+
+// the six meteorological series of a SNOW(+water) segment without ATEMP / CLOUD (BASELINE.json north_star)
+constexpr unsigned long long FM_MET6 = fbit(F_PREC) | fbit(F_PETINP) | fbit(F_AIRTMP) | fbit(F_WINMOV) | fbit(F_SOLRAD) |
+                                       fbit(F_DTMPG);
+// ... with ATEMP computing AIRTMP from GATMP
+constexpr unsigned long long FM_MET6_GATMP = (FM_MET6 & ~fbit(F_AIRTMP)) | fbit(F_GATMP);
+constexpr unsigned long long FM_PREC_PET = fbit(F_PREC) | fbit(F_PETINP);
+
+// default SAVE tables (hsp2tools/data/SaveTable.csv): SNOW 13, PWATER 11, IWATER 3
+#define SAVE_SNOW_DEFAULT(B)                                                                                      \
+    (B(O_SNOW_COVINX) | B(O_SNOW_DULL) | B(O_SNOW_PACKF) | B(O_SNOW_PACKI) | B(O_SNOW_PACKW) | B(O_SNOW_PACK) |   \
+     B(O_SNOW_PAKTMP) | B(O_SNOW_RAINF) | B(O_SNOW_RDENPF) | B(O_SNOW_SKYCLR) | B(O_SNOW_SNOCOV) |                \
+     B(O_SNOW_WYIELD) | B(O_SNOW_XLNMLT))
+#define SAVE_PWATER_DEFAULT(B)                                                                                    \
+    (B(O_PWATER_AGWO) | B(O_PWATER_AGWS) | B(O_PWATER_CEPS) | B(O_PWATER_GWVS) | B(O_PWATER_IFWO) |               \
+     B(O_PWATER_IFWS) | B(O_PWATER_LZS) | B(O_PWATER_PERO) | B(O_PWATER_SURO) | B(O_PWATER_SURS) | B(O_PWATER_UZS))
+#define SAVE_IWATER_DEFAULT(B) (B(O_IWATER_RETS) | B(O_IWATER_SURO) | B(O_IWATER_SURS))
+// the three runoff components a CBP-style watershed run keeps (tests/land_spec/hwmA51800.uci:493-495)
+#define SAVE_PWATER_FLOWS(B) (B(O_PWATER_SURO) | B(O_PWATER_IFWO) | B(O_PWATER_AGWO))
+
+// all outputs of a section: ids are contiguous per section (hsp2g_ids.h)
+constexpr unsigned long long range_lo(int a, int b) {  // bits [a, b) that fall in 0..63
+    unsigned long long m = 0;
+    for (int i = a; i < b; ++i) m |= olo(i);
+    return m;
+}
+constexpr unsigned long long range_hi(int a, int b) {
+    unsigned long long m = 0;
+    for (int i = a; i < b; ++i) m |= ohi(i);
+    return m;
+}
+
+typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_PWATER_DEFAULT(olo), SAVE_SNOW_DEFAULT(ohi) | SAVE_PWATER_DEFAULT(ohi)>
+    IO_SnowPwaterDefault;
+typedef StaticIO<FM_MET6, range_lo(O_SNOW_ALBEDO, O_PWATER_INFFAC + 1), range_hi(O_SNOW_ALBEDO, O_PWATER_INFFAC + 1)>
+    IO_SnowPwaterAll;
+typedef StaticIO<FM_MET6, SAVE_PWATER_FLOWS(olo), SAVE_PWATER_FLOWS(ohi)> IO_SnowPwaterFlows;
+typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_IWATER_DEFAULT(olo), SAVE_SNOW_DEFAULT(ohi) | SAVE_IWATER_DEFAULT(ohi)>
+    IO_SnowIwaterDefault;
+
+// does the launch record describe exactly this static configuration (rows in ascending id order)?
+template <class IO>
+static inline bool io_matches(const LandLaunch &L) {
+    if (L.nf != IO::NF || L.ns != IO::NS) return false;
+    int r = 0;
+    for (int id = 0; id < HSP2G_NFORC; ++id) {
+        const bool on = (IO::FMASK >> id) & 1ull;
+        if (L.frow[id] != (on ? r : -1)) return false;
+        r += on;
+    }
+    r = 0;
+    for (int id = 0; id < HSP2G_NOUT; ++id) {
+        const bool on = ((id < 64 ? IO::S0 : IO::S1) >> (id & 63)) & 1ull;
+        if (L.srow[id] != (on ? r : -1)) return false;
+        r += on;
+    }
+    return true;
+}

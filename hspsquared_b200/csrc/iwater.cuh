@@ -11,22 +11,26 @@ struct IwaterState {
     double rets, surs, msupy, dec, src, petadj;
     double retsc;  // daily-interpolated retention capacity
 
-    __device__ __forceinline__ void load(const Seg &s) {
+    template <class SEG>
+
+    __device__ __forceinline__ void load(const SEG &s) {
         rets = s.st(S_RETS); surs = s.st(S_SURS); msupy = s.st(S_MSUPY); dec = s.st(S_DEC); src = s.st(S_SRC);
         petadj = s.st(S_PETADJ);
     }
-    __device__ __forceinline__ void store(const Seg &s) const {
+    template <class SEG>
+    __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_RETS, rets); s.st(S_SURS, surs); s.st(S_MSUPY, msupy); s.st(S_DEC, dec); s.st(S_SRC, src);
         s.st(S_PETADJ, petadj);
     }
-    __device__ __forceinline__ void refresh_daily(const Seg &s) { retsc = s.daily(FB_M_RETSC, M_RETSC, P_RETSC); }
+    template <class SEG>
+    __device__ __forceinline__ void refresh_daily(const SEG &s) { retsc = s.daily(FB_M_RETSC, M_RETSC, P_RETSC); }
 };
 
-template <bool HOURLY>
-__device__ __forceinline__ void iwater_step(const Seg &s, IwaterState &w, const SnowLink &sn, double prec) {
+template <bool HOURLY, class SEG>
+__device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const SnowLink &sn, double prec) {
     const double delt60 = s.L.delt60;
-    const bool hrfg = HOURLY ? true : (s.cal.flags & HSP2G_CAL_HRFG);
-    const bool hr1fg = s.cal.flags & HSP2G_CAL_HR1FG;
+    const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
+    const bool hr1fg = s.calfl & HSP2G_CAL_HR1FG;
     const double oldmsupy = w.msupy;
     const double petinp = s.forcing(F_PETINP);
     double supy, pet, petadj_out = 0.0;

@@ -1,14 +1,17 @@
-// land_kernels.cuh -- the fused per-segment time loops.  One thread = one land segment; a thread walks the
-// chunk's intervals strictly in order (the recursion in time is sequential) with every storage in
-// registers, reads its forcings from its private cp.async ring and streams the SAVEd series out time-major.
+// land_kernels.cuh -- the fused per-segment time loops.  One thread = one land segment, one warp = one tile of
+// 32 segments; a warp walks the chunk's intervals strictly in order (the recursion in time is sequential,
+// SURVEY.md 5) with every storage in registers, takes its forcings from its TMA-filled shared-memory ring and
+// streams the SAVEd series out time-major (land_common.cuh).
 //
 // Activity order inside an interval is the reference registry's (configuration.py:48-52):
 //   PERLND: ATEMP -> SNOW -> PWATER -> SEDMNT -> PSTEMP -> PWTGAS        IMPLND: ATEMP -> SNOW -> IWATER
 // All couplings are same-interval, so one pass per interval is exact.
 //
-// ACT_CT >= 0 fixes the activity mask at compile time (hot configurations); ACT_CT < 0 reads it from the launch
-// record.  HOURLY = the run step is >= 60 min, where HRFG is identically 1 (calendar.py hoursval), which lets the
-// compiler drop most of SNOW's hour-gated carried scalars from the loop-carried register set.
+// Template parameters
+//   ACT_CT >= 0  fixes the activity mask at compile time (hot configurations); < 0 reads it from the launch record;
+//   HOURLY       the run step is >= 60 min, where HRFG is identically 1 (calendar.py hoursval), which lets the
+//                compiler drop most of SNOW's hour-gated carried scalars from the loop-carried register set;
+//   IO           StaticIO<...> (forcing rows and SAVE set fixed at compile time) or DynIO (launch-record tables).
 #pragma once
 #include "iwater.cuh"
 #include "land_common.cuh"
@@ -20,24 +23,33 @@
 
 #define OPT_SED_RAIN_IS_PREC 1u  // SEDMNT: no RAINF in ts -> RAIN = PREC (SEDMNT.py:86-89)
 
-__device__ __forceinline__ double atemp_step(const Seg &s, double prec) {
+#ifdef HSP2G_HOST_EMU
+#define LAND_SMEM_DECL double *smem = ring
+#else
+#define LAND_SMEM_DECL extern __shared__ __align__(128) double smem[]
+#endif
+
+template <class SEG>
+__device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
     // ATEMP.py:57-58 with k = delt*0.000833 (ATEMP.py:22)
     const double k = s.L.delt * 0.000833;
-    const double lapse = prec > k ? 0.0035 : s.cal.lapse;
+    const double lapse = prec > k ? 0.0035 : s.calp->lapse;
     const double airtmp = s.forcing(F_GATMP) - lapse * s.par(P_ELDAT);
     s.save(O_ATEMP_AIRTMP, airtmp);
     return airtmp;
 }
 
-template <int ACT_CT, bool HOURLY>
-__global__ void __launch_bounds__(LAND_BLOCK) perlnd_kernel(const __grid_constant__ LandLaunch L) {
-    extern __shared__ double ring[];
-    const long long seg = (long long)blockIdx.x * LAND_BLOCK + threadIdx.x;
-    if (seg >= L.n_seg) return;
+template <int ACT_CT, bool HOURLY, class IO, int MINB>
+__global__ void __launch_bounds__(LAND_BLOCK, MINB) perlnd_kernel(const __grid_constant__ LandLaunch L) {
+    LAND_SMEM_DECL;
+    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    const int tile = blockIdx.x * LAND_WARPS + wib;
+    if (tile >= L.ntiles) return;  // warp-uniform
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
-    Seg s(L, seg);
-    Pipe pipe{ring + threadIdx.x, L.forc + seg, (long long)L.nf * L.n_pad, L.n_pad, L.nf, L.nsteps};
-    pipe.prologue();
+    const int nf = IO::STATIC ? IO::NF : L.nf;
+    Seg<IO> s(L, tile, lane);
+    Pipe pipe;
+    pipe.init(smem, wib, lane, L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, nf, L.nsteps);
 
     SnowState sw;
     PwaterState pw;
@@ -49,10 +61,7 @@ __global__ void __launch_bounds__(LAND_BLOCK) perlnd_kernel(const __grid_constan
     if (act & HSP2G_ACT_PSTEMP) ps.load(s);
 
     for (int t = 0; t < L.nsteps; ++t) {
-        s.t = t;
-        s.stage = pipe.acquire(t);
-        pipe.release(t);
-        s.cal = L.cal[t];
+        s.begin_step(pipe.acquire(t));
         const double prec = s.forcing(F_PREC);
         const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
 
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(LAND_BLOCK) perlnd_kernel(const __grid_constan
 
         PwaterFlux fx;
         if (act & HSP2G_ACT_PWATER) {
-            if (t == 0 || (s.cal.flags & HSP2G_CAL_NEWDAY)) pw.refresh_daily(s);
+            if (t == 0 || (s.calfl & HSP2G_CAL_NEWDAY)) pw.refresh_daily(s);
             pwater_step<HOURLY>(s, pw, link, prec, fx);
         } else {
             fx.suro = s.forcing(F_SURO);
@@ -96,23 +105,26 @@ __global__ void __launch_bounds__(LAND_BLOCK) perlnd_kernel(const __grid_constan
             soil.lgtmp = s.forcing(F_LGTMP);
         }
         if (act & HSP2G_ACT_PWTGAS) pwtgas_step(s, soil, link.wyield, fx.suro, fx.ifwo, fx.agwo);
+        s.end_step();
+        pipe.release(t);
     }
-    cp_async_wait<0>();
     if (act & HSP2G_ACT_SNOW) sw.store(s);
     if (act & HSP2G_ACT_PWATER) pw.store(s);
     if (act & HSP2G_ACT_SEDMNT) sd.store(s);
     if (act & HSP2G_ACT_PSTEMP) ps.store(s);
 }
 
-template <int ACT_CT, bool HOURLY>
-__global__ void __launch_bounds__(LAND_BLOCK) implnd_kernel(const __grid_constant__ LandLaunch L) {
-    extern __shared__ double ring[];
-    const long long seg = (long long)blockIdx.x * LAND_BLOCK + threadIdx.x;
-    if (seg >= L.n_seg) return;
+template <int ACT_CT, bool HOURLY, class IO, int MINB>
+__global__ void __launch_bounds__(LAND_BLOCK, MINB) implnd_kernel(const __grid_constant__ LandLaunch L) {
+    LAND_SMEM_DECL;
+    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    const int tile = blockIdx.x * LAND_WARPS + wib;
+    if (tile >= L.ntiles) return;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
-    Seg s(L, seg);
-    Pipe pipe{ring + threadIdx.x, L.forc + seg, (long long)L.nf * L.n_pad, L.n_pad, L.nf, L.nsteps};
-    pipe.prologue();
+    const int nf = IO::STATIC ? IO::NF : L.nf;
+    Seg<IO> s(L, tile, lane);
+    Pipe pipe;
+    pipe.init(smem, wib, lane, L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, nf, L.nsteps);
 
     SnowState sw;
     IwaterState iw;
@@ -120,10 +132,7 @@ __global__ void __launch_bounds__(LAND_BLOCK) implnd_kernel(const __grid_constan
     if (act & HSP2G_ACT_IWATER) iw.load(s);
 
     for (int t = 0; t < L.nsteps; ++t) {
-        s.t = t;
-        s.stage = pipe.acquire(t);
-        pipe.release(t);
-        s.cal = L.cal[t];
+        s.begin_step(pipe.acquire(t));
         const double prec = s.forcing(F_PREC);
         const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
         SnowFlux sx;
@@ -142,11 +151,17 @@ __global__ void __launch_bounds__(LAND_BLOCK) implnd_kernel(const __grid_constan
         }
         link.airtmp = airtmp;
         if (act & HSP2G_ACT_IWATER) {
-            if (t == 0 || (s.cal.flags & HSP2G_CAL_NEWDAY)) iw.refresh_daily(s);
+            if (t == 0 || (s.calfl & HSP2G_CAL_NEWDAY)) iw.refresh_daily(s);
             iwater_step<HOURLY>(s, iw, link, prec);
         }
+        s.end_step();
+        pipe.release(t);
     }
-    cp_async_wait<0>();
     if (act & HSP2G_ACT_SNOW) sw.store(s);
     if (act & HSP2G_ACT_IWATER) iw.store(s);
+}
+
+// dynamic shared memory of one block: PIPE_STAGES interval stages per warp + one mbarrier per stage
+static inline size_t land_smem_bytes(int nf) {
+    return (size_t)LAND_WARPS * PIPE_STAGES * ((size_t)nf * LAND_TILE * sizeof(double) + 8);
 }

@@ -9,10 +9,12 @@
 
 struct PstempState {
     double sltmp, ultmp, lgtmp, airts;
-    __device__ __forceinline__ void load(const Seg &s) {
+    template <class SEG>
+    __device__ __forceinline__ void load(const SEG &s) {
         sltmp = s.st(S_SLTMP); ultmp = s.st(S_ULTMP); lgtmp = s.st(S_LGTMP); airts = s.st(S_AIRTS);
     }
-    __device__ __forceinline__ void store(const Seg &s) const {
+    template <class SEG>
+    __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_SLTMP, sltmp); s.st(S_ULTMP, ultmp); s.st(S_LGTMP, lgtmp); s.st(S_AIRTS, airts);
     }
 };
@@ -21,9 +23,9 @@ struct SoilTemps {  // deg F, what PWTGAS reads from ts
     double sltmp, ultmp, lgtmp;
 };
 
-template <bool HOURLY>
-__device__ __forceinline__ void pstemp_step(const Seg &s, PstempState &w, double airtmp, SoilTemps &o) {
-    const bool hrfg = HOURLY ? true : (s.cal.flags & HSP2G_CAL_HRFG);
+template <bool HOURLY, class SEG>
+__device__ __forceinline__ void pstemp_step(const SEG &s, PstempState &w, double airtmp, SoilTemps &o) {
+    const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
     const double airtcs = (w.airts - 32.0) * 0.555;
     const double airtc = (airtmp - 32.0) * 0.555;
     if (hrfg) {
@@ -63,12 +65,14 @@ __device__ __forceinline__ void pstemp_step(const Seg &s, PstempState &w, double
     o.sltmp = (w.sltmp * 9.0 / 5.0) + 32.0;
     o.ultmp = (w.ultmp * 9.0 / 5.0) + 32.0;
     o.lgtmp = (w.lgtmp * 9.0 / 5.0) + 32.0;
-    s.count(E_PSTEMP0, e0);
-    s.count(E_PSTEMP1, e1);
-    s.count(E_PSTEMP2, e2);
-    s.count(E_PSTEMP3, e3);
-    s.count(E_PSTEMP4, e4);
-    s.count(E_PSTEMP5, e5);
+    if (e0 | e1 | e2 | e3 | e4 | e5) {
+        s.count(E_PSTEMP0, e0);
+        s.count(E_PSTEMP1, e1);
+        s.count(E_PSTEMP2, e2);
+        s.count(E_PSTEMP3, e3);
+        s.count(E_PSTEMP4, e4);
+        s.count(E_PSTEMP5, e5);
+    }
     s.save(O_PSTEMP_AIRTC, (airtc * 9.0 / 5.0) + 32.0);
     s.save(O_PSTEMP_SLTMP, o.sltmp);
     s.save(O_PSTEMP_ULTMP, o.ultmp);

@@ -11,19 +11,23 @@ struct PwaterState {
     // interpolated-once-per-day parameters that every interval reads (refreshed at day starts)
     double cepsc, uzsn, lzetp;
 
-    __device__ __forceinline__ void load(const Seg &s) {
+    template <class SEG>
+
+    __device__ __forceinline__ void load(const SEG &s) {
         ceps = s.st(S_CEPS); surs = s.st(S_SURS); uzs = s.st(S_UZS); ifws = s.st(S_IFWS); lzs = s.st(S_LZS);
         agws = s.st(S_AGWS); gwvs = s.st(S_GWVS); msupy = s.st(S_MSUPY); dec = s.st(S_DEC); src = s.st(S_SRC);
         ifwk1 = s.st(S_IFWK1); ifwk2 = s.st(S_IFWK2); rlzrat = s.st(S_RLZRAT); lzfrac = s.st(S_LZFRAC);
         rparm = s.st(S_RPARM); petadj = s.st(S_PETADJ);
     }
-    __device__ __forceinline__ void store(const Seg &s) const {
+    template <class SEG>
+    __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_CEPS, ceps); s.st(S_SURS, surs); s.st(S_UZS, uzs); s.st(S_IFWS, ifws); s.st(S_LZS, lzs);
         s.st(S_AGWS, agws); s.st(S_GWVS, gwvs); s.st(S_MSUPY, msupy); s.st(S_DEC, dec); s.st(S_SRC, src);
         s.st(S_IFWK1, ifwk1); s.st(S_IFWK2, ifwk2); s.st(S_RLZRAT, rlzrat); s.st(S_LZFRAC, lzfrac);
         s.st(S_RPARM, rparm); s.st(S_PETADJ, petadj);
     }
-    __device__ __forceinline__ void refresh_daily(const Seg &s) {
+    template <class SEG>
+    __device__ __forceinline__ void refresh_daily(const SEG &s) {
         cepsc = s.daily(FB_M_CEPSC, M_CEPSC, P_CEPSC);
         uzsn = s.daily(FB_M_UZSN, M_UZSN, P_UZSN);
         lzetp = s.daily(FB_M_LZETP, M_LZETP, P_LZETP);
@@ -118,13 +122,13 @@ __device__ __forceinline__ int proute(double psur, bool rtop1, double delt60, do
     return nonconv;
 }
 
-template <bool HOURLY>
-__device__ __forceinline__ void pwater_step(const Seg &s, PwaterState &w, const SnowLink &sn, double prec,
+template <bool HOURLY, class SEG>
+__device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const SnowLink &sn, double prec,
                                             PwaterFlux &fx) {
     const LandLaunch &L = s.L;
     const double delt60 = L.delt60;
-    const bool dayfg = s.cal.flags & HSP2G_CAL_DAYFG;
-    const bool hrfg = HOURLY ? true : (s.cal.flags & HSP2G_CAL_HRFG);
+    const bool dayfg = s.calfl & HSP2G_CAL_DAYFG;
+    const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
     const bool csnofg = s.flag(FB_CSNOFG);
     const double oldmsupy = w.msupy;
     const double lzetp = w.lzetp, cepsc = w.cepsc, uzsn = w.uzsn;
@@ -429,12 +433,14 @@ __device__ __forceinline__ void pwater_step(const Seg &s, PwaterState &w, const 
     fx.ifwo = ifwo;
     fx.agwo = agwo;
 
-    s.count(E_PWATER1, e1);
-    s.count(E_PWATER2, e2);
-    s.count(E_PWATER3, e3);
-    s.count(E_PWATER6, e6);
-    s.count(E_PWATER7, e7);
-    s.count(E_PWATER8, e8);
+    if (e1 | e2 | e3 | e6 | e7 | e8) {  // rare: one test on the common path
+        s.count(E_PWATER1, e1);
+        s.count(E_PWATER2, e2);
+        s.count(E_PWATER3, e3);
+        s.count(E_PWATER6, e6);
+        s.count(E_PWATER7, e7);
+        s.count(E_PWATER8, e8);
+    }
 
     s.save(O_PWATER_AGWET, agwet);
     s.save(O_PWATER_AGWI, agwi);

@@ -14,7 +14,8 @@ __device__ __forceinline__ void mix_lateral(double &t, double &ox, double &co2, 
     if (lic >= 0.0) co2 = lic * fac + co2 * (1.0 - fac);
 }
 
-__device__ __forceinline__ void pwtgas_step(const Seg &s, const SoilTemps &soil, double wyield, double suro,
+template <class SEG>
+__device__ __forceinline__ void pwtgas_step(const SEG &s, const SoilTemps &soil, double wyield, double suro,
                                             double ifwo, double agwo) {
     const double EFACTA = 407960., MFACTA = 0.2266;
     const double elevgc = s.par(P_ELEVGC);

@@ -9,19 +9,22 @@
 struct SedmntState {
     double dets, cover, nvsi;
     int drydfg;
-    __device__ __forceinline__ void load(const Seg &s) {
+    template <class SEG>
+    __device__ __forceinline__ void load(const SEG &s) {
         dets = s.st(S_DETS); cover = s.st(S_SED_COVER); nvsi = s.st(S_SED_NVSI); drydfg = s.st(S_DRYDFG) != 0.0;
     }
-    __device__ __forceinline__ void store(const Seg &s) const {
+    template <class SEG>
+    __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_DETS, dets); s.st(S_SED_COVER, cover); s.st(S_SED_NVSI, nvsi); s.st(S_DRYDFG, drydfg ? 1.0 : 0.0);
     }
 };
 
 // rain: RAINF when SNOW (or the PWATER wrapper's NaN fill) put it in ts, else PREC (SEDMNT.py:86-89)
-__device__ __forceinline__ void sedmnt_step(const Seg &s, SedmntState &w, double rain, double prec, double snocov,
+template <class SEG>
+__device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double rain, double prec, double snocov,
                                             double suro, double surs) {
     const double delt = s.L.delt, delt60 = s.L.delt60;
-    const bool dayfg = s.cal.flags & HSP2G_CAL_DAYFG;
+    const bool dayfg = s.calfl & HSP2G_CAL_DAYFG;
     const double slsed = s.forcing(F_SLSED);
     if (dayfg) w.cover = s.daily(FB_M_COVER, M_COVER, P_COVER);
 

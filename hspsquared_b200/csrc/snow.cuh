@@ -12,7 +12,9 @@ struct SnowState {
     double oldprec, snotmp, dewtmp, mneghs, packwc, compct, gmeltr, mostht, neght, rdnsn, snowep, vap, albedo;
     int hr6fg;
 
-    __device__ __forceinline__ void load(const Seg &s) {
+    template <class SEG>
+
+    __device__ __forceinline__ void load(const SEG &s) {
         covinx = s.st(S_COVINX); dull = s.st(S_DULL); packf = s.st(S_PACKF); packi = s.st(S_PACKI);
         packw = s.st(S_PACKW); paktmp = s.st(S_PAKTMP); rdenpf = s.st(S_RDENPF); skyclr = s.st(S_SKYCLR);
         xlnmlt = s.st(S_XLNMLT); pdepth = s.st(S_PDEPTH); snocov = s.st(S_SNOCOV); neghts = s.st(S_NEGHTS);
@@ -21,7 +23,8 @@ struct SnowState {
         neght = s.st(S_NEGHT); rdnsn = s.st(S_RDNSN); snowep = s.st(S_SNOWEP); vap = s.st(S_VAP);
         albedo = s.st(S_ALBEDO); hr6fg = s.st(S_HR6FG) != 0.0;
     }
-    __device__ __forceinline__ void store(const Seg &s) const {
+    template <class SEG>
+    __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_COVINX, covinx); s.st(S_DULL, dull); s.st(S_PACKF, packf); s.st(S_PACKI, packi);
         s.st(S_PACKW, packw); s.st(S_PAKTMP, paktmp); s.st(S_RDENPF, rdenpf); s.st(S_SKYCLR, skyclr);
         s.st(S_XLNMLT, xlnmlt); s.st(S_PDEPTH, pdepth); s.st(S_SNOCOV, snocov); s.st(S_NEGHTS, neghts);
@@ -54,11 +57,11 @@ __device__ __forceinline__ double svp_at(double temp) {
     return a + (indx - (double)lower) * (b - a);
 }
 
-template <bool HOURLY>
-__device__ __forceinline__ void snow_step(const Seg &s, SnowState &w, SnowFlux &x, double airtmp, double prec) {
+template <bool HOURLY, class SEG>
+__device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &x, double airtmp, double prec) {
     const LandLaunch &L = s.L;
     const double delt = L.delt, delt60 = L.delt60;
-    const bool hrfg = HOURLY ? true : (s.cal.flags & HSP2G_CAL_HRFG);
+    const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
     const bool snop = s.flag(FB_SNOPFG);
     const double tsnow = s.par(P_TSNOW);
     const double reltmp = airtmp - 32.0;
@@ -167,7 +170,7 @@ __device__ __forceinline__ void snow_step(const Seg &s, SnowState &w, SnowFlux &
                 d = sqrt(w.dull / 24.0);
                 const double summer = py_max(0.45, 0.80 - 0.10 * d);
                 const double winter = py_max(0.60, 0.85 - 0.07 * d);
-                w.albedo = (s.cal.flags & HSP2G_CAL_SEASON) ? summer : winter;
+                w.albedo = (s.calfl & HSP2G_CAL_SEASON) ? summer : winter;
                 const double shade = s.par(P_SHADE);
                 const double kk = (1.0 - shade) * delt60;
                 const double long1 = (shade * 0.26 * reltmp) + kk * (0.20 * reltmp - 6.6);
@@ -257,7 +260,7 @@ __device__ __forceinline__ void snow_step(const Seg &s, SnowState &w, SnowFlux &
 
         // ---- ICING (SNOW.py:461-485)
         if (s.flag(FB_ICEFG)) {
-            if (!(s.cal.flags & HSP2G_CAL_HR6IND)) {
+            if (!(s.calfl & HSP2G_CAL_HR6IND)) {
                 if (w.hr6fg) {
                     if (w.snocov < 1.0) {
                         const double xlnem = -reltmp * 0.01;

@@ -35,14 +35,16 @@ def output_names(operation, act):
 
 class LandBatch:
     def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False):
-        """store: SegmentStore; forcing_names: ordered forcing ids the forcing arrays carry (row order);
-        save: ordered output ids '<SECTION>_<NAME>' to write (row order), or 'all'."""
+        """store: SegmentStore; forcing_names: ordered forcing ids the arrays given to run() carry (row order);
+        save: ordered output ids '<SECTION>_<NAME>' run() returns (row order), or 'all'.  The raw tile-major buffers of
+        run_host / run_device use `forcing_rows` / `save_rows` (the same names in ascending id order)."""
         lib = _lib.load()
         self.lib = lib
         self.store = store
         self.cal = calendar
         self.n = store.n
         self.device = device
+        self._keep = []
         self.h = _lib._h()
         op = _lib.PERLND if store.operation == "PERLND" else _lib.IMPLND
         _lib.check(lib.hsp2g_batch_create(device, op, self.n, store.act, float(calendar.delt), C.byref(self.h)))
@@ -78,17 +80,21 @@ class LandBatch:
         _lib.check(lib.hsp2g_set_calendar(self.h, len(fl), _ptr(fl, u8), _ptr(m0b, u8), _ptr(m1b, u8), _ptr(xm),
                                           _ptr(dxm), _ptr(lapse)))
         # forcing layout + fills
+        # The caller's row order is kept for run(); the DEVICE row order is ascending id, which is what the kernels
+        # specialised at compile time for a row set expect (include/hsp2g.h hsp2g_set_forcing_layout).
         F = _lib.index("forcings")
         self.forcing_names = tuple(forcing_names)
         for nme in self.forcing_names:
             if nme not in F:
                 raise KeyError("unknown forcing series %r" % nme)
+        self._fperm = sorted(range(len(self.forcing_names)), key=lambda i: F[self.forcing_names[i]])
+        self.forcing_rows = tuple(self.forcing_names[i] for i in self._fperm)
         fills, opts = forcing_fill(st.operation, st.act, self.forcing_names)
         fill = np.zeros(len(F))
         for nme, v in fills.items():
             if nme in F:
                 fill[F[nme]] = v
-        ids = np.array([F[nme] for nme in self.forcing_names], dtype=np.int32)
+        ids = np.array([F[nme] for nme in self.forcing_rows], dtype=np.int32)
         _lib.check(lib.hsp2g_set_forcing_layout(self.h, len(ids), _ptr(ids, C.POINTER(C.c_int32)), _ptr(fill), opts))
         self.nf = len(ids)
         # SAVE set
@@ -100,54 +106,65 @@ class LandBatch:
         for nme in self.save:
             if nme not in avail:
                 raise KeyError("output %r is not produced by the active sections" % nme)
-        sid = np.array([O[nme] for nme in self.save], dtype=np.int32)
+        sperm = sorted(range(len(self.save)), key=lambda i: O[self.save[i]])
+        self.save_rows = tuple(self.save[i] for i in sperm)
+        self._sinv = np.argsort(np.array(sperm, dtype=np.int64)) if sperm else np.zeros(0, dtype=np.int64)
+        sid = np.array([O[nme] for nme in self.save_rows], dtype=np.int32)
         _lib.check(lib.hsp2g_set_save(self.h, len(sid), _ptr(sid, C.POINTER(C.c_int32))))
         self.ns = len(sid)
         _lib.check(lib.hsp2g_set_timing(self.h, int(bool(timing))))
 
     # ------------------------------------------------------------------------------------------------
-    def run_host(self, t0, forcing, out=None):
-        """forcing: float64 [nsteps][nf][n] (host, C-contiguous).  Enqueues copy-in, kernel and copy-out; call
-        sync() before reading `out` ([nsteps][ns][n], allocated here when None)."""
-        forcing = np.ascontiguousarray(forcing, dtype=np.float64)
-        nsteps = forcing.shape[0]
-        if forcing.shape != (nsteps, self.nf, self.n):
-            raise ValueError("forcing must be [nsteps][%d][%d]" % (self.nf, self.n))
-        if out is None:
-            out = np.empty((nsteps, self.ns, self.n), dtype=np.float64)
-        elif out.shape != (nsteps, self.ns, self.n) or out.dtype != np.float64 or not out.flags.c_contiguous:
-            raise ValueError("out must be C-contiguous float64 [nsteps][%d][%d]" % (self.ns, self.n))
-        self._keep = (forcing, out)
-        _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), forcing.ctypes.data, self.n, out.ctypes.data,
-                                           self.n))
-        return out
+    @property
+    def ntiles(self):
+        return self.npad // _lib.TILE
 
-    def run_host_ptr(self, t0, nsteps, forcing_ptr, out_ptr, ld=None):
-        """Raw-pointer variant for pinned buffers owned by the caller (e.g. torch pinned tensors)."""
-        ld = self.n if ld is None else ld
-        _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), forcing_ptr, ld, out_ptr, ld))
+    def run_host(self, t0, forcing_tiled, out_tiled=None):
+        """forcing_tiled: float64 [ntiles][nsteps][nf][32] (host, C-contiguous, see tile_series) with rows in
+        `self.forcing_rows` order; saved rows come back in `self.save_rows` order.  Enqueues copy-in,
+        kernel and copy-out; call sync() before reading `out_tiled` ([ntiles][nsteps][ns][32], allocated when None)."""
+        f = forcing_tiled
+        if f.dtype != np.float64 or not f.flags.c_contiguous or f.ndim != 4 or f.shape[0] != self.ntiles or \
+                f.shape[2:] != (self.nf, _lib.TILE):
+            raise ValueError("forcing must be C-contiguous float64 [%d][nsteps][%d][%d]" % (self.ntiles, self.nf, _lib.TILE))
+        nsteps = f.shape[1]
+        shape_o = (self.ntiles, nsteps, self.ns, _lib.TILE)
+        if out_tiled is None:
+            out_tiled = np.empty(shape_o, dtype=np.float64)
+        elif out_tiled.shape != shape_o or out_tiled.dtype != np.float64 or not out_tiled.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float64 %r" % (shape_o,))
+        self._keep.append((f, out_tiled))
+        _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), f.ctypes.data, out_tiled.ctypes.data))
+        return out_tiled
+
+    def run_host_ptr(self, t0, nsteps, forcing_ptr, out_ptr):
+        """Raw-pointer variant for pinned tile-major buffers owned by the caller (e.g. torch pinned tensors)."""
+        _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), forcing_ptr, out_ptr))
 
     def run_device(self, t0, nsteps, d_forcing, d_out, stream=0):
-        """Device-resident pass: d_forcing [nsteps][nf][npad], d_out [nsteps][ns][npad] raw device pointers."""
+        """Device-resident pass: d_forcing [ntiles][nsteps][nf][32], d_out [ntiles][nsteps][ns][32] device pointers."""
         _lib.check(self.lib.hsp2g_run_device(self.h, int(t0), int(nsteps), d_forcing, d_out, stream or None))
 
     def sync(self):
         _lib.check(self.lib.hsp2g_sync(self.h))
+        self._keep = []
 
     def run(self, forcing, chunk=None):
-        """Whole series through host buffers in chunks of `chunk` intervals -> out [steps][ns][n]."""
-        forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+        """Whole series through host buffers in chunks of `chunk` intervals: forcing [steps][nf][n] -> out
+        [steps][ns][n] (plain layouts; re-tiled per chunk on the way in and out)."""
+        forcing = np.asarray(forcing, dtype=np.float64)
         steps = forcing.shape[0]
+        if forcing.shape != (steps, self.nf, self.n):
+            raise ValueError("forcing must be [steps][%d][%d]" % (self.nf, self.n))
         chunk = chunk or steps
         out = np.empty((steps, self.ns, self.n), dtype=np.float64)
-        keep = []
+        tiled = []
         for t0 in range(0, steps, chunk):
             t1 = min(steps, t0 + chunk)
-            f = forcing[t0:t1]
-            o = out[t0:t1]
-            keep.append((f, o))
-            _lib.check(self.lib.hsp2g_run_host(self.h, t0, t1 - t0, f.ctypes.data, self.n, o.ctypes.data, self.n))
+            tiled.append((t0, t1, self.run_host(t0, tile_series(forcing[t0:t1][:, self._fperm, :]))))
         self.sync()
+        for t0, t1, o in tiled:
+            out[t0:t1] = untile_series(o, self.n)[:, self._sinv, :]
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -197,6 +214,23 @@ class LandBatch:
 
     def __exit__(self, *a):
         self.close()
+
+
+def tile_series(x):
+    """[steps][rows][n] -> tile-major [ntiles][steps][rows][32] (include/hsp2g.h); lanes past n copy the last segment."""
+    x = np.asarray(x, dtype=np.float64)
+    steps, rows, n = x.shape
+    T = _lib.TILE
+    nt = (n + T - 1) // T
+    if nt * T != n:
+        x = np.concatenate([x, np.repeat(x[:, :, -1:], nt * T - n, axis=2)], axis=2)
+    return np.ascontiguousarray(x.reshape(steps, rows, nt, T).transpose(2, 0, 1, 3))
+
+
+def untile_series(y, n):
+    """tile-major [ntiles][steps][rows][32] -> [steps][rows][n]."""
+    nt, steps, rows, T = y.shape
+    return y.transpose(1, 2, 0, 3).reshape(steps, rows, nt * T)[:, :, :n]
 
 
 def pack_forcings(series, names, n):

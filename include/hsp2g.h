@@ -19,9 +19,14 @@
  *   - identifier spaces (parameter / monthly-table / flag-bit / state / forcing / output / error ids) are the
  *     positions in the comma separated lists returned by hsp2g_names(); hspsquared_b200/csrc/hsp2g_ids.h is the
  *     single definition;
- *   - 2-D host arrays are row-major [row][segment] with leading dimension `ld` >= n_seg (elements);
- *     device-resident arrays use ld = hsp2g_batch_npad() (segment count rounded up to 128);
- *   - time-major series are [interval][row][segment].
+ *   - per-segment tables (parameters, flags, monthly tables, states, error counters) are passed as row-major host
+ *     arrays [row][segment] with leading dimension `ld` >= n_seg (elements); the library re-tiles them;
+ *   - TIME SERIES (forcings in, SAVEd series out) use the device's own layout on both sides of the bus, so that a
+ *     chunk moves as one contiguous copy and a warp's interval is one contiguous span (a single 1-D TMA bulk copy):
+ *         [tile][interval][row][32]      tile = segment / 32, lane = segment % 32, ntiles = ceil(n_seg / 32)
+ *     i.e. time-major [interval][segment] blocked by 32-segment tiles.  hsp2g_pack_series / hsp2g_unpack_series
+ *     convert from / to plain [interval][row][segment]; lanes past n_seg in the last tile are padding (they carry
+ *     copies of the last segment on input and are ignored on output).
  * A handle is not thread-safe; use one handle per GPU per thread (the reference kernels hold the GIL anyway).
  */
 #ifndef HSP2G_H
@@ -33,7 +38,7 @@
 extern "C" {
 #endif
 
-#define HSP2G_ABI_VERSION 1
+#define HSP2G_ABI_VERSION 2
 
 #define HSP2G_PERLND 0 /* configuration.py:48-50 */
 #define HSP2G_IMPLND 1 /* configuration.py:51-52 */
@@ -81,21 +86,27 @@ int hsp2g_get_state(hsp2g_batch *b, double *state /*[n_states][ld]*/, int64_t ld
 int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const uint8_t *m0, const uint8_t *m1,
                        const double *xm, const double *dxm, const double *lapse);
 
-/* Which forcing ids the [interval][row][segment] forcing arrays carry (row order = ids order), and the value every
- * absent id reads (the reference wrappers' NaN / zero / -1e30 fills; get_timeseries utilities.py:274-290). */
+/* Which forcing ids the forcing series carry (row order = ids order), and the value every absent id reads (the
+ * reference wrappers' NaN / zero / -1e30 fills; get_timeseries utilities.py:274-290).  Rows in ascending id order
+ * let the library pick a kernel specialised at compile time for the row set (see hsp2g_kernel_name). */
 int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *forcing_ids,
                              const double *fill /*[n_forcings]*/, uint32_t opts);
-/* Which output ids are written (the SAVE table, utilities.py:292-333), row order = ids order. */
+/* Which output ids are written (the SAVE table, utilities.py:292-333), row order = ids order (ascending id order
+ * enables the specialised kernels). */
 int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *output_ids);
 
 /* Advance all segments over intervals [t0, t0+nsteps).  State is read at the start and written at the end, so
- * consecutive chunks are bit-identical to one pass.
- * _device: forcings and outputs already in HBM (ld = npad); `stream` is a cudaStream_t (NULL = the batch's own).
+ * consecutive chunks are bit-identical to one pass.  Series are tile-major [tile][nsteps][row][32] (see above):
+ * forcing = ntiles*nsteps*n_forcing_rows*32 doubles, out = ntiles*nsteps*n_saved_rows*32 doubles.
+ * _device: forcings and outputs already in HBM, 16-byte aligned; `stream` is a cudaStream_t (NULL = the batch's own).
  * _host:   host buffers; H2D, kernel and D2H are pipelined on three streams over two device slots; buffers must stay
  *          valid until hsp2g_sync.  Pinned host memory (hsp2g_host_alloc) is needed for real overlap. */
 int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forcing, double *d_out, void *stream);
-int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, int64_t ld_forcing,
-                   double *h_out, int64_t ld_out);
+int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, double *h_out);
+/* Host-side re-tiling between [interval][row][ld] and [tile][interval][row][32] (what get_timeseries /
+ * save_timeseries hand over per segment, utilities.py:274-333, for a whole batch). */
+int hsp2g_pack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, int64_t ld, double *dst_tiled);
+int hsp2g_unpack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src_tiled, double *dst, int64_t ld);
 int hsp2g_sync(hsp2g_batch *b);
 
 /* Error counters (the `errors` vectors returned beside ERRMSGS, main.py:255-257), int64 [n_errors][ld]. */

@@ -55,6 +55,14 @@ inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t s
                                      cudaStream_t) {
     return cudaMemcpy2D(d, dp, s, sp, w, h, k);
 }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    memcpy(d, s, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemset2D(void *p, size_t pitch, int v, size_t w, size_t h) {
+    for (size_t r = 0; r < h; ++r) memset((char *)p + r * pitch, v, w);
+    return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
