@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--segments", type=int, default=N_SEG_PER_GPU, help="segments per GPU")
     ap.add_argument("--chunk", type=int, default=512, help="intervals per step")
+    ap.add_argument("--sub", type=int, default=None, help="intervals per (tile, sub-chunk) task; default = library's")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -270,6 +271,8 @@ def main():
     store = ens.store(cal)
     save = default_save()
     batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank)
+    if args.sub is not None:
+        batch.set_schedule(args.sub)
     npad, nf, ns = batch.npad, batch.nf, batch.ns
     assert nf == 6 and ns == 24
 

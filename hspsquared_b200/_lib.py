@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsp2g.so")
+# HSP2G_LIB selects another build of the SAME library (kernel tuning experiments, hspsquared_b200/build.py)
+LIB_PATH = os.environ.get("HSP2G_LIB") or os.path.join(_HERE, "libhsp2g.so")
 
 PERLND, IMPLND = 0, 1
 ABI_VERSION = 2
@@ -47,6 +48,7 @@ _PROTOS = {
     "hsp2g_sync": (C.c_int, [_h]),
     "hsp2g_get_errors": (C.c_int, [_h, _i64p, C.c_int64]),
     "hsp2g_reset_errors": (C.c_int, [_h]),
+    "hsp2g_set_schedule": (C.c_int, [_h, C.c_int32]),
     "hsp2g_set_timing": (C.c_int, [_h, C.c_int]),
     "hsp2g_kernel_stats": (C.c_int, [_h, _i64p, _dp]),
     "hsp2g_kernel_name": (C.c_char_p, [_h]),

@@ -12,6 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libhsp2g.so")
+# tuning experiments only (profiles/): extra -D flags and an alternative output name, e.g.
+#   HSP2G_NVCC_EXTRA="-DHSP_MINB_HOT=3" HSP2G_LIB_OUT=/root/repo/gpurun_out/../exp/libhsp2g_m3.so python -m hspsquared_b200.build --force
+EXTRA = os.environ.get("HSP2G_NVCC_EXTRA", "").split()
+LIB_OUT = os.environ.get("HSP2G_LIB_OUT") or LIB
 UNITS = ("hsp2g_api.cu", "perlnd_kernel.cu", "implnd_kernel.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -37,14 +41,14 @@ def up_to_date():
 
 
 def build(force=False, verbose=False):
-    if not force and up_to_date():
+    if not force and LIB_OUT == LIB and up_to_date():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(unit):
-        obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, unit), "-o", obj]
+        obj = os.path.join(OBJ, unit.replace(".cu", ".o" if LIB_OUT == LIB else "." + os.path.basename(LIB_OUT) + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA + ["-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, r.stdout, r.stderr))
@@ -53,15 +57,15 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(len(UNITS)) as ex:
         results = list(ex.map(compile_one, UNITS))
     log = "\n".join(err for _o, err in results)
-    with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+    with open(os.path.join(OBJ, "ptxas.log" if LIB_OUT == LIB else os.path.basename(LIB_OUT) + ".ptxas.log"), "w") as f:
         f.write(log)
     if verbose:
         print(log)
     objs = [o for o, _e in results]
-    r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB_OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return LIB_OUT
 
 
 if __name__ == "__main__":

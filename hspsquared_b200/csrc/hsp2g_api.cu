@@ -57,6 +57,11 @@ struct hsp2g_batch {
     double *mon = nullptr;     // [tile][slot*12 + month][32]
     std::vector<double> h_mon; // host copy [slot][12][n_seg] (tables arrive one at a time)
     CalStep *cal = nullptr;
+    unsigned long long *d_counter = nullptr;  // task tickets (land_common.cuh Sched)
+    unsigned *d_progress = nullptr;           // [ntiles] sub-chunks completed
+    unsigned long long task_base = 0;
+    unsigned prog_base = 0;
+    int sub_steps = 64;
     int64_t ncal = 0;
     int nmon_slots = 0;
     short mslot[HSP2G_NMON];
@@ -207,9 +212,17 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
         e1 = get_event(b);
         CU(cudaEventRecord(e0, st));
     }
-    cudaError_t e = b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, st, &b->kname)
-                                          : hsp2g_launch_implnd(L, hourly, st, &b->kname);
+    L.task_counter = b->d_counter;
+    L.task_base = b->task_base;
+    L.progress = b->d_progress;
+    L.prog_base = b->prog_base;
+    int grid = 0;
+    cudaError_t e = b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
+                                          : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+    // every task draws one ticket and every block one more (the draw that tells it to stop)
+    b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid;
+    b->prog_base += (unsigned)L.nsub;
     if (b->timing) {
         CU(cudaEventRecord(e1, st));
         b->pending.emplace_back(e0, e1);
@@ -220,20 +233,42 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
 }  // namespace
 
 // Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
-// forcing rows are present) and ask for a carve-out that leaves the rest of the 256 KB to L1, where the parameter
-// rows of the resident tiles live.
-cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes) {
+// forcing rows are present); the resident-block count sizes the persistent grid.
+cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident) {
     static std::mutex mu;
     static std::map<const void *, size_t> done;
     std::lock_guard<std::mutex> lk(mu);
     auto it = done.find(kernel);
-    if (it != done.end() && it->second >= smem_bytes) return cudaSuccess;
-    if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return e;
+    if (it == done.end() || it->second < smem_bytes) {
+        if (smem_bytes > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return e;
+        }
+        done[kernel] = smem_bytes;
     }
-    done[kernel] = smem_bytes;
-    return cudaSuccess;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    *resident = per_sm * sms;
+    return *resident > 0 ? cudaSuccess : cudaErrorLaunchOutOfResources;
+}
+
+void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident, int *grid_out) {
+    if (L.ntiles <= resident || sub_pref <= 0 || sub_pref >= L.nsteps) {
+        L.sub = L.nsteps;  // every tile is resident at once (or sub-chunking is off): one task per tile
+        L.nsub = 1;
+    } else {
+        L.sub = sub_pref;
+        L.nsub = (L.nsteps + sub_pref - 1) / sub_pref;
+    }
+    const long long tasks = (long long)L.ntiles * L.nsub;
+#ifdef HSP2G_HOST_EMU
+    *grid_out = L.ntiles;  // the test double walks a tile's sub-chunks in one "thread" (land_common.cuh Sched)
+#else
+    *grid_out = (int)(tasks < resident ? tasks : resident);
+#endif
 }
 
 extern "C" {
@@ -309,6 +344,8 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
     }                                                                              \
     cudaMemset((ptr), 0, (bytes));
     ALLOC(b->segblk, np * SB_ROWS * sizeof(double));
+    ALLOC(b->d_counter, sizeof(unsigned long long));
+    ALLOC(b->d_progress, (size_t)b->ntiles * sizeof(unsigned));
 #undef ALLOC
     CU(cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
@@ -328,6 +365,8 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     cudaDeviceSynchronize();
     cudaFree(b->segblk);
     cudaFree(b->mon);
+    cudaFree(b->d_counter);
+    cudaFree(b->d_progress);
     cudaFree(b->cal);
     for (auto &s : b->slot) {
         cudaFree(s.forc);
@@ -425,7 +464,9 @@ int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const ui
     CU(cudaDeviceSynchronize());
     cudaFree(b->cal);
     b->cal = nullptr;
-    CU(cudaMalloc((void **)&b->cal, (size_t)n * sizeof(CalStep)));
+    // one zeroed record past the end: the kernels load the flags of interval t+1 while they work on t
+    CU(cudaMalloc((void **)&b->cal, (size_t)(n + 1) * sizeof(CalStep)));
+    CU(cudaMemset(b->cal, 0, (size_t)(n + 1) * sizeof(CalStep)));
     CU(cudaMemcpy(b->cal, h.data(), (size_t)n * sizeof(CalStep), cudaMemcpyHostToDevice));
     b->ncal = n;
     return 0;
@@ -565,6 +606,13 @@ int hsp2g_reset_errors(hsp2g_batch *b) {
     CU(cudaStreamSynchronize(b->comp));
     CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
                     (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
+    return 0;
+}
+
+int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps) {
+    if (!b) return fail("null batch");
+    if (sub_steps < 0) return fail("sub_steps must be >= 0 (0 = one task per tile)");
+    b->sub_steps = sub_steps;
     return 0;
 }
 

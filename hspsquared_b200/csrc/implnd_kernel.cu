@@ -3,22 +3,23 @@
 #include "land_kernels.cuh"
 #include "launch.h"
 
-template <int ACT_CT, bool HOURLY, class IO, int MINB>
-static cudaError_t launch_one(const LandLaunch &L, cudaStream_t st, const char **name, const char *nm) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf);
-    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MINB>;
-    cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem);
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, IMPLND_HOT);
+    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MAXREG>;
+    int cap = 0;
+    cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((L.ntiles + LAND_WARPS - 1) / LAND_WARPS);
-    HSP2G_LAUNCH(k, grid, LAND_BLOCK, smem, st, L);
+    hsp2g_plan_tasks(L, sub_pref, cap, grid_out);
+    HSP2G_LAUNCH(k, (unsigned)*grid_out, LAND_BLOCK, smem, st, L);
     if (name) *name = nm;
     return cudaGetLastError();
 }
 
-cudaError_t hsp2g_launch_implnd(const LandLaunch &L, bool hourly, cudaStream_t st, const char **name) {
+cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SI = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_IWATER);
     if (L.act == (unsigned)SI && hourly && io_matches<IO_SnowIwaterDefault>(L))
-        return launch_one<SI, true, IO_SnowIwaterDefault, 4>(L, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>");
-    return hourly ? launch_one<-1, true, DynIO, 3>(L, st, name, "implnd_kernel<generic,hourly,io=dynamic>")
-                  : launch_one<-1, false, DynIO, 3>(L, st, name, "implnd_kernel<generic,subhourly,io=dynamic>");
+        return launch_one<SI, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>", grid_out);
+    return hourly ? launch_one<-1, true, DynIO, 128>(L, sub_pref, st, name, "implnd_kernel<generic,hourly,io=dynamic>", grid_out)
+                  : launch_one<-1, false, DynIO, 128>(L, sub_pref, st, name, "implnd_kernel<generic,subhourly,io=dynamic>", grid_out);
 }

@@ -23,15 +23,32 @@
 #include "hsp2g_ids.h"
 
 #define LAND_TILE 32
-#define LAND_BLOCK 128
+#define LAND_BLOCK 32  // one warp = one tile per block: warps never synchronise, and residency tunes in steps of one warp
 #define LAND_WARPS (LAND_BLOCK / LAND_TILE)
-#define PIPE_STAGES 3
+#ifndef PIPE_STAGES
+#define PIPE_STAGES 3  // 2 is enough for latency, 3 measured 5 % faster (fewer barrier polls; profiles/r1d)
+#endif
 
 #define SB_FLAGS 0
 #define SB_PAR 1
 #define SB_STATE (SB_PAR + HSP2G_NPAR)
 #define SB_ERR (SB_STATE + HSP2G_NSTATE)
 #define SB_ROWS (SB_ERR + HSP2G_NERR)
+
+// Parameters read on (nearly) every interval are staged once per launch into this warp's shared memory: an L1
+// miss on a parameter row costs an L2 round trip in the middle of a serial fp64 dependency chain (profiles/r1b).
+#define PBIT(n) (1ull << P_##n)
+// Per warp: 3 stages x 6 forcing rows + 24 hot parameters + 22 cold states = 64 rows of 256 B = 16 KB (+1 KB
+// system reservation per block) -> 13 one-warp blocks per SM; residency beyond ~12 warps no longer pays
+// (profiles/r1d: 12, 14 and 16 warps within 2 %).
+#define HOT_SNOW                                                                                                   \
+    (PBIT(TSNOW) | PBIT(SNOWCF) | PBIT(RDCSN) | PBIT(COVIND) | PBIT(SNOEVP) | PBIT(CCFACT) | PBIT(MELEV) |          \
+     PBIT(SHADE) | PBIT(MWATER) | PBIT(MGMELT_IVL))
+#define HOT_PWATER                                                                                                 \
+    (PBIT(INFILT_IVL) | PBIT(KVARY) | PBIT(LZSN) | PBIT(FOREST) | PBIT(PETMAX) | PBIT(PETMIN) | PBIT(FZG) |         \
+     PBIT(FZGL) | PBIT(DEEPFR) | PBIT(KGW) | PBIT(BASETP) | PBIT(AGWETP) | PBIT(INFEXP) | PBIT(INFILD))
+#define HOT_IWATER (PBIT(PETMAX) | PBIT(PETMIN))
+static_assert(HSP2G_NPAR <= 64, "hot-parameter masks are 64 bits");
 
 struct __align__(32) CalStep {
     double xm;       // (day - first of month) in the calendar's time unit
@@ -50,6 +67,12 @@ struct LandLaunch {
     const CalStep *cal;  // already offset to the first interval of this chunk
     int ntiles;
     int nsteps;
+    int sub;          // intervals per task; a task = (tile, sub-chunk) (see Sched)
+    int nsub;         // sub-chunks per tile in this launch = ceil(nsteps / sub)
+    unsigned long long *task_counter;  // global ticket counter, monotonically increasing over the batch's life
+    unsigned long long task_base;      // its value when this launch starts
+    unsigned *progress;                // [ntiles] sub-chunks completed by each tile since the batch was created
+    unsigned prog_base;                // their common value when this launch starts
     int first_chunk;  // 1 when this chunk starts at interval 0 of the run
     int nf, ns;       // forcing rows / saved rows per interval
     int mon_rows;     // 12 * number of monthly slots (row count of one tile's table block)
@@ -61,6 +84,43 @@ struct LandLaunch {
     short srow[HSP2G_NOUT];     // output id -> row in out, or -1 (not saved)
     short mslot[HSP2G_NMON];    // monthly table id -> slot in mon, or -1
 };
+
+// A carried scalar that lives in this lane's column of the warp's shared-memory scratch instead of a register.
+// Used for state that changes slowly (once a day) or that an hourly run only needs again at the end of the chunk:
+// ~23 doubles = 46 registers per thread that would otherwise force either spills or fewer resident warps.
+// (p may also point at the value's own row of the segment block in global memory, for the rarely touched ones.)
+struct ColdD {
+    double *p;
+    __device__ __forceinline__ operator double() const { return *p; }
+    __device__ __forceinline__ ColdD &operator=(double v) {
+        *p = v;
+        return *this;
+    }
+    __device__ __forceinline__ ColdD &operator=(const ColdD &o) {
+        *p = *o.p;
+        return *this;
+    }
+    __device__ __forceinline__ ColdD &operator+=(double v) { return *this = *p + v; }
+    __device__ __forceinline__ ColdD &operator-=(double v) { return *this = *p - v; }
+    __device__ __forceinline__ ColdD &operator*=(double v) { return *this = *p * v; }
+};
+// Same idea for values only wet intervals touch, left in their state row in global memory.  L2-only accesses: a
+// tile's sub-chunks may run on different SMs within one launch, whose L1s are not coherent.
+#ifdef HSP2G_HOST_EMU
+typedef ColdD ColdG;
+#else
+struct ColdG {
+    double *p;
+    __device__ __forceinline__ operator double() const { return __ldcg(p); }
+    __device__ __forceinline__ ColdG &operator=(double v) {
+        __stcg(p, v);
+        return *this;
+    }
+};
+#endif
+#define NCOLD_SNOW 12
+#define NCOLD_PWATER 10
+#define NCOLD (NCOLD_SNOW + NCOLD_PWATER)
 
 // Python semantics: max(a,b) = b if b>a else a ; min(a,b) = b if b<a else a  
 __device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }
@@ -112,12 +172,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "HSP_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra HSP_DONE;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"  // %2: suspend-time hint, the warp sleeps
+        "@p bra HSP_DONE;\n"                                            // in hardware instead of polling
         "bra HSP_WAIT;\n"
         "HSP_DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 
@@ -125,43 +185,58 @@ struct Pipe {
     double *ring;       // this warp's ring (generic pointer into shared memory)
     unsigned ring_s;    // its shared-space address
     unsigned bar_s;     // shared-space address of this warp's first mbarrier
-    const double *src;  // forc + tile * nsteps * nf * 32
+    const double *src;  // forcings of the current tile: forc + tile * nsteps * nf * 32
     int stage_elems;    // nf * 32
-    int nsteps;
+    int t_end;          // end of the current task (no copies are issued past it)
     int st;             // stage of the current interval
     unsigned ph;        // its phase parity
     int lane;
 
-    __device__ __forceinline__ void init(double *smem, int wib, int lane_, const double *src_, int nf, int nsteps_) {
+    // smem layout: [warp][PIPE_STAGES*nf*32 ring doubles | nhot*32 hot parameters | NCOLD*32 cold state], then the mbarriers
+    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf, int nhot) {
         stage_elems = nf * LAND_TILE;
-        ring = smem + (size_t)wib * PIPE_STAGES * stage_elems;
+        const int warp_elems = PIPE_STAGES * stage_elems + (nhot + NCOLD) * LAND_TILE;
+        ring = smem + (size_t)wib * warp_elems;
         ring_s = smem_u32(ring);
-        bar_s = smem_u32(smem + (size_t)LAND_WARPS * PIPE_STAGES * stage_elems) + wib * PIPE_STAGES * 8;
-        src = src_;
-        nsteps = nf > 0 ? nsteps_ : 0;
+        bar_s = smem_u32(smem + (size_t)LAND_WARPS * warp_elems) + wib * PIPE_STAGES * 8;
         st = 0;
         ph = 0;
         lane = lane_;
+        t_end = 0;
+        src = nullptr;
         if (lane == 0) {
             for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(bar_s + s * 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            for (int s = 0; s < PIPE_STAGES; ++s) issue(s, s);
         }
         __syncwarp();
     }
     __device__ __forceinline__ void issue(int t, int s) {  // lane 0 only
-        if (t < nsteps) {
+        if (t < t_end) {
             const unsigned bytes = (unsigned)stage_elems * 8u;
             mbar_expect_tx(bar_s + s * 8, bytes);
             bulk_g2s(ring_s + (unsigned)s * bytes, src + (size_t)t * stage_elems, bytes, bar_s + s * 8);
         }
     }
-    // wait for interval t's forcings; returns this lane's column of the stage
-    __device__ __forceinline__ const double *acquire(int t) {
-        if (nsteps > 0) mbar_wait(bar_s + st * 8, ph);
+    // a new task: intervals [t0, t1) of the tile whose forcings start at src_.  Every stage is free here (the previous
+    // task consumed all it issued), so the first PIPE_STAGES intervals go out at once, starting at the current stage.
+    __device__ __forceinline__ void begin_task(const double *src_, int t0, int t1) {
+        src = src_;
+        t_end = stage_elems > 0 ? t1 : 0;
+        if (lane == 0) {
+            int s = st;
+            for (int k = 0; k < PIPE_STAGES; ++k) {
+                issue(t0 + k, s);
+                if (++s == PIPE_STAGES) s = 0;
+            }
+        }
+    }
+    // wait for the current interval's forcings; returns this lane's column of the stage
+    __device__ __forceinline__ const double *acquire() {
+        if (t_end > 0) mbar_wait(bar_s + st * 8, ph);
         return ring + st * stage_elems + lane;
     }
+    __device__ __forceinline__ double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
     __device__ __forceinline__ void release(int t) {
         __syncwarp();
@@ -172,64 +247,149 @@ struct Pipe {
         }
     }
 };
+
+// ---- task scheduler.  A launch covers nsteps intervals of every tile, cut into sub-chunks of L.sub intervals; a task
+// is one (tile, sub-chunk).  Resident warps take tickets from one global counter, handed out sub-chunk-major, so
+// the machine stays full until the last sub-chunk instead of idling through the tail of a second, partial wave of
+// whole-chunk blocks (100k segments = 3,125 tiles against ~1,900 resident warps).  Sub-chunk c of a tile needs the
+// state that c-1 left in the segment block: the warp that finished c-1 publishes it with a release store to
+// progress[tile], the warp that drew c acquires it.  Tickets are drawn in order and every drawn ticket is held by a
+// running warp, so the wait cannot deadlock.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+struct Sched {
+    const LandLaunch &L;
+    int lane, c;
+    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_) : L(l), lane(lane_), c(0) {}
+    __device__ __forceinline__ bool next(int &tile, int &t0, int &t1) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(L.task_counter, 1ull) - L.task_base;
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (unsigned long long)L.ntiles * (unsigned)L.nsub) return false;
+        c = (int)(k / (unsigned)L.ntiles);
+        tile = (int)(k - (unsigned long long)c * (unsigned)L.ntiles);
+        t0 = c * L.sub;
+        t1 = t0 + L.sub < L.nsteps ? t0 + L.sub : L.nsteps;
+        if (c > 0) {
+            if (lane == 0)
+                while ((int)(ld_acquire_u32(L.progress + tile) - (L.prog_base + (unsigned)c)) < 0) __nanosleep(256);
+            __syncwarp();
+        }
+        return true;
+    }
+    __device__ __forceinline__ void done(int tile) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(L.progress + tile, L.prog_base + (unsigned)c + 1u);
+    }
+};
 #define HSP_SYNCWARP() __syncwarp()
 
 #else
-// test double: same interface, synchronous copies (no TMA on the host); one "thread" at a time
+// test double: same interface, synchronous copies (no TMA on the host); one "thread" at a time, which walks the
+// sub-chunks of its own tile in order (no tickets)
 struct Pipe {
     double *ring;
     const double *src;
-    int stage_elems, nsteps, lane;
-    void init(double *smem, int, int lane_, const double *src_, int nf, int nsteps_) {
+    int stage_elems, lane, t_cur;
+    void init(double *smem, int, int lane_, int nf, int) {
         ring = smem;
-        src = src_;
         stage_elems = nf * LAND_TILE;
-        nsteps = nsteps_;
         lane = lane_;
     }
-    const double *acquire(int t) {
-        for (int i = lane; i < stage_elems; i += LAND_TILE) ring[i] = src[(size_t)t * stage_elems + i];
+    void begin_task(const double *src_, int t0, int) {
+        src = src_;
+        t_cur = t0;
+    }
+    const double *acquire() {
+        for (int i = lane; i < stage_elems; i += LAND_TILE) ring[i] = src[(size_t)t_cur * stage_elems + i];
         return ring + lane;
     }
-    void release(int) {}
+    void release(int t) { t_cur = t + 1; }
+    double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
+};
+struct Sched {
+    const LandLaunch &L;
+    int c;
+    Sched(const LandLaunch &l, int) : L(l), c(-1) {}
+    bool next(int &tile, int &t0, int &t1) {
+        if (++c >= L.nsub) return false;
+        tile = (int)blockIdx.x;
+        t0 = c * L.sub;
+        t1 = t0 + L.sub < L.nsteps ? t0 + L.sub : L.nsteps;
+        return true;
+    }
+    void done(int) {}
 };
 #define HSP_SYNCWARP()
 #endif
 
 // per-thread view of the batch
-template <class IO_>
+#ifdef HSP2G_HOST_EMU
+#define HSP_PIN(p)
+#else
+// stop ptxas from re-deriving a loop-invariant address from threadIdx/blockIdx at every use (it does, under
+// register pressure: ~8 % of all issued instructions in profiles/r1b)
+#define HSP_PIN(p) asm volatile("" : "+l"(p))
+#endif
+
+template <class IO_, unsigned long long HOT_>
 struct Seg {
     typedef IO_ IO;
+    static constexpr unsigned long long HOT = HOT_;
+    static constexpr int NHOT = ce_popc(HOT_);
     const LandLaunch &L;
     double *sb;            // this lane's column of the tile's segment block
+    const double *hot;     // this lane's column of the staged hot parameters (shared memory)
     const double *monp;    // this lane's column of the tile's monthly tables
     double *outp;          // this lane's column of out[tile][t]
     const double *stage;   // this lane's column of the current forcing stage (shared memory)
     const CalStep *calp;   // calendar record of the current interval (warp-uniform)
     unsigned long long fl;
-    unsigned calfl;
+    unsigned calfl;        // HSP2G_CAL_* of the current interval
+    unsigned calfl_next;   // ... of the next one, loaded an interval ahead (an L2 round trip off the critical path)
     int out_step;          // elements between consecutive intervals of out
 
-    __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane) : L(l) {
+    // view of `tile` for the task that starts at interval t0 of the launch
+    __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane, int t0, double *hot_area) : L(l) {
         sb = l.segblk + ((size_t)tile * SB_ROWS * LAND_TILE + lane);
+        HSP_PIN(sb);
         monp = l.mon + ((size_t)tile * l.mon_rows * LAND_TILE + lane);
         out_step = (IO::STATIC ? IO::NS : l.ns) * LAND_TILE;
-        outp = l.out + ((size_t)tile * l.nsteps * out_step + lane);
-        calp = l.cal;
+        outp = l.out + (((size_t)tile * l.nsteps + t0) * out_step + lane);
+        HSP_PIN(outp);
+        calp = l.cal + t0;
+        double *h = hot_area + lane;
+        int k = 0;
+#pragma unroll
+        for (int id = 0; id < HSP2G_NPAR; ++id)
+            if ((HOT >> id) & 1ull) h[(k++) * LAND_TILE] = __ldg(sb + (SB_PAR + id) * LAND_TILE);
+        hot = h;  // each lane reads back only what it wrote: no barrier needed
         fl = *reinterpret_cast<const unsigned long long *>(sb + SB_FLAGS * LAND_TILE);
         stage = nullptr;
         calfl = 0;
+        calfl_next = calp->flags;
     }
     __device__ __forceinline__ void begin_step(const double *stage_) {
         stage = stage_;
-        calfl = calp->flags;
+        calfl = calfl_next;
+        calfl_next = calp[1].flags;  // the calendar holds steps+1 records (hsp2g_set_calendar), so t+1 exists
     }
     __device__ __forceinline__ void end_step() {
         outp += out_step;
         ++calp;
     }
     __device__ __forceinline__ bool flag(int bit) const { return (fl >> bit) & 1ull; }
-    __device__ __forceinline__ double par(int id) const { return __ldg(sb + (SB_PAR + id) * LAND_TILE); }
+    __device__ __forceinline__ double par(int id) const {
+        if ((HOT >> id) & 1ull) return hot[hsp_popc(HOT & ((1ull << id) - 1ull)) * LAND_TILE];
+        return __ldg(sb + (SB_PAR + id) * LAND_TILE);
+    }
     __device__ __forceinline__ bool has_forcing(int id) const {
         if (IO::STATIC) return (IO::FMASK >> id) & 1ull;
         return L.frow[id] >= 0;
@@ -252,6 +412,28 @@ struct Seg {
         const double slope = (y1 - y0) / calp->dxm;
         return slope * xm + y0;
     }
+    // N daily values at once: every table load is issued before the first division, so a new day costs one L2
+    // round trip instead of N in series.  Same arithmetic as daily().
+    template <int N>
+    __device__ __forceinline__ void daily_batch(const int (&fb)[N], const int (&mid)[N], const int (&pid)[N],
+                                                double (&v)[N]) const {
+        double y0[N], y1[N];
+        const int m0 = calp->m0, m1 = calp->m1;
+        const double xm = calp->xm, dxm = calp->dxm;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (flag(fb[k])) {
+                const double *tab = monp + (size_t)L.mslot[mid[k]] * (12 * LAND_TILE);
+                y0[k] = __ldg(tab + m0 * LAND_TILE);
+                y1[k] = __ldg(tab + m1 * LAND_TILE);
+            } else {
+                y0[k] = par(pid[k]);
+                y1[k] = y0[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = (flag(fb[k]) && xm != 0.0) ? ((y1[k] - y0[k]) / dxm) * xm + y0[k] : y0[k];
+    }
     // initm(): the table where the segment's flag is on, else the constant parameter
     __device__ __forceinline__ double daily(int flagbit, int mid, int pid) const {
         return flag(flagbit) ? monthly(mid) : par(pid);
@@ -272,9 +454,10 @@ struct Seg {
             if (r >= 0) __stcs(outp + r * LAND_TILE, v);
         }
     }
-    __device__ __forceinline__ double st(int sid) const { return sb[(SB_STATE + sid) * LAND_TILE]; }
-    __device__ __forceinline__ void st(int sid, double v) const { sb[(SB_STATE + sid) * LAND_TILE] = v; }
+    // state rows are handed from SM to SM between the sub-chunks of a launch: L2-only accesses (L1s are not coherent)
+    __device__ __forceinline__ double st(int sid) const { return __ldcg(sb + (SB_STATE + sid) * LAND_TILE); }
+    __device__ __forceinline__ void st(int sid, double v) const { __stcg(sb + (SB_STATE + sid) * LAND_TILE, v); }
     __device__ __forceinline__ void count(int eid, int n) const {
-        if (n) reinterpret_cast<long long *>(sb)[(SB_ERR + eid) * LAND_TILE] += n;
+        if (n) atomicAdd(reinterpret_cast<unsigned long long *>(sb) + (SB_ERR + eid) * LAND_TILE, (unsigned long long)n);
     }
 };

@@ -11,7 +11,8 @@
 //   ACT_CT >= 0  fixes the activity mask at compile time (hot configurations); < 0 reads it from the launch record;
 //   HOURLY       the run step is >= 60 min, where HRFG is identically 1 (calendar.py hoursval), which lets the
 //                compiler drop most of SNOW's hour-gated carried scalars from the loop-carried register set;
-//   IO           StaticIO<...> (forcing rows and SAVE set fixed at compile time) or DynIO (launch-record tables).
+//   IO           StaticIO<...> (forcing rows and SAVE set fixed at compile time) or DynIO (launch-record tables);
+//   MAXREG       register cap per thread (__maxnreg__): resident warps per SM = 65536 / (32 * MAXREG rounded up to 8).
 #pragma once
 #include "iwater.cuh"
 #include "land_common.cuh"
@@ -21,12 +22,16 @@
 #include "sedmnt.cuh"
 #include "snow.cuh"
 
+#define PERLND_HOT (HOT_SNOW | HOT_PWATER)
+#define IMPLND_HOT (HOT_SNOW | HOT_IWATER)
 #define OPT_SED_RAIN_IS_PREC 1u  // SEDMNT: no RAINF in ts -> RAIN = PREC (SEDMNT.py:86-89)
 
 #ifdef HSP2G_HOST_EMU
 #define LAND_SMEM_DECL double *smem = ring
+#define HSP_MAXNREG(n)
 #else
 #define LAND_SMEM_DECL extern __shared__ __align__(128) double smem[]
+#define HSP_MAXNREG(n) __maxnreg__(n)
 #endif
 
 template <class SEG>
@@ -39,129 +44,143 @@ __device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
     return airtmp;
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MINB>
-__global__ void __launch_bounds__(LAND_BLOCK, MINB) perlnd_kernel(const __grid_constant__ LandLaunch L) {
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
-    const int tile = blockIdx.x * LAND_WARPS + wib;
-    if (tile >= L.ntiles) return;  // warp-uniform
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    Seg<IO> s(L, tile, lane);
+    typedef Seg<IO, PERLND_HOT> SegT;
     Pipe pipe;
-    pipe.init(smem, wib, lane, L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, nf, L.nsteps);
+    pipe.init(smem, wib, lane, nf, SegT::NHOT);
+    Sched sched(L, lane);
+    int tile, t0, t1;
+    while (sched.next(tile, t0, t1)) {  // one task = intervals [t0, t1) of one tile (land_common.cuh Sched)
+        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
+        SegT s(L, tile, lane, t0, pipe.hot_area());
 
-    SnowState sw;
-    PwaterState pw;
-    SedmntState sd;
-    PstempState ps;
-    if (act & HSP2G_ACT_SNOW) sw.load(s);
-    if (act & HSP2G_ACT_PWATER) pw.load(s);
-    if (act & HSP2G_ACT_SEDMNT) sd.load(s);
-    if (act & HSP2G_ACT_PSTEMP) ps.load(s);
+        SnowState sw;
+        PwaterState pw;
+        SedmntState sd;
+        PstempState ps;
+        double *cold = pipe.hot_area() + SegT::NHOT * LAND_TILE + lane;
+        sw.bind(cold);
+        pw.bind(cold + NCOLD_SNOW * LAND_TILE, s.sb);
+        if (act & HSP2G_ACT_SNOW) sw.load(s);
+        if (act & HSP2G_ACT_PWATER) pw.load(s);
+        if (act & HSP2G_ACT_SEDMNT) sd.load(s);
+        if (act & HSP2G_ACT_PSTEMP) ps.load(s);
 
-    for (int t = 0; t < L.nsteps; ++t) {
-        s.begin_step(pipe.acquire(t));
-        const double prec = s.forcing(F_PREC);
-        const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
+        for (int t = t0; t < t1; ++t) {
+            s.begin_step(pipe.acquire());
+            const double prec = s.forcing(F_PREC);
+            const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
 
-        SnowFlux sx;
-        SnowLink link;
-        if (act & HSP2G_ACT_SNOW) {
-            snow_step<HOURLY>(s, sw, sx, airtmp, prec);
-            link.rainf = sx.rainf;
-            link.snocov = sw.snocov;
-            link.wyield = sx.wyield;
-            link.packi = sw.packi;
-        } else {
-            link.rainf = s.forcing(F_RAINF);
-            link.snocov = s.forcing(F_SNOCOV);
-            link.wyield = s.forcing(F_WYIELD);
-            link.packi = s.forcing(F_PACKI);
-        }
-        link.airtmp = airtmp;
+            SnowFlux sx;
+            SnowLink link;
+            if (act & HSP2G_ACT_SNOW) {
+                snow_step<HOURLY>(s, sw, sx, airtmp, prec);
+                link.rainf = sx.rainf;
+                link.snocov = sw.snocov;
+                link.wyield = sx.wyield;
+                link.packi = sw.packi;
+            } else {
+                link.rainf = s.forcing(F_RAINF);
+                link.snocov = s.forcing(F_SNOCOV);
+                link.wyield = s.forcing(F_WYIELD);
+                link.packi = s.forcing(F_PACKI);
+            }
+            link.airtmp = airtmp;
 
-        PwaterFlux fx;
-        if (act & HSP2G_ACT_PWATER) {
-            if (t == 0 || (s.calfl & HSP2G_CAL_NEWDAY)) pw.refresh_daily(s);
-            pwater_step<HOURLY>(s, pw, link, prec, fx);
-        } else {
-            fx.suro = s.forcing(F_SURO);
-            fx.surs = s.forcing(F_SURS);
-            fx.ifwo = s.forcing(F_IFWO);
-            fx.agwo = s.forcing(F_AGWO);
+            PwaterFlux fx;
+            if (act & HSP2G_ACT_PWATER) {
+                if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) pw.refresh_daily(s);
+                pwater_step<HOURLY>(s, pw, link, prec, fx);
+            } else {
+                fx.suro = s.forcing(F_SURO);
+                fx.surs = s.forcing(F_SURS);
+                fx.ifwo = s.forcing(F_IFWO);
+                fx.agwo = s.forcing(F_AGWO);
+            }
+            if (act & HSP2G_ACT_SEDMNT) {
+                const double rain = (L.opts & OPT_SED_RAIN_IS_PREC) ? prec : link.rainf;
+                sedmnt_step(s, sd, rain, prec, link.snocov, fx.suro, fx.surs);
+            }
+            SoilTemps soil;
+            if (act & HSP2G_ACT_PSTEMP) {
+                if (L.first_chunk && t == 0) ps.airts = airtmp;  // PSTEMP.py:128
+                pstemp_step<HOURLY>(s, ps, airtmp, soil);
+            } else {
+                soil.sltmp = s.forcing(F_SLTMP);
+                soil.ultmp = s.forcing(F_ULTMP);
+                soil.lgtmp = s.forcing(F_LGTMP);
+            }
+            if (act & HSP2G_ACT_PWTGAS) pwtgas_step(s, soil, link.wyield, fx.suro, fx.ifwo, fx.agwo);
+            s.end_step();
+            pipe.release(t);
         }
-        if (act & HSP2G_ACT_SEDMNT) {
-            const double rain = (L.opts & OPT_SED_RAIN_IS_PREC) ? prec : link.rainf;
-            sedmnt_step(s, sd, rain, prec, link.snocov, fx.suro, fx.surs);
-        }
-        SoilTemps soil;
-        if (act & HSP2G_ACT_PSTEMP) {
-            if (L.first_chunk && t == 0) ps.airts = airtmp;  // PSTEMP.py:128
-            pstemp_step<HOURLY>(s, ps, airtmp, soil);
-        } else {
-            soil.sltmp = s.forcing(F_SLTMP);
-            soil.ultmp = s.forcing(F_ULTMP);
-            soil.lgtmp = s.forcing(F_LGTMP);
-        }
-        if (act & HSP2G_ACT_PWTGAS) pwtgas_step(s, soil, link.wyield, fx.suro, fx.ifwo, fx.agwo);
-        s.end_step();
-        pipe.release(t);
+        if (act & HSP2G_ACT_SNOW) sw.store(s);
+        if (act & HSP2G_ACT_PWATER) pw.store(s);
+        if (act & HSP2G_ACT_SEDMNT) sd.store(s);
+        if (act & HSP2G_ACT_PSTEMP) ps.store(s);
+        sched.done(tile);
     }
-    if (act & HSP2G_ACT_SNOW) sw.store(s);
-    if (act & HSP2G_ACT_PWATER) pw.store(s);
-    if (act & HSP2G_ACT_SEDMNT) sd.store(s);
-    if (act & HSP2G_ACT_PSTEMP) ps.store(s);
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MINB>
-__global__ void __launch_bounds__(LAND_BLOCK, MINB) implnd_kernel(const __grid_constant__ LandLaunch L) {
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
-    const int tile = blockIdx.x * LAND_WARPS + wib;
-    if (tile >= L.ntiles) return;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    Seg<IO> s(L, tile, lane);
+    typedef Seg<IO, IMPLND_HOT> SegT;
     Pipe pipe;
-    pipe.init(smem, wib, lane, L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, nf, L.nsteps);
+    pipe.init(smem, wib, lane, nf, SegT::NHOT);
+    Sched sched(L, lane);
+    int tile, t0, t1;
+    while (sched.next(tile, t0, t1)) {
+        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
+        SegT s(L, tile, lane, t0, pipe.hot_area());
 
-    SnowState sw;
-    IwaterState iw;
-    if (act & HSP2G_ACT_SNOW) sw.load(s);
-    if (act & HSP2G_ACT_IWATER) iw.load(s);
+        SnowState sw;
+        IwaterState iw;
+        sw.bind(pipe.hot_area() + SegT::NHOT * LAND_TILE + lane);
+        if (act & HSP2G_ACT_SNOW) sw.load(s);
+        if (act & HSP2G_ACT_IWATER) iw.load(s);
 
-    for (int t = 0; t < L.nsteps; ++t) {
-        s.begin_step(pipe.acquire(t));
-        const double prec = s.forcing(F_PREC);
-        const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
-        SnowFlux sx;
-        SnowLink link;
-        if (act & HSP2G_ACT_SNOW) {
-            snow_step<HOURLY>(s, sw, sx, airtmp, prec);
-            link.rainf = sx.rainf;
-            link.snocov = sw.snocov;
-            link.wyield = sx.wyield;
-            link.packi = sw.packi;
-        } else {
-            link.rainf = s.forcing(F_RAINF);
-            link.snocov = s.forcing(F_SNOCOV);
-            link.wyield = s.forcing(F_WYIELD);
-            link.packi = s.forcing(F_PACKI);
+        for (int t = t0; t < t1; ++t) {
+            s.begin_step(pipe.acquire());
+            const double prec = s.forcing(F_PREC);
+            const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
+            SnowFlux sx;
+            SnowLink link;
+            if (act & HSP2G_ACT_SNOW) {
+                snow_step<HOURLY>(s, sw, sx, airtmp, prec);
+                link.rainf = sx.rainf;
+                link.snocov = sw.snocov;
+                link.wyield = sx.wyield;
+                link.packi = sw.packi;
+            } else {
+                link.rainf = s.forcing(F_RAINF);
+                link.snocov = s.forcing(F_SNOCOV);
+                link.wyield = s.forcing(F_WYIELD);
+                link.packi = s.forcing(F_PACKI);
+            }
+            link.airtmp = airtmp;
+            if (act & HSP2G_ACT_IWATER) {
+                if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) iw.refresh_daily(s);
+                iwater_step<HOURLY>(s, iw, link, prec);
+            }
+            s.end_step();
+            pipe.release(t);
         }
-        link.airtmp = airtmp;
-        if (act & HSP2G_ACT_IWATER) {
-            if (t == 0 || (s.calfl & HSP2G_CAL_NEWDAY)) iw.refresh_daily(s);
-            iwater_step<HOURLY>(s, iw, link, prec);
-        }
-        s.end_step();
-        pipe.release(t);
+        if (act & HSP2G_ACT_SNOW) sw.store(s);
+        if (act & HSP2G_ACT_IWATER) iw.store(s);
+        sched.done(tile);
     }
-    if (act & HSP2G_ACT_SNOW) sw.store(s);
-    if (act & HSP2G_ACT_IWATER) iw.store(s);
 }
 
-// dynamic shared memory of one block: PIPE_STAGES interval stages per warp + one mbarrier per stage
-static inline size_t land_smem_bytes(int nf) {
-    return (size_t)LAND_WARPS * PIPE_STAGES * ((size_t)nf * LAND_TILE * sizeof(double) + 8);
+// dynamic shared memory of one block: per warp PIPE_STAGES interval stages + the hot parameters + one mbarrier per stage
+static inline size_t land_smem_bytes(int nf, unsigned long long hot) {
+    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + NCOLD) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
 }

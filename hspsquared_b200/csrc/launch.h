@@ -4,7 +4,10 @@
 #include <stddef.h>
 
 struct LandLaunch;
-cudaError_t hsp2g_launch_perlnd(const LandLaunch &L, bool hourly, cudaStream_t st, const char **name);
-cudaError_t hsp2g_launch_implnd(const LandLaunch &L, bool hourly, cudaStream_t st, const char **name);
-// opt in to the dynamic shared memory a kernel needs and size the L1/shared carve-out for it (hsp2g_api.cu)
-cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes);
+// Fill in the task plan of L (sub, nsub), launch, and report the grid size used (tickets drawn = tasks + grid).
+cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out);
+cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out);
+// opt in to the dynamic shared memory a kernel needs; *resident = blocks of `block` threads the device holds at once
+cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident);
+// tasks = (tile, sub-chunk of sub_pref intervals) when the tiles outnumber the resident warps, else one task per tile
+void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident, int *grid_out);

@@ -3,31 +3,36 @@
 #include "land_kernels.cuh"
 #include "launch.h"
 
-template <int ACT_CT, bool HOURLY, class IO, int MINB>
-static cudaError_t launch_one(const LandLaunch &L, cudaStream_t st, const char **name, const char *nm) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf);
-    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MINB>;
-    cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem);
+#ifndef HSP_MAXREG_HOT
+#define HSP_MAXREG_HOT 144  // register cap of the specialised kernels (they need 128, no spills): 14 resident warps per SM
+#endif
+
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, PERLND_HOT);
+    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG>;
+    int cap = 0;
+    cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((L.ntiles + LAND_WARPS - 1) / LAND_WARPS);
-    HSP2G_LAUNCH(k, grid, LAND_BLOCK, smem, st, L);
+    hsp2g_plan_tasks(L, sub_pref, cap, grid_out);
+    HSP2G_LAUNCH(k, (unsigned)*grid_out, LAND_BLOCK, smem, st, L);
     if (name) *name = nm;
     return cudaGetLastError();
 }
 
-cudaError_t hsp2g_launch_perlnd(const LandLaunch &L, bool hourly, cudaStream_t st, const char **name) {
+cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SP = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_PWATER);
     if (L.act == (unsigned)SP && hourly) {
         if (io_matches<IO_SnowPwaterDefault>(L))
-            return launch_one<SP, true, IO_SnowPwaterDefault, 4>(L, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24>");
+            return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24>", grid_out);
         if (io_matches<IO_SnowPwaterFlows>(L))
-            return launch_one<SP, true, IO_SnowPwaterFlows, 4>(L, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=flows3>");
+            return launch_one<SP, true, IO_SnowPwaterFlows, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=flows3>", grid_out);
         if (io_matches<IO_SnowPwaterAll>(L))
-            return launch_one<SP, true, IO_SnowPwaterAll, 4>(L, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=all53>");
+            return launch_one<SP, true, IO_SnowPwaterAll, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=all53>", grid_out);
     }
     if (L.act == (unsigned)SP)
-        return hourly ? launch_one<SP, true, DynIO, 3>(L, st, name, "perlnd_kernel<SNOW|PWATER,hourly,io=dynamic>")
-                      : launch_one<SP, false, DynIO, 3>(L, st, name, "perlnd_kernel<SNOW|PWATER,subhourly,io=dynamic>");
-    return hourly ? launch_one<-1, true, DynIO, 2>(L, st, name, "perlnd_kernel<generic,hourly,io=dynamic>")
-                  : launch_one<-1, false, DynIO, 2>(L, st, name, "perlnd_kernel<generic,subhourly,io=dynamic>");
+        return hourly ? launch_one<SP, true, DynIO, 128>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,io=dynamic>", grid_out)
+                      : launch_one<SP, false, DynIO, 128>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,subhourly,io=dynamic>", grid_out);
+    return hourly ? launch_one<-1, true, DynIO, 232>(L, sub_pref, st, name, "perlnd_kernel<generic,hourly,io=dynamic>", grid_out)
+                  : launch_one<-1, false, DynIO, 232>(L, sub_pref, st, name, "perlnd_kernel<generic,subhourly,io=dynamic>", grid_out);
 }

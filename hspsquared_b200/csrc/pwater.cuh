@@ -7,30 +7,47 @@
 #include "land_common.cuh"
 
 struct PwaterState {
-    double ceps, surs, uzs, ifws, lzs, agws, gwvs, msupy, dec, src, ifwk1, ifwk2, rlzrat, lzfrac, rparm, petadj;
+    double ceps, surs, uzs, ifws, lzs, agws, gwvs, msupy;
+    // change once a day / on the first wet interval / when LZS moves by 2 %: not in registers (land_common.cuh ColdD)
+    ColdG dec, src;
+    ColdD ifwk1, ifwk2, rlzrat, lzfrac, rparm, petadj;
     // interpolated-once-per-day parameters that every interval reads (refreshed at day starts)
-    double cepsc, uzsn, lzetp;
+    ColdD cepsc, uzsn, lzetp, intfw;
+
+    // c: this lane's shared-memory scratch column; sb: this lane's column of the segment block.  The
+    // two values that only wet intervals touch stay in their state rows in global memory (L2), the rest is shared.
+    __device__ __forceinline__ void bind(double *c, double *sb) {
+        ColdD *m[NCOLD_PWATER] = {&ifwk1, &ifwk2, &rlzrat, &lzfrac, &rparm, &petadj, &cepsc, &uzsn, &lzetp, &intfw};
+        for (int k = 0; k < NCOLD_PWATER; ++k) m[k]->p = c + k * LAND_TILE;
+        dec.p = sb + (SB_STATE + S_DEC) * LAND_TILE;
+        src.p = sb + (SB_STATE + S_SRC) * LAND_TILE;
+    }
 
     template <class SEG>
-
     __device__ __forceinline__ void load(const SEG &s) {
         ceps = s.st(S_CEPS); surs = s.st(S_SURS); uzs = s.st(S_UZS); ifws = s.st(S_IFWS); lzs = s.st(S_LZS);
-        agws = s.st(S_AGWS); gwvs = s.st(S_GWVS); msupy = s.st(S_MSUPY); dec = s.st(S_DEC); src = s.st(S_SRC);
+        agws = s.st(S_AGWS); gwvs = s.st(S_GWVS); msupy = s.st(S_MSUPY);
         ifwk1 = s.st(S_IFWK1); ifwk2 = s.st(S_IFWK2); rlzrat = s.st(S_RLZRAT); lzfrac = s.st(S_LZFRAC);
         rparm = s.st(S_RPARM); petadj = s.st(S_PETADJ);
     }
     template <class SEG>
     __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_CEPS, ceps); s.st(S_SURS, surs); s.st(S_UZS, uzs); s.st(S_IFWS, ifws); s.st(S_LZS, lzs);
-        s.st(S_AGWS, agws); s.st(S_GWVS, gwvs); s.st(S_MSUPY, msupy); s.st(S_DEC, dec); s.st(S_SRC, src);
+        s.st(S_AGWS, agws); s.st(S_GWVS, gwvs); s.st(S_MSUPY, msupy);  // dec, src live in their state rows
         s.st(S_IFWK1, ifwk1); s.st(S_IFWK2, ifwk2); s.st(S_RLZRAT, rlzrat); s.st(S_LZFRAC, lzfrac);
         s.st(S_RPARM, rparm); s.st(S_PETADJ, petadj);
     }
     template <class SEG>
     __device__ __forceinline__ void refresh_daily(const SEG &s) {
-        cepsc = s.daily(FB_M_CEPSC, M_CEPSC, P_CEPSC);
-        uzsn = s.daily(FB_M_UZSN, M_UZSN, P_UZSN);
-        lzetp = s.daily(FB_M_LZETP, M_LZETP, P_LZETP);
+        const int fb[4] = {FB_M_CEPSC, FB_M_UZSN, FB_M_LZETP, FB_M_INTFW};
+        const int mid[4] = {M_CEPSC, M_UZSN, M_LZETP, M_INTFW};
+        const int pid[4] = {P_CEPSC, P_UZSN, P_LZETP, P_INTFW};
+        double v[4];
+        s.daily_batch(fb, mid, pid, v);
+        cepsc = v[0];
+        uzsn = v[1];
+        lzetp = v[2];
+        intfw = v[3];  // read on wet intervals only (PWATER.py:442), constant within a day like the others
     }
 };
 
@@ -192,7 +209,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
             w.dec = 0.00982 * pow(dummy / sqrt(slsur), 0.6);
             w.src = 1020.0 * (sqrt(slsur) / dummy);
         }
-        const double ratio = py_max(1.0001, s.daily(FB_M_INTFW, M_INTFW, P_INTFW) * exp2(lzrat));
+        const double ratio = py_max(1.0001, w.intfw * exp2(lzrat));
         double under, over;
         if (msupy <= imin) {
             under = msupy;

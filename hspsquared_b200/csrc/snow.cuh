@@ -8,9 +8,17 @@
 #include "land_common.cuh"
 
 struct SnowState {
-    double covinx, dull, packf, packi, packw, paktmp, rdenpf, skyclr, xlnmlt, pdepth, snocov, neghts;
-    double oldprec, snotmp, dewtmp, mneghs, packwc, compct, gmeltr, mostht, neght, rdnsn, snowep, vap, albedo;
+    double covinx, dull, packf, packi, packw, paktmp, rdenpf, skyclr, xlnmlt, pdepth, snocov, neghts, oldprec;
+    // recomputed on every hourly (HRFG) interval a pack exists: carried only between HRFG intervals of a sub-hourly
+    // run and into the next chunk, so they live in shared memory (land_common.cuh ColdD)
+    ColdD snotmp, dewtmp, mneghs, packwc, compct, gmeltr, mostht, neght, rdnsn, snowep, vap, albedo;
     int hr6fg;
+
+    __device__ __forceinline__ void bind(double *c) {
+        ColdD *m[NCOLD_SNOW] = {&snotmp, &dewtmp, &mneghs, &packwc, &compct, &gmeltr,
+                                &mostht, &neght,  &rdnsn,  &snowep, &vap,    &albedo};
+        for (int k = 0; k < NCOLD_SNOW; ++k) m[k]->p = c + k * LAND_TILE;
+    }
 
     template <class SEG>
 

@@ -189,6 +189,10 @@ class LandBatch:
         state = np.ascontiguousarray(state, dtype=np.float64)
         _lib.check(self.lib.hsp2g_set_state(self.h, _ptr(state), self.n))
 
+    def set_schedule(self, sub_steps):
+        """Intervals per (tile, sub-chunk) task of one launch (include/hsp2g.h hsp2g_set_schedule); 0 = whole chunk."""
+        _lib.check(self.lib.hsp2g_set_schedule(self.h, int(sub_steps)))
+
     def kernel_stats(self):
         n = C.c_int64(0)
         ms = C.c_double(0.0)

@@ -113,6 +113,12 @@ int hsp2g_sync(hsp2g_batch *b);
 int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld);
 int hsp2g_reset_errors(hsp2g_batch *b);
 
+/* Scheduling of one launch.  When a batch has more 32-segment tiles than the GPU holds warps, a launch is cut into
+ * tasks of `sub_steps` intervals of one tile, drawn in order by the resident warps, so the device stays full to the
+ * end of the chunk; a tile's state passes from task to task through the segment store, results are bit-identical.
+ * Default 64; 0 = one task per tile (whole chunk). */
+int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps);
+
 /* Instrumentation: kernels launched so far and, when timing is on, the summed CUDA-event duration of those kernels
  * (events on the launching stream). */
 int hsp2g_set_timing(hsp2g_batch *b, int on);

@@ -73,12 +73,25 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+enum { cudaErrorLaunchOutOfResources = 7 };
+template <class K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
 template <class K>
 inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 inline void __stcs(double *p, double v) { *p = v; }
+inline void __stcg(double *p, double v) { *p = v; }
+template <class T>
+inline T __ldcg(const T *p) { return *p; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    unsigned long long o = *p;
+    *p = o + v;
+    return o;
+}
 inline double __longlong_as_double(long long v) {
     double d;
     memcpy(&d, &v, sizeof d);

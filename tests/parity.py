@@ -25,16 +25,20 @@ def run_oracle(case, time_unit="us"):
     return ts, errs
 
 
-def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0):
+def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps=None, save="all", max_steps=None):
     """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block)."""
     si = CASES.siminfo_for(case)
     cal = Calendar(si["start"], si["stop"], si["delt"], time_unit)
     forc = CASES.forcings(case)
+    if max_steps is not None:
+        forc = {k: v[:max_steps] for k, v in forc.items()}
     F = _lib.index("forcings")
     names = [n for n in forc if n in F]
     tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
     store = SegmentStore.from_tables(case["operation"], tables, cal)
-    with LandBatch(store, cal, names, "all", device=device) as b:
+    with LandBatch(store, cal, names, save, device=device) as b:
+        if sub_steps is not None:
+            b.set_schedule(sub_steps)
         out = b.run(pack_forcings(forc, names, replicate), chunk=chunk)
         e = b.errors()
         kname = b.kernel_name()

@@ -39,6 +39,23 @@ def test_chunked_equals_single_pass(name):
         assert np.array_equal(ea[k], eb[k])
 
 
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10"])
+def test_subchunk_tasks_equal_whole_chunk(name):
+    """More tiles than resident warps (the test double holds one): a launch is cut into (tile, sub-chunk) tasks and a
+    tile's state passes from task to task through the segment store -- bit-identical to one task per tile, including
+    a ragged last sub-chunk and a padded last tile (70 segments = 3 tiles)."""
+    case = ALL[name]
+    a, ea, _ = parity.run_fused(case, replicate=70, chunk=500, sub_steps=0)
+    b, eb, _ = parity.run_fused(case, replicate=70, chunk=500, sub_steps=37)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+        assert np.array_equal(a[k], np.repeat(a[k][:, :1], 70, axis=1), equal_nan=True), k
+    for k in ea:
+        assert np.array_equal(ea[k], eb[k])
+    ref, ref_err = parity.run_oracle(case)
+    assert not parity.compare(ref, b, exact=True, seg=69)
+
+
 @pytest.mark.parametrize("name", sorted(ALL))
 def test_dropin_bit_exact(name):
     case = ALL[name]

@@ -83,6 +83,25 @@ def test_many_segments_padding_and_blocks():
         assert np.array_equal(g, np.repeat(g[:, :1], 333, axis=1), equal_nan=True), k
 
 
+@pytest.mark.parametrize("name,save", [("p001_snow_pwater", ["SNOW_PACKF", "PWATER_SURO", "PWATER_AGWS", "PWATER_UZS"]),
+                                       ("i001_test10", ["SNOW_PACKF", "IWATER_SURO", "IWATER_RETS"])])
+def test_subchunk_tasks_bitwise(name, save):
+    """More tiles (80,000 segments = 2,500) than resident warps: the ticket scheduler hands (tile, sub-chunk) tasks
+    to whichever warp is free, state passes through the segment store.  Must be bit-identical to whole-chunk tasks
+    and to a 3-segment batch, whatever SM ran which sub-chunk."""
+    case = ALL[name]
+    n, T = 80000, 300
+    a, ea, _ = parity.run_fused(case, replicate=n, chunk=130, sub_steps=0, save=save, max_steps=T)
+    b, eb, _ = parity.run_fused(case, replicate=n, chunk=130, sub_steps=32, save=save, max_steps=T)
+    small, es, _ = parity.run_fused(case, replicate=3, save=save, max_steps=T)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+        assert np.array_equal(b[k], np.repeat(small[k][:, :1], n, axis=1), equal_nan=True), k
+    for k in ea:
+        assert np.array_equal(ea[k], eb[k])
+        assert np.array_equal(eb[k][:, :3], es[k])
+
+
 def test_hspf_known_answers(golden_dir):
     """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
     hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))
