@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("HSP2G_LIB") or os.path.join(_HERE, "libhsp2g.so")
 
 PERLND, IMPLND = 0, 1
 ABI_VERSION = 2
+F64, F32 = 0, 1
 TILE = 32  # segments per tile of the series layout [tile][interval][row][32] (include/hsp2g.h)
 ACT_BITS = {"ATEMP": 1, "SNOW": 2, "PWATER": 4, "SEDMNT": 8, "PSTEMP": 16, "PWTGAS": 32, "IWATER": 64}
 OPT_SED_RAIN_IS_PREC = 1
@@ -48,6 +49,7 @@ _PROTOS = {
     "hsp2g_sync": (C.c_int, [_h]),
     "hsp2g_get_errors": (C.c_int, [_h, _i64p, C.c_int64]),
     "hsp2g_reset_errors": (C.c_int, [_h]),
+    "hsp2g_set_output_dtype": (C.c_int, [_h, C.c_int]),
     "hsp2g_set_schedule": (C.c_int, [_h, C.c_int32]),
     "hsp2g_set_timing": (C.c_int, [_h, C.c_int]),
     "hsp2g_kernel_stats": (C.c_int, [_h, _i64p, _dp]),

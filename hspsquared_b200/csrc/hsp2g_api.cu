@@ -62,6 +62,7 @@ struct hsp2g_batch {
     unsigned long long task_base = 0;
     unsigned prog_base = 0;
     int sub_steps = 64;
+    int out_f32 = 0;
     int64_t ncal = 0;
     int nmon_slots = 0;
     short mslot[HSP2G_NMON];
@@ -197,6 +198,7 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.first_chunk = t0 == 0;
     L.nf = b->nf;
     L.ns = b->ns;
+    L.out_f32 = b->out_f32;
     L.act = b->act;
     L.opts = b->opts;
     L.delt = b->delt;
@@ -522,7 +524,7 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
     b->next_slot ^= 1;
     const size_t row = (size_t)b->n_pad * sizeof(double);
     const size_t need_f = row * (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0);
-    const size_t need_o = row * (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0);
+    const size_t need_o = row * (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0) / (b->out_f32 ? 2 : 1);
     if (need_f > s.cap_f || need_o > s.cap_o) {
         CU(cudaEventSynchronize(s.d2h_done));
         if (need_f > s.cap_f) {
@@ -606,6 +608,13 @@ int hsp2g_reset_errors(hsp2g_batch *b) {
     CU(cudaStreamSynchronize(b->comp));
     CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
                     (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
+    return 0;
+}
+
+int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype) {
+    if (!b) return fail("null batch");
+    if (dtype != HSP2G_F64 && dtype != HSP2G_F32) return fail("output dtype must be HSP2G_F64 or HSP2G_F32");
+    b->out_f32 = dtype == HSP2G_F32;
     return 0;
 }
 

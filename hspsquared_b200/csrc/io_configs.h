@@ -41,6 +41,8 @@ constexpr unsigned long long range_hi(int a, int b) {
 
 typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_PWATER_DEFAULT(olo), SAVE_SNOW_DEFAULT(ohi) | SAVE_PWATER_DEFAULT(ohi)>
     IO_SnowPwaterDefault;
+typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_PWATER_DEFAULT(olo), SAVE_SNOW_DEFAULT(ohi) | SAVE_PWATER_DEFAULT(ohi), true>
+    IO_SnowPwaterDefaultF32;
 typedef StaticIO<FM_MET6, range_lo(O_SNOW_ALBEDO, O_PWATER_INFFAC + 1), range_hi(O_SNOW_ALBEDO, O_PWATER_INFFAC + 1)>
     IO_SnowPwaterAll;
 typedef StaticIO<FM_MET6, SAVE_PWATER_FLOWS(olo), SAVE_PWATER_FLOWS(ohi)> IO_SnowPwaterFlows;
@@ -50,7 +52,7 @@ typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_IWATER_DEFAULT(olo), SAV
 // does the launch record describe exactly this static configuration (rows in ascending id order)?
 template <class IO>
 static inline bool io_matches(const LandLaunch &L) {
-    if (L.nf != IO::NF || L.ns != IO::NS) return false;
+    if (L.nf != IO::NF || L.ns != IO::NS || (L.out_f32 != 0) != IO::F32) return false;
     int r = 0;
     for (int id = 0; id < HSP2G_NFORC; ++id) {
         const bool on = (IO::FMASK >> id) & 1ull;

@@ -75,6 +75,7 @@ struct LandLaunch {
     unsigned prog_base;                // their common value when this launch starts
     int first_chunk;  // 1 when this chunk starts at interval 0 of the run
     int nf, ns;       // forcing rows / saved rows per interval
+    int out_f32;      // saved series are float32 [tile][t][row][32] instead of float64
     int mon_rows;     // 12 * number of monthly slots (row count of one tile's table block)
     unsigned act;
     unsigned opts;
@@ -136,15 +137,17 @@ __device__ __forceinline__ int hsp_popc(unsigned long long x) { return __popcll(
 // DynIO reads the row tables of the launch record at run time (any layout).  StaticIO<forcing mask, save mask>
 // fixes both sets at compile time with rows in ascending id order: absent outputs cost nothing (their stores and
 // the arithmetic that only feeds them disappear) and every present row is an immediate offset.
+// F32: saved series are stored as float32 (round to nearest even), which is what the reference hands its IOManager
+// (save_timeseries casts the frame with astype(np.float32), utilities.py:313): half the bytes to HBM and over PCIe.
 struct DynIO {
-    static constexpr bool STATIC = false;
+    static constexpr bool STATIC = false, F32 = false;  // DynIO reads L.out_f32 at run time
     static constexpr unsigned long long FMASK = 0, S0 = 0, S1 = 0;
     static constexpr int NF = 0, NS = 0;
 };
 constexpr int ce_popc(unsigned long long x) { return x ? (int)(x & 1ull) + ce_popc(x >> 1) : 0; }
-template <unsigned long long FM, unsigned long long SM0, unsigned long long SM1>
+template <unsigned long long FM, unsigned long long SM0, unsigned long long SM1, bool F32_ = false>
 struct StaticIO {
-    static constexpr bool STATIC = true;
+    static constexpr bool STATIC = true, F32 = F32_;
     static constexpr unsigned long long FMASK = FM, S0 = SM0, S1 = SM1;
     static constexpr int NF = ce_popc(FM), NS = ce_popc(SM0) + ce_popc(SM1);
 };
@@ -348,21 +351,22 @@ struct Seg {
     double *sb;            // this lane's column of the tile's segment block
     const double *hot;     // this lane's column of the staged hot parameters (shared memory)
     const double *monp;    // this lane's column of the tile's monthly tables
-    double *outp;          // this lane's column of out[tile][t]
+    unsigned char *outp;   // this lane's cell of out[tile][t][0] (float64 or float32 rows)
     const double *stage;   // this lane's column of the current forcing stage (shared memory)
     const CalStep *calp;   // calendar record of the current interval (warp-uniform)
     unsigned long long fl;
     unsigned calfl;        // HSP2G_CAL_* of the current interval
     unsigned calfl_next;   // ... of the next one, loaded an interval ahead (an L2 round trip off the critical path)
-    int out_step;          // elements between consecutive intervals of out
+    int out_step;          // bytes between consecutive intervals of out
 
     // view of `tile` for the task that starts at interval t0 of the launch
     __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane, int t0, double *hot_area) : L(l) {
         sb = l.segblk + ((size_t)tile * SB_ROWS * LAND_TILE + lane);
         HSP_PIN(sb);
         monp = l.mon + ((size_t)tile * l.mon_rows * LAND_TILE + lane);
-        out_step = (IO::STATIC ? IO::NS : l.ns) * LAND_TILE;
-        outp = l.out + (((size_t)tile * l.nsteps + t0) * out_step + lane);
+        const int osz = out_is_f32() ? 4 : 8;
+        out_step = (IO::STATIC ? IO::NS : l.ns) * LAND_TILE * osz;
+        outp = reinterpret_cast<unsigned char *>(l.out) + (((size_t)tile * l.nsteps + t0) * out_step + lane * osz);
         HSP_PIN(outp);
         calp = l.cal + t0;
         double *h = hot_area + lane;
@@ -384,6 +388,13 @@ struct Seg {
     __device__ __forceinline__ void end_step() {
         outp += out_step;
         ++calp;
+    }
+    __device__ __forceinline__ bool out_is_f32() const { return IO::STATIC ? IO::F32 : (L.out_f32 != 0); }
+    __device__ __forceinline__ void store_out(int r, double v) const {
+        if (out_is_f32())
+            __stcs(reinterpret_cast<float *>(outp) + r * LAND_TILE, (float)v);
+        else
+            __stcs(reinterpret_cast<double *>(outp) + r * LAND_TILE, v);
     }
     __device__ __forceinline__ bool flag(int bit) const { return (fl >> bit) & 1ull; }
     __device__ __forceinline__ double par(int id) const {
@@ -447,11 +458,11 @@ struct Seg {
             if (((oid < 64 ? IO::S0 : IO::S1) >> (oid & 63)) & 1ull) {
                 const int r = (oid < 64 ? 0 : hsp_popc(IO::S0)) +
                               hsp_popc((oid < 64 ? IO::S0 : IO::S1) & ((1ull << (oid & 63)) - 1ull));
-                __stcs(outp + r * LAND_TILE, v);
+                store_out(r, v);
             }
         } else {
             const int r = L.srow[oid];
-            if (r >= 0) __stcs(outp + r * LAND_TILE, v);
+            if (r >= 0) store_out(r, v);
         }
     }
     // state rows are handed from SM to SM between the sub-chunks of a launch: L2-only accesses (L1s are not coherent)

@@ -25,6 +25,8 @@ cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
     if (L.act == (unsigned)SP && hourly) {
         if (io_matches<IO_SnowPwaterDefault>(L))
             return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24>", grid_out);
+        if (io_matches<IO_SnowPwaterDefaultF32>(L))
+            return launch_one<SP, true, IO_SnowPwaterDefaultF32, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,f32>", grid_out);
         if (io_matches<IO_SnowPwaterFlows>(L))
             return launch_one<SP, true, IO_SnowPwaterFlows, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=flows3>", grid_out);
         if (io_matches<IO_SnowPwaterAll>(L))

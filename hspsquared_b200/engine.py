@@ -45,6 +45,7 @@ class LandBatch:
         self.n = store.n
         self.device = device
         self._keep = []
+        self.out_dtype = np.dtype(np.float64)
         self.h = _lib._h()
         op = _lib.PERLND if store.operation == "PERLND" else _lib.IMPLND
         _lib.check(lib.hsp2g_batch_create(device, op, self.n, store.act, float(calendar.delt), C.byref(self.h)))
@@ -130,9 +131,9 @@ class LandBatch:
         nsteps = f.shape[1]
         shape_o = (self.ntiles, nsteps, self.ns, _lib.TILE)
         if out_tiled is None:
-            out_tiled = np.empty(shape_o, dtype=np.float64)
-        elif out_tiled.shape != shape_o or out_tiled.dtype != np.float64 or not out_tiled.flags.c_contiguous:
-            raise ValueError("out must be C-contiguous float64 %r" % (shape_o,))
+            out_tiled = np.empty(shape_o, dtype=self.out_dtype)
+        elif out_tiled.shape != shape_o or out_tiled.dtype != self.out_dtype or not out_tiled.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous %s %r" % (self.out_dtype, shape_o))
         self._keep.append((f, out_tiled))
         _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), f.ctypes.data, out_tiled.ctypes.data))
         return out_tiled
@@ -157,7 +158,7 @@ class LandBatch:
         if forcing.shape != (steps, self.nf, self.n):
             raise ValueError("forcing must be [steps][%d][%d]" % (self.nf, self.n))
         chunk = chunk or steps
-        out = np.empty((steps, self.ns, self.n), dtype=np.float64)
+        out = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
         tiled = []
         for t0 in range(0, steps, chunk):
             t1 = min(steps, t0 + chunk)
@@ -188,6 +189,15 @@ class LandBatch:
     def set_state(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
         _lib.check(self.lib.hsp2g_set_state(self.h, _ptr(state), self.n))
+
+    def set_output_dtype(self, dtype):
+        """np.float64 (default) or np.float32: element type of the saved series the kernels write.  float32 is what
+        the reference's save_timeseries hands the IOManager (utilities.py:313)."""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("output dtype must be float64 or float32")
+        _lib.check(self.lib.hsp2g_set_output_dtype(self.h, _lib.F32 if dtype == np.float32 else _lib.F64))
+        self.out_dtype = dtype
 
     def set_schedule(self, sub_steps):
         """Intervals per (tile, sub-chunk) task of one launch (include/hsp2g.h hsp2g_set_schedule); 0 = whole chunk."""

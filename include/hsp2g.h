@@ -95,9 +95,17 @@ int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *forcing_
  * enables the specialised kernels). */
 int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *output_ids);
 
+/* Element type of the SAVEd series the kernels write (default HSP2G_F64).  HSP2G_F32 rounds each value to float32
+ * (nearest even) in the kernel's store, which is exactly what save_timeseries hands the IOManager
+ * (`df.astype(np.float32)`, utilities.py:313): half the bytes to HBM and over PCIe.  The series layout is unchanged,
+ * [tile][interval][row][32] of the chosen type. */
+#define HSP2G_F64 0
+#define HSP2G_F32 1
+int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype);
+
 /* Advance all segments over intervals [t0, t0+nsteps).  State is read at the start and written at the end, so
  * consecutive chunks are bit-identical to one pass.  Series are tile-major [tile][nsteps][row][32] (see above):
- * forcing = ntiles*nsteps*n_forcing_rows*32 doubles, out = ntiles*nsteps*n_saved_rows*32 doubles.
+ * forcing = ntiles*nsteps*n_forcing_rows*32 doubles, out = ntiles*nsteps*n_saved_rows*32 doubles (or floats).
  * _device: forcings and outputs already in HBM, 16-byte aligned; `stream` is a cudaStream_t (NULL = the batch's own).
  * _host:   host buffers; H2D, kernel and D2H are pipelined on three streams over two device slots; buffers must stay
  *          valid until hsp2g_sync.  Pinned host memory (hsp2g_host_alloc) is needed for real overlap. */

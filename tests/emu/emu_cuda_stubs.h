@@ -84,6 +84,7 @@ inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cuda
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 inline void __stcs(double *p, double v) { *p = v; }
+inline void __stcs(float *p, float v) { *p = v; }
 inline void __stcg(double *p, double v) { *p = v; }
 template <class T>
 inline T __ldcg(const T *p) { return *p; }

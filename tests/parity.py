@@ -25,7 +25,8 @@ def run_oracle(case, time_unit="us"):
     return ts, errs
 
 
-def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps=None, save="all", max_steps=None):
+def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps=None, save="all", max_steps=None,
+              out_dtype=None):
     """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block)."""
     si = CASES.siminfo_for(case)
     cal = Calendar(si["start"], si["stop"], si["delt"], time_unit)
@@ -39,6 +40,8 @@ def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps
     with LandBatch(store, cal, names, save, device=device) as b:
         if sub_steps is not None:
             b.set_schedule(sub_steps)
+        if out_dtype is not None:
+            b.set_output_dtype(out_dtype)
         out = b.run(pack_forcings(forc, names, replicate), chunk=chunk)
         e = b.errors()
         kname = b.kernel_name()
@@ -109,3 +112,20 @@ def compare(ts_ref, ts_got, exact, seg=None):
                     bad.append((k, e))
                     break
     return bad
+
+
+def f32_ulp_diff(got32, ref64):
+    """Largest distance, in float32 units in the last place, between float32 results and the float32 cast of the fp64
+    reference (what save_timeseries stores, utilities.py:313); NaN positions must agree."""
+    got32 = np.asarray(got32)
+    assert got32.dtype == np.float32
+    with np.errstate(over="ignore"):
+        ref32 = np.asarray(ref64, dtype=np.float64).astype(np.float32)
+    if not np.array_equal(np.isnan(got32), np.isnan(ref32)):
+        return np.inf
+    ok = ~np.isnan(ref32)
+    a = got32[ok].view(np.int32).astype(np.int64)
+    b = ref32[ok].view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)  # sign-magnitude -> monotone integer line
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return int(np.abs(a - b).max()) if a.size else 0

@@ -56,6 +56,20 @@ def test_subchunk_tasks_equal_whole_chunk(name):
     assert not parity.compare(ref, b, exact=True, seg=69)
 
 
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10", "p_stress_wet"])
+def test_float32_outputs_are_the_reference_cast(name):
+    """HSP2G_F32: the kernel's store rounds to float32 exactly like save_timeseries' astype(np.float32)
+    (utilities.py:313) -- bit for bit on the CPU double, where the fp64 values are the oracle's."""
+    if name not in ALL:
+        pytest.skip("case not defined")
+    case = ALL[name]
+    ref, _ = parity.run_oracle(case)
+    got, _, _ = parity.run_fused(case, replicate=2, out_dtype=np.float32, chunk=1000)
+    for k, g in got.items():
+        assert g.dtype == np.float32
+        assert parity.f32_ulp_diff(g[:, 1], ref[k][:len(g)]) == 0, k
+
+
 @pytest.mark.parametrize("name", sorted(ALL))
 def test_dropin_bit_exact(name):
     case = ALL[name]

@@ -102,6 +102,44 @@ def test_subchunk_tasks_bitwise(name, save):
         assert np.array_equal(eb[k][:, :3], es[k])
 
 
+@pytest.mark.parametrize("name", ["p001_snow_pwater", "p001_test10", "i001_test10", "cbp_fullchain"])
+def test_float32_outputs(name):
+    """HSP2G_F32 (what save_timeseries stores, utilities.py:313): within 1 float32 ulp of the oracle's fp64 series cast
+    to float32 (the fp64 values themselves agree to ~1e-14, so a rounding tie can flip at most one ulp)."""
+    case = ALL[name]
+    ref, _ = parity.run_oracle(case)
+    got, _, kname = parity.run_fused(case, replicate=2, out_dtype=np.float32)
+    worst = 0
+    for k, g in got.items():
+        assert g.dtype == np.float32
+        worst = max(worst, parity.f32_ulp_diff(g[:, 0], ref[k][:len(g)]))
+    assert worst <= 1, (kname, worst)
+
+
+def test_headline_static_kernels_are_selected():
+    """Default SAVE + the six met series in id order pick the kernels specialised at compile time."""
+    from hspsquared_b200 import synth, test10
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar("1976-01-01", "1976-01-05", 60, "ns")
+    ens = synth.Ensemble("PERLND", 64, seed=5, sections=("SNOW", "PWATER"))
+    save = ["SNOW_" + n for n in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + n for n in test10.SAVE_DEFAULT["PWATER"]]
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps)
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+        o64 = b.run(f)
+        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24>"
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+        b.set_output_dtype(np.float32)
+        o32 = b.run(f)
+        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24,f32>"
+    with np.errstate(over="ignore"):
+        assert np.array_equal(o32, o64.astype(np.float32), equal_nan=True)
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), list(reversed(save))) as b:
+        orev = b.run(f)  # caller's row order is honoured whatever the device order
+    assert np.array_equal(orev[:, ::-1, :], o64, equal_nan=True)
+
+
 def test_hspf_known_answers(golden_dir):
     """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
     hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))
