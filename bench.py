@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--segments", type=int, default=N_SEG_PER_GPU, help="segments per GPU")
     ap.add_argument("--chunk", type=int, default=512, help="intervals per step")
     ap.add_argument("--sub", type=int, default=None, help="intervals per (tile, sub-chunk) task; default = library's")
+    ap.add_argument("--order", default="none", help="experiment: order segments by a jitter key (airt, prec, ...)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -276,6 +277,10 @@ def main():
     if total_chunks * Tc > cal.steps:
         sys.exit("steps*chunk exceeds the 10-year run (%d intervals)" % cal.steps)
     ens = synth.Ensemble("PERLND", n, seed=1234 + rank, sections=("SNOW", "PWATER"))
+    if args.order == "airt":
+        ens = ens.take(np.argsort(ens.u_airt, kind="stable"))
+    elif args.order == "airt_prec":
+        ens = ens.take(np.lexsort((ens.u_prec, np.floor(ens.u_airt * 16))))
     store = ens.store(cal)
     save = default_save()
     batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank)

@@ -222,8 +222,8 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     cudaError_t e = b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
                                           : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
-    // every task draws one ticket and every block one more (the draw that tells it to stop)
-    b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid;
+    // every task draws one ticket and every warp one more (the draw that tells it to stop)
+    b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid * LAND_WARPS;
     b->prog_base += (unsigned)L.nsub;
     if (b->timing) {
         CU(cudaEventRecord(e1, st));
@@ -257,7 +257,8 @@ cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int bloc
     return *resident > 0 ? cudaSuccess : cudaErrorLaunchOutOfResources;
 }
 
-void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident, int *grid_out) {
+void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident_blocks, int warps_per_block, int *grid_out) {
+    const long long resident = (long long)resident_blocks * warps_per_block;  // warps the device holds at once
     if (L.ntiles <= resident || sub_pref <= 0 || sub_pref >= L.nsteps) {
         L.sub = L.nsteps;  // every tile is resident at once (or sub-chunking is off): one task per tile
         L.nsub = 1;
@@ -267,9 +268,11 @@ void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident, int *grid_out) 
     }
     const long long tasks = (long long)L.ntiles * L.nsub;
 #ifdef HSP2G_HOST_EMU
-    *grid_out = L.ntiles;  // the test double walks a tile's sub-chunks in one "thread" (land_common.cuh Sched)
+    (void)tasks;
+    *grid_out = (L.ntiles + warps_per_block - 1) / warps_per_block;  // the test double walks a tile's sub-chunks in one "thread"
 #else
-    *grid_out = (int)(tasks < resident ? tasks : resident);
+    const long long warps = tasks < resident ? tasks : resident;
+    *grid_out = (int)((warps + warps_per_block - 1) / warps_per_block);
 #endif
 }
 

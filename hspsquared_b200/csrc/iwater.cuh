@@ -74,25 +74,25 @@ __device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const 
         if (oldmsupy == 0.0 || hr1fg) {  // IWATER.py:204-207, 221-224
             const double slsur = s.par(P_SLSUR);
             const double dummy = s.daily(FB_M_NSUR, M_NSUR, P_NSUR) * s.par(P_LSUR);
-            w.dec = 0.00982 * pow(dummy / sqrt(slsur), 0.6);
+            w.dec = 0.00982 * hsp_pow(dummy / sqrt(slsur), 0.6);
             w.src = 1020.0 * sqrt(slsur) / dummy;
         }
         if (s.flag(FB_RTOP1)) {  // ARM / NPS closed form (IWATER.py:202-218)
             const double sursm = (w.surs + msupy) * 0.5;
             double dummy = sursm * 1.6;
             if (suri > 0.0) {
-                const double d = w.dec * pow(suri, 0.6);
+                const double d = w.dec * hsp_pow(suri, 0.6);
                 if (d > sursm) {
                     const double r = sursm / d;
                     dummy = sursm * (1.0 + 0.6 * (r * (r * r)));
                 }
             }
-            const double tsuro = delt60 * w.src * pow(dummy, 1.67);
+            const double tsuro = delt60 * w.src * hsp_pow(dummy, 1.67);
             suro = tsuro > msupy ? msupy : tsuro;
             w.surs = tsuro > msupy ? 0.0 : msupy - suro;
         } else {  // Newton (IWATER.py:219-254)
             const double ssupr = suri / delt60;
-            const double surse = ssupr > 0.0 ? w.dec * pow(ssupr, 0.6) : 0.0;
+            const double surse = ssupr > 0.0 ? w.dec * hsp_pow(ssupr, 0.6) : 0.0;
             double sursnw = msupy;
             suro = 0.0;
             bool converged = false;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const 
                     fact = 1.6;
                     ratio = 1e30;
                 }
-                const double ffact = (delt60 * w.src * pow(fact, 1.667)) * pow(sursnw, 1.667);
+                const double ffact = (delt60 * w.src * hsp_pow(fact, 1.667)) * hsp_pow(sursnw, 1.667);
                 const double fsuro = ffact - suro;
                 const double dfact = -1.667 * ffact;
                 double dfsuro = dfact / sursnw - 1.0;

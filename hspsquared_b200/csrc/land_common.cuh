@@ -23,10 +23,12 @@
 #include "hsp2g_ids.h"
 
 #define LAND_TILE 32
-#define LAND_BLOCK 32  // one warp = one tile per block: warps never synchronise, and residency tunes in steps of one warp
+#ifndef LAND_BLOCK
+#define LAND_BLOCK 64  // two independent warps per block: warps never synchronise; pairs halve the 1 KB per-block smem reservation
+#endif
 #define LAND_WARPS (LAND_BLOCK / LAND_TILE)
 #ifndef PIPE_STAGES
-#define PIPE_STAGES 3  // 2 is enough for latency, 3 measured 5 % faster (fewer barrier polls; profiles/r1d)
+#define PIPE_STAGES 2  // one interval of prefetch covers HBM latency (an interval takes a warp microseconds)
 #endif
 
 #define SB_FLAGS 0
@@ -38,11 +40,11 @@
 // Parameters read on (nearly) every interval are staged once per launch into this warp's shared memory: an L1
 // miss on a parameter row costs an L2 round trip in the middle of a serial fp64 dependency chain (profiles/r1b).
 #define PBIT(n) (1ull << P_##n)
-// Per warp: 3 stages x 6 forcing rows + 24 hot parameters + 22 cold states = 64 rows of 256 B = 16 KB (+1 KB
-// system reservation per block) -> 13 one-warp blocks per SM; residency beyond ~12 warps no longer pays
-// (profiles/r1d: 12, 14 and 16 warps within 2 %).
+// Per warp (headline kernel): 2 stages x 6 forcing rows + 23 hot parameters + 19 cold states = 54 rows of 256 B
+// = 13.5 KB; 8 two-warp blocks (+1 KB system reservation each) fit the 228 KB of an SM = 16 resident warps at <= 128
+// registers (RDCSN, read only while it snows, stays in global memory: a 55th row would cost two warps).
 #define HOT_SNOW                                                                                                   \
-    (PBIT(TSNOW) | PBIT(SNOWCF) | PBIT(RDCSN) | PBIT(COVIND) | PBIT(SNOEVP) | PBIT(CCFACT) | PBIT(MELEV) |          \
+    (PBIT(TSNOW) | PBIT(SNOWCF) | PBIT(COVIND) | PBIT(SNOEVP) | PBIT(CCFACT) | PBIT(MELEV) |          \
      PBIT(SHADE) | PBIT(MWATER) | PBIT(MGMELT_IVL))
 #define HOT_PWATER                                                                                                 \
     (PBIT(INFILT_IVL) | PBIT(KVARY) | PBIT(LZSN) | PBIT(FOREST) | PBIT(PETMAX) | PBIT(PETMIN) | PBIT(FZG) |         \
@@ -119,9 +121,49 @@ struct ColdG {
     }
 };
 #endif
+// A carried scalar that an hourly kernel recomputes before every use: the register copy `v` is then dead across
+// the time loop (no register, no shared memory), and each assignment writes the value through to its state row in
+// global memory so the next task / chunk finds it.  Where some use is NOT dominated by an assignment (an output saved
+// every interval, say) the compiler simply keeps `v` live, so the type is safe for any configuration.
+#ifdef HSP2G_HOST_EMU
+struct ColdW {
+    double v, *p;
+    operator double() const { return v; }
+    ColdW &operator=(double x) {
+        v = x;
+        *p = x;
+        return *this;
+    }
+};
+#else
+struct ColdW {
+    double v, *p;
+    __device__ __forceinline__ operator double() const { return v; }
+    __device__ __forceinline__ ColdW &operator=(double x) {
+        v = x;
+        __stcg(p, x);
+        return *this;
+    }
+};
+#endif
 #define NCOLD_SNOW 12
-#define NCOLD_PWATER 10
-#define NCOLD (NCOLD_SNOW + NCOLD_PWATER)
+#define NCOLD_SNOW2 7
+#define NCOLD_PWATER 12
+#define NCOLD_MAX (NCOLD_SNOW + NCOLD_SNOW2 + NCOLD_PWATER)
+
+// One out-of-line copy of pow's argument screening + __internal_accurate_pow instead of one per call site (17 sites,
+// ~100 SASS instructions each): the March step of profiles/r1g spent 40 % of its stall samples waiting for
+// instructions.  Same function, same bits.
+static __device__ __noinline__ double hsp_pow(double x, double y) { return pow(x, y); }
+
+// Likewise one out-of-line copy of the IEEE fp64 division sequence (MUFU.RCP64H + Newton + residual, ~20 SASS
+// instructions inline at each of ~50 sites = a quarter of the kernel).  a / b, correctly rounded, same bits.
+static __device__ __noinline__ double hsp_div(double a, double b) { return a / b; }
+#ifdef HSP_INLINE_DIV
+#define HDIV(a, b) ((a) / (b))
+#else
+#define HDIV(a, b) hsp_div((a), (b))
+#endif
 
 // Python semantics: max(a,b) = b if b>a else a ; min(a,b) = b if b<a else a  
 __device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }
@@ -195,10 +237,10 @@ struct Pipe {
     unsigned ph;        // its phase parity
     int lane;
 
-    // smem layout: [warp][PIPE_STAGES*nf*32 ring doubles | nhot*32 hot parameters | NCOLD*32 cold state], then the mbarriers
-    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf, int nhot) {
+    // smem layout: [warp][PIPE_STAGES*nf*32 ring doubles | nhot*32 hot parameters | ncold*32 cold state], then the mbarriers
+    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf, int nhot, int ncold) {
         stage_elems = nf * LAND_TILE;
-        const int warp_elems = PIPE_STAGES * stage_elems + (nhot + NCOLD) * LAND_TILE;
+        const int warp_elems = PIPE_STAGES * stage_elems + (nhot + ncold) * LAND_TILE;
         ring = smem + (size_t)wib * warp_elems;
         ring_s = smem_u32(ring);
         bar_s = smem_u32(smem + (size_t)LAND_WARPS * warp_elems) + wib * PIPE_STAGES * 8;
@@ -269,7 +311,7 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 struct Sched {
     const LandLaunch &L;
     int lane, c;
-    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_) : L(l), lane(lane_), c(0) {}
+    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int) : L(l), lane(lane_), c(0) {}
     __device__ __forceinline__ bool next(int &tile, int &t0, int &t1) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(L.task_counter, 1ull) - L.task_base;
@@ -301,7 +343,7 @@ struct Pipe {
     double *ring;
     const double *src;
     int stage_elems, lane, t_cur;
-    void init(double *smem, int, int lane_, int nf, int) {
+    void init(double *smem, int, int lane_, int nf, int, int) {
         ring = smem;
         stage_elems = nf * LAND_TILE;
         lane = lane_;
@@ -319,11 +361,11 @@ struct Pipe {
 };
 struct Sched {
     const LandLaunch &L;
-    int c;
-    Sched(const LandLaunch &l, int) : L(l), c(-1) {}
+    int c, wib;
+    Sched(const LandLaunch &l, int, int wib_) : L(l), c(-1), wib(wib_) {}
     bool next(int &tile, int &t0, int &t1) {
-        if (++c >= L.nsub) return false;
-        tile = (int)blockIdx.x;
+        tile = (int)blockIdx.x * LAND_WARPS + wib;
+        if (tile >= L.ntiles || ++c >= L.nsub) return false;
         t0 = c * L.sub;
         t1 = t0 + L.sub < L.nsteps ? t0 + L.sub : L.nsteps;
         return true;
@@ -420,7 +462,7 @@ struct Seg {
         const double xm = calp->xm;
         if (xm == 0.0) return y0;
         const double y1 = __ldg(tab + (int)calp->m1 * LAND_TILE);
-        const double slope = (y1 - y0) / calp->dxm;
+        const double slope = HDIV(y1 - y0, calp->dxm);
         return slope * xm + y0;
     }
     // N daily values at once: every table load is issued before the first division, so a new day costs one L2
@@ -443,7 +485,7 @@ struct Seg {
             }
         }
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = (flag(fb[k]) && xm != 0.0) ? ((y1[k] - y0[k]) / dxm) * xm + y0[k] : y0[k];
+        for (int k = 0; k < N; ++k) v[k] = (flag(fb[k]) && xm != 0.0) ? HDIV(y1[k] - y0[k], dxm) * xm + y0[k] : y0[k];
     }
     // initm(): the table where the segment's flag is on, else the constant parameter
     __device__ __forceinline__ double daily(int flagbit, int mid, int pid) const {

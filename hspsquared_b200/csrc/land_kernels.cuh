@@ -34,6 +34,17 @@
 #define HSP_MAXNREG(n) __maxnreg__(n)
 #endif
 
+// hourly kernels with a compile-time SAVE set keep SNOW's hour-gated scalars write-through (ColdW); the others in
+// shared memory (ColdD)
+template <bool W>
+struct ColdPick {
+    typedef ColdD type;
+};
+template <>
+struct ColdPick<true> {
+    typedef ColdW type;
+};
+
 template <class SEG>
 __device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
     // ATEMP.py:57-58 with k = delt*0.000833 (ATEMP.py:22)
@@ -51,21 +62,23 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
     typedef Seg<IO, PERLND_HOT> SegT;
+    typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
+    constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER;
     Pipe pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT);
-    Sched sched(L, lane);
+    pipe.init(smem, wib, lane, nf, SegT::NHOT, NCOLD);
+    Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {  // one task = intervals [t0, t1) of one tile (land_common.cuh Sched)
         pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
-        SnowState sw;
+        SnowStateT<SNOWCOLD> sw;
         PwaterState pw;
         SedmntState sd;
         PstempState ps;
         double *cold = pipe.hot_area() + SegT::NHOT * LAND_TILE + lane;
-        sw.bind(cold);
-        pw.bind(cold + NCOLD_SNOW * LAND_TILE, s.sb);
+        sw.bind(cold, s.sb);
+        pw.bind(cold + SnowStateT<SNOWCOLD>::SMEM_ROWS * LAND_TILE, s.sb);
         if (act & HSP2G_ACT_SNOW) sw.load(s);
         if (act & HSP2G_ACT_PWATER) pw.load(s);
         if (act & HSP2G_ACT_SEDMNT) sd.load(s);
@@ -134,17 +147,19 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
     typedef Seg<IO, IMPLND_HOT> SegT;
+    typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
+    constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS;
     Pipe pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT);
-    Sched sched(L, lane);
+    pipe.init(smem, wib, lane, nf, SegT::NHOT, NCOLD);
+    Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {
         pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
-        SnowState sw;
+        SnowStateT<SNOWCOLD> sw;
         IwaterState iw;
-        sw.bind(pipe.hot_area() + SegT::NHOT * LAND_TILE + lane);
+        sw.bind(pipe.hot_area() + SegT::NHOT * LAND_TILE + lane, s.sb);
         if (act & HSP2G_ACT_SNOW) sw.load(s);
         if (act & HSP2G_ACT_IWATER) iw.load(s);
 
@@ -181,6 +196,15 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
 }
 
 // dynamic shared memory of one block: per warp PIPE_STAGES interval stages + the hot parameters + one mbarrier per stage
-static inline size_t land_smem_bytes(int nf, unsigned long long hot) {
-    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + NCOLD) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
+static inline size_t land_smem_bytes(int nf, unsigned long long hot, int ncold) {
+    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + ncold) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
+}
+// cold-state rows of a kernel instantiation (must mirror the NCOLD constants inside the kernels)
+template <bool HOURLY, class IO>
+static inline int perlnd_ncold() {
+    return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS + NCOLD_PWATER;
+}
+template <bool HOURLY, class IO>
+static inline int implnd_ncold() {
+    return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS;
 }

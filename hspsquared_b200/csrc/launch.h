@@ -10,4 +10,4 @@ cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
 // opt in to the dynamic shared memory a kernel needs; *resident = blocks of `block` threads the device holds at once
 cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident);
 // tasks = (tile, sub-chunk of sub_pref intervals) when the tiles outnumber the resident warps, else one task per tile
-void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident, int *grid_out);
+void hsp2g_plan_tasks(LandLaunch &L, int sub_pref, int resident_blocks, int warps_per_block, int *grid_out);

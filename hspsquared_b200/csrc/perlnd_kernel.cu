@@ -4,17 +4,17 @@
 #include "launch.h"
 
 #ifndef HSP_MAXREG_HOT
-#define HSP_MAXREG_HOT 144  // register cap of the specialised kernels (they need 128, no spills): 14 resident warps per SM
+#define HSP_MAXREG_HOT 128  // register cap of the specialised kernels: 4 warps per SM sub-partition (16 per SM), no spills
 #endif
 
 template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, PERLND_HOT);
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, PERLND_HOT, perlnd_ncold<HOURLY, IO>());
     auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
-    hsp2g_plan_tasks(L, sub_pref, cap, grid_out);
+    hsp2g_plan_tasks(L, sub_pref, cap, LAND_WARPS, grid_out);
     HSP2G_LAUNCH(k, (unsigned)*grid_out, LAND_BLOCK, smem, st, L);
     if (name) *name = nm;
     return cudaGetLastError();

@@ -7,7 +7,8 @@
 #include "land_common.cuh"
 
 struct PwaterState {
-    double ceps, surs, uzs, ifws, lzs, agws, gwvs, msupy;
+    double ceps, surs, uzs, ifws, lzs, agws;
+    ColdD gwvs, msupy;  // touched once or twice per interval
     // change once a day / on the first wet interval / when LZS moves by 2 %: not in registers (land_common.cuh ColdD)
     ColdG dec, src;
     ColdD ifwk1, ifwk2, rlzrat, lzfrac, rparm, petadj;
@@ -17,7 +18,7 @@ struct PwaterState {
     // c: this lane's shared-memory scratch column; sb: this lane's column of the segment block.  The
     // two values that only wet intervals touch stay in their state rows in global memory (L2), the rest is shared.
     __device__ __forceinline__ void bind(double *c, double *sb) {
-        ColdD *m[NCOLD_PWATER] = {&ifwk1, &ifwk2, &rlzrat, &lzfrac, &rparm, &petadj, &cepsc, &uzsn, &lzetp, &intfw};
+        ColdD *m[NCOLD_PWATER] = {&ifwk1, &ifwk2, &rlzrat, &lzfrac, &rparm, &petadj, &cepsc, &uzsn, &lzetp, &intfw, &gwvs, &msupy};
         for (int k = 0; k < NCOLD_PWATER; ++k) m[k]->p = c + k * LAND_TILE;
         dec.p = sb + (SB_STATE + S_DEC) * LAND_TILE;
         src.p = sb + (SB_STATE + S_SRC) * LAND_TILE;
@@ -79,34 +80,34 @@ __device__ __forceinline__ int proute(double psur, bool rtop1, double delt60, do
     int nonconv = 0;
     if (psur > 0.0002) {
         if (!rtop1) {
-            const double ssupr = (psur - surs) / delt60;
-            const double surse = ssupr > 0.0 ? dec * pow(ssupr, 0.6) : 0.0;
+            const double ssupr = HDIV(psur - surs, delt60);
+            const double surse = ssupr > 0.0 ? dec * hsp_pow(ssupr, 0.6) : 0.0;
             double sursnw = psur;
             suro = 0.0;
             bool converged = false;
             for (int count = 0; count < 100; ++count) {
                 double ratio, fact;
                 if (ssupr > 0.0) {
-                    ratio = sursnw / surse;
+                    ratio = HDIV(sursnw, surse);
                     fact = ratio <= 1.0 ? 1.0 + 0.6 * (ratio * (ratio * ratio)) : 1.6;
                 } else {
                     ratio = 1.0e30;
                     fact = 1.6;
                 }
-                const double ffact = (delt60 * src * pow(fact, 1.667)) * pow(sursnw, 1.667);
+                const double ffact = (delt60 * src * hsp_pow(fact, 1.667)) * hsp_pow(sursnw, 1.667);
                 const double fsuro = ffact - suro;
                 const double dfact = -1.667 * ffact;
-                double dfsuro = dfact / sursnw - 1.0;
+                double dfsuro = HDIV(dfact, sursnw) - 1.0;
                 if (ratio <= 1.0) {
-                    const double dterm = dfact / (fact * surse) * 1.8 * (ratio * ratio);
+                    const double dterm = HDIV(dfact, fact * surse) * 1.8 * (ratio * ratio);
                     dfsuro = dfsuro + dterm;
                 }
-                const double dsuro = fsuro / dfsuro;
+                const double dsuro = HDIV(fsuro, dfsuro);
                 suro = suro - dsuro;
                 if (suro <= 1.0e-10) suro = 0.0;
                 sursnw = psur - suro;
                 double change = 0.0;
-                if (fabs(suro) > 0.0) change = fabs(dsuro / suro);
+                if (fabs(suro) > 0.0) change = fabs(HDIV(dsuro, suro));
                 if (change < 0.01) {
                     converged = true;
                     break;
@@ -119,15 +120,15 @@ __device__ __forceinline__ int proute(double psur, bool rtop1, double delt60, do
             const double sursm = (surs + psur) * 0.5;
             double dummy;
             if (ssupr > 0.0) {
-                dummy = dec * pow(ssupr, 0.6);
+                dummy = dec * hsp_pow(ssupr, 0.6);
                 if (dummy > sursm) {
-                    const double r = sursm / dummy;
+                    const double r = HDIV(sursm, dummy);
                     dummy = sursm * (1.0 + 0.6 * (r * (r * r)));
                 } else
                     dummy = sursm * 1.6;
             } else
                 dummy = sursm * 1.6;
-            const double tsuro = delt60 * src * pow(dummy, 1.667);
+            const double tsuro = delt60 * src * hsp_pow(dummy, 1.667);
             suro = tsuro > psur ? psur : tsuro;
             surs = tsuro > psur ? 0.0 : psur - suro;
         }
@@ -189,7 +190,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
     const double suri = cepo + s.forcing(F_SURLI);
     w.msupy = suri + w.surs + 0.0;
     const double msupy = w.msupy;
-    double lzrat = w.lzs / lzsn;
+    double lzrat = HDIV(w.lzs, lzsn);
     double suro, ifwi, infil, uzi;
 
     if (msupy <= 0.0) {
@@ -199,15 +200,15 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
         infil = 0.0;
         uzi = 0.0;
     } else {  // ---- SURFAC / DISPOS (PWATER.py:326-437)
-        double ibar = infilt / pow(lzrat, s.par(P_INFEXP));
+        double ibar = HDIV(infilt, hsp_pow(lzrat, s.par(P_INFEXP)));
         if (inffac < 1.0) ibar = ibar * inffac;
         const double imax = ibar * s.par(P_INFILD);
         const double imin = ibar - (imax - ibar);
         if (dayfg || oldmsupy == 0.0) {
             const double slsur = s.par(P_SLSUR);
             const double dummy = s.daily(FB_M_NSUR, M_NSUR, P_NSUR) * s.par(P_LSUR);
-            w.dec = 0.00982 * pow(dummy / sqrt(slsur), 0.6);
-            w.src = 1020.0 * (sqrt(slsur) / dummy);
+            w.dec = 0.00982 * hsp_pow(HDIV(dummy, sqrt(slsur)), 0.6);
+            w.src = 1020.0 * HDIV(sqrt(slsur), dummy);
         }
         const double ratio = py_max(1.0001, w.intfw * exp2(lzrat));
         double under, over;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
             under = (imin + imax) * 0.5;
             over = msupy - under;
         } else {
-            over = ((msupy - imin) * (msupy - imin)) * 0.5 / (imax - imin);
+            over = HDIV(((msupy - imin) * (msupy - imin)) * 0.5, imax - imin);
             under = msupy - over;
         }
         infil = under;
@@ -230,39 +231,39 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
         } else {
             const double pdro = over;
             if (s.flag(FB_UZFG)) {  // UZINF2 (PWATER.py:366-379)
-                const double uzrat = w.uzs / uzsn;
+                const double uzrat = HDIV(w.uzs, uzsn);
                 double uzfrac;
                 if (uzrat < 2.0) {
                     const double k1 = 3.0 - uzrat;
-                    uzfrac = 1.0 - (uzrat * 0.5) * pow(1.0 / (1.0 + k1), k1);
+                    uzfrac = 1.0 - (uzrat * 0.5) * hsp_pow(HDIV(1.0, 1.0 + k1), k1);
                 } else {
                     const double k2 = (2.0 * uzrat) - 3.0;
-                    uzfrac = pow(1.0 / (1.0 + k2), k2);
+                    uzfrac = hsp_pow(HDIV(1.0, 1.0 + k2), k2);
                 }
                 uzi = pdro * uzfrac;
             } else {  // UZINF table look-up (PWATER.py:381-404)
-                const double uzraa = w.uzs / uzsn;
+                const double uzraa = HDIV(w.uzs, uzsn);
                 int kk = first_above_m1(uzraa, UZRA_TAB);
                 if (kk == -1) {
                     kk = 8;
                     e1 = 1;
                 }
-                const double intga = INTGRL_TAB[kk] + (INTGRL_TAB[kk + 1] - INTGRL_TAB[kk]) * (uzraa - UZRA_TAB[kk]) /
-                                                          (UZRA_TAB[kk + 1] - UZRA_TAB[kk]);
-                const double intgb = (pdro / uzsn) + intga;
+                const double intga = INTGRL_TAB[kk] + HDIV((INTGRL_TAB[kk + 1] - INTGRL_TAB[kk]) * (uzraa - UZRA_TAB[kk]),
+                                                           UZRA_TAB[kk + 1] - UZRA_TAB[kk]);
+                const double intgb = HDIV(pdro, uzsn) + intga;
                 kk = first_above_m1(intgb, INTGRL_TAB);
                 if (kk == -1) {
                     e2 = 1;
                     kk = 8;
                 }
-                const double uzrab = UZRA_TAB[kk] + (UZRA_TAB[kk + 1] - UZRA_TAB[kk]) * (intgb - INTGRL_TAB[kk]) /
-                                                        (INTGRL_TAB[kk + 1] - INTGRL_TAB[kk]);
+                const double uzrab = UZRA_TAB[kk] + HDIV((UZRA_TAB[kk + 1] - UZRA_TAB[kk]) * (intgb - INTGRL_TAB[kk]),
+                                                         INTGRL_TAB[kk + 1] - INTGRL_TAB[kk]);
                 uzi = (uzrab - uzraa) * uzsn;
                 if (uzi < -1.0e-3) e7 = 1;
                 uzi = py_max(0.0, uzi);
             }
             if (uzi > pdro) uzi = pdro;
-            const double uzfrac = uzi / pdro;
+            const double uzfrac = HDIV(uzi, pdro);
             const double iimin = imin * ratio, iimax = imax * ratio;
             double over2;
             if (msupy <= iimin)
@@ -270,7 +271,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
             else if (msupy > iimax)
                 over2 = msupy - (iimin + iimax) * 0.5;
             else
-                over2 = ((msupy - iimin) * (msupy - iimin)) * 0.5 / (iimax - iimin);
+                over2 = HDIV(((msupy - iimin) * (msupy - iimin)) * 0.5, iimax - iimin);
             double psur = over2;
             const double pifwi = pdro - psur;
             ifwi = pifwi * (1.0 - uzfrac);
@@ -286,9 +287,9 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
 
     // ---- INTFLW (PWATER.py:440-455)
     if (dayfg) {
-        const double kifw = -log(s.daily(FB_M_IRC, M_IRC, P_IRC)) / (24.0 / delt60);
+        const double kifw = HDIV(-log(s.daily(FB_M_IRC, M_IRC, P_IRC)), HDIV(24.0, delt60));
         w.ifwk2 = 1.0 - exp(-kifw);
-        w.ifwk1 = 1.0 - (w.ifwk2 / kifw);
+        w.ifwk1 = 1.0 - HDIV(w.ifwk2, kifw);
     }
     const double inflo = ifwi + s.forcing(F_IFWLI);
     const double value = inflo + w.ifws;
@@ -303,7 +304,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
     }
 
     // ---- UZONE (PWATER.py:457-468)
-    double uzrat = w.uzs / uzsn;
+    double uzrat = HDIV(w.uzs, uzsn);
     w.uzs = w.uzs + uzi + s.forcing(F_UZLI) + 0.0;
     double perc = 0.0;
     if (uzrat - lzrat > 0.01) {
@@ -326,10 +327,10 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
             w.rlzrat = lzrat;
             if (lzrat <= 1.0) {
                 const double indx = 2.5 - 1.5 * lzrat;
-                w.lzfrac = ifrd ? 1.0 : 1.0 - lzrat * pow(1.0 / (1.0 + indx), indx);
+                w.lzfrac = ifrd ? 1.0 : 1.0 - lzrat * hsp_pow(HDIV(1.0, 1.0 + indx), indx);
             } else {
                 const double indx = 1.5 * lzrat - 0.5;
-                w.lzfrac = ifrd ? exp(-1.0 * (lzrat - 1.0)) : pow(1.0 / (1.0 + indx), indx);
+                w.lzfrac = ifrd ? exp(-1.0 * (lzrat - 1.0)) : hsp_pow(HDIV(1.0, 1.0 + indx), indx);
             }
         }
         lzi = w.lzfrac * lperc;
@@ -396,7 +397,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
     double uzet = 0.0;
     if (rempet > 0.0) {
         if (w.uzs > 0.001) {
-            uzrat = w.uzs / uzsn;
+            uzrat = HDIV(w.uzs, uzsn);
             const double uzpet = uzrat > 2.0 ? rempet : 0.5 * uzrat * rempet;
             if (uzpet > w.uzs) {
                 uzet = w.uzs;
@@ -425,8 +426,8 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
         rempet -= agwet;
     }
     if (dayfg) {
-        lzrat = w.lzs / lzsn;
-        w.rparm = lzetp <= 0.99999 ? 0.25 / (1.0 - lzetp) * lzrat * delt60 / 24.0 : 1.0e10;
+        lzrat = HDIV(w.lzs, lzsn);
+        w.rparm = lzetp <= 0.99999 ? HDIV(HDIV(0.25, 1.0 - lzetp) * lzrat * delt60, 24.0) : 1.0e10;
     }
     double lzet = 0.0;
     if (rempet > 0.0 && w.lzs > 0.02) {
@@ -434,7 +435,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
         if (lzetp >= 0.99999)
             lzpet = rempet * lzetp;
         else if (!s.flag(FB_VLE_GE2)) {
-            lzpet = rempet > w.rparm ? 0.5 * w.rparm : rempet * (1.0 - rempet / (2.0 * w.rparm));
+            lzpet = rempet > w.rparm ? 0.5 * w.rparm : rempet * (1.0 - HDIV(rempet, 2.0 * w.rparm));
             if (lzetp < 0.5) lzpet = lzpet * 2.0 * lzetp;
         } else
             lzpet = lzrat < 1.0 ? lzetp * lzrat * rempet : lzetp * rempet;

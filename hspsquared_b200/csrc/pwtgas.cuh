@@ -32,7 +32,7 @@ __device__ __forceinline__ void pwtgas_step(const SEG &s, const SoilTemps &soil,
         sodox = (14.652 + sotmp * (-0.41022 + dummy)) * elevgc;
         const double abstmp = sotmp + 273.16;
         dummy = 2385.73 / abstmp - 14.0184 + 0.0152642 * abstmp;
-        soco2 = pow(10.0, dummy) * 3.16e-04 * elevgc * 12000.0;
+        soco2 = hsp_pow(10.0, dummy) * 3.16e-04 * elevgc * 12000.0;
         const double slifac = s.par(P_SLIFAC);
         if (surli > 0.0 && slifac > 0.0)
             mix_lateral(sotmp, sodox, soco2, s.forcing(F_SLITMP), s.forcing(F_SLIDOX), s.forcing(F_SLICO2), slifac);

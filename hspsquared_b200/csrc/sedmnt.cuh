@@ -35,7 +35,7 @@ __device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double
             cr = snocov > 0.0 ? w.cover + (1.0 - w.cover) * snocov : w.cover;
         else
             cr = w.cover;
-        const double det = delt60 * (1.0 - cr) * s.par(P_SMPF) * s.par(P_KRER) * pow(rain / delt60, s.par(P_JRER));
+        const double det = delt60 * (1.0 - cr) * s.par(P_SMPF) * s.par(P_KRER) * hsp_pow(rain / delt60, s.par(P_JRER));
         w.dets = w.dets + det;
     }
     if (dayfg) {  // SEDMNT.py:175-179
@@ -54,17 +54,17 @@ __device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double
         const double kser = s.par(P_KSER), jser = s.par(P_JSER), kger = s.par(P_KGER), jger = s.par(P_JGER);
         if (s.flag(FB_SDOPFG)) {  // method 1 (SEDMNT.py:188-212)
             const double arg = surs + suro;
-            const double stcap = delt60 * kser * pow(arg / delt60, jser);
+            const double stcap = delt60 * kser * hsp_pow(arg / delt60, jser);
             if (stcap > w.dets)
                 wssd = w.dets * suro / arg;
             else
                 wssd = stcap * suro / arg;
             w.dets = w.dets - wssd;
-            scrsd = delt60 * kger * pow(arg / delt60, jger);
+            scrsd = delt60 * kger * hsp_pow(arg / delt60, jger);
             scrsd = scrsd * suro / arg;
             sosed = wssd + scrsd;
         } else {  // method 2 (SEDMNT.py:214-233)
-            const double stcap = delt60 * kser * pow(suro / delt60, jser);
+            const double stcap = delt60 * kser * hsp_pow(suro / delt60, jser);
             if (stcap > w.dets) {
                 wssd = w.dets;
                 w.dets = 0.0;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double
                 wssd = stcap;
                 w.dets = w.dets - wssd;
             }
-            scrsd = delt60 * kger * pow(suro / delt60, jger);
+            scrsd = delt60 * kger * hsp_pow(suro / delt60, jger);
             sosed = wssd + scrsd;
         }
     } else {

@@ -7,40 +7,63 @@
 #pragma once
 #include "land_common.cuh"
 
-struct SnowState {
-    double covinx, dull, packf, packi, packw, paktmp, rdenpf, skyclr, xlnmlt, pdepth, snocov, neghts, oldprec;
+// COLD = ColdD (shared memory; any time step) or ColdW (write-through, hourly kernels): see land_common.cuh
+template <class COLD>
+struct SnowStateT {
+    double packf, packi, packw, pdepth, snocov, neghts;
+    // touched once or twice per interval (plus their SAVE store): shared memory
+    ColdD covinx, dull, paktmp, rdenpf, skyclr, xlnmlt, oldprec;
     // recomputed on every hourly (HRFG) interval a pack exists: carried only between HRFG intervals of a sub-hourly
-    // run and into the next chunk, so they live in shared memory (land_common.cuh ColdD)
-    ColdD snotmp, dewtmp, mneghs, packwc, compct, gmeltr, mostht, neght, rdnsn, snowep, vap, albedo;
+    // run and into the next task / chunk
+    COLD snotmp, dewtmp, mneghs, packwc, compct, gmeltr, mostht, neght, rdnsn, snowep, vap, albedo;
     int hr6fg;
 
-    __device__ __forceinline__ void bind(double *c) {
-        ColdD *m[NCOLD_SNOW] = {&snotmp, &dewtmp, &mneghs, &packwc, &compct, &gmeltr,
-                                &mostht, &neght,  &rdnsn,  &snowep, &vap,    &albedo};
-        for (int k = 0; k < NCOLD_SNOW; ++k) m[k]->p = c + k * LAND_TILE;
+    static constexpr int SMEM_ROWS = NCOLD_SNOW2 + (sizeof(COLD) == sizeof(ColdD) ? NCOLD_SNOW : 0);
+
+    // c: shared-memory scratch column (ColdD); sb: this lane's column of the segment block (ColdW)
+    __device__ __forceinline__ void bind(double *c, double *sb) {
+        COLD *m[NCOLD_SNOW] = {&snotmp, &dewtmp, &mneghs, &packwc, &compct, &gmeltr,
+                               &mostht, &neght,  &rdnsn,  &snowep, &vap,    &albedo};
+        const int sid[NCOLD_SNOW] = {S_SNOTMP, S_DEWTMP, S_MNEGHS, S_PACKWC, S_COMPCT, S_GMELTR,
+                                     S_MOSTHT, S_NEGHT,  S_RDNSN,  S_SNOWEP, S_VAP,    S_ALBEDO};
+        for (int k = 0; k < NCOLD_SNOW; ++k) m[k]->p = cold_home(m[k], c + k * LAND_TILE, sb + (SB_STATE + sid[k]) * LAND_TILE);
+        ColdD *m2[NCOLD_SNOW2] = {&covinx, &dull, &paktmp, &rdenpf, &skyclr, &xlnmlt, &oldprec};
+        for (int k = 0; k < NCOLD_SNOW2; ++k) m2[k]->p = c + (SMEM_ROWS - NCOLD_SNOW2 + k) * LAND_TILE;
     }
+    static __device__ __forceinline__ double *cold_home(const ColdD *, double *smem, double *) { return smem; }
+    static __device__ __forceinline__ double *cold_home(const ColdW *, double *, double *glob) { return glob; }
 
     template <class SEG>
-
     __device__ __forceinline__ void load(const SEG &s) {
         covinx = s.st(S_COVINX); dull = s.st(S_DULL); packf = s.st(S_PACKF); packi = s.st(S_PACKI);
         packw = s.st(S_PACKW); paktmp = s.st(S_PAKTMP); rdenpf = s.st(S_RDENPF); skyclr = s.st(S_SKYCLR);
         xlnmlt = s.st(S_XLNMLT); pdepth = s.st(S_PDEPTH); snocov = s.st(S_SNOCOV); neghts = s.st(S_NEGHTS);
-        oldprec = s.st(S_OLDPREC); snotmp = s.st(S_SNOTMP); dewtmp = s.st(S_DEWTMP); mneghs = s.st(S_MNEGHS);
-        packwc = s.st(S_PACKWC); compct = s.st(S_COMPCT); gmeltr = s.st(S_GMELTR); mostht = s.st(S_MOSTHT);
-        neght = s.st(S_NEGHT); rdnsn = s.st(S_RDNSN); snowep = s.st(S_SNOWEP); vap = s.st(S_VAP);
-        albedo = s.st(S_ALBEDO); hr6fg = s.st(S_HR6FG) != 0.0;
+        oldprec = s.st(S_OLDPREC); hr6fg = s.st(S_HR6FG) != 0.0;
+        load_cold(snotmp, s, S_SNOTMP); load_cold(dewtmp, s, S_DEWTMP); load_cold(mneghs, s, S_MNEGHS);
+        load_cold(packwc, s, S_PACKWC); load_cold(compct, s, S_COMPCT); load_cold(gmeltr, s, S_GMELTR);
+        load_cold(mostht, s, S_MOSTHT); load_cold(neght, s, S_NEGHT); load_cold(rdnsn, s, S_RDNSN);
+        load_cold(snowep, s, S_SNOWEP); load_cold(vap, s, S_VAP); load_cold(albedo, s, S_ALBEDO);
     }
+    template <class SEG>
+    static __device__ __forceinline__ void load_cold(ColdD &d, const SEG &s, int sid) { d = s.st(sid); }
+    template <class SEG>
+    static __device__ __forceinline__ void load_cold(ColdW &d, const SEG &s, int sid) { d.v = s.st(sid); }  // no write-back
+
     template <class SEG>
     __device__ __forceinline__ void store(const SEG &s) const {
         s.st(S_COVINX, covinx); s.st(S_DULL, dull); s.st(S_PACKF, packf); s.st(S_PACKI, packi);
         s.st(S_PACKW, packw); s.st(S_PAKTMP, paktmp); s.st(S_RDENPF, rdenpf); s.st(S_SKYCLR, skyclr);
         s.st(S_XLNMLT, xlnmlt); s.st(S_PDEPTH, pdepth); s.st(S_SNOCOV, snocov); s.st(S_NEGHTS, neghts);
-        s.st(S_OLDPREC, oldprec); s.st(S_SNOTMP, snotmp); s.st(S_DEWTMP, dewtmp); s.st(S_MNEGHS, mneghs);
-        s.st(S_PACKWC, packwc); s.st(S_COMPCT, compct); s.st(S_GMELTR, gmeltr); s.st(S_MOSTHT, mostht);
-        s.st(S_NEGHT, neght); s.st(S_RDNSN, rdnsn); s.st(S_SNOWEP, snowep); s.st(S_VAP, vap);
-        s.st(S_ALBEDO, albedo); s.st(S_HR6FG, hr6fg ? 1.0 : 0.0);
+        s.st(S_OLDPREC, oldprec); s.st(S_HR6FG, hr6fg ? 1.0 : 0.0);
+        store_cold(snotmp, s, S_SNOTMP); store_cold(dewtmp, s, S_DEWTMP); store_cold(mneghs, s, S_MNEGHS);
+        store_cold(packwc, s, S_PACKWC); store_cold(compct, s, S_COMPCT); store_cold(gmeltr, s, S_GMELTR);
+        store_cold(mostht, s, S_MOSTHT); store_cold(neght, s, S_NEGHT); store_cold(rdnsn, s, S_RDNSN);
+        store_cold(snowep, s, S_SNOWEP); store_cold(vap, s, S_VAP); store_cold(albedo, s, S_ALBEDO);
     }
+    template <class SEG>
+    static __device__ __forceinline__ void store_cold(const ColdD &d, const SEG &s, int sid) { s.st(sid, d); }
+    template <class SEG>
+    static __device__ __forceinline__ void store_cold(const ColdW &, const SEG &, int) {}  // already written through
 };
 
 // fluxes of the current interval that the water sections consume
@@ -65,8 +88,8 @@ __device__ __forceinline__ double svp_at(double temp) {
     return a + (indx - (double)lower) * (b - a);
 }
 
-template <bool HOURLY, class SEG>
-__device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &x, double airtmp, double prec) {
+template <bool HOURLY, class SEG, class SNOWSTATE>
+__device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &x, double airtmp, double prec) {
     const LandLaunch &L = s.L;
     const double delt = L.delt, delt60 = L.delt60;
     const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
@@ -94,7 +117,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
             rainf = 0.0;
             if (hrfg || fprfg) {
                 const double rdcsn = s.par(P_RDCSN);
-                const double a = airtmp / 100.0;
+                const double a = HDIV(airtmp, 100.0);
                 w.rdnsn = airtmp > 0.0 ? rdcsn + a * a : rdcsn;
             }
         } else {
@@ -124,7 +147,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
         // ---- EFFPRC (SNOW.py:302-317)
         if (snowf > 0.0) {
             w.packf += snowf;
-            w.pdepth += (snowf / w.rdnsn);
+            w.pdepth += HDIV(snowf, w.rdnsn);
             if (w.packf > w.covinx) w.covinx = w.packf > covind ? covind : w.packf;
             if (!snop) {
                 const double d = 1000.0 * snowf;
@@ -139,7 +162,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
 
         // ---- COMPAC (SNOW.py:319-326)
         if (iregfg) {
-            w.rdenpf = w.packf / w.pdepth;
+            w.rdenpf = HDIV(w.packf, w.pdepth);
             const double d = 1.0 - (0.00002 * delt60 * w.pdepth * (0.55 - w.rdenpf));
             w.compct = w.rdenpf < 0.55 ? d : 1.0;
         }
@@ -160,7 +183,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
                 w.packi = 0.0;
                 w.packf = 0.0;
             } else {
-                w.pdepth *= (1.0 - w.snowep / w.packf);
+                w.pdepth *= (1.0 - HDIV(w.snowep, w.packf));
                 w.packf -= w.snowep;
                 snowe = w.snowep;
                 if (w.packi > w.packf) w.packi = w.packf;
@@ -173,9 +196,9 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
                 const double factr = s.par(P_CCFACT) * 0.00026 * winmov;
                 double d = 8.59 * (w.vap - 6.108);
                 const double condht = w.vap > 6.108 ? d * factr : 0.0;
-                d = reltmp * (1.0 - 0.3 * s.par(P_MELEV) / 10000.0) * factr;
+                d = reltmp * (1.0 - HDIV(0.3 * s.par(P_MELEV), 10000.0)) * factr;
                 const double convht = airtmp > 32.0 ? d : 0.0;
-                d = sqrt(w.dull / 24.0);
+                d = sqrt(HDIV(w.dull, 24.0));
                 const double summer = py_max(0.45, 0.80 - 0.10 * d);
                 const double winter = py_max(0.60, 0.85 - 0.07 * d);
                 w.albedo = (s.calfl & HSP2G_CAL_SEASON) ? summer : winter;
@@ -186,14 +209,14 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
                 double lng = reltmp > 0.0 ? long1 : long2;
                 if (lng < 0.0) lng *= w.skyclr;
                 const double shrt = s.forcing(F_SOLRAD) * (1.0 - w.albedo) * (1.0 - shade);
-                w.mostht = (shrt + lng) / 203.2 + convht + condht;
+                w.mostht = HDIV(shrt + lng, 203.2) + convht + condht;
             } else  // ---- DEGDAY (SNOW.py:380); KMELT*delt/1440 as in SNOW.py:145
                 w.mostht = (s.daily(FB_M_KMELT, M_KMELT, P_KMELT) * delt / 1440.0) * (airtmp - s.par(P_TBASE));
         }
-        const double rnsht = rainf > 0.0 ? reltmp * rainf / 144.0 : 0.0;
+        const double rnsht = rainf > 0.0 ? HDIV(reltmp * rainf, 144.0) : 0.0;
         double sumht = w.mostht + rnsht;
         if (w.snocov < 1.0) sumht = sumht * w.snocov;
-        w.paktmp = w.neghts <= 0.0 ? 32.0 : 32.0 - w.neghts / (0.00695 * w.packf);
+        w.paktmp = w.neghts <= 0.0 ? 32.0 : 32.0 - HDIV(w.neghts, 0.00695 * w.packf);
 
         // ---- COOLER (SNOW.py:391-399)
         if (iregfg) {
@@ -239,7 +262,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
             w.packi = 0.0;
         } else if (sumht > 0.0) {
             melt = sumht;
-            w.pdepth *= (1.0 - melt / w.packf);
+            w.pdepth *= (1.0 - HDIV(melt, w.packf));
             w.packf -= melt;
             if (w.packi > w.packf) w.packi = w.packf;
         } else
@@ -248,7 +271,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
         // ---- LIQUID (SNOW.py:443-458)
         if (iregfg && w.packf > 0.0) {
             const double mwater = s.par(P_MWATER);
-            w.rdenpf = w.packf / w.pdepth;
+            w.rdenpf = HDIV(w.packf, w.pdepth);
             if (w.rdenpf <= 0.6)
                 w.packwc = mwater;
             else {
@@ -313,7 +336,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
             w.pdepth = 0.0;
             w.neghts = 0.0;
         } else {
-            const double d = 1.0 - (w.gmeltr / w.packf);
+            const double d = 1.0 - HDIV(w.gmeltr, w.packf);
             w.packw += w.gmeltr;
             w.pdepth *= d;
             w.neghts *= d;
@@ -323,9 +346,9 @@ __device__ __forceinline__ void snow_step(const SEG &s, SnowState &w, SnowFlux &
 
         // ---- pack bookkeeping / pack vanishes (SNOW.py:511-537)
         if (w.packf > 0.005) {
-            w.rdenpf = w.packf / w.pdepth;
-            w.paktmp = w.neghts == 0.0 ? 32.0 : 32.0 - w.neghts / (0.00695 * w.packf);
-            w.snocov = w.packf < w.covinx ? w.packf / w.covinx : 1.0;
+            w.rdenpf = HDIV(w.packf, w.pdepth);
+            w.paktmp = w.neghts == 0.0 ? 32.0 : 32.0 - HDIV(w.neghts, 0.00695 * w.packf);
+            w.snocov = w.packf < w.covinx ? HDIV(w.packf, w.covinx) : 1.0;
         } else {
             melt += w.packf;
             wyield += w.packf + w.packw;

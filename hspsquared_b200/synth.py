@@ -79,6 +79,15 @@ class Ensemble:
         e.u_prec, e.u_airt, e.u_pet = self.u_prec[lo:hi], self.u_airt[lo:hi], self.u_pet[lo:hi]
         return e
 
+    def take(self, idx):
+        """The segments `idx` (any order) of this ensemble as an ensemble of their own."""
+        idx = np.asarray(idx)
+        e = copy.copy(self)
+        e.n = len(idx)
+        e.factor = {k: v[idx] for k, v in self.factor.items()}
+        e.u_prec, e.u_airt, e.u_pet = self.u_prec[idx], self.u_airt[idx], self.u_pet[idx]
+        return e
+
     def tables_of(self, i):
         t = copy.deepcopy(self.base)
         for (sec, grp, nm), f in self.factor.items():

@@ -14,6 +14,7 @@
 #define __constant__
 #define __shared__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
