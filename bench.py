@@ -3,8 +3,9 @@
 
 Workload (BASELINE.json configs[1]): test10 PERLND 1, SNOW+PWATER, replicated to 100,000 segments per GPU with jittered
 parameters, 10-year hourly synthetic met, default SAVE set (13 SNOW + 11 PWATER series).
-One "step" = one time chunk of `--chunk` intervals over all segments of the rank; steps walk forward through simulated
-time, state carried.  Forcings of every timed step are resident in HBM before the timed region (each chunk is ~2.5 GB,
+One "step" = one time chunk of `--chunk` intervals (default 438: the default 20 timed steps are exactly one simulated year,
+so the number averages the cheap summer intervals and the expensive snow / melt ones) over all segments of the rank; steps
+walk forward through simulated time, state carried.  Forcings of every timed step are resident in HBM before the timed region (each chunk is ~2.5 GB,
 far larger than the 126 MB L2, so nothing is served from cache between steps).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -94,6 +95,19 @@ def measured_peak():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def measured_traffic(kernel, n, Tc):
+    """DRAM bytes per launch of this kernel at this size from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            for e in json.load(f):
+                if e["kernel"] == kernel and e["segments"] == n and e["intervals"] == Tc:
+                    return e["dram_bytes_per_launch"], e["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -208,9 +222,9 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
     sees identical bits.  Lanes past n in the last tile copy the last segment."""
     from hspsquared_b200 import synth
 
-    s = synth.shared_series("PERLND", cal, t0, nsteps)
+    s = synth.shared_series(ens.operation, cal, t0, nsteps)
     n = ens.n
-    f = torch.zeros((nsteps, 6, npad), dtype=torch.float64, device=dev)
+    f = torch.zeros((nsteps, len(rows), npad), dtype=torch.float64, device=dev)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     airt = T(s["AIRTMP"])[:, None] + T(3.0 * ens.u_airt)[None, :]
     for r, nm in enumerate(rows):
@@ -218,7 +232,7 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
             f[:, r, :n] = T(s["PREC"])[:, None] * T(1.0 + 0.2 * ens.u_prec)[None, :]
         elif nm == "PETINP":
             f[:, r, :n] = T(s["PETINP"])[:, None] * T(1.0 + 0.1 * ens.u_pet)[None, :]
-        elif nm == "AIRTMP":
+        elif nm in ("AIRTMP", "GATMP"):
             f[:, r, :n] = airt
         elif nm == "DTMPG":
             f[:, r, :n] = airt - 5.0
@@ -226,7 +240,7 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
             f[:, r, :n] = T(s[nm])[:, None]
     if npad > n:
         f[:, :, n:] = f[:, :, n - 1:n]
-    return f.view(nsteps, 6, npad // 32, 32).permute(2, 0, 1, 3).contiguous()
+    return f.view(nsteps, len(rows), npad // 32, 32).permute(2, 0, 1, 3).contiguous()
 
 
 def main():
@@ -236,7 +250,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--segments", type=int, default=N_SEG_PER_GPU, help="segments per GPU")
-    ap.add_argument("--chunk", type=int, default=512, help="intervals per step")
+    ap.add_argument("--chunk", type=int, default=438,
+                    help="intervals per step; the default makes the default 20 timed steps exactly one simulated year "
+                         "(8,760 hourly intervals), so the figure is an annual average over snow, melt and summer regimes")
     ap.add_argument("--sub", type=int, default=None, help="intervals per (tile, sub-chunk) task; default = library's")
     ap.add_argument("--order", default="none", help="experiment: order segments by a jitter key (airt, prec, ...)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -322,6 +338,7 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     l1, _ = batch.kernel_stats()
+    kname = batch.kernel_name()
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,6 +381,7 @@ def main():
         e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier)
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = measured_traffic(kname, n, Tc)
     avg_launch_s = ms * 1e-3 / K
     achieved = BYTES_PER_SEGSTEP * n * Tc / avg_launch_s / 1e9
     line = {
@@ -375,9 +393,9 @@ def main():
                    "segments_per_gpu": n, "intervals_per_step": Tc, "forcings": 6, "saved_series": 24,
                    "cache": "inputs of every step (%.2f GB) and outputs (%.2f GB) are far larger than L2; %d distinct "
                             "forcing chunks resident" % (per_f / 1e9, Tc * ns * npad * 8 / 1e9, len(forc)),
-                   "kernel": batch.kernel_name(), "parallelism": "segments sharded over %d GPU(s), no collective" % world},
+                   "kernel": kname, "parallelism": "segments sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SEGSTEP * n * Tc,
                      "avg_launch_ms": avg_launch_s * 1e3},
         "gpu_launches": int(l1 - l0),

@@ -14,12 +14,13 @@ import os
 
 import numpy as np
 
-from . import test10
-from .segstore import SegmentStore, broadcast, effective
+from . import cbp, test10
+from .segstore import INIT_DEFAULT, RAW_DEFAULT, SegmentStore, broadcast, effective
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "test10_met_1976.npz")
 PERLND_FORCINGS = ("PREC", "PETINP", "AIRTMP", "WINMOV", "SOLRAD", "DTMPG")  # north_star list, 48 B / interval
 IMPLND_FORCINGS = PERLND_FORCINGS
+FULLCHAIN_FORCINGS = ("GATMP", "PREC", "PETINP", "WINMOV", "SOLRAD", "DTMPG")  # ATEMP on: gage temperature in
 
 JITTER = {
     "PERLND": {
@@ -38,8 +39,28 @@ JITTER = {
 CLIP = {"AGWRC": (None, 0.999), "IRC": (0.3, 0.85), "SHADE": (0.0, 0.8)}
 
 
-def base_tables(operation, sections=None):
-    t = test10.perlnd() if operation == "PERLND" else test10.implnd()
+# BASELINE.json configs[3] "register / divergence stress": each option flag is drawn per segment
+CBP_OPTIONS = (
+    ("RTOPFG", (("PWATER", "PARAMETERS", {"RTOPFG": 1}), ("PWATER", "PARAMETERS", {"RTOPFG": 0}))),
+    ("UZFG", (("PWATER", "PARAMETERS", {"UZFG": 0}), ("PWATER", "PARAMETERS", {"UZFG": 1}))),
+    ("SNOPFG", (("SNOW", "FLAGS", {"SNOPFG": 0}), ("SNOW", "FLAGS", {"SNOPFG": 1}))),
+    ("ICEFG", (("SNOW", "FLAGS", {"ICEFG": 1}), ("SNOW", "FLAGS", {"ICEFG": 0}))),
+    ("TSOPFG", (("PSTEMP", "PARAMETERS", {"TSOPFG": 1}),
+                ("PSTEMP", "PARAMETERS", {"TSOPFG": 0, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5, "BSLT": 0.365,
+                                          "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0}),
+                ("PSTEMP", "PARAMETERS", {"TSOPFG": 2, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5, "BSLT": 0.365,
+                                          "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0}))),
+)
+
+
+def base_tables(operation, sections=None, base="test10"):
+    if base == "cbp":
+        if operation != "PERLND":
+            raise ValueError("the CBP base segment is a PERLND")
+        t = cbp.perlnd()
+        t["SNOW"]["PARAMETERS"].setdefault("KMELT", 0.05)  # read when SNOPFG=1 is drawn
+    else:
+        t = test10.perlnd() if operation == "PERLND" else test10.implnd()
     if sections is not None:
         for a in t["ACTIVITY"]:
             t["ACTIVITY"][a] = int(a in sections)
@@ -56,10 +77,14 @@ def _clip(name, v):
 class Ensemble:
     """n jittered replicas of a base segment; `tables_of(i)` gives segment i back as UCI tables for the oracle."""
 
-    def __init__(self, operation, n, seed=1234, sections=None):
+    def __init__(self, operation, n, seed=1234, sections=None, base="test10", options=()):
+        """options: names from CBP_OPTIONS whose value is drawn uniformly per segment (categorical flags)."""
         self.operation, self.n, self.seed = operation, int(n), seed
-        self.base = base_tables(operation, sections)
+        self.base = base_tables(operation, sections, base)
         rng = np.random.default_rng(seed)
+        self.options = tuple(o for o in CBP_OPTIONS if o[0] in options)
+        if len(self.options) != len(tuple(options)):
+            raise KeyError("unknown option in %r" % (options,))
         self.factor = {}
         for sec, groups in JITTER[operation].items():
             if not self.base["ACTIVITY"].get(sec, 0):
@@ -70,6 +95,17 @@ class Ensemble:
         self.u_prec = rng.uniform(-1.0, 1.0, self.n)
         self.u_airt = rng.uniform(-1.0, 1.0, self.n)
         self.u_pet = rng.uniform(-1.0, 1.0, self.n)
+        # drawn last, so ensembles without options keep the numbers they always had
+        self.choice = np.stack([rng.integers(0, len(alts), self.n) for _nm, alts in self.options]) if self.options \
+            else np.zeros((0, self.n), dtype=np.int64)
+
+    def _variant_tables(self, combo):
+        t = copy.deepcopy(self.base)
+        for (_nm, alts), k in zip(self.options, combo):
+            sec, grp, kv = alts[int(k)]
+            if sec in t:
+                t[sec].setdefault(grp, {}).update(kv)
+        return t
 
     def shard(self, lo, hi):
         """Segments [lo, hi) of this ensemble as an ensemble of their own (multi-GPU sharding)."""
@@ -77,6 +113,7 @@ class Ensemble:
         e.n = hi - lo
         e.factor = {k: v[lo:hi] for k, v in self.factor.items()}
         e.u_prec, e.u_airt, e.u_pet = self.u_prec[lo:hi], self.u_airt[lo:hi], self.u_pet[lo:hi]
+        e.choice = self.choice[:, lo:hi]
         return e
 
     def take(self, idx):
@@ -86,10 +123,11 @@ class Ensemble:
         e.n = len(idx)
         e.factor = {k: v[idx] for k, v in self.factor.items()}
         e.u_prec, e.u_airt, e.u_pet = self.u_prec[idx], self.u_airt[idx], self.u_pet[idx]
+        e.choice = self.choice[:, idx]
         return e
 
     def tables_of(self, i):
-        t = copy.deepcopy(self.base)
+        t = self._variant_tables(self.choice[:, i])
         for (sec, grp, nm), f in self.factor.items():
             t[sec][grp][nm] = float(_clip(nm, t[sec][grp][nm] * f[i]))
             key = "MONTHLY_" + nm
@@ -99,8 +137,10 @@ class Ensemble:
 
     def store(self, calendar):
         """Vectorised build: effective values of the base, broadcast, jittered column-wise."""
-        eff = effective(self.operation, copy.deepcopy(self.base))
-        arrs = broadcast(eff, self.n)
+        if self.options:
+            arrs = self._variant_arrays()
+        else:
+            arrs = broadcast(effective(self.operation, copy.deepcopy(self.base)), self.n)
         for (sec, grp, nm), f in self.factor.items():
             base = self.base[sec][grp][nm]
             col = _clip(nm, base * f)
@@ -112,6 +152,30 @@ class Ensemble:
                 tab = np.array(list(self.base[sec]["MONTHLY_" + nm].values()), dtype=np.float64)
                 arrs["mon"][nm] = _clip(nm, tab[:, None] * f[None, :])
         return SegmentStore.build(self.operation, arrs, calendar)
+
+    def _variant_arrays(self):
+        """broadcast() for an ensemble with categorical options: effective() once per distinct combination, then a
+        gather by each segment's combination index (no per-segment Python)."""
+        combos, inv = np.unique(self.choice.T, axis=0, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        effs = [effective(self.operation, self._variant_tables(c)) for c in combos]
+        act = effs[0]["act"]
+        if any(e["act"] != act for e in effs):
+            raise ValueError("options must not change the activity mask")
+
+        def gather(group, default, dtype):
+            out = {}
+            for k in set().union(*[e[group].keys() for e in effs]):
+                vals = np.array([e[group].get(k, default[k] if default is not None else 0) for e in effs], dtype=dtype)
+                out[k] = vals[inv]
+            return out
+
+        mon = {}
+        for k in set().union(*[e["mon"].keys() for e in effs]):
+            tabs = np.stack([np.asarray(e["mon"].get(k, np.zeros(12)), dtype=np.float64) for e in effs])  # [combo][12]
+            mon[k] = np.ascontiguousarray(tabs[inv].T)
+        return {"act": act, "n": self.n, "raw": gather("raw", RAW_DEFAULT, np.float64),
+                "flag": gather("flag", None, np.uint64), "init": gather("init", INIT_DEFAULT, np.float64), "mon": mon}
 
 
 _met = {}
@@ -157,7 +221,7 @@ def forcing_chunk(ens, calendar, t0, nsteps, names=PERLND_FORCINGS, out=None):
             out[:, r, :] = s["PREC"][:, None] * (1.0 + 0.2 * ens.u_prec)[None, :]
         elif nm == "PETINP":
             out[:, r, :] = s["PETINP"][:, None] * (1.0 + 0.1 * ens.u_pet)[None, :]
-        elif nm == "AIRTMP":
+        elif nm in ("AIRTMP", "GATMP"):
             out[:, r, :] = airt
         elif nm == "DTMPG":
             out[:, r, :] = airt - 5.0
@@ -170,5 +234,6 @@ def forcing_of(ens, calendar, i, t0, nsteps):
     """{name: float64[nsteps]} forcings of segment i (what forcing_chunk puts in column i), for the oracle."""
     s = shared_series(ens.operation, calendar, t0, nsteps)
     airt = s["AIRTMP"] + 3.0 * ens.u_airt[i]
+    tname = "GATMP" if ens.base["ACTIVITY"].get("ATEMP", 0) else "AIRTMP"  # ATEMP on: the series is the gage's
     return {"PREC": s["PREC"] * (1.0 + 0.2 * ens.u_prec[i]), "PETINP": s["PETINP"] * (1.0 + 0.1 * ens.u_pet[i]),
-            "AIRTMP": airt, "DTMPG": airt - 5.0, "WINMOV": s["WINMOV"].copy(), "SOLRAD": s["SOLRAD"].copy()}
+            tname: airt, "DTMPG": airt - 5.0, "WINMOV": s["WINMOV"].copy(), "SOLRAD": s["SOLRAD"].copy()}

@@ -140,6 +140,60 @@ def test_headline_static_kernels_are_selected():
     assert np.array_equal(orev[:, ::-1, :], o64, equal_nan=True)
 
 
+def test_categorical_fullchain_ensemble():
+    """BASELINE.json configs[3] shape (full PERLND chain, option flags drawn per segment => divergent warps) on the GPU:
+    sampled segments against the oracle on their own tables (<= 1e-9, error counts exact), and divergence-aware ordering
+    (sort_by_flags) must only permute columns, bit for bit."""
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar("1976-02-20", "1976-03-20", 60, "us")
+    steps, n = cal.steps, 5000
+    ens = synth.Ensemble("PERLND", n, seed=99, base="cbp", options=("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, steps, names=names)
+    with LandBatch(ens.store(cal), cal, names, "all") as b:
+        out = b.run(f, chunk=250)
+        save, errs = b.save, b.errors()
+    assert len(save) == 84
+    for i in (0, 1234, 2500, 3777, n - 1):
+        si = {"start": cal.start, "stop": cal.stop, "delt": 60, "units": 1, "steps": steps, "time_unit": "us"}
+        ts = synth.forcing_of(ens, cal, i, 0, steps)
+        e = CASES.run_segment("PERLND", ens.tables_of(i), ts, si, parity.ORACLE_ACTS)
+        for r, full in enumerate(save):
+            err = parity.rel_err(out[:, r, i], ts[full.split("_", 1)[1]])
+            assert err <= parity.RTOL, (i, full, err)
+        assert np.array_equal(e["PWATER"], np.array([errs["PWATER%d" % j][i] for j in range(10)]))
+        assert np.array_equal(e["PSTEMP"], np.array([errs["PSTEMP%d" % j][i] for j in range(6)]))
+    store = ens.store(cal)
+    perm = store.sort_by_flags()
+    with LandBatch(store, cal, names, "all") as b:
+        out2 = b.run(np.ascontiguousarray(f[:, :, perm]), chunk=250)
+    assert np.array_equal(out2, out[:, :, perm], equal_nan=True)
+
+
+def test_water_balance_at_full_size():
+    """Size-independent property at BASELINE.json configs[1] size (100,000 jittered segments): over any window the
+    PWATER budget closes, SUPY + lateral inflow (0) = PERO + IGWI + TAET + change of PERS, per segment."""
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar("1976-01-01", "1976-01-09", 60, "ns")
+    steps, n = cal.steps, 100000
+    ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+    save = ["PWATER_SUPY", "PWATER_PERO", "PWATER_IGWI", "PWATER_TAET", "PWATER_PERS"]
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+        out = b.run(synth.forcing_chunk(ens, cal, 0, steps), chunk=96)
+        assert not any(v.any() for v in b.errors().values())
+    supy, pero, igwi, taet, pers = (out[:, r, :] for r in range(5))
+    lhs = supy[1:].sum(axis=0)
+    rhs = pero[1:].sum(axis=0) + igwi[1:].sum(axis=0) + taet[1:].sum(axis=0) + (pers[-1] - pers[0])
+    scale = np.maximum(pers[0], 1.0)
+    assert np.abs(lhs - rhs).max() / scale.max() < 1e-12, np.abs(lhs - rhs).max()
+
+
 def test_hspf_known_answers(golden_dir):
     """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
     hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))

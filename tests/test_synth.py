@@ -59,3 +59,37 @@ def test_ensemble_matches_oracle_per_segment():
         for r, full in enumerate(save):
             k = full.split("_", 1)[1]
             assert np.array_equal(out[:, r, i], ts[k], equal_nan=True), (i, k)
+
+
+def test_categorical_fullchain_ensemble_matches_oracle_and_sorting_is_invisible():
+    """BASELINE.json configs[3]: full PERLND chain on the CBP base with option flags drawn per segment.  Every segment
+    equals the oracle run on its own tables bit for bit, and divergence-aware ordering (SegmentStore.sort_by_flags)
+    only permutes columns."""
+    cal = Calendar("1976-02-20", "1976-04-05", 60, "us")
+    steps = cal.steps
+    opts = ("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG")
+    ens = synth.Ensemble("PERLND", 100, seed=99, base="cbp", options=opts)
+    assert len(np.unique(ens.choice.T, axis=0)) > 20
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, steps, names=names)
+    store = ens.store(cal)
+    assert len(np.unique(store.flags)) > 20
+    with LandBatch(store, cal, names, "all") as b:
+        out = b.run(f, chunk=300)
+        save = b.save
+        errs = b.errors()
+    assert len(save) == 84  # AIRTMP + 22 SNOW + 31 PWATER + 5 SEDMNT + 4 PSTEMP + 21 PWTGAS (SURVEY.md 8d)
+    for i in (0, 17, 42, 77, 99):
+        si = {"start": cal.start, "stop": cal.stop, "delt": 60, "units": 1, "steps": steps, "time_unit": "us"}
+        ts = synth.forcing_of(ens, cal, i, 0, steps)
+        e = CASES.run_segment("PERLND", ens.tables_of(i), ts, si, parity.ORACLE_ACTS)
+        for r, full in enumerate(save):
+            k = full.split("_", 1)[1]
+            assert np.array_equal(out[:, r, i], ts[k], equal_nan=True), (i, k)
+        assert np.array_equal(e["PWATER"], np.array([errs["PWATER%d" % j][i] for j in range(10)]))
+    sorted_store = ens.store(cal)
+    perm = sorted_store.sort_by_flags()
+    assert np.all(np.diff(sorted_store.flags.astype(np.int64)) >= 0)
+    with LandBatch(sorted_store, cal, names, "all") as b:
+        out2 = b.run(np.ascontiguousarray(f[:, :, perm]), chunk=300)
+    assert np.array_equal(out2, out[:, :, perm], equal_nan=True)

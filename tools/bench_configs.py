@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Throughput of the other BASELINE.json configurations on one GPU (device-resident forcings, CUDA events on the launching
+stream) -- the numbers quoted in profiles/ and DESIGN.md beside the headline that bench.py measures.  Not a driver contract.
+
+    python tools/bench_configs.py [implnd] [fullchain] [fullchain_sorted] [perlnd_1m] [perlnd_flows] ...
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (device_forcing, measured_peak, default_save)
+
+
+def run(name, torch, dev):
+    from hspsquared_b200 import synth, test10
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar(bench.RUN_START, bench.RUN_STOP, 60, "ns")
+    K, W, Tc = 8, 3, 256
+    note = ""
+    if name == "implnd":  # IMPLND SNOW+IWATER, default SAVE (13 + 3)
+        n = 100_000
+        ens = synth.Ensemble("IMPLND", n, seed=1234, sections=("SNOW", "IWATER"))
+        forcings = list(synth.IMPLND_FORCINGS)
+        save = ["SNOW_" + x for x in test10.SAVE_DEFAULT["SNOW"]] + ["IWATER_" + x for x in test10.SAVE_DEFAULT["IWATER"]]
+    elif name in ("fullchain", "fullchain_sorted", "fullchain_cbp10"):  # configs[3]
+        n = 250_000
+        ens = synth.Ensemble("PERLND", n, seed=1234, base="cbp", options=("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG"))
+        forcings = list(synth.FULLCHAIN_FORCINGS)
+        save = "all"
+        if name == "fullchain_cbp10":
+            save = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "SEDMNT_SOSED", "PWTGAS_SOHT", "PWTGAS_IOHT",
+                    "PWTGAS_AOHT", "PWTGAS_SODOXM", "PWTGAS_IODOXM", "PWTGAS_AODOXM"]
+        Tc = 128
+    elif name == "perlnd_1m":  # north_star target size: 1 M segments, SNOW+PWATER default SAVE
+        n = 1_000_000
+        ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+        forcings, save, Tc = list(synth.PERLND_FORCINGS), bench.default_save(), 64
+    elif name == "perlnd_flows":  # CBP-style: only the three runoff components leave the device
+        n = 100_000
+        ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+        forcings, save = list(synth.PERLND_FORCINGS), ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO"]
+    elif name == "perlnd_all":
+        n = 100_000
+        ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+        forcings, save = list(synth.PERLND_FORCINGS), "all"
+    else:
+        raise SystemExit("unknown config %r" % name)
+    store = ens.store(cal)
+    perm = None
+    if name == "fullchain_sorted":
+        perm = store.sort_by_flags()
+        ens = ens.take(perm)
+        note = "segments ordered by option word (SegmentStore.sort_by_flags)"
+    batch = LandBatch(store, cal, forcings, save, device=dev.index or 0)
+    npad, nf, ns = batch.npad, batch.nf, batch.ns
+    forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(K + W)]
+    outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    for c in range(W):
+        batch.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for c in range(W, W + K):
+        batch.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    peak, _src = bench.measured_peak()
+    B = 8 * (nf + ns)
+    value = n * Tc * K / (ms * 1e-3)
+    line = {"config": name, "kernel": batch.kernel_name(), "segments": n, "intervals_per_step": Tc, "steps": K,
+            "forcing_rows": nf, "saved_rows": ns, "bytes_per_segment_interval": B, "ms_per_step": ms / K,
+            "segment_timesteps_per_s": value, "algorithmic_GBps": value * B / 1e9, "frac_of_measured_hbm": value * B / 1e9 / peak,
+            "errors_nonzero": {k: int((v != 0).sum()) for k, v in batch.errors().items() if (v != 0).any()}, "note": note}
+    batch.close()
+    del forc, outs
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    import torch
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    for name in sys.argv[1:] or ["implnd", "perlnd_flows", "perlnd_all", "fullchain", "fullchain_sorted", "fullchain_cbp10", "perlnd_1m"]:
+        print(json.dumps(run(name, torch, dev)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
