@@ -49,6 +49,15 @@ typedef StaticIO<FM_MET6, SAVE_PWATER_FLOWS(olo), SAVE_PWATER_FLOWS(ohi)> IO_Sno
 typedef StaticIO<FM_MET6, SAVE_SNOW_DEFAULT(olo) | SAVE_IWATER_DEFAULT(olo), SAVE_SNOW_DEFAULT(ohi) | SAVE_IWATER_DEFAULT(ohi)>
     IO_SnowIwaterDefault;
 
+// full PERLND chain (BASELINE.json configs[3]): every output of the six sections, or the ten series a CBP land-segment
+// UCI sends to its river model (tests/land_spec/hwmA51800.uci:493-502)
+#define SAVE_CBP10(B)                                                                                             \
+    (B(O_PWATER_SURO) | B(O_PWATER_IFWO) | B(O_PWATER_AGWO) | B(O_SEDMNT_SOSED) | B(O_PWTGAS_SOHT) |              \
+     B(O_PWTGAS_IOHT) | B(O_PWTGAS_AOHT) | B(O_PWTGAS_SODOXM) | B(O_PWTGAS_IODOXM) | B(O_PWTGAS_AODOXM))
+typedef StaticIO<FM_MET6_GATMP, range_lo(O_ATEMP_AIRTMP, O_IWATER_IMPEV), range_hi(O_ATEMP_AIRTMP, O_IWATER_IMPEV)>
+    IO_FullChainAll;
+typedef StaticIO<FM_MET6_GATMP, SAVE_CBP10(olo), SAVE_CBP10(ohi)> IO_FullChainCbp10;
+
 // does the launch record describe exactly this static configuration (rows in ascending id order)?
 template <class IO>
 static inline bool io_matches(const LandLaunch &L) {

@@ -50,6 +50,10 @@
     (PBIT(INFILT_IVL) | PBIT(KVARY) | PBIT(LZSN) | PBIT(FOREST) | PBIT(PETMAX) | PBIT(PETMIN) | PBIT(FZG) |         \
      PBIT(FZGL) | PBIT(DEEPFR) | PBIT(KGW) | PBIT(BASETP) | PBIT(AGWETP) | PBIT(INFEXP) | PBIT(INFILD))
 #define HOT_IWATER (PBIT(PETMAX) | PBIT(PETMIN))
+// full PERLND chain: ATEMP / SEDMNT / PWTGAS constants read on every (wet) interval
+#define HOT_CHAIN                                                                                                  \
+    (PBIT(ELDAT) | PBIT(SMPF) | PBIT(KRER) | PBIT(JRER) | PBIT(KSER) | PBIT(JSER) | PBIT(KGER) | PBIT(JGER) |       \
+     PBIT(ELEVGC) | PBIT(SLIFAC) | PBIT(ILIFAC) | PBIT(ALIFAC))
 static_assert(HSP2G_NPAR <= 64, "hot-parameter masks are 64 bits");
 
 struct __align__(32) CalStep {
@@ -149,7 +153,9 @@ struct ColdW {
 #define NCOLD_SNOW 12
 #define NCOLD_SNOW2 7
 #define NCOLD_PWATER 12
-#define NCOLD_MAX (NCOLD_SNOW + NCOLD_SNOW2 + NCOLD_PWATER)
+#define NCOLD_PSTEMP 6
+#define NCOLD_PWTGAS 4
+#define NCOLD_CHAIN (NCOLD_PSTEMP + NCOLD_PWTGAS)
 
 // One out-of-line copy of pow's argument screening + __internal_accurate_pow instead of one per call site (17 sites,
 // ~100 SASS instructions each): the March step of profiles/r1g spent 40 % of its stall samples waiting for

@@ -22,8 +22,12 @@
 #include "sedmnt.cuh"
 #include "snow.cuh"
 
-#define PERLND_HOT (HOT_SNOW | HOT_PWATER)
 #define IMPLND_HOT (HOT_SNOW | HOT_IWATER)
+#define CHAIN_ACTS (HSP2G_ACT_ATEMP | HSP2G_ACT_SEDMNT | HSP2G_ACT_PSTEMP | HSP2G_ACT_PWTGAS)
+// shared-memory plan of a PERLND kernel instantiation: hot-parameter set and cold-state rows depend on whether the
+// sections beyond SNOW+PWATER can run (ACT_CT < 0: any mask)
+__host__ __device__ constexpr bool perlnd_has_chain(int act_ct) { return act_ct < 0 || (act_ct & (int)CHAIN_ACTS) != 0; }
+__host__ __device__ constexpr unsigned long long perlnd_hot(int act_ct) { return HOT_SNOW | HOT_PWATER | (perlnd_has_chain(act_ct) ? HOT_CHAIN : 0ull); }
 #define OPT_SED_RAIN_IS_PREC 1u  // SEDMNT: no RAINF in ts -> RAIN = PREC (SEDMNT.py:86-89)
 
 #ifdef HSP2G_HOST_EMU
@@ -61,9 +65,9 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, PERLND_HOT> SegT;
+    typedef Seg<IO, perlnd_hot(ACT_CT)> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
-    constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER;
+    constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER + (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
     Pipe pipe;
     pipe.init(smem, wib, lane, nf, SegT::NHOT, NCOLD);
     Sched sched(L, lane, wib);
@@ -79,6 +83,11 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
         double *cold = pipe.hot_area() + SegT::NHOT * LAND_TILE + lane;
         sw.bind(cold, s.sb);
         pw.bind(cold + SnowStateT<SNOWCOLD>::SMEM_ROWS * LAND_TILE, s.sb);
+        PwtgasDaily pg;
+        if (perlnd_has_chain(ACT_CT)) {
+            ps.bind(cold + (SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER) * LAND_TILE);
+            pg.bind(cold + (SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER + NCOLD_PSTEMP) * LAND_TILE);
+        }
         if (act & HSP2G_ACT_SNOW) sw.load(s);
         if (act & HSP2G_ACT_PWATER) pw.load(s);
         if (act & HSP2G_ACT_SEDMNT) sd.load(s);
@@ -120,7 +129,9 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
                 sedmnt_step(s, sd, rain, prec, link.snocov, fx.suro, fx.surs);
             }
             SoilTemps soil;
+            const bool newday = t == t0 || (s.calfl & HSP2G_CAL_NEWDAY);
             if (act & HSP2G_ACT_PSTEMP) {
+                if (newday) ps.refresh_daily(s);
                 if (L.first_chunk && t == 0) ps.airts = airtmp;  // PSTEMP.py:128
                 pstemp_step<HOURLY>(s, ps, airtmp, soil);
             } else {
@@ -128,7 +139,10 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
                 soil.ultmp = s.forcing(F_ULTMP);
                 soil.lgtmp = s.forcing(F_LGTMP);
             }
-            if (act & HSP2G_ACT_PWTGAS) pwtgas_step(s, soil, link.wyield, fx.suro, fx.ifwo, fx.agwo);
+            if (act & HSP2G_ACT_PWTGAS) {
+                if (newday) pg.refresh_daily(s);
+                pwtgas_step(s, pg, soil, link.wyield, fx.suro, fx.ifwo, fx.agwo);
+            }
             s.end_step();
             pipe.release(t);
         }
@@ -200,9 +214,10 @@ static inline size_t land_smem_bytes(int nf, unsigned long long hot, int ncold) 
     return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + ncold) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
 }
 // cold-state rows of a kernel instantiation (must mirror the NCOLD constants inside the kernels)
-template <bool HOURLY, class IO>
+template <bool HOURLY, class IO, int ACT_CT>
 static inline int perlnd_ncold() {
-    return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS + NCOLD_PWATER;
+    return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS + NCOLD_PWATER +
+           (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
 }
 template <bool HOURLY, class IO>
 static inline int implnd_ncold() {

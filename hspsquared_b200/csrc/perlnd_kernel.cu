@@ -3,13 +3,16 @@
 #include "land_kernels.cuh"
 #include "launch.h"
 
+#ifndef HSP_MAXREG_CHAIN
+#define HSP_MAXREG_CHAIN 168  // full-chain kernels: 3 warps per SM sub-partition
+#endif
 #ifndef HSP_MAXREG_HOT
 #define HSP_MAXREG_HOT 128  // register cap of the specialised kernels: 4 warps per SM sub-partition (16 per SM), no spills
 #endif
 
 template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, PERLND_HOT, perlnd_ncold<HOURLY, IO>());
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>());
     auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
@@ -30,11 +33,19 @@ cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
         if (io_matches<IO_SnowPwaterFlows>(L))
             return launch_one<SP, true, IO_SnowPwaterFlows, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=flows3>", grid_out);
         if (io_matches<IO_SnowPwaterAll>(L))
-            return launch_one<SP, true, IO_SnowPwaterAll, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=all53>", grid_out);
+            return launch_one<SP, true, IO_SnowPwaterAll, 168>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=all53>", grid_out);
+    }
+    constexpr int FULL = (int)(HSP2G_ACT_ATEMP | HSP2G_ACT_SNOW | HSP2G_ACT_PWATER | HSP2G_ACT_SEDMNT | HSP2G_ACT_PSTEMP |
+                               HSP2G_ACT_PWTGAS);
+    if (L.act == (unsigned)FULL && hourly) {
+        if (io_matches<IO_FullChainAll>(L))
+            return launch_one<FULL, true, IO_FullChainAll, HSP_MAXREG_CHAIN>(L, sub_pref, st, name, "perlnd_kernel<full chain,hourly,save=all84>", grid_out);
+        if (io_matches<IO_FullChainCbp10>(L))
+            return launch_one<FULL, true, IO_FullChainCbp10, HSP_MAXREG_CHAIN>(L, sub_pref, st, name, "perlnd_kernel<full chain,hourly,save=cbp10>", grid_out);
     }
     if (L.act == (unsigned)SP)
-        return hourly ? launch_one<SP, true, DynIO, 128>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,io=dynamic>", grid_out)
-                      : launch_one<SP, false, DynIO, 128>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,subhourly,io=dynamic>", grid_out);
+        return hourly ? launch_one<SP, true, DynIO, 168>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,io=dynamic>", grid_out)
+                      : launch_one<SP, false, DynIO, 168>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,subhourly,io=dynamic>", grid_out);
     return hourly ? launch_one<-1, true, DynIO, 232>(L, sub_pref, st, name, "perlnd_kernel<generic,hourly,io=dynamic>", grid_out)
                   : launch_one<-1, false, DynIO, 232>(L, sub_pref, st, name, "perlnd_kernel<generic,subhourly,io=dynamic>", grid_out);
 }

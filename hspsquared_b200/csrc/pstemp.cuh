@@ -9,6 +9,23 @@
 
 struct PstempState {
     double sltmp, ultmp, lgtmp, airts;
+    // the six (optionally monthly) coefficients, interpolated once per simulated day instead of on every interval
+    // (PSTEMP.py:120-126 builds them as per-interval arrays that are constant within a day): shared memory
+    ColdD aslt, bslt, ultp1, ultp2, lgtp1, lgtp2;
+
+    __device__ __forceinline__ void bind(double *c) {
+        ColdD *m[NCOLD_PSTEMP] = {&aslt, &bslt, &ultp1, &ultp2, &lgtp1, &lgtp2};
+        for (int k = 0; k < NCOLD_PSTEMP; ++k) m[k]->p = c + k * LAND_TILE;
+    }
+    template <class SEG>
+    __device__ __forceinline__ void refresh_daily(const SEG &s) {
+        const int fb[6] = {FB_M_ASLT, FB_M_BSLT, FB_M_ULTP1, FB_M_ULTP2, FB_M_LGTP1, FB_M_LGTP2};
+        const int mid[6] = {M_ASLT, M_BSLT, M_ULTP1, M_ULTP2, M_LGTP1, M_LGTP2};
+        const int pid[6] = {P_ASLT, P_BSLT, P_ULTP1, P_ULTP2, P_LGTP1, P_LGTP2};
+        double v[6];
+        s.daily_batch(fb, mid, pid, v);
+        aslt = v[0]; bslt = v[1]; ultp1 = v[2]; ultp2 = v[3]; lgtp1 = v[4]; lgtp2 = v[5];
+    }
     template <class SEG>
     __device__ __forceinline__ void load(const SEG &s) {
         sltmp = s.st(S_SLTMP); ultmp = s.st(S_ULTMP); lgtmp = s.st(S_LGTMP); airts = s.st(S_AIRTS);
@@ -29,24 +46,24 @@ __device__ __forceinline__ void pstemp_step(const SEG &s, PstempState &w, double
     const double airtcs = (w.airts - 32.0) * 0.555;
     const double airtc = (airtmp - 32.0) * 0.555;
     if (hrfg) {
-        const double aslt = (s.daily(FB_M_ASLT, M_ASLT, P_ASLT) - 32.0) * 0.555;
-        const double bslt = s.daily(FB_M_BSLT, M_BSLT, P_BSLT);
+        const double aslt = (w.aslt - 32.0) * 0.555;
+        const double bslt = w.bslt;
         w.sltmp = aslt + bslt * airtc;
     }
     if (s.flag(FB_TSOP1)) {
         if (hrfg) {
-            const double ault = (s.daily(FB_M_ULTP1, M_ULTP1, P_ULTP1) - 32.0) * 0.5555;
-            const double bult = s.daily(FB_M_ULTP2, M_ULTP2, P_ULTP2);
+            const double ault = (w.ultp1 - 32.0) * 0.5555;
+            const double bult = w.ultp2;
             w.ultmp = ault + bult * airtc;
-            w.lgtmp = (s.daily(FB_M_LGTP1, M_LGTP1, P_LGTP1) - 32.0) * 0.5555;
+            w.lgtmp = (w.lgtp1 - 32.0) * 0.5555;
         }
     } else {
-        const double ulsmo = s.daily(FB_M_ULTP1, M_ULTP1, P_ULTP1);
-        const double ultdif = 0.555 * s.daily(FB_M_ULTP2, M_ULTP2, P_ULTP2);
+        const double ulsmo = w.ultp1;
+        const double ultdif = 0.555 * w.ultp2;
         const double ultmps = w.ultmp;
         w.ultmp = ultmps + ulsmo * (airtcs + ultdif - ultmps);
-        const double lgsmo = s.daily(FB_M_LGTP1, M_LGTP1, P_LGTP1);
-        const double lgtdif = 0.555 * s.daily(FB_M_LGTP2, M_LGTP2, P_LGTP2);
+        const double lgsmo = w.lgtp1;
+        const double lgtdif = 0.555 * w.lgtp2;
         const double lgtmps = w.lgtmp;
         if (s.flag(FB_TSOP0))
             w.lgtmp = lgtmps + lgsmo * (airtcs + lgtdif - lgtmps);

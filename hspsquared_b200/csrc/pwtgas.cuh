@@ -14,8 +14,26 @@ __device__ __forceinline__ void mix_lateral(double &t, double &ox, double &co2, 
     if (lic >= 0.0) co2 = lic * fac + co2 * (1.0 - fac);
 }
 
+// interflow / groundwater DO and CO2 concentrations (optionally monthly), interpolated once per simulated day
+struct PwtgasDaily {
+    ColdD idoxp, ico2p, adoxp, aco2p;
+    __device__ __forceinline__ void bind(double *c) {
+        ColdD *m[NCOLD_PWTGAS] = {&idoxp, &ico2p, &adoxp, &aco2p};
+        for (int k = 0; k < NCOLD_PWTGAS; ++k) m[k]->p = c + k * LAND_TILE;
+    }
+    template <class SEG>
+    __device__ __forceinline__ void refresh_daily(const SEG &s) {
+        const int fb[4] = {FB_M_IDOXP, FB_M_ICO2P, FB_M_ADOXP, FB_M_ACO2P};
+        const int mid[4] = {M_IDOXP, M_ICO2P, M_ADOXP, M_ACO2P};
+        const int pid[4] = {P_IDOXP, P_ICO2P, P_ADOXP, P_ACO2P};
+        double v[4];
+        s.daily_batch(fb, mid, pid, v);
+        idoxp = v[0]; ico2p = v[1]; adoxp = v[2]; aco2p = v[3];
+    }
+};
+
 template <class SEG>
-__device__ __forceinline__ void pwtgas_step(const SEG &s, const SoilTemps &soil, double wyield, double suro,
+__device__ __forceinline__ void pwtgas_step(const SEG &s, const PwtgasDaily &g, const SoilTemps &soil, double wyield, double suro,
                                             double ifwo, double agwo) {
     const double EFACTA = 407960., MFACTA = 0.2266;
     const double elevgc = s.par(P_ELEVGC);
@@ -41,8 +59,8 @@ __device__ __forceinline__ void pwtgas_step(const SEG &s, const SoilTemps &soil,
     if (ifwo > 0.0) {
         iotmp = (soil.ultmp - 32.0) * 5. / 9.;
         if (iotmp < 0.5) iotmp = 0.5;
-        iodox = s.daily(FB_M_IDOXP, M_IDOXP, P_IDOXP);
-        ioco2 = s.daily(FB_M_ICO2P, M_ICO2P, P_ICO2P);
+        iodox = g.idoxp;
+        ioco2 = g.ico2p;
         const double ilifac = s.par(P_ILIFAC);
         if (ifwli > 0.0 && ilifac > 0.0)
             mix_lateral(iotmp, iodox, ioco2, s.forcing(F_ILITMP), s.forcing(F_ILIDOX), s.forcing(F_ILICO2), ilifac);
@@ -51,8 +69,8 @@ __device__ __forceinline__ void pwtgas_step(const SEG &s, const SoilTemps &soil,
     if (agwo > 0.0) {
         aotmp = (soil.lgtmp - 32.0) * 5. / 9.;
         if (aotmp < 0.5) aotmp = 0.5;
-        aodox = s.daily(FB_M_ADOXP, M_ADOXP, P_ADOXP);
-        aoco2 = s.daily(FB_M_ACO2P, M_ACO2P, P_ACO2P);
+        aodox = g.adoxp;
+        aoco2 = g.aco2p;
         const double alifac = s.par(P_ALIFAC);
         if (agwli > 0.0 && alifac > 0.0)
             mix_lateral(aotmp, aodox, aoco2, s.forcing(F_ALITMP), s.forcing(F_ALIDOX), s.forcing(F_ALICO2), alifac);
