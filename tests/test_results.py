@@ -1,0 +1,72 @@
+"""Output path: save_batch hands an IOManager-like sink exactly the float32 frames the reference's
+save_timeseries would build from the oracle's ts (utilities.py:292-333), with the float32 cast done in the kernel."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from hspsquared_b200 import synth, test10
+from hspsquared_b200.calendar import Calendar
+from hspsquared_b200.engine import LandBatch
+from hspsquared_b200.results import save_batch
+from oracle import cases as CASES
+
+from . import parity
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _use_emu(emu_library):
+    yield
+
+
+class Sink:
+    """Records write_ts calls (the reference's SupportsWriteTS surface as IOManager exposes it, hsp2io/io.py:58-66)."""
+
+    def __init__(self):
+        self.calls = {}
+
+    def write_ts(self, data_frame, save_columns, category, operation=None, segment=None, activity=None, compress=True,
+                 outstep=2):
+        self.calls[(operation, segment, activity)] = (data_frame.copy(), list(save_columns), category, outstep)
+
+
+def reference_frame(ts, savedict, tindex):
+    """save_timeseries' frame for a land activity (utilities.py:308-313), restated for the test."""
+    df = pd.DataFrame(index=tindex)
+    for y in (savedict.keys() & set(ts.keys())):
+        df[y] = ts[y]
+    return df.astype(np.float32).sort_index(axis="columns")
+
+
+def test_save_batch_frames_equal_reference_frames():
+    cal = Calendar("1976-01-01", "1976-02-15", 60, "us")
+    steps = cal.steps
+    tindex = pd.date_range("1976-01-01", "1976-02-15", freq="60min")[:-1]
+    assert len(tindex) == steps
+    n = 40
+    ens = synth.Ensemble("PERLND", n, seed=11, sections=("SNOW", "PWATER"))
+    save_tables = {"SNOW": {k: 1 for k in test10.SAVE_DEFAULT["SNOW"]}, "PWATER": {k: 1 for k in test10.SAVE_DEFAULT["PWATER"]}}
+    save_tables["PWATER"]["TAET"] = 0  # present in SAVE with flag 0: a column of the frame, not of save_columns
+    save = ["SNOW_" + k for k in save_tables["SNOW"]] + ["PWATER_" + k for k in save_tables["PWATER"]]
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+        b.set_output_dtype(np.float32)
+        out = b.run(synth.forcing_chunk(ens, cal, 0, steps), chunk=400)
+        rows = b.save
+    assert out.dtype == np.float32
+    sink = Sink()
+    names = ["P%03d" % (i + 1) for i in range(n)]
+    save_batch(sink, {"tindex": tindex}, "PERLND", names, save_tables, rows, out, outstep=3)
+    assert len(sink.calls) == 2 * n
+    for i in (0, 17, 39):
+        si = {"start": cal.start, "stop": cal.stop, "delt": 60, "units": 1, "steps": steps, "time_unit": "us"}
+        ts = synth.forcing_of(ens, cal, i, 0, steps)
+        CASES.run_segment("PERLND", ens.tables_of(i), ts, si, parity.ORACLE_ACTS)
+        for act in ("SNOW", "PWATER"):
+            df, cols, cat, outstep = sink.calls[("PERLND", names[i], act)]
+            ref = reference_frame(ts, save_tables[act], tindex)
+            assert list(df.columns) == list(ref.columns)
+            assert df.index.equals(ref.index) and outstep == 3
+            assert np.array_equal(df.to_numpy(), ref.to_numpy(), equal_nan=True)
+            assert df.to_numpy().dtype == np.float32
+            assert cols == [k for k, v in save_tables[act].items() if v]
+    assert "TAET" in sink.calls[("PERLND", "P001", "PWATER")][0].columns
+    assert "TAET" not in sink.calls[("PERLND", "P001", "PWATER")][1]
