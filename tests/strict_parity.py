@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # run as: python tests/strict_parity.py
 sys.path.insert(0, ROOT)
 from oracle import cases as CASES  # noqa: E402
 from tests import parity  # noqa: E402
