@@ -34,12 +34,27 @@ def output_names(operation, act):
 
 
 class LandBatch:
-    def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False):
+    def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False, order=None):
         """store: SegmentStore; forcing_names: ordered forcing ids the arrays given to run() carry (row order);
         save: ordered output ids '<SECTION>_<NAME>' run() returns (row order), or 'all'.  The raw tile-major buffers of
-        run_host / run_device use `forcing_rows` / `save_rows` (the same names in ascending id order)."""
+        run_host / run_device use `forcing_rows` / `save_rows` (the same names in ascending id order).
+        order: None, "flags" (SegmentStore.divergence_order()) or a permutation: device position i holds the caller's
+        segment order[i].  run(), errors(), get_state() and set_state() keep speaking the caller's order; the raw
+        tile-major buffers of run_host / run_device are in device order (`self.order`)."""
         lib = _lib.load()
         self.lib = lib
+        if order is not None:
+            import copy as _copy
+
+            store = _copy.copy(store)  # the caller's store keeps its order
+            store.monthly = dict(store.monthly)
+            perm = store.divergence_order() if isinstance(order, str) and order == "flags" else np.asarray(order, dtype=np.int64)
+            store.permute(perm)
+            self.order = perm
+            self._inv = np.argsort(perm)
+        else:
+            self.order = None
+            self._inv = None
         self.store = store
         self.cal = calendar
         self.n = store.n
@@ -162,10 +177,14 @@ class LandBatch:
         tiled = []
         for t0 in range(0, steps, chunk):
             t1 = min(steps, t0 + chunk)
-            tiled.append((t0, t1, self.run_host(t0, tile_series(forcing[t0:t1][:, self._fperm, :]))))
+            f = forcing[t0:t1][:, self._fperm, :]
+            if self.order is not None:
+                f = f[:, :, self.order]
+            tiled.append((t0, t1, self.run_host(t0, tile_series(f))))
         self.sync()
         for t0, t1, o in tiled:
-            out[t0:t1] = untile_series(o, self.n)[:, self._sinv, :]
+            u = untile_series(o, self.n)[:, self._sinv, :]
+            out[t0:t1] = u if self._inv is None else u[:, :, self._inv]
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -174,6 +193,8 @@ class LandBatch:
         E = _lib.index("errors")
         buf = np.zeros((len(E), self.n), dtype=np.int64)
         _lib.check(self.lib.hsp2g_get_errors(self.h, _ptr(buf, C.POINTER(C.c_int64)), self.n))
+        if self._inv is not None:
+            buf = buf[:, self._inv]
         return {nme: buf[i] for nme, i in E.items()}
 
     def errors_for(self, section, seg=0):
@@ -184,10 +205,12 @@ class LandBatch:
         S = _lib.index("states")
         buf = np.zeros((len(S), self.n), dtype=np.float64)
         _lib.check(self.lib.hsp2g_get_state(self.h, _ptr(buf), self.n))
-        return buf
+        return buf if self._inv is None else np.ascontiguousarray(buf[:, self._inv])
 
     def set_state(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
+        if self.order is not None:
+            state = np.ascontiguousarray(state[:, self.order])
         _lib.check(self.lib.hsp2g_set_state(self.h, _ptr(state), self.n))
 
     def set_output_dtype(self, dtype):

@@ -417,15 +417,28 @@ class SegmentStore:
         return st
 
     # ------------------------------------------------------------------------------------------------
-    def sort_by_flags(self):
-        """Divergence-aware ordering: segments with equal option words become neighbours, so warps are uniform.
-        Returns the permutation applied (new position i holds old segment perm[i])."""
-        perm = np.argsort(self.flags, kind="stable")
+    def permute(self, perm):
+        """Reorder the segments in place: new position i holds old segment perm[i]."""
+        perm = np.asarray(perm, dtype=np.int64)
+        if perm.shape != (self.n,) or not np.array_equal(np.sort(perm), np.arange(self.n)):
+            raise ValueError("perm must be a permutation of range(n)")
         self.par = np.ascontiguousarray(self.par[:, perm])
         self.state = np.ascontiguousarray(self.state[:, perm])
         self.flags = np.ascontiguousarray(self.flags[perm])
         self.monthly = {k: np.ascontiguousarray(v[:, perm]) for k, v in self.monthly.items()}
         return perm
+
+    def divergence_order(self, keys=()):
+        """Divergence-aware ordering (BASELINE north_star, subsystem 3): the permutation that makes segments with equal
+        option words neighbours -- a warp is 32 consecutive segments, so its lanes then take the same branches -- and,
+        within equal option words, orders by the caller's `keys` (most significant first; e.g. met station, elevation
+        band, temperature offset: segments that freeze, melt and get wet together)."""
+        cols = [np.asarray(k) for k in reversed(tuple(keys))] + [self.flags]
+        return np.lexsort(cols) if len(cols) > 1 else np.argsort(self.flags, kind="stable")
+
+    def sort_by_flags(self, keys=()):
+        """Apply divergence_order(); returns the permutation (new position i holds old segment perm[i])."""
+        return self.permute(self.divergence_order(keys))
 
 
 def forcing_fill(operation, act, provided):

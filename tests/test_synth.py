@@ -93,3 +93,28 @@ def test_categorical_fullchain_ensemble_matches_oracle_and_sorting_is_invisible(
     with LandBatch(sorted_store, cal, names, "all") as b:
         out2 = b.run(np.ascontiguousarray(f[:, :, perm]), chunk=300)
     assert np.array_equal(out2, out[:, :, perm], equal_nan=True)
+
+
+def test_landbatch_order_is_invisible_to_the_caller():
+    """LandBatch(order=...) reorders segments on the device (divergence-aware ordering with caller keys) but run(),
+    errors() and get_state() keep the caller's order, bit for bit."""
+    cal = Calendar("1976-03-01", "1976-03-25", 60, "us")
+    ens = synth.Ensemble("PERLND", 90, seed=5, base="cbp", options=("RTOPFG", "UZFG", "ICEFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
+    store = ens.store(cal)
+    with LandBatch(store, cal, names, "all") as b:
+        ref, ref_e, ref_s = b.run(f, chunk=211), b.errors(), b.get_state()
+    perm = store.divergence_order(keys=(np.floor(ens.u_airt * 4), ens.u_prec))
+    assert not np.array_equal(perm, np.arange(90))
+    flags_sorted = store.flags[perm]
+    assert np.all(np.diff(flags_sorted.astype(np.int64)) >= 0)
+    for order in ("flags", perm):
+        with LandBatch(store, cal, names, "all", order=order) as b:
+            out, e, st = b.run(f, chunk=211), b.errors(), b.get_state()
+            assert b.order is not None
+        assert np.array_equal(out, ref, equal_nan=True)
+        assert np.array_equal(st, ref_s, equal_nan=True)
+        for k in ref_e:
+            assert np.array_equal(e[k], ref_e[k]), k
+    assert np.array_equal(store.flags, ens.store(cal).flags)  # the caller's store is untouched
