@@ -33,6 +33,8 @@ ERRMSGS = {
                "LGTMP temperature less than -100C", "SLTMP temperature greater than 100C",
                "ULTMP temperature greater than 100C", "LGTMP temperature greater than 100C"],
     "PWTGAS": [],  # PWTGAS.py:12
+    "SOLIDS": [],  # SOLIDS.py:14
+    "IWTGAS": [],  # IWTGAS.py:11
 }
 
 # series each section may read from ts (kernel forcing ids)
@@ -46,6 +48,8 @@ INPUTS = {
     "PSTEMP": ("AIRTMP",),
     "PWTGAS": ("WYIELD", "SURO", "IFWO", "AGWO", "SURLI", "IFWLI", "AGWLI", "SLTMP", "ULTMP", "LGTMP", "SLITMP",
                "SLIDOX", "SLICO2", "ILITMP", "ILIDOX", "ILICO2", "ALITMP", "ALIDOX", "ALICO2"),
+    "SOLIDS": ("SURO", "SURS", "PREC"),
+    "IWTGAS": ("AIRTMP", "WYIELD", "SURO", "SURLI", "SLITMP", "SLIDOX", "SLICO2"),
 }
 DEVICE = 0
 
@@ -213,9 +217,40 @@ def pwtgas(io_manager, siminfo, uci, ts):
     return errors, ERRMSGS["PWTGAS"]
 
 
+def solids(io_manager, siminfo, uci, ts):
+    """SOLIDS.py:16-49"""
+    n = siminfo["steps"]
+    errors, cal = _run_section("SOLIDS", "IMPLND", siminfo, uci, ts)
+    for name in ("SURO", "SURS", "PREC", "SLSLD"):
+        if name not in ts:
+            ts[name] = np.zeros(n)
+    u = uci["PARAMETERS"]
+    ts["ACCSDP"] = cal.initm(uci, u["VASDFG"], "MONTHLY_ACCSDP", u["ACCSDP"]) if "VASDFG" in u else _full(n, u["ACCSDP"])
+    ts["REMSDP"] = cal.initm(uci, u["VRSDFG"], "MONTHLY_REMSDP", u["REMSDP"]) if "VRSDFG" in u else _full(n, u["REMSDP"])
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return errors, ERRMSGS["SOLIDS"]
+
+
+def iwtgas(io_manager, siminfo, uci, ts):
+    """IWTGAS.py:33-63.  Like the reference, raises KeyError when the IWT-INIT states are absent (IWTGAS.py:79-81)."""
+    n = siminfo["steps"]
+    errors, cal = _run_section("IWTGAS", "IMPLND", siminfo, uci, ts)
+    u = uci["PARAMETERS"]
+    for nm in ("AWTF", "BWTF"):
+        ts[nm] = cal.initm(uci, u["WTFVFG"], "MONTHLY_" + nm, u[nm]) if "WTFVFG" in u else _full(n, u[nm])
+    for name in ("AIRTMP", "WYIELD", "SURO", "SURLI"):
+        if name not in ts:
+            ts[name] = np.zeros(n)
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    for name in ("SLITMP", "SLIDOX", "SLICO2"):
+        if name not in ts:
+            ts[name] = np.full(n, -1.0e30)
+    return errors, ERRMSGS["IWTGAS"]
+
+
 ACTIVITIES = {
     "PERLND": {"ATEMP": atemp, "SNOW": snow, "PWATER": pwater, "SEDMNT": sedmnt, "PSTEMP": pstemp, "PWTGAS": pwtgas},
-    "IMPLND": {"ATEMP": atemp, "SNOW": snow, "IWATER": iwater},
+    "IMPLND": {"ATEMP": atemp, "SNOW": snow, "IWATER": iwater, "SOLIDS": solids, "IWTGAS": iwtgas},
 }
 
 

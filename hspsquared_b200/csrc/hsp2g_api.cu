@@ -19,7 +19,8 @@
 
 static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && HSP2G_PWATER == HSP2G_ACT_PWATER &&
                   HSP2G_SEDMNT == HSP2G_ACT_SEDMNT && HSP2G_PSTEMP == HSP2G_ACT_PSTEMP &&
-                  HSP2G_PWTGAS == HSP2G_ACT_PWTGAS && HSP2G_IWATER == HSP2G_ACT_IWATER,
+                  HSP2G_PWTGAS == HSP2G_ACT_PWTGAS && HSP2G_IWATER == HSP2G_ACT_IWATER &&
+                  HSP2G_SOLIDS == HSP2G_ACT_SOLIDS && HSP2G_IWTGAS == HSP2G_ACT_IWTGAS,
               "public activity bits must match the kernel's");
 static_assert(HSP2G_ABI_VERSION == 2, "bump _lib.py with the header");
 static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
@@ -109,8 +110,10 @@ const char *k_errors = HSP2G_ERRORS(NAME_ITEM);
 #define OT(n) "PSTEMP_" #n ","
 #define OG(n) "PWTGAS_" #n ","
 #define OI(n) "IWATER_" #n ","
+#define OL(n) "SOLIDS_" #n ","
+#define OW(n) "IWTGAS_" #n ","
 const char *k_outputs = HSP2G_OUT_ATEMP(OA) HSP2G_OUT_SNOW(OS) HSP2G_OUT_PWATER(OP) HSP2G_OUT_SEDMNT(OD)
-    HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI);
+    HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI) HSP2G_OUT_SOLIDS(OL) HSP2G_OUT_IWTGAS(OW);
 
 // host [rows][ld] (segment-minor) <-> device tile-major rows [tile][row0 + r][32] of a block with `blk_rows` rows per
 // tile.  Padded lanes of the last tile receive copies of the last real segment (land_common.cuh).
@@ -312,7 +315,7 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
     if (delt > 360.0 && (act & HSP2G_SNOW))
         return fail("SNOW with delt > 360: the reference raises KeyError('ICEFLG') (SNOW.py:85); refused");
     const unsigned perl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_PWATER | HSP2G_SEDMNT | HSP2G_PSTEMP | HSP2G_PWTGAS;
-    const unsigned impl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_IWATER;
+    const unsigned impl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_IWATER | HSP2G_SOLIDS | HSP2G_IWTGAS;
     if (act == 0 || (act & ~(operation == HSP2G_PERLND ? perl : impl)))
         return fail("activity mask 0x%x is not valid for this operation", act);
     int ndev = 0;

@@ -22,6 +22,8 @@
 #define HSP2G_ACT_PSTEMP 16u
 #define HSP2G_ACT_PWTGAS 32u
 #define HSP2G_ACT_IWATER 64u
+#define HSP2G_ACT_SOLIDS 128u /* IMPLND, after IWATER (configuration.py:51-52) */
+#define HSP2G_ACT_IWTGAS 256u
 
 /* ---- per-segment scalar parameters: par[P_x][segment], fp64 -------------------------------------- */
 /* derived columns (computed by the host with the reference's own expression order):
@@ -37,13 +39,15 @@
     X(SMPF) X(KRER) X(JRER) X(AFFIX) X(COVER) X(NVSI) X(KSER) X(JSER) X(KGER) X(JGER)                     \
     X(ASLT) X(BSLT) X(ULTP1) X(ULTP2) X(LGTP1) X(LGTP2)                                                   \
     X(ELEVGC) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(SLIFAC) X(ILIFAC) X(ALIFAC)                           \
-    X(RETSC)
+    X(RETSC)                                                                                              \
+    /* IMPLND SOLIDS (SOLIDS.py:62-64) and IWTGAS (IWTGAS.py:76-86; ELEVGC and SLIFAC share the PWTGAS columns) */ \
+    X(KEIM) X(JEIM) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF)
 
 /* ---- monthly tables: mon[slot][12][segment]; a parameter follows its table only where the segment's
  *      M_<name> flag bit is set (utilities.py:205-211 initm: flag truthy AND table present) -------------- */
 #define HSP2G_MONTHLY(X)                                                                                  \
     X(KMELT) X(LZETP) X(CEPSC) X(INTFW) X(IRC) X(NSUR) X(UZSN) X(COVER) X(NVSI) X(ASLT) X(BSLT) X(ULTP1)  \
-    X(ULTP2) X(LGTP1) X(LGTP2) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(RETSC)
+    X(ULTP2) X(LGTP1) X(LGTP2) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(RETSC) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF)
 
 /* ---- per-segment option flags: one 64-bit word per segment ---------------------------------------- */
 #define HSP2G_FLAGS(X)                                                                                    \
@@ -63,7 +67,9 @@
     X(GDVFG)                                                                                              \
     X(M_KMELT) X(M_LZETP) X(M_CEPSC) X(M_INTFW) X(M_IRC) X(M_NSUR) X(M_UZSN) X(M_COVER) X(M_NVSI)         \
     X(M_ASLT) X(M_BSLT) X(M_ULTP1) X(M_ULTP2) X(M_LGTP1) X(M_LGTP2) X(M_IDOXP) X(M_ICO2P) X(M_ADOXP)      \
-    X(M_ACO2P) X(M_RETSC)
+    X(M_ACO2P) X(M_RETSC)                                                                                 \
+    X(SLD_SDOP1)  /* SOLIDS: SDOPFG == 1 (SOLIDS.py:103) */                                               \
+    X(M_ACCSDP) X(M_REMSDP) X(M_AWTF) X(M_BWTF)
 
 /* ---- carried state: state[S_x][segment], fp64.  Named states (restart.py:9-14) AND the hidden scalars the
  *      reference carries across steps, so a run split into time chunks is bit-identical
@@ -81,7 +87,9 @@
     /* PSTEMP (deg C internally) */                                                                       \
     X(SLTMP) X(ULTMP) X(LGTMP) X(AIRTS)                                                                   \
     /* IWATER (SURS, MSUPY, DEC, SRC, PETADJ shared with the PWATER slots: a batch is one operation) */    \
-    X(RETS)
+    X(RETS)                                                                                               \
+    /* SOLIDS: storage and the dry-day latch; IWTGAS: the day's temperature regression coefficients */    \
+    X(SLDS) X(SLD_DRYDFG) X(IWG_AWTF) X(IWG_BWTF)
 
 /* ---- forcing / input series ids: forc[t][row][segment]; absent ids read a per-batch fill value that the
  *      host derives by replaying the reference wrappers' NaN / zero / -1e30 fills (SNOW.py:44-46,
@@ -110,6 +118,8 @@
     X(AOHT) X(POHT) X(SODOXM) X(SOCO2M) X(IODOXM) X(IOCO2M) X(AODOXM) X(AOCO2M) X(PODOXM) X(POCO2M)
 /* IWATER outputs: IMPEV PET PETADJ RETS SUPY SURI SURO SURS (IWATER.py:119-126) */
 #define HSP2G_OUT_IWATER(X) X(IMPEV) X(PET) X(PETADJ) X(RETS) X(SUPY) X(SURI) X(SURO) X(SURS)
+#define HSP2G_OUT_SOLIDS(X) X(SOSLD) X(SLDS)                         /* SOLIDS.py:72-73 */
+#define HSP2G_OUT_IWTGAS(X) X(SOTMP) X(SODOX) X(SOCO2) X(SOHT) X(SODOXM) X(SOCO2M) /* IWTGAS.py:104-109 */
 
 /* ---- error counters: err[E_x][segment], int64 (ERRMSGS tuples of the reference) ---------------------- */
 #define HSP2G_ERRORS(X)                                                                                   \
@@ -179,7 +189,13 @@ enum {
 #define X(n) O_IWATER_##n,
                             HSP2G_OUT_IWATER(X)
 #undef X
-                                HSP2G_NOUT
+#define X(n) O_SOLIDS_##n,
+                                HSP2G_OUT_SOLIDS(X)
+#undef X
+#define X(n) O_IWTGAS_##n,
+                                    HSP2G_OUT_IWTGAS(X)
+#undef X
+                                        HSP2G_NOUT
 };
 enum {
 #define X(n) E_##n,

@@ -18,8 +18,16 @@ static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 
 cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SI = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_IWATER);
-    if (L.act == (unsigned)SI && hourly && io_matches<IO_SnowIwaterDefault>(L))
-        return launch_one<SI, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>", grid_out);
+    // test10's IMPLND chain: SNOW -> IWATER -> SOLIDS (-> IWTGAS); SaveTable.csv saves nothing of SOLIDS / IWTGAS by default
+    constexpr int SIS = SI | (int)HSP2G_ACT_SOLIDS, SISG = SIS | (int)HSP2G_ACT_IWTGAS;
+    if (hourly && io_matches<IO_SnowIwaterDefault>(L)) {
+        if (L.act == (unsigned)SI)
+            return launch_one<SI, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>", grid_out);
+        if (L.act == (unsigned)SIS)
+            return launch_one<SIS, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER|SOLIDS,hourly,save=default16>", grid_out);
+        if (L.act == (unsigned)SISG)
+            return launch_one<SISG, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER|SOLIDS|IWTGAS,hourly,save=default16>", grid_out);
+    }
     return hourly ? launch_one<-1, true, DynIO, 128>(L, sub_pref, st, name, "implnd_kernel<generic,hourly,io=dynamic>", grid_out)
                   : launch_one<-1, false, DynIO, 128>(L, sub_pref, st, name, "implnd_kernel<generic,subhourly,io=dynamic>", grid_out);
 }

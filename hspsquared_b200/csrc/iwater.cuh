@@ -27,7 +27,8 @@ struct IwaterState {
 };
 
 template <bool HOURLY, class SEG>
-__device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const SnowLink &sn, double prec) {
+__device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const SnowLink &sn, double prec, double &suro_out,
+                                            double &surs_out) {
     const double delt60 = s.L.delt60;
     const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
     const bool hr1fg = s.calfl & HSP2G_CAL_HR1FG;
@@ -139,6 +140,8 @@ __device__ __forceinline__ void iwater_step(const SEG &s, IwaterState &w, const 
     } else
         impev = 0.0;
 
+    suro_out = suro;
+    surs_out = w.surs;
     s.count(E_IWATER0, e0);
     s.save(O_IWATER_IMPEV, impev);
     s.save(O_IWATER_PET, pet);

@@ -54,7 +54,7 @@
 #define HOT_CHAIN                                                                                                  \
     (PBIT(ELDAT) | PBIT(SMPF) | PBIT(KRER) | PBIT(JRER) | PBIT(KSER) | PBIT(JSER) | PBIT(KGER) | PBIT(JGER) |       \
      PBIT(ELEVGC) | PBIT(SLIFAC) | PBIT(ILIFAC) | PBIT(ALIFAC))
-static_assert(HSP2G_NPAR <= 64, "hot-parameter masks are 64 bits");
+static_assert(P_RETSC < 64, "hot-parameter masks are 64 bits: hot ids must be below 64 (later ids are never hot)");
 
 struct __align__(32) CalStep {
     double xm;       // (day - first of month) in the calendar's time unit
@@ -420,7 +420,7 @@ struct Seg {
         double *h = hot_area + lane;
         int k = 0;
 #pragma unroll
-        for (int id = 0; id < HSP2G_NPAR; ++id)
+        for (int id = 0; id < 64 && id < HSP2G_NPAR; ++id)
             if ((HOT >> id) & 1ull) h[(k++) * LAND_TILE] = __ldg(sb + (SB_PAR + id) * LAND_TILE);
         hot = h;  // each lane reads back only what it wrote: no barrier needed
         fl = *reinterpret_cast<const unsigned long long *>(sb + SB_FLAGS * LAND_TILE);
@@ -446,7 +446,7 @@ struct Seg {
     }
     __device__ __forceinline__ bool flag(int bit) const { return (fl >> bit) & 1ull; }
     __device__ __forceinline__ double par(int id) const {
-        if ((HOT >> id) & 1ull) return hot[hsp_popc(HOT & ((1ull << id) - 1ull)) * LAND_TILE];
+        if (id < 64 && ((HOT >> (id & 63)) & 1ull)) return hot[hsp_popc(HOT & ((1ull << (id & 63)) - 1ull)) * LAND_TILE];
         return __ldg(sb + (SB_PAR + id) * LAND_TILE);
     }
     __device__ __forceinline__ bool has_forcing(int id) const {

@@ -15,12 +15,14 @@
 //   MAXREG       register cap per thread (__maxnreg__): resident warps per SM = 65536 / (32 * MAXREG rounded up to 8).
 #pragma once
 #include "iwater.cuh"
+#include "iwtgas.cuh"
 #include "land_common.cuh"
 #include "pstemp.cuh"
 #include "pwater.cuh"
 #include "pwtgas.cuh"
 #include "sedmnt.cuh"
 #include "snow.cuh"
+#include "solids.cuh"
 
 #define IMPLND_HOT (HOT_SNOW | HOT_IWATER)
 #define CHAIN_ACTS (HSP2G_ACT_ATEMP | HSP2G_ACT_SEDMNT | HSP2G_ACT_PSTEMP | HSP2G_ACT_PWTGAS)
@@ -173,9 +175,13 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
 
         SnowStateT<SNOWCOLD> sw;
         IwaterState iw;
+        SolidsState sl;
+        IwtgasState ig;
         sw.bind(pipe.hot_area() + SegT::NHOT * LAND_TILE + lane, s.sb);
         if (act & HSP2G_ACT_SNOW) sw.load(s);
         if (act & HSP2G_ACT_IWATER) iw.load(s);
+        if (act & HSP2G_ACT_SOLIDS) sl.load(s);
+        if (act & HSP2G_ACT_IWTGAS) ig.load(s);
 
         for (int t = t0; t < t1; ++t) {
             s.begin_step(pipe.acquire());
@@ -196,15 +202,23 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
                 link.packi = s.forcing(F_PACKI);
             }
             link.airtmp = airtmp;
+            double suro, surs;
             if (act & HSP2G_ACT_IWATER) {
                 if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) iw.refresh_daily(s);
-                iwater_step<HOURLY>(s, iw, link, prec);
+                iwater_step<HOURLY>(s, iw, link, prec, suro, surs);
+            } else {
+                suro = s.forcing(F_SURO);
+                surs = s.forcing(F_SURS);
             }
+            if (act & HSP2G_ACT_SOLIDS) solids_step(s, sl, suro, surs, prec);
+            if (act & HSP2G_ACT_IWTGAS) iwtgas_step(s, ig, airtmp, link.wyield, suro);
             s.end_step();
             pipe.release(t);
         }
         if (act & HSP2G_ACT_SNOW) sw.store(s);
         if (act & HSP2G_ACT_IWATER) iw.store(s);
+        if (act & HSP2G_ACT_SOLIDS) sl.store(s);
+        if (act & HSP2G_ACT_IWTGAS) ig.store(s);
         sched.done(tile);
     }
 }

@@ -17,10 +17,11 @@ from .segstore import SegmentStore, forcing_fill
 
 _dp = C.POINTER(C.c_double)
 
-SECTION_OF = {"PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"), "IMPLND": ("ATEMP", "SNOW", "IWATER")}
+SECTION_OF = {"PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"),
+              "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS")}
 ERRORS_OF = {"SNOW": ("SNOW0",), "PWATER": tuple("PWATER%d" % i for i in range(10)),
              "PSTEMP": tuple("PSTEMP%d" % i for i in range(6)), "IWATER": ("IWATER0",), "ATEMP": (), "SEDMNT": (),
-             "PWTGAS": ()}
+             "PWTGAS": (), "SOLIDS": (), "IWTGAS": ()}
 
 
 def _ptr(a, typ=_dp):

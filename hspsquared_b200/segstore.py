@@ -28,7 +28,7 @@ from .test10 import MONTHS
 NAN = float("nan")
 
 PERLND_ORDER = ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS")
-IMPLND_ORDER = ("ATEMP", "SNOW", "IWATER")
+IMPLND_ORDER = ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS")
 
 # raw (pre-derivation) per-segment values collected by effective(); derived columns are made in build()
 RAW_DEFAULT = {
@@ -43,12 +43,14 @@ RAW_DEFAULT = {
     "ASLT": 32.0, "BSLT": 1.0, "ULTP1": 0.0, "ULTP2": 0.0, "LGTP1": 0.0, "LGTP2": 0.0,
     "ELEV": 0.0, "IDOXP": 0.0, "ICO2P": 0.0, "ADOXP": 0.0, "ACO2P": 0.0, "SLIFAC": 0.0, "ILIFAC": 0.0, "ALIFAC": 0.0,
     "RETSC": 0.0,
+    "KEIM": 0.0, "JEIM": -999.0, "ACCSDP": 0.0, "REMSDP": 0.0, "AWTF": 32.0, "BWTF": 1.0,  # ParseTable.csv rows 1291-1329
 }
 INIT_DEFAULT = {
     "PACKF": 0.0, "PACKI": 0.0, "PACKW": 0.0, "RDENPF": 0.2, "DULL": 400.0, "PAKTMP": 32.0, "COVINX": 0.01,
     "XLNMLT": 0.0, "SKYCLR": 1.0,
     "CEPS": 0.0, "SURS": 0.0, "UZS": 0.001, "IFWS": 0.0, "LZS": 0.001, "AGWS": 0.0, "GWVS": 0.0,
     "RETS": 0.001,
+    "SLDS": 0.0,
     "DETS": 0.0, "PST_SLTMP": 60.0, "PST_ULTMP": 60.0, "PST_LGTMP": 60.0,
 }
 
@@ -197,6 +199,35 @@ def effective(operation, tables, pw_icefg=None, airtfg=None, ext_names=()):
         init["RETS"] = _need(ui, "RETS", "IWATER")
         init["SURS"] = _need(ui, "SURS", "IWATER")
 
+    if act & _lib.ACT_BITS["SOLIDS"]:  # SOLIDS.py:19-49
+        uci = tables["SOLIDS"]
+        ui = make_ui(uci)
+        u = uci["PARAMETERS"]
+        for n in ("KEIM", "JEIM"):
+            raw[n] = _need(ui, n, "SOLIDS")
+        for n in ("ACCSDP", "REMSDP"):
+            raw[n] = float(_need(u, n, "SOLIDS"))
+        init["SLDS"] = _need(ui, "SLDS", "SOLIDS")
+        flag["SLD_SDOP1"] = int(ui.get("SDOPFG", 0.0) == 1)
+        for fl, n in (("VASDFG", "ACCSDP"), ("VRSDFG", "REMSDP")):
+            if fl in u and _initm(uci, u[fl], "MONTHLY_" + n):
+                flag["M_" + n] = 1
+                mon[n] = _table(uci, "MONTHLY_" + n)
+
+    if act & _lib.ACT_BITS["IWTGAS"]:  # IWTGAS.py:33-63, 76-86
+        uci = tables["IWTGAS"]
+        ui = make_ui(uci)
+        u = uci["PARAMETERS"]
+        for n in ("SOTMP", "SODOX", "SOCO2"):
+            _need(ui, n, "IWTGAS")  # initial values the loop overwrites, but their absence is a KeyError in the reference
+        for n in ("SLIFAC", "ELEV"):
+            raw[n] = _need(ui, n, "IWTGAS")
+        for n in ("AWTF", "BWTF"):
+            raw[n] = float(_need(u, n, "IWTGAS"))
+            if "WTFVFG" in u and _initm(uci, u["WTFVFG"], "MONTHLY_" + n):
+                flag["M_" + n] = 1
+                mon[n] = _table(uci, "MONTHLY_" + n)
+
     if act & _lib.ACT_BITS["SEDMNT"]:
         uci = tables["SEDMNT"]
         ui = make_ui(uci)
@@ -336,8 +367,8 @@ class SegmentStore:
         st.par[st.P["INFILT_IVL"]] = R("INFILT") * delt60  # PWATER.py:215
         if act & B["PWATER"]:
             st.par[st.P["KGW"]] = 1.0 - _vpow(R("AGWRC"), delt60 / 24.0)  # PWATER.py:247
-        if act & B["PWTGAS"]:
-            st.par[st.P["ELEVGC"]] = _vpow((288.0 - 0.00198 * R("ELEV")) / 288.0, 5.256)  # PWTGAS.py:95
+        if act & (B["PWTGAS"] | B["IWTGAS"]):
+            st.par[st.P["ELEVGC"]] = _vpow((288.0 - 0.00198 * R("ELEV")) / 288.0, 5.256)  # PWTGAS.py:95, IWTGAS.py:84
 
         # ---- flag word and monthly tables
         for name, v in flag.items():
@@ -404,6 +435,12 @@ class SegmentStore:
             s[S["MSUPY"]] = I("SURS")
             s[S["DEC"]] = NAN
             s[S["SRC"]] = NAN
+        if act & B["SOLIDS"]:  # SOLIDS.py:64,75
+            s[S["SLDS"]] = I("SLDS")
+            s[S["SLD_DRYDFG"]] = 1.0
+        if act & B["IWTGAS"]:  # IWTGAS.py:119-120: the raw interval-0 values, converted on the first DAYFG interval
+            s[S["IWG_AWTF"]] = daily0("AWTF")
+            s[S["IWG_BWTF"]] = daily0("BWTF")
         if act & B["SEDMNT"]:  # SEDMNT.py:75,80,127,145
             s[S["DETS"]] = I("DETS")
             s[S["SED_NVSI"]] = R("NVSI") * delt / 1440.0
@@ -475,6 +512,12 @@ def forcing_fill(operation, act, provided):
     if act & B["IWATER"]:  # IWATER.py:35-42
         put(("AIRTMP", "PETINP", "PREC", "RAINF", "SNOCOV", "WYIELD"), NAN)
         put(("SURLI",), 0.0)
+        present.update(("SURO", "SURS"))
+    if act & B["SOLIDS"]:  # SOLIDS.py:24-26 (SLSLD is filled too, but never read by the loop)
+        put(("SURO", "SURS", "PREC"), 0.0)
+    if act & B["IWTGAS"]:  # IWTGAS.py:51-53, 92-94
+        put(("AIRTMP", "WYIELD", "SURO", "SURLI"), 0.0)
+        put(("SLITMP", "SLIDOX", "SLICO2"), -1.0e30)
     if act & B["SEDMNT"]:  # SEDMNT.py:86-96
         if "RAINF" not in present:
             opts |= _lib.OPT_SED_RAIN_IS_PREC

@@ -62,15 +62,20 @@ P001 = {
     },
 }
 
-# IMPLND 1 "DONIGIAN INDUSTRY": ACTIVITY SNOW, IWATER (+ SOLIDS/IWTGAS/IQUAL, out of scope) (test10.uci:173-177)
+# IMPLND 1 "DONIGIAN INDUSTRY": ACTIVITY SNOW, IWATER, SOLIDS, IWTGAS (+ IQUAL, out of scope) (test10.uci:173-177).
+# IWTGAS is OFF here although the UCI switches it on: the UCI has no IWT-INIT table, readUCI adds no default for it
+# (readUCI.py:244-250 only patches LAT-FACTOR), and the reference then raises KeyError('SOTMP') at IWTGAS.py:79 (checked
+# against the reference in the build container).  The `i001_iwtgas` parity case supplies the table.
 I001 = {
-    "ACTIVITY": {"ATEMP": 0, "SNOW": 1, "IWATER": 1},
+    "ACTIVITY": {"ATEMP": 0, "SNOW": 1, "IWATER": 1, "SOLIDS": 1, "IWTGAS": 0},
     "SNOW": _snow(450.0),
     "IWATER": {
         "PARAMETERS": {"CSNOFG": 1, "RTOPFG": 0, "VRSFG": 0, "VNNFG": 0, "RTLIFG": 1, "LSUR": 200.0, "SLSUR": 0.010,
                        "NSUR": 0.010, "RETSC": 0.01, "PETMAX": 40.0, "PETMIN": 35.0},
         "STATES": {"RETS": 0.01, "SURS": 0.01},
     },
+    "SOLIDS": {"PARAMETERS": {"KEIM": 0.08, "JEIM": 1.9, "ACCSDP": 0.01, "REMSDP": 0.5, "SLDS": 0.2}},  # test10.uci:250-260
+    "IWTGAS": {"PARAMETERS": {"ELEV": 410.0, "AWTF": 40.0, "BWTF": 0.8, "SDLFAC": 0.0, "SLIFAC": 0.0}},  # :264-268 + readUCI.py:244-250
 }
 
 # default SAVE sets, hsp2tools/data/SaveTable.csv
@@ -79,6 +84,7 @@ SAVE_DEFAULT = {
              "SNOCOV", "WYIELD", "XLNMLT"),
     "PWATER": ("AGWO", "AGWS", "CEPS", "GWVS", "IFWO", "IFWS", "LZS", "PERO", "SURO", "SURS", "UZS"),
     "IWATER": ("RETS", "SURO", "SURS"),
+    "SOLIDS": (), "IWTGAS": (),  # SaveTable.csv rows 256-263: every SOLIDS / IWTGAS series defaults to 0
 }
 
 

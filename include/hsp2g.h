@@ -4,10 +4,11 @@
  * What it replaces.  In respec/HSPsquared every land segment is advanced by Numba loops called one segment and
  * one activity at a time:
  *     errors, errmsgs = function(io_manager, siminfo, ui, ts)          src/hsp2/hsp2/main.py:249-250
- * with `function` one of atemp/snow/pwater/sedmnt/pstemp/pwtgas (PERLND) or atemp/snow/iwater (IMPLND) from the
+ * with `function` one of atemp/snow/pwater/sedmnt/pstemp/pwtgas (PERLND) or atemp/snow/iwater/solids/iwtgas (IMPLND) from the
  * registry at src/hsp2/hsp2/configuration.py:45-55, each of which ends in an @njit core:
  *     _atemp_  ATEMP.py:33    _snow_   SNOW.py:91     _pwater_ PWATER.py:102 (+ proute :696)
  *     _iwater_ IWATER.py:75   _sedmnt_ SEDMNT.py:52   _pstemp_ PSTEMP.py:62  _pwtgas_ PWTGAS.py:65
+ *     _solids_ SOLIDS.py:53   _iwtgas_ IWTGAS.py:65
  * This library runs the same arithmetic for a BATCH of independent segments of one operation,
  * all active sections fused into one pass per interval, in time chunks.  The reference has no FFI of its own (it is
  * pure Python); the binding a maintainer adds is the ctypes stub of hspsquared_b200/_lib.py, see INTEGRATION.md.
@@ -51,6 +52,8 @@ extern "C" {
 #define HSP2G_PSTEMP 16u
 #define HSP2G_PWTGAS 32u
 #define HSP2G_IWATER 64u
+#define HSP2G_SOLIDS 128u /* IMPLND SOLIDS, SOLIDS.py:53 */
+#define HSP2G_IWTGAS 256u /* IMPLND IWTGAS, IWTGAS.py:65 */
 
 /* hsp2g_set_forcing_layout opts */
 #define HSP2G_OPT_SED_RAIN_IS_PREC 1u /* SEDMNT.py:86-89: no RAINF in ts -> RAIN = PREC */

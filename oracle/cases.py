@@ -15,7 +15,7 @@ from hspsquared_b200.test10 import monthly
 
 ORDER = {
     "PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"),  # configuration.py:48-50
-    "IMPLND": ("ATEMP", "SNOW", "IWATER"),  # configuration.py:51-52 (SOLIDS/IWTGAS/IQUAL out of scope)
+    "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS"),  # configuration.py:51-52 (IQUAL out of scope)
 }
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hspsquared_b200", "data")
@@ -92,6 +92,9 @@ def forcings(case):
         out[n] = np.where(a > 0.97, 0.02 * rng.random(steps), 0.0)
     for n, (lo, hi) in case.get("lateral_conc", {}).items():
         out[n] = lo + (hi - lo) * rng.random(steps)
+    if case.get("runoff_inputs"):  # SURO / SURS given as external series (the sections that make them are off)
+        out["SURO"] = np.where(out["PREC"] > 0.0, 0.8 * out["PREC"], 0.0) * rng.random(steps)
+        out["SURS"] = 0.05 * rng.random(steps)
     return out
 
 
@@ -209,6 +212,31 @@ def build_cases():
     t["ACTIVITY"]["ATEMP"] = 1
     t["ATEMP"] = {"PARAMETERS": {"ELDAT": -300.0, "AIRTMP": 30.0}}
     add("i_atemp_snow", "IMPLND", t, "implnd", gatmp=0.0, drop=("CLOUD",), rain_mult=2.0)
+
+    # -- IMPLND SOLIDS + IWTGAS: test10's chain with the IWT-INIT table the shipped UCI lacks ---------
+    t = test10.implnd()
+    t["ACTIVITY"]["IWTGAS"] = 1
+    t["IWTGAS"]["STATES"] = {"SOTMP": 60.0, "SODOX": 0.0, "SOCO2": 0.0}  # ParseTable.csv rows 1360-1362 defaults
+    add("i001_iwtgas", "IMPLND", t, "implnd")
+    # washoff method 1, monthly accumulation / removal / regression coefficients, ATEMP, lateral inflow with
+    # temperature and DO but no CO2 concentration (the nested mixing of IWTGAS.py:151-158)
+    t = test10.implnd()
+    t["ACTIVITY"].update({"ATEMP": 1, "IWTGAS": 1})
+    t["ATEMP"] = {"PARAMETERS": {"ELDAT": 120.0, "AIRTMP": 30.0}}
+    t["SOLIDS"]["PARAMETERS"].update({"SDOPFG": 1, "VASDFG": 1, "VRSDFG": 1, "KEIM": 0.3, "JEIM": 1.4})
+    t["SOLIDS"]["MONTHLY_ACCSDP"] = monthly([.004, .004, .006, .01, .012, .014, .014, .012, .01, .008, .006, .004])
+    t["SOLIDS"]["MONTHLY_REMSDP"] = monthly([.03, .03, .04, .05, .06, .07, .07, .06, .05, .04, .03, .03])
+    t["IWTGAS"]["PARAMETERS"].update({"WTFVFG": 1, "SLIFAC": 0.4, "ELEV": 1250.0})
+    t["IWTGAS"]["STATES"] = {"SOTMP": 60.0, "SODOX": 0.0, "SOCO2": 0.0}
+    t["IWTGAS"]["MONTHLY_AWTF"] = monthly([34., 35., 38., 44., 52., 60., 66., 65., 58., 48., 40., 35.])
+    t["IWTGAS"]["MONTHLY_BWTF"] = monthly([.3, .3, .35, .4, .45, .5, .5, .5, .45, .4, .35, .3])
+    add("i_solids_m1_wtf_monthly", "IMPLND", t, "implnd", gatmp=1.0, drop=("CLOUD",), rain_mult=2.5, lateral=("SURLI",),
+        lateral_conc={"SLITMP": (35., 70.), "SLIDOX": (4., 12.)})
+    # SOLIDS / IWTGAS alone on given runoff series (no SNOW, no IWATER in the batch): zero / -1e30 fills
+    t = test10.implnd()
+    t["ACTIVITY"].update({"SNOW": 0, "IWATER": 0, "IWTGAS": 1})
+    t["IWTGAS"]["STATES"] = {"SOTMP": 60.0, "SODOX": 0.0, "SOCO2": 0.0}
+    add("i_solids_iwtgas_alone", "IMPLND", t, "implnd", steps=24 * 120, runoff_inputs=True)
 
     # -- the reference's own unit-test cases (tests/ipwater/test_ipwater.py:43-84) ----------------
     fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}

@@ -31,7 +31,7 @@ from oracle import ref_harness as H  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 DATA = os.path.join(ROOT, "hspsquared_b200", "data")
-FULL = ("p001_test10", "i001_test10", "cbp_fullchain", "p001_snow_pwater")
+FULL = ("p001_test10", "i001_test10", "cbp_fullchain", "p001_snow_pwater", "i001_iwtgas")
 
 
 def sha(a):
@@ -72,6 +72,10 @@ def gen_hbn():
         s = hbn.get_time_series("IMPLND", 1, cons, "IWATER", "hourly")
         out[cons] = s.values.astype(np.float64)
         out["_first_stamp"] = np.array(str(s.index[0]))
+    # SOLIDS and IWTGAS groups of the same HSPF run (keys prefixed with the section)
+    for act, names in (("SOLIDS", ("SLDS", "SOSLD")), ("IWTGAS", ("SOTMP", "SODOX", "SOCO2", "SOHT", "SODOXM", "SOCO2M"))):
+        for cons in names:
+            out["%s_%s" % (act, cons)] = hbn.get_time_series("IMPLND", 1, cons, act, "hourly").values.astype(np.float64)
     np.savez_compressed(os.path.join(GOLD, "hspf_test10I.npz"), **out)
 
 
@@ -79,7 +83,7 @@ def ref_activities():
     m = H.load()
     return {"ATEMP": m["ATEMP"].atemp, "SNOW": m["SNOW"].snow, "PWATER": m["PWATER"].pwater,
             "IWATER": m["IWATER"].iwater, "SEDMNT": m["SEDMNT"].sedmnt, "PSTEMP": m["PSTEMP"].pstemp,
-            "PWTGAS": m["PWTGAS"].pwtgas}
+            "PWTGAS": m["PWTGAS"].pwtgas, "SOLIDS": m["SOLIDS"].solids, "IWTGAS": m["IWTGAS"].iwtgas}
 
 
 def run_reference(case):

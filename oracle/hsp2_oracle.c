@@ -34,6 +34,8 @@ const char *hsp2o_fields(const char *r) {
     REC(sedmnt, SEDMNT_UI, SEDMNT_IN, SEDMNT_OUT)
     REC(pstemp, PSTEMP_UI, PSTEMP_IN, PSTEMP_OUT)
     REC(pwtgas, PWTGAS_UI, PWTGAS_IN, PWTGAS_OUT)
+    REC(solids, SOLIDS_UI, SOLIDS_IN, SOLIDS_OUT)
+    REC(iwtgas, IWTGAS_UI, IWTGAS_IN, IWTGAS_OUT)
 #undef REC
     if (!strcmp(r, "batch_par")) return FIELDS(BATCH_PAR);
     return "";
@@ -1221,6 +1223,105 @@ void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *ou
         out->IOCO2M[t] = ioco2m;
         out->AODOXM[t] = aodoxm;
         out->AOCO2M[t] = aoco2m;
+    }
+}
+
+/* ============================================================================================== */
+/* SOLIDS  (SOLIDS.py:52-146), IMPLND, English units.  SLSLD is read by the reference but unused.   */
+/* ============================================================================================== */
+void hsp2o_solids(const solids_ui *ui, const solids_in *in, const solids_out *out, int64_t nsteps) {
+    const double delt60 = ui->delt60, keim = ui->KEIM, jeim = ui->JEIM;
+    const double SDOPFG = ui->SDOPFG; /* compared as a float in the reference (SOLIDS.py:103) */
+    double slds = ui->SLDS;
+    int drydfg = 1; /* SOLIDS.py:75 */
+    for (int64_t t = 0; t < nsteps; ++t) {
+        const double suro = in->SURO[t], surs = in->SURS[t], prec = in->PREC[t];
+        const double accsdp = in->ACCSDP[t], remsdp = in->REMSDP[t];
+        const int dayfg = (int)in->DAYFG[t];
+        double sosld;
+        if (SDOPFG == 1) { /* method 1 (SOLIDS.py:103-114) */
+            if (suro > 0.0) {
+                const double arg = surs + suro;
+                const double stcap = delt60 * keim * pow(arg / delt60, jeim);
+                if (stcap > slds)
+                    sosld = slds * suro / arg;
+                else
+                    sosld = stcap * suro / arg;
+                slds = slds - sosld;
+            } else
+                sosld = 0.0;
+        } else { /* method 2 (SOLIDS.py:115-126) */
+            if (suro > 0.0) {
+                const double stcap = delt60 * keim * pow(suro / delt60, jeim);
+                if (stcap > slds) {
+                    sosld = slds;
+                    slds = 0.0;
+                } else {
+                    sosld = stcap;
+                    slds = slds - sosld;
+                }
+            } else
+                sosld = 0.0;
+        }
+        if (dayfg == 0) { /* SOLIDS.py:129-142 */
+            if (prec > 0.0) drydfg = 0;
+        } else {
+            if (drydfg == 1) slds = accsdp + slds * (1.0 - remsdp);
+            drydfg = prec > 0.0 ? 0 : 1;
+        }
+        out->SOSLD[t] = sosld;
+        out->SLDS[t] = slds;
+    }
+}
+
+/* ============================================================================================== */
+/* IWTGAS  (IWTGAS.py:65-183), IMPLND, English units                                               */
+/* ============================================================================================== */
+void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *out, int64_t nsteps) {
+    const double EFACTA = 407960., MFACTA = 0.2266;
+    const double slifac = ui->SLIFAC;
+    double sotmp = ui->SOTMP, sodox = ui->SODOX, soco2 = ui->SOCO2;
+    const double elevgc = pow((288.0 - 0.00198 * ui->ELEV) / 288.0, 5.256);
+    double awtf = in->AWTF[0], bwtf = in->BWTF[0]; /* raw until the first DAYFG interval (IWTGAS.py:119-120) */
+    for (int64_t t = 0; t < nsteps; ++t) {
+        const double airtc = (in->AIRTMP[t] - 32.0) * 0.555;
+        const double suro = in->SURO[t], wyield = in->WYIELD[t], surli = in->SURLI[t];
+        const double slitmp = in->SLITMP[t], slidox = in->SLIDOX[t], slico2 = in->SLICO2[t];
+        if ((int)in->DAYFG[t] == 1) {
+            awtf = (in->AWTF[t] - 32.0) * 0.555;
+            bwtf = in->BWTF[t];
+        }
+        if (suro > 0.0) {
+            sotmp = awtf + bwtf * airtc;
+            if (sotmp < 0.5) sotmp = 0.5;
+            if (wyield > 0.0) sotmp = 0.5;
+            double dummy = sotmp * (0.007991 - 0.77774e-4 * sotmp);
+            sodox = (14.652 + sotmp * (-0.41022 + dummy)) * elevgc;
+            const double abstmp = sotmp + 273.16;
+            dummy = 2385.73 / abstmp - 14.0184 + 0.0152642 * abstmp;
+            soco2 = pow(10.0, dummy) * 3.16e-04 * elevgc * 12000.0;
+            if (surli > 0.0 && slifac > 0.0 && slitmp >= -1.0e10) { /* IWTGAS.py:151-158 */
+                sotmp = slitmp * slifac + sotmp * (1.0 - slifac);
+                if (slidox >= 0.0) sodox = slidox * slifac + sodox * (1.0 - slifac);
+                if (slico2 >= 0.0) soco2 = slico2 * slifac + soco2 * (1.0 - slifac);
+            }
+            out->SOHT[t] = sotmp * suro * EFACTA;
+            out->SODOXM[t] = sodox * suro * MFACTA;
+            out->SOCO2M[t] = soco2 * suro * MFACTA;
+            out->SOTMP[t] = (sotmp * 9.0 / 5.0) + 32.0;
+            out->SODOX[t] = sodox;
+            out->SOCO2[t] = soco2;
+        } else {
+            sotmp = -1.0e30;
+            sodox = -1.0e30;
+            soco2 = -1.0e30;
+            out->SOHT[t] = 0.0;
+            out->SODOXM[t] = 0.0;
+            out->SOCO2M[t] = 0.0;
+            out->SOTMP[t] = sotmp;
+            out->SODOX[t] = sodox;
+            out->SOCO2[t] = soco2;
+        }
     }
 }
 

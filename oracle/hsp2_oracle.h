@@ -85,6 +85,16 @@ extern "C" {
     X(SOHT) X(IOHT) X(AOHT) X(POHT) X(SODOXM) X(SOCO2M) X(IODOXM) X(IOCO2M) X(AODOXM) X(AOCO2M) \
     X(PODOXM) X(POCO2M)
 
+/* ---- SOLIDS (IMPLND) ------------------------------------------------------------------------- */
+#define SOLIDS_UI(X) X(delt60) X(SDOPFG) X(KEIM) X(JEIM) X(SLDS)
+#define SOLIDS_IN(X) X(SURO) X(SURS) X(PREC) X(ACCSDP) X(REMSDP) X(DAYFG)
+#define SOLIDS_OUT(X) X(SOSLD) X(SLDS)
+
+/* ---- IWTGAS (IMPLND) ------------------------------------------------------------------------- */
+#define IWTGAS_UI(X) X(SLIFAC) X(SOTMP) X(SODOX) X(SOCO2) X(ELEV)
+#define IWTGAS_IN(X) X(AIRTMP) X(WYIELD) X(SURO) X(SURLI) X(SLITMP) X(SLIDOX) X(SLICO2) X(AWTF) X(BWTF) X(DAYFG)
+#define IWTGAS_OUT(X) X(SOTMP) X(SODOX) X(SOCO2) X(SOHT) X(SODOXM) X(SOCO2M)
+
 #define HSP2O_DECL_UI(n) double n;
 #define HSP2O_DECL_IN(n) const double *n;
 #define HSP2O_DECL_OUT(n) double *n;
@@ -101,6 +111,8 @@ HSP2O_RECORDS(iwater, IWATER_UI, IWATER_IN, IWATER_OUT)
 HSP2O_RECORDS(sedmnt, SEDMNT_UI, SEDMNT_IN, SEDMNT_OUT)
 HSP2O_RECORDS(pstemp, PSTEMP_UI, PSTEMP_IN, PSTEMP_OUT)
 HSP2O_RECORDS(pwtgas, PWTGAS_UI, PWTGAS_IN, PWTGAS_OUT)
+HSP2O_RECORDS(solids, SOLIDS_UI, SOLIDS_IN, SOLIDS_OUT)
+HSP2O_RECORDS(iwtgas, IWTGAS_UI, IWTGAS_IN, IWTGAS_OUT)
 
 /* error-count vector lengths (ERRMSGS tuples: SNOW.py:23, PWATER.py:15-25, IWATER.py:15, PSTEMP.py:13-18) */
 #define HSP2O_NERR_SNOW 1
@@ -117,6 +129,8 @@ void hsp2o_iwater(const iwater_ui *ui, const iwater_in *in, const iwater_out *ou
 void hsp2o_sedmnt(const sedmnt_ui *ui, const sedmnt_in *in, const sedmnt_out *out, int64_t nsteps);
 void hsp2o_pstemp(const pstemp_ui *ui, const pstemp_in *in, const pstemp_out *out, int64_t nsteps, int64_t *errors);
 void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *out, int64_t nsteps);
+void hsp2o_solids(const solids_ui *ui, const solids_in *in, const solids_out *out, int64_t nsteps);
+void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *out, int64_t nsteps);
 
 /*
  * Multi-threaded CPU baseline over independent segments (bench.py cpu_baseline / --impl reference).

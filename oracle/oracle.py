@@ -147,6 +147,22 @@ def _pwtgas_(ui, ts):
     return _run("pwtgas", ui, ts, n, None, ui_defaults={"GDVFG": 0})
 
 
+def _solids_(ui, ts):
+    n = int(ui["simlen"])
+    for nm in ("SURO", "SURS", "PREC", "SLSLD"):  # SOLIDS.py:24-26 zero fills
+        if nm not in ts:
+            ts[nm] = np.zeros(n)
+    return _run("solids", ui, ts, n, None, ui_defaults={"SDOPFG": 0})
+
+
+def _iwtgas_(ui, ts):
+    n = int(ui["simlen"])
+    for nm in ("SLITMP", "SLIDOX", "SLICO2"):  # IWTGAS.py:92-94
+        if nm not in ts:
+            ts[nm] = np.full(n, -1.0e30)
+    return _run("iwtgas", ui, ts, n, None)
+
+
 def perlnd_batch(nsteps, delt, forc, par, mon, cal, nthreads=0):
     """SNOW->PWATER over independent segments with OpenMP; returns (sums[nseg,24], errors[nseg,11], threads)."""
     forc = np.ascontiguousarray(forc, dtype=np.float64)

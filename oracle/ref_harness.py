@@ -44,7 +44,8 @@ def load():
         sys.path.insert(0, REF_SRC)
     import hsp2.hsp2.utilities  # noqa: F401
 
-    names = ["utilities", "ATEMP", "SNOW", "PWATER", "IWATER", "SEDMNT", "PSTEMP", "PWTGAS", "configuration"]
+    names = ["utilities", "ATEMP", "SNOW", "PWATER", "IWATER", "SEDMNT", "PSTEMP", "PWTGAS", "SOLIDS", "IWTGAS",
+             "configuration"]
     import importlib
 
     for n in names:

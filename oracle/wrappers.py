@@ -158,6 +158,40 @@ def sedmnt(io_manager, siminfo, uci, ts):
     return O._sedmnt_(ui, ts), []
 
 
+def solids(io_manager, siminfo, uci, ts):
+    """SOLIDS.py:16-49"""
+    _english(siminfo)
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    for nm in ("SURO", "SURS", "PREC", "SLSLD"):
+        if nm not in ts:
+            ts[nm] = np.zeros(n)
+    u = uci["PARAMETERS"]
+    ts["ACCSDP"] = cal.initm(uci, u["VASDFG"], "MONTHLY_ACCSDP", u["ACCSDP"]) if "VASDFG" in u else np.full(n, u["ACCSDP"])
+    ts["REMSDP"] = cal.initm(uci, u["VRSDFG"], "MONTHLY_REMSDP", u["REMSDP"]) if "VRSDFG" in u else np.full(n, u["REMSDP"])
+    ui = make_ui(uci)
+    ui.update(simlen=n, delt60=siminfo["delt"] / 60)
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return O._solids_(ui, ts), []
+
+
+def iwtgas(io_manager, siminfo, uci, ts):
+    """IWTGAS.py:33-63"""
+    _english(siminfo)
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    ui = make_ui(uci)
+    ui.update(simlen=n)
+    u = uci["PARAMETERS"]
+    for nm in ("AWTF", "BWTF"):
+        ts[nm] = cal.initm(uci, u["WTFVFG"], "MONTHLY_" + nm, u[nm]) if "WTFVFG" in u else np.full(n, u[nm])
+    for nm in ("AIRTMP", "WYIELD", "SURO", "SURLI"):
+        if nm not in ts:
+            ts[nm] = np.zeros(n)
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return O._iwtgas_(ui, ts), []
+
+
 def pstemp(io_manager, siminfo, uci, ts):
     _english(siminfo)
     cal = _cal(siminfo)

@@ -13,7 +13,7 @@ from oracle import cases as CASES
 from oracle import wrappers as W
 
 ORACLE_ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt,
-               "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas}
+               "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas, "SOLIDS": W.solids, "IWTGAS": W.iwtgas}
 RTOL = 1e-9  # BASELINE.json north_star: max relative error <= 1e-9 on all saved flows and storages
 
 

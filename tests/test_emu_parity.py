@@ -79,3 +79,20 @@ def test_dropin_bit_exact(name):
     assert not parity.compare(ref, got, exact=True)
     for a, e in ref_err.items():
         assert np.array_equal(got_err[a], e), a
+
+
+def test_iwtgas_without_its_states_raises_like_the_reference():
+    """test10.uci switches IWTGAS on for IMPLND 1 but has no IWT-INIT table, and readUCI supplies no default for it: the
+    reference's _iwtgas_ then raises KeyError('SOTMP') (IWTGAS.py:79; checked against the reference in the build
+    container).  The drop-in refuses the same way instead of inventing a value."""
+    from hspsquared_b200 import activities, test10
+
+    case = ALL["i001_test10"]
+    si = CASES.siminfo_for(case)
+    si["time_unit"] = "us"
+    ts = dict(CASES.forcings(case))
+    ts["SURO"] = np.zeros(case["steps"])
+    uci = test10.implnd()["IWTGAS"]
+    assert "STATES" not in uci
+    with pytest.raises(KeyError):
+        activities.iwtgas(None, si, uci, ts)

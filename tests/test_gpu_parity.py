@@ -51,7 +51,8 @@ def test_chunked_equals_single_pass_bitwise(name):
 
 
 @pytest.mark.parametrize("name", ["p001_test10", "i001_test10", "cbp_fullchain", "p_nosnow_iffc2", "flowtest_pwater",
-                                  "flowtest_iwater", "i_atemp_snow"])
+                                  "flowtest_iwater", "i_atemp_snow", "i001_iwtgas", "i_solids_m1_wtf_monthly",
+                                  "i_solids_iwtgas_alone"])
 def test_dropin_vs_oracle(name):
     case = ALL[name]
     ref, ref_err = parity.run_oracle(case)
@@ -208,3 +209,12 @@ def test_hspf_known_answers(golden_dir):
     got, _, _ = parity.run_fused(ALL["i001_test10"])
     for v, t in {"SUPY": 2e-6, "SURO": 2e-6, "SURS": 1e-6, "RETS": 1e-6, "PET": 1e-7, "IMPEV": 1e-7}.items():
         assert np.abs(got[v][:, 0] - h10[v]).max() < t, v
+    # SOLIDS and IWTGAS groups of the same HSPF run, through the fused IMPLND kernel
+    got, _, kname = parity.run_fused(ALL["i001_iwtgas"], save=["SOLIDS_SLDS", "SOLIDS_SOSLD", "IWTGAS_SOTMP", "IWTGAS_SODOX",
+                                                                "IWTGAS_SOCO2", "IWTGAS_SOHT", "IWTGAS_SODOXM", "IWTGAS_SOCO2M"])
+    for key in ("SOLIDS_SLDS", "SOLIDS_SOSLD", "IWTGAS_SOTMP", "IWTGAS_SODOX", "IWTGAS_SOCO2", "IWTGAS_SOHT",
+                "IWTGAS_SODOXM", "IWTGAS_SOCO2M"):
+        ref, g = h10[key], got[key.split("_", 1)[1]][:, 0]
+        ok = ref > -1e29
+        assert np.array_equal(ok, g > -1e29), key
+        assert np.abs(g[ok] - ref[ok]).max() <= 2e-6 * np.abs(ref[ok]).max(), key

@@ -17,7 +17,7 @@ import pytest
 from oracle import cases as CASES
 from oracle import wrappers as W
 
-ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt,
+ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt, "SOLIDS": W.solids, "IWTGAS": W.iwtgas,
         "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas}
 ALL = CASES.build_cases()
 
@@ -83,3 +83,17 @@ def test_full_reference_arrays_match(oracle_lib, golden_dir):
         ts, _ = run_oracle(ALL[name], "us")
         for k in ref.files:
             assert np.array_equal(ref[k], ts[k], equal_nan=True), (name, k)
+
+
+def test_test10_implnd_solids_iwtgas_hspf_kat(oracle_lib, golden_dir):
+    """HSPF's own hourly SOLIDS and IWTGAS output for test10 IMPLND 1 (test10I.hbn) against the oracle chain
+    SNOW -> IWATER -> SOLIDS -> IWTGAS: -1e30 "no runoff" sentinels at the same intervals, values to HSPF's fp32 precision
+    (2e-6 of each series' scale)."""
+    h = np.load(os.path.join(golden_dir, "hspf_test10I.npz"))
+    ts, _ = run_oracle(ALL["i001_iwtgas"], "us")
+    for key in ("SOLIDS_SLDS", "SOLIDS_SOSLD", "IWTGAS_SOTMP", "IWTGAS_SODOX", "IWTGAS_SOCO2", "IWTGAS_SOHT",
+                "IWTGAS_SODOXM", "IWTGAS_SOCO2M"):
+        ref, got = h[key], ts[key.split("_", 1)[1]]
+        ok = ref > -1e29
+        assert np.array_equal(ok, got > -1e29), key
+        assert np.abs(got[ok] - ref[ok]).max() <= 2e-6 * np.abs(ref[ok]).max(), key
