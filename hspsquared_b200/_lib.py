@@ -55,6 +55,7 @@ _PROTOS = {
     "hsp2g_set_timing": (C.c_int, [_h, C.c_int]),
     "hsp2g_kernel_stats": (C.c_int, [_h, _i64p, _dp]),
     "hsp2g_kernel_name": (C.c_char_p, [_h]),
+    "hsp2g_math_probe": (C.c_int, [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp]),
     "hsp2g_host_alloc": (C.c_void_p, [C.c_size_t]),
     "hsp2g_host_free": (C.c_int, [C.c_void_p]),
     "hsp2g_device_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),

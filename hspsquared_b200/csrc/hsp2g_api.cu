@@ -237,6 +237,14 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
 }
 }  // namespace
 
+#ifndef HSP2G_HOST_EMU
+__global__ void math_probe_kernel(int fn, long long n, const double *x, const double *y, double *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fn == 0 ? hsp_pow(x[i], y[i]) : fn == 1 ? hsp_exp(x[i]) : fn == 2 ? hsp_exp2(x[i]) : hsp_log(x[i]);
+}
+#endif
+
 // Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
 // forcing rows are present); the resident-block count sizes the persistent grid.
 cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident) {
@@ -615,6 +623,34 @@ int hsp2g_reset_errors(hsp2g_batch *b) {
     CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
                     (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
     return 0;
+}
+
+int hsp2g_math_probe(int device, int fn, int64_t n, const double *x, const double *y, double *out) {
+    if (!x || !out || (fn == 0 && !y) || fn < 0 || fn > 3 || n <= 0) return fail("bad math probe arguments");
+#ifdef HSP2G_HOST_EMU
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = fn == 0 ? hsp_pow(x[i], y[i]) : fn == 1 ? hsp_exp(x[i]) : fn == 2 ? hsp_exp2(x[i]) : hsp_log(x[i]);
+    (void)device;
+    return 0;
+#else
+    DeviceGuard g(device);
+    if (!g.ok) return fail("cudaSetDevice(%d) failed", device);
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    const size_t bytes = (size_t)n * sizeof(double);
+    CU(cudaMalloc((void **)&dx, bytes));
+    CU(cudaMalloc((void **)&dy, bytes));
+    CU(cudaMalloc((void **)&dout, bytes));
+    CU(cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dy, y ? y : x, bytes, cudaMemcpyHostToDevice));
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(fn, (long long)n, dx, dy, dout);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail("math probe: %s", cudaGetErrorString(e));
+    return 0;
+#endif
 }
 
 int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype) {

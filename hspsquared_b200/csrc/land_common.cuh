@@ -20,6 +20,7 @@
 #include "cuda_rt.h"
 #include <stdint.h>
 
+#include "glibc_math.cuh"
 #include "hsp2g_ids.h"
 
 #define LAND_TILE 32
@@ -157,12 +158,7 @@ struct ColdW {
 #define NCOLD_PWTGAS 4
 #define NCOLD_CHAIN (NCOLD_PSTEMP + NCOLD_PWTGAS)
 
-// One out-of-line copy of pow's argument screening + __internal_accurate_pow instead of one per call site (17 sites,
-// ~100 SASS instructions each): the March step of profiles/r1g spent 40 % of its stall samples waiting for
-// instructions.  Same function, same bits.
-static __device__ __noinline__ double hsp_pow(double x, double y) { return pow(x, y); }
-
-// Likewise one out-of-line copy of the IEEE fp64 division sequence (MUFU.RCP64H + Newton + residual, ~20 SASS
+// One out-of-line copy of the IEEE fp64 division sequence (MUFU.RCP64H + Newton + residual, ~20 SASS
 // instructions inline at each of ~50 sites = a quarter of the kernel).  a / b, correctly rounded, same bits.
 static __device__ __noinline__ double hsp_div(double a, double b) { return a / b; }
 #ifdef HSP_INLINE_DIV

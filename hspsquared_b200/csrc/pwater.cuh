@@ -210,7 +210,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
             w.dec = 0.00982 * hsp_pow(HDIV(dummy, sqrt(slsur)), 0.6);
             w.src = 1020.0 * HDIV(sqrt(slsur), dummy);
         }
-        const double ratio = py_max(1.0001, w.intfw * exp2(lzrat));
+        const double ratio = py_max(1.0001, w.intfw * hsp_exp2(lzrat));
         double under, over;
         if (msupy <= imin) {
             under = msupy;
@@ -287,8 +287,8 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
 
     // ---- INTFLW (PWATER.py:440-455)
     if (dayfg) {
-        const double kifw = HDIV(-log(s.daily(FB_M_IRC, M_IRC, P_IRC)), HDIV(24.0, delt60));
-        w.ifwk2 = 1.0 - exp(-kifw);
+        const double kifw = HDIV(-hsp_log(s.daily(FB_M_IRC, M_IRC, P_IRC)), HDIV(24.0, delt60));
+        w.ifwk2 = 1.0 - hsp_exp(-kifw);
         w.ifwk1 = 1.0 - HDIV(w.ifwk2, kifw);
     }
     const double inflo = ifwi + s.forcing(F_IFWLI);
@@ -330,7 +330,7 @@ __device__ __forceinline__ void pwater_step(const SEG &s, PwaterState &w, const 
                 w.lzfrac = ifrd ? 1.0 : 1.0 - lzrat * hsp_pow(HDIV(1.0, 1.0 + indx), indx);
             } else {
                 const double indx = 1.5 * lzrat - 0.5;
-                w.lzfrac = ifrd ? exp(-1.0 * (lzrat - 1.0)) : hsp_pow(HDIV(1.0, 1.0 + indx), indx);
+                w.lzfrac = ifrd ? hsp_exp(-1.0 * (lzrat - 1.0)) : hsp_pow(HDIV(1.0, 1.0 + indx), indx);
             }
         }
         lzi = w.lzfrac * lperc;

@@ -136,6 +136,11 @@ int hsp2g_set_timing(hsp2g_batch *b, int on);
 int hsp2g_kernel_stats(hsp2g_batch *b, int64_t *launches, double *kernel_ms);
 const char *hsp2g_kernel_name(const hsp2g_batch *b);
 
+/* The kernels' pow / exp / exp2 / log restate glibc 2.39's libm -- the library the reference's Numba code reaches --
+ * bit for bit (hspsquared_b200/csrc/glibc_math_core.h).  This probe evaluates them on the device for n arguments
+ * (fn: 0 pow(x,y), 1 exp(x), 2 exp2(x), 3 log(x); y may be NULL unless fn == 0) so that a test can compare with libm. */
+int hsp2g_math_probe(int device, int fn, int64_t n, const double *x, const double *y, double *out);
+
 /* Pinned host memory / raw device memory helpers for callers without a CUDA runtime of their own. */
 void *hsp2g_host_alloc(size_t bytes);
 int hsp2g_host_free(void *p);

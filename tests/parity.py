@@ -67,7 +67,7 @@ def run_dropin(case, time_unit="us", device=0):
 
 
 def rel_err(got, ref):
-    """max elementwise |got-ref| / max(|ref|, 1e-5*max|ref|, tiny), with NaN==NaN and +-1e30 sentinels exact."""
+    """max elementwise |got-ref| / max(|ref|, 1e-4*max|ref|, tiny), with NaN==NaN and +-1e30 sentinels exact."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     if got.shape != ref.shape:
@@ -82,7 +82,7 @@ def rel_err(got, ref):
     if not ok.any():
         return 0.0
     scale = np.abs(ref[ok]).max()
-    den = np.maximum(np.abs(ref[ok]), max(1e-5 * scale, 1e-300))
+    den = np.maximum(np.abs(ref[ok]), max(1e-4 * scale, 1e-300))
     return float((np.abs(got[ok] - ref[ok]) / den).max())
 
 
