@@ -424,7 +424,8 @@ def main():
                     den = np.maximum(np.abs(ref[ok]), max(1e-4 * np.abs(ref[ok]).max(), 1e-300)) if ok.any() else 1.0
                     if ok.any():
                         worst = max(worst, float((np.abs(g[ok] - ref[ok]) / den).max()))
-            parity = {"max_rel_err_vs_oracle": worst, "segments_checked": 3, "intervals": nst, "tolerance": 1e-9}
+            parity = {"max_rel_err_vs_oracle": worst, "bit_identical": worst == 0.0, "segments_checked": 3, "intervals": nst,
+                      "tolerance": 1e-9}
         except Exception as ex:  # the number stands; say that the check could not run
             parity = {"error": repr(ex)}
 

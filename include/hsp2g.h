@@ -17,6 +17,8 @@
  *   - plain pointers and sizes only; the caller owns host buffers, the library owns device memory behind the handle;
  *   - every function returns 0 on success, non-zero on failure with a message in hsp2g_last_error() (thread local);
  *   - there is NO CPU fallback: without a CUDA device hsp2g_batch_create fails;
+ *   - results are bit-identical to the reference's Numba kernels on a glibc 2.39 / FMA x86-64 host (every fp64 operation is
+ *     IEEE-exact and pow / exp / exp2 / log restate that libm, csrc/glibc_math_core.h);
  *   - identifier spaces (parameter / monthly-table / flag-bit / state / forcing / output / error ids) are the
  *     positions in the comma separated lists returned by hsp2g_names(); hspsquared_b200/csrc/hsp2g_ids.h is the
  *     single definition;
