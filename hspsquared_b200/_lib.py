@@ -42,6 +42,7 @@ _PROTOS = {
     "hsp2g_get_state": (C.c_int, [_h, _dp, C.c_int64]),
     "hsp2g_set_calendar": (C.c_int, [_h, C.c_int64, _u8p, _u8p, _u8p, _dp, _dp, _dp]),
     "hsp2g_set_forcing_layout": (C.c_int, [_h, C.c_int, _i32p, _dp, C.c_uint32]),
+    "hsp2g_set_shared_forcing": (C.c_int, [_h, C.c_int32, C.c_int64, _dp, _i32p, _dp, C.c_int64]),
     "hsp2g_set_save": (C.c_int, [_h, C.c_int, _i32p]),
     "hsp2g_run_device": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -64,6 +64,12 @@ struct hsp2g_batch {
     unsigned prog_base = 0;
     int sub_steps = 64;
     int out_f32 = 0;
+    // shared-met mode
+    double *met = nullptr;   // [n_met_steps][nf][n_stations]
+    int *station = nullptr;  // [ntiles][32]
+    double *mfac = nullptr;  // [ntiles][nf][32]
+    int n_stations = 0;
+    int64_t n_met_steps = 0;
     int64_t ncal = 0;
     int nmon_slots = 0;
     short mslot[HSP2G_NMON];
@@ -194,6 +200,15 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.mon = b->mon;
     L.forc = d_forc;
     L.out = d_out;
+    if (b->met) {
+        if (t0 + nsteps > b->n_met_steps)
+            return fail("intervals [%lld, %lld) outside the shared met series (%lld intervals)", (long long)t0,
+                        (long long)(t0 + nsteps), (long long)b->n_met_steps);
+        L.met = b->met + (size_t)t0 * b->nf * b->n_stations;
+        L.station = b->station;
+        L.mfac = b->mfac;
+        L.n_stations = b->n_stations;
+    }
     L.cal = b->cal + t0;
     L.ntiles = (int)b->ntiles;
     L.mon_rows = 12 * b->nmon_slots;
@@ -383,6 +398,9 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     cudaFree(b->mon);
     cudaFree(b->d_counter);
     cudaFree(b->d_progress);
+    cudaFree(b->met);
+    cudaFree(b->station);
+    cudaFree(b->mfac);
     cudaFree(b->cal);
     for (auto &s : b->slot) {
         cudaFree(s.forc);
@@ -505,6 +523,41 @@ int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *ids, con
     return 0;
 }
 
+int hsp2g_set_shared_forcing(hsp2g_batch *b, int32_t n_stations, int64_t n_steps, const double *series,
+                             const int32_t *station, const double *mfactor, int64_t ld) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    CU(cudaDeviceSynchronize());
+    cudaFree(b->met);
+    cudaFree(b->station);
+    cudaFree(b->mfac);
+    b->met = nullptr;
+    b->station = nullptr;
+    b->mfac = nullptr;
+    b->n_stations = 0;
+    b->n_met_steps = 0;
+    if (n_stations == 0) return 0;  // back to per-segment forcings
+    if (b->nf <= 0) return fail("hsp2g_set_forcing_layout must name the rows before hsp2g_set_shared_forcing");
+    if (!series || !station || !mfactor) return fail("null argument");
+    if (n_stations < 0 || n_steps <= 0 || ld < b->n_seg) return fail("bad shared forcing shape");
+    std::vector<int> st((size_t)b->n_pad);
+    for (int64_t i = 0; i < b->n_pad; ++i) {
+        const int64_t seg = i < b->n_seg ? i : b->n_seg - 1;
+        if (station[seg] < 0 || station[seg] >= n_stations) return fail("station index %d of segment %lld out of range", station[seg], (long long)seg);
+        st[(size_t)i] = station[seg];
+    }
+    const size_t met_bytes = (size_t)n_steps * b->nf * n_stations * sizeof(double);
+    CU(cudaMalloc((void **)&b->met, met_bytes));
+    CU(cudaMemcpy(b->met, series, met_bytes, cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&b->station, st.size() * sizeof(int)));
+    CU(cudaMemcpy(b->station, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&b->mfac, (size_t)b->ntiles * b->nf * LAND_TILE * sizeof(double)));
+    if (upload_rows(b->mfac, b->nf, 0, mfactor, ld, b->n_seg, b->ntiles, b->nf)) return 1;
+    b->n_stations = n_stations;
+    b->n_met_steps = n_steps;
+    return 0;
+}
+
 int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *ids) {
     if (!b || (n_rows > 0 && !ids)) return fail("null argument");
     if (n_rows < 0 || n_rows > HSP2G_NOUT) return fail("n_rows out of range");
@@ -522,7 +575,7 @@ int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *ids) {
 
 int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, void *stream) {
     if (check_ready(b, t0, nsteps)) return 1;
-    if (b->nf > 0 && !d_forc) return fail("null forcing pointer");
+    if (b->nf > 0 && !d_forc && !b->met) return fail("null forcing pointer");
     if (b->ns > 0 && !d_out) return fail("null output pointer");
     if (((uintptr_t)d_forc | (uintptr_t)d_out) & 15) return fail("device series must be 16-byte aligned (TMA bulk copies)");
     DeviceGuard g(b->device);
@@ -531,13 +584,14 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
 
 int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, double *h_out) {
     if (check_ready(b, t0, nsteps)) return 1;
-    if (b->nf > 0 && !h_forc) return fail("null forcing buffer");
+    if (b->nf > 0 && !h_forc && !b->met) return fail("null forcing buffer");
+    if (b->met) h_forc = nullptr;  // shared-met mode: nothing to copy in
     if (b->ns > 0 && !h_out) return fail("null output buffer");
     DeviceGuard g(b->device);
     Slot &s = b->slot[b->next_slot];
     b->next_slot ^= 1;
     const size_t row = (size_t)b->n_pad * sizeof(double);
-    const size_t need_f = row * (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0);
+    const size_t need_f = b->met ? 0 : row * (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0);
     const size_t need_o = row * (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0) / (b->out_f32 ? 2 : 1);
     if (need_f > s.cap_f || need_o > s.cap_o) {
         CU(cudaEventSynchronize(s.d2h_done));

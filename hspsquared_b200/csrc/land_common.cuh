@@ -72,6 +72,12 @@ struct LandLaunch {
     const double *forc;
     double *out;
     const CalStep *cal;  // already offset to the first interval of this chunk
+    // shared-met mode (hsp2g_set_shared_forcing): forc is unused; interval t, row r of a segment is
+    // met[(t*nf + r)*n_stations + station[seg]] * mfac[tile][r][lane]   (get_timeseries' series * MFACTOR)
+    const double *met;   // already offset to the first interval of this chunk; nullptr = per-segment forcings
+    const int *station;  // [tile][32]
+    const double *mfac;  // [tile][nf][32]
+    int n_stations;
     int ntiles;
     int nsteps;
     int sub;          // intervals per task; a task = (tile, sub-chunk) (see Sched)
@@ -228,19 +234,34 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
 }
 
-struct Pipe {
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// SHARED = false: per-segment forcings, one TMA bulk copy per warp-interval (above).
+// SHARED = true : forcings come from a small table of met-station series shared by all segments; each lane gathers
+//                 its station's value of every row with an 8-byte cp.async (LDGSTS) into the same ring, one group per
+//                 interval, and forcing() multiplies by the segment's MFACTOR at the point of use.  Lanes only ever
+//                 touch their own ring column, so no barrier of any kind is involved.
+template <bool SHARED>
+struct PipeT {
     double *ring;       // this warp's ring (generic pointer into shared memory)
     unsigned ring_s;    // its shared-space address
     unsigned bar_s;     // shared-space address of this warp's first mbarrier
-    const double *src;  // forcings of the current tile: forc + tile * nsteps * nf * 32
+    const double *src;  // SHARED ? met + station of this lane : forcings of the current tile (forc + tile*nsteps*nf*32)
     int stage_elems;    // nf * 32
+    int nf, nst;        // SHARED: rows per interval, stations
     int t_end;          // end of the current task (no copies are issued past it)
     int st;             // stage of the current interval
     unsigned ph;        // its phase parity
     int lane;
 
-    // smem layout: [warp][PIPE_STAGES*nf*32 ring doubles | nhot*32 hot parameters | ncold*32 cold state], then the mbarriers
-    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf, int nhot, int ncold) {
+    // smem layout: [warp][PIPE_STAGES*nf*32 ring | nhot*32 hot parameters (+ nf*32 MFACTORs when SHARED) | ncold*32 cold
+    // state], then the mbarriers
+    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf_, int nhot, int ncold, int nst_) {
+        nf = nf_;
+        nst = nst_;
         stage_elems = nf * LAND_TILE;
         const int warp_elems = PIPE_STAGES * stage_elems + (nhot + ncold) * LAND_TILE;
         ring = smem + (size_t)wib * warp_elems;
@@ -251,26 +272,35 @@ struct Pipe {
         lane = lane_;
         t_end = 0;
         src = nullptr;
-        if (lane == 0) {
-            for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(bar_s + s * 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (!SHARED) {
+            if (lane == 0) {
+                for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(bar_s + s * 8, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
-    __device__ __forceinline__ void issue(int t, int s) {  // lane 0 only
-        if (t < t_end) {
+    __device__ __forceinline__ void issue(int t, int s) {  // SHARED: every lane; else lane 0 only
+        if (SHARED) {
+            if (t < t_end) {
+                double *dst = ring + s * stage_elems + lane;
+                const double *g = src + (size_t)t * nf * nst;
+                for (int r = 0; r < nf; ++r) cp_async8(dst + r * LAND_TILE, g + (size_t)r * nst);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");  // empty groups keep the wait arithmetic uniform
+        } else if (t < t_end) {
             const unsigned bytes = (unsigned)stage_elems * 8u;
             mbar_expect_tx(bar_s + s * 8, bytes);
             bulk_g2s(ring_s + (unsigned)s * bytes, src + (size_t)t * stage_elems, bytes, bar_s + s * 8);
         }
     }
-    // a new task: intervals [t0, t1) of the tile whose forcings start at src_.  Every stage is free here (the previous
-    // task consumed all it issued), so the first PIPE_STAGES intervals go out at once, starting at the current stage.
+    // a new task: intervals [t0, t1).  Every stage is free here (the previous task consumed all it issued), so the first
+    // PIPE_STAGES intervals go out at once, starting at the current stage.
     __device__ __forceinline__ void begin_task(const double *src_, int t0, int t1) {
         src = src_;
         t_end = stage_elems > 0 ? t1 : 0;
-        if (lane == 0) {
+        if (SHARED || lane == 0) {
             int s = st;
             for (int k = 0; k < PIPE_STAGES; ++k) {
                 issue(t0 + k, s);
@@ -280,18 +310,28 @@ struct Pipe {
     }
     // wait for the current interval's forcings; returns this lane's column of the stage
     __device__ __forceinline__ const double *acquire() {
-        if (t_end > 0) mbar_wait(bar_s + st * 8, ph);
+        if (SHARED)
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(PIPE_STAGES - 1) : "memory");
+        else if (t_end > 0)
+            mbar_wait(bar_s + st * 8, ph);
         return ring + st * stage_elems + lane;
     }
     __device__ __forceinline__ double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
     __device__ __forceinline__ void release(int t) {
-        __syncwarp();
-        if (lane == 0) issue(t + PIPE_STAGES, st);
+        if (SHARED) {
+            issue(t + PIPE_STAGES, st);
+        } else {
+            __syncwarp();
+            if (lane == 0) issue(t + PIPE_STAGES, st);
+        }
         if (++st == PIPE_STAGES) {
             st = 0;
             ph ^= 1u;
         }
+    }
+    __device__ __forceinline__ void end_task() {
+        if (SHARED) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
 };
 
@@ -341,12 +381,15 @@ struct Sched {
 #else
 // test double: same interface, synchronous copies (no TMA on the host); one "thread" at a time, which walks the
 // sub-chunks of its own tile in order (no tickets)
-struct Pipe {
+template <bool SHARED>
+struct PipeT {
     double *ring;
     const double *src;
-    int stage_elems, lane, t_cur;
-    void init(double *smem, int, int lane_, int nf, int, int) {
+    int stage_elems, lane, t_cur, nf, nst;
+    void init(double *smem, int, int lane_, int nf_, int, int, int nst_) {
         ring = smem;
+        nf = nf_;
+        nst = nst_;
         stage_elems = nf * LAND_TILE;
         lane = lane_;
     }
@@ -355,10 +398,14 @@ struct Pipe {
         t_cur = t0;
     }
     const double *acquire() {
-        for (int i = lane; i < stage_elems; i += LAND_TILE) ring[i] = src[(size_t)t_cur * stage_elems + i];
+        if (SHARED)
+            for (int r = 0; r < nf; ++r) ring[r * LAND_TILE + lane] = src[((size_t)t_cur * nf + r) * nst];
+        else
+            for (int i = lane; i < stage_elems; i += LAND_TILE) ring[i] = src[(size_t)t_cur * stage_elems + i];
         return ring + lane;
     }
     void release(int t) { t_cur = t + 1; }
+    void end_task() {}
     double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
 };
 struct Sched {
@@ -386,14 +433,16 @@ struct Sched {
 #define HSP_PIN(p) asm volatile("" : "+l"(p))
 #endif
 
-template <class IO_, unsigned long long HOT_>
+template <class IO_, unsigned long long HOT_, bool SHARED_ = false>
 struct Seg {
     typedef IO_ IO;
+    static constexpr bool SHARED = SHARED_;
     static constexpr unsigned long long HOT = HOT_;
     static constexpr int NHOT = ce_popc(HOT_);
     const LandLaunch &L;
     double *sb;            // this lane's column of the tile's segment block
     const double *hot;     // this lane's column of the staged hot parameters (shared memory)
+    const double *mfacp;   // SHARED: this lane's column of the staged MFACTORs, one row per forcing row (shared memory)
     const double *monp;    // this lane's column of the tile's monthly tables
     unsigned char *outp;   // this lane's cell of out[tile][t][0] (float64 or float32 rows)
     const double *stage;   // this lane's column of the current forcing stage (shared memory)
@@ -419,6 +468,12 @@ struct Seg {
         for (int id = 0; id < 64 && id < HSP2G_NPAR; ++id)
             if ((HOT >> id) & 1ull) h[(k++) * LAND_TILE] = __ldg(sb + (SB_PAR + id) * LAND_TILE);
         hot = h;  // each lane reads back only what it wrote: no barrier needed
+        mfacp = h + NHOT * LAND_TILE;
+        if (SHARED) {
+            const int nfr = IO::STATIC ? IO::NF : l.nf;
+            const double *mg = l.mfac + ((size_t)tile * nfr * LAND_TILE + lane);
+            for (int r = 0; r < nfr; ++r) h[(NHOT + r) * LAND_TILE] = __ldg(mg + r * LAND_TILE);
+        }
         fl = *reinterpret_cast<const unsigned long long *>(sb + SB_FLAGS * LAND_TILE);
         stage = nullptr;
         calfl = 0;
@@ -451,11 +506,15 @@ struct Seg {
     }
     __device__ __forceinline__ double forcing(int id) const {
         if (IO::STATIC) {
-            if ((IO::FMASK >> id) & 1ull) return stage[hsp_popc(IO::FMASK & ((1ull << id) - 1ull)) * LAND_TILE];
+            if ((IO::FMASK >> id) & 1ull) {
+                const int r = hsp_popc(IO::FMASK & ((1ull << id) - 1ull));
+                return SHARED ? stage[r * LAND_TILE] * mfacp[r * LAND_TILE] : stage[r * LAND_TILE];
+            }
             return L.ffill[id];
         }
         const int r = L.frow[id];
-        return r >= 0 ? stage[r * LAND_TILE] : L.ffill[id];
+        if (r < 0) return L.ffill[id];
+        return SHARED ? stage[r * LAND_TILE] * mfacp[r * LAND_TILE] : stage[r * LAND_TILE];
     }
     // monthly table value for the current day: numpy's slope*(x-x0)+y0 (calendar.py dayval), no FMA
     __device__ __forceinline__ double monthly(int mid) const {

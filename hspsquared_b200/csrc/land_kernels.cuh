@@ -61,28 +61,29 @@ __device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
     return airtmp;
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED>
 __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, perlnd_hot(ACT_CT)> SegT;
+    typedef Seg<IO, perlnd_hot(ACT_CT), SHARED> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER + (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
-    Pipe pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT, NCOLD);
+    PipeT<SHARED> pipe;
+    pipe.init(smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD, L.n_stations);
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {  // one task = intervals [t0, t1) of one tile (land_common.cuh Sched)
-        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
+        pipe.begin_task(SHARED ? L.met + L.station[tile * LAND_TILE + lane] : L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE,
+                        t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
         SnowStateT<SNOWCOLD> sw;
         PwaterState pw;
         SedmntState sd;
         PstempState ps;
-        double *cold = pipe.hot_area() + SegT::NHOT * LAND_TILE + lane;
+        double *cold = pipe.hot_area() + (SegT::NHOT + (SHARED ? nf : 0)) * LAND_TILE + lane;
         sw.bind(cold, s.sb);
         pw.bind(cold + SnowStateT<SNOWCOLD>::SMEM_ROWS * LAND_TILE, s.sb);
         PwtgasDaily pg;
@@ -152,32 +153,34 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
         if (act & HSP2G_ACT_PWATER) pw.store(s);
         if (act & HSP2G_ACT_SEDMNT) sd.store(s);
         if (act & HSP2G_ACT_PSTEMP) ps.store(s);
+        pipe.end_task();
         sched.done(tile);
     }
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED>
 __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, IMPLND_HOT> SegT;
+    typedef Seg<IO, IMPLND_HOT, SHARED> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS;
-    Pipe pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT, NCOLD);
+    PipeT<SHARED> pipe;
+    pipe.init(smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD, L.n_stations);
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {
-        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
+        pipe.begin_task(SHARED ? L.met + L.station[tile * LAND_TILE + lane] : L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE,
+                        t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
         SnowStateT<SNOWCOLD> sw;
         IwaterState iw;
         SolidsState sl;
         IwtgasState ig;
-        sw.bind(pipe.hot_area() + SegT::NHOT * LAND_TILE + lane, s.sb);
+        sw.bind(pipe.hot_area() + (SegT::NHOT + (SHARED ? nf : 0)) * LAND_TILE + lane, s.sb);
         if (act & HSP2G_ACT_SNOW) sw.load(s);
         if (act & HSP2G_ACT_IWATER) iw.load(s);
         if (act & HSP2G_ACT_SOLIDS) sl.load(s);
@@ -219,13 +222,15 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
         if (act & HSP2G_ACT_IWATER) iw.store(s);
         if (act & HSP2G_ACT_SOLIDS) sl.store(s);
         if (act & HSP2G_ACT_IWTGAS) ig.store(s);
+        pipe.end_task();
         sched.done(tile);
     }
 }
 
 // dynamic shared memory of one block: per warp PIPE_STAGES interval stages + the hot parameters + one mbarrier per stage
-static inline size_t land_smem_bytes(int nf, unsigned long long hot, int ncold) {
-    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + ncold) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
+static inline size_t land_smem_bytes(int nf, unsigned long long hot, int ncold, bool shared) {
+    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + (shared ? nf : 0) + ncold) * LAND_TILE * sizeof(double) +
+                                 PIPE_STAGES * 8);
 }
 // cold-state rows of a kernel instantiation (must mirror the NCOLD constants inside the kernels)
 template <bool HOURLY, class IO, int ACT_CT>

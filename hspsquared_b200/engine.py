@@ -160,7 +160,45 @@ class LandBatch:
 
     def run_device(self, t0, nsteps, d_forcing, d_out, stream=0):
         """Device-resident pass: d_forcing [ntiles][nsteps][nf][32], d_out [ntiles][nsteps][ns][32] device pointers."""
-        _lib.check(self.lib.hsp2g_run_device(self.h, int(t0), int(nsteps), d_forcing, d_out, stream or None))
+        _lib.check(self.lib.hsp2g_run_device(self.h, int(t0), int(nsteps), d_forcing or None, d_out, stream or None))
+
+    def set_shared_forcing(self, series, station, mfactor=None):
+        """Shared-met mode (include/hsp2g.h hsp2g_set_shared_forcing): `series` [steps][rows][stations] float64 with rows
+        in the order of the `forcing_names` given to the constructor, `station` int[n] (which station each segment draws
+        on), `mfactor` [rows][n] (default 1.0).  Interval t of segment i then reads series[t][r][station[i]] * mfactor[r][i]
+        -- what get_timeseries computes per segment (utilities.py:274-290) -- and run_shared() needs no forcing arrays."""
+        series = np.ascontiguousarray(np.asarray(series, dtype=np.float64)[:, self._fperm, :])
+        steps, rows, nst = series.shape
+        if rows != self.nf:
+            raise ValueError("series must have %d rows" % self.nf)
+        station = np.asarray(station, dtype=np.int32)
+        mf = np.ones((self.nf, self.n)) if mfactor is None else np.asarray(mfactor, dtype=np.float64)[self._fperm, :]
+        if station.shape != (self.n,) or mf.shape != (self.nf, self.n):
+            raise ValueError("station must be [n], mfactor [rows][n]")
+        if self.order is not None:
+            station, mf = station[self.order], mf[:, self.order]
+        station, mf = np.ascontiguousarray(station), np.ascontiguousarray(mf)
+        _lib.check(self.lib.hsp2g_set_shared_forcing(self.h, nst, steps, _ptr(series), _ptr(station, C.POINTER(C.c_int32)),
+                                                     _ptr(mf), self.n))
+        self.shared_steps = steps
+
+    def run_shared(self, t0=0, steps=None, chunk=None):
+        """Advance over [t0, t0+steps) in shared-met mode -> out [steps][ns][n] (caller's row and segment order)."""
+        steps = self.shared_steps - t0 if steps is None else steps
+        chunk = chunk or steps
+        out = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
+        tiled = []
+        for a in range(0, steps, chunk):
+            b = min(steps, a + chunk)
+            o = np.empty((self.ntiles, b - a, self.ns, _lib.TILE), dtype=self.out_dtype)
+            self._keep.append(o)
+            _lib.check(self.lib.hsp2g_run_host(self.h, int(t0 + a), int(b - a), None, o.ctypes.data))
+            tiled.append((a, b, o))
+        self.sync()
+        for a, b, o in tiled:
+            u = untile_series(o, self.n)[:, self._sinv, :]
+            out[a:b] = u if self._inv is None else u[:, :, self._inv]
+        return out
 
     def sync(self):
         _lib.check(self.lib.hsp2g_sync(self.h))

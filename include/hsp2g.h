@@ -96,6 +96,15 @@ int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const ui
  * let the library pick a kernel specialised at compile time for the row set (see hsp2g_kernel_name). */
 int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *forcing_ids,
                              const double *fill /*[n_forcings]*/, uint32_t opts);
+/* Shared-met mode (replaces get_timeseries' per-segment `series * MFACTOR`, utilities.py:274-290, for watersheds whose
+ * segments draw on a few met stations): the whole run's series of every forcing row, one column per station, live in
+ * HBM once -- series[interval][row][station], rows as named by hsp2g_set_forcing_layout -- and interval t of segment i
+ * reads series[t][row][station[i]] * mfactor[row][i] (one IEEE multiplication, what `temp1 *= MFACTOR` does to a
+ * float64 series).  No forcing crosses PCIe per chunk and the kernels read no per-segment forcing from HBM:
+ * hsp2g_run_device / hsp2g_run_host then take a NULL forcing pointer.  n_stations = 0 switches the mode off. */
+int hsp2g_set_shared_forcing(hsp2g_batch *b, int32_t n_stations, int64_t n_steps, const double *series,
+                             const int32_t *station /*[n_seg]*/, const double *mfactor /*[n_rows][ld]*/, int64_t ld);
+
 /* Which output ids are written (the SAVE table, utilities.py:292-333), row order = ids order (ascending id order
  * enables the specialised kernels). */
 int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *output_ids);

@@ -5,7 +5,7 @@ import copy
 
 import numpy as np
 
-from hspsquared_b200 import _lib, activities
+from hspsquared_b200 import _lib, activities, synth, test10
 from hspsquared_b200.calendar import Calendar
 from hspsquared_b200.engine import ERRORS_OF, LandBatch, pack_forcings
 from hspsquared_b200.segstore import SegmentStore
@@ -144,3 +144,44 @@ def f32_ulp_diff(got32, ref64):
     a = np.where(a < 0, -(a & 0x7FFFFFFF), a)  # sign-magnitude -> monotone integer line
     b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
     return int(np.abs(a - b).max()) if a.size else 0
+
+
+def check_shared_met_mode(n=75):
+    """hsp2g_set_shared_forcing: a few met stations + per-segment station index and MFACTOR give bit-identical results to
+    handing every segment its own series * MFACTOR arrays (what get_timeseries builds, utilities.py:274-290); generic and
+    compile-time-specialised kernels, with and without divergence ordering."""
+    cal = Calendar("1976-02-01", "1976-03-10", 60, "us")
+    steps, nst = cal.steps, 5
+    rng = np.random.default_rng(3)
+    ens = synth.Ensemble("PERLND", n, seed=21, sections=("SNOW", "PWATER"))
+    names = list(synth.PERLND_FORCINGS)
+    s0 = synth.shared_series("PERLND", cal, 0, steps)
+    series = np.empty((steps, len(names), nst))
+    for k in range(nst):  # stations differ by a temperature offset and a rain factor
+        for r, nm in enumerate(names):
+            a = s0[nm].copy()
+            if nm == "AIRTMP":
+                a = a + (k - 2) * 1.5
+            elif nm == "DTMPG":
+                a = (s0["AIRTMP"] + (k - 2) * 1.5) - 5.0
+            elif nm == "PREC":
+                a = a * (1.0 + 0.05 * k)
+            series[:, r, k] = a
+    station = rng.integers(0, nst, n).astype(np.int32)
+    mfac = np.ones((len(names), n))
+    mfac[names.index("PREC")] = 1.0 + 0.2 * ens.u_prec
+    mfac[names.index("PETINP")] = 1.0 + 0.1 * ens.u_pet
+    expanded = series[:, :, station] * mfac[None, :, :]
+    store = ens.store(cal)
+    for save in ("all", ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] +
+                 ["PWATER_" + k for k in test10.SAVE_DEFAULT["PWATER"]]):
+        with LandBatch(store, cal, names, save) as b:
+            ref = b.run(expanded, chunk=300)
+            ref_state = b.get_state()
+        for order in (None, "flags", np.argsort(station, kind="stable")):
+            with LandBatch(store, cal, names, save, order=order) as b:
+                b.set_shared_forcing(series, station, mfac)
+                got = b.run_shared(chunk=300)
+                assert "met=shared" in b.kernel_name()
+                assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
+            assert np.array_equal(got, ref, equal_nan=True)

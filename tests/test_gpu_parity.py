@@ -235,6 +235,12 @@ def test_water_balance_at_full_size():
     assert np.abs(lhs - rhs).max() / scale.max() < 1e-12, np.abs(lhs - rhs).max()
 
 
+def test_shared_met_mode_on_gpu():
+    """Shared-met mode (cp.async gathers from the station table + MFACTOR at the point of use) == per-segment forcing
+    arrays through the TMA ring, bit for bit, on 2,000 segments."""
+    parity.check_shared_met_mode(n=2000)
+
+
 def test_hspf_known_answers(golden_dir):
     """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
     hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))

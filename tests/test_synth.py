@@ -118,3 +118,7 @@ def test_landbatch_order_is_invisible_to_the_caller():
         for k in ref_e:
             assert np.array_equal(e[k], ref_e[k]), k
     assert np.array_equal(store.flags, ens.store(cal).flags)  # the caller's store is untouched
+
+
+def test_shared_met_mode_equals_expanded_forcings():
+    parity.check_shared_met_mode(n=75)

@@ -45,6 +45,10 @@ def run(name, torch, dev):
         n = 100_000
         ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
         forcings, save = list(synth.PERLND_FORCINGS), ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO"]
+    elif name == "perlnd_shared_met":  # headline segments, forcings from 16 met stations + per-segment MFACTOR (own row: never mixed in)
+        n = 100_000
+        ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+        forcings, save = list(synth.PERLND_FORCINGS), bench.default_save()
     elif name == "perlnd_all":
         n = 100_000
         ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
@@ -59,7 +63,33 @@ def run(name, torch, dev):
         note = "segments ordered by option word (SegmentStore.sort_by_flags)"
     batch = LandBatch(store, cal, forcings, save, device=dev.index or 0)
     npad, nf, ns = batch.npad, batch.nf, batch.ns
-    forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(K + W)]
+    shared = name == "perlnd_shared_met"
+    if shared:
+        nst = 16
+        total = (K + W) * Tc
+        s0 = synth.shared_series("PERLND", cal, 0, total)
+        series = np.empty((total, nf, nst))
+        for k in range(nst):
+            for r, nm in enumerate(forcings):
+                a = s0[nm].copy()
+                if nm == "AIRTMP":
+                    a = a + (k - nst / 2) * 0.4
+                elif nm == "DTMPG":
+                    a = (s0["AIRTMP"] + (k - nst / 2) * 0.4) - 5.0
+                series[:, r, k] = a
+        station = np.minimum((np.argsort(np.argsort(ens.u_airt)) * nst // n), nst - 1).astype(np.int32)
+        mfac = np.ones((nf, n))
+        mfac[forcings.index("PREC")] = 1.0 + 0.2 * ens.u_prec
+        mfac[forcings.index("PETINP")] = 1.0 + 0.1 * ens.u_pet
+        batch.set_shared_forcing(series, station, mfac)
+        note = "forcings: %d met stations x MFACTOR (hsp2g_set_shared_forcing); no per-segment forcing in HBM" % nst
+
+        class _Null:
+            def data_ptr(self):
+                return 0
+        forc = [_Null() for _ in range(K + W)]
+    else:
+        forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(K + W)]
     outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
     stream = torch.cuda.Stream(dev)
     torch.cuda.synchronize(dev)
@@ -74,7 +104,7 @@ def run(name, torch, dev):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     peak, _src = bench.measured_peak()
-    B = 8 * (nf + ns)
+    B = 8 * ((0 if shared else nf) + ns)
     value = n * Tc * K / (ms * 1e-3)
     line = {"config": name, "kernel": batch.kernel_name(), "segments": n, "intervals_per_step": Tc, "steps": K,
             "forcing_rows": nf, "saved_rows": ns, "bytes_per_segment_interval": B, "ms_per_step": ms / K,
@@ -91,7 +121,7 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    for name in sys.argv[1:] or ["implnd", "perlnd_flows", "perlnd_all", "fullchain", "fullchain_sorted", "fullchain_cbp10", "perlnd_1m"]:
+    for name in sys.argv[1:] or ["implnd", "perlnd_flows", "perlnd_all", "perlnd_shared_met", "fullchain", "fullchain_sorted", "fullchain_cbp10", "perlnd_1m"]:
         print(json.dumps(run(name, torch, dev)), flush=True)
 
 
