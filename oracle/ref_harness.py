@@ -166,7 +166,7 @@ def read_wdm(wdmfile):
     return out
 
 
-def transform(series, name, how, siminfo):
+def transform(series, name, how, siminfo, base=None):
     """utilities.transform (utilities.py:83-133) with the one pandas-3 incompatibility (offset / offset at
     :125 and the offset compares at :108,:116) restated for sources coarser than the run step."""
     import pandas as pd
@@ -183,7 +183,7 @@ def transform(series, name, how, siminfo):
         ts = (ts * (tgt / src)).resample(pd.tseries.offsets.Minute(delt)).ffill()
         start, stop, steps = siminfo["start"], siminfo["stop"], siminfo["steps"]
         return ts[start:stop].to_numpy().astype("float64")[0:steps]
-    return u.transform(series.copy(), name, how, siminfo)
+    return (base or u.transform)(series.copy(), name, how, siminfo)
 
 
 def make_siminfo(start, stop, delt=60, units=1):

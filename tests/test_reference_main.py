@@ -1,0 +1,45 @@
+"""The drop-in boundary exercised where the reference itself calls it: the UNMODIFIED `hsp2.hsp2.main.main()` runs test10's
+PERLND P001 and IMPLND I001 over an in-memory IO backend (oracle/ref_main.py) -- once with the reference's
+own Numba activities and once with `hspsquared_b200.activities.install()` patched into its registry
+(configuration.py:45-55) -- and every frame its `save_timeseries` hands to `IOManager.write_ts` must be identical.
+Build-container only: needs /root/reference (skipped elsewhere); the CUDA library is replaced by the CPU test double."""
+import numpy as np
+import pytest
+
+from oracle import ref_harness as H
+
+pytestmark = pytest.mark.skipif(not H.available(), reason="reference tree not present (only in the build container)")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _use_emu(emu_library):
+    yield
+
+
+@pytest.mark.parametrize("saveall", [False, True])
+def test_main_with_dropin_activities_writes_the_same_frames(saveall):
+    from hspsquared_b200 import activities
+    from oracle import ref_main as R
+
+    uci, wdm = R.test10_land_model("1976-01-01", "1976-03-01")
+    ref = R.run_main(uci, wdm, saveall=saveall)
+    cfg = H.load()["configuration"]
+    stock = {op: dict(acts) for op, acts in cfg.activities.items() if op in ("PERLND", "IMPLND")}
+    saved = activities.install(cfg)
+    try:
+        for op in ("PERLND", "IMPLND"):  # the registry really dispatches to the drop-ins
+            for a, fn in activities.ACTIVITIES[op].items():
+                assert cfg.activities[op][a] is fn and stock[op][a] is not fn
+        got = R.run_main(uci, wdm, saveall=saveall)
+    finally:
+        activities.uninstall(saved, cfg)
+    assert cfg.activities["PERLND"]["PWATER"] is stock["PERLND"]["PWATER"]
+    assert set(got) == set(ref) and len(ref) >= 4
+    for key, df in ref.items():
+        g = got[key]
+        assert list(g.columns) == list(df.columns), key
+        assert g.index.equals(df.index), key
+        a, b = g.to_numpy(), df.to_numpy()
+        assert a.dtype == b.dtype == np.float32
+        assert np.array_equal(a, b, equal_nan=True), (key, [c for i, c in enumerate(df.columns)
+                                                            if not np.array_equal(a[:, i], b[:, i], equal_nan=True)])
