@@ -8,6 +8,8 @@ import numpy as np
 from hspsquared_b200 import _lib, activities, synth, test10
 from hspsquared_b200.calendar import Calendar
 from hspsquared_b200.engine import ERRORS_OF, LandBatch, pack_forcings
+from hspsquared_b200.ingest import MetStore, SourceRow, resample
+from hspsquared_b200.wdm import WdmSeries
 from hspsquared_b200.segstore import SegmentStore
 from oracle import cases as CASES
 from oracle import wrappers as W
@@ -185,3 +187,79 @@ def check_shared_met_mode(n=75):
                 assert "met=shared" in b.kernel_name()
                 assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
             assert np.array_equal(got, ref, equal_nan=True)
+
+
+def synthetic_sources():
+    rng = np.random.default_rng(11)
+    t0 = np.datetime64("1976-01-01", "s")
+
+    def mk(dsn, step_s, tcode, tstep, n, scale, offset=0.0):
+        return WdmSeries(dsn, {"TCODE": tcode, "TSSTEP": tstep}, t0 + np.arange(n) * np.timedelta64(step_s, "s"),
+                         (rng.random(n) * scale + offset).astype(np.float32).astype(np.float64))
+
+    days = 120
+    src = {"P1": mk(1, 3600, 3, 1, 24 * days, 0.05), "P2": mk(2, 3600, 3, 1, 24 * days, 0.08),
+           "T1": mk(3, 7200, 3, 2, 12 * days, 30.0, 10.0), "T2": mk(4, 7200, 3, 2, 12 * days, 25.0, 5.0),
+           "E1": mk(5, 86400, 4, 1, days, 0.2), "W1": mk(6, 86400, 4, 1, days, 100.0),
+           "S1": mk(7, 7200, 3, 2, 12 * days, 40.0), "D1": mk(8, 86400, 4, 1, days, 20.0, 5.0)}
+    src["P1"].values[rng.random(24 * days) < 0.8] = 0.0
+    src["P2"].values[rng.random(24 * days) < 0.8] = 0.0
+    return src
+
+
+def _rows(prec, pf, temp, pet_f):
+    return [SourceRow(prec, pf, "SAME", "PREC"), SourceRow(temp, 1.0, "SAME", "AIRTMP"), SourceRow("E1", pet_f, "DIV", "PETINP"),
+            SourceRow("W1", 1.0, "DIV", "WINMOV"), SourceRow("S1", 1.0, "DIV", "SOLRAD"), SourceRow("D1", 1.0, "SAME", "DTMPG")]
+
+
+def check_metstore_shared():
+    """40 segments on 2 rain gages x 2 temperature gages with per-segment PREC MFACTORs: 4 + 2 stations, factors on the
+    device where that is exact, and the shared-met kernels reproduce the per-segment-array kernels bit for bit."""
+    cal = Calendar("1976-01-10", "1976-03-20", 60, "us")
+    src = synthetic_sources()
+    n = 40
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(n):
+        rows.append(_rows("P1" if i % 2 else "P2", float(1.0 + 0.01 * (i % 7)), "T1" if (i // 2) % 2 else "T2",
+                          0.7 if i % 5 else 0.75))
+    rows[3].append(SourceRow("P2", 0.5, "SAME", "PREC"))  # a second row feeding the same target is summed on the host
+    names = list(synth.PERLND_FORCINGS)
+    calls = []
+    ms = MetStore.build(cal, names, rows, lambda k: (calls.append(k), src[k])[1])
+    assert sorted(calls) == sorted(src)  # every source read once
+    assert ms.n_stations == 2 * 2 * 2 + 1 and ms.series.shape == (cal.steps, 6, ms.n_stations)
+    j = names.index("PREC")
+    assert ms.mfactor[j, 5] == 1.0 + 0.01 * 5 and ms.mfactor[j, 3] == 1.0  # the summed target is baked into its own station
+    assert np.all(ms.mfactor[names.index("PETINP")] == 1.0)  # DIV: (x * MFACTOR) * ratio is formed on the host
+    full = ms.expand()
+    # the reference's order of operations, spelled out for two segments
+    for i in (3, 5):
+        acc = {}
+        for r in rows[i]:
+            s = src[r.svolno]
+            v = s.values * r.mfactor if r.mfactor != 1.0 else s.values
+            t = resample(s.times, v, s.step, r.tmemn, r.tran, cal, s.tcode)
+            acc[r.tmemn] = acc[r.tmemn] + t if r.tmemn in acc else t
+        for jj, nm in enumerate(names):
+            assert np.array_equal(full[:, jj, i], acc[nm]), (i, nm)
+    ens = synth.Ensemble("PERLND", n, seed=3, sections=("SNOW", "PWATER"))
+    store = ens.store(cal)
+    save = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + k for k in test10.SAVE_DEFAULT["PWATER"]]
+    with LandBatch(store, cal, names, save) as b:
+        ref = b.run(full, chunk=500)
+        ref_state = b.get_state()
+    with LandBatch(store, cal, names, save, order="flags") as b:
+        ms.apply(b)
+        got = b.run_shared(chunk=500)
+        assert "met=shared" in b.kernel_name()
+        assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
+    assert np.array_equal(got, ref, equal_nan=True)
+    assert np.nanmax(ref[:, save.index("SNOW_PACKF")]) > 0 and np.nanmax(ref[:, save.index("PWATER_SURO")]) > 0
+    with LandBatch(store, cal, names[:5] + ["CLOUD"], save) as b:
+        try:
+            ms.apply(b)
+        except ValueError:
+            pass
+        else:
+            raise AssertionError("a store built for other forcings was accepted")

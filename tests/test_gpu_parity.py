@@ -264,3 +264,8 @@ def test_hspf_known_answers(golden_dir):
         ok = ref > -1e29
         assert np.array_equal(ok, g > -1e29), key
         assert np.abs(g[ok] - ref[ok]).max() <= 2e-6 * np.abs(ref[ok]).max(), key
+
+
+def test_metstore_feeds_shared_met_kernels():
+    """EXT SOURCES rows -> MetStore (hspsquared_b200/ingest.py) -> hsp2g_set_shared_forcing: bit-identical to per-segment arrays."""
+    parity.check_metstore_shared()
