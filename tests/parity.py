@@ -2,6 +2,7 @@
 (c) the drop-in activities, and compare.  Used by the CPU suite (against the host-compiled test double, bit-exact) and
 by the `-m gpu` suite (against the CUDA library through the C ABI, <= 1e-9 relative, integers exact)."""
 import copy
+import os
 
 import numpy as np
 
@@ -263,3 +264,125 @@ def check_metstore_shared():
             pass
         else:
             raise AssertionError("a store built for other forcings was accepted")
+
+
+class FrameSink:
+    """Records write_ts calls: the SupportsWriteTS surface as IOManager exposes it (hsp2io/io.py:58-66)."""
+
+    def __init__(self):
+        self.calls, self.bytes = {}, 0
+
+    def write_ts(self, data_frame, save_columns, category, operation=None, segment=None, activity=None, compress=True,
+                 outstep=2):
+        self.calls[(operation, segment, activity)] = (data_frame, list(save_columns))
+        self.bytes += data_frame.to_numpy().nbytes
+
+
+def write_gage_wdm(path, start, days, gages):
+    """A synthetic WDM file of `gages` met stations built from test10's 1976 met (datasets 100g+1 .. 100g+6: hourly PREC,
+    2-hourly ATMP, daily EVAP, daily WIND, 2-hourly SOLR, daily DEWP), written with tests/wdm_writer.py."""
+    from tests.wdm_writer import write_wdm
+
+    start = np.datetime64(start, "s")
+    cal = Calendar(start, start + np.timedelta64(days, "D"), 60, "ns")
+    m = synth.shared_series("PERLND", cal, 0, cal.steps)
+    sets = []
+    for g in range(gages):
+        hourly = lambda a: a
+        two = lambda a: a.reshape(-1, 2)
+        day = lambda a: a.reshape(-1, 24)
+        series = {1: (3, 1, hourly(m["PREC"]) * (1.0 + 0.04 * g)),
+                  2: (3, 2, two(m["AIRTMP"])[:, 0] + 0.8 * (g - gages / 2)),
+                  3: (4, 1, day(m["PETINP"]).sum(axis=1) / 0.7),
+                  4: (4, 1, day(m["WINMOV"]).sum(axis=1)),
+                  5: (3, 2, two(m["SOLRAD"]).sum(axis=1)),
+                  6: (4, 1, day(m["DTMPG"])[:, 0] + 0.8 * (g - gages / 2))}
+        for k, (tcode, tstep, v) in series.items():
+            v = np.asarray(v, dtype=np.float32)
+            # yearly groups; long hourly records are cut into blocks, and runs of zeros are stored compressed
+            blocks, i = [], 0
+            while i < len(v):
+                j = i
+                if v[i] == 0.0:
+                    while j < len(v) and v[j] == 0.0 and j - i < 30000:
+                        j += 1
+                    blocks.append((v[i:j], True))
+                else:
+                    while j < len(v) and v[j] != 0.0 and j - i < 400:
+                        j += 1
+                    blocks.append((v[i:j], False))
+                i = j
+            year_end = (start.astype("datetime64[Y]") + 1).astype("datetime64[s]")  # a group is always full: pad with TFILL
+            per = np.timedelta64(3600 * tstep if tcode == 3 else 86400 * tstep, "s")
+            missing = int((year_end - start) / per) - len(v)
+            if missing > 0:
+                blocks.append((np.full(missing, -999.0, dtype=np.float32), True))
+            sets.append({"dsn": 100 * g + k, "tcode": tcode, "tstep": tstep, "tgroup": 6, "groups": [(start, blocks)]})
+    write_wdm(path, sets)
+
+
+def check_watershed(tmpdir, n=48, gages=4, days=40, sample=(0, 7, 21), chunk=480):
+    """BASELINE.json configs[4] in miniature: a watershed of `n` PERLND segments running the full chain with per-segment option
+    flags draws its forcings from a WDM file of `gages` met stations (WdmFile -> MetStore -> shared-met kernels, no per-segment
+    forcing arrays), and its SAVEd series leave as the float32 frames save_timeseries builds (results.save_batch).  Sampled
+    segments must equal the oracle run on get_timeseries-style arrays, after the float32 cast, bit for bit."""
+    import pandas as pd
+
+    from hspsquared_b200.results import save_batch
+    from hspsquared_b200.wdm import WdmFile
+
+    path = os.path.join(str(tmpdir), "gages.wdm")
+    start = "1976-01-01"
+    write_gage_wdm(path, start, days + 2, gages)
+    stop = np.datetime64(start, "s") + np.timedelta64(days, "D")
+    cal = Calendar(start, stop, 60, "us")
+    wdm = WdmFile(path)
+    assert len(wdm.dsns) == 6 * gages
+    ens = synth.Ensemble("PERLND", n, seed=99, base="cbp", options=("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    member = {"PREC": (1, "SAME"), "GATMP": (2, "SAME"), "PETINP": (3, "DIV"), "WINMOV": (4, "DIV"), "SOLRAD": (5, "DIV"),
+              "DTMPG": (6, "SAME")}
+    rows = []
+    for i in range(n):
+        g = (i * 7) % gages
+        rows.append([SourceRow("TS%03d" % (100 * g + member[nm][0]),
+                               (1.0 + 0.02 * (i % 5)) if nm == "PREC" else 0.7 if nm == "PETINP" else 1.0, member[nm][1], nm)
+                     for nm in names])
+    ms = MetStore.build(cal, names, rows, lambda k: wdm.series(int(k[2:])))
+    assert ms.n_stations == gages
+    store = ens.store(cal)
+    with LandBatch(store, cal, names, "all", order="flags") as b:
+        ms.apply(b)
+        b.set_output_dtype(np.float32)
+        out = b.run_shared(chunk=chunk)
+        saved = b.save
+        assert "met=shared" in b.kernel_name()
+    acts = ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS")
+    save_tables = {}
+    for full in saved:
+        a, k = full.split("_", 1)
+        save_tables.setdefault(a, {})[k] = 1
+    assert set(save_tables) == set(acts) and len(saved) == 84
+    tindex = pd.date_range(start, periods=cal.steps + 1, freq="60min")[1:]  # main.py:93-95
+    sink = FrameSink()
+    seg_names = ["P%04d" % (i + 1) for i in range(n)]
+    save_batch(sink, {"tindex": tindex}, "PERLND", seg_names, save_tables, saved, out)
+    assert len(sink.calls) == n * len(acts)
+    for i in sample:
+        f = ms.expand(segments=[i])[:, :, 0]
+        ts = {nm: np.ascontiguousarray(f[:, j]) for j, nm in enumerate(names)}
+        si = {"start": cal.start, "stop": cal.stop, "delt": 60, "units": 1, "steps": cal.steps, "time_unit": "us"}
+        CASES.run_segment("PERLND", ens.tables_of(i), ts, si, ORACLE_ACTS)
+        for a in acts:
+            df, cols = sink.calls[("PERLND", seg_names[i], a)]
+            assert list(df.columns) == sorted(save_tables[a]) and sorted(cols) == sorted(save_tables[a])
+            for k in df.columns:
+                with np.errstate(over="ignore"):
+                    want = ts[k].astype(np.float32)
+                got = df[k].to_numpy()
+                assert got.dtype == np.float32
+                if GPU_EXACT:
+                    assert np.array_equal(got, want, equal_nan=True), (i, a, k)
+                else:
+                    assert f32_ulp_diff(got, ts[k]) <= 2, (i, a, k)
+    return sink

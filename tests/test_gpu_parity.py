@@ -269,3 +269,9 @@ def test_hspf_known_answers(golden_dir):
 def test_metstore_feeds_shared_met_kernels():
     """EXT SOURCES rows -> MetStore (hspsquared_b200/ingest.py) -> hsp2g_set_shared_forcing: bit-identical to per-segment arrays."""
     parity.check_metstore_shared()
+
+
+def test_watershed_wdm_to_frames(tmp_path):
+    """BASELINE.json configs[4] in miniature on the GPU: 3,000 full-chain segments on 12 gages of a WDM file, three simulated
+    months, float32 frames out; sampled segments equal the oracle."""
+    parity.check_watershed(tmp_path, n=3000, gages=12, days=90, sample=(0, 1234, 2999), chunk=720)

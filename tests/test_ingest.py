@@ -58,6 +58,12 @@ def test_metstore_layout_and_shared_kernels(emu_library):
     parity.check_metstore_shared()
 
 
+def test_watershed_wdm_to_frames(emu_library, tmp_path):
+    """WDM file -> MetStore -> shared-met full-chain kernels -> save_timeseries frames, against the oracle."""
+    sink = parity.check_watershed(tmp_path)
+    assert sink.bytes == 48 * 84 * 40 * 24 * 4
+
+
 @needs_ref
 def test_metstore_on_test10_ext_sources_matches_reference():
     """test10's EXT SOURCES (test10.uci:891-914) through WdmFile + MetStore == the arrays the reference's get_timeseries
