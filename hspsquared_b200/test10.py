@@ -94,3 +94,42 @@ def perlnd():
 
 def implnd():
     return copy.deepcopy(I001)
+
+
+def iqual_tables():
+    """IQUAL of IMPLND 1 (test10.uci:272-290: one constituent, COD, associated with solids and with overland flow) the way
+    readUCI lays it out (readUCI.py:690-711 per-constituent tables, :252-258 LAT-FACTOR defaults)."""
+    return {
+        "PARAMETERS": {"NQUAL": 1, "SDLFAC": 0.0, "SLIFAC": 0.0},
+        "IQUAL1_FLAGS": {"QUALID": "COD", "QTYID": "LB", "QSDFG": 1, "VPFWFG": 0, "QSOFG": 1, "VQOFG": 0},
+        "IQUAL1_PARAMETERS": {"SQO": 1.20, "POTFW": 0.175, "ACQOP": 0.02, "SQOLIM": 2.0, "WSQOP": 1.7},
+    }
+
+
+def pqual_tables():
+    """A three-constituent PQUAL block (the table layout of readUCI.py:690-711; flag combinations after
+    tests/GRW_Plaster/HSPF.uci:1385-1560): sediment-associated, overland-flow-associated with subsurface concentrations,
+    and QSOFG=2 with atmospheric deposition."""
+    return {
+        "PARAMETERS": {"NQUAL": 3, "SDLFAC": 0.0, "SLIFAC": 0.3, "ILIFAC": 0.2, "ALIFAC": 0.1},
+        "FLAGS": dict({"PQADFG%d" % k: 0 for k in range(1, 21)}, PQADFG5=1, PQADFG6=1),
+        "PQUAL1_FLAGS": {"QUALID": "PO4", "QTYID": "LB", "QSDFG": 1, "VPFWFG": 1, "VPFSFG": 0, "QSOFG": 0, "VQOFG": 0,
+                         "QIFWFG": 0, "VIQCFG": 0, "QAGWFG": 0, "VAQCFG": 0},
+        "PQUAL1_PARAMETERS": {"SQO": 0.0, "POTFW": 1.2, "POTFS": 0.3, "ACQOP": 0.0, "SQOLIM": 0.000001, "WSQOP": 1.64,
+                              "IOQC": 0.0, "AOQC": 0.0},
+        "PQUAL1_MONTHLY/POTFW": monthly([1.0, 1.0, 1.1, 1.3, 1.5, 1.8, 2.0, 2.0, 1.7, 1.4, 1.2, 1.0]),
+        "PQUAL2_FLAGS": {"QUALID": "E.COLI", "QTYID": "CFU", "QSDFG": 0, "VPFWFG": 0, "VPFSFG": 0, "QSOFG": 1, "VQOFG": 1,
+                         "QIFWFG": 1, "VIQCFG": 1, "QAGWFG": 1, "VAQCFG": 3},
+        "PQUAL2_PARAMETERS": {"SQO": 4.0e8, "POTFW": 0.0, "POTFS": 0.0, "ACQOP": 1.0e6, "SQOLIM": 8.0e8, "WSQOP": 0.7,
+                              "IOQC": 2.83e3, "AOQC": 1.42e3},
+        "PQUAL2_MONTHLY/ACQOP": monthly([1.0e6, 1.0e6, 1.5e6, 2.0e6, 3.0e6, 4.0e6, 4.0e6, 4.0e6, 3.0e6, 2.0e6, 1.5e6, 1.0e6]),
+        "PQUAL2_MONTHLY/SQOLIM": monthly([8.0e8, 8.0e8, 9.0e8, 1.0e9, 1.2e9, 1.4e9, 1.4e9, 1.4e9, 1.2e9, 1.0e9, 9.0e8, 8.0e8]),
+        "PQUAL2_MONTHLY/IOQC": monthly([2.0e3, 2.0e3, 2.4e3, 2.8e3, 3.2e3, 3.6e3, 3.6e3, 3.6e3, 3.2e3, 2.8e3, 2.4e3, 2.0e3]),
+        "PQUAL2_MONTHLY/AOQC": monthly([10., 10., 11., 12., 13., 14., 14., 14., 13., 12., 11., 10.]),
+        "PQUAL3_FLAGS": {"QUALID": "NH3", "QTYID": "LB", "QSDFG": 1, "VPFWFG": 0, "VPFSFG": 0, "QSOFG": 2, "VQOFG": 0,
+                         "QIFWFG": 1, "VIQCFG": 0, "QAGWFG": 1, "VAQCFG": 0},
+        "PQUAL3_PARAMETERS": {"SQO": 0.6, "POTFW": 0.4, "POTFS": 0.1, "ACQOP": 0.05, "SQOLIM": 1.0, "WSQOP": 1.1,
+                              "IOQC": 0.8, "AOQC": 0.3},
+        "PQUAL3_MONTHLY/PQADFX": monthly([.001, .001, .002, .002, .003, .003, .003, .003, .002, .002, .001, .001]),
+        "PQUAL3_MONTHLY/PQADCN": monthly([.01, .01, .012, .014, .016, .018, .018, .016, .014, .012, .01, .01]),
+    }

@@ -14,8 +14,8 @@ from hspsquared_b200 import cbp, test10
 from hspsquared_b200.test10 import monthly
 
 ORDER = {
-    "PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"),  # configuration.py:48-50
-    "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS"),  # configuration.py:51-52 (IQUAL out of scope)
+    "PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS", "PQUAL"),  # configuration.py:48-50
+    "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS", "IQUAL"),  # configuration.py:51-52
 }
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hspsquared_b200", "data")
@@ -92,6 +92,14 @@ def forcings(case):
         out[n] = np.where(a > 0.97, 0.02 * rng.random(steps), 0.0)
     for n, (lo, hi) in case.get("lateral_conc", {}).items():
         out[n] = lo + (hi - lo) * rng.random(steps)
+    if case.get("qual_inputs"):  # PQUAL alone: every flow and sediment series it reads is an external series
+        wet = out["PREC"] > 0.0
+        out["SURO"] = np.where(wet, 0.6 * out["PREC"], 0.0) * rng.random(steps)
+        out["IFWO"] = 0.002 * rng.random(steps) * (rng.random(steps) > 0.3)
+        out["AGWO"] = 0.001 + 0.001 * rng.random(steps)
+        out["PERO"] = out["SURO"] + out["IFWO"] + out["AGWO"]
+        out["WSSD"] = np.where(out["SURO"] > 0.0, 0.05 * rng.random(steps), 0.0)
+        out["SCRSD"] = np.where(out["SURO"] > 0.01, 0.01 * rng.random(steps), 0.0)
     if case.get("runoff_inputs"):  # SURO / SURS given as external series (the sections that make them are off)
         out["SURO"] = np.where(out["PREC"] > 0.0, 0.8 * out["PREC"], 0.0) * rng.random(steps)
         out["SURS"] = 0.05 * rng.random(steps)
@@ -237,6 +245,48 @@ def build_cases():
     t["ACTIVITY"].update({"SNOW": 0, "IWATER": 0, "IWTGAS": 1})
     t["IWTGAS"]["STATES"] = {"SOTMP": 60.0, "SODOX": 0.0, "SOCO2": 0.0}
     add("i_solids_iwtgas_alone", "IMPLND", t, "implnd", steps=24 * 120, runoff_inputs=True)
+
+    # -- IQUAL: test10's I001 as shipped (one constituent, COD: QSDFG=1, QSOFG=1; test10.uci:274-290) --------------
+    t = test10.implnd()
+    t["ACTIVITY"]["IQUAL"] = 1
+    t["IQUAL"] = test10.iqual_tables()
+    add("i001_iqual", "IMPLND", t, "implnd")
+    # three constituents: QSOFG=2 with monthly accumulation / limit and atmospheric deposition (monthly flux and
+    # concentration); the constant-concentration special case QSOFG=-1; solids-associated with monthly potency, lateral potency
+    t = test10.implnd()
+    t["ACTIVITY"]["IQUAL"] = 1
+    t["IQUAL"] = {
+        "PARAMETERS": {"NQUAL": 3, "SDLFAC": 0.0, "SLIFAC": 0.35},
+        "FLAGS": {"IQADFG%d" % k: 0 for k in range(1, 21)},
+        "IQUAL1_FLAGS": {"QUALID": "NO3", "QTYID": "LB", "QSDFG": 0, "VPFWFG": 0, "QSOFG": 2, "VQOFG": 1},
+        "IQUAL1_PARAMETERS": {"SQO": 0.8, "POTFW": 0.0, "ACQOP": 0.03, "SQOLIM": 1.5, "WSQOP": 0.9},
+        "IQUAL1_MONTHLY/ACQOP": monthly([.02, .02, .025, .03, .035, .04, .04, .04, .035, .03, .025, .02]),
+        "IQUAL1_MONTHLY/SQOLIM": monthly([1., 1., 1.2, 1.4, 1.6, 1.8, 1.8, 1.8, 1.6, 1.4, 1.2, 1.]),
+        "IQUAL1_MONTHLY/IQADFX": monthly([.001, .001, .002, .002, .003, .003, .003, .003, .002, .002, .001, .001]),
+        "IQUAL1_MONTHLY/IQADCN": monthly([.01, .01, .012, .014, .016, .018, .018, .016, .014, .012, .01, .01]),
+        "IQUAL2_FLAGS": {"QUALID": "CL", "QTYID": "LB", "QSDFG": 0, "VPFWFG": 0, "QSOFG": -1, "VQOFG": 0},
+        "IQUAL2_PARAMETERS": {"SQO": 0.0, "POTFW": 0.0, "ACQOP": 12.0, "SQOLIM": 1.0, "WSQOP": 1.64},
+        "IQUAL3_FLAGS": {"QUALID": "PB", "QTYID": "LB", "QSDFG": 1, "VPFWFG": 1, "QSOFG": 0, "VQOFG": 0},
+        "IQUAL3_PARAMETERS": {"SQO": 0.4, "POTFW": 0.2, "ACQOP": 0.0, "SQOLIM": 0.000001, "WSQOP": 1.64},
+        "IQUAL3_MONTHLY/POTFW": monthly([.1, .1, .12, .15, .2, .25, .25, .25, .2, .15, .12, .1]),
+    }
+    t["IQUAL"]["FLAGS"].update({"IQADFG1": 1, "IQADFG2": 2})
+    add("i_iqual_variants", "IMPLND", t, "implnd", rain_mult=2.0, lateral_conc={"SLIQSP": (-0.2, 0.6)})
+
+    # -- PQUAL on the CBP full chain: sediment-associated with monthly potency; overland-flow-associated with monthly
+    #    accumulation / limit + interflow and groundwater concentrations (monthly, mg/l flavour VAQCFG=3); QSOFG=2 with
+    #    atmospheric deposition, constant concentrations, lateral concentrations ------------------------------------------
+    t = _cbp_tables()
+    t["ACTIVITY"]["PQUAL"] = 1
+    t["PQUAL"] = test10.pqual_tables()
+    add("cbp_pqual", "PERLND", t, "perlnd", drop=("CLOUD",), gatmp=2.0, rain_mult=2.0,
+        lateral_conc={"SLIQSP": (-0.3, 1.0), "ILIQC": (-5.0, 20.0), "ALIQC": (-5.0, 20.0)})
+    # PQUAL alone on external flow / sediment series; constituent 2 takes deposition without QSOFG (errors[0] = 1)
+    t = {"ACTIVITY": {"PQUAL": 1}, "PQUAL": test10.pqual_tables()}
+    t["PQUAL"]["PQUAL2_FLAGS"].update({"QSOFG": 0})
+    t["PQUAL"]["FLAGS"].update({"PQADFG3": 1})
+    t["PQUAL"]["PQUAL2_MONTHLY/PQADFX"] = monthly([.001] * 12)
+    add("p_pqual_alone", "PERLND", t, "perlnd", steps=24 * 150, qual_inputs=True)
 
     # -- the reference's own unit-test cases (tests/ipwater/test_ipwater.py:43-84) ----------------
     fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}

@@ -76,6 +76,8 @@ def gen_hbn():
     for act, names in (("SOLIDS", ("SLDS", "SOSLD")), ("IWTGAS", ("SOTMP", "SODOX", "SOCO2", "SOHT", "SODOXM", "SOCO2M"))):
         for cons in names:
             out["%s_%s" % (act, cons)] = hbn.get_time_series("IMPLND", 1, cons, act, "hourly").values.astype(np.float64)
+    for cons in ("SQO", "SOQSP", "SOQOC", "SOQC", "SOQS", "SOQO", "SOQUAL"):  # IQUAL group; HSPF appends the QUALID (COD)
+        out["IQUAL_" + cons] = hbn.get_time_series("IMPLND", 1, cons + "COD", "IQUAL", "hourly").values.astype(np.float64)
     np.savez_compressed(os.path.join(GOLD, "hspf_test10I.npz"), **out)
 
 
@@ -83,7 +85,8 @@ def ref_activities():
     m = H.load()
     return {"ATEMP": m["ATEMP"].atemp, "SNOW": m["SNOW"].snow, "PWATER": m["PWATER"].pwater,
             "IWATER": m["IWATER"].iwater, "SEDMNT": m["SEDMNT"].sedmnt, "PSTEMP": m["PSTEMP"].pstemp,
-            "PWTGAS": m["PWTGAS"].pwtgas, "SOLIDS": m["SOLIDS"].solids, "IWTGAS": m["IWTGAS"].iwtgas}
+            "PWTGAS": m["PWTGAS"].pwtgas, "SOLIDS": m["SOLIDS"].solids, "IWTGAS": m["IWTGAS"].iwtgas,
+            "PQUAL": m["PQUAL"].pqual, "IQUAL": m["IQUAL"].iqual}
 
 
 def run_reference(case):
@@ -103,9 +106,15 @@ def run_reference(case):
     return {k: np.asarray(ts[k]) for k in ts.keys()}, errs
 
 
-def gen_cases():
+def gen_cases(only=None):
+    """only: iterable of case names to (re)generate; the other records of reference_hashes.json are kept."""
     hashes = {}
+    path = os.path.join(GOLD, "reference_hashes.json")
+    if only and os.path.exists(path):
+        hashes = json.load(open(path))
     for name, case in CASES.build_cases().items():
+        if only and name not in only:
+            continue
         ts, errs = run_reference(case)
         inputs = set(CASES.forcings(case).keys())
         rec = {"series": {}, "errors": {a: [int(x) for x in e] for a, e in errs.items()}, "sums": {}}
@@ -154,6 +163,10 @@ if __name__ == "__main__":
     if not H.available():
         sys.exit("reference tree not found at %s" % H.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1:  # python -m oracle.gen_golden <case> ...: only those cases (and the HSPF file)
+        gen_hbn()
+        gen_cases(set(sys.argv[1:]))
+        sys.exit(0)
     gen_met()
     gen_hbn()
     gen_calendar()

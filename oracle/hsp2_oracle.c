@@ -36,6 +36,8 @@ const char *hsp2o_fields(const char *r) {
     REC(pwtgas, PWTGAS_UI, PWTGAS_IN, PWTGAS_OUT)
     REC(solids, SOLIDS_UI, SOLIDS_IN, SOLIDS_OUT)
     REC(iwtgas, IWTGAS_UI, IWTGAS_IN, IWTGAS_OUT)
+    REC(pqual, PQUAL_UI, PQUAL_IN, PQUAL_OUT)
+    REC(iqual, IQUAL_UI, IQUAL_IN, IQUAL_OUT)
 #undef REC
     if (!strcmp(r, "batch_par")) return FIELDS(BATCH_PAR);
     return "";
@@ -1322,6 +1324,184 @@ void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *ou
             out->SODOX[t] = sodox;
             out->SOCO2[t] = soco2;
         }
+    }
+}
+
+/* ============================================================================================== */
+/* PQUAL  (PQUAL.py:147-397), one constituent, English units                                       */
+/* ============================================================================================== */
+void hsp2o_pqual(const pqual_ui *ui, const pqual_in *in, const pqual_out *out, int64_t nsteps) {
+    const double delt60 = ui->delt60, slifac = ui->SLIFAC, ilifac = ui->ILIFAC, alifac = ui->ALIFAC;
+    const double QSDFG = ui->QSDFG, QSOFG = ui->QSOFG, QIFWFG = ui->QIFWFG, QAGWFG = ui->QAGWFG;
+    double sqo = QSOFG != 0.0 ? ui->SQO : 0.0; /* PQUAL.py:161-164 */
+    const double wsfac = 2.30 / ui->WSQOP;
+    double soqo = 0.0, soqs = 0.0;
+    for (int64_t t = 0; t < nsteps; ++t) {
+        const int dayfg = (int)in->DAYFG[t];
+        const double suro = in->SURO[t], ifwo = in->IFWO[t], agwo = in->AGWO[t], pero = in->PERO[t];
+        const double wssd = in->WSSD[t], scrsd = in->SCRSD[t], sliqsp = in->SLIQSP[t];
+        const double sliqo = 0.0; /* the name is rebound to a zeros output array (PQUAL.py:205,222) */
+        const double potfw = in->POTFW[t], potfs = in->POTFS[t], acqop = in->ACQOP[t], remqop = in->REMQOP[t];
+        const double iliqc = in->ILIQC[t], aliqc = in->ALIQC[t];
+        (void)dayfg;
+        double suroqs = 0.0, soqsp = -1.0e30, scrqs = 0.0, washqs = 0.0;
+        if (QSDFG != 0.0) { /* qualsd, PQUAL.py:250-276 */
+            if (wssd == 0.0)
+                washqs = 0.0;
+            else if (sliqsp >= 0.0)
+                washqs = wssd * (sliqsp * slifac + potfw * (1.0 - slifac));
+            else
+                washqs = wssd * potfw;
+            scrqs = scrsd == 0.0 ? 0.0 : scrsd * potfs;
+            soqs = washqs + scrqs;
+            const double lsosed = wssd + scrsd;
+            soqsp = lsosed > 0.0 ? soqs / lsosed : -1.0e30;
+            suroqs = soqs;
+        }
+        double suroqo = 0.0, adtot = 0.0, adfxfx = 0.0, adcnfx = 0.0, soqoc = -1.0e30;
+        if (QSOFG != 0.0) { /* qualof, PQUAL.py:284-325 */
+            if (dayfg && QSOFG == 1) sqo = acqop + sqo * (1.0 - remqop);
+            adfxfx = in->PQADFX[t];
+            adcnfx = in->PQADCN[t] * in->PREC[t] * 3630.0;
+            adtot = adfxfx + adcnfx;
+            const double intot = adtot + sliqo;
+            if (QSOFG == 2) {
+                double dummy = remqop + intot / (acqop / remqop);
+                if (dummy > 1.0) dummy = 1.0;
+                sqo = acqop * (delt60 / 24.0) + sqo * pow(1.0 - dummy, delt60 / 24.0);
+            }
+            sqo = sqo + intot;
+            soqo = 0.0;
+            if (suro > 0.0 && sqo > 0.0) {
+                double dummy = suro * wsfac;
+                if (dummy < 1.0e-5)
+                    soqo = 0.0;
+                else {
+                    dummy = 1.0 - exp(-dummy);
+                    soqo = sqo * dummy;
+                    sqo = sqo - soqo;
+                }
+            }
+            soqoc = suro > 0.0 ? soqo / suro : -1.0e30;
+            suroqo = soqo;
+        }
+        const double soqual = suroqs + suroqo;
+        double poqual = soqual, ioqual = 0.0, aoqual = 0.0;
+        const double soqc = suro > 0.0 ? soqual / suro : -1.0e30;
+        if (QIFWFG != 0.0) { /* qualif, PQUAL.py:339-353 */
+            double ioqc = in->IOQCP[t] * 3630.0;
+            if (ui->VIQCFG == 3 || ui->VIQCFG == 4) ioqc = ioqc * 6.238e-5;
+            if (ifwo > 0.0) {
+                const double ioqce = iliqc >= 0.0 ? iliqc * ilifac + ioqc * (1.0 - ilifac) : ioqc;
+                ioqual = ioqce * ifwo;
+            } else
+                ioqual = 0.0;
+            poqual = poqual + ioqual;
+        }
+        if (QAGWFG != 0.0) { /* qualgw, PQUAL.py:356-371 */
+            double aoqc = in->AOQCP[t] * 3630.0;
+            if (ui->VAQCFG == 3 || ui->VAQCFG == 4) aoqc = aoqc * 6.238e-5;
+            if (agwo > 0.0) {
+                const double aoqce = aliqc >= 0.0 ? aliqc * alifac + aoqc * (1.0 - alifac) : aoqc;
+                aoqual = aoqce * agwo;
+            } else
+                aoqual = 0.0;
+            poqual = poqual + aoqual;
+        }
+        const double poqc = pero > 0.0 ? poqual / pero : -1.0e30;
+        out->SOQUAL[t] = soqual;
+        out->IOQUAL[t] = ioqual;
+        out->AOQUAL[t] = aoqual;
+        out->POQUAL[t] = poqual;
+        out->SQO[t] = sqo;
+        out->SOQSP[t] = soqsp;
+        out->SOQOC[t] = soqoc > -1 ? soqoc / 3630.0 : soqoc;
+        out->SOQC[t] = soqc / 3630.0;
+        out->IOQC[t] = ifwo > 0.0 ? ioqual / ifwo / 3630.0 : -1.0e30;
+        out->AOQC[t] = agwo > 0.0 ? aoqual / agwo / 3630.0 : -1.0e30;
+        out->POQC[t] = pero > 0.0 ? poqc / 3630.0 : -1.0e30;
+        out->WASHQS[t] = washqs;
+        out->SCRQS[t] = scrqs;
+        out->SOQS[t] = soqs;
+        out->SOQO[t] = soqo;
+        out->PQADWT[t] = adcnfx;
+        out->PQADDR[t] = adfxfx;
+        out->PQADEP[t] = adtot;
+        out->SLIQO[t] = 0.0;  /* allocated, never written (PQUAL.py:205-206) */
+        out->INFLOW[t] = 0.0;
+    }
+}
+
+/* ============================================================================================== */
+/* IQUAL  (IQUAL.py:131-284), one constituent, English units                                       */
+/* ============================================================================================== */
+void hsp2o_iqual(const iqual_ui *ui, const iqual_in *in, const iqual_out *out, int64_t nsteps) {
+    const double delt60 = ui->delt60, slifac = ui->SLIFAC, QSDFG = ui->QSDFG, QSOFG = ui->QSOFG;
+    double sqo = ui->SQO;
+    const double wsfac = 2.30 / ui->WSQOP;
+    double soqo = 0.0, remqop = 0.0, soqs = 0.0, soqoc = 0.0, soqsp = 0.0; /* carried (IQUAL.py:184-188) */
+    for (int64_t t = 0; t < nsteps; ++t) {
+        const double suro = in->SURO[t], sosld = in->SOSLD[t], sliqsp = in->SLIQSP[t];
+        const int dayfg = (int)in->DAYFG[t];
+        const double sliqo = 0.0; /* rebound to a zeros output array (IQUAL.py:174) */
+        const double potfw = in->POTFW[t];
+        double acqop = in->ACQOP[t];
+        double suroqs = 0.0;
+        if (QSDFG != 0.0) { /* washsd, IQUAL.py:201-217 */
+            if (sosld == 0.0)
+                soqs = 0.0;
+            else if (sliqsp >= 0.0) {
+                soqsp = sliqsp * slifac + potfw * (1.0 - slifac);
+                soqs = sosld * soqsp;
+            } else {
+                soqsp = potfw;
+                soqs = sosld * potfw;
+            }
+            suroqs = soqs;
+        }
+        double suroqo = 0.0, adtot = 0.0, adfxfx = 0.0, adcnfx = 0.0;
+        if (QSOFG != 0.0) {
+            if (QSOFG >= 1) { /* washof, IQUAL.py:226-257 */
+                if (dayfg == 1) {
+                    remqop = in->REMQOP[t];
+                    if (QSOFG == 1) sqo = acqop + sqo * (1.0 - remqop);
+                }
+                adfxfx = in->IQADFX[t];
+                adcnfx = in->IQADCN[t] * in->PREC[t] * 3630.0;
+                adtot = adfxfx + adcnfx;
+                if (QSOFG == 2) {
+                    double dummy = remqop + (adtot + sliqo) / (acqop / remqop);
+                    if (dummy > 1.0) dummy = 1.0;
+                    sqo = acqop * (delt60 / 24.0) + sqo * pow(1.0 - dummy, delt60 / 24.0);
+                }
+                sqo = sqo + sliqo + adtot;
+                soqo = 0.0;
+                if (suro > 0.0 && sqo > 0.0) {
+                    soqo = sqo * (1.0 - exp(-suro * wsfac));
+                    sqo = sqo - soqo;
+                }
+                soqoc = suro > 0.0 ? soqo / suro / 3630.0 : -1.0e30;
+            } else if (QSOFG == -1) { /* IQUAL.py:259-269 */
+                acqop = acqop * 0.2266;
+                soqo = suro * acqop;
+                soqoc = acqop / 3630.0;
+                sqo = 0.0;
+            }
+            suroqo = soqo;
+        }
+        const double soqual = suroqs + suroqo;
+        out->SOQUAL[t] = soqual;
+        out->SOQC[t] = suro > 0.0 ? soqual / suro / 3630.0 : -1.0e30;
+        out->SQO[t] = sqo;
+        out->SOQS[t] = soqs;
+        out->SOQOC[t] = soqoc;
+        out->SOQO[t] = soqo;
+        out->SOQSP[t] = soqsp;
+        out->IQADWT[t] = adcnfx;
+        out->IQADDR[t] = adfxfx;
+        out->IQADEP[t] = adtot;
+        out->SLIQO[t] = 0.0;
+        out->INFLOW[t] = 0.0;
     }
 }
 

@@ -95,6 +95,19 @@ extern "C" {
 #define IWTGAS_IN(X) X(AIRTMP) X(WYIELD) X(SURO) X(SURLI) X(SLITMP) X(SLIDOX) X(SLICO2) X(AWTF) X(BWTF) X(DAYFG)
 #define IWTGAS_OUT(X) X(SOTMP) X(SODOX) X(SOCO2) X(SOHT) X(SODOXM) X(SOCO2M)
 
+/* ---- PQUAL (PERLND) / IQUAL (IMPLND): ONE constituent per call; the reference loops constituents inside its kernel
+ *      with per-constituent ui keys (PQUAL.py:148-170, IQUAL.py:131-150) and oracle.py does that loop ------------- */
+#define PQUAL_UI(X) X(delt60) X(QSDFG) X(QSOFG) X(QIFWFG) X(QAGWFG) X(VIQCFG) X(VAQCFG) X(SQO) X(WSQOP) X(SLIFAC) \
+    X(ILIFAC) X(ALIFAC)
+#define PQUAL_IN(X) X(SURO) X(IFWO) X(AGWO) X(PERO) X(WSSD) X(SCRSD) X(PREC) X(SLIQSP) X(ILIQC) X(ALIQC) X(POTFW) \
+    X(POTFS) X(ACQOP) X(REMQOP) X(IOQCP) X(AOQCP) X(PQADFX) X(PQADCN) X(DAYFG)
+#define PQUAL_OUT(X) X(SQO) X(SOQSP) X(SOQOC) X(SOQC) X(IOQC) X(AOQC) X(POQC) X(WASHQS) X(SCRQS) X(SOQS) X(SOQO) \
+    X(SOQUAL) X(IOQUAL) X(AOQUAL) X(POQUAL) X(PQADDR) X(PQADWT) X(PQADEP) X(SLIQO) X(INFLOW)
+#define IQUAL_UI(X) X(delt60) X(QSDFG) X(QSOFG) X(SQO) X(WSQOP) X(SLIFAC)
+#define IQUAL_IN(X) X(SURO) X(SOSLD) X(PREC) X(SLIQSP) X(POTFW) X(ACQOP) X(REMQOP) X(IQADFX) X(IQADCN) X(DAYFG)
+#define IQUAL_OUT(X) X(SOQUAL) X(SOQC) X(SOQO) X(SQO) X(SOQOC) X(SOQS) X(SOQSP) X(IQADDR) X(IQADWT) X(IQADEP) \
+    X(SLIQO) X(INFLOW)
+
 #define HSP2O_DECL_UI(n) double n;
 #define HSP2O_DECL_IN(n) const double *n;
 #define HSP2O_DECL_OUT(n) double *n;
@@ -113,6 +126,8 @@ HSP2O_RECORDS(pstemp, PSTEMP_UI, PSTEMP_IN, PSTEMP_OUT)
 HSP2O_RECORDS(pwtgas, PWTGAS_UI, PWTGAS_IN, PWTGAS_OUT)
 HSP2O_RECORDS(solids, SOLIDS_UI, SOLIDS_IN, SOLIDS_OUT)
 HSP2O_RECORDS(iwtgas, IWTGAS_UI, IWTGAS_IN, IWTGAS_OUT)
+HSP2O_RECORDS(pqual, PQUAL_UI, PQUAL_IN, PQUAL_OUT)
+HSP2O_RECORDS(iqual, IQUAL_UI, IQUAL_IN, IQUAL_OUT)
 
 /* error-count vector lengths (ERRMSGS tuples: SNOW.py:23, PWATER.py:15-25, IWATER.py:15, PSTEMP.py:13-18) */
 #define HSP2O_NERR_SNOW 1
@@ -131,6 +146,8 @@ void hsp2o_pstemp(const pstemp_ui *ui, const pstemp_in *in, const pstemp_out *ou
 void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *out, int64_t nsteps);
 void hsp2o_solids(const solids_ui *ui, const solids_in *in, const solids_out *out, int64_t nsteps);
 void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *out, int64_t nsteps);
+void hsp2o_pqual(const pqual_ui *ui, const pqual_in *in, const pqual_out *out, int64_t nsteps);
+void hsp2o_iqual(const iqual_ui *ui, const iqual_in *in, const iqual_out *out, int64_t nsteps);
 
 /*
  * Multi-threaded CPU baseline over independent segments (bench.py cpu_baseline / --impl reference).

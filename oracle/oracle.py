@@ -163,6 +163,46 @@ def _iwtgas_(ui, ts):
     return _run("iwtgas", ui, ts, n, None)
 
 
+def _pqual_(ui, ts):
+    """_pqual_(ui, ts) (PQUAL.py:147-397): constituents 1..nquals with per-constituent ui / ts keys; outputs
+    ts['PQUAL<k>_<NAME>']; errors[0] counts constituents that take atmospheric deposition without QSOFG (:171-174)."""
+    n, nq = int(ui["simlen"]), int(ui["nquals"])
+    errors = np.zeros(int(ui["errlen"]), dtype=np.int64)
+    for k in range(1, nq + 1):
+        K = str(k)
+        if ui["QSOFG" + K] == 0 and (ui["pqadfgf" + K] != 0 or ui["pqadfgc" + K] != 0):
+            errors[0] += 1
+        u = {"delt60": ui["delt60"], "SLIFAC": ui["SLIFAC"], "ILIFAC": ui["ILIFAC"], "ALIFAC": ui["ALIFAC"]}
+        for nm in ("QSDFG", "QSOFG", "QIFWFG", "QAGWFG", "VIQCFG", "VAQCFG", "SQO", "WSQOP"):
+            u[nm] = ui[nm + K]
+        t = {nm: ts[nm] for nm in ("SURO", "IFWO", "AGWO", "PERO", "WSSD", "SCRSD", "PREC", "SLIQSP", "ILIQC", "ALIQC", "DAYFG")}
+        for nm in ("POTFW", "POTFS", "ACQOP", "REMQOP", "IOQCP", "AOQCP", "PQADFX", "PQADCN"):
+            t[nm] = ts[nm + K]
+        _run("pqual", u, t, n, None)
+        for f in fields("pqual_out"):
+            ts["PQUAL%s_%s" % (K, f)] = t[f]
+    return errors
+
+
+def _iqual_(ui, ts):
+    """_iqual_(ui, ts) (IQUAL.py:109-284); outputs ts['IQUAL<k>_<NAME>']."""
+    n, nq = int(ui["simlen"]), int(ui["nquals"])
+    errors = np.zeros(int(ui["errlen"]), dtype=np.int64)
+    for k in range(1, nq + 1):
+        K = str(k)
+        if ui["QSOFG" + K] == 0 and (ui["iqadfgf" + K] != 0 or ui["iqadfgc" + K] != 0):
+            errors[0] += 1
+        u = {"delt60": ui["delt60"], "SLIFAC": ui["SLIFAC"], "QSDFG": ui["QSDFG" + K], "QSOFG": ui["QSOFG" + K],
+             "SQO": ui["sqo" + K], "WSQOP": ui["wsqop" + K]}
+        t = {nm: ts[nm] for nm in ("SURO", "SOSLD", "PREC", "SLIQSP", "DAYFG")}
+        for nm in ("POTFW", "ACQOP", "REMQOP", "IQADFX", "IQADCN"):
+            t[nm] = ts[nm + K]
+        _run("iqual", u, t, n, None)
+        for f in fields("iqual_out"):
+            ts["IQUAL%s_%s" % (K, f)] = t[f]
+    return errors
+
+
 def perlnd_batch(nsteps, delt, forc, par, mon, cal, nthreads=0):
     """SNOW->PWATER over independent segments with OpenMP; returns (sums[nseg,24], errors[nseg,11], threads)."""
     forc = np.ascontiguousarray(forc, dtype=np.float64)

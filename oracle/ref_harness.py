@@ -45,7 +45,7 @@ def load():
     import hsp2.hsp2.utilities  # noqa: F401
 
     names = ["utilities", "ATEMP", "SNOW", "PWATER", "IWATER", "SEDMNT", "PSTEMP", "PWTGAS", "SOLIDS", "IWTGAS",
-             "configuration"]
+             "PQUAL", "IQUAL", "configuration"]
     import importlib
 
     for n in names:

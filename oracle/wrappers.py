@@ -1,6 +1,6 @@
 """CPU-oracle activities with the reference's module contract.  TEST INFRASTRUCTURE, NOT PRODUCT.
 
-`atemp/snow/pwater/iwater/sedmnt/pstemp/pwtgas(io_manager, siminfo, uci, ts) -> (errors, errmsgs)` restate the
+`atemp/snow/pwater/iwater/sedmnt/pstemp/pwtgas/solids/iwtgas/pqual/iqual(io_manager, siminfo, uci, ts) -> (errors, errmsgs)` restate the
 Python wrappers of the reference (ATEMP.py:16-30, SNOW.py:27-88, PWATER.py:27-99, IWATER.py:19-72,
 SEDMNT.py:21-49, PSTEMP.py:23-59, PWTGAS.py:28-62) on top of the C cores in hsp2_oracle.c.  The calendar
 series come from hspsquared_b200.calendar (numpy), which tests/test_calendar.py pins against series produced
@@ -217,3 +217,91 @@ def pwtgas(io_manager, siminfo, uci, ts):
         ts[nm] = cal.initm(uci, u[flag], "MONTHLY_" + nm, u[nm]) if flag in u else np.full(n, u[nm])
     ts["DAYFG"] = cal.hourflag(0, dofirst=True)
     return O._pwtgas_(ui, ts), []
+
+
+ERRMSGS_PQUAL = ("PQUAL: A constituent must be associated with overland flow in order to receive atmospheric deposition inputs", "")
+ERRMSGS_IQUAL = ("IQUAL: A constituent must be associated with overland flow in order to receive atmospheric deposition inputs", "")
+
+
+def _initmdiv(cal, uci, flag, monthly1, monthly2, default1, default2):
+    """utilities.py:214-225: the ACQOP / SQOLIM special case (monthly tables divided month by month)."""
+    if flag and monthly1 and monthly2 in uci:
+        m1, m2 = list(uci[monthly1].values()), list(uci[monthly2].values())
+        return cal.dayval(np.array([m1[m] / m2[m] for m in range(12)]))
+    return np.full(cal.steps, default1 / default2)
+
+
+def _qual_common(pre, siminfo, uci, ts, monthly_names, adname):
+    """The part of pqual() / iqual() that is the same (PQUAL.py:32-108, IQUAL.py:29-99)."""
+    cal = _cal(siminfo)
+    n = siminfo["steps"]
+    nquals = 1
+    if "PARAMETERS" in uci and "NQUAL" in uci["PARAMETERS"]:
+        nquals = int(uci["PARAMETERS"]["NQUAL"])
+    for k in range(nquals):
+        uci[pre + str(k + 1) + "_FLAGS"]["QUALID"]  # KeyError like the reference when a constituent's tables are missing
+    ui = make_ui(uci)
+    ui.update(simlen=n, delt60=siminfo["delt"] / 60, nquals=nquals, errlen=2)
+    u = uci.get("FLAGS")
+    for k in range(1, nquals + 1):
+        K = str(k)
+        f, p = uci[pre + K + "_FLAGS"], uci[pre + K + "_PARAMETERS"]
+        for key, flagname in monthly_names:
+            tab = pre + K + "_MONTHLY/" + ("IOQC" if key == "IOQCP" else "AOQC" if key == "AOQCP" else key)
+            ts[key + K] = cal.initm(uci, f[flagname], tab, p["IOQC" if key == "IOQCP" else "AOQC" if key == "AOQCP" else key])
+        ts["REMQOP" + K] = _initmdiv(cal, uci, f["VQOFG"], pre + K + "_MONTHLY/ACQOP", pre + K + "_MONTHLY/SQOLIM",
+                                     p["ACQOP"], p["SQOLIM"])
+        adf = adc = 0
+        ts[adname + "FX" + K] = np.zeros(n)
+        ts[adname + "CN" + K] = np.zeros(n)
+        if u is not None:
+            adf = u[adname + "FG" + str(2 * k - 1)]
+            if adf > 0:
+                ts[adname + "FX" + K] = cal.initm(uci, adf, pre + K + "_MONTHLY/" + adname + "FX", 0.0)
+            elif adf == -1:
+                ts[adname + "FX" + K] = ts[adname + "FX" + K + " 1"]
+            adc = u[adname + "FG" + str(2 * k)]
+            if adc > 0:
+                ts[adname + "CN" + K] = cal.initm(uci, adc, pre + K + "_MONTHLY/" + adname + "CN", 0.0)
+            elif adc == -1:
+                ts[adname + "CN" + K] = ts[adname + "CN" + K + " 1"]
+        ui[adname.lower() + "fgf" + K] = adf
+        ui[adname.lower() + "fgc" + K] = adc
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    return ui, nquals, n
+
+
+def pqual(io_manager, siminfo, uci, ts):
+    """PQUAL.py:26-113"""
+    _english(siminfo)
+    ui, nquals, n = _qual_common(
+        "PQUAL", siminfo, uci, ts,
+        (("POTFW", "VPFWFG"), ("POTFS", "VPFSFG"), ("ACQOP", "VQOFG"), ("SQOLIM", "VQOFG"), ("IOQCP", "VIQCFG"), ("AOQCP", "VAQCFG")),
+        "PQAD")
+    for k in range(1, nquals + 1):
+        K = str(k)
+        f, p = uci["PQUAL" + K + "_FLAGS"], uci["PQUAL" + K + "_PARAMETERS"]
+        for nm in ("QSDFG", "QSOFG", "QIFWFG", "QAGWFG", "VIQCFG", "VAQCFG"):
+            ui[nm + K] = f[nm]
+        ui["SQO" + K], ui["WSQOP" + K] = p["SQO"], p["WSQOP"]
+    for nm in ("SLIQSP", "ILIQC", "ALIQC", "SURO", "IFWO", "AGWO", "PERO", "WSSD", "SCRSD"):  # PQUAL.py:98-106
+        if nm not in ts:
+            ts[nm] = np.zeros(n)
+    return O._pqual_(ui, ts), ERRMSGS_PQUAL
+
+
+def iqual(io_manager, siminfo, uci, ts):
+    """IQUAL.py:24-107"""
+    _english(siminfo)
+    ui, nquals, n = _qual_common("IQUAL", siminfo, uci, ts, (("POTFW", "VPFWFG"), ("ACQOP", "VQOFG"), ("SQOLIM", "VQOFG")),
+                                 "IQAD")
+    for k in range(1, nquals + 1):
+        K = str(k)
+        f, p = uci["IQUAL" + K + "_FLAGS"], uci["IQUAL" + K + "_PARAMETERS"]
+        for nm in ("QSDFG", "QSOFG", "VQOFG"):
+            ui[nm + K] = f[nm]
+        ui["sqo" + K], ui["wsqop" + K] = p["SQO"], p["WSQOP"]
+    for nm in ("SLIQSX", "SLIQO", "SLIQSP"):  # IQUAL.py:96-98
+        if nm not in ts:
+            ts[nm] = np.full(n, -1.0e30)
+    return O._iqual_(ui, ts), ERRMSGS_IQUAL

@@ -16,7 +16,7 @@ from oracle import cases as CASES
 from oracle import wrappers as W
 
 ORACLE_ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt,
-               "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas, "SOLIDS": W.solids, "IWTGAS": W.iwtgas}
+               "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas, "SOLIDS": W.solids, "IWTGAS": W.iwtgas, "PQUAL": W.pqual, "IQUAL": W.iqual}
 RTOL = 1e-9  # BASELINE.json north_star: max relative error <= 1e-9 on all saved flows and storages
 
 

@@ -18,7 +18,7 @@ from oracle import cases as CASES
 from oracle import wrappers as W
 
 ACTS = {"ATEMP": W.atemp, "SNOW": W.snow, "PWATER": W.pwater, "IWATER": W.iwater, "SEDMNT": W.sedmnt, "SOLIDS": W.solids, "IWTGAS": W.iwtgas,
-        "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas}
+        "PSTEMP": W.pstemp, "PWTGAS": W.pwtgas, "PQUAL": W.pqual, "IQUAL": W.iqual}
 ALL = CASES.build_cases()
 
 
@@ -97,3 +97,18 @@ def test_test10_implnd_solids_iwtgas_hspf_kat(oracle_lib, golden_dir):
         ok = ref > -1e29
         assert np.array_equal(ok, got > -1e29), key
         assert np.abs(got[ok] - ref[ok]).max() <= 2e-6 * np.abs(ref[ok]).max(), key
+
+
+def test_test10_implnd_iqual_hspf_kat(oracle_lib, golden_dir):
+    """HSPF's own hourly IQUAL output for test10 IMPLND 1 (constituent COD, test10I.hbn) against the oracle chain
+    SNOW -> IWATER -> SOLIDS -> IQUAL: storages and fluxes to 2e-6 of scale, the concentrations (a flux divided by a fp32 runoff
+    and HSPF's own ft3 conversion constant) to 1e-5."""
+    h = np.load(os.path.join(golden_dir, "hspf_test10I.npz"))
+    ts, errs = run_oracle(ALL["i001_iqual"], "us")
+    assert not errs["IQUAL"].any()
+    for cons in ("SQO", "SOQSP", "SOQOC", "SOQC", "SOQS", "SOQO", "SOQUAL"):
+        ref, got = h["IQUAL_" + cons], ts["IQUAL1_" + cons]
+        ok = ref > -1e29
+        assert np.array_equal(ok, got > -1e29), cons
+        assert np.abs(got[ok] - ref[ok]).max() <= (1e-5 if cons in ("SOQOC", "SOQC") else 2e-6) * np.abs(ref[ok]).max(), cons
+    assert abs(ts["IQUAL1_SOQUAL"].sum() - h["IQUAL_SOQUAL"].sum()) < 1e-5 * h["IQUAL_SOQUAL"].sum()
