@@ -35,6 +35,8 @@ ERRMSGS = {
     "PWTGAS": [],  # PWTGAS.py:12
     "SOLIDS": [],  # SOLIDS.py:14
     "IWTGAS": [],  # IWTGAS.py:11
+    "PQUAL": ("PQUAL: A constituent must be associated with overland flow in order to receive atmospheric deposition inputs", ""),
+    "IQUAL": ("IQUAL: A constituent must be associated with overland flow in order to receive atmospheric deposition inputs", ""),
 }
 
 # series each section may read from ts (kernel forcing ids)
@@ -248,9 +250,91 @@ def iwtgas(io_manager, siminfo, uci, ts):
     return errors, ERRMSGS["IWTGAS"]
 
 
+def _qual(operation, siminfo, uci, ts):
+    """PQUAL.py:26-113 / IQUAL.py:24-107: all constituents of the segment in one launch, one row each."""
+    from .qualstore import IQUAL_INPUTS, PQUAL_INPUTS, nquals, qual_store
+
+    if siminfo.get("units", 1) != 1:
+        raise NotImplementedError("libhsp2g implements English units (uunits=1) only")
+    imp = operation == "IMPLND"
+    sec, adname = ("IQUAL", "IQAD") if imp else ("PQUAL", "PQAD")
+    cal = _calendar(siminfo)
+    n = int(siminfo["steps"])
+    if n != cal.steps:
+        raise ValueError("siminfo['steps'] does not match start/stop/delt")
+    nq = nquals(uci)
+    store = qual_store(operation, [uci], cal)
+    # helper series the wrapper leaves in ts (visible to saveall)
+    u = uci.get("FLAGS")
+    for k in range(1, nq + 1):
+        K = str(k)
+        f, p = uci[sec + K + "_FLAGS"], uci[sec + K + "_PARAMETERS"]
+        tabs = [("POTFW", "VPFWFG", "POTFW"), ("ACQOP", "VQOFG", "ACQOP"), ("SQOLIM", "VQOFG", "SQOLIM")]
+        if not imp:
+            tabs[1:1] = [("POTFS", "VPFSFG", "POTFS")]
+            tabs += [("IOQCP", "VIQCFG", "IOQC"), ("AOQCP", "VAQCFG", "AOQC")]
+        for key, vflag, tab in tabs:
+            ts[key + K] = cal.initm(uci, f[vflag], sec + K + "_MONTHLY/" + tab, p[tab])
+        ts["REMQOP" + K] = cal.initmdiv(uci, f["VQOFG"], sec + K + "_MONTHLY/ACQOP", sec + K + "_MONTHLY/SQOLIM",
+                                        p["ACQOP"], p["SQOLIM"])
+        ts[adname + "FX" + K] = np.zeros(n)
+        ts[adname + "CN" + K] = np.zeros(n)
+        if u is not None:
+            for nm, val in (("FX", u[adname + "FG" + str(2 * k - 1)]), ("CN", u[adname + "FG" + str(2 * k)])):
+                if val > 0:
+                    ts[adname + nm + K] = cal.initm(uci, val, sec + K + "_MONTHLY/" + adname + nm, 0.0)
+                elif val == -1:
+                    ts[adname + nm + K] = ts[adname + nm + K + " 1"]
+    if imp:
+        for name in ("SLIQSX", "SLIQO", "SLIQSP"):  # IQUAL.py:96-98
+            if name not in ts:
+                ts[name] = np.full(n, -1.0e30)
+    else:
+        for name in ("SLIQSP", "ILIQC", "ALIQC"):  # PQUAL.py:98-100
+            if name not in ts:
+                ts[name] = np.zeros(n)
+    ts["DAYFG"] = cal.hourflag(0, dofirst=True)
+    if not imp:
+        for name in ("SURO", "IFWO", "AGWO", "PERO", "WSSD", "SCRSD"):  # PQUAL.py:104-106
+            if name not in ts:
+                ts[name] = np.zeros(n)
+    names = [nm for nm in (IQUAL_INPUTS if imp else PQUAL_INPUTS) if nm in ts]
+    forcing = np.empty((n, len(names) + 2, nq))
+    for r, nm in enumerate(names):
+        forcing[:, r, :] = np.asarray(ts[nm], dtype=np.float64)[:n, None]
+    if any(store.dep_series):  # a constituent's deposition is an input series: every row then reads its own column
+        for k in range(1, nq + 1):
+            forcing[:, len(names), k - 1] = ts[adname + "FX" + str(k)][:n]
+            forcing[:, len(names) + 1, k - 1] = ts[adname + "CN" + str(k)][:n]
+        names = names + ["QADFX", "QADCN"]
+    else:
+        forcing = np.ascontiguousarray(forcing[:, :len(names), :])
+    save = output_names(operation, store.act)
+    with LandBatch(store, cal, names, save, device=DEVICE) as batch:
+        out = batch.run(forcing)
+    for r, full in enumerate(save):
+        nm = full.split("_", 1)[1]
+        for k in range(1, nq + 1):
+            ts["%s%d_%s" % (sec, k, nm)] = np.ascontiguousarray(out[:, r, k - 1])
+    errors = np.zeros(len(ERRMSGS[sec]), dtype=np.int64)
+    errors[0] = int(store.dep_without_qsofg.sum())
+    return errors, ERRMSGS[sec]
+
+
+def pqual(io_manager, siminfo, uci, ts):
+    """PQUAL.py:26-113"""
+    return _qual("PERLND", siminfo, uci, ts)
+
+
+def iqual(io_manager, siminfo, uci, ts):
+    """IQUAL.py:24-107"""
+    return _qual("IMPLND", siminfo, uci, ts)
+
+
 ACTIVITIES = {
-    "PERLND": {"ATEMP": atemp, "SNOW": snow, "PWATER": pwater, "SEDMNT": sedmnt, "PSTEMP": pstemp, "PWTGAS": pwtgas},
-    "IMPLND": {"ATEMP": atemp, "SNOW": snow, "IWATER": iwater, "SOLIDS": solids, "IWTGAS": iwtgas},
+    "PERLND": {"ATEMP": atemp, "SNOW": snow, "PWATER": pwater, "SEDMNT": sedmnt, "PSTEMP": pstemp, "PWTGAS": pwtgas,
+               "PQUAL": pqual},
+    "IMPLND": {"ATEMP": atemp, "SNOW": snow, "IWATER": iwater, "SOLIDS": solids, "IWTGAS": iwtgas, "IQUAL": iqual},
 }
 
 

@@ -178,6 +178,14 @@ class Calendar:
             return self.dayval(list(uci[monthly_key].values()))
         return np.full(self.steps, float(default))
 
+    def initmdiv(self, uci, flag, monthly1, monthly2, default1, default2):
+        """utilities.py:214-225: a parameter that is the month-by-month ratio of two tables (ACQOP / SQOLIM), or of the two
+        constants.  Like the reference, only the SECOND table's presence is tested."""
+        if flag and monthly1 and monthly2 in uci:
+            m1, m2 = list(uci[monthly1].values()), list(uci[monthly2].values())
+            return self.dayval([m1[m] / m2[m] for m in range(12)])
+        return np.full(self.steps, default1 / default2)
+
     @classmethod
     def from_siminfo(cls, siminfo, time_unit=None):
         return cls(siminfo["start"], siminfo["stop"], siminfo["delt"], time_unit)

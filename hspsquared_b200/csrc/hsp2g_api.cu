@@ -20,7 +20,8 @@
 static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && HSP2G_PWATER == HSP2G_ACT_PWATER &&
                   HSP2G_SEDMNT == HSP2G_ACT_SEDMNT && HSP2G_PSTEMP == HSP2G_ACT_PSTEMP &&
                   HSP2G_PWTGAS == HSP2G_ACT_PWTGAS && HSP2G_IWATER == HSP2G_ACT_IWATER &&
-                  HSP2G_SOLIDS == HSP2G_ACT_SOLIDS && HSP2G_IWTGAS == HSP2G_ACT_IWTGAS,
+                  HSP2G_SOLIDS == HSP2G_ACT_SOLIDS && HSP2G_IWTGAS == HSP2G_ACT_IWTGAS &&
+                  HSP2G_PQUAL == HSP2G_ACT_PQUAL && HSP2G_IQUAL == HSP2G_ACT_IQUAL,
               "public activity bits must match the kernel's");
 static_assert(HSP2G_ABI_VERSION == 2, "bump _lib.py with the header");
 static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
@@ -118,8 +119,11 @@ const char *k_errors = HSP2G_ERRORS(NAME_ITEM);
 #define OI(n) "IWATER_" #n ","
 #define OL(n) "SOLIDS_" #n ","
 #define OW(n) "IWTGAS_" #n ","
+#define OQ(n) "PQUAL_" #n ","
+#define OJ(n) "IQUAL_" #n ","
 const char *k_outputs = HSP2G_OUT_ATEMP(OA) HSP2G_OUT_SNOW(OS) HSP2G_OUT_PWATER(OP) HSP2G_OUT_SEDMNT(OD)
-    HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI) HSP2G_OUT_SOLIDS(OL) HSP2G_OUT_IWTGAS(OW);
+    HSP2G_OUT_PSTEMP(OT) HSP2G_OUT_PWTGAS(OG) HSP2G_OUT_IWATER(OI) HSP2G_OUT_SOLIDS(OL) HSP2G_OUT_IWTGAS(OW)
+    HSP2G_OUT_PQUAL(OQ) HSP2G_OUT_IQUAL(OJ);
 
 // host [rows][ld] (segment-minor) <-> device tile-major rows [tile][row0 + r][32] of a block with `blk_rows` rows per
 // tile.  Padded lanes of the last tile receive copies of the last real segment (land_common.cuh).
@@ -237,8 +241,10 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.progress = b->d_progress;
     L.prog_base = b->prog_base;
     int grid = 0;
-    cudaError_t e = b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
-                                          : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
+    const bool qual = (b->act & (HSP2G_ACT_PQUAL | HSP2G_ACT_IQUAL)) != 0;
+    cudaError_t e = qual                    ? hsp2g_launch_qual(L, b->op == HSP2G_IMPLND, b->sub_steps, st, &b->kname, &grid)
+                    : b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
+                                            : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     // every task draws one ticket and every warp one more (the draw that tells it to stop)
     b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid * LAND_WARPS;
@@ -339,8 +345,9 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
         return fail("SNOW with delt > 360: the reference raises KeyError('ICEFLG') (SNOW.py:85); refused");
     const unsigned perl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_PWATER | HSP2G_SEDMNT | HSP2G_PSTEMP | HSP2G_PWTGAS;
     const unsigned impl = HSP2G_ATEMP | HSP2G_SNOW | HSP2G_IWATER | HSP2G_SOLIDS | HSP2G_IWTGAS;
-    if (act == 0 || (act & ~(operation == HSP2G_PERLND ? perl : impl)))
-        return fail("activity mask 0x%x is not valid for this operation", act);
+    const unsigned qual = operation == HSP2G_PERLND ? HSP2G_PQUAL : HSP2G_IQUAL;
+    if (act != qual && (act == 0 || (act & ~(operation == HSP2G_PERLND ? perl : impl))))
+        return fail("activity mask 0x%x is not valid for this operation (PQUAL / IQUAL rows form a batch of their own)", act);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

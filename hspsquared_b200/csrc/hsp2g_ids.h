@@ -24,6 +24,10 @@
 #define HSP2G_ACT_IWATER 64u
 #define HSP2G_ACT_SOLIDS 128u /* IMPLND, after IWATER (configuration.py:51-52) */
 #define HSP2G_ACT_IWTGAS 256u
+/* quality constituents: a batch with ONLY this bit set holds one row per (segment, constituent) and reads the flows and
+ * sediment / solids outflows it is associated with as input series (PQUAL.py:147, IQUAL.py:109) */
+#define HSP2G_ACT_PQUAL 512u
+#define HSP2G_ACT_IQUAL 1024u
 
 /* ---- per-segment scalar parameters: par[P_x][segment], fp64 -------------------------------------- */
 /* derived columns (computed by the host with the reference's own expression order):
@@ -41,13 +45,17 @@
     X(ELEVGC) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(SLIFAC) X(ILIFAC) X(ALIFAC)                           \
     X(RETSC)                                                                                              \
     /* IMPLND SOLIDS (SOLIDS.py:62-64) and IWTGAS (IWTGAS.py:76-86; ELEVGC and SLIFAC share the PWTGAS columns) */ \
-    X(KEIM) X(JEIM) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF)
+    X(KEIM) X(JEIM) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF)                                                   \
+    /* PQUAL / IQUAL rows: Q_WSFAC = 2.30 / WSQOP (PQUAL.py:166, IQUAL.py:147); Q_REMQOP = ACQOP / SQOLIM (initmdiv,  \
+     * utilities.py:214-225); Q_ADFX / Q_ADCN = atmospheric deposition flux / concentration (0 unless monthly or a series) */ \
+    X(Q_WSFAC) X(Q_POTFW) X(Q_POTFS) X(Q_ACQOP) X(Q_REMQOP) X(Q_IOQC) X(Q_AOQC) X(Q_ADFX) X(Q_ADCN)
 
 /* ---- monthly tables: mon[slot][12][segment]; a parameter follows its table only where the segment's
  *      M_<name> flag bit is set (utilities.py:205-211 initm: flag truthy AND table present) -------------- */
 #define HSP2G_MONTHLY(X)                                                                                  \
     X(KMELT) X(LZETP) X(CEPSC) X(INTFW) X(IRC) X(NSUR) X(UZSN) X(COVER) X(NVSI) X(ASLT) X(BSLT) X(ULTP1)  \
-    X(ULTP2) X(LGTP1) X(LGTP2) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(RETSC) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF)
+    X(ULTP2) X(LGTP1) X(LGTP2) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(RETSC) X(ACCSDP) X(REMSDP) X(AWTF) X(BWTF) \
+    X(Q_POTFW) X(Q_POTFS) X(Q_ACQOP) X(Q_REMQOP) X(Q_IOQC) X(Q_AOQC) X(Q_ADFX) X(Q_ADCN)
 
 /* ---- per-segment option flags: one 64-bit word per segment ---------------------------------------- */
 #define HSP2G_FLAGS(X)                                                                                    \
@@ -69,7 +77,11 @@
     X(M_ASLT) X(M_BSLT) X(M_ULTP1) X(M_ULTP2) X(M_LGTP1) X(M_LGTP2) X(M_IDOXP) X(M_ICO2P) X(M_ADOXP)      \
     X(M_ACO2P) X(M_RETSC)                                                                                 \
     X(SLD_SDOP1)  /* SOLIDS: SDOPFG == 1 (SOLIDS.py:103) */                                               \
-    X(M_ACCSDP) X(M_REMSDP) X(M_AWTF) X(M_BWTF)
+    X(M_ACCSDP) X(M_REMSDP) X(M_AWTF) X(M_BWTF)                                                           \
+    /* PQUAL / IQUAL rows: QSDFG; QSOFG != 0, >= 1, == 1, == 2, == -1; QIFWFG; QAGWFG; VIQCFG / VAQCFG in (3, 4) */    \
+    X(Q_QSDFG) X(Q_QSO_NZ) X(Q_QSO_GE1) X(Q_QSO_EQ1) X(Q_QSO_EQ2) X(Q_QSO_M1) X(Q_QIFWFG) X(Q_QAGWFG) X(Q_VIQC34)  \
+    X(Q_VAQC34)                                                                                           \
+    X(M_Q_POTFW) X(M_Q_POTFS) X(M_Q_ACQOP) X(M_Q_REMQOP) X(M_Q_IOQC) X(M_Q_AOQC) X(M_Q_ADFX) X(M_Q_ADCN)
 
 /* ---- carried state: state[S_x][segment], fp64.  Named states (restart.py:9-14) AND the hidden scalars the
  *      reference carries across steps, so a run split into time chunks is bit-identical
@@ -89,7 +101,9 @@
     /* IWATER (SURS, MSUPY, DEC, SRC, PETADJ shared with the PWATER slots: a batch is one operation) */    \
     X(RETS)                                                                                               \
     /* SOLIDS: storage and the dry-day latch; IWTGAS: the day's temperature regression coefficients */    \
-    X(SLDS) X(SLD_DRYDFG) X(IWG_AWTF) X(IWG_BWTF)
+    X(SLDS) X(SLD_DRYDFG) X(IWG_AWTF) X(IWG_BWTF)                                                         \
+    /* PQUAL / IQUAL: surface storage; IQUAL's carried washoff potency (IQUAL.py:188, 207-214) */          \
+    X(Q_SQO) X(Q_SOQSP)
 
 /* ---- forcing / input series ids: forc[t][row][segment]; absent ids read a per-batch fill value that the
  *      host derives by replaying the reference wrappers' NaN / zero / -1e30 fills (SNOW.py:44-46,
@@ -99,7 +113,10 @@
     X(SURLI) X(UZLI) X(IFWLI) X(LZLI) X(AGWLI) X(LGTMP)                                                   \
     X(RAINF) X(SNOCOV) X(WYIELD) X(PACKI)                                                                 \
     X(SLSED) X(SURO) X(SURS) X(IFWO) X(AGWO) X(SLTMP) X(ULTMP)                                            \
-    X(SLITMP) X(SLIDOX) X(SLICO2) X(ILITMP) X(ILIDOX) X(ILICO2) X(ALITMP) X(ALIDOX) X(ALICO2)
+    X(SLITMP) X(SLIDOX) X(SLICO2) X(ILITMP) X(ILIDOX) X(ILICO2) X(ALITMP) X(ALIDOX) X(ALICO2)             \
+    /* inputs of PQUAL / IQUAL rows (PQUAL.py:119-126,208-210, IQUAL.py:118-124); QADFX / QADCN = the constituent's       \
+     * deposition series when its PQADFG / IQADFG flag is -1 */                                                          \
+    X(PERO) X(WSSD) X(SCRSD) X(SOSLD) X(SLIQSP) X(ILIQC) X(ALIQC) X(QADFX) X(QADCN)
 
 /* ---- output series ids (the reference's ts[...] outputs; SAVE selects the rows that are written) ------ */
 #define HSP2G_OUT_ATEMP(X) X(AIRTMP)
@@ -120,6 +137,12 @@
 #define HSP2G_OUT_IWATER(X) X(IMPEV) X(PET) X(PETADJ) X(RETS) X(SUPY) X(SURI) X(SURO) X(SURS)
 #define HSP2G_OUT_SOLIDS(X) X(SOSLD) X(SLDS)                         /* SOLIDS.py:72-73 */
 #define HSP2G_OUT_IWTGAS(X) X(SOTMP) X(SODOX) X(SOCO2) X(SOHT) X(SODOXM) X(SOCO2M) /* IWTGAS.py:104-109 */
+/* per constituent: ts['PQUAL<k>_<NAME>'] (PQUAL.py:176-206), ts['IQUAL<k>_<NAME>'] (IQUAL.py:152-175) */
+#define HSP2G_OUT_PQUAL(X)                                                                                \
+    X(SQO) X(SOQSP) X(SOQOC) X(SOQC) X(IOQC) X(AOQC) X(POQC) X(WASHQS) X(SCRQS) X(SOQS) X(SOQO) X(SOQUAL)  \
+    X(IOQUAL) X(AOQUAL) X(POQUAL) X(PQADDR) X(PQADWT) X(PQADEP) X(SLIQO) X(INFLOW)
+#define HSP2G_OUT_IQUAL(X)                                                                                \
+    X(SOQUAL) X(SOQC) X(SOQO) X(SQO) X(SOQOC) X(SOQS) X(SOQSP) X(IQADDR) X(IQADWT) X(IQADEP) X(SLIQO) X(INFLOW)
 
 /* ---- error counters: err[E_x][segment], int64 (ERRMSGS tuples of the reference) ---------------------- */
 #define HSP2G_ERRORS(X)                                                                                   \
@@ -127,7 +150,9 @@
     X(PWATER0) X(PWATER1) X(PWATER2) X(PWATER3) X(PWATER4) X(PWATER5) X(PWATER6) X(PWATER7) X(PWATER8)    \
     X(PWATER9)                                                                                            \
     X(PSTEMP0) X(PSTEMP1) X(PSTEMP2) X(PSTEMP3) X(PSTEMP4) X(PSTEMP5)                                     \
-    X(IWATER0)
+    X(IWATER0)                                                                                            \
+    /* PQUAL / IQUAL: deposition on a constituent without QSOFG, counted once per run by the host (PQUAL.py:171-174) */ \
+    X(PQUAL0) X(PQUAL1) X(IQUAL0) X(IQUAL1)
 
 /* per-step shared calendar flag bits (hspsquared_b200/calendar.py) */
 #define HSP2G_CAL_HRFG 1u
@@ -195,7 +220,13 @@ enum {
 #define X(n) O_IWTGAS_##n,
                                     HSP2G_OUT_IWTGAS(X)
 #undef X
-                                        HSP2G_NOUT
+#define X(n) O_PQUAL_##n,
+                                        HSP2G_OUT_PQUAL(X)
+#undef X
+#define X(n) O_IQUAL_##n,
+                                            HSP2G_OUT_IQUAL(X)
+#undef X
+                                                HSP2G_NOUT
 };
 enum {
 #define X(n) E_##n,

@@ -70,7 +70,7 @@ static inline bool io_matches(const LandLaunch &L) {
     }
     r = 0;
     for (int id = 0; id < HSP2G_NOUT; ++id) {
-        const bool on = ((id < 64 ? IO::S0 : IO::S1) >> (id & 63)) & 1ull;
+        const bool on = id < 128 && (((id < 64 ? IO::S0 : IO::S1) >> (id & 63)) & 1ull);
         if (L.srow[id] != (on ? r : -1)) return false;
         r += on;
     }

@@ -201,7 +201,8 @@ struct StaticIO {
     static constexpr unsigned long long FMASK = FM, S0 = SM0, S1 = SM1;
     static constexpr int NF = ce_popc(FM), NS = ce_popc(SM0) + ce_popc(SM1);
 };
-static_assert(HSP2G_NFORC <= 64 && HSP2G_NOUT <= 128, "StaticIO masks are 64 + 128 bits");
+static_assert(HSP2G_NFORC <= 64 && (int)O_PQUAL_SQO <= 128,
+              "StaticIO masks are 64 + 128 bits; the PQUAL / IQUAL outputs beyond them exist for DynIO kernels only");
 
 #ifndef HSP2G_HOST_EMU
 // ---- forcing pipeline: a PIPE_STAGES-deep ring per warp in shared memory, filled by the TMA engine.  Lane 0 arms

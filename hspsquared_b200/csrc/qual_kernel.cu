@@ -1,0 +1,58 @@
+// qual_kernel.cu -- PQUAL / IQUAL: one thread = one (segment, constituent) row, one warp = one tile of 32 rows.
+// Same machinery as the land kernels (land_common.cuh): the rows' input series -- the flows and sediment / solids outflows
+// the constituent is associated with -- arrive through the per-warp TMA ring, (tile, sub-chunk) tasks are handed out by
+// the ticket scheduler, the storage is carried in registers and handed on through the segment block, saved series stream
+// out tile-major.  A constituent needs ~40 fp64 operations per interval against 7 series read and up to 20 written, so the
+// kernel is bound by HBM like the land kernels; no hot-parameter staging is needed (the day's parameters sit in registers).
+#include "land_kernels.cuh"
+#include "launch.h"
+#include "qual.cuh"
+
+template <bool IMP, int MAXREG>
+__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) qual_kernel(const __grid_constant__ LandLaunch L) {
+    LAND_SMEM_DECL;
+    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    const int nf = L.nf;
+    typedef Seg<DynIO, 0ull, false> SegT;
+    PipeT<false> pipe;
+    pipe.init(smem, wib, lane, nf, 0, 0, 0);
+    Sched sched(L, lane, wib);
+    int tile, t0, t1;
+    while (sched.next(tile, t0, t1)) {
+        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
+        SegT s(L, tile, lane, t0, pipe.hot_area());
+        QualState q;
+        q.load(s);
+        for (int t = t0; t < t1; ++t) {
+            s.begin_step(pipe.acquire());
+            if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) q.refresh_daily(s);
+            if (IMP)
+                iqual_step(s, q);
+            else
+                pqual_step(s, q);
+            s.end_step();
+            pipe.release(t);
+        }
+        q.store(s);
+        pipe.end_task();
+        sched.done(tile);
+    }
+}
+
+template <bool IMP>
+static cudaError_t launch_qual(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
+    const size_t smem = land_smem_bytes(L.nf, 0ull, 0, false);
+    auto k = qual_kernel<IMP, 96>;
+    int cap = 0;
+    cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
+    if (e != cudaSuccess) return e;
+    hsp2g_plan_tasks(L, sub_pref, cap, LAND_WARPS, grid_out);
+    HSP2G_LAUNCH(k, (unsigned)*grid_out, LAND_BLOCK, smem, st, L);
+    if (name) *name = nm;
+    return cudaGetLastError();
+}
+
+cudaError_t hsp2g_launch_qual(LandLaunch &L, bool implnd, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
+    return implnd ? launch_qual<true>(L, sub_pref, st, name, "qual_kernel<IQUAL,io=dynamic>", grid_out)
+                  : launch_qual<false>(L, sub_pref, st, name, "qual_kernel<PQUAL,io=dynamic>", grid_out);
+}

@@ -17,11 +17,11 @@ from .segstore import SegmentStore, forcing_fill
 
 _dp = C.POINTER(C.c_double)
 
-SECTION_OF = {"PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS"),
-              "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS")}
+SECTION_OF = {"PERLND": ("ATEMP", "SNOW", "PWATER", "SEDMNT", "PSTEMP", "PWTGAS", "PQUAL"),
+              "IMPLND": ("ATEMP", "SNOW", "IWATER", "SOLIDS", "IWTGAS", "IQUAL")}
 ERRORS_OF = {"SNOW": ("SNOW0",), "PWATER": tuple("PWATER%d" % i for i in range(10)),
              "PSTEMP": tuple("PSTEMP%d" % i for i in range(6)), "IWATER": ("IWATER0",), "ATEMP": (), "SEDMNT": (),
-             "PWTGAS": (), "SOLIDS": (), "IWTGAS": ()}
+             "PWTGAS": (), "SOLIDS": (), "IWTGAS": (), "PQUAL": ("PQUAL0", "PQUAL1"), "IQUAL": ("IQUAL0", "IQUAL1")}
 
 
 def _ptr(a, typ=_dp):
@@ -290,6 +290,42 @@ class LandBatch:
 
     def __exit__(self, *a):
         self.close()
+
+
+class QualBatch(LandBatch):
+    """PQUAL / IQUAL of many segments: one device row per (segment, constituent) (qualstore.qual_store).
+
+    `uci_list[i]` is segment i's PQUAL / IQUAL table set.  `forcing_names` are the input series the rows read (qualstore.
+    PQUAL_INPUTS / IQUAL_INPUTS); `gather()` spreads per-SEGMENT series -- the land batch's SURO, IFWO, ... outputs and the
+    met / lateral inputs -- over the rows, `run()` then works as for any batch.  Output row j belongs to `self.rows[j]` =
+    (segment index, constituent number); in the reference's ts that series is '<P|I>QUAL<k>_<NAME>'."""
+
+    def __init__(self, operation, uci_list, calendar, forcing_names, save="all", device=0, timing=False):
+        from .qualstore import qual_store
+
+        store = qual_store(operation, uci_list, calendar)
+        if any(store.dep_series):
+            raise NotImplementedError("atmospheric deposition given as input series (PQADFG / IQADFG = -1): use the drop-in "
+                                      "activities, which feed every row its own column")
+        self.rows = store.rows
+        self.row_segment = np.array([i for i, _k in store.rows], dtype=np.int64)
+        super().__init__(store, calendar, forcing_names, save, device=device, timing=timing)
+
+    def gather(self, series):
+        """{name: [steps][n_segments] or [steps]} -> forcing [steps][nf][rows] in `forcing_names` order."""
+        steps = len(next(iter(series.values())))
+        out = np.empty((steps, len(self.forcing_names), self.n))
+        for r, nme in enumerate(self.forcing_names):
+            a = np.asarray(series[nme], dtype=np.float64)
+            out[:, r, :] = a[:steps, None] if a.ndim == 1 else a[:steps][:, self.row_segment]
+        return out
+
+    def segment_errors(self, n_segments):
+        """int64[2][n_segments]: the reference's error vector of each segment (errors[0] = constituents that take
+        atmospheric deposition without being associated with overland flow, PQUAL.py:171-174)."""
+        e = np.zeros((2, n_segments), dtype=np.int64)
+        np.add.at(e[0], self.row_segment, self.store.dep_without_qsofg)
+        return e
 
 
 def tile_series(x):

@@ -44,6 +44,9 @@ RAW_DEFAULT = {
     "ELEV": 0.0, "IDOXP": 0.0, "ICO2P": 0.0, "ADOXP": 0.0, "ACO2P": 0.0, "SLIFAC": 0.0, "ILIFAC": 0.0, "ALIFAC": 0.0,
     "RETSC": 0.0,
     "KEIM": 0.0, "JEIM": -999.0, "ACCSDP": 0.0, "REMSDP": 0.0, "AWTF": 32.0, "BWTF": 1.0,  # ParseTable.csv rows 1291-1329
+    # columns of PQUAL / IQUAL rows (qualstore.py); unused by land-segment batches
+    "Q_WSFAC": 0.0, "Q_POTFW": 0.0, "Q_POTFS": 0.0, "Q_ACQOP": 0.0, "Q_REMQOP": 0.0, "Q_IOQC": 0.0, "Q_AOQC": 0.0,
+    "Q_ADFX": 0.0, "Q_ADCN": 0.0,
 }
 INIT_DEFAULT = {
     "PACKF": 0.0, "PACKI": 0.0, "PACKW": 0.0, "RDENPF": 0.2, "DULL": 400.0, "PAKTMP": 32.0, "COVINX": 0.01,
@@ -529,4 +532,10 @@ def forcing_fill(operation, act, provided):
         put(("WYIELD", "SURO", "IFWO", "AGWO", "SURLI", "IFWLI", "AGWLI"), 0.0)
         put(("SLTMP", "ULTMP", "LGTMP", "SLITMP", "SLIDOX", "SLICO2", "ILITMP", "ILIDOX", "ILICO2", "ALITMP", "ALIDOX",
              "ALICO2"), -1.0e30)
+    if act & B.get("PQUAL", 0):  # PQUAL.py:98-106 (PREC is indexed unconditionally, :125)
+        require(("PREC",), "PQUAL")
+        put(("SLIQSP", "ILIQC", "ALIQC", "SURO", "IFWO", "AGWO", "PERO", "WSSD", "SCRSD"), 0.0)
+    if act & B.get("IQUAL", 0):  # IQUAL.py:96-98, 118-120
+        require(("SURO", "SOSLD", "PREC"), "IQUAL")
+        put(("SLIQSP",), -1.0e30)
     return fill, opts

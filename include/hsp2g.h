@@ -56,6 +56,12 @@ extern "C" {
 #define HSP2G_IWATER 64u
 #define HSP2G_SOLIDS 128u /* IMPLND SOLIDS, SOLIDS.py:53 */
 #define HSP2G_IWTGAS 256u /* IMPLND IWTGAS, IWTGAS.py:65 */
+/* Quality constituents, _pqual_ PQUAL.py:124 / _iqual_ IQUAL.py:109.  A batch created with ONLY one of these bits holds one
+ * row per (segment, constituent): the reference loops constituents inside a segment, they do not interact, so each is a row
+ * of its own.  The rows read the segment's SURO IFWO AGWO PERO WSSD SCRSD PREC (PQUAL) / SURO SOSLD PREC (IQUAL) as
+ * forcing series.  Combining these bits with the hydrology sections in one batch is refused. */
+#define HSP2G_PQUAL 512u
+#define HSP2G_IQUAL 1024u
 
 /* hsp2g_set_forcing_layout opts */
 #define HSP2G_OPT_SED_RAIN_IS_PREC 1u /* SEDMNT.py:86-89: no RAINF in ts -> RAIN = PREC */

@@ -45,31 +45,56 @@ def run_oracle(case, time_unit="us"):
 
 def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps=None, save="all", max_steps=None,
               out_dtype=None):
-    """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block)."""
+    """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block).  A PQUAL /
+    IQUAL section runs as a batch of (segment, constituent) rows fed by the land batch's outputs (engine.QualBatch)."""
     si = CASES.siminfo_for(case)
     cal = Calendar(si["start"], si["stop"], si["delt"], time_unit)
     forc = CASES.forcings(case)
     if max_steps is not None:
         forc = {k: v[:max_steps] for k, v in forc.items()}
     F = _lib.index("forcings")
-    names = [n for n in forc if n in F]
-    tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
-    store = SegmentStore.from_tables(case["operation"], tables, cal)
-    with LandBatch(store, cal, names, save, device=device) as b:
-        if sub_steps is not None:
-            b.set_schedule(sub_steps)
-        if out_dtype is not None:
-            b.set_output_dtype(out_dtype)
-        out = b.run(pack_forcings(forc, names, replicate), chunk=chunk)
-        e = b.errors()
-        kname = b.kernel_name()
-        save = b.save
-    order = CASES.ORDER[case["operation"]]
-    errs = {}
-    for a in order:
-        if store.act & _lib.ACT_BITS[a]:
-            errs[a] = np.stack([e[k] for k in ERRORS_OF[a]]) if ERRORS_OF[a] else np.zeros((0, replicate), dtype=np.int64)
-    ts = {full.split("_", 1)[1]: out[:, r, :] for r, full in enumerate(save)}
+    op = case["operation"]
+    qsec = "PQUAL" if op == "PERLND" else "IQUAL"
+    has_qual = bool(case["tables"]["ACTIVITY"].get(qsec, 0))
+    land_on = any(v for k, v in case["tables"]["ACTIVITY"].items() if k != qsec)
+    ts, errs, kname = {}, {}, None
+    if land_on:
+        names = [n for n in forc if n in F and n not in ("SLIQSP", "ILIQC", "ALIQC")]
+        tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
+        store = SegmentStore.from_tables(op, tables, cal)
+        with LandBatch(store, cal, names, save, device=device) as b:
+            if sub_steps is not None:
+                b.set_schedule(sub_steps)
+            if out_dtype is not None:
+                b.set_output_dtype(out_dtype)
+            out = b.run(pack_forcings(forc, names, replicate), chunk=chunk)
+            e = b.errors()
+            kname = b.kernel_name()
+            saved = b.save
+        for a in CASES.ORDER[op]:
+            if a != qsec and store.act & _lib.ACT_BITS[a]:
+                errs[a] = np.stack([e[k] for k in ERRORS_OF[a]]) if ERRORS_OF[a] else np.zeros((0, replicate), dtype=np.int64)
+        ts = {full.split("_", 1)[1]: out[:, r, :] for r, full in enumerate(saved)}
+    if has_qual and save == "all" and out_dtype is None:
+        from hspsquared_b200.engine import QualBatch
+        from hspsquared_b200.qualstore import IQUAL_INPUTS, PQUAL_INPUTS
+
+        series = dict(forc)
+        series.update(ts)  # the land sections' outputs override nothing the constituents read from outside
+        qn = [n for n in (PQUAL_INPUTS if op == "PERLND" else IQUAL_INPUTS) if n in series]
+        ucis = [copy.deepcopy(case["tables"][qsec]) for _ in range(replicate)]
+        with QualBatch(op, ucis, cal, qn, "all", device=device) as q:
+            if sub_steps is not None:
+                q.set_schedule(sub_steps)
+            qout = q.run(q.gather(series), chunk=chunk)
+            errs[qsec] = q.segment_errors(replicate)
+            kname = kname or q.kernel_name()
+            for j, (i, k) in enumerate(q.rows):
+                for r, full in enumerate(q.save):
+                    key = "%s%d_%s" % (qsec, k, full.split("_", 1)[1])
+                    if key not in ts:
+                        ts[key] = np.empty((qout.shape[0], replicate))
+                    ts[key][:, i] = qout[:, r, j]
     return ts, errs, kname
 
 

@@ -27,7 +27,8 @@ def test_fused_bit_exact(name):
         assert np.array_equal(got_err[a], np.repeat(e[:, None], 3, axis=1)), a
 
 
-@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear"])
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear", "cbp_pqual",
+                                  "i_iqual_variants"])
 def test_chunked_equals_single_pass(name):
     """State (named + hidden) carried through the per-segment state record makes chunked runs bit-identical."""
     case = ALL[name]
@@ -39,7 +40,7 @@ def test_chunked_equals_single_pass(name):
         assert np.array_equal(ea[k], eb[k])
 
 
-@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10"])
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10", "i_iqual_variants"])
 def test_subchunk_tasks_equal_whole_chunk(name):
     """More tiles than resident warps (the test double holds one): a launch is cut into (tile, sub-chunk) tasks and a
     tile's state passes from task to task through the segment store -- bit-identical to one task per tile, including

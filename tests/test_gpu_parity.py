@@ -75,7 +75,8 @@ def test_fused_bit_exact_on_gpu(name):
         assert np.array_equal(got_err[a], np.repeat(e[:, None], 2, axis=1)), (a, got_err[a][:, 0], e)
 
 
-@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear"])
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear", "cbp_pqual",
+                                  "i_iqual_variants"])
 def test_chunked_equals_single_pass_bitwise(name):
     case = ALL[name]
     a, ea, _ = parity.run_fused(case)
