@@ -70,9 +70,22 @@ static inline bool io_matches(const LandLaunch &L) {
     }
     r = 0;
     for (int id = 0; id < HSP2G_NOUT; ++id) {
-        const bool on = id < 128 && (((id < 64 ? IO::S0 : IO::S1) >> (id & 63)) & 1ull);
+        const bool on = io_saved<IO>(id);
         if (L.srow[id] != (on ? r : -1)) return false;
         r += on;
     }
     return true;
 }
+
+// PQUAL / IQUAL rows with the inputs a land batch produces (+ PREC) and every output of the constituent
+#define FM_PQUAL7 ((1ull << F_SURO) | (1ull << F_IFWO) | (1ull << F_AGWO) | (1ull << F_PERO) | (1ull << F_WSSD) | \
+                   (1ull << F_SCRSD) | (1ull << F_PREC))
+#define FM_IQUAL3 ((1ull << F_SURO) | (1ull << F_SOSLD) | (1ull << F_PREC))
+constexpr unsigned long long out_range_mask(int lo, int n, int word) {  // ids [lo, lo+n) that fall in 64-bit word `word`
+    unsigned long long m = 0;
+    for (int id = lo; id < lo + n; ++id)
+        if (id / 64 == word) m |= 1ull << (id & 63);
+    return m;
+}
+typedef StaticIO<FM_PQUAL7, 0, out_range_mask(O_PQUAL_SQO, 20, 1), false, out_range_mask(O_PQUAL_SQO, 20, 2)> IO_PqualAll;
+typedef StaticIO<FM_IQUAL3, 0, out_range_mask(O_IQUAL_SOQUAL, 12, 1), false, out_range_mask(O_IQUAL_SOQUAL, 12, 2)> IO_IqualAll;

@@ -182,6 +182,11 @@ __device__ __forceinline__ int hsp_popc(unsigned long long x) { return __builtin
 #else
 __device__ __forceinline__ int hsp_popc(unsigned long long x) { return __popcll(x); }  // folds on constants
 #endif
+template <class IO>
+__device__ __forceinline__ int io_row(int oid) {
+    return (oid < 64 ? 0 : hsp_popc(IO::S0)) + (oid < 128 ? 0 : hsp_popc(IO::S1)) +
+           hsp_popc((oid < 64 ? IO::S0 : oid < 128 ? IO::S1 : IO::S2) & ((1ull << (oid & 63)) - 1ull));
+}
 
 // ---- I/O policy: which forcing rows exist and which outputs are saved --------------------------------------
 // DynIO reads the row tables of the launch record at run time (any layout).  StaticIO<forcing mask, save mask>
@@ -191,19 +196,24 @@ __device__ __forceinline__ int hsp_popc(unsigned long long x) { return __popcll(
 // (save_timeseries casts the frame with astype(np.float32), utilities.py:313): half the bytes to HBM and over PCIe.
 struct DynIO {
     static constexpr bool STATIC = false, F32 = false;  // DynIO reads L.out_f32 at run time
-    static constexpr unsigned long long FMASK = 0, S0 = 0, S1 = 0;
+    static constexpr unsigned long long FMASK = 0, S0 = 0, S1 = 0, S2 = 0;
     static constexpr int NF = 0, NS = 0;
 };
 constexpr int ce_popc(unsigned long long x) { return x ? (int)(x & 1ull) + ce_popc(x >> 1) : 0; }
-template <unsigned long long FM, unsigned long long SM0, unsigned long long SM1, bool F32_ = false>
+// forcing ids < 64 in FM; output ids 0..63 in SM0, 64..127 in SM1, 128..191 in SM2
+template <unsigned long long FM, unsigned long long SM0, unsigned long long SM1, bool F32_ = false, unsigned long long SM2 = 0>
 struct StaticIO {
     static constexpr bool STATIC = true, F32 = F32_;
-    static constexpr unsigned long long FMASK = FM, S0 = SM0, S1 = SM1;
-    static constexpr int NF = ce_popc(FM), NS = ce_popc(SM0) + ce_popc(SM1);
+    static constexpr unsigned long long FMASK = FM, S0 = SM0, S1 = SM1, S2 = SM2;
+    static constexpr int NF = ce_popc(FM), NS = ce_popc(SM0) + ce_popc(SM1) + ce_popc(SM2);
 };
-static_assert(HSP2G_NFORC <= 64 && (int)O_PQUAL_SQO <= 128,
-              "StaticIO masks are 64 + 128 bits; the PQUAL / IQUAL outputs beyond them exist for DynIO kernels only");
-
+static_assert(HSP2G_NFORC <= 64 && HSP2G_NOUT <= 192, "StaticIO masks are 64 + 192 bits");
+// compile-time SAVE set: is output `oid` saved; its row (rows are in ascending id order) is io_row<IO>() above, written with
+// the device population count, which folds on constants (ce_popc is a host constexpr and must not be reached at run time).
+template <class IO>
+__host__ __device__ constexpr bool io_saved(int oid) {
+    return ((oid < 64 ? IO::S0 : oid < 128 ? IO::S1 : IO::S2) >> (oid & 63)) & 1ull;
+}
 #ifndef HSP2G_HOST_EMU
 // ---- forcing pipeline: a PIPE_STAGES-deep ring per warp in shared memory, filled by the TMA engine.  Lane 0 arms
 // the stage's mbarrier with the byte count and issues one cp.async.bulk for the whole interval (nf rows x 256 B,
@@ -554,16 +564,12 @@ struct Seg {
         return flag(flagbit) ? monthly(mid) : par(pid);
     }
     __device__ __forceinline__ bool saved(int oid) const {
-        if (IO::STATIC) return ((oid < 64 ? IO::S0 : IO::S1) >> (oid & 63)) & 1ull;
+        if (IO::STATIC) return io_saved<IO>(oid);
         return L.srow[oid] >= 0;
     }
     __device__ __forceinline__ void save(int oid, double v) const {
         if (IO::STATIC) {
-            if (((oid < 64 ? IO::S0 : IO::S1) >> (oid & 63)) & 1ull) {
-                const int r = (oid < 64 ? 0 : hsp_popc(IO::S0)) +
-                              hsp_popc((oid < 64 ? IO::S0 : IO::S1) & ((1ull << (oid & 63)) - 1ull));
-                store_out(r, v);
-            }
+            if (io_saved<IO>(oid)) store_out(io_row<IO>(oid), v);
         } else {
             const int r = L.srow[oid];
             if (r >= 0) store_out(r, v);

@@ -4,16 +4,21 @@
 // the ticket scheduler, the storage is carried in registers and handed on through the segment block, saved series stream
 // out tile-major.  A constituent needs ~40 fp64 operations per interval against 7 series read and up to 20 written, so the
 // kernel is bound by HBM like the land kernels; no hot-parameter staging is needed (the day's parameters sit in registers).
+#include "io_configs.h"
 #include "land_kernels.cuh"
 #include "launch.h"
 #include "qual.cuh"
 
-template <bool IMP, int MAXREG>
+#ifndef HSP_MAXREG_QUAL
+#define HSP_MAXREG_QUAL 96
+#endif
+
+template <bool IMP, class IO, int MAXREG>
 __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) qual_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
-    const int nf = L.nf;
-    typedef Seg<DynIO, 0ull, false> SegT;
+    const int nf = IO::STATIC ? IO::NF : L.nf;
+    typedef Seg<IO, 0ull, false> SegT;
     PipeT<false> pipe;
     pipe.init(smem, wib, lane, nf, 0, 0, 0);
     Sched sched(L, lane, wib);
@@ -39,10 +44,10 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) qual_kernel(co
     }
 }
 
-template <bool IMP>
+template <bool IMP, class IO>
 static cudaError_t launch_qual(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(L.nf, 0ull, 0, false);
-    auto k = qual_kernel<IMP, 96>;
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, 0ull, 0, false);
+    auto k = qual_kernel<IMP, IO, HSP_MAXREG_QUAL>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -53,6 +58,10 @@ static cudaError_t launch_qual(LandLaunch &L, int sub_pref, cudaStream_t st, con
 }
 
 cudaError_t hsp2g_launch_qual(LandLaunch &L, bool implnd, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
-    return implnd ? launch_qual<true>(L, sub_pref, st, name, "qual_kernel<IQUAL,io=dynamic>", grid_out)
-                  : launch_qual<false>(L, sub_pref, st, name, "qual_kernel<PQUAL,io=dynamic>", grid_out);
+    if (implnd) {
+        if (io_matches<IO_IqualAll>(L)) return launch_qual<true, IO_IqualAll>(L, sub_pref, st, name, "qual_kernel<IQUAL,in=3,save=all12>", grid_out);
+        return launch_qual<true, DynIO>(L, sub_pref, st, name, "qual_kernel<IQUAL,io=dynamic>", grid_out);
+    }
+    if (io_matches<IO_PqualAll>(L)) return launch_qual<false, IO_PqualAll>(L, sub_pref, st, name, "qual_kernel<PQUAL,in=7,save=all20>", grid_out);
+    return launch_qual<false, DynIO>(L, sub_pref, st, name, "qual_kernel<PQUAL,io=dynamic>", grid_out);
 }

@@ -89,7 +89,7 @@ def test_chunked_equals_single_pass_bitwise(name):
 
 @pytest.mark.parametrize("name", ["p001_test10", "i001_test10", "cbp_fullchain", "p_nosnow_iffc2", "flowtest_pwater",
                                   "flowtest_iwater", "i_atemp_snow", "i001_iwtgas", "i_solids_m1_wtf_monthly",
-                                  "i_solids_iwtgas_alone"])
+                                  "i_solids_iwtgas_alone", "i001_iqual", "i_iqual_variants", "cbp_pqual", "p_pqual_alone"])
 def test_dropin_vs_oracle(name):
     case = ALL[name]
     ref, ref_err = parity.run_oracle(case)
@@ -265,6 +265,57 @@ def test_hspf_known_answers(golden_dir):
         ok = ref > -1e29
         assert np.array_equal(ok, g > -1e29), key
         assert np.abs(g[ok] - ref[ok]).max() <= 2e-6 * np.abs(ref[ok]).max(), key
+    # IQUAL group (constituent COD) of the same HSPF run: IMPLND kernel -> qual kernel
+    got, errs, _ = parity.run_fused(ALL["i001_iqual"])
+    assert not errs["IQUAL"].any()
+    for cons in ("SQO", "SOQSP", "SOQOC", "SOQC", "SOQS", "SOQO", "SOQUAL"):
+        ref, g = h10["IQUAL_" + cons], got["IQUAL1_" + cons][:, 0]
+        ok = ref > -1e29
+        assert np.array_equal(ok, g > -1e29), cons
+        assert np.abs(g[ok] - ref[ok]).max() <= (1e-5 if cons in ("SOQOC", "SOQC") else 2e-6) * np.abs(ref[ok]).max(), cons
+
+
+def test_qual_rows_many_segments():
+    """PQUAL as a batch of (segment, constituent) rows: 5,000 jittered full-chain segments x 3 constituents fed by the land
+    batch's outputs; sampled segments equal the oracle's chain, and rows of different segments do not mix."""
+    from hspsquared_b200 import synth, test10
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch, QualBatch
+    from hspsquared_b200.qualstore import PQUAL_INPUTS
+
+    cal = Calendar("1976-02-01", "1976-04-01", 60, "us")
+    n = 5000
+    ens = synth.Ensemble("PERLND", n, seed=17, base="cbp", options=("RTOPFG", "UZFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
+    need = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "PWATER_PERO", "SEDMNT_WSSD", "SEDMNT_SCRSD"]
+    with LandBatch(ens.store(cal), cal, names, need) as b:
+        land = b.run(f, chunk=480)
+    series = {full.split("_", 1)[1]: land[:, r, :] for r, full in enumerate(need)}
+    series["PREC"] = f[:, names.index("PREC"), :]
+    qt = test10.pqual_tables()
+    qn = [k for k in PQUAL_INPUTS if k in series]
+    with QualBatch("PERLND", [qt] * n, cal, qn, "all") as q:
+        assert q.n == 3 * n
+        out = q.run(q.gather(series), chunk=480)
+        rows, save = q.rows, q.save
+        assert "qual_kernel<PQUAL" in q.kernel_name()
+    for i in (0, 2500, 4999):
+        t = ens.tables_of(i)
+        t["ACTIVITY"]["PQUAL"] = 1
+        t["PQUAL"] = test10.pqual_tables()
+        si = {"start": cal.start, "stop": cal.stop, "delt": 60, "units": 1, "steps": cal.steps, "time_unit": "us"}
+        ts = synth.forcing_of(ens, cal, i, 0, cal.steps)
+        CASES.run_segment("PERLND", t, ts, si, parity.ORACLE_ACTS)
+        for j, (seg, k) in enumerate(rows):
+            if seg != i:
+                continue
+            for r, full in enumerate(save):
+                key = "PQUAL%d_%s" % (k, full.split("_", 1)[1])
+                if parity.GPU_EXACT:
+                    assert np.array_equal(out[:, r, j], ts[key], equal_nan=True), (i, key)
+                else:
+                    assert parity.rel_err(out[:, r, j], ts[key]) <= parity.RTOL, (i, key)
 
 
 def test_metstore_feeds_shared_met_kernels():

@@ -15,7 +15,73 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (device_forcing, measured_peak, default_save)
 
 
+def run_qual(name, torch, dev):
+    """PQUAL / IQUAL rows: `n` (segment, constituent) rows reading synthetic flow / sediment series resident in HBM."""
+    from hspsquared_b200 import test10
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import QualBatch
+    from hspsquared_b200.qualstore import IQUAL_INPUTS, PQUAL_INPUTS
+
+    cal = Calendar(bench.RUN_START, bench.RUN_STOP, 60, "ns")
+    K, W, Tc = 8, 3, 256
+    imp = name == "iqual"
+    nseg = 100_000
+    tabs = test10.iqual_tables() if imp else test10.pqual_tables()
+    names = list(IQUAL_INPUTS[:3] if imp else PQUAL_INPUTS[:7])
+    with QualBatch("IMPLND" if imp else "PERLND", [tabs] * nseg, cal, names, "all", device=dev.index or 0) as batch:
+        npad, nf, ns, n = batch.npad, batch.nf, batch.ns, batch.n
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        forc = []
+        for c in range(K + W):
+            # storms are shared by all rows (7 % of the intervals), magnitudes differ per row; dry intervals carry no
+            # surface runoff, sediment or solids, subsurface flows are small and always there
+            u = torch.rand((npad // 32, Tc, nf, 32), generator=g, device=dev, dtype=torch.float64)
+            wet = (torch.rand((1, Tc, 1), generator=g, device=dev) > 0.93).to(torch.float64)
+            f = torch.empty_like(u)
+            if imp:  # SURO SOSLD PREC
+                f[:, :, 0] = wet * 0.03 * u[:, :, 0]
+                f[:, :, 1] = wet * 0.002 * u[:, :, 1]
+                f[:, :, 2] = wet * 0.05 * u[:, :, 2]
+            else:  # SURO IFWO AGWO PERO WSSD SCRSD PREC
+                f[:, :, 0] = wet * 0.02 * u[:, :, 0]
+                f[:, :, 1] = 0.001 * u[:, :, 1]
+                f[:, :, 2] = 0.001 + 0.001 * u[:, :, 2]
+                f[:, :, 3] = f[:, :, 0] + f[:, :, 1] + f[:, :, 2]
+                f[:, :, 4] = wet * 0.05 * u[:, :, 4]
+                f[:, :, 5] = wet * 0.01 * u[:, :, 5] * (u[:, :, 3] > 0.5)
+                f[:, :, 6] = wet * 0.05 * u[:, :, 6]
+            forc.append(f)
+            del u
+        outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+        stream = torch.cuda.Stream(dev)
+        torch.cuda.synchronize(dev)
+        for c in range(W):
+            batch.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for c in range(W, W + K):
+            batch.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        peak, _src = bench.measured_peak()
+        B = 8 * (nf + ns)
+        value = n * Tc * K / (ms * 1e-3)
+        line = {"config": name, "kernel": batch.kernel_name(), "rows": n, "segments": nseg, "intervals_per_step": Tc, "steps": K,
+                "forcing_rows": nf, "saved_rows": ns, "bytes_per_row_interval": B, "ms_per_step": ms / K,
+                "row_timesteps_per_s": value, "algorithmic_GBps": value * B / 1e9, "frac_of_measured_hbm": value * B / 1e9 / peak,
+                "note": "one row = one (segment, constituent) pair; synthetic flow / sediment series: storms in 7 % of the intervals, "
+                        "shared by all rows, per-row magnitudes"}
+    del forc, outs
+    torch.cuda.empty_cache()
+    return line
+
+
 def run(name, torch, dev):
+    if name in ("pqual", "iqual"):
+        return run_qual(name, torch, dev)
     from hspsquared_b200 import synth, test10
     from hspsquared_b200.calendar import Calendar
     from hspsquared_b200.engine import LandBatch
