@@ -64,7 +64,10 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01"):
     m = H.load()
     UCI = sys.modules["hsp2.hsp2.uci"].UCI if "hsp2.hsp2.uci" in sys.modules else __import__("hsp2.hsp2.uci", fromlist=["UCI"]).UCI
     u = UCI()
-    tables = {"PERLND": ("P001", test10.perlnd(), PERLND_ACTS), "IMPLND": ("I001", test10.implnd(), IMPLND_ACTS)}
+    imp = test10.implnd()
+    imp["ACTIVITY"]["IQUAL"] = 1  # test10.uci:173-177 switches IQUAL on for IMPLND 1
+    imp["IQUAL"] = test10.iqual_tables()
+    tables = {"PERLND": ("P001", test10.perlnd(), PERLND_ACTS), "IMPLND": ("I001", imp, IMPLND_ACTS)}
     rows = []
     for op, (seg, t, acts) in tables.items():
         u.uci[(op, "GENERAL", seg)] = {"ACTIVITY": {a: int(t["ACTIVITY"].get(a, 0)) for a in acts}}
@@ -73,6 +76,8 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01"):
                 continue
             ui = copy.deepcopy(tab)
             ui["SAVE"] = {k: 1 for k in test10.SAVE_DEFAULT.get(act, ())}
+            if act == "IQUAL":  # SaveTable.csv:264-273 (all 0: written only under saveall)
+                ui["SAVE"] = {k: 0 for k in ("SQO", "SOQSP", "SOQS", "SOQO", "SOQOC", "SOQUAL", "SOQC", "IQADDR", "IQADWT", "IQADEP")}
             u.uci[(op, act, seg)] = ui
         rows.append((op, seg, 60))
         u.ddext_sources[(op, seg)] = [Row(dsn, mf, name, tran, "") for dsn, mf, tran, name in H.TEST10_EXT[op]]
