@@ -266,6 +266,37 @@ __global__ void math_probe_kernel(int fn, long long n, const double *x, const do
 }
 #endif
 
+// ---- row gather between tile-major series buffers (hsp2g_gather_*): destination entity j = (dtile, lane) takes its rows from
+// source segment seg_of[j].  One warp per destination tile walks the intervals; per interval and row a lane moves 8 bytes
+// (neighbouring lanes read neighbouring segments' cells of the same 256-byte source row, so the reads stay sector-efficient).
+#define GATHER_MAXROWS 16
+struct GatherArgs {
+    const double *src;
+    double *dst;
+    const long long *seg_of;
+    long long n_dst_pad;
+    int nsteps, src_rows, dst_rows, k;
+    short src_row[GATHER_MAXROWS], dst_row[GATHER_MAXROWS];
+};
+#ifndef HSP2G_HOST_EMU
+__global__ void __launch_bounds__(128) gather_kernel(const __grid_constant__ GatherArgs A) {
+    const long long j = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (j >= A.n_dst_pad) return;
+    const long long seg = A.seg_of[j];
+    const double *s = A.src + ((size_t)(seg / LAND_TILE) * A.nsteps * A.src_rows) * LAND_TILE + (seg % LAND_TILE);
+    double *d = A.dst + ((size_t)(j / LAND_TILE) * A.nsteps * A.dst_rows) * LAND_TILE + (j % LAND_TILE);
+    for (int t = 0; t < A.nsteps; ++t) {
+        double v[GATHER_MAXROWS];
+#pragma unroll
+        for (int r = 0; r < GATHER_MAXROWS; ++r)
+            if (r < A.k) v[r] = __ldcs(s + ((size_t)t * A.src_rows + A.src_row[r]) * LAND_TILE);
+#pragma unroll
+        for (int r = 0; r < GATHER_MAXROWS; ++r)
+            if (r < A.k) d[((size_t)t * A.dst_rows + A.dst_row[r]) * LAND_TILE] = v[r];
+    }
+}
+#endif
+
 // Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
 // forcing rows are present); the resident-block count sizes the persistent grid.
 cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident) {
@@ -589,6 +620,8 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
     return launch(b, t0, nsteps, d_forc, d_out, stream ? (cudaStream_t)stream : b->comp);
 }
 
+void *hsp2g_batch_stream(hsp2g_batch *b) { return b ? (void *)b->comp : nullptr; }
+
 int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, double *h_out) {
     if (check_ready(b, t0, nsteps)) return 1;
     if (b->nf > 0 && !h_forc && !b->met) return fail("null forcing buffer");
@@ -710,6 +743,82 @@ int hsp2g_math_probe(int device, int fn, int64_t n, const double *x, const doubl
     cudaFree(dy);
     cudaFree(dout);
     if (e != cudaSuccess) return fail("math probe: %s", cudaGetErrorString(e));
+    return 0;
+#endif
+}
+
+struct hsp2g_gather {
+    int device;
+    long long n_dst, n_dst_pad, n_src;
+    long long *seg_of;  // device [n_dst_pad]; padded entries repeat the last one
+};
+
+int hsp2g_gather_create(int device, int64_t n_src_seg, int64_t n_dst, const int64_t *seg_of, hsp2g_gather **out) {
+    if (!out) return fail("null out");
+    *out = nullptr;
+    if (!seg_of || n_dst <= 0 || n_src_seg <= 0) return fail("bad gather arguments");
+    for (int64_t j = 0; j < n_dst; ++j)
+        if (seg_of[j] < 0 || seg_of[j] >= n_src_seg) return fail("seg_of[%lld] = %lld outside [0, %lld)", (long long)j, (long long)seg_of[j], (long long)n_src_seg);
+    DeviceGuard g(device);
+    if (!g.ok) return fail("cudaSetDevice(%d) failed", device);
+    hsp2g_gather *h = new hsp2g_gather();
+    h->device = device;
+    h->n_dst = n_dst;
+    h->n_src = n_src_seg;
+    h->n_dst_pad = (n_dst + LAND_TILE - 1) / LAND_TILE * LAND_TILE;
+    std::vector<long long> v((size_t)h->n_dst_pad);
+    for (long long j = 0; j < h->n_dst_pad; ++j) v[(size_t)j] = seg_of[j < n_dst ? j : n_dst - 1];
+    if (cudaMalloc((void **)&h->seg_of, v.size() * sizeof(long long)) != cudaSuccess) {
+        delete h;
+        return fail("out of device memory");
+    }
+    cudaMemcpy(h->seg_of, v.data(), v.size() * sizeof(long long), cudaMemcpyHostToDevice);
+    *out = h;
+    return 0;
+}
+
+void hsp2g_gather_destroy(hsp2g_gather *h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    cudaFree(h->seg_of);
+    delete h;
+}
+
+int hsp2g_gather_run(hsp2g_gather *h, const double *d_src, int32_t src_rows, double *d_dst, int32_t dst_rows, int32_t k,
+                     const int32_t *src_row, const int32_t *dst_row, int32_t nsteps, void *stream) {
+    if (!h || !d_src || !d_dst || !src_row || !dst_row) return fail("null argument");
+    if (k <= 0 || k > GATHER_MAXROWS) return fail("between 1 and %d rows per call", GATHER_MAXROWS);
+    if (nsteps <= 0 || src_rows <= 0 || dst_rows <= 0) return fail("bad series shape");
+    GatherArgs A;
+    memset(&A, 0, sizeof A);
+    A.src = d_src;
+    A.dst = d_dst;
+    A.seg_of = h->seg_of;
+    A.n_dst_pad = h->n_dst_pad;
+    A.nsteps = nsteps;
+    A.src_rows = src_rows;
+    A.dst_rows = dst_rows;
+    A.k = k;
+    for (int r = 0; r < k; ++r) {
+        if (src_row[r] < 0 || src_row[r] >= src_rows || dst_row[r] < 0 || dst_row[r] >= dst_rows) return fail("row index out of range");
+        A.src_row[r] = (short)src_row[r];
+        A.dst_row[r] = (short)dst_row[r];
+    }
+    DeviceGuard g(h->device);
+#ifdef HSP2G_HOST_EMU
+    (void)stream;
+    for (long long j = 0; j < A.n_dst_pad; ++j) {
+        const long long seg = A.seg_of[j];
+        for (int t = 0; t < nsteps; ++t)
+            for (int r = 0; r < k; ++r)
+                A.dst[(((size_t)(j / LAND_TILE) * nsteps + t) * dst_rows + A.dst_row[r]) * LAND_TILE + (j % LAND_TILE)] =
+                    A.src[(((size_t)(seg / LAND_TILE) * nsteps + t) * src_rows + A.src_row[r]) * LAND_TILE + (seg % LAND_TILE)];
+    }
+    return 0;
+#else
+    gather_kernel<<<(unsigned)((A.n_dst_pad + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("gather launch failed: %s", cudaGetErrorString(e));
     return 0;
 #endif
 }

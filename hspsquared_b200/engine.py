@@ -320,6 +320,60 @@ class QualBatch(LandBatch):
             out[:, r, :] = a[:steps, None] if a.ndim == 1 else a[:steps][:, self.row_segment]
         return out
 
+    # -- device-resident chain: land batch -> gather -> constituents (no host round trip of the flow series) ------------------
+    OUTPUT_OF = {"PERLND": {"SURO": "PWATER_SURO", "IFWO": "PWATER_IFWO", "AGWO": "PWATER_AGWO", "PERO": "PWATER_PERO",
+                            "WSSD": "SEDMNT_WSSD", "SCRSD": "SEDMNT_SCRSD"},
+                 "IMPLND": {"SURO": "IWATER_SURO", "SOSLD": "SOLIDS_SOSLD"}}
+
+    def attach(self, land):
+        """Take this batch's input series from `land`'s device buffers: a series the land sections produce comes from
+        land's output rows (it must be in land's SAVE set, float64), anything else from land's forcing rows."""
+        if land.out_dtype != np.float64:
+            raise ValueError("the land batch must write float64 outputs to feed constituents")
+        seg = self.row_segment if land._inv is None else np.asarray(land._inv)[self.row_segment]
+        seg = np.ascontiguousarray(seg, dtype=np.int64)
+        self._gather = _lib._h()
+        _lib.check(self.lib.hsp2g_gather_create(self.device, land.npad, self.n, _ptr(seg, C.POINTER(C.c_int64)),
+                                                C.byref(self._gather)))
+        from_out, from_forc = [], []
+        for r, nme in enumerate(self.forcing_rows):
+            full = self.OUTPUT_OF[self.store.operation].get(nme)
+            if full is not None and full in land.save_rows:
+                from_out.append((land.save_rows.index(full), r))
+            elif nme in land.forcing_rows and full is None:
+                from_forc.append((land.forcing_rows.index(nme), r))
+            else:
+                raise KeyError("%s: neither saved by the land batch (%s) nor one of its forcing rows" % (nme, full))
+        self._plan = (land.ns, from_out, land.nf, from_forc)
+        self._land = land
+        return self
+
+    def run_device_from(self, t0, nsteps, d_land_forcing, d_land_out, d_scratch, d_out, stream=0):
+        """Gather the inputs of intervals [t0, t0+nsteps) from the land batch's device buffers of the same chunk into
+        `d_scratch` ([ntiles][nsteps][nf][32] float64) and run the constituents into `d_out`.  With an explicit `stream` the
+        caller orders this after the land launch (same stream); without one the land batch is synchronised first and the
+        gather and the constituents run on this batch's own stream."""
+        ns, from_out, nf, from_forc = self._plan
+        if not stream:
+            self._land.sync()
+            stream = self.lib.hsp2g_batch_stream(self.h)
+        i32 = C.POINTER(C.c_int32)
+        for src, rows, pairs in ((d_land_out, ns, from_out), (d_land_forcing, nf, from_forc)):
+            if not pairs:
+                continue
+            a = np.array([p[0] for p in pairs], dtype=np.int32)
+            b = np.array([p[1] for p in pairs], dtype=np.int32)
+            _lib.check(self.lib.hsp2g_gather_run(self._gather, src, rows, d_scratch, self.nf, len(pairs), _ptr(a, i32),
+                                                 _ptr(b, i32), int(nsteps), stream or None))
+        self.run_device(t0, nsteps, d_scratch, d_out, stream)
+
+    def close(self):
+        g = getattr(self, "_gather", None)
+        if g is not None and g.value:
+            self.lib.hsp2g_gather_destroy(g)
+            self._gather = None
+        super().close()
+
     def segment_errors(self, n_segments):
         """int64[2][n_segments]: the reference's error vector of each segment (errors[0] = constituents that take
         atmospheric deposition without being associated with overland flow, PQUAL.py:171-174)."""

@@ -133,6 +133,20 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
 int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, double *h_out);
 /* Host-side re-tiling between [interval][row][ld] and [tile][interval][row][32] (what get_timeseries /
  * save_timeseries hand over per segment, utilities.py:274-333, for a whole batch). */
+/* The stream hsp2g_run_device uses when it is given none (non-blocking; nothing orders it against other streams): pass it to
+ * hsp2g_gather_run, or to another batch's hsp2g_run_device, to chain work on the device in order. */
+void *hsp2g_batch_stream(hsp2g_batch *b);
+
+/* Row gather between two device-resident tile-major series buffers with the same interval count: destination entity j takes
+ * row dst_row[r] from row src_row[r] of source segment seg_of[j] (r < k <= 16 per call).  Feeds a PQUAL / IQUAL batch, whose
+ * entities are (segment, constituent) rows, from the land batch's output and forcing buffers without leaving the device; the
+ * reference has no counterpart (its constituents read the segment's ts arrays in place, PQUAL.py:119-126). */
+typedef struct hsp2g_gather hsp2g_gather;
+int hsp2g_gather_create(int device, int64_t n_src_seg, int64_t n_dst, const int64_t *seg_of, hsp2g_gather **out);
+int hsp2g_gather_run(hsp2g_gather *g, const double *d_src, int32_t src_rows, double *d_dst, int32_t dst_rows, int32_t k,
+                     const int32_t *src_row, const int32_t *dst_row, int32_t nsteps, void *stream);
+void hsp2g_gather_destroy(hsp2g_gather *g);
+
 int hsp2g_pack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, int64_t ld, double *dst_tiled);
 int hsp2g_unpack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src_tiled, double *dst, int64_t ld);
 int hsp2g_sync(hsp2g_batch *b);

@@ -411,3 +411,62 @@ def check_watershed(tmpdir, n=48, gages=4, days=40, sample=(0, 7, 21), chunk=480
                 else:
                     assert f32_ulp_diff(got, ts[k]) <= 2, (i, a, k)
     return sink
+
+
+def check_qual_chain_on_device(n=70, chunk=300, order=None):
+    """Land batch -> hsp2g_gather_* -> PQUAL rows with every buffer device-resident (hsp2g_run_device on both batches) gives the
+    same bits as feeding the constituents from the land batch's host-side outputs (QualBatch.gather), with and without a
+    divergence-aware device order of the land segments."""
+    import ctypes as C
+
+    from hspsquared_b200.engine import QualBatch, tile_series, untile_series
+    from hspsquared_b200.qualstore import PQUAL_INPUTS
+
+    cal = Calendar("1976-02-10", "1976-03-25", 60, "us")
+    steps = cal.steps
+    ens = synth.Ensemble("PERLND", n, seed=31, base="cbp", options=("RTOPFG", "UZFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, steps, names=names)
+    need = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "PWATER_PERO", "SEDMNT_WSSD", "SEDMNT_SCRSD", "SNOW_PACKF"]
+    qn = list(PQUAL_INPUTS[:7])
+    ucis = [test10.pqual_tables() for _ in range(n)]
+    lib = _lib.load()
+    # reference path: host round trip
+    with LandBatch(ens.store(cal), cal, names, need) as land:
+        lo = land.run(f, chunk=chunk)
+    series = {full.split("_", 1)[1]: lo[:, r, :] for r, full in enumerate(need)}
+    series["PREC"] = f[:, names.index("PREC"), :]
+    with QualBatch("PERLND", ucis, cal, qn, "all") as q:
+        want = q.run(q.gather(series), chunk=chunk)
+    # device-resident chain
+    with LandBatch(ens.store(cal), cal, names, need, order=order) as land, QualBatch("PERLND", ucis, cal, qn, "all") as q:
+        q.attach(land)
+        got = np.empty_like(want)
+        dev = []
+
+        def dalloc(nbytes):
+            p = lib.hsp2g_device_alloc(0, nbytes)
+            assert p
+            dev.append(p)
+            return p
+
+        for t0 in range(0, steps, chunk):
+            m = min(chunk, steps - t0)
+            fc = f[t0:t0 + m][:, land._fperm, :]
+            if land.order is not None:
+                fc = fc[:, :, land.order]
+            ft = tile_series(fc)
+            d_f, d_lo = dalloc(ft.nbytes), dalloc(land.ntiles * m * land.ns * 32 * 8)
+            d_qf, d_qo = dalloc(q.ntiles * m * q.nf * 32 * 8), dalloc(q.ntiles * m * q.ns * 32 * 8)
+            _lib.check(lib.hsp2g_memcpy_h2d(0, d_f, ft.ctypes.data, ft.nbytes))
+            land.run_device(t0, m, d_f, d_lo)
+            q.run_device_from(t0, m, d_f, d_lo, d_qf, d_qo)
+            land.sync()
+            q.sync()
+            ho = np.empty((q.ntiles, m, q.ns, 32))
+            _lib.check(lib.hsp2g_memcpy_d2h(0, ho.ctypes.data, d_qo, ho.nbytes))
+            got[t0:t0 + m] = untile_series(ho, q.n)[:, q._sinv, :]
+        for p in dev:
+            lib.hsp2g_device_free(0, C.c_void_p(p))
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.nanmax(want[:, q.save.index("PQUAL_SOQUAL"), :]) > 0

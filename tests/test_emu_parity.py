@@ -97,3 +97,9 @@ def test_iwtgas_without_its_states_raises_like_the_reference():
     assert "STATES" not in uci
     with pytest.raises(KeyError):
         activities.iwtgas(None, si, uci, ts)
+
+
+@pytest.mark.parametrize("order", [None, "flags"])
+def test_constituents_fed_on_the_device(order):
+    """Land batch -> device gather -> PQUAL rows without a host round trip == the host-side chain, bit for bit."""
+    parity.check_qual_chain_on_device(order=order)

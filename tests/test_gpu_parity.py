@@ -318,6 +318,12 @@ def test_qual_rows_many_segments():
                     assert parity.rel_err(out[:, r, j], ts[key]) <= parity.RTOL, (i, key)
 
 
+def test_constituents_fed_on_the_device():
+    """Land kernel -> gather kernel -> qual kernel with every buffer in HBM: same bits as the host-side chain (3,000 segments,
+    divergence-ordered land batch)."""
+    parity.check_qual_chain_on_device(n=3000, chunk=256, order="flags")
+
+
 def test_metstore_feeds_shared_met_kernels():
     """EXT SOURCES rows -> MetStore (hspsquared_b200/ingest.py) -> hsp2g_set_shared_forcing: bit-identical to per-segment arrays."""
     parity.check_metstore_shared()
