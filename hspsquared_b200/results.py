@@ -62,3 +62,43 @@ def save_batch(io_manager, siminfo, operation, segment_names, save_tables, saved
             save_columns = list(df.columns) if saveall else [k for k, v in savedict.items() if v or saveall]
             io_manager.write_ts(data_frame=df, save_columns=save_columns, category=category, operation=operation,
                                 segment=seg, activity=act, compress=compress, outstep=outstep)
+
+
+def save_qual_batch(io_manager, siminfo, operation, segment_names, save_tables, qual_batch, out, saveall=False,
+                    compress=True, outstep=2, category=None):
+    """Results of a PQUAL / IQUAL batch (engine.QualBatch: rows = (segment, constituent)) the way save_timeseries writes them:
+    for these two activities the reference collects every ts name that CONTAINS '_<key>' for a key of the SAVE table
+    (utilities.py:294-301) -- so one frame per segment holds '<P|I>QUAL<k>_<NAME>' columns of all its constituents, and the key
+    SOQO also pulls in SOQOC -- then casts to float32 and sorts the columns.
+
+    save_tables : the activity's SAVE dict ({series name: 0/1}), one for the batch or a list with one per segment
+    out         : [steps][len(qual_batch.save)][rows]
+    """
+    import pandas as pd
+
+    category = result_category() if category is None else category
+    tindex = siminfo["tindex"]
+    out = np.asarray(out)
+    if out.shape[0] != len(tindex):
+        raise ValueError("out has %d intervals, tindex %d" % (out.shape[0], len(tindex)))
+    act = "PQUAL" if operation == "PERLND" else "IQUAL"
+    names = [full.split("_", 1)[1] for full in qual_batch.save]
+    rows_of = {}
+    for j, (i, k) in enumerate(qual_batch.rows):
+        rows_of.setdefault(i, []).append((k, j))
+    for i, seg in enumerate(segment_names):
+        savedict = save_tables[i] if isinstance(save_tables, (list, tuple)) else save_tables
+        cols = {}
+        for k, j in rows_of.get(i, ()):
+            for r, nm in enumerate(names):
+                z = "%s%d_%s" % (act, k, nm)
+                if any(("_" + y) in z for y in savedict):
+                    cols[z] = out[:, r, j]
+        if not cols:
+            print("DataFrame Empty for %s|%s|%s" % (operation, act, seg))
+            continue
+        order = sorted(cols)
+        df = pd.DataFrame(np.stack([cols[z] for z in order], axis=1).astype(np.float32, copy=False), index=tindex, columns=order)
+        save_columns = list(df.columns) if saveall else [k for k, v in savedict.items() if v or saveall]
+        io_manager.write_ts(data_frame=df, save_columns=save_columns, category=category, operation=operation, segment=seg,
+                            activity=act, compress=compress, outstep=outstep)

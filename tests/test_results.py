@@ -70,3 +70,37 @@ def test_save_batch_frames_equal_reference_frames():
             assert cols == [k for k, v in save_tables[act].items() if v]
     assert "TAET" in sink.calls[("PERLND", "P001", "PWATER")][0].columns
     assert "TAET" not in sink.calls[("PERLND", "P001", "PWATER")][1]
+
+
+def test_save_qual_batch_frames_equal_reference_frames():
+    """IQUAL rows -> one frame per segment with the reference's substring-matched column set (utilities.py:294-301)."""
+    from hspsquared_b200.engine import QualBatch
+    from hspsquared_b200.results import save_qual_batch
+
+    case = CASES.build_cases()["i_iqual_variants"]
+    ref, _ = parity.run_oracle(case)
+    si = CASES.siminfo_for(case)
+    cal = Calendar(si["start"], si["stop"], si["delt"], "us")
+    steps = case["steps"]
+    tindex = pd.date_range("1976-01-01", periods=steps + 1, freq="60min")[1:]
+    n = 3
+    series = {k: ref[k] for k in ("SURO", "SOSLD", "PREC", "SLIQSP")}
+    with QualBatch("IMPLND", [case["tables"]["IQUAL"]] * n, cal, list(series), "all") as q:
+        out = q.run(q.gather(series))
+        savedict = {k: 0 for k in ("SQO", "SOQSP", "SOQS", "SOQO", "SOQOC", "SOQUAL", "SOQC", "IQADDR", "IQADWT", "IQADEP")}
+        savedict["SOQUAL"] = 1
+        sink = Sink()
+        save_qual_batch(sink, {"tindex": tindex}, "IMPLND", ["I001", "I002", "I003"], savedict, q, out)
+    assert len(sink.calls) == n
+    # the reference's frame, restated: every ts key that contains '_<key>'
+    want = pd.DataFrame(index=tindex)
+    for y in savedict:
+        for z in ref:
+            if "_" + y in z:
+                want[z] = ref[z]
+    want = want.astype(np.float32).sort_index(axis="columns")
+    assert len(want.columns) == 3 * 10 and "IQUAL2_SOQOC" in want.columns and "IQUAL1_SLIQO" not in want.columns
+    for seg in ("I001", "I003"):
+        df, cols, cat, outstep = sink.calls[("IMPLND", seg, "IQUAL")]
+        assert list(df.columns) == list(want.columns) and cols == ["SOQUAL"]
+        assert np.array_equal(df.to_numpy(), want.to_numpy(), equal_nan=True) and df.to_numpy().dtype == np.float32
