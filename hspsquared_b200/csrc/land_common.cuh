@@ -382,7 +382,12 @@ struct Sched {
         return true;
     }
     __device__ __forceinline__ void done(int tile) {
+#ifdef HSP_TASK_FENCE
         __threadfence();
+#endif
+        // every lane's state rows (weak L2 stores) are ordered before lane 0's release by the warp barrier, and the release
+        // is cumulative at gpu scope: the warp that acquires progress[tile] and passes its own warp barrier sees them all.
+        // (A __threadfence() by all 32 lanes here cost a second MEMBAR and an L1 invalidate per task.)
         __syncwarp();
         if (lane == 0) st_release_u32(L.progress + tile, L.prog_base + (unsigned)c + 1u);
     }
