@@ -79,6 +79,8 @@ struct hsp2g_batch {
     short srow[HSP2G_NOUT];
     int nf = -1, ns = -1;
     bool have_par = false, have_flags = false, have_state = false;
+    int flags_uniform = 0;  // every segment carries flags_word (a replicated ensemble): kernels specialised on the word apply
+    unsigned long long flags_word = 0;
     cudaStream_t comp = nullptr, h2d = nullptr, d2h = nullptr;
     Slot slot[2];
     int next_slot = 0;
@@ -223,6 +225,8 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.out_f32 = b->out_f32;
     L.act = b->act;
     L.opts = b->opts;
+    L.flags_uniform = b->flags_uniform;
+    L.flags_word = b->flags_word;
     L.delt = b->delt;
     L.delt60 = b->delt / 60.0;
     memcpy(L.frow, b->frow, sizeof L.frow);
@@ -474,6 +478,9 @@ int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags) {
     if (!b || !flags) return fail("null argument");
     DeviceGuard g(b->device);
     if (upload_rows(b->segblk, SB_ROWS, SB_FLAGS, flags, b->n_seg, b->n_seg, b->ntiles, 1)) return 1;
+    b->flags_word = flags[0];
+    b->flags_uniform = 1;
+    for (int64_t i = 1; i < b->n_seg && b->flags_uniform; ++i) b->flags_uniform = flags[i] == flags[0];
     b->have_flags = true;
     return 0;
 }

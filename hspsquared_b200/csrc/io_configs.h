@@ -77,6 +77,10 @@ static inline bool io_matches(const LandLaunch &L) {
     return true;
 }
 
+// option word of test10's PERLND 1 with SNOW + PWATER (ICEFG, CSNOFG, PWATER sees ICEFG; CEPSC, UZSN, NSUR, LZETP follow their
+// monthly tables; everything else off: energy-balance snow, Newton routing, UZINF1, IFFCFG 1, VLEFG 1)
+#define FLAGW_TEST10_P001 (FLAG(ICEFG) | FLAG(CSNOFG) | FLAG(PW_ICEFG) | FLAG(M_LZETP) | FLAG(M_CEPSC) | FLAG(M_NSUR) | FLAG(M_UZSN))
+
 // PQUAL / IQUAL rows with the inputs a land batch produces (+ PREC) and every output of the constituent
 #define FM_PQUAL7 ((1ull << F_SURO) | (1ull << F_IFWO) | (1ull << F_AGWO) | (1ull << F_PERO) | (1ull << F_WSSD) | \
                    (1ull << F_SCRSD) | (1ull << F_PREC))

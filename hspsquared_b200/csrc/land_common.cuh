@@ -92,6 +92,8 @@ struct LandLaunch {
     int mon_rows;     // 12 * number of monthly slots (row count of one tile's table block)
     unsigned act;
     unsigned opts;
+    int flags_uniform;              // 1: every segment of the batch carries the option word flags_word
+    unsigned long long flags_word;
     double delt, delt60;
     short frow[HSP2G_NFORC];    // forcing id -> row in forc, or -1
     double ffill[HSP2G_NFORC];  // value read when the id is absent
@@ -449,9 +451,23 @@ struct Sched {
 #define HSP_PIN(p) asm volatile("" : "+l"(p))
 #endif
 
-template <class IO_, unsigned long long HOT_, bool SHARED_ = false>
+// Option word of the batch: DynFlags reads each segment's 64-bit word from its segment block; StaticFlags<W> is for batches
+// whose segments all carry the word W (a replicated / calibration ensemble): every option test folds at compile time, the
+// sections a word switches off (degree-day snow, ARM routing, UZINF2, ...) vanish from the kernel.
+struct DynFlags {
+    static constexpr bool KNOWN = false;
+    static constexpr unsigned long long W = 0;
+};
+template <unsigned long long W_>
+struct StaticFlags {
+    static constexpr bool KNOWN = true;
+    static constexpr unsigned long long W = W_;
+};
+
+template <class IO_, unsigned long long HOT_, bool SHARED_ = false, class FW_ = DynFlags>
 struct Seg {
     typedef IO_ IO;
+    typedef FW_ FW;
     static constexpr bool SHARED = SHARED_;
     static constexpr unsigned long long HOT = HOT_;
     static constexpr int NHOT = ce_popc(HOT_);
@@ -511,7 +527,7 @@ struct Seg {
         else
             __stcs(reinterpret_cast<double *>(outp) + r * LAND_TILE, v);
     }
-    __device__ __forceinline__ bool flag(int bit) const { return (fl >> bit) & 1ull; }
+    __device__ __forceinline__ bool flag(int bit) const { return ((FW::KNOWN ? FW::W : fl) >> bit) & 1ull; }
     __device__ __forceinline__ double par(int id) const {
         if (id < 64 && ((HOT >> (id & 63)) & 1ull)) return hot[hsp_popc(HOT & ((1ull << (id & 63)) - 1ull)) * LAND_TILE];
         return __ldg(sb + (SB_PAR + id) * LAND_TILE);

@@ -10,10 +10,10 @@
 #define HSP_MAXREG_HOT 128  // register cap of the specialised kernels: 4 warps per SM sub-partition (16 per SM), no spills
 #endif
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false, class FW = DynFlags>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
     const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>(), SHARED);
-    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED>;
+    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, FW>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -34,6 +34,11 @@ cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
                       : launch_one<-1, false, DynIO, 232, true>(L, sub_pref, st, name, "perlnd_kernel<generic,subhourly,io=dynamic,met=shared>", grid_out);
     }
     if (L.act == (unsigned)SP && hourly) {
+#ifndef HSP_NO_STATIC_FLAGS
+        // a replicated ensemble: every segment carries test10 PERLND 1's option word (test10.uci:65-169)
+        if (L.flags_uniform && L.flags_word == FLAGW_TEST10_P001 && io_matches<IO_SnowPwaterDefault>(L))
+            return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT, false, StaticFlags<FLAGW_TEST10_P001>>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>", grid_out);
+#endif
         if (io_matches<IO_SnowPwaterDefault>(L))
             return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24>", grid_out);
         if (io_matches<IO_SnowPwaterDefaultF32>(L))

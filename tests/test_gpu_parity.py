@@ -167,7 +167,14 @@ def test_headline_static_kernels_are_selected():
     f = synth.forcing_chunk(ens, cal, 0, cal.steps)
     with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
         o64 = b.run(f)
+        # every segment carries test10 PERLND 1's option word: the kernel with the word fixed at compile time
+        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>"
+    st = ens.store(cal)
+    st.flags[-1] ^= np.uint64(1) << np.uint64(st.FB["IFRDFG"])  # one segment differs: run-time option words, same bits elsewhere
+    with LandBatch(st, cal, list(synth.PERLND_FORCINGS), save) as b:
+        omix = b.run(f)
         assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24>"
+    assert np.array_equal(omix[:, :, :-1], o64[:, :, :-1], equal_nan=True)
     with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
         b.set_output_dtype(np.float32)
         o32 = b.run(f)
