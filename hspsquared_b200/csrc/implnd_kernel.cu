@@ -3,10 +3,10 @@
 #include "land_kernels.cuh"
 #include "launch.h"
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false, class FW = DynFlags>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
     const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, IMPLND_HOT, implnd_ncold<HOURLY, IO>(), SHARED);
-    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED>;
+    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, FW>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -24,6 +24,9 @@ cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
     // test10's IMPLND chain: SNOW -> IWATER -> SOLIDS (-> IWTGAS); SaveTable.csv saves nothing of SOLIDS / IWTGAS by default
     constexpr int SIS = SI | (int)HSP2G_ACT_SOLIDS, SISG = SIS | (int)HSP2G_ACT_IWTGAS;
     if (hourly && io_matches<IO_SnowIwaterDefault>(L)) {
+        // a replicated ensemble of test10's IMPLND 1 (test10.uci:194-248): option word known at compile time
+        if (L.act == (unsigned)SI && L.flags_uniform && L.flags_word == FLAGW_TEST10_I001)
+            return launch_one<SI, true, IO_SnowIwaterDefault, 128, false, StaticFlags<FLAGW_TEST10_I001>>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16,options=test10-I001>", grid_out);
         if (L.act == (unsigned)SI)
             return launch_one<SI, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>", grid_out);
         if (L.act == (unsigned)SIS)

@@ -81,6 +81,9 @@ static inline bool io_matches(const LandLaunch &L) {
 // monthly tables; everything else off: energy-balance snow, Newton routing, UZINF1, IFFCFG 1, VLEFG 1)
 #define FLAGW_TEST10_P001 (FLAG(ICEFG) | FLAG(CSNOFG) | FLAG(PW_ICEFG) | FLAG(M_LZETP) | FLAG(M_CEPSC) | FLAG(M_NSUR) | FLAG(M_UZSN))
 
+// ... and of test10's IMPLND 1 with SNOW + IWATER (ICEFG, CSNOFG, RTLIFG; constant RETSC / NSUR, Newton routing)
+#define FLAGW_TEST10_I001 (FLAG(ICEFG) | FLAG(CSNOFG) | FLAG(RTLIFG))
+
 // PQUAL / IQUAL rows with the inputs a land batch produces (+ PREC) and every output of the constituent
 #define FM_PQUAL7 ((1ull << F_SURO) | (1ull << F_IFWO) | (1ull << F_AGWO) | (1ull << F_PERO) | (1ull << F_WSSD) | \
                    (1ull << F_SCRSD) | (1ull << F_PREC))

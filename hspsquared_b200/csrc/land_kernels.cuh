@@ -158,13 +158,13 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
     }
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED, class FW = DynFlags>
 __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(const __grid_constant__ LandLaunch L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, IMPLND_HOT, SHARED> SegT;
+    typedef Seg<IO, IMPLND_HOT, SHARED, FW> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS;
     PipeT<SHARED> pipe;
