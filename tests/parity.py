@@ -470,3 +470,60 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
             lib.hsp2g_device_free(0, C.c_void_p(p))
     assert np.array_equal(got, want, equal_nan=True)
     assert np.nanmax(want[:, q.save.index("PQUAL_SOQUAL"), :]) > 0
+
+
+def check_abi_errors_and_edges():
+    """Error behaviour of the C ABI (status + hsp2g_last_error, never a crash or a silent default) and the smallest shapes:
+    one segment, one interval, one interval per chunk, an empty SAVE set."""
+    import ctypes as C
+
+    lib = _lib.load()
+    h = _lib._h()
+
+    def err():
+        return lib.hsp2g_last_error().decode()
+
+    assert lib.hsp2g_batch_create(0, 7, 4, 6, 60.0, C.byref(h)) != 0 and "operation" in err()
+    assert lib.hsp2g_batch_create(0, 0, 0, 6, 60.0, C.byref(h)) != 0 and "n_seg" in err()
+    assert lib.hsp2g_batch_create(0, 0, 4, 6, 0.0, C.byref(h)) != 0 and "delt" in err()
+    assert lib.hsp2g_batch_create(0, 0, 4, 64, 60.0, C.byref(h)) != 0 and "activity mask" in err()  # IWATER on PERLND
+    assert lib.hsp2g_batch_create(0, 0, 4, 512 | 4, 60.0, C.byref(h)) != 0 and "PQUAL" in err()  # constituents + hydrology
+    assert lib.hsp2g_batch_create(0, 0, 4, 2, 720.0, C.byref(h)) != 0 and "ICEFLG" in err()  # SNOW.py:85
+    assert lib.hsp2g_batch_create(0, 0, 4, 6, 60.0, None) != 0
+    assert lib.hsp2g_batch_create(0, 0, 3, 6, 60.0, C.byref(h)) == 0 and h.value
+    out = np.zeros(3 * 24 * 2)
+    assert lib.hsp2g_run_host(h, 0, 1, out.ctypes.data, out.ctypes.data) != 0 and "hsp2g_set_params" in err()
+    assert lib.hsp2g_set_params(h, None, 3) != 0
+    assert lib.hsp2g_set_monthly(h, 999, out.ctypes.data_as(C.POINTER(C.c_double)), 3) != 0 and "out of range" in err()
+    assert lib.hsp2g_set_schedule(h, -1) != 0
+    assert lib.hsp2g_set_output_dtype(h, 5) != 0
+    bad = np.array([9999], dtype=np.int32)
+    assert lib.hsp2g_set_save(h, 1, bad.ctypes.data_as(C.POINTER(C.c_int32))) != 0
+    assert lib.hsp2g_batch_destroy(h) == 0
+    assert lib.hsp2g_run_host(None, 0, 1, None, None) != 0 and "null" in err()
+    # ---- smallest shapes against the oracle
+    case = dict(CASES.build_cases()["p001_snow_pwater"])
+    for steps, chunk in ((1, None), (2, 1), (25, 1)):
+        c = dict(case, steps=steps)
+        ref, _ = run_oracle(c)
+        got, _, _ = run_fused(c, chunk=chunk)
+        assert not compare(ref, got, exact=GPU_EXACT), (steps, chunk)
+    si = CASES.siminfo_for(dict(case, steps=30))
+    cal = Calendar(si["start"], si["stop"], 60, "us")
+    forc = {k: v[:30] for k, v in CASES.forcings(case).items()}
+    names = [n for n in forc if n in _lib.index("forcings")]
+    store = SegmentStore.from_tables("PERLND", [copy.deepcopy(case["tables"])], cal)
+    with LandBatch(store, cal, names, []) as b:  # nothing saved: the state still advances
+        o = b.run(pack_forcings(forc, names, 1), chunk=7)
+        assert o.shape == (30, 0, 1)
+        st_none = b.get_state()
+    with LandBatch(store, cal, names, "all") as b:
+        b.run(pack_forcings(forc, names, 1))
+        assert np.array_equal(b.get_state(), st_none, equal_nan=True)
+    with LandBatch(store, cal, names, "all") as b:
+        try:
+            b.run_host(25, np.zeros((1, 10, len(names), 32)))  # 25 + 10 > 30 intervals of calendar
+        except _lib.Hsp2gError as e:
+            assert "outside the calendar" in str(e)
+        else:
+            raise AssertionError("a chunk past the calendar was accepted")

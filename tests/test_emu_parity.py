@@ -103,3 +103,7 @@ def test_iwtgas_without_its_states_raises_like_the_reference():
 def test_constituents_fed_on_the_device(order):
     """Land batch -> device gather -> PQUAL rows without a host round trip == the host-side chain, bit for bit."""
     parity.check_qual_chain_on_device(order=order)
+
+
+def test_abi_error_behaviour_and_smallest_shapes():
+    parity.check_abi_errors_and_edges()

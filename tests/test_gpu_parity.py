@@ -325,6 +325,10 @@ def test_qual_rows_many_segments():
                     assert parity.rel_err(out[:, r, j], ts[key]) <= parity.RTOL, (i, key)
 
 
+def test_abi_error_behaviour_and_smallest_shapes():
+    parity.check_abi_errors_and_edges()
+
+
 def test_constituents_fed_on_the_device():
     """Land kernel -> gather kernel -> qual kernel with every buffer in HBM: same bits as the host-side chain (3,000 segments,
     divergence-ordered land batch)."""
