@@ -18,15 +18,14 @@ static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 
 cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SI = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_IWATER);
+    cudaError_t e_hot = cudaSuccess;
+    if (hsp2g_launch_implnd_hot(L, hourly, sub_pref, st, name, grid_out, &e_hot)) return e_hot;  // hot_kernels.cu
     if (L.met)
         return hourly ? launch_one<-1, true, DynIO, 128, true>(L, sub_pref, st, name, "implnd_kernel<generic,hourly,io=dynamic,met=shared>", grid_out)
                       : launch_one<-1, false, DynIO, 128, true>(L, sub_pref, st, name, "implnd_kernel<generic,subhourly,io=dynamic,met=shared>", grid_out);
     // test10's IMPLND chain: SNOW -> IWATER -> SOLIDS (-> IWTGAS); SaveTable.csv saves nothing of SOLIDS / IWTGAS by default
     constexpr int SIS = SI | (int)HSP2G_ACT_SOLIDS, SISG = SIS | (int)HSP2G_ACT_IWTGAS;
     if (hourly && io_matches<IO_SnowIwaterDefault>(L)) {
-        // a replicated ensemble of test10's IMPLND 1 (test10.uci:194-248): option word known at compile time
-        if (L.act == (unsigned)SI && L.flags_uniform && L.flags_word == FLAGW_TEST10_I001)
-            return launch_one<SI, true, IO_SnowIwaterDefault, 128, false, StaticFlags<FLAGW_TEST10_I001>>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16,options=test10-I001>", grid_out);
         if (L.act == (unsigned)SI)
             return launch_one<SI, true, IO_SnowIwaterDefault, 128>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16>", grid_out);
         if (L.act == (unsigned)SIS)

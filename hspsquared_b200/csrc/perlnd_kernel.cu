@@ -25,6 +25,8 @@ static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 
 cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SP = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_PWATER);
+    cudaError_t e_hot = cudaSuccess;
+    if (hsp2g_launch_perlnd_hot(L, hourly, sub_pref, st, name, grid_out, &e_hot)) return e_hot;  // hot_kernels.cu
     if (L.met) {  // shared-met mode: forcings gathered from the station table (hsp2g_set_shared_forcing)
         if (L.act == (unsigned)SP && hourly && io_matches<IO_SnowPwaterDefault>(L))
             return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT, true>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,met=shared>", grid_out);
@@ -34,11 +36,6 @@ cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaSt
                       : launch_one<-1, false, DynIO, 232, true>(L, sub_pref, st, name, "perlnd_kernel<generic,subhourly,io=dynamic,met=shared>", grid_out);
     }
     if (L.act == (unsigned)SP && hourly) {
-#ifndef HSP_NO_STATIC_FLAGS
-        // a replicated ensemble: every segment carries test10 PERLND 1's option word (test10.uci:65-169)
-        if (L.flags_uniform && L.flags_word == FLAGW_TEST10_P001 && io_matches<IO_SnowPwaterDefault>(L))
-            return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT, false, StaticFlags<FLAGW_TEST10_P001>>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>", grid_out);
-#endif
         if (io_matches<IO_SnowPwaterDefault>(L))
             return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24>", grid_out);
         if (io_matches<IO_SnowPwaterDefaultF32>(L))
