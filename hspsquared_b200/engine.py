@@ -300,7 +300,13 @@ class QualBatch(LandBatch):
     met / lateral inputs -- over the rows, `run()` then works as for any batch.  Output row j belongs to `self.rows[j]` =
     (segment index, constituent number); in the reference's ts that series is '<P|I>QUAL<k>_<NAME>'."""
 
-    def __init__(self, operation, uci_list, calendar, forcing_names, save="all", device=0, timing=False):
+    def __init__(self, operation, uci_list, calendar, forcing_names, save="all", device=0, timing=False, order="flags",
+                 land=None):
+        """order="flags" (default) puts rows with equal option words next to each other on the device: the constituents of a
+        segment differ in kind (sediment-associated, overland-flow-associated, subsurface concentrations ...), segment-major rows
+        would make every warp execute every kind.  Invisible to run() / gather(); run_device buffers are in device order.
+        land: the LandBatch whose device buffers will feed this batch (attach() is called): within equal option words the rows
+        then follow the land batch's device order, so that 32 consecutive rows gather 32 consecutive cells of a land tile."""
         from .qualstore import qual_store
 
         store = qual_store(operation, uci_list, calendar)
@@ -309,7 +315,12 @@ class QualBatch(LandBatch):
                                       "activities, which feed every row its own column")
         self.rows = store.rows
         self.row_segment = np.array([i for i, _k in store.rows], dtype=np.int64)
-        super().__init__(store, calendar, forcing_names, save, device=device, timing=timing)
+        if land is not None and isinstance(order, str) and order == "flags":
+            pos = self.row_segment if land._inv is None else np.asarray(land._inv)[self.row_segment]
+            order = store.divergence_order(keys=(pos,))
+        super().__init__(store, calendar, forcing_names, save, device=device, timing=timing, order=order)
+        if land is not None:
+            self.attach(land)
 
     def gather(self, series):
         """{name: [steps][n_segments] or [steps]} -> forcing [steps][nf][rows] in `forcing_names` order."""
@@ -330,7 +341,8 @@ class QualBatch(LandBatch):
         land's output rows (it must be in land's SAVE set, float64), anything else from land's forcing rows."""
         if land.out_dtype != np.float64:
             raise ValueError("the land batch must write float64 outputs to feed constituents")
-        seg = self.row_segment if land._inv is None else np.asarray(land._inv)[self.row_segment]
+        rows = self.row_segment if self.order is None else self.row_segment[self.order]  # device row -> caller's segment
+        seg = rows if land._inv is None else np.asarray(land._inv)[rows]  # -> the land batch's device position
         seg = np.ascontiguousarray(seg, dtype=np.int64)
         self._gather = _lib._h()
         _lib.check(self.lib.hsp2g_gather_create(self.device, land.npad, self.n, _ptr(seg, C.POINTER(C.c_int64)),

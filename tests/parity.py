@@ -439,8 +439,8 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
     with QualBatch("PERLND", ucis, cal, qn, "all") as q:
         want = q.run(q.gather(series), chunk=chunk)
     # device-resident chain
-    with LandBatch(ens.store(cal), cal, names, need, order=order) as land, QualBatch("PERLND", ucis, cal, qn, "all") as q:
-        q.attach(land)
+    with LandBatch(ens.store(cal), cal, names, need, order=order) as land, \
+            QualBatch("PERLND", ucis, cal, qn, "all", land=land) as q:
         got = np.empty_like(want)
         dev = []
 
@@ -465,7 +465,8 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
             q.sync()
             ho = np.empty((q.ntiles, m, q.ns, 32))
             _lib.check(lib.hsp2g_memcpy_d2h(0, ho.ctypes.data, d_qo, ho.nbytes))
-            got[t0:t0 + m] = untile_series(ho, q.n)[:, q._sinv, :]
+            u = untile_series(ho, q.n)[:, q._sinv, :]  # device row order -> the caller's
+            got[t0:t0 + m] = u if q._inv is None else u[:, :, q._inv]
         for p in dev:
             lib.hsp2g_device_free(0, C.c_void_p(p))
     assert np.array_equal(got, want, equal_nan=True)

@@ -94,8 +94,7 @@ def run_chain(name, torch, dev):
     need = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "PWATER_PERO", "SEDMNT_WSSD", "SEDMNT_SCRSD"]
     qt = test10.pqual_tables()
     with LandBatch(ens.store(cal), cal, forcings, need, device=dev.index or 0, order="flags") as land, \
-            QualBatch("PERLND", [qt] * n, cal, list(PQUAL_INPUTS[:7]), "all", device=dev.index or 0) as q:
-        q.attach(land)
+            QualBatch("PERLND", [qt] * n, cal, list(PQUAL_INPUTS[:7]), "all", device=dev.index or 0, land=land) as q:
         ens2 = ens.take(land.order)  # forcings generated in the land batch's device order
         forc = [bench.device_forcing(torch, ens2, cal, c * Tc, Tc, land.npad, dev, land.forcing_rows) for c in range(K + W)]
         lo = torch.empty((land.npad // 32, Tc, land.ns, 32), dtype=torch.float64, device=dev)
