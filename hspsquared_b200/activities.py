@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from .calendar import SEASONS, Calendar
-from .engine import ERRORS_OF, LandBatch, output_names, pack_forcings
+from .engine import LandBatch, output_names, pack_forcings
 from .segstore import SegmentStore
 
 ERRMSGS = {

@@ -23,7 +23,6 @@ import math
 import numpy as np
 
 from . import _lib
-from .test10 import MONTHS
 
 NAN = float("nan")
 

@@ -109,8 +109,6 @@ def _patch_pandas3(mods):
 # ------------------------------------------------------------------------------------------------
 def read_wdm(wdmfile):
     """Returns {dsn: pandas.Series(float64, DatetimeIndex with freq)} for every timeseries dataset."""
-    import datetime
-
     import numpy as np
     import pandas as pd
 

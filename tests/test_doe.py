@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 
 from hspsquared_b200 import doe as DOE
-from hspsquared_b200 import test10
 from oracle import cases as CASES
 
 from . import parity

@@ -1,11 +1,10 @@
 """Synthetic ensembles: the vectorised segment store equals the per-segment table path, and a jittered
 ensemble run through the (test-double) library matches the CPU oracle segment by segment."""
-import copy
 
 import numpy as np
 import pytest
 
-from hspsquared_b200 import _lib, synth
+from hspsquared_b200 import synth
 from hspsquared_b200.calendar import Calendar
 from hspsquared_b200.engine import LandBatch
 from hspsquared_b200.segstore import SegmentStore
