@@ -12,10 +12,10 @@
 #define HSP_MAXREG_HOT 128
 #endif
 
-template <int ACT_CT, class IO, class FW>
+template <int ACT_CT, class IO, class FW, int MAXREG = HSP_MAXREG_HOT>
 static cudaError_t launch_hot(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
     const size_t smem = land_smem_bytes(IO::NF, perlnd_hot(ACT_CT), perlnd_ncold<true, IO, ACT_CT>(), false);
-    auto k = perlnd_kernel<ACT_CT, true, IO, HSP_MAXREG_HOT, false, FW>;
+    auto k = perlnd_kernel<ACT_CT, true, IO, MAXREG, false, FW>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -30,12 +30,17 @@ bool hsp2g_launch_perlnd_hot(LandLaunch &L, bool hourly, int sub_pref, cudaStrea
     constexpr int SP = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_PWATER);
     if (L.met || !hourly || L.act != (unsigned)SP || !L.flags_uniform) return false;
     // a replicated ensemble: every segment carries test10 PERLND 1's option word (test10.uci:65-169)
-    if (L.flags_word == FLAGW_TEST10_P001 && io_matches<IO_SnowPwaterDefault>(L)) {
-        *err = launch_hot<SP, IO_SnowPwaterDefault, StaticFlags<FLAGW_TEST10_P001>>(
-            L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>", grid_out);
-        return true;
-    }
-    return false;
+    if (L.flags_word != FLAGW_TEST10_P001) return false;
+    typedef StaticFlags<FLAGW_TEST10_P001> FW;
+    if (io_matches<IO_SnowPwaterDefault>(L))
+        *err = launch_hot<SP, IO_SnowPwaterDefault, FW>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>", grid_out);
+    else if (io_matches<IO_SnowPwaterFlows>(L))
+        *err = launch_hot<SP, IO_SnowPwaterFlows, FW>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=flows3,options=test10-P001>", grid_out);
+    else if (io_matches<IO_SnowPwaterAll>(L))
+        *err = launch_hot<SP, IO_SnowPwaterAll, FW, 168>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=all53,options=test10-P001>", grid_out);
+    else
+        return false;
+    return true;
 }
 
 template <int ACT_CT, class IO, class FW>
