@@ -17,11 +17,15 @@ struct QualState {
     double sqo, soqsp;  // carried: surface storage; IQUAL's last computed washoff potency
     // the constituent's parameters for the current day (monthly tables are interpolated to the day, constant within it)
     double wsfac, potfw, potfs, acqop, remqop, ioqc, aoqc, adfx, adcn;
+    double slifac, ilifac, alifac;  // lateral-inflow weights: constant, read once per task instead of once per interval
     template <class SEG>
     __device__ __forceinline__ void load(const SEG &s) {
         sqo = s.st(S_Q_SQO);
         soqsp = s.st(S_Q_SOQSP);
         wsfac = s.par(P_Q_WSFAC);
+        slifac = s.par(P_SLIFAC);
+        ilifac = s.par(P_ILIFAC);
+        alifac = s.par(P_ALIFAC);
     }
     template <class SEG>
     __device__ __forceinline__ void store(const SEG &s) const {
@@ -49,7 +53,7 @@ __device__ __forceinline__ void pqual_step(const SEG &s, QualState &w) {
     double suroqs = 0.0, soqsp = -1.0e30, scrqs = 0.0, washqs = 0.0, soqs = 0.0;
     if (s.flag(FB_Q_QSDFG)) {  // qualsd, PQUAL.py:250-276
         const double wssd = s.forcing(F_WSSD), scrsd = s.forcing(F_SCRSD), sliqsp = s.forcing(F_SLIQSP);
-        const double slifac = s.par(P_SLIFAC);
+        const double slifac = w.slifac;
         if (wssd == 0.0)
             washqs = 0.0;
         else if (sliqsp >= 0.0)
@@ -93,7 +97,7 @@ __device__ __forceinline__ void pqual_step(const SEG &s, QualState &w) {
         double ioqc = w.ioqc * 3630.0;
         if (s.flag(FB_Q_VIQC34)) ioqc = ioqc * 6.238e-5;
         if (ifwo > 0.0) {
-            const double iliqc = s.forcing(F_ILIQC), ilifac = s.par(P_ILIFAC);
+            const double iliqc = s.forcing(F_ILIQC), ilifac = w.ilifac;
             const double ioqce = iliqc >= 0.0 ? iliqc * ilifac + ioqc * (1.0 - ilifac) : ioqc;
             ioqual = ioqce * ifwo;
         }
@@ -103,7 +107,7 @@ __device__ __forceinline__ void pqual_step(const SEG &s, QualState &w) {
         double aoqc = w.aoqc * 3630.0;
         if (s.flag(FB_Q_VAQC34)) aoqc = aoqc * 6.238e-5;
         if (agwo > 0.0) {
-            const double aliqc = s.forcing(F_ALIQC), alifac = s.par(P_ALIFAC);
+            const double aliqc = s.forcing(F_ALIQC), alifac = w.alifac;
             const double aoqce = aliqc >= 0.0 ? aliqc * alifac + aoqc * (1.0 - alifac) : aoqc;
             aoqual = aoqce * agwo;
         }
@@ -143,7 +147,7 @@ __device__ __forceinline__ void iqual_step(const SEG &s, QualState &w) {
         if (sosld != 0.0) {
             const double sliqsp = s.forcing(F_SLIQSP);
             if (sliqsp >= 0.0) {
-                const double slifac = s.par(P_SLIFAC);
+                const double slifac = w.slifac;
                 w.soqsp = sliqsp * slifac + w.potfw * (1.0 - slifac);
                 soqs = sosld * w.soqsp;
             } else {
