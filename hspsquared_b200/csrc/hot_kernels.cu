@@ -12,10 +12,10 @@
 #define HSP_MAXREG_HOT 128
 #endif
 
-template <int ACT_CT, class IO, class FW, int MAXREG = HSP_MAXREG_HOT>
+template <int ACT_CT, class IO, class FW, int MAXREG = HSP_MAXREG_HOT, bool SHARED = false>
 static cudaError_t launch_hot(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::NF, perlnd_hot(ACT_CT), perlnd_ncold<true, IO, ACT_CT>(), false);
-    auto k = perlnd_kernel<ACT_CT, true, IO, MAXREG, false, FW>;
+    const size_t smem = land_smem_bytes(IO::NF, perlnd_hot(ACT_CT), perlnd_ncold<true, IO, ACT_CT>(), SHARED);
+    auto k = perlnd_kernel<ACT_CT, true, IO, MAXREG, SHARED, FW>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -28,10 +28,15 @@ static cudaError_t launch_hot(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 // true when a specialised kernel exists for this launch (and was launched; *err holds the result)
 bool hsp2g_launch_perlnd_hot(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out, cudaError_t *err) {
     constexpr int SP = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_PWATER);
-    if (L.met || !hourly || L.act != (unsigned)SP || !L.flags_uniform) return false;
+    if (!hourly || L.act != (unsigned)SP || !L.flags_uniform) return false;
     // a replicated ensemble: every segment carries test10 PERLND 1's option word (test10.uci:65-169)
     if (L.flags_word != FLAGW_TEST10_P001) return false;
     typedef StaticFlags<FLAGW_TEST10_P001> FW;
+    if (L.met) {  // shared-met mode (hsp2g_set_shared_forcing)
+        if (!io_matches<IO_SnowPwaterDefault>(L)) return false;
+        *err = launch_hot<SP, IO_SnowPwaterDefault, FW, HSP_MAXREG_HOT, true>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,met=shared,options=test10-P001>", grid_out);
+        return true;
+    }
     if (io_matches<IO_SnowPwaterDefault>(L))
         *err = launch_hot<SP, IO_SnowPwaterDefault, FW>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>", grid_out);
     else if (io_matches<IO_SnowPwaterFlows>(L))
