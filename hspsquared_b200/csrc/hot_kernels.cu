@@ -63,12 +63,18 @@ static cudaError_t launch_hot_implnd(LandLaunch &L, int sub_pref, cudaStream_t s
 
 bool hsp2g_launch_implnd_hot(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out, cudaError_t *err) {
     constexpr int SI = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_IWATER);
-    if (L.met || !hourly || L.act != (unsigned)SI || !L.flags_uniform) return false;
-    // a replicated ensemble of test10's IMPLND 1 (test10.uci:194-248)
-    if (L.flags_word == FLAGW_TEST10_I001 && io_matches<IO_SnowIwaterDefault>(L)) {
-        *err = launch_hot_implnd<SI, IO_SnowIwaterDefault, StaticFlags<FLAGW_TEST10_I001>>(
-            L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16,options=test10-I001>", grid_out);
-        return true;
-    }
-    return false;
+    constexpr int SIS = SI | (int)HSP2G_ACT_SOLIDS, SISG = SIS | (int)HSP2G_ACT_IWTGAS;
+    if (L.met || !hourly || !L.flags_uniform) return false;
+    // a replicated ensemble of test10's IMPLND 1 (test10.uci:194-248), with or without its SOLIDS / IWTGAS sections
+    if (L.flags_word != FLAGW_TEST10_I001 || !io_matches<IO_SnowIwaterDefault>(L)) return false;
+    typedef StaticFlags<FLAGW_TEST10_I001> FW;
+    if (L.act == (unsigned)SI)
+        *err = launch_hot_implnd<SI, IO_SnowIwaterDefault, FW>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER,hourly,save=default16,options=test10-I001>", grid_out);
+    else if (L.act == (unsigned)SIS)
+        *err = launch_hot_implnd<SIS, IO_SnowIwaterDefault, FW>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER|SOLIDS,hourly,save=default16,options=test10-I001>", grid_out);
+    else if (L.act == (unsigned)SISG)
+        *err = launch_hot_implnd<SISG, IO_SnowIwaterDefault, FW>(L, sub_pref, st, name, "implnd_kernel<SNOW|IWATER|SOLIDS|IWTGAS,hourly,save=default16,options=test10-I001>", grid_out);
+    else
+        return false;
+    return true;
 }

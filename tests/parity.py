@@ -528,3 +528,33 @@ def check_abi_errors_and_edges():
             assert "outside the calendar" in str(e)
         else:
             raise AssertionError("a chunk past the calendar was accepted")
+
+
+def check_option_word_kernels():
+    """Kernels instantiated on a batch-wide option word (csrc/hot_kernels.cu) against the same batch with one segment's word
+    changed (run-time option tests, the general kernels): every other segment must come out bit for bit the same, outputs and
+    state, for each SAVE configuration that has such a kernel."""
+    cal = Calendar("1976-01-20", "1976-03-05", 60, "us")
+    pd_ = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + k for k in test10.SAVE_DEFAULT["PWATER"]]
+    id_ = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["IWATER_" + k for k in test10.SAVE_DEFAULT["IWATER"]]
+    jobs = [("PERLND", ("SNOW", "PWATER"), pd_, "IFRDFG", "save=default24,options=test10-P001"),
+            ("PERLND", ("SNOW", "PWATER"), "all", "IFRDFG", "save=all53,options=test10-P001"),
+            ("PERLND", ("SNOW", "PWATER"), ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO"], "IFRDFG", "save=flows3,options=test10-P001"),
+            ("IMPLND", ("SNOW", "IWATER"), id_, "RTOP1", "save=default16,options=test10-I001"),
+            ("IMPLND", ("SNOW", "IWATER", "SOLIDS"), id_, "RTOP1", "SOLIDS,hourly,save=default16,options=test10-I001")]
+    for op, secs, save, bit, tag in jobs:
+        ens = synth.Ensemble(op, 70, seed=9, sections=secs)
+        names = list(synth.PERLND_FORCINGS)
+        f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
+        with LandBatch(ens.store(cal), cal, names, save) as b:
+            a = b.run(f, chunk=400)
+            assert tag in b.kernel_name(), b.kernel_name()
+            sa = b.get_state()
+        st = ens.store(cal)
+        st.flags[-1] ^= np.uint64(1) << np.uint64(st.FB[bit])
+        with LandBatch(st, cal, names, save) as b:
+            g = b.run(f, chunk=400)
+            assert "options=" not in b.kernel_name()
+            sg = b.get_state()
+        assert np.array_equal(a[:, :, :-1], g[:, :, :-1], equal_nan=True), tag
+        assert np.array_equal(sa[:, :-1], sg[:, :-1], equal_nan=True), tag

@@ -107,3 +107,7 @@ def test_constituents_fed_on_the_device(order):
 
 def test_abi_error_behaviour_and_smallest_shapes():
     parity.check_abi_errors_and_edges()
+
+
+def test_option_word_kernels_equal_the_general_ones():
+    parity.check_option_word_kernels()

@@ -325,6 +325,10 @@ def test_qual_rows_many_segments():
                     assert parity.rel_err(out[:, r, j], ts[key]) <= parity.RTOL, (i, key)
 
 
+def test_option_word_kernels_equal_the_general_ones():
+    parity.check_option_word_kernels()
+
+
 def test_abi_error_behaviour_and_smallest_shapes():
     parity.check_abi_errors_and_edges()
 
