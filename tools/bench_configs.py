@@ -144,6 +144,9 @@ def run(name, torch, dev):
     cal = Calendar(bench.RUN_START, bench.RUN_STOP, 60, "ns")
     K, W, Tc = 8, 3, 256
     note = ""
+    year = name.endswith("_year")  # 20 timed steps x 438 intervals = one simulated year, like bench.py
+    if year:
+        name = name[:-5]
     if name == "implnd":  # IMPLND SNOW+IWATER, default SAVE (13 + 3)
         n = 100_000
         ens = synth.Ensemble("IMPLND", n, seed=1234, sections=("SNOW", "IWATER"))
@@ -176,6 +179,9 @@ def run(name, torch, dev):
         forcings, save = list(synth.PERLND_FORCINGS), "all"
     else:
         raise SystemExit("unknown config %r" % name)
+    if year:
+        K, Tc = 20, 438
+        note = (note + "; " if note else "") + "one simulated year (20 x 438 intervals)"
     store = ens.store(cal)
     perm = None
     if name == "fullchain_sorted":
