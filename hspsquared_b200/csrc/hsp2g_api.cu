@@ -301,6 +301,63 @@ __global__ void __launch_bounds__(128) gather_kernel(const __grid_constant__ Gat
 }
 #endif
 
+// ---- period aggregation of saved float32 series (hsp2g_aggregate_f32): what IOManager.write_ts does with pandas for
+// outstep 3 / 4 / 5 (hsp2io/io.py:74-94: resample(...).last() / .sum() / .mean() of the float32 frame).  pandas' group_sum /
+// group_mean run a compensated (Kahan) sum IN float32 over the non-NaN values in arrival order, group_last takes the last non-NaN
+// value; the same recurrences here, one thread per (tile, row, lane) walking the chunk's intervals.  bin[t] (which period an
+// interval belongs to) comes from the host, which asks pandas itself for the binning.
+struct AggArgs {
+    const float *src;
+    float *dst;
+    const int *bin;
+    long long n_threads;  // ntiles * ns * 32
+    int nsteps, ns, nbins;
+};
+__host__ __device__ inline void agg_flush(float *d, float last, float sum, int cnt) {
+    const float nanf_ = __builtin_nanf("");
+    d[0 * LAND_TILE] = last;
+    d[1 * LAND_TILE] = sum;                               // min_count = 0: an all-NaN period sums to 0
+    d[2 * LAND_TILE] = cnt ? sum / (float)cnt : nanf_;   // mean = compensated sum / count, in float32
+}
+__host__ __device__ inline void agg_thread(const AggArgs &A, long long j) {
+    const int lane = (int)(j % LAND_TILE);
+    const long long tr = j / LAND_TILE;
+    const int r = (int)(tr % A.ns);
+    const long long tile = tr / A.ns;
+    const float *s = A.src + (((size_t)tile * A.nsteps) * A.ns + r) * LAND_TILE + lane;
+    float *d = A.dst + ((((size_t)tile * A.nbins) * A.ns + r) * 3) * LAND_TILE + lane;
+    const float nanf_ = __builtin_nanf("");
+    float sum = 0.f, comp = 0.f, last = nanf_;
+    int cnt = 0, cur = A.bin[0];
+    for (int b = 0; b < cur; ++b) agg_flush(d + (size_t)b * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);  // leading empty periods
+    for (int t = 0; t < A.nsteps; ++t) {
+        const int b = A.bin[t];
+        if (b != cur) {
+            agg_flush(d + (size_t)cur * A.ns * 3 * LAND_TILE, last, sum, cnt);
+            for (int e = cur + 1; e < b; ++e) agg_flush(d + (size_t)e * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);
+            sum = 0.f, comp = 0.f, last = nanf_, cnt = 0, cur = b;
+        }
+        const float v = s[(size_t)t * A.ns * LAND_TILE];
+        if (v == v) {  // skipna
+            ++cnt;
+            last = v;
+            const float y = v - comp;
+            const float tt = sum + y;
+            comp = (tt - sum) - y;
+            if (comp != comp) comp = 0.f;  // pandas resets the compensation after an inf
+            sum = tt;
+        }
+    }
+    agg_flush(d + (size_t)cur * A.ns * 3 * LAND_TILE, last, sum, cnt);
+    for (int e = cur + 1; e < A.nbins; ++e) agg_flush(d + (size_t)e * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);
+}
+#ifndef HSP2G_HOST_EMU
+__global__ void __launch_bounds__(128) aggregate_kernel(const __grid_constant__ AggArgs A) {
+    const long long j = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (j < A.n_threads) agg_thread(A, j);
+}
+#endif
+
 // Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
 // forcing rows are present); the resident-block count sizes the persistent grid.
 cudaError_t hsp2g_prepare_kernel(const void *kernel, size_t smem_bytes, int block, int *resident) {
@@ -826,6 +883,41 @@ int hsp2g_gather_run(hsp2g_gather *h, const double *d_src, int32_t src_rows, dou
     gather_kernel<<<(unsigned)((A.n_dst_pad + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("gather launch failed: %s", cudaGetErrorString(e));
+    return 0;
+#endif
+}
+
+int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t nsteps, int32_t ns, const int32_t *bin_of_step,
+                        int32_t nbins, float *d_dst, void *stream) {
+    if (!d_src || !d_dst || !bin_of_step) return fail("null argument");
+    if (ntiles <= 0 || nsteps <= 0 || ns <= 0 || nbins <= 0) return fail("bad aggregation shape");
+    for (int t = 0; t < nsteps; ++t)
+        if (bin_of_step[t] < 0 || bin_of_step[t] >= nbins || (t && bin_of_step[t] < bin_of_step[t - 1]))
+            return fail("bin_of_step must be non-decreasing within [0, nbins)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail("cudaSetDevice(%d) failed", device);
+    AggArgs A;
+    A.src = d_src;
+    A.dst = d_dst;
+    A.n_threads = (long long)ntiles * ns * LAND_TILE;
+    A.nsteps = nsteps;
+    A.ns = ns;
+    A.nbins = nbins;
+#ifdef HSP2G_HOST_EMU
+    (void)stream;
+    A.bin = bin_of_step;
+    for (long long j = 0; j < A.n_threads; ++j) agg_thread(A, j);
+    return 0;
+#else
+    int *d_bin = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMallocAsync((void **)&d_bin, (size_t)nsteps * sizeof(int), st));
+    CU(cudaMemcpyAsync(d_bin, bin_of_step, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
+    A.bin = d_bin;
+    aggregate_kernel<<<(unsigned)((A.n_threads + 127) / 128), 128, 0, st>>>(A);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_bin, st);
+    if (e != cudaSuccess) return fail("aggregate launch failed: %s", cudaGetErrorString(e));
     return 0;
 #endif
 }

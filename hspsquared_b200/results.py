@@ -102,3 +102,76 @@ def save_qual_batch(io_manager, siminfo, operation, segment_names, save_tables, 
         save_columns = list(df.columns) if saveall else [k for k, v in savedict.items() if v or saveall]
         io_manager.write_ts(data_frame=df, save_columns=save_columns, category=category, operation=operation, segment=seg,
                             activity=act, compress=compress, outstep=outstep)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# outstep 3 / 4 / 5: the period statistics IOManager.write_ts computes with pandas (hsp2io/io.py:74-94), on the device
+# ---------------------------------------------------------------------------------------------------------------------------
+OUTSTEP_FREQ = {3: "D", 4: "ME", 5: "YE"}  # io.py:76,83,90 ('M' and 'Y' in the pandas the reference was written for)
+
+
+def period_bins(tindex, outstep):
+    """-> (bin_of_step int32[len(tindex)], labels): which period of `tindex.resample(freq)` every interval falls in, asked of
+    pandas itself so that the binning (calendar days of the interval-END labels, month-end bins closed on the right ...) is
+    the reference's by construction."""
+    import pandas as pd
+
+    sizes = pd.Series(np.zeros(len(tindex), dtype=np.int8), index=tindex).resample(OUTSTEP_FREQ[outstep]).size()
+    return np.repeat(np.arange(len(sizes), dtype=np.int32), sizes.to_numpy()), sizes.index
+
+
+def aggregate_host_series(out32, bin_of_step, nbins, device=0):
+    """[steps][rows][n] float32 -> [nbins][rows][3 = last, sum, mean][n] float32 through hsp2g_aggregate_f32 (upload, one launch,
+    download): the device-resident entry point is what a streaming run calls on its output slot before the copy-out, which then
+    moves 3 / (intervals per period) of the bytes."""
+    import ctypes as C
+
+    from . import _lib
+    from .engine import tile_series
+
+    lib = _lib.load()
+    out32 = np.asarray(out32)
+    if out32.dtype != np.float32:
+        raise ValueError("period statistics are defined on the float32 frames save_timeseries builds")
+    steps, rows, n = out32.shape
+    t = np.ascontiguousarray(tile_series(out32.astype(np.float64)).astype(np.float32))  # [tiles][steps][rows][32]
+    ntiles = t.shape[0]
+    res = np.empty((ntiles, nbins, rows, 3, 32), dtype=np.float32)
+    d_src, d_dst = lib.hsp2g_device_alloc(device, t.nbytes), lib.hsp2g_device_alloc(device, res.nbytes)
+    if not d_src or not d_dst:
+        raise MemoryError(lib.hsp2g_last_error().decode())
+    try:
+        _lib.check(lib.hsp2g_memcpy_h2d(device, d_src, t.ctypes.data, t.nbytes))
+        b = np.ascontiguousarray(bin_of_step, dtype=np.int32)
+        _lib.check(lib.hsp2g_aggregate_f32(device, d_src, ntiles, steps, rows, b.ctypes.data_as(C.POINTER(C.c_int32)), int(nbins),
+                                           d_dst, None))
+        _lib.check(lib.hsp2g_memcpy_d2h(device, res.ctypes.data, d_dst, res.nbytes))  # synchronous: orders after the launch
+    finally:
+        lib.hsp2g_device_free(device, C.c_void_p(d_src))
+        lib.hsp2g_device_free(device, C.c_void_p(d_dst))
+    return np.ascontiguousarray(res.transpose(1, 2, 3, 0, 4).reshape(nbins, rows, 3, ntiles * 32)[:, :, :, :n])
+
+
+def save_batch_aggregated(backend, labels, operation, segment_names, save_tables, saved_rows, agg, saveall=False, category=None):
+    """Hand an output BACKEND (hsp2io's SupportsWriteTS below IOManager: write_ts(data_frame, category, operation, segment,
+    activity), io.py:95) the frames IOManager.write_ts builds for outstep 3 / 4 / 5: the saved columns with the suffixes
+    _last, _sum, _aver, in that block order (io.py:79-81).  agg: [nbins][len(saved_rows)][3][n] from aggregate_host_series."""
+    import pandas as pd
+
+    category = result_category() if category is None else category
+    rows_of = {}
+    for r, full in enumerate(saved_rows):
+        act, name = full.split("_", 1)
+        rows_of.setdefault(act, {})[name] = r
+    for i, seg in enumerate(segment_names):
+        tabs = save_tables[i] if isinstance(save_tables, (list, tuple)) else save_tables
+        for act, savedict in tabs.items():
+            have = rows_of.get(act, {})
+            cols = sorted(k for k in savedict if k in have and (saveall or savedict[k]))  # io.py:70-72 drops the rest first
+            if not cols:
+                continue
+            blocks, names = [], []
+            for stat, suffix in ((0, "_last"), (1, "_sum"), (2, "_aver")):
+                blocks += [agg[:, have[k], stat, i] for k in cols]
+                names += [k + suffix for k in cols]
+            backend.write_ts(pd.DataFrame(np.stack(blocks, axis=1), index=labels, columns=names), category, operation, seg, act)

@@ -133,6 +133,15 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
 int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, double *h_out);
 /* Host-side re-tiling between [interval][row][ld] and [tile][interval][row][32] (what get_timeseries /
  * save_timeseries hand over per segment, utilities.py:274-333, for a whole batch). */
+/* Period aggregation of saved float32 series on the device: what IOManager.write_ts computes with pandas for outstep 3 / 4 / 5
+ * (hsp2io/io.py:74-94: last, sum and mean per day / month / year of the float32 frame save_timeseries hands it).
+ * d_src [tile][nsteps][ns][32] float32 (hsp2g_set_output_dtype(HSP2G_F32)); bin_of_step[t] = period of interval t (host array,
+ * non-decreasing, < nbins; the host takes it from pandas so that the binning is the reference's); d_dst
+ * [tile][nbins][ns][3][32] float32 with the three statistics in the order last, sum, mean.  Sums are pandas' compensated
+ * float32 sums over the non-NaN values; an all-NaN period gives last = NaN, sum = 0, mean = NaN. */
+int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t nsteps, int32_t ns, const int32_t *bin_of_step,
+                        int32_t nbins, float *d_dst, void *stream);
+
 /* The stream hsp2g_run_device uses when it is given none (non-blocking; nothing orders it against other streams): pass it to
  * hsp2g_gather_run, or to another batch's hsp2g_run_device, to chain work on the device in order. */
 void *hsp2g_batch_stream(hsp2g_batch *b);

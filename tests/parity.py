@@ -3,6 +3,7 @@
 by the `-m gpu` suite (against the CUDA library through the C ABI, <= 1e-9 relative, integers exact)."""
 import copy
 import os
+import warnings
 
 import numpy as np
 
@@ -558,3 +559,52 @@ def check_option_word_kernels():
             sg = b.get_state()
         assert np.array_equal(a[:, :, :-1], g[:, :, :-1], equal_nan=True), tag
         assert np.array_equal(sa[:, :-1], sg[:, :-1], equal_nan=True), tag
+
+
+def check_period_aggregation(n=40, days=75):
+    """hsp2g_aggregate_f32 against pandas on the float32 frames (what IOManager.write_ts does for outstep 3 / 4 / 5,
+    hsp2io/io.py:74-94): last / sum / mean per day, month and year, NaN series included, bit for bit."""
+    import pandas as pd
+
+    from hspsquared_b200.results import aggregate_host_series, period_bins, save_batch_aggregated
+
+    start = np.datetime64("1976-01-20T00:00:00")
+    cal = Calendar(start, start + np.timedelta64(days, "D"), 60, "us")
+    ens = synth.Ensemble("PERLND", n, seed=4, sections=("SNOW", "PWATER"))
+    names = list(synth.PERLND_FORCINGS)
+    with LandBatch(ens.store(cal), cal, names, "all") as b:
+        b.set_output_dtype(np.float32)
+        out = b.run(synth.forcing_chunk(ens, cal, 0, cal.steps, names=names), chunk=600)
+        saved = b.save
+    tindex = pd.date_range(pd.Timestamp(str(start)), periods=cal.steps + 1, freq="60min")[1:]
+    assert np.isnan(out[:, saved.index("SNOW_RDENPF")]).any()  # a series with NaN stretches (no pack)
+    for outstep in (3, 4, 5):
+        bins, labels = period_bins(tindex, outstep)
+        agg = aggregate_host_series(out, bins, len(labels))
+        for i in (0, n // 2, n - 1):
+            df = pd.DataFrame(out[:, :, i], index=tindex, columns=[s.split("_", 1)[1] + "." + s.split("_", 1)[0] for s in saved])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # pandas 3: origin= has no effect for calendar frequencies (it says so)
+                r = df.resample({3: "D", 4: "ME", 5: "YE"}[outstep], origin="start")
+            for stat, want in enumerate((r.last(), r.sum(), r.mean())):
+                assert want.index.equals(labels)
+                w = want.to_numpy()
+                assert w.dtype == np.float32
+                assert np.array_equal(agg[:, :, stat, i], w, equal_nan=True), (outstep, stat, i)
+    # frame layout of the merged result (io.py:79-81)
+    sink = FrameSinkBackend()
+    bins, labels = period_bins(tindex, 3)
+    agg = aggregate_host_series(out, bins, len(labels))
+    tabs = {"SNOW": {"PACKF": 1, "RDENPF": 1, "DULL": 0}, "PWATER": {"SURO": 1}}
+    save_batch_aggregated(sink, labels, "PERLND", ["P%03d" % k for k in range(n)], tabs, saved, agg)
+    df = sink.calls[("PERLND", "P003", "SNOW")]
+    assert list(df.columns) == ["PACKF_last", "RDENPF_last", "PACKF_sum", "RDENPF_sum", "PACKF_aver", "RDENPF_aver"]
+    assert len(sink.calls) == 2 * n and df.index.equals(labels)
+
+
+class FrameSinkBackend:
+    def __init__(self):
+        self.calls = {}
+
+    def write_ts(self, data_frame, category, operation=None, segment=None, activity=None, *a, **k):
+        self.calls[(operation, segment, activity)] = data_frame

@@ -325,6 +325,11 @@ def test_qual_rows_many_segments():
                     assert parity.rel_err(out[:, r, j], ts[key]) <= parity.RTOL, (i, key)
 
 
+def test_period_aggregation_equals_pandas():
+    """outstep 3 / 4 / 5 statistics on the device == pandas on the float32 frames (IOManager.write_ts, io.py:74-94)."""
+    parity.check_period_aggregation(n=300, days=400)
+
+
 def test_option_word_kernels_equal_the_general_ones():
     parity.check_option_word_kernels()
 

@@ -104,3 +104,7 @@ def test_save_qual_batch_frames_equal_reference_frames():
         df, cols, cat, outstep = sink.calls[("IMPLND", seg, "IQUAL")]
         assert list(df.columns) == list(want.columns) and cols == ["SOQUAL"]
         assert np.array_equal(df.to_numpy(), want.to_numpy(), equal_nan=True) and df.to_numpy().dtype == np.float32
+
+
+def test_period_aggregation_equals_pandas():
+    parity.check_period_aggregation()

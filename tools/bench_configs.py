@@ -132,7 +132,81 @@ def run_chain(name, torch, dev):
     return line
 
 
+def run_daily_e2e(name, torch, dev):
+    """Headline ensemble end to end with DAILY output (outstep 3): pinned host forcings in, float32 series on the device, period
+    statistics on the device (hsp2g_aggregate_f32), and only last / sum / mean per day copied back -- 3/24 of the hourly bytes."""
+    import ctypes as C
+
+    import pandas as pd
+
+    from hspsquared_b200 import _lib, synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+    from hspsquared_b200.results import period_bins
+
+    lib = _lib.load()
+    cal = Calendar(bench.RUN_START, bench.RUN_STOP, 60, "ns")
+    K, W, Tc, n = 12, 3, 432, 100_000  # 432 = 18 days: chunks end where days end (labels are interval ends: offset by one)
+    ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
+    save = bench.default_save()
+    tindex = pd.date_range(bench.RUN_START, periods=(K + W) * Tc + 1, freq="60min")[1:]
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=dev.index or 0) as b:
+        b.set_output_dtype(np.float32)
+        npad, nf, ns = b.npad, b.nf, b.ns
+        hf = [torch.empty((npad // 32, Tc, nf, 32), dtype=torch.float64).pin_memory() for _ in range(2)]
+        for k in range(2):
+            hf[k].copy_(bench.device_forcing(torch, ens, cal, k * Tc, Tc, npad, dev, b.forcing_rows).cpu())
+        df_ = [torch.empty((npad // 32, Tc, nf, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+        do = torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float32, device=dev)
+        bins = [period_bins(tindex[c * Tc:(c + 1) * Tc], 3)[0] for c in range(K + W)]
+        nb = max(int(x[-1]) + 1 for x in bins)
+        da = torch.empty((npad // 32, nb, ns, 3, 32), dtype=torch.float32, device=dev)
+        ha = [torch.empty((npad // 32, nb, ns, 3, 32), dtype=torch.float32).pin_memory() for _ in range(2)]
+        s_in, stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)  # copy-in runs ahead of kernel + statistics + copy-out
+        i32 = C.POINTER(C.c_int32)
+        ready = [torch.cuda.Event() for _ in range(2)]   # forcing slot filled
+        freed = [torch.cuda.Event() for _ in range(2)]   # forcing slot consumed by its kernel
+        copied = [torch.cuda.Event() for _ in range(2)]  # host result slot written
+
+        def step(c):
+            k = c % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(freed[k])
+                df_[k].copy_(hf[k], non_blocking=True)
+                ready[k].record(s_in)
+            with torch.cuda.stream(stream):
+                stream.wait_event(ready[k])
+                b.run_device(c * Tc, Tc, df_[k].data_ptr(), do.data_ptr(), stream.cuda_stream)
+                freed[k].record(stream)
+                x = np.ascontiguousarray(bins[c])
+                _lib.check(lib.hsp2g_aggregate_f32(dev.index or 0, do.data_ptr(), npad // 32, Tc, ns, x.ctypes.data_as(i32), nb,
+                                                   da.data_ptr(), stream.cuda_stream))
+                ha[k].copy_(da, non_blocking=True)
+                copied[k].record(stream)
+
+        for c in range(W):
+            step(c)
+        torch.cuda.synchronize(dev)
+        import time
+        t0 = time.perf_counter()
+        for c in range(W, W + K):
+            step(c)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        chk = float(ha[(W + K - 1) % 2][:, :, 13:, 1].sum())
+        value = n * Tc * K / dt
+        line = {"config": name, "kernel": b.kernel_name(), "segments": n, "intervals_per_step": Tc, "steps": K,
+                "ms_per_step": 1e3 * dt / K, "segment_timesteps_per_s": value,
+                "h2d_bytes_per_step": Tc * nf * npad * 8, "d2h_bytes_per_step": nb * ns * 3 * npad * 4, "result_checksum": chk,
+                "frac_of_measured_hbm": None,
+                "note": "copy-in stream + compute stream: H2D of fp64 forcings, kernel with float32 stores, hsp2g_aggregate_f32 (daily last / "
+                        "sum / mean), D2H of the statistics; wall clock around the timed steps"}
+    return line
+
+
 def run(name, torch, dev):
+    if name == "perlnd_daily_e2e":
+        return run_daily_e2e(name, torch, dev)
     if name in ("pqual", "iqual"):
         return run_qual(name, torch, dev)
     if name == "fullchain_pqual":
