@@ -138,7 +138,8 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
  * d_src [tile][nsteps][ns][32] float32 (hsp2g_set_output_dtype(HSP2G_F32)); bin_of_step[t] = period of interval t (host array,
  * non-decreasing, < nbins; the host takes it from pandas so that the binning is the reference's); d_dst
  * [tile][nbins][ns][3][32] float32 with the three statistics in the order last, sum, mean.  Sums are pandas' compensated
- * float32 sums over the non-NaN values; an all-NaN period gives last = NaN, sum = 0, mean = NaN. */
+ * float32 sums over the non-NaN values; an all-NaN period gives last = NaN, sum = 0, mean = NaN.  One call covers whole periods:
+ * cut the run into chunks that end where periods end (the compensated sum of a period is not carried from call to call). */
 int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t nsteps, int32_t ns, const int32_t *bin_of_step,
                         int32_t nbins, float *d_dst, void *stream);
 
