@@ -47,6 +47,7 @@ _PROTOS = {
     "hsp2g_run_device": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "hsp2g_aggregate_f32": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "hsp2g_set_output_periods": (C.c_int, [_h, C.c_int64, _i32p]),
     "hsp2g_batch_stream": (C.c_void_p, [_h]),
     "hsp2g_gather_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i64p, C.POINTER(_h)]),
     "hsp2g_gather_run": (C.c_int, [_h, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, C.c_int32, C.c_void_p]),

@@ -46,7 +46,8 @@ static int fail(const char *fmt, ...) {
 
 struct Slot {
     double *forc = nullptr, *out = nullptr;
-    size_t cap_f = 0, cap_o = 0;
+    float *agg = nullptr;  // period statistics of the slot's chunk (hsp2g_set_output_periods)
+    size_t cap_f = 0, cap_o = 0, cap_a = 0;
     cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
 
@@ -79,6 +80,7 @@ struct hsp2g_batch {
     short srow[HSP2G_NOUT];
     int nf = -1, ns = -1;
     bool have_par = false, have_flags = false, have_state = false;
+    std::vector<int> periods;  // hsp2g_set_output_periods: period of every interval of the run (empty = series out)
     int flags_uniform = 0;  // every segment carries flags_word (a replicated ensemble): kernels specialised on the word apply
     unsigned long long flags_word = 0;
     cudaStream_t comp = nullptr, h2d = nullptr, d2h = nullptr;
@@ -504,6 +506,7 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     for (auto &s : b->slot) {
         cudaFree(s.forc);
         cudaFree(s.out);
+        cudaFree(s.agg);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.k_done) cudaEventDestroy(s.k_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -712,6 +715,25 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
             s.cap_o = need_o;
         }
     }
+    // period statistics instead of series (hsp2g_set_output_periods): the chunk must be made of whole periods
+    int nb = 0;
+    size_t need_a = 0;
+    if (!b->periods.empty() && b->ns > 0) {
+        const std::vector<int> &P = b->periods;
+        if (!b->out_f32) return fail("period statistics are defined on float32 outputs: hsp2g_set_output_dtype(HSP2G_F32)");
+        if (t0 + nsteps > (int64_t)P.size()) return fail("intervals beyond the %lld given to hsp2g_set_output_periods", (long long)P.size());
+        if ((t0 > 0 && P[t0 - 1] == P[t0]) || (t0 + nsteps < (int64_t)P.size() && P[t0 + nsteps] == P[t0 + nsteps - 1]))
+            return fail("a chunk must start and end on period boundaries when period statistics are requested");
+        nb = P[t0 + nsteps - 1] - P[t0] + 1;
+        need_a = (size_t)nb * b->ns * 3 * b->n_pad * sizeof(float);
+        if (need_a > s.cap_a) {
+            CU(cudaEventSynchronize(s.d2h_done));
+            cudaFree(s.agg);
+            s.agg = nullptr;
+            CU(cudaMalloc((void **)&s.agg, need_a));
+            s.cap_a = need_a;
+        }
+    }
     // the slot is free once its previous outputs have left the device; host and device share the tile-major
     // layout, so each direction is ONE contiguous copy
     CU(cudaStreamWaitEvent(b->h2d, s.d2h_done, 0));
@@ -719,9 +741,17 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
     CU(cudaEventRecord(s.h2d_done, b->h2d));
     CU(cudaStreamWaitEvent(b->comp, s.h2d_done, 0));
     if (launch(b, t0, nsteps, s.forc, s.out, b->comp)) return 1;
+    if (nb) {
+        std::vector<int> local((size_t)nsteps);
+        for (int t = 0; t < nsteps; ++t) local[(size_t)t] = b->periods[(size_t)(t0 + t)] - b->periods[(size_t)t0];
+        if (hsp2g_aggregate_f32(b->device, (const float *)s.out, b->ntiles, nsteps, b->ns, local.data(), nb, s.agg, b->comp)) return 1;
+    }
     CU(cudaEventRecord(s.k_done, b->comp));
     CU(cudaStreamWaitEvent(b->d2h, s.k_done, 0));
-    if (need_o) CU(cudaMemcpyAsync(h_out, s.out, need_o, cudaMemcpyDeviceToHost, b->d2h));
+    if (nb)
+        CU(cudaMemcpyAsync(h_out, s.agg, need_a, cudaMemcpyDeviceToHost, b->d2h));
+    else if (need_o)
+        CU(cudaMemcpyAsync(h_out, s.out, need_o, cudaMemcpyDeviceToHost, b->d2h));
     CU(cudaEventRecord(s.d2h_done, b->d2h));
     return 0;
 }
@@ -920,6 +950,20 @@ int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t 
     if (e != cudaSuccess) return fail("aggregate launch failed: %s", cudaGetErrorString(e));
     return 0;
 #endif
+}
+
+int hsp2g_set_output_periods(hsp2g_batch *b, int64_t n, const int32_t *period_of_step) {
+    if (!b) return fail("null batch");
+    if (n == 0 || !period_of_step) {  // back to series
+        b->periods.clear();
+        return 0;
+    }
+    if (n < 0) return fail("n must be >= 0");
+    for (int64_t t = 0; t < n; ++t)
+        if (period_of_step[t] < 0 || (t && (period_of_step[t] < period_of_step[t - 1] || period_of_step[t] > period_of_step[t - 1] + 1)))
+            return fail("period_of_step must start at >= 0 and grow by 0 or 1 from interval to interval");
+    b->periods.assign(period_of_step, period_of_step + n);
+    return 0;
 }
 
 int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype) {

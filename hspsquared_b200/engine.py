@@ -226,6 +226,41 @@ class LandBatch:
             out[t0:t1] = u if self._inv is None else u[:, :, self._inv]
         return out
 
+    def run_periods(self, forcing, period_of_step, periods_per_chunk=32):
+        """Period statistics straight from hsp2g_run_host (include/hsp2g.h hsp2g_set_output_periods): forcing [steps][nf][n],
+        period_of_step int[steps] (results.period_bins) -> [periods][ns][3 = last, sum, mean][n] float32, the numbers
+        IOManager.write_ts computes with pandas for outstep 3 / 4 / 5.  Chunks are cut at period ends."""
+        forcing = np.asarray(forcing, dtype=np.float64)
+        steps = forcing.shape[0]
+        P = np.ascontiguousarray(period_of_step, dtype=np.int32)
+        if forcing.shape != (steps, self.nf, self.n) or P.shape != (steps,):
+            raise ValueError("forcing must be [steps][%d][%d] and period_of_step [steps]" % (self.nf, self.n))
+        self.set_output_dtype(np.float32)
+        _lib.check(self.lib.hsp2g_set_output_periods(self.h, steps, _ptr(P, C.POINTER(C.c_int32))))
+        nper = int(P[-1]) + 1
+        out = np.empty((nper, self.ns, 3, self.n), dtype=np.float32)
+        starts = np.flatnonzero(np.diff(P, prepend=P[0] - 1))  # first interval of every period present
+        cuts = list(starts[::periods_per_chunk]) + [steps]
+        pending = []
+        try:
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                f = forcing[a:b][:, self._fperm, :]
+                if self.order is not None:
+                    f = f[:, :, self.order]
+                ft = tile_series(f)
+                nb = int(P[b - 1] - P[a]) + 1
+                o = np.empty((self.ntiles, nb, self.ns, 3, _lib.TILE), dtype=np.float32)
+                self._keep.append((ft, o))
+                _lib.check(self.lib.hsp2g_run_host(self.h, int(a), int(b - a), ft.ctypes.data, o.ctypes.data))
+                pending.append((int(P[a]), nb, o))
+            self.sync()
+        finally:
+            _lib.check(self.lib.hsp2g_set_output_periods(self.h, 0, None))
+        for p0, nb, o in pending:
+            u = o.transpose(1, 2, 3, 0, 4).reshape(nb, self.ns, 3, self.ntiles * _lib.TILE)[:, :, :, :self.n][:, self._sinv]
+            out[p0:p0 + nb] = u if self._inv is None else u[:, :, :, self._inv]
+        return out
+
     # ------------------------------------------------------------------------------------------------
     def errors(self):
         """{error id: int64[n]} for the counters of the active sections."""

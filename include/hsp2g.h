@@ -143,6 +143,12 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
 int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t nsteps, int32_t ns, const int32_t *bin_of_step,
                         int32_t nbins, float *d_dst, void *stream);
 
+/* Make hsp2g_run_host deliver period statistics instead of series (outstep 3 / 4 / 5 of main.py:259-262 -> io.py:74-94):
+ * period_of_step[t] = period of interval t of the run (grows by 0 or 1), n = 0 switches back to series.  Needs float32 outputs.
+ * Every chunk given to hsp2g_run_host must then consist of whole periods; its h_out receives
+ * [tile][periods of the chunk][row][3 = last, sum, mean][32] float32 -- 3 / (intervals per period) of the series' bytes cross PCIe. */
+int hsp2g_set_output_periods(hsp2g_batch *b, int64_t n, const int32_t *period_of_step);
+
 /* The stream hsp2g_run_device uses when it is given none (non-blocking; nothing orders it against other streams): pass it to
  * hsp2g_gather_run, or to another batch's hsp2g_run_device, to chain work on the device in order. */
 void *hsp2g_batch_stream(hsp2g_batch *b);

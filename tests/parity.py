@@ -564,6 +564,8 @@ def check_option_word_kernels():
 def check_period_aggregation(n=40, days=75):
     """hsp2g_aggregate_f32 against pandas on the float32 frames (what IOManager.write_ts does for outstep 3 / 4 / 5,
     hsp2io/io.py:74-94): last / sum / mean per day, month and year, NaN series included, bit for bit."""
+    import ctypes as C
+
     import pandas as pd
 
     from hspsquared_b200.results import aggregate_host_series, period_bins, save_batch_aggregated
@@ -591,6 +593,21 @@ def check_period_aggregation(n=40, days=75):
                 w = want.to_numpy()
                 assert w.dtype == np.float32
                 assert np.array_equal(agg[:, :, stat, i], w, equal_nan=True), (outstep, stat, i)
+    # the same statistics delivered by hsp2g_run_host itself (hsp2g_set_output_periods), chunks cut at period ends
+    bins, labels = period_bins(tindex, 3)
+    want = aggregate_host_series(out, bins, len(labels))
+    with LandBatch(ens.store(cal), cal, names, "all", order="flags") as b:
+        got = b.run_periods(synth.forcing_chunk(ens, cal, 0, cal.steps, names=names), bins, periods_per_chunk=9)
+        try:
+            b.set_output_dtype(np.float32)
+            _lib.check(b.lib.hsp2g_set_output_periods(b.h, len(bins), bins.ctypes.data_as(C.POINTER(C.c_int32))))
+            bad = np.zeros((b.ntiles, 30, b.nf, 32))
+            b.run_host(0, bad, np.empty((b.ntiles, 30, b.ns, 32), dtype=np.float32))  # 30 intervals: not whole days
+        except _lib.Hsp2gError as e:
+            assert "period boundaries" in str(e)
+        else:
+            raise AssertionError("a chunk that splits a period was accepted")
+    assert np.array_equal(got, want, equal_nan=True)
     # frame layout of the merged result (io.py:79-81)
     sink = FrameSinkBackend()
     bins, labels = period_bins(tindex, 3)
