@@ -535,18 +535,28 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
     fb = Te * nf * npad * 8
     bufs = []
 
-    def timed(out_dtype, steps, base):
+    def timed(out_dtype, steps, base, daily=False):
         osz = np.dtype(out_dtype).itemsize
         ob = Te * ns * npad * osz
         batch.set_output_dtype(out_dtype)
         ctype = C.c_float if osz == 4 else C.c_double
+        shape = (nt, Te, ns, 32)
+        if daily:  # 24-interval statistics (last, sum, mean) computed on the device, a new period at every chunk start
+            nb = (Te + 23) // 24
+            t = np.arange(cal.steps, dtype=np.int64)
+            p0 = (base - 1) // 24 if base else -1  # intervals before the timed region: plain 24-interval periods
+            per = np.where(t < base, t // 24, p0 + 1 + ((t - base) // Te) * nb + ((t - base) % Te) // 24).astype(np.int32)
+            per = np.ascontiguousarray(per)
+            _lib.check(lib.hsp2g_set_output_periods(batch.h, len(per), per.ctypes.data_as(C.POINTER(C.c_int32))))
+            ob = nb * ns * 3 * npad * 4
+            shape = (nt, nb, ns, 3, 32)
         ho = []
         for _ in range(2):
             q = lib.hsp2g_host_alloc(ob)
             if not q:
                 raise MemoryError(lib.hsp2g_last_error().decode())
             bufs.append(q)
-            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(ctype)), shape=(nt, Te, ns, 32)))
+            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(ctype)), shape=shape))
         nwarm = 2
         for c in range(nwarm):
             batch.run_host_ptr(base + c * Te, Te, hf[c % 2].ctypes.data, ho[c % 2].ctypes.data)
@@ -565,7 +575,9 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             dist.all_gather(allt, t)
             per_rank = [round(1e3 * float(x.item()) / steps, 2) for x in allt]
             dt = max(float(x.item()) for x in allt)
-        chk = float(np.nansum(ho[(nwarm + steps - 1) % 2][:, -1, 13:, :], dtype=np.float64))  # read the step's result
+        if daily:
+            _lib.check(lib.hsp2g_set_output_periods(batch.h, 0, None))
+        chk = float(np.nansum(ho[(nwarm + steps - 1) % 2][:, -1, 13:], dtype=np.float64))  # read the step's result
         del ho
         for q in bufs[-2:]:
             lib.hsp2g_host_free(q)
@@ -592,12 +604,20 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             hf[j][...] = tile_series(synth.forcing_chunk(ens, cal, base + j * Te, Te, names=batch.forcing_rows))
         r32, base = timed(np.float32, K, base)
         r64, base = timed(np.float64, K64, base)
+        try:
+            rd, base = timed(np.float32, K64, base, daily=True)
+            daily = {"value": rd["value"], "d2h_bytes_per_step": rd["d2h_bytes_per_step"], "ms_per_step": rd["ms_per_step"],
+                     "steps": rd["steps"], "note": "hsp2g_set_output_periods: last / sum / mean per 24 intervals computed on the "
+                     "device (IOManager.write_ts outstep 3, hsp2io/io.py:74-81), only the statistics cross PCIe"}
+        except Exception as ex:
+            daily = {"error": repr(ex)}
         return {"value": r32["value"], "unit": "segment-timesteps/s", "h2d_bytes_per_step": fb,
                 "d2h_bytes_per_step": r32["d2h_bytes_per_step"], "intervals_per_step": Te, "steps": K,
                 "ms_per_step": r32["ms_per_step"], "pcie_gbs": r32["pcie_gbs"], "result_checksum": r32["result_checksum"],
                 "per_rank_ms_per_step": r32["per_rank_ms_per_step"],
                 "out_dtype": "float32 (the cast save_timeseries applies before IOManager.write_ts, utilities.py:313)",
                 "kernel": batch.kernel_name(),
+                "daily_statistics": daily,
                 "fp64_outputs": {"value": r64["value"], "d2h_bytes_per_step": r64["d2h_bytes_per_step"],
                                  "ms_per_step": r64["ms_per_step"], "pcie_gbs": r64["pcie_gbs"], "steps": r64["steps"]},
                 "note": "pinned tile-major host buffers -> hsp2g_run_host (one contiguous H2D, kernel, one contiguous "
