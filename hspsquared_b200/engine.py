@@ -235,6 +235,7 @@ class LandBatch:
         P = np.ascontiguousarray(period_of_step, dtype=np.int32)
         if forcing.shape != (steps, self.nf, self.n) or P.shape != (steps,):
             raise ValueError("forcing must be [steps][%d][%d] and period_of_step [steps]" % (self.nf, self.n))
+        previous = self.out_dtype
         self.set_output_dtype(np.float32)
         _lib.check(self.lib.hsp2g_set_output_periods(self.h, steps, _ptr(P, C.POINTER(C.c_int32))))
         nper = int(P[-1]) + 1
@@ -256,6 +257,7 @@ class LandBatch:
             self.sync()
         finally:
             _lib.check(self.lib.hsp2g_set_output_periods(self.h, 0, None))
+            self.set_output_dtype(previous)
         for p0, nb, o in pending:
             u = o.transpose(1, 2, 3, 0, 4).reshape(nb, self.ns, 3, self.ntiles * _lib.TILE)[:, :, :, :self.n][:, self._sinv]
             out[p0:p0 + nb] = u if self._inv is None else u[:, :, :, self._inv]
