@@ -8,12 +8,18 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# HSP2G_LIB selects another build of the SAME library (kernel tuning experiments, hspsquared_b200/build.py)
+# HSP2G_LIB selects another build of the SAME library (kernel tuning experiments, hspsquared_b200/build.py); whatever the
+# path, load() accepts only a library that says it is the CUDA build (hsp2g_names("build")), so no host-compiled stand-in
+# can ever serve the product path.  The CPU test suite's double is admitted by tests/conftest.py alone, through ALLOW_BUILDS.
 LIB_PATH = os.environ.get("HSP2G_LIB") or os.path.join(_HERE, "libhsp2g.so")
+CUDA_BUILD = "cuda/sm_100a"
+ALLOW_BUILDS = {CUDA_BUILD}
 
 PERLND, IMPLND = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 F64, F32 = 0, 1
+TILED, PLAIN = 0, 1
+HOST_WRITE_COMBINED, HOST_PORTABLE = 1, 2
 TILE = 32  # segments per tile of the series layout [tile][interval][row][32] (include/hsp2g.h)
 ACT_BITS = {"ATEMP": 1, "SNOW": 2, "PWATER": 4, "SEDMNT": 8, "PSTEMP": 16, "PWTGAS": 32, "IWATER": 64, "SOLIDS": 128,
             "IWTGAS": 256, "PQUAL": 512, "IQUAL": 1024}
@@ -46,6 +52,11 @@ _PROTOS = {
     "hsp2g_set_save": (C.c_int, [_h, C.c_int, _i32p]),
     "hsp2g_run_device": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "hsp2g_run_device_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hsp2g_run_host_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "hsp2g_set_series_layout": (C.c_int, [_h, C.c_int]),
+    "hsp2g_set_forcing_dtype": (C.c_int, [_h, C.c_int]),
+    "hsp2g_set_kernel_image": (C.c_int, [_h, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p]),
     "hsp2g_aggregate_f32": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_void_p]),
     "hsp2g_set_output_periods": (C.c_int, [_h, C.c_int64, _i32p]),
     "hsp2g_batch_stream": (C.c_void_p, [_h]),
@@ -64,6 +75,9 @@ _PROTOS = {
     "hsp2g_kernel_name": (C.c_char_p, [_h]),
     "hsp2g_math_probe": (C.c_int, [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp]),
     "hsp2g_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "hsp2g_host_alloc_flags": (C.c_void_p, [C.c_size_t, C.c_uint]),
+    "hsp2g_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "hsp2g_host_unregister": (C.c_int, [C.c_void_p]),
     "hsp2g_host_free": (C.c_int, [C.c_void_p]),
     "hsp2g_device_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
     "hsp2g_device_free": (C.c_int, [C.c_int, C.c_void_p]),
@@ -95,8 +109,17 @@ def load():
         fn.argtypes = args
     if lib.hsp2g_abi_version() != ABI_VERSION:
         raise Hsp2gError("libhsp2g ABI version mismatch")
+    kind = lib.hsp2g_names(b"build").decode()
+    if kind not in ALLOW_BUILDS:
+        raise Hsp2gError("%s is a %r build of libhsp2g; the land-segment path runs on the CUDA build (%s) only -- there is no "
+                         "CPU fallback" % (LIB_PATH, kind, CUDA_BUILD))
     _lib = lib
     return lib
+
+
+def build_kind():
+    """'cuda/sm_100a' for the product library (load() admits nothing else outside the CPU test suite)."""
+    return load().hsp2g_names(b"build").decode()
 
 
 def check(rc):

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libhsp2g.so")
 #   HSP2G_NVCC_EXTRA="-DHSP_MINB_HOT=3" HSP2G_LIB_OUT=/root/repo/gpurun_out/../exp/libhsp2g_m3.so python -m hspsquared_b200.build --force
 EXTRA = os.environ.get("HSP2G_NVCC_EXTRA", "").split()
 LIB_OUT = os.environ.get("HSP2G_LIB_OUT") or LIB
-UNITS = ("hsp2g_api.cu", "perlnd_kernel.cu", "hot_kernels.cu", "implnd_kernel.cu", "qual_kernel.cu")
+UNITS = ("hsp2g_api.cu", "perlnd_kernel.cu", "implnd_kernel.cu", "qual_kernel.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -4,9 +4,15 @@
 // device slots so that copy-in of chunk k+1, the kernel of chunk k and copy-out of chunk k-1 overlap (SURVEY 8b
 // "Threading": one handle per GPU, internal streams).
 #include "cuda_rt.h"
+#ifdef HSP2G_HOST_EMU
+#include <dlfcn.h>
+#else
+#include <cuda.h>
+#endif
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -14,6 +20,7 @@
 #include <vector>
 
 #include "../../include/hsp2g.h"
+#include "jit_info.h"
 #include "land_common.cuh"
 #include "launch.h"
 
@@ -23,7 +30,7 @@ static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && 
                   HSP2G_SOLIDS == HSP2G_ACT_SOLIDS && HSP2G_IWTGAS == HSP2G_ACT_IWTGAS &&
                   HSP2G_PQUAL == HSP2G_ACT_PQUAL && HSP2G_IQUAL == HSP2G_ACT_IQUAL,
               "public activity bits must match the kernel's");
-static_assert(HSP2G_ABI_VERSION == 2, "bump _lib.py with the header");
+static_assert(HSP2G_ABI_VERSION == 3, "bump _lib.py with the header");
 static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
 static_assert(sizeof(CalStep) == 32, "CalStep layout");
 
@@ -43,6 +50,21 @@ static int fail(const char *fmt, ...) {
         cudaError_t e_ = (call);                                                                  \
         if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// A kernel built for one batch's exact configuration (hspsquared_b200/jit.py -> hsp2g_set_kernel_image)
+struct JitKernel {
+    bool on = false;
+    unsigned long long info[JI_N] = {0};
+    int resident = 0;  // blocks the device holds at once
+    std::string name;
+#ifdef HSP2G_HOST_EMU
+    void *dl = nullptr;
+    void (*fn)(const LandLaunch &) = nullptr;
+#else
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+#endif
+};
 
 struct Slot {
     double *forc = nullptr, *out = nullptr;
@@ -66,6 +88,12 @@ struct hsp2g_batch {
     unsigned prog_base = 0;
     int sub_steps = 64;
     int out_f32 = 0;
+    int plain = 0;     // series layout of run_device / run_host: 0 = TILED [tile][t][row][32], 1 = PLAIN [t][row][ld]
+    int forc_f32 = 0;  // forcing series are float32
+    JitKernel jit;
+    int *d_periods = nullptr;  // device copy of `periods`
+    cudaEvent_t last_launch = nullptr;  // recorded after every launch on the stream it used (state / error accessors wait for it)
+    bool have_last = false;
     // shared-met mode
     double *met = nullptr;   // [n_met_steps][nf][n_stations]
     int *station = nullptr;  // [ntiles][32]
@@ -177,6 +205,16 @@ int check_ready(const hsp2g_batch *b, int64_t t0, int32_t nsteps) {
     return 0;
 }
 
+// the batch's kernels may run on a caller's stream (hsp2g_run_device): state and error rows are read / written only after the
+// last launch has finished, whatever stream it used
+int wait_last_launch(hsp2g_batch *b) {
+    CU(cudaStreamSynchronize(b->comp));
+    if (b->have_last) CU(cudaEventSynchronize(b->last_launch));
+    return 0;
+}
+
+void drop_kernel_image(hsp2g_batch *b);
+
 cudaEvent_t get_event(hsp2g_batch *b) {
     if (!b->ev_pool.empty()) {
         cudaEvent_t e = b->ev_pool.back();
@@ -201,13 +239,158 @@ int drain_timing(hsp2g_batch *b) {
     return 0;
 }
 
-int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, cudaStream_t st) {
+#ifndef HSP2G_HOST_EMU
+// The few driver-API entry points the library needs (module loading for kernels built at run time, tensor maps for the PLAIN
+// layout), resolved through the runtime so that libhsp2g.so does not link libcuda and still loads on a box without a driver.
+struct Driver {
+    bool ok = false;
+    std::string why;
+    CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **,
+                             void **) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+};
+const Driver &driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        struct {
+            const char *name;
+            void **slot;
+        } want[] = {{"cuModuleLoadData", (void **)&d.ModuleLoadData},
+                    {"cuModuleUnload", (void **)&d.ModuleUnload},
+                    {"cuModuleGetFunction", (void **)&d.ModuleGetFunction},
+                    {"cuModuleGetGlobal", (void **)&d.ModuleGetGlobal},
+                    {"cuFuncSetAttribute", (void **)&d.FuncSetAttribute},
+                    {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void **)&d.OccupancyMaxActiveBlocksPerMultiprocessor},
+                    {"cuLaunchKernel", (void **)&d.LaunchKernel},
+                    {"cuGetErrorString", (void **)&d.GetErrorString},
+                    {"cuTensorMapEncodeTiled", (void **)&d.TensorMapEncodeTiled}};
+        for (auto &w : want) {
+            cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+            cudaError_t e = cudaGetDriverEntryPoint(w.name, w.slot, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*w.slot) {
+                d.why = std::string("driver entry point ") + w.name + " unavailable";
+                return;
+            }
+        }
+        d.ok = true;
+    });
+    return d;
+}
+const char *cu_str(CUresult r) {
+    const char *m = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &m);
+    return m ? m : "unknown driver error";
+}
+// CUtensorMap of a PLAIN forcing buffer [nsteps][nf][ld] (elements of esz bytes) as the 3-D tensor (segment, row, interval)
+// with a box of 32 segments x nf rows x 1 interval: what one warp needs for one interval, fetched by one TMA instruction.
+bool make_tmap(unsigned long long *out16, const void *base, int esz, long long ld, int nf, long long nsteps) {
+    const Driver &d = driver();
+    if (!d.ok || nf <= 0 || nf > 256 || ((uintptr_t)base & 15) || ((ld * esz) & 15)) return false;
+    alignas(64) CUtensorMap m;
+    const cuuint64_t dim[3] = {(cuuint64_t)ld, (cuuint64_t)nf, (cuuint64_t)nsteps};
+    const cuuint64_t stride[2] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * nf};
+    const cuuint32_t box[3] = {LAND_TILE, (cuuint32_t)nf, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = d.TensorMapEncodeTiled(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                                        const_cast<void *>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(out16, &m, sizeof m);
+    return true;
+}
+#endif
+
+void drop_kernel_image(hsp2g_batch *b) {
+    if (!b) return;
+#ifdef HSP2G_HOST_EMU
+    if (b->jit.dl) dlclose(b->jit.dl);
+    b->jit.dl = nullptr;
+#else
+    if (b->jit.mod && driver().ok) driver().ModuleUnload(b->jit.mod);
+    b->jit.mod = nullptr;
+#endif
+    b->jit.fn = nullptr;
+    b->jit.on = false;
+}
+
+// Does the kernel built for this batch (hsp2g_set_kernel_image) still describe the launch?  Anything that was fixed at
+// compile time must equal the batch's current configuration; otherwise the library's general kernels run.
+bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
+    const unsigned long long *I = b->jit.info;
+    const unsigned long long bits = I[JI_BITS];
+    const bool qual = (b->act & (HSP2G_ACT_PQUAL | HSP2G_ACT_IQUAL)) != 0;
+    if (I[JI_OP] != (unsigned long long)b->op || ((bits & JB_QUAL) != 0) != qual) return false;
+    if (!qual && I[JI_ACT] != ~0ull && I[JI_ACT] != b->act) return false;
+    if (I[JI_HOURLY] && !(b->delt >= 60.0)) return false;
+    if (((bits & JB_SHARED) != 0) != (L.met != nullptr)) return false;
+    if (bits & JB_WORD) {
+        if (!L.flags_uniform || L.flags_word != I[JI_WORD]) return false;
+    }
+    if (bits & JB_LAYSTATIC) {
+        if (((bits & JB_PLAIN) != 0) != (L.plain != 0)) return false;
+        if (!(bits & JB_SHARED) && ((bits & JB_F32IN) != 0) != (L.forc_f32 != 0)) return false;
+    }
+    if (bits & JB_IOSTATIC) {
+        if (((bits & JB_F32OUT) != 0) != (L.out_f32 != 0)) return false;
+        int r = 0;
+        for (int id = 0; id < HSP2G_NFORC; ++id) {
+            const bool on = (I[JI_FMASK] >> id) & 1ull;
+            if (L.frow[id] != (on ? r : -1)) return false;
+            r += on;
+        }
+        if (r != L.nf) return false;
+        r = 0;
+        for (int id = 0; id < HSP2G_NOUT; ++id) {
+            const bool on = (I[JI_S0 + id / 64] >> (id & 63)) & 1ull;
+            if (L.srow[id] != (on ? r : -1)) return false;
+            r += on;
+        }
+        if (r != L.ns) return false;
+    }
+    return true;
+}
+
+int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid) {
+    hsp2g_plan_tasks(L, b->sub_steps, b->jit.resident, LAND_WARPS, grid);
+#ifdef HSP2G_HOST_EMU
+    (void)st;
+    for (unsigned blk = 0; blk < (unsigned)*grid; ++blk)
+        for (unsigned t = 0; t < LAND_BLOCK; ++t) {
+            blockIdx.x = blk;
+            threadIdx.x = t;
+            b->jit.fn(L);
+        }
+#else
+    void *params[1] = {&L};
+    CUresult r = driver().LaunchKernel(b->jit.fn, (unsigned)*grid, 1, 1, LAND_BLOCK, 1, 1, (unsigned)b->jit.info[JI_SMEM], (CUstream)st,
+                                       params, nullptr);
+    if (r != CUDA_SUCCESS) return fail("launch of the batch's own kernel failed: %s", cu_str(r));
+#endif
+    b->kname = b->jit.name.c_str();
+    return 0;
+}
+
+// One launch over intervals [t0, t0+nsteps).  Series layout: b->plain ? PLAIN with rows forc_ld / out_ld elements apart : TILED.
+int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long long forc_ld, void *d_out, long long out_ld,
+           cudaStream_t st) {
     LandLaunch L;
     memset(&L, 0, sizeof L);
     L.segblk = b->segblk;
     L.mon = b->mon;
-    L.forc = d_forc;
-    L.out = d_out;
+    L.forc = (const double *)d_forc;
+    L.out = (double *)d_out;
     if (b->met) {
         if (t0 + nsteps > b->n_met_steps)
             return fail("intervals [%lld, %lld) outside the shared met series (%lld intervals)", (long long)t0,
@@ -225,6 +408,10 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.nf = b->nf;
     L.ns = b->ns;
     L.out_f32 = b->out_f32;
+    L.plain = b->plain;
+    L.forc_f32 = b->met ? 0 : b->forc_f32;
+    L.forc_ld = forc_ld;
+    L.out_ld = out_ld;
     L.act = b->act;
     L.opts = b->opts;
     L.flags_uniform = b->flags_uniform;
@@ -235,7 +422,13 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     memcpy(L.ffill, b->ffill, sizeof L.ffill);
     memcpy(L.srow, b->srow, sizeof L.srow);
     memcpy(L.mslot, b->mslot, sizeof L.mslot);
+#ifndef HSP2G_HOST_EMU
+    if (b->plain && !b->met && b->nf > 0 && !getenv("HSP2G_NO_TMAP"))
+        L.tmap_ok = make_tmap(L.tmap, d_forc, L.forc_f32 ? 4 : 8, forc_ld, b->nf, nsteps) ? 1 : 0;
+#endif
     const bool hourly = b->delt >= 60.0;
+    // launches of one batch share its ticket counter and state rows: each waits for the previous one, whatever its stream
+    if (b->have_last) CU(cudaStreamWaitEvent(st, b->last_launch, 0));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (b->timing) {
         e0 = get_event(b);
@@ -248,10 +441,20 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
     L.prog_base = b->prog_base;
     int grid = 0;
     const bool qual = (b->act & (HSP2G_ACT_PQUAL | HSP2G_ACT_IQUAL)) != 0;
-    cudaError_t e = qual                    ? hsp2g_launch_qual(L, b->op == HSP2G_IMPLND, b->sub_steps, st, &b->kname, &grid)
-                    : b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
-                                            : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
-    if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
+    int rc = 0;
+    if (b->jit.on && jit_matches(b, L))
+        rc = launch_jit(b, L, st, &grid);
+    else {
+        cudaError_t e = qual                    ? hsp2g_launch_qual(L, b->op == HSP2G_IMPLND, b->sub_steps, st, &b->kname, &grid)
+                        : b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
+                                                : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
+        if (e != cudaSuccess) rc = fail("kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        if (e0) b->ev_pool.push_back(e0);
+        if (e1) b->ev_pool.push_back(e1);
+        return rc;
+    }
     // every task draws one ticket and every warp one more (the draw that tells it to stop)
     b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid * LAND_WARPS;
     b->prog_base += (unsigned)L.nsub;
@@ -259,6 +462,9 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, dou
         CU(cudaEventRecord(e1, st));
         b->pending.emplace_back(e0, e1);
     }
+    // the state / error accessors and the next launch of this batch order themselves after this one, whatever stream it is on
+    CU(cudaEventRecord(b->last_launch, st));
+    b->have_last = true;
     b->launches += 1;
     return 0;
 }
@@ -311,35 +517,54 @@ __global__ void __launch_bounds__(128) gather_kernel(const __grid_constant__ Gat
 struct AggArgs {
     const float *src;
     float *dst;
-    const int *bin;
-    long long n_threads;  // ntiles * ns * 32
-    int nsteps, ns, nbins;
+    const int *bin;       // period of every interval, bin[0] belongs to the first interval of the chunk
+    int bin_base;         // subtracted from bin[t]
+    long long n_threads;  // TILED: ntiles * ns * 32; PLAIN: ns * ld
+    long long ld;         // PLAIN: elements per row of src and dst
+    int nsteps, ns, nbins, plain;
 };
-__host__ __device__ inline void agg_flush(float *d, float last, float sum, int cnt) {
-    const float nanf_ = __builtin_nanf("");
-    d[0 * LAND_TILE] = last;
-    d[1 * LAND_TILE] = sum;                               // min_count = 0: an all-NaN period sums to 0
-    d[2 * LAND_TILE] = cnt ? sum / (float)cnt : nanf_;   // mean = compensated sum / count, in float32
-}
 __host__ __device__ inline void agg_thread(const AggArgs &A, long long j) {
-    const int lane = (int)(j % LAND_TILE);
-    const long long tr = j / LAND_TILE;
-    const int r = (int)(tr % A.ns);
-    const long long tile = tr / A.ns;
-    const float *s = A.src + (((size_t)tile * A.nsteps) * A.ns + r) * LAND_TILE + lane;
-    float *d = A.dst + ((((size_t)tile * A.nbins) * A.ns + r) * 3) * LAND_TILE + lane;
+    // this thread's series: element t at s[t * sstep]; its three statistics of period p at d[p * dstep + k * kstep]
+    const float *s;
+    float *d;
+    size_t sstep, dstep, kstep;
+    if (A.plain) {
+        const long long seg = j % A.ld, r = j / A.ld;
+        s = A.src + (size_t)r * A.ld + seg;
+        sstep = (size_t)A.ns * A.ld;
+        d = A.dst + ((size_t)r * 3) * A.ld + seg;
+        dstep = (size_t)A.ns * 3 * A.ld;
+        kstep = (size_t)A.ld;
+    } else {
+        const int lane = (int)(j % LAND_TILE);
+        const long long tr = j / LAND_TILE;
+        const int r = (int)(tr % A.ns);
+        const long long tile = tr / A.ns;
+        s = A.src + (((size_t)tile * A.nsteps) * A.ns + r) * LAND_TILE + lane;
+        sstep = (size_t)A.ns * LAND_TILE;
+        d = A.dst + ((((size_t)tile * A.nbins) * A.ns + r) * 3) * LAND_TILE + lane;
+        dstep = (size_t)A.ns * 3 * LAND_TILE;
+        kstep = LAND_TILE;
+    }
     const float nanf_ = __builtin_nanf("");
+#define AGG_FLUSH(p, last_, sum_, cnt_)                                                            \
+    do {                                                                                           \
+        float *q_ = d + (size_t)(p) * dstep;                                                       \
+        q_[0] = (last_);                                                                           \
+        q_[kstep] = (sum_);                             /* min_count = 0: an all-NaN period sums to 0 */ \
+        q_[2 * kstep] = (cnt_) ? (sum_) / (float)(cnt_) : nanf_; /* mean = compensated sum / count, in float32 */ \
+    } while (0)
     float sum = 0.f, comp = 0.f, last = nanf_;
-    int cnt = 0, cur = A.bin[0];
-    for (int b = 0; b < cur; ++b) agg_flush(d + (size_t)b * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);  // leading empty periods
+    int cnt = 0, cur = A.bin[0] - A.bin_base;
+    for (int b = 0; b < cur; ++b) AGG_FLUSH(b, nanf_, 0.f, 0);  // leading empty periods
     for (int t = 0; t < A.nsteps; ++t) {
-        const int b = A.bin[t];
+        const int b = A.bin[t] - A.bin_base;
         if (b != cur) {
-            agg_flush(d + (size_t)cur * A.ns * 3 * LAND_TILE, last, sum, cnt);
-            for (int e = cur + 1; e < b; ++e) agg_flush(d + (size_t)e * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);
+            AGG_FLUSH(cur, last, sum, cnt);
+            for (int e = cur + 1; e < b; ++e) AGG_FLUSH(e, nanf_, 0.f, 0);
             sum = 0.f, comp = 0.f, last = nanf_, cnt = 0, cur = b;
         }
-        const float v = s[(size_t)t * A.ns * LAND_TILE];
+        const float v = s[(size_t)t * sstep];
         if (v == v) {  // skipna
             ++cnt;
             last = v;
@@ -350,8 +575,9 @@ __host__ __device__ inline void agg_thread(const AggArgs &A, long long j) {
             sum = tt;
         }
     }
-    agg_flush(d + (size_t)cur * A.ns * 3 * LAND_TILE, last, sum, cnt);
-    for (int e = cur + 1; e < A.nbins; ++e) agg_flush(d + (size_t)e * A.ns * 3 * LAND_TILE, nanf_, 0.f, 0);
+    AGG_FLUSH(cur, last, sum, cnt);
+    for (int e = cur + 1; e < A.nbins; ++e) AGG_FLUSH(e, nanf_, 0.f, 0);
+#undef AGG_FLUSH
 }
 #ifndef HSP2G_HOST_EMU
 __global__ void __launch_bounds__(128) aggregate_kernel(const __grid_constant__ AggArgs A) {
@@ -359,6 +585,19 @@ __global__ void __launch_bounds__(128) aggregate_kernel(const __grid_constant__ 
     if (j < A.n_threads) agg_thread(A, j);
 }
 #endif
+// enqueue the aggregation of one chunk; `bin` is a DEVICE array in the product build (a host array in the test double)
+static int run_aggregate(const AggArgs &A, cudaStream_t st) {
+#ifdef HSP2G_HOST_EMU
+    (void)st;
+    for (long long j = 0; j < A.n_threads; ++j) agg_thread(A, j);
+    return 0;
+#else
+    aggregate_kernel<<<(unsigned)((A.n_threads + 127) / 128), 128, 0, st>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("aggregate launch failed: %s", cudaGetErrorString(e));
+    return 0;
+#endif
+}
 
 // Kernels opt in to their dynamic shared memory once (the per-warp TMA rings can exceed the 48 KB default when many
 // forcing rows are present); the resident-block count sizes the persistent grid.
@@ -416,6 +655,13 @@ const char *hsp2g_names(const char *t) {
     if (!strcmp(t, "forcings")) return k_forcings;
     if (!strcmp(t, "outputs")) return k_outputs;
     if (!strcmp(t, "errors")) return k_errors;
+    if (!strcmp(t, "build")) {  // which build of the library this is: the product loader refuses anything but the CUDA one
+#ifdef HSP2G_HOST_EMU
+        return "host-emu";
+#else
+        return "cuda/sm_100a";
+#endif
+    }
     return "";
 }
 
@@ -479,13 +725,18 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
     ALLOC(b->d_counter, sizeof(unsigned long long));
     ALLOC(b->d_progress, (size_t)b->ntiles * sizeof(unsigned));
 #undef ALLOC
-    CU(cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking));
+    ce = cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->last_launch, cudaEventDisableTiming);
     for (auto &s : b->slot) {
-        CU(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) {
+        hsp2g_batch_destroy(b);
+        return fail("stream / event creation: %s", cudaGetErrorString(ce));
     }
     *out = b;
     return 0;
@@ -503,6 +754,9 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     cudaFree(b->station);
     cudaFree(b->mfac);
     cudaFree(b->cal);
+    cudaFree(b->d_periods);
+    if (b->last_launch) cudaEventDestroy(b->last_launch);
+    drop_kernel_image(b);
     for (auto &s : b->slot) {
         cudaFree(s.forc);
         cudaFree(s.out);
@@ -551,16 +805,21 @@ int hsp2g_set_monthly(hsp2g_batch *b, int id, const double *tab, int64_t ld) {
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
     const size_t one = (size_t)12 * b->n_seg;
-    if (b->mslot[id] < 0) {  // a new table: grow the host copy and the tile-major device block by one slot
-        b->mslot[id] = (short)b->nmon_slots++;
-        b->h_mon.resize(one * b->nmon_slots);
+    int slot = b->mslot[id];
+    if (slot < 0) {  // a new table: grow the host copy and the tile-major device block by one slot
+        slot = b->nmon_slots;
+        double *grown = nullptr;
         CU(cudaDeviceSynchronize());
+        CU(cudaMalloc((void **)&grown, (size_t)b->ntiles * 12 * (slot + 1) * LAND_TILE * sizeof(double)));
         cudaFree(b->mon);
-        b->mon = nullptr;
-        CU(cudaMalloc((void **)&b->mon, (size_t)b->ntiles * 12 * b->nmon_slots * LAND_TILE * sizeof(double)));
+        b->mon = grown;
+        b->h_mon.resize(one * (slot + 1));
+        // the slot is committed only now that its storage exists; its rows are uploaded below
+        b->nmon_slots = slot + 1;
+        b->mslot[id] = (short)slot;
     }
     for (int m = 0; m < 12; ++m)
-        memcpy(&b->h_mon[one * b->mslot[id] + (size_t)m * b->n_seg], tab + (size_t)m * ld, (size_t)b->n_seg * sizeof(double));
+        memcpy(&b->h_mon[one * slot + (size_t)m * b->n_seg], tab + (size_t)m * ld, (size_t)b->n_seg * sizeof(double));
     return upload_rows(b->mon, 12 * b->nmon_slots, 0, b->h_mon.data(), b->n_seg, b->n_seg, b->ntiles, 12 * b->nmon_slots);
 }
 
@@ -568,7 +827,7 @@ int hsp2g_set_state(hsp2g_batch *b, const double *st, int64_t ld) {
     if (!b || !st) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
-    CU(cudaStreamSynchronize(b->comp));
+    if (wait_last_launch(b)) return 1;
     if (upload_rows(b->segblk, SB_ROWS, SB_STATE, st, ld, b->n_seg, b->ntiles, HSP2G_NSTATE)) return 1;
     b->have_state = true;
     return 0;
@@ -578,7 +837,7 @@ int hsp2g_get_state(hsp2g_batch *b, double *st, int64_t ld) {
     if (!b || !st) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
-    CU(cudaStreamSynchronize(b->comp));
+    if (wait_last_launch(b)) return 1;
     return download_rows(st, ld, b->segblk, SB_ROWS, SB_STATE, b->n_seg, b->ntiles, HSP2G_NSTATE);
 }
 
@@ -621,6 +880,9 @@ int hsp2g_set_forcing_layout(hsp2g_batch *b, int n_rows, const int32_t *ids, con
         if (row[ids[r]] >= 0) return fail("forcing id %d listed twice", ids[r]);
         row[ids[r]] = (short)r;
     }
+    if (b->met && n_rows != b->nf)
+        return fail("the shared met table holds %d rows per interval: switch shared-met mode off (hsp2g_set_shared_forcing with "
+                    "n_stations = 0) before changing the number of forcing rows", b->nf);
     memcpy(b->frow, row, sizeof row);
     memcpy(b->ffill, fill, sizeof(double) * HSP2G_NFORC);
     b->nf = n_rows;
@@ -678,39 +940,69 @@ int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *ids) {
     return 0;
 }
 
-int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, void *stream) {
+int hsp2g_set_series_layout(hsp2g_batch *b, int layout) {
+    if (!b) return fail("null batch");
+    if (layout != HSP2G_TILED && layout != HSP2G_PLAIN) return fail("layout must be HSP2G_TILED or HSP2G_PLAIN");
+    b->plain = layout == HSP2G_PLAIN;
+    return 0;
+}
+
+int hsp2g_set_forcing_dtype(hsp2g_batch *b, int dtype) {
+    if (!b) return fail("null batch");
+    if (dtype != HSP2G_F64 && dtype != HSP2G_F32) return fail("forcing dtype must be HSP2G_F64 or HSP2G_F32");
+    b->forc_f32 = dtype == HSP2G_F32;
+    return 0;
+}
+
+int hsp2g_run_device_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, int64_t ldf, void *d_out, int64_t ldo,
+                        void *stream) {
     if (check_ready(b, t0, nsteps)) return 1;
     if (b->nf > 0 && !d_forc && !b->met) return fail("null forcing pointer");
     if (b->ns > 0 && !d_out) return fail("null output pointer");
     if (((uintptr_t)d_forc | (uintptr_t)d_out) & 15) return fail("device series must be 16-byte aligned (TMA bulk copies)");
+    if (b->plain) {
+        if ((b->nf > 0 && !b->met && ldf < b->n_pad) || (b->ns > 0 && ldo < b->n_pad))
+            return fail("PLAIN device series need rows of at least %lld elements (32 x tiles)", (long long)b->n_pad);
+        if ((ldf & 3) || (ldo & 3)) return fail("PLAIN row lengths must be multiples of 4 elements (16-byte rows)");
+    }
     DeviceGuard g(b->device);
-    return launch(b, t0, nsteps, d_forc, d_out, stream ? (cudaStream_t)stream : b->comp);
+    return launch(b, t0, nsteps, d_forc, ldf, d_out, ldo, stream ? (cudaStream_t)stream : b->comp);
+}
+
+int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, void *stream) {
+    if (!b) return fail("null batch");
+    return hsp2g_run_device_ld(b, t0, nsteps, d_forc, b->n_pad, d_out, b->n_pad, stream);
 }
 
 void *hsp2g_batch_stream(hsp2g_batch *b) { return b ? (void *)b->comp : nullptr; }
 
-int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, double *h_out) {
+int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_forc, int64_t ldf, void *h_out, int64_t ldo) {
     if (check_ready(b, t0, nsteps)) return 1;
     if (b->nf > 0 && !h_forc && !b->met) return fail("null forcing buffer");
     if (b->met) h_forc = nullptr;  // shared-met mode: nothing to copy in
     if (b->ns > 0 && !h_out) return fail("null output buffer");
+    if (b->plain && ((h_forc && ldf < b->n_seg) || (b->ns > 0 && ldo < b->n_seg))) return fail("ld < n_seg");
     DeviceGuard g(b->device);
     Slot &s = b->slot[b->next_slot];
     b->next_slot ^= 1;
-    const size_t row = (size_t)b->n_pad * sizeof(double);
-    const size_t need_f = b->met ? 0 : row * (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0);
-    const size_t need_o = row * (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0) / (b->out_f32 ? 2 : 1);
+    const size_t fesz = b->forc_f32 ? 4 : 8, osz = b->out_f32 ? 4 : 8;
+    const size_t frows = (size_t)nsteps * (size_t)(b->nf > 0 ? b->nf : 0), orows = (size_t)nsteps * (size_t)(b->ns > 0 ? b->ns : 0);
+    const size_t need_f = h_forc ? (size_t)b->n_pad * fesz * frows : 0;
+    const size_t need_o = (size_t)b->n_pad * osz * orows;
     if (need_f > s.cap_f || need_o > s.cap_o) {
         CU(cudaEventSynchronize(s.d2h_done));
         if (need_f > s.cap_f) {
             cudaFree(s.forc);
             s.forc = nullptr;
+            s.cap_f = 0;
             CU(cudaMalloc((void **)&s.forc, need_f));
+            CU(cudaMemset(s.forc, 0, need_f));  // PLAIN: columns past n_seg of the last tile are never copied in; they read 0
             s.cap_f = need_f;
         }
         if (need_o > s.cap_o) {
             cudaFree(s.out);
             s.out = nullptr;
+            s.cap_o = 0;
             CU(cudaMalloc((void **)&s.out, need_o));
             s.cap_o = need_o;
         }
@@ -730,30 +1022,61 @@ int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_f
             CU(cudaEventSynchronize(s.d2h_done));
             cudaFree(s.agg);
             s.agg = nullptr;
+            s.cap_a = 0;
             CU(cudaMalloc((void **)&s.agg, need_a));
             s.cap_a = need_a;
         }
     }
-    // the slot is free once its previous outputs have left the device; host and device share the tile-major
-    // layout, so each direction is ONE contiguous copy
+    // the slot is free once its previous outputs have left the device.  TILED: host and device share the tile-major layout, each
+    // direction is ONE contiguous copy.  PLAIN: host rows are ld elements long, device rows n_pad: one strided (2-D) copy each
+    // way, contiguous when the host rows are n_pad long too.
     CU(cudaStreamWaitEvent(b->h2d, s.d2h_done, 0));
-    if (need_f) CU(cudaMemcpyAsync(s.forc, h_forc, need_f, cudaMemcpyHostToDevice, b->h2d));
+    if (need_f) {
+        if (!b->plain || ldf == b->n_pad)
+            CU(cudaMemcpyAsync(s.forc, h_forc, need_f, cudaMemcpyHostToDevice, b->h2d));
+        else
+            CU(cudaMemcpy2DAsync(s.forc, (size_t)b->n_pad * fesz, h_forc, (size_t)ldf * fesz, (size_t)b->n_seg * fesz, frows,
+                                 cudaMemcpyHostToDevice, b->h2d));
+    }
     CU(cudaEventRecord(s.h2d_done, b->h2d));
     CU(cudaStreamWaitEvent(b->comp, s.h2d_done, 0));
-    if (launch(b, t0, nsteps, s.forc, s.out, b->comp)) return 1;
+    if (launch(b, t0, nsteps, s.forc, b->n_pad, s.out, b->n_pad, b->comp)) return 1;
     if (nb) {
-        std::vector<int> local((size_t)nsteps);
-        for (int t = 0; t < nsteps; ++t) local[(size_t)t] = b->periods[(size_t)(t0 + t)] - b->periods[(size_t)t0];
-        if (hsp2g_aggregate_f32(b->device, (const float *)s.out, b->ntiles, nsteps, b->ns, local.data(), nb, s.agg, b->comp)) return 1;
+        AggArgs A;
+        A.src = (const float *)s.out;
+        A.dst = s.agg;
+#ifdef HSP2G_HOST_EMU
+        A.bin = b->periods.data() + t0;
+#else
+        A.bin = b->d_periods + t0;
+#endif
+        A.bin_base = b->periods[(size_t)t0];
+        A.plain = b->plain;
+        A.ld = b->n_pad;
+        A.n_threads = (long long)b->n_pad * b->ns;
+        A.nsteps = nsteps;
+        A.ns = b->ns;
+        A.nbins = nb;
+        if (run_aggregate(A, b->comp)) return 1;
     }
     CU(cudaEventRecord(s.k_done, b->comp));
     CU(cudaStreamWaitEvent(b->d2h, s.k_done, 0));
-    if (nb)
-        CU(cudaMemcpyAsync(h_out, s.agg, need_a, cudaMemcpyDeviceToHost, b->d2h));
-    else if (need_o)
-        CU(cudaMemcpyAsync(h_out, s.out, need_o, cudaMemcpyDeviceToHost, b->d2h));
+    const void *d_res = nb ? (const void *)s.agg : (const void *)s.out;
+    const size_t res_rows = nb ? (size_t)nb * b->ns * 3 : orows, res_bytes = nb ? need_a : need_o;
+    if (res_bytes) {
+        if (!b->plain || ldo == b->n_pad)
+            CU(cudaMemcpyAsync(h_out, d_res, res_bytes, cudaMemcpyDeviceToHost, b->d2h));
+        else
+            CU(cudaMemcpy2DAsync(h_out, (size_t)ldo * osz, d_res, (size_t)b->n_pad * osz, (size_t)b->n_seg * osz, res_rows,
+                                 cudaMemcpyDeviceToHost, b->d2h));
+    }
     CU(cudaEventRecord(s.d2h_done, b->d2h));
     return 0;
+}
+
+int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forc, double *h_out) {
+    if (!b) return fail("null batch");
+    return hsp2g_run_host_ld(b, t0, nsteps, h_forc, b->plain ? b->n_seg : b->n_pad, h_out, b->plain ? b->n_seg : b->n_pad);
 }
 
 int hsp2g_pack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, int64_t ld, double *dst) {
@@ -793,6 +1116,7 @@ int hsp2g_sync(hsp2g_batch *b) {
     CU(cudaStreamSynchronize(b->h2d));
     CU(cudaStreamSynchronize(b->comp));
     CU(cudaStreamSynchronize(b->d2h));
+    if (b->have_last) CU(cudaEventSynchronize(b->last_launch));
     return drain_timing(b);
 }
 
@@ -800,14 +1124,14 @@ int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld) {
     if (!b || !err) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
-    CU(cudaStreamSynchronize(b->comp));
+    if (wait_last_launch(b)) return 1;
     return download_rows(err, ld, b->segblk, SB_ROWS, SB_ERR, b->n_seg, b->ntiles, HSP2G_NERR);
 }
 
 int hsp2g_reset_errors(hsp2g_batch *b) {
     if (!b) return fail("null batch");
     DeviceGuard g(b->device);
-    CU(cudaStreamSynchronize(b->comp));
+    if (wait_last_launch(b)) return 1;
     CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
                     (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
     return 0;
@@ -929,40 +1253,122 @@ int hsp2g_aggregate_f32(int device, const float *d_src, int64_t ntiles, int32_t 
     AggArgs A;
     A.src = d_src;
     A.dst = d_dst;
+    A.bin_base = 0;
+    A.plain = 0;
+    A.ld = 0;
     A.n_threads = (long long)ntiles * ns * LAND_TILE;
     A.nsteps = nsteps;
     A.ns = ns;
     A.nbins = nbins;
 #ifdef HSP2G_HOST_EMU
-    (void)stream;
     A.bin = bin_of_step;
-    for (long long j = 0; j < A.n_threads; ++j) agg_thread(A, j);
-    return 0;
+    return run_aggregate(A, (cudaStream_t)stream);
 #else
+    // stand-alone use: the bins travel to the device for this call (hsp2g_run_host keeps the whole run's periods resident)
     int *d_bin = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CU(cudaMallocAsync((void **)&d_bin, (size_t)nsteps * sizeof(int), st));
-    CU(cudaMemcpyAsync(d_bin, bin_of_step, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st));
-    A.bin = d_bin;
-    aggregate_kernel<<<(unsigned)((A.n_threads + 127) / 128), 128, 0, st>>>(A);
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(d_bin, st);
-    if (e != cudaSuccess) return fail("aggregate launch failed: %s", cudaGetErrorString(e));
-    return 0;
+    CU(cudaMalloc((void **)&d_bin, (size_t)nsteps * sizeof(int)));
+    cudaError_t e = cudaMemcpyAsync(d_bin, bin_of_step, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (e != cudaSuccess)
+        rc = fail("cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    else {
+        A.bin = d_bin;
+        rc = run_aggregate(A, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(d_bin);
+    return rc;
 #endif
 }
 
 int hsp2g_set_output_periods(hsp2g_batch *b, int64_t n, const int32_t *period_of_step) {
     if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
     if (n == 0 || !period_of_step) {  // back to series
+        CU(cudaDeviceSynchronize());
         b->periods.clear();
+        cudaFree(b->d_periods);
+        b->d_periods = nullptr;
         return 0;
     }
     if (n < 0) return fail("n must be >= 0");
     for (int64_t t = 0; t < n; ++t)
         if (period_of_step[t] < 0 || (t && (period_of_step[t] < period_of_step[t - 1] || period_of_step[t] > period_of_step[t - 1] + 1)))
             return fail("period_of_step must start at >= 0 and grow by 0 or 1 from interval to interval");
+    // the whole run's periods live on the device: a chunk's aggregation reads them in place, no per-chunk host copy
+    CU(cudaDeviceSynchronize());
+    cudaFree(b->d_periods);
+    b->d_periods = nullptr;
+    CU(cudaMalloc((void **)&b->d_periods, (size_t)n * sizeof(int)));
+    CU(cudaMemcpy(b->d_periods, period_of_step, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     b->periods.assign(period_of_step, period_of_step + n);
+    return 0;
+}
+
+// ---- kernels built for one batch (hspsquared_b200/jit.py).  The image is a cubin for sm_100a whose entry point `entry` takes
+// the launch record by value and whose global `<entry>_info` (16 x u64) states what was fixed at compile time; launch() uses the
+// kernel only while that still matches the batch (jit_matches).
+int hsp2g_set_kernel_image(hsp2g_batch *b, const void *image, size_t nbytes, const char *entry, const char *display_name) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    CU(cudaDeviceSynchronize());
+    drop_kernel_image(b);
+    if (!image || !nbytes) return 0;  // back to the library's own kernels
+    if (!entry) return fail("null entry point name");
+    const std::string info_name = std::string(entry) + "_info";
+    unsigned long long info[JI_N];
+#ifdef HSP2G_HOST_EMU
+    // test double: `image` is the path of a host-compiled shared object with the same entry point
+    const std::string path((const char *)image, nbytes);
+    b->jit.dl = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!b->jit.dl) return fail("dlopen(%s): %s", path.c_str(), dlerror());
+    b->jit.fn = (void (*)(const LandLaunch &))dlsym(b->jit.dl, entry);
+    const void *ip = dlsym(b->jit.dl, info_name.c_str());
+    if (!b->jit.fn || !ip) {
+        drop_kernel_image(b);
+        return fail("%s or %s missing from %s", entry, info_name.c_str(), path.c_str());
+    }
+    memcpy(info, ip, sizeof info);
+    b->jit.resident = 1;
+#else
+    const Driver &d = driver();
+    if (!d.ok) return fail("%s", d.why.c_str());
+    CUresult r = d.ModuleLoadData(&b->jit.mod, image);
+    if (r != CUDA_SUCCESS) return fail("cuModuleLoadData: %s", cu_str(r));
+    CUdeviceptr ip = 0;
+    size_t isz = 0;
+    if ((r = d.ModuleGetFunction(&b->jit.fn, b->jit.mod, entry)) != CUDA_SUCCESS ||
+        (r = d.ModuleGetGlobal(&ip, &isz, b->jit.mod, info_name.c_str())) != CUDA_SUCCESS || isz != sizeof info) {
+        drop_kernel_image(b);
+        return fail("kernel image lacks %s / %s: %s", entry, info_name.c_str(), cu_str(r));
+    }
+    CU(cudaMemcpy(info, (const void *)ip, sizeof info, cudaMemcpyDeviceToHost));
+#endif
+    if (info[JI_MAGIC] != HSP2G_JIT_MAGIC || info[JI_LAUNCH_BYTES] != sizeof(LandLaunch) || info[JI_SBROWS] != SB_ROWS ||
+        info[JI_BLOCK] != LAND_BLOCK) {
+        drop_kernel_image(b);
+        return fail("kernel image was built against other kernel sources than this library (launch record %llu vs %zu bytes)",
+                    info[JI_LAUNCH_BYTES], sizeof(LandLaunch));
+    }
+#ifndef HSP2G_HOST_EMU
+    if (info[JI_SMEM] > 48 * 1024 &&
+        (r = driver().FuncSetAttribute(b->jit.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)info[JI_SMEM])) != CUDA_SUCCESS) {
+        drop_kernel_image(b);
+        return fail("cuFuncSetAttribute(max dynamic shared memory = %llu): %s", info[JI_SMEM], cu_str(r));
+    }
+    int per_sm = 0, sms = 0;
+    r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->jit.fn, LAND_BLOCK, (size_t)info[JI_SMEM]);
+    if (r != CUDA_SUCCESS || per_sm <= 0) {
+        drop_kernel_image(b);
+        return fail("the batch's kernel does not fit an SM (%llu bytes of shared memory): %s", info[JI_SMEM], cu_str(r));
+    }
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    b->jit.resident = per_sm * sms;
+#endif
+    memcpy(b->jit.info, info, sizeof info);
+    b->jit.name = display_name ? display_name : entry;
+    b->jit.on = true;
     return 0;
 }
 
@@ -997,14 +1403,27 @@ int hsp2g_kernel_stats(hsp2g_batch *b, int64_t *launches, double *kernel_ms) {
 
 const char *hsp2g_kernel_name(const hsp2g_batch *b) { return b ? b->kname : ""; }
 
-void *hsp2g_host_alloc(size_t bytes) {
+void *hsp2g_host_alloc_flags(size_t bytes, unsigned flags) {
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    unsigned f = cudaHostAllocDefault;
+    if (flags & HSP2G_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (flags & HSP2G_HOST_PORTABLE) f |= cudaHostAllocPortable;
+    cudaError_t e = cudaHostAlloc(&p, bytes, f);
     if (e != cudaSuccess) {
         fail("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
     return p;
+}
+void *hsp2g_host_alloc(size_t bytes) { return hsp2g_host_alloc_flags(bytes, 0); }
+int hsp2g_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail("null argument");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int hsp2g_host_unregister(void *p) {
+    if (p) CU(cudaHostUnregister(p));
+    return 0;
 }
 int hsp2g_host_free(void *p) {
     if (p) CU(cudaFreeHost(p));

@@ -3,10 +3,11 @@
 #include "land_kernels.cuh"
 #include "launch.h"
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false, class FW = DynFlags>
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, IMPLND_HOT, implnd_ncold<HOURLY, IO>(), SHARED);
-    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, FW>;
+    typedef typename LayFor<IO>::type LAY;
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, IMPLND_HOT, implnd_ncold<HOURLY, IO>(), SHARED, L.forc_f32 ? 4 : 8);
+    auto k = implnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, DynFlags, LAY>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -18,8 +19,6 @@ static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 
 cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SI = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_IWATER);
-    cudaError_t e_hot = cudaSuccess;
-    if (hsp2g_launch_implnd_hot(L, hourly, sub_pref, st, name, grid_out, &e_hot)) return e_hot;  // hot_kernels.cu
     if (L.met)
         return hourly ? launch_one<-1, true, DynIO, 128, true>(L, sub_pref, st, name, "implnd_kernel<generic,hourly,io=dynamic,met=shared>", grid_out)
                       : launch_one<-1, false, DynIO, 128, true>(L, sub_pref, st, name, "implnd_kernel<generic,subhourly,io=dynamic,met=shared>", grid_out);

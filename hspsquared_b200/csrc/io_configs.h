@@ -61,6 +61,7 @@ typedef StaticIO<FM_MET6_GATMP, SAVE_CBP10(olo), SAVE_CBP10(ohi)> IO_FullChainCb
 // does the launch record describe exactly this static configuration (rows in ascending id order)?
 template <class IO>
 static inline bool io_matches(const LandLaunch &L) {
+    if (L.plain || L.forc_f32) return false;  // the library's static kernels are built for the TILED float64 layout
     if (L.nf != IO::NF || L.ns != IO::NS || (L.out_f32 != 0) != IO::F32) return false;
     int r = 0;
     for (int id = 0; id < HSP2G_NFORC; ++id) {
@@ -76,6 +77,16 @@ static inline bool io_matches(const LandLaunch &L) {
     }
     return true;
 }
+
+// layout policy of the library's own kernels: static row sets are TILED float64, the general kernels follow the launch record
+template <class IO>
+struct LayFor {
+    typedef TiledLay type;
+};
+template <>
+struct LayFor<DynIO> {
+    typedef DynLay type;
+};
 
 // option word of test10's PERLND 1 with SNOW + PWATER (ICEFG, CSNOFG, PWATER sees ICEFG; CEPSC, UZSN, NSUR, LZETP follow their
 // monthly tables; everything else off: energy-balance snow, Newton routing, UZINF1, IFFCFG 1, VLEFG 1)

@@ -9,9 +9,14 @@
 //                                       HSP2G_NSTATE carried states (read at chunk start, written at chunk end),
 //                                       HSP2G_NERR int64 error counters
 //   mon    [tile][slot*12 + month][32]  monthly tables that at least one segment uses
-//   forc   [tile][t][row][32]           time-major forcings of the chunk: interval t of a tile is nf*256
+//   forc   TILED  [tile][t][row][32]    time-major forcings of the chunk: interval t of a tile is nf*256
 //                                       contiguous bytes -> ONE 1-D TMA bulk copy (cp.async.bulk) per warp-interval
-//   out    [tile][t][row][32]           time-major saved series: a warp stores 256 contiguous bytes per row
+//          PLAIN  [t][row][ld]          the reference's own orientation ([t][segment] per series, ld >= 32*ntiles): interval t
+//                                       of a tile is a box of nf rows x 32 segments -> ONE tensor-map TMA copy
+//                                       (cp.async.bulk.tensor.3d) per warp-interval; no re-tiling on either side of PCIe
+//   out    TILED  [tile][t][row][32]    time-major saved series: a warp stores 256 contiguous bytes per row
+//          PLAIN  [t][row][ld]          ... the same 256-byte stores, rows ld elements apart
+//          forcings may be float32 (widened on the way out of shared memory), saved series float32 or float64
 //   cal    [steps+1]                    shared per-interval calendar record (warp-uniform loads)
 //
 // The last tile is padded to 32 lanes with copies of the last real segment (hsp2g_api.cu), so padded lanes run
@@ -30,6 +35,14 @@
 #define LAND_WARPS (LAND_BLOCK / LAND_TILE)
 #ifndef PIPE_STAGES
 #define PIPE_STAGES 2  // one interval of prefetch covers HBM latency (an interval takes a warp microseconds)
+#endif
+
+#ifdef HSP2G_HOST_EMU
+#define LAND_SMEM_DECL double *smem = ring
+#define HSP_MAXNREG(n)
+#else
+#define LAND_SMEM_DECL extern __shared__ __align__(128) double smem[]
+#define HSP_MAXNREG(n) __maxnreg__(n)
 #endif
 
 #define SB_FLAGS 0
@@ -88,7 +101,11 @@ struct LandLaunch {
     unsigned prog_base;                // their common value when this launch starts
     int first_chunk;  // 1 when this chunk starts at interval 0 of the run
     int nf, ns;       // forcing rows / saved rows per interval
-    int out_f32;      // saved series are float32 [tile][t][row][32] instead of float64
+    int out_f32;      // saved series are float32 instead of float64
+    int plain;        // series layout: 0 = TILED [tile][t][row][32], 1 = PLAIN [t][row][ld]
+    int forc_f32;     // forcing series are float32 (exactly representable inputs, e.g. WDM / HDF5 float32 stores)
+    int tmap_ok;      // PLAIN: `tmap` describes forc (else the rows of an interval are fetched by nf 1-D bulk copies)
+    long long forc_ld, out_ld;  // PLAIN: elements between consecutive rows of forc / out
     int mon_rows;     // 12 * number of monthly slots (row count of one tile's table block)
     unsigned act;
     unsigned opts;
@@ -99,6 +116,8 @@ struct LandLaunch {
     double ffill[HSP2G_NFORC];  // value read when the id is absent
     short srow[HSP2G_NOUT];     // output id -> row in out, or -1 (not saved)
     short mslot[HSP2G_NMON];    // monthly table id -> slot in mon, or -1
+    // PLAIN: CUtensorMap of forc as a 3-D tensor (segment, row, interval), box = 32 x nf x 1 (hsp2g_api.cu make_tmap)
+    alignas(64) unsigned long long tmap[16];
 };
 
 // A carried scalar that lives in this lane's column of the warp's shared-memory scratch instead of a register.
@@ -201,7 +220,7 @@ struct DynIO {
     static constexpr unsigned long long FMASK = 0, S0 = 0, S1 = 0, S2 = 0;
     static constexpr int NF = 0, NS = 0;
 };
-constexpr int ce_popc(unsigned long long x) { return x ? (int)(x & 1ull) + ce_popc(x >> 1) : 0; }
+__host__ __device__ constexpr int ce_popc(unsigned long long x) { return x ? (int)(x & 1ull) + ce_popc(x >> 1) : 0; }
 // forcing ids < 64 in FM; output ids 0..63 in SM0, 64..127 in SM1, 128..191 in SM2
 template <unsigned long long FM, unsigned long long SM0, unsigned long long SM1, bool F32_ = false, unsigned long long SM2 = 0>
 struct StaticIO {
@@ -216,6 +235,26 @@ template <class IO>
 __host__ __device__ constexpr bool io_saved(int oid) {
     return ((oid < 64 ? IO::S0 : oid < 128 ? IO::S1 : IO::S2) >> (oid & 63)) & 1ull;
 }
+// ---- series layout policy: where interval t, row r of a tile lives (see the header of this file) and the element type
+// of the forcings.  StaticLay fixes both at compile time (kernels built for one batch, hspsquared_b200/jit.py);
+// DynLay reads them from the launch record (the general kernels of the library).
+struct DynLay {
+    static constexpr bool STATIC = false, PLAIN = false, F32IN = false;
+};
+template <bool PLAIN_, bool F32IN_>
+struct StaticLay {
+    static constexpr bool STATIC = true, PLAIN = PLAIN_, F32IN = F32IN_;
+};
+typedef StaticLay<false, false> TiledLay;
+template <class LAY>
+__device__ __forceinline__ bool lay_plain(const LandLaunch &L) {
+    return LAY::STATIC ? LAY::PLAIN : (L.plain != 0);
+}
+template <class LAY>
+__device__ __forceinline__ bool lay_f32in(const LandLaunch &L) {
+    return LAY::STATIC ? LAY::F32IN : (L.forc_f32 != 0);
+}
+
 #ifndef HSP2G_HOST_EMU
 // ---- forcing pipeline: a PIPE_STAGES-deep ring per warp in shared memory, filled by the TMA engine.  Lane 0 arms
 // the stage's mbarrier with the byte count and issues one cp.async.bulk for the whole interval (nf rows x 256 B,
@@ -252,38 +291,53 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 
-// SHARED = false: per-segment forcings, one TMA bulk copy per warp-interval (above).
+// 3-D tensor-map copy: the box at (segment c0, row 0, interval c2) of the PLAIN forcing tensor -> shared memory
+__device__ __forceinline__ void tensor_g2s(unsigned dst, const void *tmap, int c0, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(0), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+// SHARED = false: per-segment forcings, one TMA copy per warp-interval: a 1-D bulk copy of the tile's contiguous interval
+//                 (TILED) or a tensor-map copy of the interval's [nf rows x 32 segments] box (PLAIN).
 // SHARED = true : forcings come from a small table of met-station series shared by all segments; each lane gathers
 //                 its station's value of every row with an 8-byte cp.async (LDGSTS) into the same ring, one group per
 //                 interval, and forcing() multiplies by the segment's MFACTOR at the point of use.  Lanes only ever
 //                 touch their own ring column, so no barrier of any kind is involved.
-template <bool SHARED>
+template <bool SHARED, class LAY = TiledLay>
 struct PipeT {
-    double *ring;       // this warp's ring (generic pointer into shared memory)
-    unsigned ring_s;    // its shared-space address
-    unsigned bar_s;     // shared-space address of this warp's first mbarrier
-    const double *src;  // SHARED ? met + station of this lane : forcings of the current tile (forc + tile*nsteps*nf*32)
-    int stage_elems;    // nf * 32
-    int nf, nst;        // SHARED: rows per interval, stations
-    int t_end;          // end of the current task (no copies are issued past it)
-    int st;             // stage of the current interval
-    unsigned ph;        // its phase parity
+    unsigned char *ring;  // this warp's ring (generic pointer into shared memory)
+    unsigned ring_s;      // its shared-space address
+    unsigned bar_s;       // shared-space address of this warp's first mbarrier
+    const LandLaunch *Lp;
+    const unsigned char *src;  // SHARED: met + station of this lane; TILED: forcings of the current tile; PLAIN: column tile*32 of forc
+    int stage_bytes;      // nf * 32 * element size
+    int nf, nst;          // rows per interval; SHARED: stations
+    int esz;              // forcing element size in bytes (8, or 4 for float32 forcings)
+    int tile;             // PLAIN: current tile
+    int t_end;            // end of the current task (no copies are issued past it)
+    int st;               // stage of the current interval
+    unsigned ph;          // its phase parity
     int lane;
 
     // smem layout: [warp][PIPE_STAGES*nf*32 ring | nhot*32 hot parameters (+ nf*32 MFACTORs when SHARED) | ncold*32 cold
     // state], then the mbarriers
-    __device__ __forceinline__ void init(double *smem, int wib, int lane_, int nf_, int nhot, int ncold, int nst_) {
+    __device__ __forceinline__ void init(const LandLaunch &L, double *smem, int wib, int lane_, int nf_, int nhot, int ncold) {
+        Lp = &L;
         nf = nf_;
-        nst = nst_;
-        stage_elems = nf * LAND_TILE;
-        const int warp_elems = PIPE_STAGES * stage_elems + (nhot + ncold) * LAND_TILE;
-        ring = smem + (size_t)wib * warp_elems;
+        nst = L.n_stations;
+        esz = (!SHARED && lay_f32in<LAY>(L)) ? 4 : 8;
+        stage_bytes = nf * LAND_TILE * esz;
+        const int warp_bytes = PIPE_STAGES * stage_bytes + (nhot + ncold) * LAND_TILE * 8;
+        ring = reinterpret_cast<unsigned char *>(smem) + (size_t)wib * warp_bytes;
         ring_s = smem_u32(ring);
-        bar_s = smem_u32(smem + (size_t)LAND_WARPS * warp_elems) + wib * PIPE_STAGES * 8;
+        bar_s = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)LAND_WARPS * warp_bytes) + wib * PIPE_STAGES * 8;
         st = 0;
         ph = 0;
         lane = lane_;
         t_end = 0;
+        tile = 0;
         src = nullptr;
         if (!SHARED) {
             if (lane == 0) {
@@ -297,22 +351,38 @@ struct PipeT {
     __device__ __forceinline__ void issue(int t, int s) {  // SHARED: every lane; else lane 0 only
         if (SHARED) {
             if (t < t_end) {
-                double *dst = ring + s * stage_elems + lane;
-                const double *g = src + (size_t)t * nf * nst;
+                double *dst = reinterpret_cast<double *>(ring + s * stage_bytes) + lane;
+                const double *g = reinterpret_cast<const double *>(src) + (size_t)t * nf * nst;
                 for (int r = 0; r < nf; ++r) cp_async8(dst + r * LAND_TILE, g + (size_t)r * nst);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");  // empty groups keep the wait arithmetic uniform
         } else if (t < t_end) {
-            const unsigned bytes = (unsigned)stage_elems * 8u;
-            mbar_expect_tx(bar_s + s * 8, bytes);
-            bulk_g2s(ring_s + (unsigned)s * bytes, src + (size_t)t * stage_elems, bytes, bar_s + s * 8);
+            const unsigned bytes = (unsigned)stage_bytes;
+            const unsigned bar = bar_s + s * 8, dst = ring_s + (unsigned)s * bytes;
+            mbar_expect_tx(bar, bytes);
+            if (!lay_plain<LAY>(*Lp))
+                bulk_g2s(dst, src + (size_t)t * bytes, bytes, bar);
+            else if (Lp->tmap_ok)
+                tensor_g2s(dst, Lp->tmap, tile * LAND_TILE, t, bar);
+            else {  // row by row: nf bulk copies of one 32-segment row each
+                const size_t ldb = (size_t)Lp->forc_ld * esz;
+                const unsigned rowb = (unsigned)(LAND_TILE * esz);
+                for (int r = 0; r < nf; ++r) bulk_g2s(dst + r * rowb, src + ((size_t)t * nf + r) * ldb, rowb, bar);
+            }
         }
     }
-    // a new task: intervals [t0, t1).  Every stage is free here (the previous task consumed all it issued), so the first
-    // PIPE_STAGES intervals go out at once, starting at the current stage.
-    __device__ __forceinline__ void begin_task(const double *src_, int t0, int t1) {
-        src = src_;
-        t_end = stage_elems > 0 ? t1 : 0;
+    // a new task: intervals [t0, t1) of `tile`.  Every stage is free here (the previous task consumed all it issued), so the
+    // first PIPE_STAGES intervals go out at once, starting at the current stage.
+    __device__ __forceinline__ void begin_task(int tile_, int t0, int t1) {
+        const LandLaunch &L = *Lp;
+        tile = tile_;
+        if (SHARED)
+            src = reinterpret_cast<const unsigned char *>(L.met + L.station[tile * LAND_TILE + lane]);
+        else if (lay_plain<LAY>(L))
+            src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * LAND_TILE * esz;
+        else
+            src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * L.nsteps * stage_bytes;
+        t_end = stage_bytes > 0 ? t1 : 0;
         if (SHARED || lane == 0) {
             int s = st;
             for (int k = 0; k < PIPE_STAGES; ++k) {
@@ -321,15 +391,15 @@ struct PipeT {
             }
         }
     }
-    // wait for the current interval's forcings; returns this lane's column of the stage
-    __device__ __forceinline__ const double *acquire() {
+    // wait for the current interval's forcings; returns this lane's cell of row 0 of the stage
+    __device__ __forceinline__ const unsigned char *acquire() {
         if (SHARED)
             asm volatile("cp.async.wait_group %0;\n" ::"n"(PIPE_STAGES - 1) : "memory");
         else if (t_end > 0)
             mbar_wait(bar_s + st * 8, ph);
-        return ring + st * stage_elems + lane;
+        return ring + st * stage_bytes + lane * esz;
     }
-    __device__ __forceinline__ double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
+    __device__ __forceinline__ double *hot_area() const { return reinterpret_cast<double *>(ring + PIPE_STAGES * stage_bytes); }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
     __device__ __forceinline__ void release(int t) {
         if (SHARED) {
@@ -399,32 +469,47 @@ struct Sched {
 #else
 // test double: same interface, synchronous copies (no TMA on the host); one "thread" at a time, which walks the
 // sub-chunks of its own tile in order (no tickets)
-template <bool SHARED>
+template <bool SHARED, class LAY = TiledLay>
 struct PipeT {
-    double *ring;
-    const double *src;
-    int stage_elems, lane, t_cur, nf, nst;
-    void init(double *smem, int, int lane_, int nf_, int, int, int nst_) {
-        ring = smem;
+    unsigned char *ring;
+    const LandLaunch *Lp;
+    const unsigned char *src;
+    int stage_bytes, lane, t_cur, nf, nst, esz, tile;
+    void init(const LandLaunch &L, double *smem, int, int lane_, int nf_, int, int) {
+        Lp = &L;
+        ring = reinterpret_cast<unsigned char *>(smem);
         nf = nf_;
-        nst = nst_;
-        stage_elems = nf * LAND_TILE;
+        nst = L.n_stations;
+        esz = (!SHARED && lay_f32in<LAY>(L)) ? 4 : 8;
+        stage_bytes = nf * LAND_TILE * esz;
         lane = lane_;
     }
-    void begin_task(const double *src_, int t0, int) {
-        src = src_;
+    void begin_task(int tile_, int t0, int) {
+        const LandLaunch &L = *Lp;
+        tile = tile_;
+        if (SHARED)
+            src = reinterpret_cast<const unsigned char *>(L.met + L.station[tile * LAND_TILE + lane]);
+        else if (lay_plain<LAY>(L))
+            src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * LAND_TILE * esz;
+        else
+            src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * L.nsteps * stage_bytes;
         t_cur = t0;
     }
-    const double *acquire() {
-        if (SHARED)
-            for (int r = 0; r < nf; ++r) ring[r * LAND_TILE + lane] = src[((size_t)t_cur * nf + r) * nst];
-        else
-            for (int i = lane; i < stage_elems; i += LAND_TILE) ring[i] = src[(size_t)t_cur * stage_elems + i];
-        return ring + lane;
+    const unsigned char *acquire() {
+        if (SHARED) {
+            const double *g = reinterpret_cast<const double *>(src);
+            for (int r = 0; r < nf; ++r) reinterpret_cast<double *>(ring)[r * LAND_TILE + lane] = g[((size_t)t_cur * nf + r) * nst];
+        } else if (lay_plain<LAY>(*Lp)) {
+            const size_t ldb = (size_t)Lp->forc_ld * esz;
+            for (int r = 0; r < nf; ++r)
+                memcpy(ring + (size_t)r * LAND_TILE * esz, src + ((size_t)t_cur * nf + r) * ldb, (size_t)LAND_TILE * esz);
+        } else
+            memcpy(ring, src + (size_t)t_cur * stage_bytes, (size_t)stage_bytes);
+        return ring + lane * esz;
     }
     void release(int t) { t_cur = t + 1; }
     void end_task() {}
-    double *hot_area() const { return ring + PIPE_STAGES * stage_elems; }
+    double *hot_area() const { return reinterpret_cast<double *>(ring + PIPE_STAGES * stage_bytes); }
 };
 struct Sched {
     const LandLaunch &L;
@@ -464,10 +549,11 @@ struct StaticFlags {
     static constexpr unsigned long long W = W_;
 };
 
-template <class IO_, unsigned long long HOT_, bool SHARED_ = false, class FW_ = DynFlags>
+template <class IO_, unsigned long long HOT_, bool SHARED_ = false, class FW_ = DynFlags, class LAY_ = TiledLay>
 struct Seg {
     typedef IO_ IO;
     typedef FW_ FW;
+    typedef LAY_ LAY;
     static constexpr bool SHARED = SHARED_;
     static constexpr unsigned long long HOT = HOT_;
     static constexpr int NHOT = ce_popc(HOT_);
@@ -476,13 +562,14 @@ struct Seg {
     const double *hot;     // this lane's column of the staged hot parameters (shared memory)
     const double *mfacp;   // SHARED: this lane's column of the staged MFACTORs, one row per forcing row (shared memory)
     const double *monp;    // this lane's column of the tile's monthly tables
-    unsigned char *outp;   // this lane's cell of out[tile][t][0] (float64 or float32 rows)
-    const double *stage;   // this lane's column of the current forcing stage (shared memory)
+    unsigned char *outp;   // this lane's cell of row 0 of the current interval of out (float64 or float32 rows)
+    const unsigned char *stage;  // this lane's cell of row 0 of the current forcing stage (shared memory; float64 or float32 rows)
     const CalStep *calp;   // calendar record of the current interval (warp-uniform)
     unsigned long long fl;
     unsigned calfl;        // HSP2G_CAL_* of the current interval
     unsigned calfl_next;   // ... of the next one, loaded an interval ahead (an L2 round trip off the critical path)
-    int out_step;          // bytes between consecutive intervals of out
+    long long out_step;    // bytes between consecutive intervals of out
+    long long out_row;     // bytes between consecutive rows of out (PLAIN; TILED: 32 elements, a compile-time constant)
 
     // view of `tile` for the task that starts at interval t0 of the launch
     __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane, int t0, double *hot_area) : L(l) {
@@ -490,8 +577,16 @@ struct Seg {
         HSP_PIN(sb);
         monp = l.mon + ((size_t)tile * l.mon_rows * LAND_TILE + lane);
         const int osz = out_is_f32() ? 4 : 8;
-        out_step = (IO::STATIC ? IO::NS : l.ns) * LAND_TILE * osz;
-        outp = reinterpret_cast<unsigned char *>(l.out) + (((size_t)tile * l.nsteps + t0) * out_step + lane * osz);
+        const int nsr = IO::STATIC ? IO::NS : l.ns;
+        if (lay_plain<LAY>(l)) {
+            out_row = l.out_ld * osz;
+            out_step = out_row * nsr;
+            outp = reinterpret_cast<unsigned char *>(l.out) + ((size_t)t0 * out_step + ((size_t)tile * LAND_TILE + lane) * osz);
+        } else {
+            out_row = LAND_TILE * osz;
+            out_step = (long long)nsr * LAND_TILE * osz;
+            outp = reinterpret_cast<unsigned char *>(l.out) + (((size_t)tile * l.nsteps + t0) * out_step + lane * osz);
+        }
         HSP_PIN(outp);
         calp = l.cal + t0;
         double *h = hot_area + lane;
@@ -511,7 +606,7 @@ struct Seg {
         calfl = 0;
         calfl_next = calp->flags;
     }
-    __device__ __forceinline__ void begin_step(const double *stage_) {
+    __device__ __forceinline__ void begin_step(const unsigned char *stage_) {
         stage = stage_;
         calfl = calfl_next;
         calfl_next = calp[1].flags;  // the calendar holds steps+1 records (hsp2g_set_calendar), so t+1 exists
@@ -522,10 +617,17 @@ struct Seg {
     }
     __device__ __forceinline__ bool out_is_f32() const { return IO::STATIC ? IO::F32 : (L.out_f32 != 0); }
     __device__ __forceinline__ void store_out(int r, double v) const {
+        // TILED: rows at immediate offsets; PLAIN: rows out_row bytes apart (one multiply-add per store)
+        unsigned char *q = outp + ((LAY::STATIC && !LAY::PLAIN) ? (long long)r * LAND_TILE * (out_is_f32() ? 4 : 8) : r * out_row);
         if (out_is_f32())
-            __stcs(reinterpret_cast<float *>(outp) + r * LAND_TILE, (float)v);
+            __stcs(reinterpret_cast<float *>(q), (float)v);
         else
-            __stcs(reinterpret_cast<double *>(outp) + r * LAND_TILE, v);
+            __stcs(reinterpret_cast<double *>(q), v);
+    }
+    // forcing row r of the current interval (this lane's segment), widened when the series are float32
+    __device__ __forceinline__ double stage_row(int r) const {
+        if (!SHARED && lay_f32in<LAY>(L)) return (double)reinterpret_cast<const float *>(stage)[r * LAND_TILE];
+        return reinterpret_cast<const double *>(stage)[r * LAND_TILE];
     }
     __device__ __forceinline__ bool flag(int bit) const { return ((FW::KNOWN ? FW::W : fl) >> bit) & 1ull; }
     __device__ __forceinline__ double par(int id) const {
@@ -540,13 +642,13 @@ struct Seg {
         if (IO::STATIC) {
             if ((IO::FMASK >> id) & 1ull) {
                 const int r = hsp_popc(IO::FMASK & ((1ull << id) - 1ull));
-                return SHARED ? stage[r * LAND_TILE] * mfacp[r * LAND_TILE] : stage[r * LAND_TILE];
+                return SHARED ? stage_row(r) * mfacp[r * LAND_TILE] : stage_row(r);
             }
             return L.ffill[id];
         }
         const int r = L.frow[id];
         if (r < 0) return L.ffill[id];
-        return SHARED ? stage[r * LAND_TILE] * mfacp[r * LAND_TILE] : stage[r * LAND_TILE];
+        return SHARED ? stage_row(r) * mfacp[r * LAND_TILE] : stage_row(r);
     }
     // monthly table value for the current day: numpy's slope*(x-x0)+y0 (calendar.py dayval), no FMA
     __device__ __forceinline__ double monthly(int mid) const {

@@ -32,13 +32,6 @@ __host__ __device__ constexpr bool perlnd_has_chain(int act_ct) { return act_ct 
 __host__ __device__ constexpr unsigned long long perlnd_hot(int act_ct) { return HOT_SNOW | HOT_PWATER | (perlnd_has_chain(act_ct) ? HOT_CHAIN : 0ull); }
 #define OPT_SED_RAIN_IS_PREC 1u  // SEDMNT: no RAINF in ts -> RAIN = PREC (SEDMNT.py:86-89)
 
-#ifdef HSP2G_HOST_EMU
-#define LAND_SMEM_DECL double *smem = ring
-#define HSP_MAXNREG(n)
-#else
-#define LAND_SMEM_DECL extern __shared__ __align__(128) double smem[]
-#define HSP_MAXNREG(n) __maxnreg__(n)
-#endif
 
 // hourly kernels with a compile-time SAVE set keep SNOW's hour-gated scalars write-through (ColdW); the others in
 // shared memory (ColdD)
@@ -61,22 +54,23 @@ __device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
     return airtmp;
 }
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED, class FW = DynFlags>
-__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(const __grid_constant__ LandLaunch L) {
+// The time loop of a PERLND warp.  The __global__ wrappers below (and the ones hspsquared_b200/jit.py generates for one
+// batch's exact configuration) only fix the template arguments.
+template <int ACT_CT, bool HOURLY, class IO, bool SHARED, class FW, class LAY>
+__device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, perlnd_hot(ACT_CT), SHARED, FW> SegT;
+    typedef Seg<IO, perlnd_hot(ACT_CT), SHARED, FW, LAY> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER + (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
-    PipeT<SHARED> pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD, L.n_stations);
+    PipeT<SHARED, LAY> pipe;
+    pipe.init(L, smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD);
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {  // one task = intervals [t0, t1) of one tile (land_common.cuh Sched)
-        pipe.begin_task(SHARED ? L.met + L.station[tile * LAND_TILE + lane] : L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE,
-                        t0, t1);
+        pipe.begin_task(tile, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
         SnowStateT<SNOWCOLD> sw;
@@ -157,23 +151,26 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
         sched.done(tile);
     }
 }
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED, class FW = DynFlags, class LAY = TiledLay>
+__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(const __grid_constant__ LandLaunch L) {
+    perlnd_body<ACT_CT, HOURLY, IO, SHARED, FW, LAY>(L);
+}
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED, class FW = DynFlags>
-__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(const __grid_constant__ LandLaunch L) {
+template <int ACT_CT, bool HOURLY, class IO, bool SHARED, class FW, class LAY>
+__device__ __forceinline__ void implnd_body(const LandLaunch &L) {
     LAND_SMEM_DECL;
     const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, IMPLND_HOT, SHARED, FW> SegT;
+    typedef Seg<IO, IMPLND_HOT, SHARED, FW, LAY> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS;
-    PipeT<SHARED> pipe;
-    pipe.init(smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD, L.n_stations);
+    PipeT<SHARED, LAY> pipe;
+    pipe.init(L, smem, wib, lane, nf, SegT::NHOT + (SHARED ? nf : 0), NCOLD);
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {
-        pipe.begin_task(SHARED ? L.met + L.station[tile * LAND_TILE + lane] : L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE,
-                        t0, t1);
+        pipe.begin_task(tile, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
         SnowStateT<SNOWCOLD> sw;
@@ -226,19 +223,24 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(
         sched.done(tile);
     }
 }
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED, class FW = DynFlags, class LAY = TiledLay>
+__global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) implnd_kernel(const __grid_constant__ LandLaunch L) {
+    implnd_body<ACT_CT, HOURLY, IO, SHARED, FW, LAY>(L);
+}
 
-// dynamic shared memory of one block: per warp PIPE_STAGES interval stages + the hot parameters + one mbarrier per stage
-static inline size_t land_smem_bytes(int nf, unsigned long long hot, int ncold, bool shared) {
-    return (size_t)LAND_WARPS * ((size_t)(PIPE_STAGES * nf + ce_popc(hot) + (shared ? nf : 0) + ncold) * LAND_TILE * sizeof(double) +
-                                 PIPE_STAGES * 8);
+// dynamic shared memory of one block: per warp PIPE_STAGES interval stages (forcing elements of fesz bytes) + the hot
+// parameters + the cold state + one mbarrier per stage
+__host__ __device__ constexpr size_t land_smem_bytes(int nf, unsigned long long hot, int ncold, bool shared, int fesz = 8) {
+    return (size_t)LAND_WARPS * ((size_t)PIPE_STAGES * nf * LAND_TILE * (shared ? 8 : fesz) +
+                                 (size_t)(ce_popc(hot) + (shared ? nf : 0) + ncold) * LAND_TILE * sizeof(double) + PIPE_STAGES * 8);
 }
 // cold-state rows of a kernel instantiation (must mirror the NCOLD constants inside the kernels)
 template <bool HOURLY, class IO, int ACT_CT>
-static inline int perlnd_ncold() {
+__host__ __device__ constexpr int perlnd_ncold() {
     return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS + NCOLD_PWATER +
            (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
 }
 template <bool HOURLY, class IO>
-static inline int implnd_ncold() {
+__host__ __device__ constexpr int implnd_ncold() {
     return SnowStateT<typename ColdPick<HOURLY && IO::STATIC>::type>::SMEM_ROWS;
 }

@@ -7,9 +7,6 @@ struct LandLaunch;
 // Fill in the task plan of L (sub, nsub), launch, and report the grid size used (tickets drawn = tasks + grid).
 cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out);
 cudaError_t hsp2g_launch_implnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out);
-// kernels instantiated on a batch-wide option word (hot_kernels.cu); false = no such kernel for this launch
-bool hsp2g_launch_perlnd_hot(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out, cudaError_t *err);
-bool hsp2g_launch_implnd_hot(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out, cudaError_t *err);
 // PQUAL (implnd = false) / IQUAL rows: a batch whose activity mask is that one bit (qual_kernel.cu)
 cudaError_t hsp2g_launch_qual(LandLaunch &L, bool implnd, int sub_pref, cudaStream_t st, const char **name, int *grid_out);
 // opt in to the dynamic shared memory a kernel needs; *resident = blocks of `block` threads the device holds at once

@@ -10,10 +10,14 @@
 #define HSP_MAXREG_HOT 128  // register cap of the specialised kernels: 4 warps per SM sub-partition (16 per SM), no spills
 #endif
 
-template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false, class FW = DynFlags>
+// Kernels with a compile-time row set (StaticIO) are built for the TILED float64 layout; the general ones (DynIO) read the
+// layout from the launch record (DynLay).  Kernels for any other exact configuration are built per batch (hspsquared_b200/jit.py).
+template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>(), SHARED);
-    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, FW>;
+    typedef typename LayFor<IO>::type LAY;
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>(), SHARED,
+                                        L.forc_f32 ? 4 : 8);
+    auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, DynFlags, LAY>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;
@@ -25,8 +29,6 @@ static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, cons
 
 cudaError_t hsp2g_launch_perlnd(LandLaunch &L, bool hourly, int sub_pref, cudaStream_t st, const char **name, int *grid_out) {
     constexpr int SP = (int)(HSP2G_ACT_SNOW | HSP2G_ACT_PWATER);
-    cudaError_t e_hot = cudaSuccess;
-    if (hsp2g_launch_perlnd_hot(L, hourly, sub_pref, st, name, grid_out, &e_hot)) return e_hot;  // hot_kernels.cu
     if (L.met) {  // shared-met mode: forcings gathered from the station table (hsp2g_set_shared_forcing)
         if (L.act == (unsigned)SP && hourly && io_matches<IO_SnowPwaterDefault>(L))
             return launch_one<SP, true, IO_SnowPwaterDefault, HSP_MAXREG_HOT, true>(L, sub_pref, st, name, "perlnd_kernel<SNOW|PWATER,hourly,save=default24,met=shared>", grid_out);

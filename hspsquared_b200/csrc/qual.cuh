@@ -196,3 +196,36 @@ __device__ __forceinline__ void iqual_step(const SEG &s, QualState &w) {
     s.save(O_IQUAL_SLIQO, 0.0);
     s.save(O_IQUAL_INFLOW, 0.0);
 }
+
+// The time loop of a warp of (segment, constituent) rows; the __global__ wrappers (qual_kernel.cu, hspsquared_b200/jit.py)
+// only fix the template arguments.
+template <bool IMP, class IO, class LAY>
+__device__ __forceinline__ void qual_body(const LandLaunch &L) {
+    LAND_SMEM_DECL;
+    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    const int nf = IO::STATIC ? IO::NF : L.nf;
+    typedef Seg<IO, 0ull, false, DynFlags, LAY> SegT;
+    PipeT<false, LAY> pipe;
+    pipe.init(L, smem, wib, lane, nf, 0, 0);
+    Sched sched(L, lane, wib);
+    int tile, t0, t1;
+    while (sched.next(tile, t0, t1)) {
+        pipe.begin_task(tile, t0, t1);
+        SegT s(L, tile, lane, t0, pipe.hot_area());
+        QualState q;
+        q.load(s);
+        for (int t = t0; t < t1; ++t) {
+            s.begin_step(pipe.acquire());
+            if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) q.refresh_daily(s);
+            if (IMP)
+                iqual_step(s, q);
+            else
+                pqual_step(s, q);
+            s.end_step();
+            pipe.release(t);
+        }
+        q.store(s);
+        pipe.end_task();
+        sched.done(tile);
+    }
+}

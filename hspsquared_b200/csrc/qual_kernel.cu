@@ -13,41 +13,15 @@
 #define HSP_MAXREG_QUAL 128  // no spills; 96 (20 warps) spills 88-128 B and is 7 % slower on PQUAL
 #endif
 
-template <bool IMP, class IO, int MAXREG>
+template <bool IMP, class IO, int MAXREG, class LAY = TiledLay>
 __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) qual_kernel(const __grid_constant__ LandLaunch L) {
-    LAND_SMEM_DECL;
-    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
-    const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, 0ull, false> SegT;
-    PipeT<false> pipe;
-    pipe.init(smem, wib, lane, nf, 0, 0, 0);
-    Sched sched(L, lane, wib);
-    int tile, t0, t1;
-    while (sched.next(tile, t0, t1)) {
-        pipe.begin_task(L.forc + (size_t)tile * L.nsteps * nf * LAND_TILE, t0, t1);
-        SegT s(L, tile, lane, t0, pipe.hot_area());
-        QualState q;
-        q.load(s);
-        for (int t = t0; t < t1; ++t) {
-            s.begin_step(pipe.acquire());
-            if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) q.refresh_daily(s);
-            if (IMP)
-                iqual_step(s, q);
-            else
-                pqual_step(s, q);
-            s.end_step();
-            pipe.release(t);
-        }
-        q.store(s);
-        pipe.end_task();
-        sched.done(tile);
-    }
+    qual_body<IMP, IO, LAY>(L);
 }
 
 template <bool IMP, class IO>
 static cudaError_t launch_qual(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, 0ull, 0, false);
-    auto k = qual_kernel<IMP, IO, HSP_MAXREG_QUAL>;
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, 0ull, 0, false, L.forc_f32 ? 4 : 8);
+    auto k = qual_kernel<IMP, IO, HSP_MAXREG_QUAL, typename LayFor<IO>::type>;
     int cap = 0;
     cudaError_t e = hsp2g_prepare_kernel((const void *)k, smem, LAND_BLOCK, &cap);
     if (e != cudaSuccess) return e;

@@ -34,16 +34,40 @@ def output_names(operation, act):
     return [n for n in _lib.names("outputs") if n.split("_", 1)[0] in secs]
 
 
+def pinned_empty(shape, dtype=np.float64, write_combined=False):
+    """numpy array over page-locked host memory (cudaHostAlloc through the C ABI): copies from / to it run asynchronously at
+    PCIe speed.  write_combined=True for buffers the host only WRITES (forcings); reading such memory from the CPU is slow."""
+    import weakref
+
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    nbytes = max(1, int(np.prod(shape)) * dtype.itemsize)
+    ptr = lib.hsp2g_host_alloc_flags(nbytes, _lib.HOST_WRITE_COMBINED if write_combined else 0)
+    if not ptr:
+        raise MemoryError(lib.hsp2g_last_error().decode())
+    raw = (C.c_char * nbytes).from_address(ptr)
+    weakref.finalize(raw, lib.hsp2g_host_free, ptr)
+    return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 class LandBatch:
-    def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False, order=None):
+    def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False, order="flags",
+                 layout="plain", jit=None):
         """store: SegmentStore; forcing_names: ordered forcing ids the arrays given to run() carry (row order);
-        save: ordered output ids '<SECTION>_<NAME>' run() returns (row order), or 'all'.  The raw tile-major buffers of
+        save: ordered output ids '<SECTION>_<NAME>' run() returns (row order), or 'all'.  The raw series buffers of
         run_host / run_device use `forcing_rows` / `save_rows` (the same names in ascending id order).
-        order: None, "flags" (SegmentStore.divergence_order()) or a permutation: device position i holds the caller's
-        segment order[i].  run(), errors(), get_state() and set_state() keep speaking the caller's order; the raw
-        tile-major buffers of run_host / run_device are in device order (`self.order`)."""
+        order: "flags" (default: SegmentStore.divergence_order(), the identity when every segment carries the same option
+        word), None, or a permutation: device position i holds the caller's segment order[i].  run(), errors(), get_state()
+        and set_state() keep speaking the caller's order; the raw buffers of run_host / run_device are in device order
+        (`self.order`).
+        layout: "plain" (default) -- series are [interval][row][segment], the orientation of the reference's ts arrays, on
+        both sides of PCIe and in HBM (include/hsp2g.h HSP2G_PLAIN) -- or "tiled" ([tile][interval][row][32]).
+        jit: build a kernel for exactly this batch (hspsquared_b200/jit.py); None = for batches of at least jit.MIN_SEGMENTS
+        segments, unless HSP2G_JIT=0."""
         lib = _lib.load()
         self.lib = lib
+        if isinstance(order, str) and order == "flags" and bool((store.flags == store.flags[0]).all()):
+            order = None  # one option word: nothing to sort
         if order is not None:
             import copy as _copy
 
@@ -62,6 +86,19 @@ class LandBatch:
         self.device = device
         self._keep = []
         self.out_dtype = np.dtype(np.float64)
+        self.forcing_dtype = np.dtype(np.float64)
+        self.shared = False
+        if layout not in ("plain", "tiled"):
+            raise ValueError("layout must be 'plain' or 'tiled'")
+        self.layout = layout
+        from . import jit as _jit
+
+        self._jit = _jit
+        self.jit = _jit.enabled(store.n) if jit is None else bool(jit)
+        self.jit_word = True  # fix the batch-wide option word at compile time when there is one
+        self.jit_error = None
+        self.jit_meta = None
+        self._kernel_for = None
         self.h = _lib._h()
         op = _lib.PERLND if store.operation == "PERLND" else _lib.IMPLND
         _lib.check(lib.hsp2g_batch_create(device, op, self.n, store.act, float(calendar.delt), C.byref(self.h)))
@@ -130,37 +167,96 @@ class LandBatch:
         _lib.check(lib.hsp2g_set_save(self.h, len(sid), _ptr(sid, C.POINTER(C.c_int32))))
         self.ns = len(sid)
         _lib.check(lib.hsp2g_set_timing(self.h, int(bool(timing))))
+        _lib.check(lib.hsp2g_set_series_layout(self.h, _lib.PLAIN if self.layout == "plain" else _lib.TILED))
 
     # ------------------------------------------------------------------------------------------------
     @property
     def ntiles(self):
         return self.npad // _lib.TILE
 
+    def _kernel(self):
+        """Before every launch: make sure the kernel built for this batch matches its current configuration (output and
+        forcing element types, layout and shared-met mode can change after construction)."""
+        if not self.jit:
+            return
+        key = (self.out_dtype.itemsize, self.forcing_dtype.itemsize, self.layout, self.shared, self.jit_word)
+        if key != self._kernel_for:
+            self._kernel_for = key
+            self._jit.specialize(self, word=self.jit_word)
+
+    def set_layout(self, layout):
+        if layout not in ("plain", "tiled"):
+            raise ValueError("layout must be 'plain' or 'tiled'")
+        _lib.check(self.lib.hsp2g_set_series_layout(self.h, _lib.PLAIN if layout == "plain" else _lib.TILED))
+        self.layout = layout
+
+    def set_forcing_dtype(self, dtype):
+        """np.float64 (default) or np.float32: element type of the forcing series given to run() / run_host / run_device.
+        float32 is exact whenever the source is float32 (WDM, HDF5 /TIMESERIES; utilities.py:283-287) and halves the bytes."""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("forcing dtype must be float64 or float32")
+        _lib.check(self.lib.hsp2g_set_forcing_dtype(self.h, _lib.F32 if dtype == np.float32 else _lib.F64))
+        self.forcing_dtype = dtype
+
     def run_host(self, t0, forcing_tiled, out_tiled=None):
         """forcing_tiled: float64 [ntiles][nsteps][nf][32] (host, C-contiguous, see tile_series) with rows in
         `self.forcing_rows` order; saved rows come back in `self.save_rows` order.  Enqueues copy-in,
         kernel and copy-out; call sync() before reading `out_tiled` ([ntiles][nsteps][ns][32], allocated when None)."""
         f = forcing_tiled
-        if f.dtype != np.float64 or not f.flags.c_contiguous or f.ndim != 4 or f.shape[0] != self.ntiles or \
+        if f.dtype != self.forcing_dtype or not f.flags.c_contiguous or f.ndim != 4 or f.shape[0] != self.ntiles or \
                 f.shape[2:] != (self.nf, _lib.TILE):
-            raise ValueError("forcing must be C-contiguous float64 [%d][nsteps][%d][%d]" % (self.ntiles, self.nf, _lib.TILE))
+            raise ValueError("forcing must be C-contiguous %s [%d][nsteps][%d][%d]" % (self.forcing_dtype, self.ntiles, self.nf, _lib.TILE))
         nsteps = f.shape[1]
         shape_o = (self.ntiles, nsteps, self.ns, _lib.TILE)
         if out_tiled is None:
             out_tiled = np.empty(shape_o, dtype=self.out_dtype)
         elif out_tiled.shape != shape_o or out_tiled.dtype != self.out_dtype or not out_tiled.flags.c_contiguous:
             raise ValueError("out must be C-contiguous %s %r" % (self.out_dtype, shape_o))
+        if self.layout != "tiled":
+            raise ValueError("run_host takes tile-major buffers: LandBatch(layout='tiled'); run_chunk is the plain-layout call")
         self._keep.append((f, out_tiled))
+        self._kernel()
         _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), f.ctypes.data, out_tiled.ctypes.data))
         return out_tiled
 
-    def run_host_ptr(self, t0, nsteps, forcing_ptr, out_ptr):
-        """Raw-pointer variant for pinned tile-major buffers owned by the caller (e.g. torch pinned tensors)."""
-        _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), forcing_ptr, out_ptr))
+    def run_host_ptr(self, t0, nsteps, forcing_ptr, out_ptr, ldf=None, ldo=None):
+        """Raw-pointer variant for host buffers owned by the caller (pinned_empty, torch pinned tensors): tile-major buffers,
+        or with layout "plain" [nsteps][rows][ld] with ld = ldf / ldo (default n)."""
+        self._kernel()
+        if self.layout == "plain":
+            _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(nsteps), forcing_ptr, int(ldf or self.n), out_ptr,
+                                                  int(ldo or self.n)))
+        else:
+            _lib.check(self.lib.hsp2g_run_host(self.h, int(t0), int(nsteps), forcing_ptr, out_ptr))
 
-    def run_device(self, t0, nsteps, d_forcing, d_out, stream=0):
-        """Device-resident pass: d_forcing [ntiles][nsteps][nf][32], d_out [ntiles][nsteps][ns][32] device pointers."""
-        _lib.check(self.lib.hsp2g_run_device(self.h, int(t0), int(nsteps), d_forcing or None, d_out, stream or None))
+    def run_chunk(self, t0, forcing, out=None):
+        """One time chunk in the plain layout, asynchronously: forcing [nsteps][nf][n] of `forcing_dtype` with rows in
+        `forcing_rows` order and segments in device order (C-contiguous; pinned memory -- pinned_empty -- for copies that
+        overlap the kernels), out [nsteps][ns][n] of `out_dtype` (allocated when None), rows in `save_rows` order.  Nothing
+        is re-tiled or copied on the host.  Call sync() before reading `out`."""
+        f = forcing
+        if self.layout != "plain":
+            raise ValueError("run_chunk is the plain-layout call: LandBatch(layout='plain')")
+        if f.dtype != self.forcing_dtype or not f.flags.c_contiguous or f.ndim != 3 or f.shape[1:] != (self.nf, self.n):
+            raise ValueError("forcing must be C-contiguous %s [nsteps][%d][%d]" % (self.forcing_dtype, self.nf, self.n))
+        nsteps = f.shape[0]
+        if out is None:
+            out = np.empty((nsteps, self.ns, self.n), dtype=self.out_dtype)
+        elif out.shape != (nsteps, self.ns, self.n) or out.dtype != self.out_dtype or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous %s %r" % (self.out_dtype, (nsteps, self.ns, self.n)))
+        self._keep.append((f, out))
+        self._kernel()
+        _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(nsteps), f.ctypes.data if self.nf and not self.shared else None,
+                                              self.n, out.ctypes.data, self.n))
+        return out
+
+    def run_device(self, t0, nsteps, d_forcing, d_out, stream=0, ldf=None, ldo=None):
+        """Device-resident pass.  layout "tiled": d_forcing [ntiles][nsteps][nf][32], d_out [ntiles][nsteps][ns][32] device
+        pointers; "plain": d_forcing [nsteps][nf][ldf], d_out [nsteps][ns][ldo] with ld >= npad (default npad)."""
+        self._kernel()
+        _lib.check(self.lib.hsp2g_run_device_ld(self.h, int(t0), int(nsteps), d_forcing or None, int(ldf or self.npad), d_out,
+                                                int(ldo or self.npad), stream or None))
 
     def set_shared_forcing(self, series, station, mfactor=None):
         """Shared-met mode (include/hsp2g.h hsp2g_set_shared_forcing): `series` [steps][rows][stations] float64 with rows
@@ -181,11 +277,21 @@ class LandBatch:
         _lib.check(self.lib.hsp2g_set_shared_forcing(self.h, nst, steps, _ptr(series), _ptr(station, C.POINTER(C.c_int32)),
                                                      _ptr(mf), self.n))
         self.shared_steps = steps
+        self.shared = True
 
     def run_shared(self, t0=0, steps=None, chunk=None):
         """Advance over [t0, t0+steps) in shared-met mode -> out [steps][ns][n] (caller's row and segment order)."""
         steps = self.shared_steps - t0 if steps is None else steps
         chunk = chunk or steps
+        self._kernel()
+        if self.layout == "plain":
+            dev = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
+            self._keep.append(dev)
+            for a in range(0, steps, chunk):
+                b = min(steps, a + chunk)
+                _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0 + a), int(b - a), None, self.n, dev[a:b].ctypes.data, self.n))
+            self.sync()
+            return self._to_caller(dev)
         out = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
         tiled = []
         for a in range(0, steps, chunk):
@@ -200,6 +306,25 @@ class LandBatch:
             out[a:b] = u if self._inv is None else u[:, :, self._inv]
         return out
 
+    def _to_device_order(self, forcing):
+        """caller's [steps][forcing_names][segments] -> device rows (ascending id) and device segment order; no copy when
+        both already agree"""
+        f = forcing
+        if list(self._fperm) != list(range(self.nf)):
+            f = f[:, self._fperm, :]
+        if self.order is not None:
+            f = f[:, :, self.order]
+        return np.ascontiguousarray(f, dtype=self.forcing_dtype)
+
+    def _to_caller(self, dev):
+        """device-order series [steps][save_rows][device segments] -> the caller's row and segment order"""
+        u = dev
+        if list(self._sinv) != list(range(self.ns)):
+            u = u[:, self._sinv, :]
+        if self._inv is not None:
+            u = u[:, :, self._inv]
+        return u
+
     def sync(self):
         _lib.check(self.lib.hsp2g_sync(self.h))
         self._keep = []
@@ -207,11 +332,25 @@ class LandBatch:
     def run(self, forcing, chunk=None):
         """Whole series through host buffers in chunks of `chunk` intervals: forcing [steps][nf][n] -> out
         [steps][ns][n] (plain layouts; re-tiled per chunk on the way in and out)."""
-        forcing = np.asarray(forcing, dtype=np.float64)
+        forcing = np.asarray(forcing)
         steps = forcing.shape[0]
         if forcing.shape != (steps, self.nf, self.n):
             raise ValueError("forcing must be [steps][%d][%d]" % (self.nf, self.n))
         chunk = chunk or steps
+        if self.layout == "plain":
+            # the arrays go to the device as they are: one strided copy per chunk each way, no host re-tiling (a host copy is
+            # made only when the caller's row order or a segment permutation differs from the device's)
+            f = self._to_device_order(forcing)
+            dev = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
+            self._keep.append((f, dev))
+            self._kernel()
+            for t0 in range(0, steps, chunk):
+                t1 = min(steps, t0 + chunk)
+                _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(t1 - t0), f[t0:t1].ctypes.data if self.nf else None,
+                                                      self.n, dev[t0:t1].ctypes.data, self.n))
+            self.sync()
+            return self._to_caller(dev)
+        forcing = np.asarray(forcing, dtype=self.forcing_dtype)
         out = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
         tiled = []
         for t0 in range(0, steps, chunk):
@@ -219,7 +358,7 @@ class LandBatch:
             f = forcing[t0:t1][:, self._fperm, :]
             if self.order is not None:
                 f = f[:, :, self.order]
-            tiled.append((t0, t1, self.run_host(t0, tile_series(f))))
+            tiled.append((t0, t1, self.run_host(t0, tile_series(f, self.forcing_dtype))))
         self.sync()
         for t0, t1, o in tiled:
             u = untile_series(o, self.n)[:, self._sinv, :]
@@ -230,25 +369,47 @@ class LandBatch:
         """Period statistics straight from hsp2g_run_host (include/hsp2g.h hsp2g_set_output_periods): forcing [steps][nf][n],
         period_of_step int[steps] (results.period_bins) -> [periods][ns][3 = last, sum, mean][n] float32, the numbers
         IOManager.write_ts computes with pandas for outstep 3 / 4 / 5.  Chunks are cut at period ends."""
-        forcing = np.asarray(forcing, dtype=np.float64)
+        forcing = np.asarray(forcing)
         steps = forcing.shape[0]
         P = np.ascontiguousarray(period_of_step, dtype=np.int32)
         if forcing.shape != (steps, self.nf, self.n) or P.shape != (steps,):
             raise ValueError("forcing must be [steps][%d][%d] and period_of_step [steps]" % (self.nf, self.n))
+        if P[0] != 0:
+            raise ValueError("period_of_step must start at period 0")
         previous = self.out_dtype
         self.set_output_dtype(np.float32)
         _lib.check(self.lib.hsp2g_set_output_periods(self.h, steps, _ptr(P, C.POINTER(C.c_int32))))
         nper = int(P[-1]) + 1
-        out = np.empty((nper, self.ns, 3, self.n), dtype=np.float32)
         starts = np.flatnonzero(np.diff(P, prepend=P[0] - 1))  # first interval of every period present
         cuts = list(starts[::periods_per_chunk]) + [steps]
+        if self.layout == "plain":
+            f = self._to_device_order(forcing)
+            dev = np.empty((nper, self.ns, 3, self.n), dtype=np.float32)
+            self._keep.append((f, dev))
+            try:
+                self._kernel()
+                for a, b in zip(cuts[:-1], cuts[1:]):
+                    _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(a), int(b - a), f[a:b].ctypes.data if self.nf else None, self.n,
+                                                          dev[int(P[a]):].ctypes.data, self.n))
+                self.sync()
+            finally:
+                self.sync()
+                _lib.check(self.lib.hsp2g_set_output_periods(self.h, 0, None))
+                self.set_output_dtype(previous)
+            u = dev
+            if list(self._sinv) != list(range(self.ns)):
+                u = u[:, self._sinv]
+            return u if self._inv is None else u[:, :, :, self._inv]
+        forcing = np.asarray(forcing, dtype=self.forcing_dtype)
+        out = np.empty((nper, self.ns, 3, self.n), dtype=np.float32)
         pending = []
         try:
+            self._kernel()
             for a, b in zip(cuts[:-1], cuts[1:]):
                 f = forcing[a:b][:, self._fperm, :]
                 if self.order is not None:
                     f = f[:, :, self.order]
-                ft = tile_series(f)
+                ft = tile_series(f, self.forcing_dtype)
                 nb = int(P[b - 1] - P[a]) + 1
                 o = np.empty((self.ntiles, nb, self.ns, 3, _lib.TILE), dtype=np.float32)
                 self._keep.append((ft, o))
@@ -256,6 +417,7 @@ class LandBatch:
                 pending.append((int(P[a]), nb, o))
             self.sync()
         finally:
+            self.sync()  # nothing of this call may still be in flight when periods and dtype are restored
             _lib.check(self.lib.hsp2g_set_output_periods(self.h, 0, None))
             self.set_output_dtype(previous)
         for p0, nb, o in pending:
@@ -338,7 +500,7 @@ class QualBatch(LandBatch):
     (segment index, constituent number); in the reference's ts that series is '<P|I>QUAL<k>_<NAME>'."""
 
     def __init__(self, operation, uci_list, calendar, forcing_names, save="all", device=0, timing=False, order="flags",
-                 land=None):
+                 land=None, layout="plain", jit=None):
         """order="flags" (default) puts rows with equal option words next to each other on the device: the constituents of a
         segment differ in kind (sediment-associated, overland-flow-associated, subsurface concentrations ...), segment-major rows
         would make every warp execute every kind.  Invisible to run() / gather(); run_device buffers are in device order.
@@ -355,7 +517,8 @@ class QualBatch(LandBatch):
         if land is not None and isinstance(order, str) and order == "flags":
             pos = self.row_segment if land._inv is None else np.asarray(land._inv)[self.row_segment]
             order = store.divergence_order(keys=(pos,))
-        super().__init__(store, calendar, forcing_names, save, device=device, timing=timing, order=order)
+        super().__init__(store, calendar, forcing_names, save, device=device, timing=timing, order=order,
+                         layout="tiled" if land is not None else layout, jit=jit)
         if land is not None:
             self.attach(land)
 
@@ -378,6 +541,8 @@ class QualBatch(LandBatch):
         land's output rows (it must be in land's SAVE set, float64), anything else from land's forcing rows."""
         if land.out_dtype != np.float64:
             raise ValueError("the land batch must write float64 outputs to feed constituents")
+        if land.layout != "tiled" or self.layout != "tiled":
+            raise ValueError("the device-resident chain gathers between tile-major buffers: LandBatch(layout='tiled')")
         rows = self.row_segment if self.order is None else self.row_segment[self.order]  # device row -> caller's segment
         seg = rows if land._inv is None else np.asarray(land._inv)[rows]  # -> the land batch's device position
         seg = np.ascontiguousarray(seg, dtype=np.int64)
@@ -431,9 +596,9 @@ class QualBatch(LandBatch):
         return e
 
 
-def tile_series(x):
+def tile_series(x, dtype=np.float64):
     """[steps][rows][n] -> tile-major [ntiles][steps][rows][32] (include/hsp2g.h); lanes past n copy the last segment."""
-    x = np.asarray(x, dtype=np.float64)
+    x = np.asarray(x, dtype=dtype)
     steps, rows, n = x.shape
     T = _lib.TILE
     nt = (n + T - 1) // T

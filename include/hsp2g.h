@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define HSP2G_ABI_VERSION 2
+#define HSP2G_ABI_VERSION 3
 
 #define HSP2G_PERLND 0 /* configuration.py:48-50 */
 #define HSP2G_IMPLND 1 /* configuration.py:51-52 */
@@ -71,7 +71,8 @@ typedef struct hsp2g_batch hsp2g_batch;
 int hsp2g_abi_version(void);
 const char *hsp2g_last_error(void);
 /* table in {"params","monthly","flags","states","forcings","outputs","errors"}; comma separated ids in order.
- * Output ids are prefixed with their section, e.g. "SNOW_PACKF", "PWATER_SURO", "IWATER_SURO". */
+ * Output ids are prefixed with their section, e.g. "SNOW_PACKF", "PWATER_SURO", "IWATER_SURO".
+ * "build" names the build of the library: "cuda/sm_100a" for the product; the host loader refuses anything else. */
 const char *hsp2g_names(const char *table);
 int hsp2g_device_count(int *count);
 
@@ -123,6 +124,20 @@ int hsp2g_set_save(hsp2g_batch *b, int n_rows, const int32_t *output_ids);
 #define HSP2G_F32 1
 int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype);
 
+/* Series layout of hsp2g_run_device / hsp2g_run_host (default HSP2G_TILED, described at the top of this file).
+ * HSP2G_PLAIN is the orientation the reference itself keeps -- ts[name] is one array per series, a batch is
+ * [interval][row][segment] (get_timeseries / save_timeseries, utilities.py:274-333): forcing [nsteps][n_forcing_rows][ld],
+ * out [nsteps][n_saved_rows][ld].  Nothing is re-tiled on the host: a warp fetches its interval's box of n_forcing_rows x 32
+ * segments with one tensor-map TMA copy and stores 256 contiguous bytes per saved row.  On the device ld >= 32*ntiles
+ * (hsp2g_batch_npad); host buffers may have any ld >= n_seg. */
+#define HSP2G_TILED 0
+#define HSP2G_PLAIN 1
+int hsp2g_set_series_layout(hsp2g_batch *b, int layout);
+/* Element type of the forcing series (default HSP2G_F64).  HSP2G_F32: the series are float32 and are widened on the device --
+ * exact whenever the source is float32 (WDM and the HDF5 /TIMESERIES tables are; `series * MFACTOR` stays in the stored
+ * dtype, utilities.py:283-287) -- half the bytes over PCIe and out of HBM.  Ignored in shared-met mode. */
+int hsp2g_set_forcing_dtype(hsp2g_batch *b, int dtype);
+
 /* Advance all segments over intervals [t0, t0+nsteps).  State is read at the start and written at the end, so
  * consecutive chunks are bit-identical to one pass.  Series are tile-major [tile][nsteps][row][32] (see above):
  * forcing = ntiles*nsteps*n_forcing_rows*32 doubles, out = ntiles*nsteps*n_saved_rows*32 doubles (or floats).
@@ -131,6 +146,20 @@ int hsp2g_set_output_dtype(hsp2g_batch *b, int dtype);
  *          valid until hsp2g_sync.  Pinned host memory (hsp2g_host_alloc) is needed for real overlap. */
 int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forcing, double *d_out, void *stream);
 int hsp2g_run_host(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *h_forcing, double *h_out);
+/* The same with explicit row lengths (elements) for the HSP2G_PLAIN layout: forcing [nsteps][rows][ld_forcing] of the forcing
+ * dtype, out [nsteps][rows][ld_out] of the output dtype (period statistics: [periods][rows][3][ld_out] float32).  _device:
+ * ld >= hsp2g_batch_npad, a multiple of 4; _host: ld >= n_seg (one strided copy each way; contiguous when ld = npad).
+ * hsp2g_run_device / hsp2g_run_host use ld = npad / ld = n_seg when the layout is PLAIN. */
+int hsp2g_run_device_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forcing, int64_t ld_forcing, void *d_out,
+                        int64_t ld_out, void *stream);
+int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_forcing, int64_t ld_forcing, void *h_out,
+                      int64_t ld_out);
+/* A kernel built for exactly this batch -- activity mask, forcing rows, SAVE set, element types, layout and, when every segment
+ * carries the same option word, that word fixed at compile time (hspsquared_b200/jit.py generates the instantiation from
+ * csrc/land_kernels.cuh and compiles it with `nvcc -cubin`).  image = the cubin (sm_100a), entry = its kernel, whose companion
+ * global `<entry>_info` states what was fixed; the library launches it as long as that still describes the batch and runs its
+ * own general kernels otherwise (hsp2g_kernel_name tells).  image = NULL drops the kernel. */
+int hsp2g_set_kernel_image(hsp2g_batch *b, const void *image, size_t nbytes, const char *entry, const char *display_name);
 /* Host-side re-tiling between [interval][row][ld] and [tile][interval][row][32] (what get_timeseries /
  * save_timeseries hand over per segment, utilities.py:274-333, for a whole batch). */
 /* Period aggregation of saved float32 series on the device: what IOManager.write_ts computes with pandas for outstep 3 / 4 / 5
@@ -190,6 +219,13 @@ int hsp2g_math_probe(int device, int fn, int64_t n, const double *x, const doubl
 
 /* Pinned host memory / raw device memory helpers for callers without a CUDA runtime of their own. */
 void *hsp2g_host_alloc(size_t bytes);
+/* flags: HSP2G_HOST_WRITE_COMBINED for buffers the host only writes and the device reads (forcings: no cache snooping on the way
+ * over PCIe); hsp2g_host_register pins an existing allocation (a numpy array, say) so that copies from / to it run asynchronously. */
+#define HSP2G_HOST_WRITE_COMBINED 1u
+#define HSP2G_HOST_PORTABLE 2u
+void *hsp2g_host_alloc_flags(size_t bytes, unsigned flags);
+int hsp2g_host_register(void *p, size_t bytes);
+int hsp2g_host_unregister(void *p);
 int hsp2g_host_free(void *p);
 void *hsp2g_device_alloc(int device, size_t bytes);
 int hsp2g_device_free(int device, void *p);

@@ -33,10 +33,13 @@ def emu_library(oracle_lib):
     from tests.emu import build_emu
 
     path = build_emu.build()
-    saved = (_lib.LIB_PATH, _lib._lib, dict(_lib._names))
+    saved = (_lib.LIB_PATH, _lib._lib, dict(_lib._names), set(_lib.ALLOW_BUILDS))
     _lib.LIB_PATH, _lib._lib = path, None
+    _lib.ALLOW_BUILDS.add("host-emu")  # only the CPU test suite admits the double
     _lib._names.clear()
     yield path
     _lib.LIB_PATH, _lib._lib = saved[0], saved[1]
+    _lib.ALLOW_BUILDS.clear()
+    _lib.ALLOW_BUILDS.update(saved[3])
     _lib._names.clear()
     _lib._names.update(saved[2])

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "hspsquared_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libhsp2g_emu.so")
-UNITS = ("hsp2g_api.cu", "perlnd_kernel.cu", "hot_kernels.cu", "implnd_kernel.cu", "qual_kernel.cu")
+UNITS = ("hsp2g_api.cu", "perlnd_kernel.cu", "implnd_kernel.cu", "qual_kernel.cu")
 # strict IEEE like the device build (-fmad=false): no contraction, no fast-math
 FLAGS = ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c++17", "-DHSP2G_HOST_EMU", "-I", HERE, "-I", CSRC]
 

@@ -24,7 +24,8 @@ enum { cudaSuccess = 0, cudaErrorEmu = 1 };
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaHostAllocPortable = 1,
+       cudaHostAllocWriteCombined = 4, cudaHostRegisterDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 struct cudaDeviceProp {
     int major, minor;
@@ -46,6 +47,8 @@ inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); retu
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy2D(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {

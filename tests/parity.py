@@ -175,7 +175,7 @@ def f32_ulp_diff(got32, ref64):
     return int(np.abs(a - b).max()) if a.size else 0
 
 
-def check_shared_met_mode(n=75):
+def check_shared_met_mode(n=75, jit=None):
     """hsp2g_set_shared_forcing: a few met stations + per-segment station index and MFACTOR give bit-identical results to
     handing every segment its own series * MFACTOR arrays (what get_timeseries builds, utilities.py:274-290); generic and
     compile-time-specialised kernels, with and without divergence ordering."""
@@ -204,14 +204,15 @@ def check_shared_met_mode(n=75):
     store = ens.store(cal)
     for save in ("all", ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] +
                  ["PWATER_" + k for k in test10.SAVE_DEFAULT["PWATER"]]):
-        with LandBatch(store, cal, names, save) as b:
+        with LandBatch(store, cal, names, save, jit=False) as b:
             ref = b.run(expanded, chunk=300)
             ref_state = b.get_state()
         for order in (None, "flags", np.argsort(station, kind="stable")):
-            with LandBatch(store, cal, names, save, order=order) as b:
+            with LandBatch(store, cal, names, save, order=order, jit=jit, layout="tiled" if order is None else "plain") as b:
                 b.set_shared_forcing(series, station, mfac)
                 got = b.run_shared(chunk=300)
                 assert "met=shared" in b.kernel_name()
+                assert jit is None or (",jit>" in b.kernel_name()) == bool(jit), b.kernel_name()
                 assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
             assert np.array_equal(got, ref, equal_nan=True)
 
@@ -440,7 +441,7 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
     with QualBatch("PERLND", ucis, cal, qn, "all") as q:
         want = q.run(q.gather(series), chunk=chunk)
     # device-resident chain
-    with LandBatch(ens.store(cal), cal, names, need, order=order) as land, \
+    with LandBatch(ens.store(cal), cal, names, need, order=order, layout="tiled") as land, \
             QualBatch("PERLND", ucis, cal, qn, "all", land=land) as q:
         got = np.empty_like(want)
         dev = []
@@ -522,7 +523,7 @@ def check_abi_errors_and_edges():
     with LandBatch(store, cal, names, "all") as b:
         b.run(pack_forcings(forc, names, 1))
         assert np.array_equal(b.get_state(), st_none, equal_nan=True)
-    with LandBatch(store, cal, names, "all") as b:
+    with LandBatch(store, cal, names, "all", layout="tiled") as b:
         try:
             b.run_host(25, np.zeros((1, 10, len(names), 32)))  # 25 + 10 > 30 intervals of calendar
         except _lib.Hsp2gError as e:
@@ -532,33 +533,51 @@ def check_abi_errors_and_edges():
 
 
 def check_option_word_kernels():
-    """Kernels instantiated on a batch-wide option word (csrc/hot_kernels.cu) against the same batch with one segment's word
-    changed (run-time option tests, the general kernels): every other segment must come out bit for bit the same, outputs and
-    state, for each SAVE configuration that has such a kernel."""
+    """Kernels built for one batch (hspsquared_b200/jit.py: activity mask, row sets, element types, layout and the batch-wide
+    option word fixed at compile time) against (i) the same batch with one segment's word changed, whose kernel tests the
+    options at run time, and (ii) the library's own general kernels: every segment must come out bit for bit the same, outputs
+    and state.  The words are test10's PERLND 1 / IMPLND 1 and the CBP full-chain segment's -- any word gets its kernel."""
     cal = Calendar("1976-01-20", "1976-03-05", 60, "us")
     pd_ = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + k for k in test10.SAVE_DEFAULT["PWATER"]]
     id_ = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["IWATER_" + k for k in test10.SAVE_DEFAULT["IWATER"]]
-    jobs = [("PERLND", ("SNOW", "PWATER"), pd_, "IFRDFG", "save=default24,options=test10-P001"),
-            ("PERLND", ("SNOW", "PWATER"), "all", "IFRDFG", "save=all53,options=test10-P001"),
-            ("PERLND", ("SNOW", "PWATER"), ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO"], "IFRDFG", "save=flows3,options=test10-P001"),
-            ("IMPLND", ("SNOW", "IWATER"), id_, "RTOP1", "save=default16,options=test10-I001"),
-            ("IMPLND", ("SNOW", "IWATER", "SOLIDS"), id_, "RTOP1", "SOLIDS,hourly,save=default16,options=test10-I001")]
-    for op, secs, save, bit, tag in jobs:
-        ens = synth.Ensemble(op, 70, seed=9, sections=secs)
-        names = list(synth.PERLND_FORCINGS)
+    P6, FC = list(synth.PERLND_FORCINGS), list(synth.FULLCHAIN_FORCINGS)
+    jobs = [("PERLND", dict(sections=("SNOW", "PWATER")), P6, pd_, "IFRDFG", "plain"),
+            ("PERLND", dict(sections=("SNOW", "PWATER")), P6, "all", "IFRDFG", "tiled"),
+            ("PERLND", dict(sections=("SNOW", "PWATER")), P6, ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO"], "IFRDFG", "plain"),
+            ("PERLND", dict(base="cbp"), FC, "all", "RTOP1", "plain"),
+            ("PERLND", dict(base="cbp"), FC, list(cbp10()), "UZFG", "tiled"),
+            ("IMPLND", dict(sections=("SNOW", "IWATER")), P6, id_, "RTOP1", "plain"),
+            ("IMPLND", dict(sections=("SNOW", "IWATER", "SOLIDS")), P6, id_, "RTOP1", "tiled")]
+    for op, kw, names, save, bit, layout in jobs:
+        ens = synth.Ensemble(op, 70, seed=9, **kw)
         f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
-        with LandBatch(ens.store(cal), cal, names, save) as b:
+        word = int(ens.store(cal).flags[0])
+        with LandBatch(ens.store(cal), cal, names, save, layout=layout, jit=True) as b:
             a = b.run(f, chunk=400)
-            assert tag in b.kernel_name(), b.kernel_name()
+            assert b.jit_error is None, b.jit_error
+            assert "options=%#x" % word in b.kernel_name() and ",jit>" in b.kernel_name() and layout in b.kernel_name(), b.kernel_name()
             sa = b.get_state()
         st = ens.store(cal)
         st.flags[-1] ^= np.uint64(1) << np.uint64(st.FB[bit])
-        with LandBatch(st, cal, names, save) as b:
+        with LandBatch(st, cal, names, save, layout=layout, jit=True, order=None) as b:
             g = b.run(f, chunk=400)
-            assert "options=" not in b.kernel_name()
+            assert "options=per-segment" in b.kernel_name() and ",jit>" in b.kernel_name(), b.kernel_name()
             sg = b.get_state()
+        with LandBatch(ens.store(cal), cal, names, save, layout=layout, jit=False) as b:
+            c = b.run(f, chunk=400)
+            assert "jit" not in b.kernel_name(), b.kernel_name()
+            sc = b.get_state()
+        tag = (op, kw, layout)
         assert np.array_equal(a[:, :, :-1], g[:, :, :-1], equal_nan=True), tag
         assert np.array_equal(sa[:, :-1], sg[:, :-1], equal_nan=True), tag
+        assert np.array_equal(a, c, equal_nan=True), tag
+        assert np.array_equal(sa, sc, equal_nan=True), tag
+
+
+def cbp10():
+    """the ten series a CBP land-segment UCI hands its river model (tests/land_spec/hwmA51800.uci:493-502)"""
+    return ("PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "SEDMNT_SOSED", "PWTGAS_SOHT", "PWTGAS_IOHT", "PWTGAS_AOHT",
+            "PWTGAS_SODOXM", "PWTGAS_IODOXM", "PWTGAS_AODOXM")
 
 
 def check_period_aggregation(n=40, days=75):
@@ -601,8 +620,7 @@ def check_period_aggregation(n=40, days=75):
         try:
             b.set_output_dtype(np.float32)
             _lib.check(b.lib.hsp2g_set_output_periods(b.h, len(bins), bins.ctypes.data_as(C.POINTER(C.c_int32))))
-            bad = np.zeros((b.ntiles, 30, b.nf, 32))
-            b.run_host(0, bad, np.empty((b.ntiles, 30, b.ns, 32), dtype=np.float32))  # 30 intervals: not whole days
+            b.run_chunk(0, np.zeros((30, b.nf, b.n)), np.empty((30, b.ns, b.n), dtype=np.float32))  # 30 intervals: not whole days
         except _lib.Hsp2gError as e:
             assert "period boundaries" in str(e)
         else:

@@ -30,7 +30,8 @@ def test_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "libhsp2g.so does not export %s" % s
     assert set(syms) == set(_lib.EXPORTS), "ctypes prototypes and the header disagree"
-    assert lib.hsp2g_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.hsp2g_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.build_kind() == "cuda/sm_100a"
 
 
 def test_name_tables(lib):
@@ -83,4 +84,13 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(_lib.Hsp2gError):
+        _lib.load()
+
+
+def test_loader_refuses_a_host_build(emu_library, monkeypatch):
+    """HSP2G_LIB may name another build of the library, but the product loader opens CUDA builds only: the host-compiled test
+    double (the one thing in this repo that could pass for a CPU path) is refused unless the test suite itself admits it."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "ALLOW_BUILDS", {_lib.CUDA_BUILD})
+    with pytest.raises(_lib.Hsp2gError, match="host-emu"):
         _lib.load()

@@ -28,6 +28,7 @@ def _worker(rank, world, port, emu_path, n_total, q):
     from hspsquared_b200.calendar import Calendar
 
     _lib.LIB_PATH = emu_path  # test double (tests/emu/README.md)
+    _lib.ALLOW_BUILDS.add("host-emu")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cal = Calendar("1976-01-01", "1976-01-15", 60, "us")
     lo, hi = D.shard_bounds(n_total, rank, world)

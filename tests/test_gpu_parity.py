@@ -155,8 +155,10 @@ def test_float32_outputs(name):
     assert worst <= (0 if parity.GPU_EXACT else 1), (kname, worst)
 
 
-def test_headline_static_kernels_are_selected():
-    """Default SAVE + the six met series in id order pick the kernels specialised at compile time."""
+def test_batch_kernels_are_built_and_selected():
+    """Every batch gets a kernel built for its own configuration (hspsquared_b200/jit.py): the option word of a uniform
+    ensemble is fixed at compile time whatever the word (test10's and the CBP full-chain segment's here); the float32 and
+    plain-layout variants are kernels of their own; the library's general kernels give the same bits."""
     from hspsquared_b200 import synth, test10
     from hspsquared_b200.calendar import Calendar
     from hspsquared_b200.engine import LandBatch
@@ -165,23 +167,40 @@ def test_headline_static_kernels_are_selected():
     ens = synth.Ensemble("PERLND", 64, seed=5, sections=("SNOW", "PWATER"))
     save = ["SNOW_" + n for n in test10.SAVE_DEFAULT["SNOW"]] + ["PWATER_" + n for n in test10.SAVE_DEFAULT["PWATER"]]
     f = synth.forcing_chunk(ens, cal, 0, cal.steps)
-    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+    word = int(ens.store(cal).flags[0])
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, jit=True) as b:
         o64 = b.run(f)
-        # every segment carries test10 PERLND 1's option word: the kernel with the word fixed at compile time
-        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24,options=test10-P001>"
+        assert b.jit_error is None, b.jit_error
+        k = b.kernel_name()
+        assert k.startswith("perlnd_kernel<SNOW|PWATER,hourly,forc=6:") and "save=24:" in k and "plain" in k
+        assert "options=%#x" % word in k and k.endswith(",jit>")
+        assert b.jit_meta["spill_bytes"] == 0 and b.jit_meta["registers"] <= 128
+    cbp = synth.Ensemble("PERLND", 64, seed=5, base="cbp")  # a non-test10 word: the CBP land segment's full chain
+    fc = synth.forcing_chunk(cbp, cal, 0, cal.steps, names=list(synth.FULLCHAIN_FORCINGS))
+    with LandBatch(cbp.store(cal), cal, list(synth.FULLCHAIN_FORCINGS), list(parity.cbp10()), jit=True) as b:
+        oc = b.run(fc)
+        assert b.jit_error is None, b.jit_error
+        assert "options=%#x" % int(cbp.store(cal).flags[0]) in b.kernel_name() and "save=10:" in b.kernel_name()
+    with LandBatch(cbp.store(cal), cal, list(synth.FULLCHAIN_FORCINGS), list(parity.cbp10()), jit=False) as b:
+        assert np.array_equal(b.run(fc), oc, equal_nan=True)
+        assert "jit" not in b.kernel_name()
     st = ens.store(cal)
     st.flags[-1] ^= np.uint64(1) << np.uint64(st.FB["IFRDFG"])  # one segment differs: run-time option words, same bits elsewhere
-    with LandBatch(st, cal, list(synth.PERLND_FORCINGS), save) as b:
+    with LandBatch(st, cal, list(synth.PERLND_FORCINGS), save, jit=True, order=None) as b:
         omix = b.run(f)
-        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24>"
+        assert "options=per-segment" in b.kernel_name()
     assert np.array_equal(omix[:, :, :-1], o64[:, :, :-1], equal_nan=True)
-    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save) as b:
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, jit=True) as b:
         b.set_output_dtype(np.float32)
-        o32 = b.run(f)
-        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24,f32>"
-    with np.errstate(over="ignore"):
-        assert np.array_equal(o32, o64.astype(np.float32), equal_nan=True)
-    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), list(reversed(save))) as b:
+        b.set_forcing_dtype(np.float32)
+        f32 = f.astype(np.float32)
+        o32 = b.run(f32)
+        assert "forc=6:0x7e,f32" in b.kernel_name() and ",f32,plain" in b.kernel_name()
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, jit=False, layout="tiled") as b:
+        o32g = b.run(f32.astype(np.float64)).astype(np.float32)  # general kernel, tiled, widened inputs
+        assert b.kernel_name() == "perlnd_kernel<SNOW|PWATER,hourly,save=default24>"
+    assert np.array_equal(o32, o32g, equal_nan=True)
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), list(reversed(save)), jit=True) as b:
         orev = b.run(f)  # caller's row order is honoured whatever the device order
     assert np.array_equal(orev[:, ::-1, :], o64, equal_nan=True)
 
