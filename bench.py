@@ -267,10 +267,11 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
-    """Tile-major [ntiles][nsteps][6][32] fp64 forcings (include/hsp2g.h) generated ON the device with the same
-    elementwise expressions as synth.forcing_chunk (separate mul / add kernels: no FMA), so the oracle spot-check
-    sees identical bits.  Lanes past n in the last tile copy the last segment."""
+def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows, layout="plain", dtype=None):
+    """fp64 forcings of intervals [t0, t0+nsteps) generated ON the device with the same elementwise expressions as
+    synth.forcing_chunk (separate mul / add kernels: no FMA), so the oracle spot-check sees identical bits.
+    layout "plain": [nsteps][rows][npad] (include/hsp2g.h HSP2G_PLAIN, ld = npad); "tiled": [ntiles][nsteps][rows][32].
+    Columns past n copy the last segment."""
     from hspsquared_b200 import synth
 
     s = synth.shared_series(ens.operation, cal, t0, nsteps)
@@ -291,7 +292,47 @@ def device_forcing(torch, ens, cal, t0, nsteps, npad, dev, rows):
             f[:, r, :n] = T(s[nm])[:, None]
     if npad > n:
         f[:, :, n:] = f[:, :, n - 1:n]
+    if dtype is not None:
+        f = f.to(dtype)
+    if layout == "plain":
+        return f
     return f.view(nsteps, len(rows), npad // 32, 32).permute(2, 0, 1, 3).contiguous()
+
+
+def out_buffers(torch, npad, Tc, ns, dev, layout="plain", dtype=None, count=2):
+    shape = (Tc, ns, npad) if layout == "plain" else (npad // 32, Tc, ns, 32)
+    return [torch.empty(shape, dtype=dtype or torch.float64, device=dev) for _ in range(count)]
+
+
+def out_column(got, i, layout):
+    """series [interval][row] of segment i from a device output buffer brought to the host"""
+    return got[:, :, i] if layout == "plain" else got[i // 32, :, :, i % 32]
+
+
+def time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0):
+    """W untimed + K timed launches of `batch` over consecutive chunks (state carried), CUDA events on the launching stream,
+    barrier + synchronize on both sides, max over ranks.  -> ms for the K launches"""
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for c in range(first, first + W):
+        batch.run_device(c * Tc, Tc, forc[c % len(forc)].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for c in range(first + W, first + W + K):
+        batch.run_device(c * Tc, Tc, forc[c % len(forc)].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def main():
@@ -304,11 +345,16 @@ def main():
     ap.add_argument("--chunk", type=int, default=438,
                     help="intervals per step; the default makes the default 20 timed steps exactly one simulated year "
                          "(8,760 hourly intervals), so the figure is an annual average over snow, melt and summer regimes")
+    ap.add_argument("--layout", default="plain", choices=("plain", "tiled"),
+                    help="series layout in HBM: plain = [interval][row][segment] (the reference's orientation, tensor-map TMA), "
+                         "tiled = [tile][interval][row][32]")
     ap.add_argument("--sub", type=int, default=None, help="intervals per (tile, sub-chunk) task; default = library's")
-    ap.add_argument("--order", default="none", help="experiment: order segments by a jitter key (airt, prec, ...)")
+    ap.add_argument("--no-jit", action="store_true", help="run the library's general kernels instead of one built for the batch")
     ap.add_argument("--no-ordered", action="store_true", help="skip the extra divergence-ordered measurement")
+    ap.add_argument("--no-alt-layout", action="store_true", help="skip the extra measurement in the other series layout")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations timed beside the headline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -335,6 +381,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    pin_to_gpu_numa_node(local_rank)
 
     from hspsquared_b200 import _lib, synth
     from hspsquared_b200.calendar import Calendar
@@ -347,13 +394,10 @@ def main():
     if total_chunks * Tc > cal.steps:
         sys.exit("steps*chunk exceeds the 10-year run (%d intervals)" % cal.steps)
     ens = synth.Ensemble("PERLND", n, seed=1234 + rank, sections=("SNOW", "PWATER"))
-    if args.order == "airt":
-        ens = ens.take(np.argsort(ens.u_airt, kind="stable"))
-    elif args.order == "airt_prec":
-        ens = ens.take(np.lexsort((ens.u_prec, np.floor(ens.u_airt * 16))))
     store = ens.store(cal)
     save = default_save()
-    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank)
+    jit = not args.no_jit
+    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit)
     if args.sub is not None:
         batch.set_schedule(args.sub)
     npad, nf, ns = batch.npad, batch.nf, batch.ns
@@ -363,41 +407,25 @@ def main():
     free, _tot = torch.cuda.mem_get_info(dev)
     per_f = Tc * nf * npad * 8
     ring = max(2, min(total_chunks, int((free * 0.6 - 2 * Tc * ns * npad * 8) // per_f)))
-    forc = [device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(min(ring, total_chunks))]
-    outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+    forc = [device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows, args.layout) for c in range(min(ring, total_chunks))]
+    outs = out_buffers(torch, npad, Tc, ns, dev, args.layout)
     torch.cuda.synchronize(dev)
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the kernels, and the events that time them, live here
     assert stream.cuda_stream != 0
-
-    def step(c):
-        batch.run_device(c * Tc, Tc, forc[c % len(forc)].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for c in range(W):
-        step(c)
-    barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0, _ = batch.kernel_stats()
-    e0.record(stream)
-    for c in range(W, W + K):
-        step(c)
-    e1.record(stream)
-    barrier()
+    sampler.start()  # the warm-up launches are sampled too; the timed region is tens of milliseconds
+    ms = time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
     l1, _ = batch.kernel_stats()
     kname = batch.kernel_name()
     n_forcing_chunks = len(forc)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     seg_steps = n * Tc * K * world
     value = seg_steps / (ms * 1e-3)
 
@@ -418,9 +446,10 @@ def main():
                       "steps": nst, "time_unit": "ns"}
                 ts = synth.forcing_of(ens, cal, i, 0, nst)
                 CASES.run_segment("PERLND", ens.tables_of(i), ts, si, acts)
+                col = out_column(got, i, args.layout)
                 for r, full in enumerate(batch.save_rows):
                     ref = ts[full.split("_", 1)[1]][last * Tc:]
-                    g = got[i // 32, :, r, i % 32]
+                    g = col[:, r]
                     ok = ~np.isnan(ref)
                     assert np.array_equal(np.isnan(g), ~ok)
                     den = np.maximum(np.abs(ref[ok]), max(1e-4 * np.abs(ref[ok]).max(), 1e-300)) if ok.any() else 1.0
@@ -431,50 +460,68 @@ def main():
         except Exception as ex:  # the number stands; say that the check could not run
             parity = {"error": repr(ex)}
 
+    peak, peak_src = measured_peak()
+    frac_of = lambda ms_: BYTES_PER_SEGSTEP * n * Tc / (ms_ * 1e-3 / K) / 1e9 / peak
+
+    # ---- the same year in the other series layout (same kernel template, same bits): reported beside the headline
+    alt = None
+    if not args.no_alt_layout:
+        other = "tiled" if args.layout == "plain" else "plain"
+        try:
+            b2 = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=other, jit=jit)
+            if args.sub is not None:
+                b2.set_schedule(args.sub)
+            for c in range(len(forc)):  # re-layout chunk by chunk, in place of the first copy
+                f = forc[c]
+                forc[c] = None
+                forc[c] = (f.view(Tc, nf, npad // 32, 32).permute(2, 0, 1, 3).contiguous() if other == "tiled"
+                           else f.permute(1, 2, 0, 3).reshape(Tc, nf, npad).contiguous())
+                del f
+            outs2 = out_buffers(torch, npad, Tc, ns, dev, other)
+            ms2 = time_device(torch, b2, forc, outs2, Tc, K, W, stream, dev, dist)
+            same = bool(torch.equal(torch.nan_to_num(outs2[(W + K - 1) % 2].cpu() if other == "plain" else
+                                                     outs2[(W + K - 1) % 2].permute(1, 2, 0, 3).reshape(Tc, ns, npad).cpu()),
+                                    torch.nan_to_num(outs[(W + K - 1) % 2].cpu() if args.layout == "plain" else
+                                                     outs[(W + K - 1) % 2].permute(1, 2, 0, 3).reshape(Tc, ns, npad).cpu())))
+            alt = {"layout": other, "value": seg_steps / (ms2 * 1e-3), "ms_per_step": ms2 / K, "frac": frac_of(ms2),
+                   "kernel": b2.kernel_name(), "same_bits_as_headline": same}
+            b2.close()
+            del outs2
+        except Exception as ex:
+            alt = {"error": repr(ex)}
+
     # ---- the same year with the segments in divergence-aware order (SegmentStore.divergence_order with a climate key):
     # reported beside the headline, never instead of it
     ordered = None
-    if not args.no_ordered and args.order == "none":
+    if not args.no_ordered:
         try:
             del forc
             torch.cuda.empty_cache()
             perm = store.divergence_order(keys=(np.floor(ens.u_airt * 16), ens.u_prec))
             ens2 = ens.take(perm)
-            b2 = LandBatch(ens2.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=local_rank)
+            b2 = LandBatch(ens2.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit)
             if args.sub is not None:
                 b2.set_schedule(args.sub)
-            forc2 = [device_forcing(torch, ens2, cal, c * Tc, Tc, npad, dev, b2.forcing_rows) for c in range(total_chunks)]
+            forc2 = [device_forcing(torch, ens2, cal, c * Tc, Tc, npad, dev, b2.forcing_rows, args.layout) for c in range(total_chunks)]
             torch.cuda.synchronize(dev)
-            for c in range(W):
-                b2.run_device(c * Tc, Tc, forc2[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            for c in range(W, W + K):
-                b2.run_device(c * Tc, Tc, forc2[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
-            f1.record(stream)
-            barrier()
-            ms2 = f0.elapsed_time(f1)
-            if dist is not None:
-                t = torch.tensor([ms2], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms2 = float(t.item())
+            ms2 = time_device(torch, b2, forc2, outs, Tc, K, W, stream, dev, dist)
             b2.close()
             del forc2
             torch.cuda.empty_cache()
-            ordered = {"value": seg_steps / (ms2 * 1e-3), "ms_per_step": ms2 / K,
-                       "frac": BYTES_PER_SEGSTEP * n * Tc / (ms2 * 1e-3 / K) / 1e9 / measured_peak()[0],
+            ordered = {"value": seg_steps / (ms2 * 1e-3), "ms_per_step": ms2 / K, "frac": frac_of(ms2),
                        "key": "option word, then floor(16 * air-temperature jitter), then precipitation jitter "
                               "(SegmentStore.divergence_order): same segments, same arithmetic, warps see similar weather"}
         except Exception as ex:
             ordered = {"error": repr(ex)}
+    forc = None
+    del outs
+    torch.cuda.empty_cache()
 
-    # ---- end-to-end through the C ABI with HOST buffers (H2D and D2H inside the timed region)
+    # ---- end to end through the public API with plain HOST buffers (H2D and D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier)
+        e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier)
 
-    peak, peak_src = measured_peak()
     traffic, traffic_src = measured_traffic(kname, n, Tc)
     avg_launch_s = ms * 1e-3 / K
     achieved = BYTES_PER_SEGSTEP * n * Tc / avg_launch_s / 1e9
@@ -485,6 +532,8 @@ def main():
         "config": {"workload": "test10 PERLND SNOW+PWATER replicated to %d segments/GPU, jittered params, 10-yr hourly "
                                "synthetic met, default SAVE (13 SNOW + 11 PWATER)" % n,
                    "segments_per_gpu": n, "intervals_per_step": Tc, "forcings": 6, "saved_series": 24,
+                   "series_layout": "%s (%s)" % (args.layout, "[interval][row][segment], as the reference's ts arrays"
+                                                 if args.layout == "plain" else "[tile][interval][row][32]"),
                    "cache": "inputs of every step (%.2f GB) and outputs (%.2f GB) are far larger than L2; %d distinct "
                             "forcing chunks resident" % (per_f / 1e9, Tc * ns * npad * 8 / 1e9, n_forcing_chunks),
                    "kernel": kname, "parallelism": "segments sharded over %d GPU(s), no collective" % world},
@@ -492,19 +541,25 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_SEGSTEP * n * Tc,
                      "avg_launch_ms": avg_launch_s * 1e3},
-        "gpu_launches": int(l1 - l0),
+        "gpu_launches": int(l1 - l0) - W,
+        "other_layout": alt,
         "divergence_ordered": ordered,
         "clocks": clocks,
         "parity": parity,
     }
     if e2e is not None:
         line["e2e"] = e2e
+    batch.close()
+    if not args.no_extras:
+        try:
+            line["other_configs"] = run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak)
+        except Exception as ex:
+            line["other_configs"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_baseline()
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
-    batch.close()
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -512,13 +567,51 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world, barrier):
-    """Same metric through hsp2g_run_host (the C-ABI call a host program makes): pinned host forcings in, pinned host
-    outputs back, every step, H2D and D2H inside the timed region.  Outputs cross the bus as float32 -- the element
-    type the reference's save_timeseries hands its IOManager (utilities.py:313); the fp64-output variant is timed
-    beside it on fewer steps."""
+def gpu_local_cpus(index):
+    """cores of the NUMA node / root complex GPU `index` hangs off, from sysfs; None where it does not say"""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(index)
+        addr = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % addr) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        return sorted(cpus) or None
+    except Exception:
+        return None
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Host threads of this rank run on the cores of its GPU's NUMA node, so that the pinned buffers it allocates (first touch)
+    and the copies it drives stay local to the GPU's root complex.  A no-op where sysfs does not say (single-node VMs)."""
+    try:
+        cpus = gpu_local_cpus(local_rank)
+        have = set(os.sched_getaffinity(0))
+        allowed = sorted(set(cpus or ()) & have)
+        if allowed and len(allowed) < len(have):
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
+def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier):
+    """Same metric through the public API a host program calls -- LandBatch.run_chunk -> hsp2g_run_host_ld -- with PLAIN host
+    buffers, [interval][row][segment] exactly as the reference's ts arrays stack: nothing is re-tiled on the host, each chunk
+    is one (strided) copy each way, H2D, kernel and D2H pipelined over 3 streams / 2 device slots, all inside the timed region.
+    Outputs cross the bus as float32 -- the element type the reference's save_timeseries hands its IOManager
+    (utilities.py:313).  Variants timed beside the headline: float32 forcings (exact for float32 sources such as WDM / HDF5),
+    float64 outputs, daily statistics computed on the device, and pageable (ordinary numpy) buffers through LandBatch.run()."""
     from hspsquared_b200 import _lib, synth
-    from hspsquared_b200.engine import tile_series
+    from hspsquared_b200.engine import LandBatch, pinned_empty
 
     lib = _lib.load()
     try:
@@ -527,20 +620,23 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64 << 30
-    npad = batch.npad
-    nt = npad // 32
+    nf, ns = batch.nf, batch.ns
     Te = Tc
-    while Te > 32 and 2 * Te * (nf + ns) * npad * 8 > 0.35 * avail / world:  # every rank pins its own buffers
+    R = 3  # distinct forcing chunks resident on the host, sent round robin
+    while Te > 32 and (R * nf * 8 + 2 * ns * 8) * Te * n > 0.35 * avail / world:  # every rank pins its own buffers
         Te //= 2
-    fb = Te * nf * npad * 8
-    bufs = []
+    if batch.layout != "plain":
+        batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), list(batch.save), device=batch.device, layout="plain", jit=batch.jit)
+        own = True
+    else:
+        own = False
 
-    def timed(out_dtype, steps, base, daily=False):
-        osz = np.dtype(out_dtype).itemsize
-        ob = Te * ns * npad * osz
-        batch.set_output_dtype(out_dtype)
-        ctype = C.c_float if osz == 4 else C.c_double
-        shape = (nt, Te, ns, 32)
+    def timed(fdtype, odtype, steps, base, daily=False, wc=True):
+        batch.set_forcing_dtype(fdtype)
+        batch.set_output_dtype(odtype)
+        hf = [pinned_empty((Te, nf, n), fdtype, write_combined=wc) for _ in range(R)]
+        for j in range(R):
+            hf[j][...] = synth.forcing_chunk(ens, cal, base + j * Te, Te, names=batch.forcing_rows)
         if daily:  # 24-interval statistics (last, sum, mean) computed on the device, a new period at every chunk start
             nb = (Te + 23) // 24
             t = np.arange(cal.steps, dtype=np.int64)
@@ -548,23 +644,17 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             per = np.where(t < base, t // 24, p0 + 1 + ((t - base) // Te) * nb + ((t - base) % Te) // 24).astype(np.int32)
             per = np.ascontiguousarray(per)
             _lib.check(lib.hsp2g_set_output_periods(batch.h, len(per), per.ctypes.data_as(C.POINTER(C.c_int32))))
-            ob = nb * ns * 3 * npad * 4
-            shape = (nt, nb, ns, 3, 32)
-        ho = []
-        for _ in range(2):
-            q = lib.hsp2g_host_alloc(ob)
-            if not q:
-                raise MemoryError(lib.hsp2g_last_error().decode())
-            bufs.append(q)
-            ho.append(np.ctypeslib.as_array(C.cast(q, C.POINTER(ctype)), shape=shape))
+            ho = [pinned_empty((nb, ns, 3, n), np.float32) for _ in range(2)]
+        else:
+            ho = [pinned_empty((Te, ns, n), odtype) for _ in range(2)]
         nwarm = 2
         for c in range(nwarm):
-            batch.run_host_ptr(base + c * Te, Te, hf[c % 2].ctypes.data, ho[c % 2].ctypes.data)
+            batch.run_host_ptr(base + c * Te, Te, hf[c % R].ctypes.data, ho[c % 2].ctypes.data)
         batch.sync()
         barrier()
         t0 = time.perf_counter()
         for c in range(nwarm, nwarm + steps):
-            batch.run_host_ptr(base + c * Te, Te, hf[c % 2].ctypes.data, ho[c % 2].ctypes.data)
+            batch.run_host_ptr(base + c * Te, Te, hf[c % R].ctypes.data, ho[c % 2].ctypes.data)
         batch.sync()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
@@ -577,56 +667,84 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, nf, ns, dev, dist, world
             dt = max(float(x.item()) for x in allt)
         if daily:
             _lib.check(lib.hsp2g_set_output_periods(batch.h, 0, None))
-        chk = float(np.nansum(ho[(nwarm + steps - 1) % 2][:, -1, 13:], dtype=np.float64))  # read the step's result
-        del ho
-        for q in bufs[-2:]:
-            lib.hsp2g_host_free(q)
-        del bufs[-2:]
-        return {"value": n * Te * steps * world / dt, "ms_per_step": 1e3 * dt / steps, "d2h_bytes_per_step": ob,
-                "pcie_gbs": (fb + ob) * steps / dt / 1e9, "result_checksum": chk, "steps": steps,
-                "per_rank_ms_per_step": per_rank}, base + (nwarm + steps) * Te
+        last = ho[(nwarm + steps - 1) % 2]
+        chk = float(np.nansum(last[-1, 13:], dtype=np.float64))  # read the step's result
+        fb, ob = hf[0].nbytes, ho[0].nbytes
+        del hf, ho
+        return {"value": n * Te * steps * world / dt, "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": fb,
+                "d2h_bytes_per_step": ob, "pcie_gbs": (fb + ob) * steps / dt / 1e9, "result_checksum": chk, "steps": steps,
+                "per_rank_ms_per_step": per_rank, "kernel": batch.kernel_name()}, base + (nwarm + steps) * Te
+
+    def pageable(steps, base):
+        """ordinary numpy arrays through LandBatch.run(): what a caller who knows nothing about pinned memory pays"""
+        batch.set_forcing_dtype(np.float64)
+        batch.set_output_dtype(np.float32)
+        f = synth.forcing_chunk(ens, cal, base, Te, names=batch.forcing_rows)
+        batch.set_state(store.state)
+        batch.run(f, chunk=Te)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        chk = 0.0
+        for _ in range(steps):
+            o = batch.run(f, chunk=Te)
+            chk = float(np.nansum(o[-1, 13:], dtype=np.float64))
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return {"value": n * Te * steps * world / dt, "ms_per_step": 1e3 * dt / steps, "steps": steps, "result_checksum": chk,
+                "note": "pageable numpy arrays in and out through LandBatch.run(): the driver stages every copy, the output "
+                        "array is allocated per call"}
 
     try:
-        hf = []
-        for _ in range(2):
-            p = lib.hsp2g_host_alloc(fb)
-            if not p:
-                raise MemoryError(lib.hsp2g_last_error().decode())
-            bufs.append(p)
-            hf.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(nt, Te, nf, 32)))
         # continue the simulation where the device-resident run stopped: keeps state and calendar consistent
         base = (W + K) * Tc
-        K64 = max(2, K // 4)
-        if base + (4 + K + K64) * Te > cal.steps:
+        K4 = max(2, K // 4)
+        if base + (2 + K + 4 * (2 + K4)) * Te > cal.steps:
             base = 0
             batch.set_state(store.state)
-        for j in range(2):
-            hf[j][...] = tile_series(synth.forcing_chunk(ens, cal, base + j * Te, Te, names=batch.forcing_rows))
-        r32, base = timed(np.float32, K, base)
-        r64, base = timed(np.float64, K64, base)
+        r32, base = timed(np.float64, np.float32, K, base)
+        out = {"value": r32["value"], "unit": "segment-timesteps/s", "h2d_bytes_per_step": r32["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": r32["d2h_bytes_per_step"], "intervals_per_step": Te, "steps": K,
+               "ms_per_step": r32["ms_per_step"], "pcie_gbs": r32["pcie_gbs"], "result_checksum": r32["result_checksum"],
+               "per_rank_ms_per_step": r32["per_rank_ms_per_step"], "kernel": r32["kernel"],
+               "host_buffers": "plain [interval][row][segment] pinned arrays (forcings write-combined), %d distinct forcing chunks "
+                               "sent round robin; no host-side re-tiling" % R,
+               "api": "LandBatch.run_host_ptr -> hsp2g_run_host_ld (one strided H2D, kernel, one strided D2H per step, pipelined "
+                      "over 3 streams / 2 device slots)",
+               "out_dtype": "float32 (the cast save_timeseries applies before IOManager.write_ts, utilities.py:313)",
+               "forcing_dtype": "float64"}
+        for key, fd, od, kw in (("float32_forcings", np.float32, np.float32, {}),
+                                ("fp64_outputs", np.float64, np.float64, {}),
+                                ("daily_statistics", np.float64, np.float32, {"daily": True}),
+                                ("daily_statistics_float32_forcings", np.float32, np.float32, {"daily": True})):
+            try:
+                r, base = timed(fd, od, K4, base, **kw)
+                out[key] = {k: r[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "pcie_gbs", "steps",
+                                             "kernel", "per_rank_ms_per_step")}
+            except Exception as ex:
+                out[key] = {"error": repr(ex)}
+        out["float32_forcings"]["note"] = ("forcings cross PCIe and HBM as float32 and are widened in the kernel: exact when the "
+                                           "source is float32 (WDM, HDF5 /TIMESERIES; utilities.py:283-287)")
+        out["daily_statistics"]["note"] = ("hsp2g_set_output_periods: last / sum / mean per 24 intervals computed on the device "
+                                           "(IOManager.write_ts outstep 3, hsp2io/io.py:74-81), only the statistics cross PCIe")
         try:
-            rd, base = timed(np.float32, K64, base, daily=True)
-            daily = {"value": rd["value"], "d2h_bytes_per_step": rd["d2h_bytes_per_step"], "ms_per_step": rd["ms_per_step"],
-                     "steps": rd["steps"], "note": "hsp2g_set_output_periods: last / sum / mean per 24 intervals computed on the "
-                     "device (IOManager.write_ts outstep 3, hsp2io/io.py:74-81), only the statistics cross PCIe"}
+            out["pageable_numpy"] = pageable(max(2, K // 10), base)
         except Exception as ex:
-            daily = {"error": repr(ex)}
-        return {"value": r32["value"], "unit": "segment-timesteps/s", "h2d_bytes_per_step": fb,
-                "d2h_bytes_per_step": r32["d2h_bytes_per_step"], "intervals_per_step": Te, "steps": K,
-                "ms_per_step": r32["ms_per_step"], "pcie_gbs": r32["pcie_gbs"], "result_checksum": r32["result_checksum"],
-                "per_rank_ms_per_step": r32["per_rank_ms_per_step"],
-                "out_dtype": "float32 (the cast save_timeseries applies before IOManager.write_ts, utilities.py:313)",
-                "kernel": batch.kernel_name(),
-                "daily_statistics": daily,
-                "fp64_outputs": {"value": r64["value"], "d2h_bytes_per_step": r64["d2h_bytes_per_step"],
-                                 "ms_per_step": r64["ms_per_step"], "pcie_gbs": r64["pcie_gbs"], "steps": r64["steps"]},
-                "note": "pinned tile-major host buffers -> hsp2g_run_host (one contiguous H2D, kernel, one contiguous "
-                        "D2H per step, pipelined over 3 streams / 2 device slots); PCIe-bound by construction"}
+            out["pageable_numpy"] = {"error": repr(ex)}
+        return out
     except Exception as ex:
         return {"error": repr(ex)}
     finally:
-        for p in bufs:
-            lib.hsp2g_host_free(p)
+        if own:
+            batch.close()
+
+
+def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
+    """The other BASELINE.json configurations, each a short device-resident measurement (same rules as the headline: W = 3,
+    CUDA events on the launching stream, inputs far larger than L2), so that the driver's record carries them."""
+    return None
 
 
 if __name__ == "__main__":

@@ -70,24 +70,39 @@ def _sources_hash():
     return _src_hash
 
 
-def spec_of(batch, word=True):
-    """Everything of `batch` (engine.LandBatch / QualBatch) that the kernel can fix at compile time."""
+def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="float64", out_dtype="float64", shared=False,
+             word=True):
+    """The compile-time description of a batch that does not exist yet (no GPU needed): store = SegmentStore, forcing_names /
+    save = the names LandBatch would be given (save may be 'all')."""
+    import numpy as np
+
     F, O = _lib.index("forcings"), _lib.index("outputs")
     fmask = 0
-    for nme in batch.forcing_rows:
+    for nme in forcing_names:
         fmask |= 1 << F[nme]
+    act = int(store.act)
+    if isinstance(save, str) and save == "all":
+        from .engine import output_names
+
+        save = output_names(store.operation, act)
     s = [0, 0, 0]
-    for nme in batch.save_rows:
+    for nme in save:
         s[O[nme] // 64] |= 1 << (O[nme] % 64)
-    act = int(batch.store.act)
     qual = bool(act & (_lib.ACT_BITS["PQUAL"] | _lib.ACT_BITS["IQUAL"]))
-    uniform = len(batch.store.flags) > 0 and bool((batch.store.flags == batch.store.flags[0]).all())
+    uniform = len(store.flags) > 0 and bool((store.flags == store.flags[0]).all())
+    f32in = np.dtype(forcing_dtype).itemsize == 4 and not shared
     return {
-        "op": 0 if batch.store.operation == "PERLND" else 1, "qual": qual, "act": act, "hourly": bool(batch.cal.delt >= 60),
-        "fmask": fmask, "s0": s[0], "s1": s[1], "s2": s[2], "f32out": bool(batch.out_dtype.itemsize == 4),
-        "plain": bool(batch.layout == "plain"), "f32in": bool(batch.forcing_dtype.itemsize == 4) and not batch.shared,
-        "shared": bool(batch.shared), "word": int(batch.store.flags[0]) if (word and uniform and not qual) else None,
+        "op": 0 if store.operation == "PERLND" else 1, "qual": qual, "act": act, "hourly": bool(delt >= 60),
+        "fmask": fmask, "s0": s[0], "s1": s[1], "s2": s[2], "f32out": bool(np.dtype(out_dtype).itemsize == 4),
+        "plain": bool(layout == "plain"), "f32in": bool(f32in), "shared": bool(shared),
+        "word": int(store.flags[0]) if (word and uniform and not qual) else None,
     }
+
+
+def spec_of(batch, word=True):
+    """Everything of `batch` (engine.LandBatch / QualBatch) that the kernel can fix at compile time."""
+    return spec_for(batch.store, batch.cal.delt, batch.forcing_rows, batch.save_rows, batch.layout, batch.forcing_dtype,
+                    batch.out_dtype, batch.shared, word)
 
 
 def _popc(x):
@@ -264,3 +279,13 @@ def specialize(batch, word=True):
 
 def drop(batch):
     _lib.check(batch.lib.hsp2g_set_kernel_image(batch.h, None, 0, None, None))
+
+
+def prebuild(specs, kind=None):
+    """Build the kernels of `specs` now (hspsquared_b200.build / __graft_entry__.build: the cubins travel with the tree, so a
+    fresh GPU box does not spend its first seconds in nvcc).  Returns the display names."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    kind = kind or _lib.CUDA_BUILD
+    with ThreadPoolExecutor(min(8, max(1, len(specs)))) as ex:
+        return [r[2] for r in ex.map(lambda sp: ensure(sp, kind), specs)]

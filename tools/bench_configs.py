@@ -28,7 +28,7 @@ def run_qual(name, torch, dev):
     nseg = 100_000
     tabs = test10.iqual_tables() if imp else test10.pqual_tables()
     names = list(IQUAL_INPUTS[:3] if imp else PQUAL_INPUTS[:7])
-    with QualBatch("IMPLND" if imp else "PERLND", [tabs] * nseg, cal, names, "all", device=dev.index or 0) as batch:
+    with QualBatch("IMPLND" if imp else "PERLND", [tabs] * nseg, cal, names, "all", device=dev.index or 0, layout="tiled") as batch:
         npad, nf, ns, n = batch.npad, batch.nf, batch.ns, batch.n
         g = torch.Generator(device=dev)
         g.manual_seed(5)
@@ -93,10 +93,10 @@ def run_chain(name, torch, dev):
     forcings = list(synth.FULLCHAIN_FORCINGS)
     need = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "PWATER_PERO", "SEDMNT_WSSD", "SEDMNT_SCRSD"]
     qt = test10.pqual_tables()
-    with LandBatch(ens.store(cal), cal, forcings, need, device=dev.index or 0, order="flags") as land, \
+    with LandBatch(ens.store(cal), cal, forcings, need, device=dev.index or 0, order="flags", layout="tiled") as land, \
             QualBatch("PERLND", [qt] * n, cal, list(PQUAL_INPUTS[:7]), "all", device=dev.index or 0, land=land) as q:
         ens2 = ens.take(land.order)  # forcings generated in the land batch's device order
-        forc = [bench.device_forcing(torch, ens2, cal, c * Tc, Tc, land.npad, dev, land.forcing_rows) for c in range(K + W)]
+        forc = [bench.device_forcing(torch, ens2, cal, c * Tc, Tc, land.npad, dev, land.forcing_rows, "tiled") for c in range(K + W)]
         lo = torch.empty((land.npad // 32, Tc, land.ns, 32), dtype=torch.float64, device=dev)
         qf = torch.empty((q.npad // 32, Tc, q.nf, 32), dtype=torch.float64, device=dev)
         qo = [torch.empty((q.npad // 32, Tc, q.ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
@@ -151,7 +151,7 @@ def run_daily_e2e(name, torch, dev):
     ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
     save = bench.default_save()
     tindex = pd.date_range(bench.RUN_START, periods=(K + W) * Tc + 1, freq="60min")[1:]
-    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=dev.index or 0) as b:
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=dev.index or 0, layout="tiled") as b:
         b.set_output_dtype(np.float32)
         npad, nf, ns = b.npad, b.nf, b.ns
         if shared:
@@ -175,7 +175,7 @@ def run_daily_e2e(name, torch, dev):
         else:
             hf = [torch.empty((npad // 32, Tc, nf, 32), dtype=torch.float64).pin_memory() for _ in range(2)]
             for k in range(2):
-                hf[k].copy_(bench.device_forcing(torch, ens, cal, k * Tc, Tc, npad, dev, b.forcing_rows).cpu())
+                hf[k].copy_(bench.device_forcing(torch, ens, cal, k * Tc, Tc, npad, dev, b.forcing_rows, "tiled").cpu())
             df_ = [torch.empty((npad // 32, Tc, nf, 32), dtype=torch.float64, device=dev) for _ in range(2)]
         do = torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float32, device=dev)
         bins = [period_bins(tindex[c * Tc:(c + 1) * Tc], 3)[0] for c in range(K + W)]
@@ -286,7 +286,7 @@ def run(name, torch, dev):
         perm = store.sort_by_flags()
         ens = ens.take(perm)
         note = "segments ordered by option word (SegmentStore.sort_by_flags)"
-    batch = LandBatch(store, cal, forcings, save, device=dev.index or 0)
+    batch = LandBatch(store, cal, forcings, save, device=dev.index or 0, layout="tiled")
     npad, nf, ns = batch.npad, batch.nf, batch.ns
     shared = name == "perlnd_shared_met"
     if shared:
@@ -314,7 +314,7 @@ def run(name, torch, dev):
                 return 0
         forc = [_Null() for _ in range(K + W)]
     else:
-        forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows) for c in range(K + W)]
+        forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, npad, dev, batch.forcing_rows, "tiled") for c in range(K + W)]
     outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
     stream = torch.cuda.Stream(dev)
     torch.cuda.synchronize(dev)

@@ -50,7 +50,7 @@ def main():
         ens = ens.take(perm)
         store = ens.store(cal)
     save = bench.default_save()
-    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=0)
+    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=0, layout="tiled")
     npad, nf, ns = batch.npad, batch.nf, batch.ns
     outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
     stream = torch.cuda.Stream(dev)
@@ -61,7 +61,7 @@ def main():
     ev = []
     l0, _ = batch.kernel_stats()
     for c, (t0, m) in enumerate(chunks):
-        f = bench.device_forcing(torch, ens, cal, t0, m, npad, dev, batch.forcing_rows)
+        f = bench.device_forcing(torch, ens, cal, t0, m, npad, dev, batch.forcing_rows, "tiled")
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
