@@ -741,10 +741,111 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrie
             batch.close()
 
 
+CBP10 = ("PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "SEDMNT_SOSED", "PWTGAS_SOHT", "PWTGAS_IOHT", "PWTGAS_AOHT",
+         "PWTGAS_SODOXM", "PWTGAS_IODOXM", "PWTGAS_AODOXM")  # tests/land_spec/hwmA51800.uci:493-502
+FULLCHAIN_OPTIONS = ("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG")
+
+
+def config_workload(name, n=None, seed=1234):
+    """(ensemble, forcing names, SAVE set, segments, intervals per step, note) of a named BASELINE.json configuration"""
+    from hspsquared_b200 import synth
+
+    if name == "headline":  # configs[1]
+        n = n or 100_000
+        return synth.Ensemble("PERLND", n, seed=seed, sections=("SNOW", "PWATER")), list(synth.PERLND_FORCINGS), default_save(), n, 438, \
+            "test10 PERLND SNOW+PWATER, default SAVE"
+    if name == "implnd":  # the IMPLND half of configs[2]
+        from hspsquared_b200 import test10
+
+        n = n or 100_000
+        save = ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] + ["IWATER_" + k for k in test10.SAVE_DEFAULT["IWATER"]]
+        return synth.Ensemble("IMPLND", n, seed=seed, sections=("SNOW", "IWATER")), list(synth.IMPLND_FORCINGS), save, n, 438, \
+            "test10 IMPLND SNOW+IWATER, default SAVE"
+    if name in ("fullchain_all", "fullchain_cbp10", "fullchain_uniform_all", "fullchain_uniform_cbp10"):  # configs[3]
+        n = n or 250_000
+        uniform = "uniform" in name
+        ens = synth.Ensemble("PERLND", n, seed=seed, base="cbp", options=() if uniform else FULLCHAIN_OPTIONS)
+        save = "all" if name.endswith("_all") else list(CBP10)
+        return ens, list(synth.FULLCHAIN_FORCINGS), save, n, 128 if save == "all" else 438, \
+            "full PERLND chain ATEMP/SNOW/PWATER/SEDMNT/PSTEMP/PWTGAS on the CBP land segment (tests/land_spec/hwmA51800.uci), " + \
+            ("one option word" if uniform else "option flags %s drawn per segment" % "/".join(FULLCHAIN_OPTIONS)) + \
+            (", all 84 outputs" if save == "all" else ", the 10 series a CBP land segment hands its river model")
+    raise KeyError(name)
+
+
+def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=True, order="flags", K=20, W=3, Tc=None, sub=None,
+               dist=None, out_dtype=None, first_chunk=0, seed=1234):
+    """One device-resident measurement of a named configuration (same rules as the headline: W >= 3 warm-up launches, CUDA events
+    on the launching stream, inputs of every launch far larger than L2 and distinct from the previous launch's).
+    order: None | "flags" (option word) | "climate" (option word, then the climate key LandBatch.climate_order derives from the
+    first chunk's forcings)."""
+    from hspsquared_b200 import synth
+    from hspsquared_b200.engine import LandBatch
+
+    ens, forcings, save, n, Tc0, note = config_workload(name, n, seed)
+    Tc = Tc or Tc0
+    store = ens.store(cal)
+    perm = None
+    if order == "climate":
+        f0 = synth.forcing_chunk(ens, cal, first_chunk * Tc, min(Tc, 24 * 14), names=forcings)
+        perm = LandBatch.climate_order(store, forcings, f0)
+    elif order == "flags":
+        perm = store.divergence_order()
+    if perm is not None and not np.array_equal(perm, np.arange(n)):
+        ens = ens.take(perm)
+        store = ens.store(cal)
+    batch = LandBatch(store, cal, forcings, save, device=dev.index or 0, layout=layout, jit=jit, order=None)
+    try:
+        if sub is not None:
+            batch.set_schedule(sub)
+        if out_dtype is not None:
+            batch.set_output_dtype(out_dtype)
+        npad, nf, ns = batch.npad, batch.nf, batch.ns
+        osz = batch.out_dtype.itemsize
+        forc = [device_forcing(torch, ens, cal, (first_chunk + c) * Tc, Tc, npad, dev, batch.forcing_rows, layout) for c in range(K + W)]
+        outs = out_buffers(torch, npad, Tc, ns, dev, layout, torch.float32 if osz == 4 else None)
+        torch.cuda.synchronize(dev)
+        ms = time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0) if first_chunk == 0 else None
+        if ms is None:  # a window that does not start at interval 0: chunk indices are offset
+            class _Shift(list):
+                pass
+            for c in range(W):
+                batch.run_device((first_chunk + c) * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for c in range(W, W + K):
+                batch.run_device((first_chunk + c) * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+        B = 8 * nf + osz * ns
+        value = n * Tc * K / (ms * 1e-3)
+        errs = {k: int((v != 0).sum()) for k, v in batch.errors().items() if (v != 0).any()}
+        return {"config": name, "workload": note, "segments": n, "intervals_per_step": Tc, "steps": K, "warmup": W,
+                "series_layout": layout, "segment_order": order, "kernel": batch.kernel_name(),
+                "registers": (batch.jit_meta or {}).get("registers"), "forcing_rows": nf, "saved_rows": ns,
+                "bytes_per_segment_interval": B, "ms_per_step": ms / K, "value": value, "unit": "segment-timesteps/s",
+                "achieved_GBps": value * B / 1e9, "frac_of_measured_hbm": value * B / 1e9 / peak, "segments_with_error_counts": errs}
+    finally:
+        batch.close()
+        torch.cuda.empty_cache()
+
+
 def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
-    """The other BASELINE.json configurations, each a short device-resident measurement (same rules as the headline: W = 3,
-    CUDA events on the launching stream, inputs far larger than L2), so that the driver's record carries them."""
-    return None
+    """The other BASELINE.json configurations, each a short device-resident measurement on this rank's GPU, so that the
+    driver's record carries them beside the headline (rank 0 only)."""
+    if rank != 0:
+        return None
+    out = {}
+    for key, name, kw in (("implnd_100k", "implnd", {}),
+                          ("fullchain_250k_all84", "fullchain_all", {"K": 12}),
+                          ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10})):
+        try:
+            out[key] = run_config(torch, dev, name, cal, stream, peak, **kw)
+        except Exception as ex:
+            out[key] = {"error": repr(ex)}
+    return out
 
 
 if __name__ == "__main__":

@@ -235,6 +235,17 @@ template <class IO>
 __host__ __device__ constexpr bool io_saved(int oid) {
     return ((oid < 64 ? IO::S0 : oid < 128 ? IO::S1 : IO::S2) >> (oid & 63)) & 1ull;
 }
+#ifdef HSP2G_HOST_EMU
+#define HSP_PIN(p)
+#define HSP_PIN32(v)
+#else
+// stop ptxas from re-deriving a loop-invariant address (or the lane index itself) from threadIdx / blockIdx / the shared
+// window at every use: under register pressure it rematerialises them (an S2R and a few integer operations each time;
+// ~8 % of all issued instructions in profiles/r1b, 48 S2R in a kernel built without the pins in round 2)
+#define HSP_PIN(p) asm volatile("" : "+l"(p))
+#define HSP_PIN32(v) asm volatile("" : "+r"(v))
+#endif
+
 // ---- series layout policy: where interval t, row r of a tile lives (see the header of this file) and the element type
 // of the forcings.  StaticLay fixes both at compile time (kernels built for one batch, hspsquared_b200/jit.py);
 // DynLay reads them from the launch record (the general kernels of the library).
@@ -308,6 +319,7 @@ __device__ __forceinline__ void tensor_g2s(unsigned dst, const void *tmap, int c
 template <bool SHARED, class LAY = TiledLay>
 struct PipeT {
     unsigned char *ring;  // this warp's ring (generic pointer into shared memory)
+    unsigned char *lane_ring;  // this lane's cell of row 0 of stage 0
     unsigned ring_s;      // its shared-space address
     unsigned bar_s;       // shared-space address of this warp's first mbarrier
     const LandLaunch *Lp;
@@ -330,9 +342,18 @@ struct PipeT {
         esz = (!SHARED && lay_f32in<LAY>(L)) ? 4 : 8;
         stage_bytes = nf * LAND_TILE * esz;
         const int warp_bytes = PIPE_STAGES * stage_bytes + (nhot + ncold) * LAND_TILE * 8;
-        ring = reinterpret_cast<unsigned char *>(smem) + (size_t)wib * warp_bytes;
-        ring_s = smem_u32(ring);
-        bar_s = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)LAND_WARPS * warp_bytes) + wib * PIPE_STAGES * 8;
+        // byte offsets inside the block's shared array, made opaque (HSP_PIN32) so that they live in registers; the pointers are
+        // formed from the shared array itself, which keeps every access an LDS / STS (a pinned POINTER turns them generic)
+        unsigned ring_off = (unsigned)wib * (unsigned)warp_bytes;
+        unsigned lane_off = ring_off + (unsigned)lane_ * (unsigned)esz;
+        HSP_PIN32(ring_off);
+        HSP_PIN32(lane_off);
+        ring = reinterpret_cast<unsigned char *>(smem) + ring_off;
+        lane_ring = reinterpret_cast<unsigned char *>(smem) + lane_off;
+        ring_s = smem_u32(smem) + ring_off;
+        bar_s = smem_u32(smem) + (unsigned)(LAND_WARPS * warp_bytes) + wib * PIPE_STAGES * 8;
+        HSP_PIN32(ring_s);
+        HSP_PIN32(bar_s);
         st = 0;
         ph = 0;
         lane = lane_;
@@ -367,6 +388,7 @@ struct PipeT {
             else {  // row by row: nf bulk copies of one 32-segment row each
                 const size_t ldb = (size_t)Lp->forc_ld * esz;
                 const unsigned rowb = (unsigned)(LAND_TILE * esz);
+#pragma unroll 1
                 for (int r = 0; r < nf; ++r) bulk_g2s(dst + r * rowb, src + ((size_t)t * nf + r) * ldb, rowb, bar);
             }
         }
@@ -397,7 +419,7 @@ struct PipeT {
             asm volatile("cp.async.wait_group %0;\n" ::"n"(PIPE_STAGES - 1) : "memory");
         else if (t_end > 0)
             mbar_wait(bar_s + st * 8, ph);
-        return ring + st * stage_bytes + lane * esz;
+        return lane_ring + st * stage_bytes;
     }
     __device__ __forceinline__ double *hot_area() const { return reinterpret_cast<double *>(ring + PIPE_STAGES * stage_bytes); }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
@@ -528,13 +550,6 @@ struct Sched {
 #endif
 
 // per-thread view of the batch
-#ifdef HSP2G_HOST_EMU
-#define HSP_PIN(p)
-#else
-// stop ptxas from re-deriving a loop-invariant address from threadIdx/blockIdx at every use (it does, under
-// register pressure: ~8 % of all issued instructions in profiles/r1b)
-#define HSP_PIN(p) asm volatile("" : "+l"(p))
-#endif
 
 // Option word of the batch: DynFlags reads each segment's 64-bit word from its segment block; StaticFlags<W> is for batches
 // whose segments all carry the word W (a replicated / calibration ensemble): every option test folds at compile time, the
@@ -569,7 +584,7 @@ struct Seg {
     unsigned calfl;        // HSP2G_CAL_* of the current interval
     unsigned calfl_next;   // ... of the next one, loaded an interval ahead (an L2 round trip off the critical path)
     long long out_step;    // bytes between consecutive intervals of out
-    long long out_row;     // bytes between consecutive rows of out (PLAIN; TILED: 32 elements, a compile-time constant)
+    unsigned out_row;      // bytes between consecutive rows of out (PLAIN; TILED: 32 elements, a compile-time constant)
 
     // view of `tile` for the task that starts at interval t0 of the launch
     __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane, int t0, double *hot_area) : L(l) {
@@ -579,8 +594,9 @@ struct Seg {
         const int osz = out_is_f32() ? 4 : 8;
         const int nsr = IO::STATIC ? IO::NS : l.ns;
         if (lay_plain<LAY>(l)) {
-            out_row = l.out_ld * osz;
-            out_step = out_row * nsr;
+            out_row = (unsigned)(l.out_ld * osz);  // < 2^32: rows of fewer than 512 M segments
+            HSP_PIN32(out_row);                    // an opaque 32-bit value: each store address is one IMAD.WIDE.U32
+            out_step = (long long)out_row * nsr;
             outp = reinterpret_cast<unsigned char *>(l.out) + ((size_t)t0 * out_step + ((size_t)tile * LAND_TILE + lane) * osz);
         } else {
             out_row = LAND_TILE * osz;
@@ -617,8 +633,9 @@ struct Seg {
     }
     __device__ __forceinline__ bool out_is_f32() const { return IO::STATIC ? IO::F32 : (L.out_f32 != 0); }
     __device__ __forceinline__ void store_out(int r, double v) const {
-        // TILED: rows at immediate offsets; PLAIN: rows out_row bytes apart (one multiply-add per store)
-        unsigned char *q = outp + ((LAY::STATIC && !LAY::PLAIN) ? (long long)r * LAND_TILE * (out_is_f32() ? 4 : 8) : r * out_row);
+        // TILED: rows at immediate offsets; PLAIN: rows out_row bytes apart, one widening multiply-add (IMAD.WIDE.U32) per store
+        unsigned char *q = outp + ((LAY::STATIC && !LAY::PLAIN) ? (unsigned long long)(r * LAND_TILE * (out_is_f32() ? 4 : 8))
+                                                                 : (unsigned long long)(unsigned)r * (unsigned long long)out_row);
         if (out_is_f32())
             __stcs(reinterpret_cast<float *>(q), (float)v);
         else

@@ -59,7 +59,9 @@ __device__ __forceinline__ double atemp_step(const SEG &s, double prec) {
 template <int ACT_CT, bool HOURLY, class IO, bool SHARED, class FW, class LAY>
 __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
     LAND_SMEM_DECL;
-    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    int lane = threadIdx.x & (LAND_TILE - 1);
+    const int wib = threadIdx.x / LAND_TILE;
+    HSP_PIN32(lane);  // kept in a register: rematerialising it costs an S2R per use
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
     typedef Seg<IO, perlnd_hot(ACT_CT), SHARED, FW, LAY> SegT;
@@ -159,7 +161,9 @@ __global__ void __launch_bounds__(LAND_BLOCK) HSP_MAXNREG(MAXREG) perlnd_kernel(
 template <int ACT_CT, bool HOURLY, class IO, bool SHARED, class FW, class LAY>
 __device__ __forceinline__ void implnd_body(const LandLaunch &L) {
     LAND_SMEM_DECL;
-    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    int lane = threadIdx.x & (LAND_TILE - 1);
+    const int wib = threadIdx.x / LAND_TILE;
+    HSP_PIN32(lane);  // kept in a register: rematerialising it costs an S2R per use
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
     typedef Seg<IO, IMPLND_HOT, SHARED, FW, LAY> SegT;

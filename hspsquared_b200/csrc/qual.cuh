@@ -202,7 +202,9 @@ __device__ __forceinline__ void iqual_step(const SEG &s, QualState &w) {
 template <bool IMP, class IO, class LAY>
 __device__ __forceinline__ void qual_body(const LandLaunch &L) {
     LAND_SMEM_DECL;
-    const int lane = threadIdx.x & (LAND_TILE - 1), wib = threadIdx.x / LAND_TILE;
+    int lane = threadIdx.x & (LAND_TILE - 1);
+    const int wib = threadIdx.x / LAND_TILE;
+    HSP_PIN32(lane);  // kept in a register: rematerialising it costs an S2R per use
     const int nf = IO::STATIC ? IO::NF : L.nf;
     typedef Seg<IO, 0ull, false, DynFlags, LAY> SegT;
     PipeT<false, LAY> pipe;

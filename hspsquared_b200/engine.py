@@ -109,6 +109,26 @@ class LandBatch:
             self.close()
             raise
 
+    @staticmethod
+    def climate_order(store, forcing_names, forcing_sample, bins=16):
+        """Divergence-aware segment order from the forcings themselves: option word first (SegmentStore.divergence_order), then
+        a climate key read off a sample of the batch's own forcing series ([steps][rows][n], rows = forcing_names; a few days
+        are enough) -- the segment's mean air temperature in `bins` classes, then its mean precipitation.  A warp is 32
+        consecutive segments: lanes that see similar weather build, melt and lose their snowpack in the same intervals and
+        get wet together, so they take the same branches.  Pass the result as LandBatch(order=...); run() and the state /
+        error accessors keep speaking the caller's order."""
+        names = list(forcing_names)
+        f = np.asarray(forcing_sample)
+        keys = []
+        tname = "AIRTMP" if "AIRTMP" in names else ("GATMP" if "GATMP" in names else None)
+        if tname is not None:
+            t = f[:, names.index(tname), :].mean(axis=0)
+            span = float(t.max() - t.min())
+            keys.append(np.floor((t - t.min()) / span * bins).clip(0, bins - 1) if span > 0 else np.zeros_like(t))
+        if "PREC" in names:
+            keys.append(f[:, names.index("PREC"), :].mean(axis=0))
+        return store.divergence_order(keys=tuple(keys))
+
     # ------------------------------------------------------------------------------------------------
     def _upload(self, forcing_names, save, timing):
         lib, st, cal = self.lib, self.store, self.cal

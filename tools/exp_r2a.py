@@ -101,15 +101,18 @@ def main():
     run("plain, built for the batch, tensor-map TMA", "plain", True)
     run("plain, built for the batch, row-wise bulk copies", "plain", True, env={"HSP2G_NO_TMAP": "1"})
     run("plain, built for the batch, per-segment option words", "plain", True, word=False)
-    run("plain, library kernel (DynIO)", "plain", False)
+    if not os.environ.get("EXP_SHORT"):
+        run("plain, library kernel (DynIO)", "plain", False)
     run("plain, float32 forcings", "plain", True, f32in=True)
     run("plain, float32 forcings and outputs", "plain", True, f32in=True, f32out=True)
     run("tiled, float32 outputs", "tiled", True, f32out=True)
     run("plain, float32 outputs", "plain", True, f32out=True)
-    for sub in (32, 128):
+    for sub in (() if os.environ.get("EXP_SHORT") else (32, 128)):
         run("plain, sub-chunk %d" % sub, "plain", True, sub=sub)
     del plain64
     torch.cuda.empty_cache()
+    if os.environ.get("EXP_SKIP_E2E"):
+        return
 
     # ---- end to end from plain host buffers through LandBatch.run_chunk (hsp2g_run_host_ld)
     def e2e(label, f32in, f32out, wc, steps=12, pageable=False, registered=False):
