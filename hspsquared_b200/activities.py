@@ -2,12 +2,15 @@
 
 `install()` swaps these into the reference's registry `hsp2.hsp2.configuration.activities` (configuration.py:45-55 --
 the same dict object main.py:15 and mainDoE.py:16 imported), so `hsp2.main` dispatches land activities to libhsp2g
-without any reference file being edited.  Each call advances ONE segment through ONE section on the GPU (the
-reference's granularity, main.py:249-250): inputs are read from `ts`, every output series the reference would create
-is written back into `ts` as float64[steps], the error-count vector and message tuple have the reference's shapes, and
-the two dict side effects are kept (SNOW.py:60-63 siminfo['ICEFG'], PWATER.py:89-93 uci['PARAMETERS']['CSNOFG']).
-This path is for compatibility and parity at 1..10^3 segments; ensembles use hspsquared_b200.engine.LandBatch, which
-fuses the sections and batches the segments.  There is no CPU fallback.
+without any reference file being edited.  Each call has the reference's granularity -- ONE segment,
+ONE section (main.py:249-250): inputs are read from `ts`, every output series the reference would create is written back
+into `ts` as float64[steps], the error-count vector and message tuple have the reference's shapes, and the two dict side
+effects are kept (SNOW.py:60-63 siminfo['ICEFG'], PWATER.py:89-93 uci['PARAMETERS']['CSNOFG']).  When the caller is
+`hsp2.main`, the work is NOT done at that granularity: the first call of a segment advances a whole window of the
+operation sequence's segments through all their sections in one fused batch and the later calls are served from its
+columns (lazybatch.py); a call that cannot be matched to such a batch runs its one segment, one section on the GPU by
+itself.  Ensembles that do not need the reference dispatcher use hspsquared_b200.engine.LandBatch directly.  There is no
+CPU fallback.
 """
 from __future__ import annotations
 
@@ -72,6 +75,12 @@ def _run_section(section, operation, siminfo, uci, ts, **eff_kw):
     steps = int(siminfo["steps"])
     if steps != cal.steps:
         raise ValueError("siminfo['steps'] does not match start/stop/delt")
+    # called from hsp2.main: all segments of the window were advanced together, fused, on the first call (lazybatch.py)
+    from . import lazybatch
+
+    served = lazybatch.serve(section, operation, siminfo, uci, ts, cal, DEVICE)
+    if served is not None:
+        return served, cal
     tables = {"ACTIVITY": {section: 1}, section: uci}
     names = [n for n in INPUTS[section] if n in ts]
     store = SegmentStore.from_tables(operation, [tables], cal, ext_names=[k for k in ts.keys()], **eff_kw)

@@ -111,11 +111,24 @@ OUTSTEP_FREQ = {3: "D", 4: "ME", 5: "YE"}  # io.py:76,83,90 ('M' and 'Y' in the 
 
 
 def period_bins(tindex, outstep):
-    """-> (bin_of_step int32[len(tindex)], labels): which period of `tindex.resample(freq)` every interval falls in, asked of
-    pandas itself so that the binning (calendar days of the interval-END labels, month-end bins closed on the right ...) is
-    the reference's by construction."""
+    """-> (bin_of_step int32[len(tindex)], labels): which period of the reference's `resample(freq, origin='start')` every
+    interval falls in (hsp2io/io.py:76-92).
+
+    outstep 3 (daily): in the pandas the reference pins (1.2 / 2.x; environment.yml) 'D' is a fixed 24-hour Tick, for which
+      origin='start' anchors the bins at the FIRST label of the frame: period k holds the labels in
+      [tindex[0] + k days, tindex[0] + (k+1) days) and is labelled tindex[0] + k days.  An hourly run from midnight has its
+      first label at 01:00, so every day holds 24 values and is labelled 01:00 -- not the calendar days that pandas 3 (where
+      'D' became a calendar offset and ignores origin=) would give.  Computed here directly, identical to
+      `resample('24h', origin='start')` in every pandas (tests/test_results.py pins that).
+    outstep 4 / 5 (month / year ends): calendar offsets, for which origin= never had an effect; asked of pandas itself."""
     import pandas as pd
 
+    if outstep == 3:
+        if len(tindex) == 0:
+            return np.zeros(0, dtype=np.int32), tindex[:0]
+        day = pd.Timedelta(days=1)
+        bins = np.asarray((tindex - tindex[0]) // day, dtype=np.int32)
+        return np.ascontiguousarray(bins), pd.DatetimeIndex(tindex[0] + day * np.arange(int(bins[-1]) + 1))
     sizes = pd.Series(np.zeros(len(tindex), dtype=np.int8), index=tindex).resample(OUTSTEP_FREQ[outstep]).size()
     return np.repeat(np.arange(len(sizes), dtype=np.int32), sizes.to_numpy()), sizes.index
 

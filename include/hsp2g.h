@@ -165,7 +165,8 @@ int hsp2g_set_kernel_image(hsp2g_batch *b, const void *image, size_t nbytes, con
 /* Period aggregation of saved float32 series on the device: what IOManager.write_ts computes with pandas for outstep 3 / 4 / 5
  * (hsp2io/io.py:74-94: last, sum and mean per day / month / year of the float32 frame save_timeseries hands it).
  * d_src [tile][nsteps][ns][32] float32 (hsp2g_set_output_dtype(HSP2G_F32)); bin_of_step[t] = period of interval t (host array,
- * non-decreasing, < nbins; the host takes it from pandas so that the binning is the reference's); d_dst
+ * non-decreasing, < nbins; hspsquared_b200/results.py period_bins computes it: days are 24-hour periods anchored at the run's
+ * first label, as `resample('D', origin='start')` bins them in the pandas the reference pins, months / years calendar periods); d_dst
  * [tile][nbins][ns][3][32] float32 with the three statistics in the order last, sum, mean.  Sums are pandas' compensated
  * float32 sums over the non-NaN values; an all-NaN period gives last = NaN, sum = 0, mean = NaN.  One call covers whole periods:
  * cut the run into chunks that end where periods end (the compensated sum of a period is not carried from call to call). */

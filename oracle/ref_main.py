@@ -56,9 +56,12 @@ class MemoryBackend:
             pass
 
 
-def test10_land_model(start="1976-01-01", stop="1976-04-01"):
+def test10_land_model(start="1976-01-01", stop="1976-04-01", clones=1):
     """UCI object + input series for test10's PERLND P001 and IMPLND I001 (tables of hspsquared_b200/test10.py, EXT SOURCES
-    of test10.uci:891-914 as in ref_harness.TEST10_EXT), SAVE tables = the SaveTable.csv defaults."""
+    of test10.uci:891-914 as in ref_harness.TEST10_EXT), SAVE tables = the SaveTable.csv defaults.
+    clones > 1: P001..Pnnn and I001..Innn interleaved in the operation sequence, each with its own parameters and MFACTORs;
+    every fifth PERLND runs without SNOW (another activity mask, and its PWATER finds the ICEFG the previous segment's SNOW
+    left in siminfo)."""
     import pandas as pd
 
     m = H.load()
@@ -68,6 +71,8 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01"):
     imp["ACTIVITY"]["IQUAL"] = 1  # test10.uci:173-177 switches IQUAL on for IMPLND 1
     imp["IQUAL"] = test10.iqual_tables()
     tables = {"PERLND": ("P001", test10.perlnd(), PERLND_ACTS), "IMPLND": ("I001", imp, IMPLND_ACTS)}
+    if clones > 1:
+        return _cloned_model(u, tables, clones, start, stop)
     rows = []
     for op, (seg, t, acts) in tables.items():
         u.uci[(op, "GENERAL", seg)] = {"ACTIVITY": {a: int(t["ACTIVITY"].get(a, 0)) for a in acts}}
@@ -85,6 +90,43 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01"):
     u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": 1}
     wdm = H.read_wdm(H.TEST10_WDM)
     return u, wdm
+
+
+def _cloned_model(u, tables, clones, start, stop):
+    import pandas as pd
+
+    rows = []
+    for k in range(clones):
+        for op, (seg0, t0, acts) in tables.items():
+            seg = "%s%03d" % (seg0[0], k + 1)
+            t = copy.deepcopy(t0)
+            f = 1.0 + 0.004 * k
+            if op == "PERLND":
+                t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})  # SNOW + PWATER (+ ATEMP off): the water budget sections
+                p = t["PWATER"]["PARAMETERS"]
+                p["LZSN"], p["INFILT"], p["UZSN"] = p["LZSN"] * f, p["INFILT"] / f, p["UZSN"] * f
+                if k % 5 == 4:
+                    t["ACTIVITY"]["SNOW"] = 0
+                    p["CSNOFG"] = 0
+            else:
+                t["ACTIVITY"].update({"SOLIDS": 0, "IWTGAS": 0, "IQUAL": 0})
+                t["IWATER"]["PARAMETERS"]["RETSC"] = t["IWATER"]["PARAMETERS"]["RETSC"] * f
+                if k % 3 == 0:
+                    t["SNOW"].setdefault("FLAGS", {})["ICEFG"] = 0
+            t["SNOW"]["PARAMETERS"]["SNOWCF"] = t["SNOW"]["PARAMETERS"]["SNOWCF"] * f
+            u.uci[(op, "GENERAL", seg)] = {"ACTIVITY": {a: int(t["ACTIVITY"].get(a, 0)) for a in acts}}
+            for act, tab in t.items():
+                if act == "ACTIVITY":
+                    continue
+                ui = copy.deepcopy(tab)
+                ui["SAVE"] = {kk: 1 for kk in test10.SAVE_DEFAULT.get(act, ())}
+                u.uci[(op, act, seg)] = ui
+            rows.append((op, seg, 60))
+            u.ddext_sources[(op, seg)] = [Row(dsn, mf * (1.0 + 0.01 * k) if name == "PREC" else mf, name, tran, "")
+                                          for dsn, mf, tran, name in H.TEST10_EXT[op]]
+    u.opseq = pd.DataFrame(rows, columns=["OPERATION", "SEGMENT", "INDELT_minutes"])
+    u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": 1}
+    return u, H.read_wdm(H.TEST10_WDM)
 
 
 def run_main(uci_obj, inputs, saveall=False):

@@ -606,7 +606,9 @@ def check_period_aggregation(n=40, days=75):
             df = pd.DataFrame(out[:, :, i], index=tindex, columns=[s.split("_", 1)[1] + "." + s.split("_", 1)[0] for s in saved])
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")  # pandas 3: origin= has no effect for calendar frequencies (it says so)
-                r = df.resample({3: "D", 4: "ME", 5: "YE"}[outstep], origin="start")
+                # daily: the 24-hour Tick anchored at the first label, which is what 'D' with origin='start' means in the pandas
+                # the reference pins (results.period_bins)
+                r = df.resample({3: "24h", 4: "ME", 5: "YE"}[outstep], origin="start")
             for stat, want in enumerate((r.last(), r.sum(), r.mean())):
                 assert want.index.equals(labels)
                 w = want.to_numpy()
@@ -643,3 +645,135 @@ class FrameSinkBackend:
 
     def write_ts(self, data_frame, category, operation=None, segment=None, activity=None, *a, **k):
         self.calls[(operation, segment, activity)] = data_frame
+
+
+def check_doe(doe_list, device=0):
+    """doe.run_doe (mainDoE.py:19-140 as ONE batch of (run, segment) rows) against the oracle run by run: every saved series
+    and every error vector of every (run, segment) equals the oracle on that run's tables."""
+    from hspsquared_b200 import doe as DOE
+
+    case = CASES.build_cases()["p001_snow_pwater"]
+    case = dict(case, steps=24 * 100)
+    si = CASES.siminfo_for(case)
+    si["time_unit"] = "us"
+    forc = CASES.forcings(case)
+    t2 = copy.deepcopy(case["tables"])
+    t2["PWATER"]["PARAMETERS"]["LZSN"] = 6.0
+    segments = {"P001": case["tables"], "P002": t2}
+    forcings = {"P001": forc, "P002": {k: v * (1.1 if k == "PREC" else 1.0) for k, v in forc.items()}}
+    results, errors = DOE.run_doe("PERLND", segments, forcings, si, doe_list, chunk=700, device=device)
+    assert set(results) == {"1", "2", "5", "10", "12", "13", "14", "15"}
+    runlist = DOE.make_runlist(doe_list)
+    for run in results:
+        for seg in segments:
+            tabs = DOE.tables_for_run("PERLND", seg, segments[seg], runlist[run])
+            ts = dict(forcings[seg])
+            e = CASES.run_segment("PERLND", tabs, ts, dict(si), ORACLE_ACTS)
+            for k, g in results[run][seg].items():
+                if GPU_EXACT:
+                    assert np.array_equal(g, ts[k], equal_nan=True), (run, seg, k)
+                else:
+                    assert rel_err(g, ts[k]) <= RTOL, (run, seg, k)
+            for a in e:
+                assert np.array_equal(errors[run][seg][a], e[a]), (run, seg, a)
+    # the runs really differ
+    assert not np.array_equal(results["1"]["P001"]["SURO"], results["2"]["P001"]["SURO"])
+    # ICEFG 0 / 1 (runs 14 / 15): the ice content of the pack grows only with ICEFG on (SNOW.py:461-485), and PWATER's
+    # frozen-ground infiltration factor follows it (PWATER.py:295-296)
+    assert results["15"]["P001"]["PACKI"].max() > results["14"]["P001"]["PACKI"].max()
+    assert not np.array_equal(results["14"]["P001"]["INFFAC"], results["15"]["P001"]["INFFAC"])
+    assert np.array_equal(results["12"]["P002"]["CEPS"], results["14"]["P002"]["CEPS"])  # untouched segment: same run
+    return results
+
+
+# ---- a dispatcher shaped like hsp2.main (main.py:91-275) for boxes without the reference tree: the same local variable
+# names, the same call, so that the drop-in activities find it the way they find main() (lazybatch.main_context)
+_DISPATCH_SERIES = {}
+
+
+def get_timeseries(io_manager, ext_sourcesdd, siminfo):  # noqa: D401 -- stands in for utilities.get_timeseries
+    return {k: v.copy() for k, v in _DISPATCH_SERIES[ext_sourcesdd].items()}
+
+
+def _dispatch_like_main(io_manager, uci_obj, registry):
+    import pandas as pd
+
+    opseq, uci, ddext_sources, siminfo = uci_obj["opseq"], uci_obj["uci"], uci_obj["ddext_sources"], uci_obj["siminfo"]
+    ddlinks = {}
+    results, errors_of = {}, {}
+    for _, operation, segment, delt in opseq.itertuples():
+        siminfo["delt"] = delt
+        ts = get_timeseries(io_manager, ddext_sources[(operation, segment)], siminfo)
+        flags = uci[(operation, "GENERAL", segment)]["ACTIVITY"]
+        for activity, function in registry[operation].items():
+            if (activity in flags) and (not flags[activity]):
+                continue
+            if (operation, activity, segment) not in uci:
+                continue
+            ui = uci[(operation, activity, segment)]
+            if operation == "PERLND" and activity in ("SEDMNT", "PWTGAS"):
+                ui["PARAMETERS"]["CSNOFG"] = uci[(operation, "PWATER", segment)]["PARAMETERS"]["CSNOFG"]
+            if operation == "PERLND" and activity == "PSTEMP":
+                ui["PARAMETERS"]["AIRTFG"] = flags["ATEMP"]
+            errors, errmessages = function(io_manager, siminfo, ui, ts)
+            errors_of[(operation, segment, activity)] = np.asarray(errors)
+        results[(operation, segment)] = ts
+    del pd
+    return results, errors_of
+
+
+def check_lazy_dispatch(n=24, device=0):
+    """The drop-in activities called one (segment, activity) at a time by a dispatcher shaped like hsp2.main, over n clones of
+    the CBP full-chain PERLND and n of test10's IMPLND 1 with per-segment parameters and forcings: every series left in ts and
+    every error vector equals the oracle's run of that segment, while the work was done in one fused batch per operation."""
+    import pandas as pd
+
+    from hspsquared_b200 import lazybatch
+
+    cases = CASES.build_cases()
+    uci, rows, ddext = {}, [], {}
+    _DISPATCH_SERIES.clear()
+    si = None
+    for op, cname in (("PERLND", "cbp_fullchain"), ("IMPLND", "i001_test10")):
+        case = cases[cname]
+        s = CASES.siminfo_for(case)
+        steps = min(24 * 45, s["steps"])
+        if si is None:
+            si = dict(s, steps=steps, stop=s["start"] + np.timedelta64(steps * int(s["delt"]), "m"), time_unit="us")
+        forc = {k: v[:steps] for k, v in CASES.forcings(case).items()}
+        for k in range(n):
+            seg = "%s%03d" % (op[0], k + 1)
+            t = copy.deepcopy(case["tables"])
+            f = 1.0 + 0.01 * k
+            if op == "PERLND":
+                t["PWATER"]["PARAMETERS"]["LZSN"] *= f
+                t["PWATER"]["PARAMETERS"]["INFILT"] /= f
+            else:
+                t["IWATER"]["PARAMETERS"]["RETSC"] *= f
+            t["SNOW"]["PARAMETERS"]["SNOWCF"] *= f
+            uci[(op, "GENERAL", seg)] = {"ACTIVITY": dict(t["ACTIVITY"])}
+            for act, tab in t.items():
+                if act != "ACTIVITY":
+                    uci[(op, act, seg)] = tab
+            rows.append((op, seg, int(s["delt"])))
+            ddext[(op, seg)] = (op, seg)
+            _DISPATCH_SERIES[(op, seg)] = {kk: (v * f if kk == "PREC" else v.copy()) for kk, v in forc.items()}
+    opseq = pd.DataFrame(rows, columns=["OPERATION", "SEGMENT", "INDELT_minutes"])
+    activities.DEVICE = device
+    registry = {op: {a: fn for a, fn in acts.items() if a not in ("PQUAL", "IQUAL")} for op, acts in activities.ACTIVITIES.items()}
+    lazybatch.reset()
+    got, got_err = _dispatch_like_main(None, {"opseq": opseq, "uci": copy.deepcopy(uci), "ddext_sources": ddext,
+                                              "siminfo": dict(si)}, registry)
+    stats = dict(lazybatch.STATS)
+    assert stats["windows"] == 2 and stats["segments"] == 2 * n and stats["fallback"] == 0 and stats["launches"] == 2, stats
+    for (op, seg), ts in got.items():
+        tables = {"ACTIVITY": uci[(op, "GENERAL", seg)]["ACTIVITY"]}
+        tables.update({act: copy.deepcopy(tab) for (o, act, s2), tab in uci.items() if o == op and s2 == seg and act != "GENERAL"})
+        ref = dict(_DISPATCH_SERIES[(op, seg)])
+        ref_err = CASES.run_segment(op, tables, ref, dict(si), ORACLE_ACTS)
+        assert set(ref) <= set(ts), sorted(set(ref) - set(ts))
+        bad = compare(ref, ts, exact=GPU_EXACT)
+        assert not bad, (op, seg, bad[:6])
+        for a, e in ref_err.items():
+            assert np.array_equal(got_err[(op, seg, a)], e), (op, seg, a)
+    return stats

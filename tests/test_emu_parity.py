@@ -111,3 +111,7 @@ def test_abi_error_behaviour_and_smallest_shapes():
 
 def test_option_word_kernels_equal_the_general_ones():
     parity.check_option_word_kernels()
+
+
+def test_dispatcher_calls_are_served_from_fused_batches():
+    parity.check_lazy_dispatch(n=12)

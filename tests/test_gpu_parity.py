@@ -372,3 +372,17 @@ def test_watershed_wdm_to_frames(tmp_path):
     """BASELINE.json configs[4] in miniature on the GPU: 3,000 full-chain segments on 12 gages of a WDM file, three simulated
     months, float32 frames out; sampled segments equal the oracle."""
     parity.check_watershed(tmp_path, n=3000, gages=12, days=90, sample=(0, 1234, 2999), chunk=720)
+
+
+def test_doe_on_gpu():
+    """mainDoE's parameter sweep (mainDoE.py:19-140) as one batch of (run, segment) rows through the CUDA library: every run of
+    the reference's own docstring example equals the oracle on that run's tables."""
+    from .test_doe import DOE_LIST
+
+    parity.check_doe(DOE_LIST)
+
+
+def test_dispatcher_calls_are_served_from_fused_batches():
+    """SURVEY 8b "granularity mismatch" on the GPU: (segment, activity) calls of a dispatcher shaped like hsp2.main are served
+    from one fused batch per operation (hspsquared_b200/lazybatch.py), every series and error vector equal to the oracle's."""
+    parity.check_lazy_dispatch(n=40)

@@ -48,3 +48,32 @@ def test_main_with_dropin_activities_writes_the_same_frames(saveall):
         assert a.dtype == b.dtype == np.float32
         assert np.array_equal(a, b, equal_nan=True), (key, [c for i, c in enumerate(df.columns)
                                                             if not np.array_equal(a[:, i], b[:, i], equal_nan=True)])
+
+
+def test_main_over_many_segments_is_served_from_one_fused_batch():
+    """SURVEY 8b "granularity mismatch": the unmodified main() walks 70 PERLND + 70 IMPLND clones (parameters and met
+    factors varied per segment) one (segment, activity) at a time; the drop-ins advance each operation's segments in ONE fused
+    batch on the first call and serve every later call from it.  Frames identical to the stock Numba run, a handful of kernel
+    launches instead of one per (segment, activity)."""
+    from hspsquared_b200 import activities, lazybatch
+    from oracle import ref_main as R
+
+    uci, wdm = R.test10_land_model("1976-01-01", "1976-02-15", clones=70)
+    ref = R.run_main(uci, wdm)
+    cfg = H.load()["configuration"]
+    saved = activities.install(cfg)
+    lazybatch.reset()
+    try:
+        got = R.run_main(uci, wdm)
+        stats = dict(lazybatch.STATS)
+    finally:
+        activities.uninstall(saved, cfg)
+    assert set(got) == set(ref) and len(ref) == 56 * 2 + 14 + 70 * 2  # (segment, activity) frames
+    for key, df in ref.items():
+        g = got[key]
+        assert list(g.columns) == list(df.columns) and g.index.equals(df.index), key
+        assert np.array_equal(g.to_numpy(), df.to_numpy(), equal_nan=True), key
+    # two windows (one per operation), every land section of every segment served from them, one launch per window and chunk
+    assert stats["windows"] == 2 and stats["segments"] == 140, stats
+    assert stats["served"] == len(ref) and stats["fallback"] == 0, stats
+    assert stats["launches"] == 3, stats  # PERLND with and without SNOW (two activity masks), IMPLND

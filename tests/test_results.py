@@ -108,3 +108,29 @@ def test_save_qual_batch_frames_equal_reference_frames():
 
 def test_period_aggregation_equals_pandas():
     parity.check_period_aggregation()
+
+
+def test_daily_bins_are_anchored_at_the_first_label():
+    """IOManager.write_ts resamples with ('D', origin='start') (hsp2io/io.py:76-78): 'D' is a 24-hour Tick in the pandas the
+    reference pins, so the bins start at the frame's first label.  A 48-hour hourly run from midnight therefore has 2 periods of
+    24 values labelled 01:00 -- not 23 / 24 / 1 values on calendar days."""
+    import pandas as pd
+
+    from hspsquared_b200.results import period_bins
+
+    tindex = pd.date_range("1976-03-01", periods=49, freq="60min")[1:]  # interval-END labels, main.py:94
+    bins, labels = period_bins(tindex, 3)
+    assert np.array_equal(np.bincount(bins), [24, 24])
+    assert list(labels) == [pd.Timestamp("1976-03-01 01:00"), pd.Timestamp("1976-03-02 01:00")]
+    want = pd.Series(np.arange(48.0), index=tindex).resample("24h", origin="start").sum()
+    assert want.index.equals(labels) and list(want) == [float(sum(range(24))), float(sum(range(24, 48)))]
+    # a run that starts mid-day, 30-minute step: still whole 24-hour periods from the first label
+    t2 = pd.date_range("1976-03-01 14:00", periods=48 * 3 + 1, freq="30min")[1:]
+    b2, l2 = period_bins(t2, 3)
+    assert np.array_equal(np.bincount(b2), [48, 48, 48]) and l2[0] == pd.Timestamp("1976-03-01 14:30")
+    w2 = pd.Series(np.ones(len(t2)), index=t2).resample("24h", origin="start").size()
+    assert w2.index.equals(l2)
+    # months and years are calendar periods (origin= has no effect on calendar offsets in any pandas)
+    t3 = pd.date_range("1976-01-01", periods=24 * 70 + 1, freq="60min")[1:]
+    b3, l3 = period_bins(t3, 4)
+    assert np.array_equal(np.bincount(b3), [24 * 31 - 1, 24 * 29, 24 * 10 + 1]) and l3[0] == pd.Timestamp("1976-01-31")
