@@ -217,52 +217,104 @@ def time_cpu(nthreads, nseg, nsteps, min_seconds, max_reps=5000):
     return nseg * nsteps * reps / t_total, used, reps, t_total
 
 
-def cpu_baseline(budget_s=12.0):
+WORKLOAD = ("test10 PERLND SNOW+PWATER replicated to %d segments/GPU, jittered params, 10-yr hourly synthetic met, "
+            "default SAVE (13 SNOW + 11 PWATER)")
+
+
+def numba_reference(procs, per_proc, serial_segments, repeats=1, warm=1, timeout=900):
+    """The UNMODIFIED reference's Numba implementation of the path (installed under baseline/_ref), serial and in a
+    multiprocessing pool, in a subprocess of its own (oracle/numba_baseline.py) -> its JSON record."""
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    env.setdefault("NUMBA_CACHE_DIR", "/tmp/hsp2_ref_numba_cache")
+    cmd = [sys.executable, "-W", "ignore", "-m", "oracle.numba_baseline", "--procs", str(procs), "--segments-per-proc", str(per_proc),
+           "--serial-segments", str(serial_segments), "--repeats", str(repeats), "--warm", str(warm)]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+        for line in reversed(r.stdout.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": "oracle.numba_baseline produced no record: " + (r.stderr or "")[-300:]}
+    except Exception as ex:
+        return {"unavailable": repr(ex)}
+
+
+def port_baseline(cores, budget_s=8.0):
+    """The C restatement of the same cores (oracle/hsp2_oracle.c), OpenMP over segments: a second, faster CPU figure"""
     from oracle import oracle
 
     oracle.build()
-    cores = host_threads()
     nsteps = 8784
     nseg = min(4096, 64 * cores)
     v, used, reps, tt = time_cpu(cores, nseg, nsteps, budget_s)
-    vs, _, _, _ = time_cpu(1, 48, nsteps, 3.0)
+    vs, _, _, _ = time_cpu(1, 48, nsteps, 2.0)
     return {"value": v, "unit": "segment-timesteps/s", "cores": used, "kind": "port",
             "sample": "%d segments x %d hourly intervals (1976), SNOW+PWATER, x%d repeats, %.1f s; OpenMP over segments"
-                      % (nseg, nsteps, reps, tt),
-            "serial_value": vs, "serial_cores": 1, "host_cpus": cores}
+                      % (nseg, nsteps, reps, tt), "serial_value": vs}
+
+
+def cpu_baseline():
+    """The CPU implementations of the path on this box's host cores, beside the GPU number: (1) the reference itself -- its
+    Numba kernels through its own snow() / pwater(), serial and multiprocess over segments (kind "reference"; kernel-only =
+    time inside the @njit cores, SURVEY.md 8d; wrapper-inclusive = what a call of the reference costs with its pandas glue);
+    (2) the C port with OpenMP.  A reported baseline, not the optimisation target."""
+    cores = host_threads()
+    ref = numba_reference(cores, 12, 16)
+    try:
+        port = port_baseline(cores)
+    except Exception as ex:
+        port = {"error": repr(ex)}
+    if "multiprocess" in ref:
+        m = ref["multiprocess"]
+        return {"value": m["kernel_only"], "unit": "segment-timesteps/s", "cores": m["processes"], "kind": "reference",
+                "sample": "%d segments x %d hourly intervals (1976) of the bench ensemble in a multiprocessing.Pool(%d): time inside "
+                          "the reference's @njit cores _snow_ + _pwater_ (kernel-only, slowest process)" % (m["segments"], m["intervals"], m["processes"]),
+                "wrapper_inclusive_value": m["wrapper_inclusive"], "serial_value": ref["serial"]["kernel_only"],
+                "serial_wrapper_inclusive_value": ref["serial"]["wrapper_inclusive"], "serial_cores": 1, "host_cpus": cores,
+                "implementation": ref["implementation"], "numba": ref.get("numba"), "loaded_from": ref.get("reference_loaded_from"),
+                "port": port}
+    port["reference_unavailable"] = ref.get("unavailable")
+    port["host_cpus"] = cores
+    return port
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU implementation of the path on the host cores (oracle port; see module docstring)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores -- the unmodified respec/HSPsquared
+    package from baseline/_ref, its snow() and pwater() for segments of the same synthetic ensemble in a multiprocessing pool over
+    all cores.  One step = one pass of the pool over a bounded sample (a few dozen segment-years per process).  value = kernel-only
+    rate (time inside the @njit cores); the wrapper-inclusive rate and the C port's are in the same line."""
     if rank != 0:
         return
-    from oracle import oracle
-
-    oracle.build()
     cores = host_threads()
-    nsteps, nseg = 8784, min(4096, 64 * cores)
-    forc, par, mon, cal = cpu_sample(nseg, nsteps)
-    for _ in range(max(1, args.warmup)):
-        oracle.perlnd_batch(nsteps, 60.0, forc, par, mon, cal, cores)
-    t0 = time.perf_counter()
-    used = 0
-    for _ in range(args.steps):
-        _s, _e, used = oracle.perlnd_batch(nsteps, 60.0, forc, par, mon, cal, cores)
-    dt = time.perf_counter() - t0
-    v = nseg * nsteps * args.steps / dt
-    sample = "%d segments x %d hourly intervals per step, SNOW+PWATER, default SAVE set computed" % (nseg, nsteps)
+    per_proc = 32
+    ref = numba_reference(cores, per_proc, 8, repeats=args.steps, warm=max(1, args.warmup))
+    n = N_SEG_PER_GPU
+    config = {"workload": WORKLOAD % n, "segments_per_gpu": n, "intervals_per_step": 438, "forcings": 6, "saved_series": 24}
+    if "multiprocess" in ref:
+        m = ref["multiprocess"]
+        v = m["kernel_only"]
+        sample = ("bounded sample of the configuration: %d segments x %d hourly intervals (one year) per step in a "
+                  "multiprocessing.Pool(%d); time inside the reference's @njit cores, slowest process" % (m["segments"], m["intervals"], m["processes"]))
+        cb = {"value": v, "unit": "segment-timesteps/s", "cores": m["processes"], "kind": "reference", "sample": sample,
+              "wrapper_inclusive_value": m["wrapper_inclusive"], "serial_value": ref["serial"]["kernel_only"],
+              "implementation": ref["implementation"], "numba": ref.get("numba"), "loaded_from": ref.get("reference_loaded_from")}
+        ms = 1e3 * m["wall_s_per_pass"]
+    else:  # no installed reference on this box: the C port stands in (kind "port")
+        cb = port_baseline(cores, budget_s=max(4.0, 0.5 * args.steps))
+        cb["reference_unavailable"] = ref.get("unavailable")
+        v, ms = cb["value"], None
     line = {
         "impl": "reference", "metric": "segment-timesteps/sec PERLND SNOW+PWATER fp64", "value": v,
         "unit": "segment-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "test10 PERLND SNOW+PWATER replicated, jittered params, hourly synthetic met "
-                               "(CPU sample of the 100k-segment x 10-yr job)", "segments_per_step": nseg,
-                   "intervals_per_step": nsteps},
-        "cpu_baseline": {"value": v, "unit": "segment-timesteps/s", "cores": used, "kind": "port", "sample": sample},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "segment-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["c_port_openmp"] = port_baseline(cores, budget_s=4.0) if "multiprocess" in ref else None
+    except Exception as ex:
+        line["c_port_openmp"] = {"error": repr(ex)}
     print(json.dumps(line))
 
 
@@ -529,8 +581,7 @@ def main():
         "metric": "segment-timesteps/sec PERLND SNOW+PWATER fp64", "value": value, "unit": "segment-timesteps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "test10 PERLND SNOW+PWATER replicated to %d segments/GPU, jittered params, 10-yr hourly "
-                               "synthetic met, default SAVE (13 SNOW + 11 PWATER)" % n,
+        "config": {"workload": WORKLOAD % n,
                    "segments_per_gpu": n, "intervals_per_step": Tc, "forcings": 6, "saved_series": 24,
                    "series_layout": "%s (%s)" % (args.layout, "[interval][row][segment], as the reference's ts arrays"
                                                  if args.layout == "plain" else "[tile][interval][row][32]"),

@@ -66,6 +66,7 @@ _PROTOS = {
     "hsp2g_pack_series": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "hsp2g_unpack_series": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "hsp2g_sync": (C.c_int, [_h]),
+    "hsp2g_sync_oldest": (C.c_int, [_h]),
     "hsp2g_get_errors": (C.c_int, [_h, _i64p, C.c_int64]),
     "hsp2g_reset_errors": (C.c_int, [_h]),
     "hsp2g_set_output_dtype": (C.c_int, [_h, C.c_int]),

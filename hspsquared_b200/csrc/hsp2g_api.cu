@@ -1120,6 +1120,14 @@ int hsp2g_sync(hsp2g_batch *b) {
     return drain_timing(b);
 }
 
+int hsp2g_sync_oldest(hsp2g_batch *b) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    // the slot the NEXT hsp2g_run_host call will use holds the older of the (at most two) chunks in flight
+    CU(cudaEventSynchronize(b->slot[b->next_slot].d2h_done));
+    return 0;
+}
+
 int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld) {
     if (!b || !err) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");

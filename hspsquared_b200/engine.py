@@ -266,6 +266,7 @@ class LandBatch:
         elif out.shape != (nsteps, self.ns, self.n) or out.dtype != self.out_dtype or not out.flags.c_contiguous:
             raise ValueError("out must be C-contiguous %s %r" % (self.out_dtype, (nsteps, self.ns, self.n)))
         self._keep.append((f, out))
+        del self._keep[:-4]  # at most two chunks are in flight: older buffers may go
         self._kernel()
         _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(nsteps), f.ctypes.data if self.nf and not self.shared else None,
                                               self.n, out.ctypes.data, self.n))
@@ -348,6 +349,10 @@ class LandBatch:
     def sync(self):
         _lib.check(self.lib.hsp2g_sync(self.h))
         self._keep = []
+
+    def sync_oldest(self):
+        """Wait until the older of the (at most two) chunks in flight through run_chunk / run_host has arrived on the host."""
+        _lib.check(self.lib.hsp2g_sync_oldest(self.h))
 
     def run(self, forcing, chunk=None):
         """Whole series through host buffers in chunks of `chunk` intervals: forcing [steps][nf][n] -> out

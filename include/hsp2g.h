@@ -196,6 +196,9 @@ void hsp2g_gather_destroy(hsp2g_gather *g);
 int hsp2g_pack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src, int64_t ld, double *dst_tiled);
 int hsp2g_unpack_series(int64_t n_seg, int64_t nsteps, int32_t nrows, const double *src_tiled, double *dst, int64_t ld);
 int hsp2g_sync(hsp2g_batch *b);
+/* Wait only until the OLDER of the (at most two) chunks in flight through hsp2g_run_host has arrived in its host buffer: a
+ * caller that streams results out (save_timeseries' job, utilities.py:292-333) consumes chunk k-1 while chunk k computes. */
+int hsp2g_sync_oldest(hsp2g_batch *b);
 
 /* Error counters (the `errors` vectors returned beside ERRMSGS, main.py:255-257), int64 [n_errors][ld]. */
 int hsp2g_get_errors(hsp2g_batch *b, int64_t *err, int64_t ld);

@@ -16,10 +16,17 @@ import sys
 
 REF_ROOT = os.environ.get("HSP2_REFERENCE", "/root/reference")
 REF_SRC = os.path.join(REF_ROOT, "src")
+# The reference as installed (unmodified, `pip install --no-deps --target baseline/_ref`): git-ignored, but it travels
+# to the GPU box with the tree, where bench.py's CPU baseline times the reference's own Numba kernels (oracle/numba_baseline.py).
+REF_SITE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 def available():
     return os.path.isdir(os.path.join(REF_SRC, "hsp2", "hsp2"))
+
+
+def site_available():
+    return os.path.isdir(os.path.join(REF_SITE, "hsp2", "hsp2"))
 
 
 _loaded = {}
@@ -29,8 +36,11 @@ def load():
     """Import the reference's hot-path modules; returns a dict of module objects."""
     if _loaded:
         return _loaded
+    global REF_SRC
     if not available():
-        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+        if not site_available():
+            raise RuntimeError("reference tree not present at %s (nor installed under %s)" % (REF_ROOT, REF_SITE))
+        REF_SRC = REF_SITE
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/hsp2_ref_numba_cache")
     _orig = _md.version
 

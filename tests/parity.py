@@ -777,3 +777,45 @@ def check_lazy_dispatch(n=24, device=0):
         for a, e in ref_err.items():
             assert np.array_equal(got_err[(op, seg, a)], e), (op, seg, a)
     return stats
+
+
+def check_streaming_sink(tmpdir, n=37, days=9, chunk=50, device=0, pinned=False):
+    """sink.stream_batch (chunks leave the device while the next one computes, a writer thread puts them into the memory-mapped
+    store) against results.save_batch on the whole-run array: every (segment, activity) frame read back from the store equals
+    the frame save_timeseries would hand IOManager.write_ts -- same columns (SAVE flags), float32, same values."""
+    import pandas as pd
+
+    from hspsquared_b200.results import save_batch
+    from hspsquared_b200.sink import NpyResults, stream_batch
+
+    start = np.datetime64("1976-02-01T00:00:00")
+    cal = Calendar(start, start + np.timedelta64(days, "D"), 60, "us")
+    ens = synth.Ensemble("PERLND", n, seed=8, sections=("SNOW", "PWATER"))
+    names = list(synth.PERLND_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
+    tindex = pd.date_range(pd.Timestamp(str(start)), periods=cal.steps + 1, freq="60min")[1:]
+    si = {"tindex": tindex}
+    segs = ["P%03d" % (i + 1) for i in range(n)]
+    tabs = {"SNOW": {k: 1 for k in test10.SAVE_DEFAULT["SNOW"]}, "PWATER": {k: 1 for k in test10.SAVE_DEFAULT["PWATER"]}}
+    tabs["PWATER"]["PET"] = 0  # produced, present in the SAVE table, switched off: must not be stored (io.py:70-72)
+    order = np.argsort(ens.u_airt, kind="stable")  # a device order that differs from the caller's
+    with LandBatch(ens.store(cal), cal, names, "all", device=device, order=order) as b:
+        whole = b.run(f, chunk=chunk)
+        saved = b.save
+    ref = FrameSink()
+    save_batch(ref, si, "PERLND", segs, tabs, saved, whole.astype(np.float32))
+    sink = NpyResults(os.path.join(str(tmpdir), "results"), mode="w")
+    with LandBatch(ens.store(cal), cal, names, "all", device=device, order=order) as b:
+        fdev = np.ascontiguousarray(f[:, b._fperm, :][:, :, b.order])
+        stream_batch(sink, b, si, "PERLND", segs, tabs, lambda t0, t1: np.ascontiguousarray(fdev[t0:t1]), chunk, pinned=pinned)
+    sink.close()
+    store = NpyResults(os.path.join(str(tmpdir), "results"))
+    assert len(ref.calls) == 2 * n
+    for (op, seg, act), (df, save_columns) in ref.calls.items():
+        want = df[[c for c in df.columns if c in save_columns]]  # IOManager.write_ts drops the unsaved columns (io.py:70-72)
+        got = store.read_ts("RESULT", op, seg, act)
+        assert list(got.columns) == list(want.columns), (seg, act)
+        assert got.index.equals(want.index)
+        assert got.to_numpy().dtype == np.float32
+        assert np.array_equal(got.to_numpy(), want.to_numpy(), equal_nan=True), (seg, act)
+    assert "PET" not in store.read_ts("RESULT", "PERLND", segs[0], "PWATER").columns

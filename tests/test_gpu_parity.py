@@ -386,3 +386,10 @@ def test_dispatcher_calls_are_served_from_fused_batches():
     """SURVEY 8b "granularity mismatch" on the GPU: (segment, activity) calls of a dispatcher shaped like hsp2.main are served
     from one fused batch per operation (hspsquared_b200/lazybatch.py), every series and error vector equal to the oracle's."""
     parity.check_lazy_dispatch(n=40)
+
+
+def test_results_stream_into_the_product_store(tmp_path):
+    """north_star subsystem 4 on the GPU: SAVEd series leave the device chunk by chunk into pinned buffers and a writer thread
+    puts them into the NpyResults store (a SupportsWriteTS / SupportsReadTS backend) while the next chunk computes; every frame
+    read back equals what save_timeseries would have written (2,500 segments in a device order that differs from the caller's)."""
+    parity.check_streaming_sink(tmp_path, n=2500, days=20, chunk=100, pinned=True)
