@@ -393,3 +393,47 @@ def test_results_stream_into_the_product_store(tmp_path):
     puts them into the NpyResults store (a SupportsWriteTS / SupportsReadTS backend) while the next chunk computes; every frame
     read back equals what save_timeseries would have written (2,500 segments in a device order that differs from the caller's)."""
     parity.check_streaming_sink(tmp_path, n=2500, days=20, chunk=100, pinned=True)
+
+
+def test_handles_driven_from_threads_of_one_process():
+    """SURVEY 8b "Threading": one handle per thread, several threads of ONE process (the reference's kernels hold the GIL; this
+    library's calls release it in ctypes).  Six threads each own a batch on cuda:0 and run it concurrently -- creation, uploads,
+    kernel builds, chunked runs, state and error read-back all overlap -- and every thread's result equals the same batch run
+    alone."""
+    import threading
+
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar("1976-02-01", "1976-02-11", 60, "us")
+    jobs = []
+    for k in range(6):
+        op, secs = (("PERLND", ("SNOW", "PWATER")), ("IMPLND", ("SNOW", "IWATER")))[k % 2]
+        ens = synth.Ensemble(op, 3000 + 37 * k, seed=40 + k, sections=secs)
+        jobs.append((ens, synth.forcing_chunk(ens, cal, 0, cal.steps)))
+
+    def run(job, jit):
+        ens, f = job
+        with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), "all", jit=jit) as b:
+            out = b.run(f, chunk=60)
+            return out, b.get_state(), b.errors()
+
+    alone = [run(j, False) for j in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def worker(i):
+        try:
+            got[i] = run(jobs[i], True)
+        except Exception as ex:  # pragma: no cover
+            errs.append((i, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not errs, errs
+    for (o, st, er), (o2, st2, er2) in zip(alone, got):
+        assert np.array_equal(o, o2, equal_nan=True) and np.array_equal(st, st2, equal_nan=True)
+        assert all(np.array_equal(er[k], er2[k]) for k in er)
