@@ -402,7 +402,9 @@ def main():
                          "tiled = [tile][interval][row][32]")
     ap.add_argument("--sub", type=int, default=None, help="intervals per (tile, sub-chunk) task; default = library's")
     ap.add_argument("--no-jit", action="store_true", help="run the library's general kernels instead of one built for the batch")
-    ap.add_argument("--no-ordered", action="store_true", help="skip the extra divergence-ordered measurement")
+    ap.add_argument("--caller-order", action="store_true", help="keep the ensemble generator's segment order on the device "
+                    "instead of the engine's automatic divergence-aware order")
+    ap.add_argument("--no-ordered", action="store_true", help="skip the extra measurement in the other segment order")
     ap.add_argument("--no-alt-layout", action="store_true", help="skip the extra measurement in the other series layout")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -445,11 +447,20 @@ def main():
     total_chunks = K + W
     if total_chunks * Tc > cal.steps:
         sys.exit("steps*chunk exceeds the 10-year run (%d intervals)" % cal.steps)
-    ens = synth.Ensemble("PERLND", n, seed=1234 + rank, sections=("SNOW", "PWATER"))
+    ens0 = synth.Ensemble("PERLND", n, seed=1234 + rank, sections=("SNOW", "PWATER"))
+    # Segment order on the device: the engine's divergence-aware ordering, automatic -- option word, then a climate key read off
+    # the first week of the batch's own forcings (LandBatch.climate_order).  Same segments, same arithmetic, same bits per
+    # segment; `--caller-order` keeps the generator's order (also measured beside the headline unless --no-ordered).
+    if args.caller_order:
+        ens = ens0
+    else:
+        sample = synth.forcing_chunk(ens0, cal, 0, 24 * 7)
+        ens = ens0.take(LandBatch.climate_order(ens0.store(cal), list(synth.PERLND_FORCINGS), sample))
+        del sample
     store = ens.store(cal)
     save = default_save()
     jit = not args.no_jit
-    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit)
+    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit, order=None)
     if args.sub is not None:
         batch.set_schedule(args.sub)
     npad, nf, ns = batch.npad, batch.nf, batch.ns
@@ -542,16 +553,21 @@ def main():
         except Exception as ex:
             alt = {"error": repr(ex)}
 
-    # ---- the same year with the segments in divergence-aware order (SegmentStore.divergence_order with a climate key):
-    # reported beside the headline, never instead of it
+    # ---- the same year with the segments in the other order (the generator's own / the automatic one): beside the headline
     ordered = None
     if not args.no_ordered:
         try:
             del forc
             torch.cuda.empty_cache()
-            perm = store.divergence_order(keys=(np.floor(ens.u_airt * 16), ens.u_prec))
-            ens2 = ens.take(perm)
-            b2 = LandBatch(ens2.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit)
+            if args.caller_order:
+                sample = synth.forcing_chunk(ens0, cal, 0, 24 * 7)
+                ens2 = ens0.take(LandBatch.climate_order(ens0.store(cal), list(synth.PERLND_FORCINGS), sample))
+                del sample
+                what = "automatic divergence-aware order (LandBatch.climate_order)"
+            else:
+                ens2, what = ens0, "segments in the ensemble generator's own order (no ordering)"
+            b2 = LandBatch(ens2.store(cal), cal, list(synth.PERLND_FORCINGS), save, device=local_rank, layout=args.layout, jit=jit,
+                           order=None)
             if args.sub is not None:
                 b2.set_schedule(args.sub)
             forc2 = [device_forcing(torch, ens2, cal, c * Tc, Tc, npad, dev, b2.forcing_rows, args.layout) for c in range(total_chunks)]
@@ -560,9 +576,7 @@ def main():
             b2.close()
             del forc2
             torch.cuda.empty_cache()
-            ordered = {"value": seg_steps / (ms2 * 1e-3), "ms_per_step": ms2 / K, "frac": frac_of(ms2),
-                       "key": "option word, then floor(16 * air-temperature jitter), then precipitation jitter "
-                              "(SegmentStore.divergence_order): same segments, same arithmetic, warps see similar weather"}
+            ordered = {"order": what, "value": seg_steps / (ms2 * 1e-3), "ms_per_step": ms2 / K, "frac": frac_of(ms2)}
         except Exception as ex:
             ordered = {"error": repr(ex)}
     forc = None
@@ -585,6 +599,8 @@ def main():
                    "segments_per_gpu": n, "intervals_per_step": Tc, "forcings": 6, "saved_series": 24,
                    "series_layout": "%s (%s)" % (args.layout, "[interval][row][segment], as the reference's ts arrays"
                                                  if args.layout == "plain" else "[tile][interval][row][32]"),
+                   "segment_order": "caller's" if args.caller_order else "automatic: option word, then climate key from the first "
+                                    "week of the batch's forcings (LandBatch.climate_order)",
                    "cache": "inputs of every step (%.2f GB) and outputs (%.2f GB) are far larger than L2; %d distinct "
                             "forcing chunks resident" % (per_f / 1e9, Tc * ns * npad * 8 / 1e9, n_forcing_chunks),
                    "kernel": kname, "parallelism": "segments sharded over %d GPU(s), no collective" % world},
@@ -594,13 +610,20 @@ def main():
                      "avg_launch_ms": avg_launch_s * 1e3},
         "gpu_launches": int(l1 - l0) - W,
         "other_layout": alt,
-        "divergence_ordered": ordered,
+        "other_segment_order": ordered,
         "clocks": clocks,
         "parity": parity,
     }
     if e2e is not None:
         line["e2e"] = e2e
     batch.close()
+    if world > 1 and not args.no_extras:
+        try:
+            r = run_sharded_ensemble(torch, dev, local_rank, rank, world, dist, cal, stream, peak, jit)
+            if rank == 0:
+                line["ensemble_1m_sharded"] = r
+        except Exception as ex:
+            line["ensemble_1m_sharded"] = {"error": repr(ex)}
     if not args.no_extras:
         try:
             line["other_configs"] = run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak)
@@ -881,6 +904,76 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
     finally:
         batch.close()
         torch.cuda.empty_cache()
+
+
+def run_sharded_ensemble(torch, dev, local_rank, rank, world, dist, cal, stream, peak, jit, n_total=1_000_000, Tc=128, K=12, W=3):
+    """BASELINE.json configs[2]: ONE 1M-segment PERLND + IMPLND water-balance ensemble (500k + 500k) split over the ranks with
+    dist.shard_bounds (hspsquared_b200.dist.ShardedBatch); every rank advances its shard of both operations, device-resident;
+    no collective on the data path; at the end the per-segment sums of the runoff series are gathered to every rank over NCCL
+    (the numbers a calibration run keeps per ensemble member).  Strong scaling: the total is fixed, per-GPU work shrinks with N."""
+    import torch.distributed as tdist
+
+    from hspsquared_b200 import synth, test10
+    from hspsquared_b200.dist import ShardedBatch
+
+    half = n_total // 2
+    parts = []
+    for op, secs, save in (("PERLND", ("SNOW", "PWATER"), default_save()),
+                           ("IMPLND", ("SNOW", "IWATER"), ["SNOW_" + k for k in test10.SAVE_DEFAULT["SNOW"]] +
+                            ["IWATER_" + k for k in test10.SAVE_DEFAULT["IWATER"]])):
+        ens = synth.Ensemble(op, half, seed=777, sections=secs)
+        sb = ShardedBatch(lambda lo, hi, e=ens: e.shard(lo, hi).store(cal), half, cal, list(synth.PERLND_FORCINGS), save,
+                          device=local_rank, layout="plain", jit=jit, order=None)
+        shard = ens.shard(sb.lo, sb.hi)
+        b = sb.batch
+        forc = [device_forcing(torch, shard, cal, c * Tc, Tc, b.npad, dev, b.forcing_rows, "plain") for c in range(K + W)]
+        outs = out_buffers(torch, b.npad, Tc, b.ns, dev, "plain")
+        flow_row = b.save_rows.index("PWATER_SURO" if op == "PERLND" else "IWATER_SURO")
+        parts.append((op, sb, b, forc, outs, flow_row, torch.zeros(b.npad, dtype=torch.float64, device=dev)))
+    torch.cuda.synchronize(dev)
+
+    def step(c, accumulate):
+        for _op, _sb, b, forc, outs, row, acc in parts:
+            b.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
+            if accumulate:
+                with torch.cuda.stream(stream):
+                    acc += outs[c % 2][:, row, :].sum(dim=0)
+
+    for c in range(W):
+        step(c, False)
+    tdist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for c in range(W, W + K):
+        step(c, True)
+    e1.record(stream)
+    tdist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    ms = float(t.item())
+    # the one collective of the job: per-segment runoff sums of every rank, in segment order, on every rank (NCCL all-gather)
+    g0 = time.perf_counter()
+    sums = [sb.gather(acc[: sb.n]) for _op, sb, _b, _f, _o, _r, acc in parts]
+    torch.cuda.synchronize(dev)
+    gather_ms = 1e3 * (time.perf_counter() - g0)
+    res = {"workload": "one %d-segment ensemble = %d PERLND (SNOW+PWATER) + %d IMPLND (SNOW+IWATER), default SAVE sets, split with "
+                       "dist.shard_bounds over %d ranks" % (n_total, half, half, world),
+           "scaling": "strong", "segments_total": n_total, "segments_per_rank": [p[1].n for p in parts], "intervals_per_step": Tc,
+           "steps": K, "warmup": W, "ms_per_step": ms / K, "value": n_total * Tc * K / (ms * 1e-3), "unit": "segment-timesteps/s",
+           "kernels": [p[2].kernel_name() for p in parts],
+           "bytes_per_segment_interval": {"PERLND": 240, "IMPLND": 176},
+           "frac_of_measured_hbm_per_gpu": (half * 240 + half * 176) / world * Tc * K / (ms * 1e-3) / 1e9 / peak,
+           "final_gather": {"what": "per-segment sums of SURO over the timed window, float64, all-gather over NCCL",
+                            "elements": int(sum(x.numel() for x in sums)), "ms": gather_ms,
+                            "checksum": float(sum(x.sum().item() for x in sums))}}
+    for p in parts:
+        p[1].close()
+    del parts
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):

@@ -22,6 +22,7 @@ import os
 import re
 import subprocess
 import tempfile
+import threading
 import time
 
 from . import _lib
@@ -185,7 +186,7 @@ def _compile(text, out, kind, maxreg=128):
     src = os.path.join(d, "k.cu")
     with open(src, "w") as f:
         f.write(text)
-    tmp = out + ".tmp%d" % os.getpid()
+    tmp = out + ".tmp%d_%d" % (os.getpid(), threading.get_ident())  # unique per process AND thread
     if kind == _lib.CUDA_BUILD:
         nvcc = _nvcc()
         if not nvcc:
@@ -236,9 +237,10 @@ def ensure(spec, kind=None, maxreg=None):
             regs, spill = _ptxas(log) if kind == _lib.CUDA_BUILD else (None, 0)
             meta = {"spec": spec, "name": display_name(spec, mr), "maxreg": mr, "registers": regs, "spill_bytes": spill,
                     "compile_s": round(secs, 2), "kind": kind}
-            with open(meta_p + ".tmp%d" % os.getpid(), "w") as f:
+            mtmp = meta_p + ".tmp%d_%d" % (os.getpid(), threading.get_ident())
+            with open(mtmp, "w") as f:
                 json.dump(meta, f)
-            os.replace(meta_p + ".tmp%d" % os.getpid(), meta_p)
+            os.replace(mtmp, meta_p)
         tried.append((mr, meta.get("spill_bytes", 0)))
         # a spilling kernel loses more than the occupancy it keeps (profiles/README.md): give it registers
         if maxreg is None and not os.environ.get("HSP2G_JIT_MAXREG") and meta.get("spill_bytes", 0) > 0 and mr < 232:
