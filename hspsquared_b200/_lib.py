@@ -24,6 +24,7 @@ TILE = 32  # segments per tile of the series layout [tile][interval][row][32] (i
 ACT_BITS = {"ATEMP": 1, "SNOW": 2, "PWATER": 4, "SEDMNT": 8, "PSTEMP": 16, "PWTGAS": 32, "IWATER": 64, "SOLIDS": 128,
             "IWTGAS": 256, "PQUAL": 512, "IQUAL": 1024}
 OPT_SED_RAIN_IS_PREC = 1
+OPT_METRIC = 2
 CAL_HRFG, CAL_DAYFG, CAL_HR1FG, CAL_HR6IND, CAL_SEASON, CAL_NEWDAY = 1, 2, 4, 8, 16, 32
 
 _dp = C.POINTER(C.c_double)

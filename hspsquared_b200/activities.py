@@ -69,8 +69,9 @@ def _calendar(siminfo):
 
 
 def _run_section(section, operation, siminfo, uci, ts, **eff_kw):
-    if siminfo.get("units", 1) != 1:
-        raise NotImplementedError("libhsp2g implements English units (uunits=1) only")
+    units = int(siminfo.get("units", 1))
+    if units != 1 and section not in ("ATEMP", "SNOW", "PWATER", "IWATER"):
+        raise NotImplementedError("libhsp2g: metric units (siminfo['units'] = 2) are implemented for ATEMP, SNOW, PWATER, IWATER")
     cal = _calendar(siminfo)
     steps = int(siminfo["steps"])
     if steps != cal.steps:
@@ -83,7 +84,7 @@ def _run_section(section, operation, siminfo, uci, ts, **eff_kw):
         return served, cal
     tables = {"ACTIVITY": {section: 1}, section: uci}
     names = [n for n in INPUTS[section] if n in ts]
-    store = SegmentStore.from_tables(operation, [tables], cal, ext_names=[k for k in ts.keys()], **eff_kw)
+    store = SegmentStore.from_tables(operation, [tables], cal, ext_names=[k for k in ts.keys()], units=units, **eff_kw)
     save = output_names(operation, store.act)
     with LandBatch(store, cal, names, save, device=DEVICE) as batch:
         forcing = pack_forcings({n: np.asarray(ts[n]) for n in names}, names, 1)

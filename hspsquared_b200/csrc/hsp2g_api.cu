@@ -32,6 +32,7 @@ static_assert(HSP2G_ATEMP == HSP2G_ACT_ATEMP && HSP2G_SNOW == HSP2G_ACT_SNOW && 
               "public activity bits must match the kernel's");
 static_assert(HSP2G_ABI_VERSION == 3, "bump _lib.py with the header");
 static_assert(HSP2G_NFLAG <= 64, "flag word is 64 bits");
+static_assert(HSP2G_OPT_METRIC == OPT_METRIC, "public option bits must match the kernel's");
 static_assert(sizeof(CalStep) == 32, "CalStep layout");
 
 static thread_local std::string g_err;

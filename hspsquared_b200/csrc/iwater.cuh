@@ -23,7 +23,10 @@ struct IwaterState {
         s.st(S_PETADJ, petadj);
     }
     template <class SEG>
-    __device__ __forceinline__ void refresh_daily(const SEG &s) { retsc = s.daily(FB_M_RETSC, M_RETSC, P_RETSC); }
+    __device__ __forceinline__ void refresh_daily(const SEG &s) {
+        const double v = s.daily(FB_M_RETSC, M_RETSC, P_RETSC);
+        retsc = s.metric() ? v * 0.0394 : v;  // IWATER.py:112-113: RETSC series * 0.0394 after the monthly interpolation
+    }
 };
 
 template <bool HOURLY, class SEG>

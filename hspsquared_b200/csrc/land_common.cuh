@@ -549,6 +549,23 @@ struct Sched {
 #define HSP_SYNCWARP()
 #endif
 
+// ---- metric units (siminfo['units'] == 2; HSP2G_OPT_METRIC in L.opts).  The reference keeps every state in English units and
+// converts (a) parameters and initial states on entry -- done by the host in the reference's expression order
+// (hspsquared_b200/segstore.py) --, (b) some parameter SERIES on entry, elementwise after any monthly interpolation (CEPSC, UZSN,
+// RETSC * 0.0394: refresh_daily) and the series one section hands the next (WYIELD), and (c) the STORED series on exit
+// (SNOW.py:569-585, PWATER.py:660-688, IWATER.py:276-283): `x * 25.4`, or `x * 0.555 - 17.777` for the three snow temperatures.
+#define OPT_METRIC 2u
+__host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 25.4, 2 x * 0.555 - 17.777
+    return (oid == O_SNOW_PAKTMP || oid == O_SNOW_DEWTMP || oid == O_SNOW_SNOTMP) ? 2
+           : (oid == O_SNOW_PACKF || oid == O_SNOW_PACKI || oid == O_SNOW_PACKW || oid == O_SNOW_PDEPTH || oid == O_SNOW_NEGHTS ||
+              oid == O_SNOW_COVINX || oid == O_SNOW_SNOWE || oid == O_SNOW_SNOWF || oid == O_SNOW_WYIELD || oid == O_SNOW_XLNMLT ||
+              oid == O_SNOW_MELT || oid == O_SNOW_PRAIN)
+               ? 1
+           : (oid >= O_PWATER_AGWET && oid <= O_PWATER_UZS && oid != O_PWATER_PETADJ && oid != O_PWATER_TGWS)                     ? 1
+           : (oid >= O_IWATER_IMPEV && oid <= O_IWATER_SURS && oid != O_IWATER_PETADJ)                                             ? 1
+                                                                                                                                   : 0;
+}
+
 // per-thread view of the batch
 
 // Option word of the batch: DynFlags reads each segment's 64-bit word from its segment block; StaticFlags<W> is for batches
@@ -707,7 +724,15 @@ struct Seg {
         if (IO::STATIC) return io_saved<IO>(oid);
         return L.srow[oid] >= 0;
     }
+    __device__ __forceinline__ bool metric() const { return (L.opts & OPT_METRIC) != 0; }
     __device__ __forceinline__ void save(int oid, double v) const {
+        if (metric()) {  // the stored series only (the state stays in English units); a warp-uniform branch
+            const int c = metric_out_code(oid);
+            if (c == 1)
+                v = v * 25.4;
+            else if (c == 2)
+                v = (v * 0.555) - 17.777;
+        }
         if (IO::STATIC) {
             if (io_saved<IO>(oid)) store_out(io_row<IO>(oid), v);
         } else {

@@ -105,12 +105,17 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
                 link.snocov = sw.snocov;
                 link.wyield = sx.wyield;
                 link.packi = sw.packi;
+                if (s.metric()) {  // the water section reads the series SNOW stored, i.e. converted (SNOW.py:575,582)
+                    link.wyield = link.wyield * 25.4;
+                    link.packi = link.packi * 25.4;
+                }
             } else {
                 link.rainf = s.forcing(F_RAINF);
                 link.snocov = s.forcing(F_SNOCOV);
                 link.wyield = s.forcing(F_WYIELD);
                 link.packi = s.forcing(F_PACKI);
             }
+            if (s.metric()) link.wyield = link.wyield * 0.0394;  // ... and takes WYIELD back to inches (PWATER.py:244, IWATER.py:114)
             link.airtmp = airtmp;
 
             PwaterFlux fx;
@@ -199,12 +204,17 @@ __device__ __forceinline__ void implnd_body(const LandLaunch &L) {
                 link.snocov = sw.snocov;
                 link.wyield = sx.wyield;
                 link.packi = sw.packi;
+                if (s.metric()) {  // the water section reads the series SNOW stored, i.e. converted (SNOW.py:575,582)
+                    link.wyield = link.wyield * 25.4;
+                    link.packi = link.packi * 25.4;
+                }
             } else {
                 link.rainf = s.forcing(F_RAINF);
                 link.snocov = s.forcing(F_SNOCOV);
                 link.wyield = s.forcing(F_WYIELD);
                 link.packi = s.forcing(F_PACKI);
             }
+            if (s.metric()) link.wyield = link.wyield * 0.0394;  // ... and takes WYIELD back to inches (PWATER.py:244, IWATER.py:114)
             link.airtmp = airtmp;
             double suro, surs;
             if (act & HSP2G_ACT_IWATER) {

@@ -45,6 +45,10 @@ struct PwaterState {
         const int pid[4] = {P_CEPSC, P_UZSN, P_LZETP, P_INTFW};
         double v[4];
         s.daily_batch(fb, mid, pid, v);
+        if (s.metric()) {  // CEPSC, UZSN series * 0.0394 after the monthly interpolation (PWATER.py:236-238)
+            v[0] = v[0] * 0.0394;
+            v[1] = v[1] * 0.0394;
+        }
         cepsc = v[0];
         uzsn = v[1];
         lzetp = v[2];

@@ -391,7 +391,8 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
     s.save(O_SNOW_PACKF, w.packf);
     s.save(O_SNOW_PACKI, w.packi);
     s.save(O_SNOW_PACKW, w.packw);
-    s.save(O_SNOW_PACK, w.packf + w.packw);
+    // metric: PACK[step] = PACKF[step] + PACKW[step] of the CONVERTED series (SNOW.py:576); save() leaves PACK itself as is
+    s.save(O_SNOW_PACK, s.metric() ? (w.packf * 25.4) + (w.packw * 25.4) : w.packf + w.packw);
     s.save(O_SNOW_PAKTMP, w.paktmp);
     s.save(O_SNOW_PDEPTH, w.pdepth);
     s.save(O_SNOW_PRAIN, prain);

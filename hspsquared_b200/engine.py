@@ -169,6 +169,8 @@ class LandBatch:
             if nme in F:
                 fill[F[nme]] = v
         ids = np.array([F[nme] for nme in self.forcing_rows], dtype=np.int32)
+        if getattr(st, "units", 1) == 2:
+            opts |= _lib.OPT_METRIC  # the store's parameters and states are already in English units (segstore.build)
         _lib.check(lib.hsp2g_set_forcing_layout(self.h, len(ids), _ptr(ids, C.POINTER(C.c_int32)), _ptr(fill), opts))
         self.nf = len(ids)
         # SAVE set

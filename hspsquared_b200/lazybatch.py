@@ -193,7 +193,7 @@ def _build_window(loc, glob, operation, first_seg, siminfo, calendar, device):
     for (act, names), members in groups.items():
         if len(members) < 1:
             continue
-        store = SegmentStore.build(operation, stack([m[2] for m in members]), calendar)
+        store = SegmentStore.build(operation, stack([m[2] for m in members]), calendar, units=int(siminfo.get("units", 1)))
         save = output_names(operation, act)
         forcing = np.empty((steps, len(names), len(members)))
         for i, m in enumerate(members):

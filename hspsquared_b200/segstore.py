@@ -328,6 +328,8 @@ def _vpow(base, expo):
 class SegmentStore:
     """SoA host image of one batch: par [NPAR][n], flags [n], monthly {id: [12][n]}, state [NSTATE][n]."""
 
+    units = 1  # 1 English, 2 metric (siminfo['units'])
+
     def __init__(self, operation, act, n, delt):
         self.operation = operation
         self.act = int(act)
@@ -341,24 +343,58 @@ class SegmentStore:
         self.monthly = {}
 
     @classmethod
-    def from_tables(cls, operation, tables_list, calendar, pw_icefg=None, airtfg=None, ext_names=()):
+    def from_tables(cls, operation, tables_list, calendar, pw_icefg=None, airtfg=None, ext_names=(), units=1):
         effs = [effective(operation, t, pw_icefg, airtfg, ext_names) for t in tables_list]
-        return cls.build(operation, stack(effs), calendar)
+        return cls.build(operation, stack(effs), calendar, units=units)
+
+    # metric units (siminfo['units'] == 2): what the reference converts on entry of each core, in its expression order
+    # (`x * 9./5. + 32.` is ((x * 9.) / 5.) + 32.).  The kernels work in English units; the per-interval conversions
+    # (parameter series after monthly interpolation, the SNOW -> water link, the stored series) are theirs (HSP2G_OPT_METRIC).
+    METRIC_RAW = {
+        "SNOW": {"MELEV": lambda x: x * 3.28084, "TBASE": lambda x: (x * 9. / 5.) + 32., "TSNOW": lambda x: (x * 9. / 5.) + 32.,
+                 "COVIND": lambda x: x / 25.4},  # SNOW.py:120,131-133,157-158; MGMELT below (after its time conversion)
+        "PWATER": {"LSUR": lambda x: x * 3.28, "KVARY": lambda x: x / 0.0394, "LZSN": lambda x: x * 0.0394,
+                   "PETMAX": lambda x: (x * 9. / 5.) + 32., "PETMIN": lambda x: (x * 9. / 5.) + 32.,
+                   "FZG": lambda x: x * 0.0394},  # PWATER.py:194,206-207,240-243; INFILT below; CEPSC / UZSN on the device
+        "IWATER": {"LSUR": lambda x: x * 3.28, "PETMAX": lambda x: (x * 9. / 5.) + 32., "PETMIN": lambda x: (x * 9. / 5.) + 32.},
+    }
+    METRIC_INIT = {
+        "SNOW": {"PACKI": lambda x: x / 25.4, "PACKW": lambda x: x / 25.4, "COVINX": lambda x: x / 25.4,
+                 "PAKTMP": lambda x: (x * 9. / 5.) + 32.},  # SNOW.py:114-119; PACKF below (the ice is added first)
+        "PWATER": {k: (lambda x: x * 0.0394) for k in ("CEPS", "SURS", "UZS", "IFWS", "LZS", "AGWS", "GWVS")},  # PWATER.py:195-201
+        "IWATER": {"RETS": lambda x: x * 0.0394, "SURS": lambda x: x * 0.0394},  # IWATER.py:131-133
+    }
 
     @classmethod
-    def build(cls, operation, arrs, calendar):
+    def build(cls, operation, arrs, calendar, units=1):
         n, act = arrs["n"], arrs["act"]
         delt = float(calendar.delt)
         delt60 = delt / 60.0
         st = cls(operation, act, n, delt)
         raw, flag, init, mon = arrs["raw"], arrs["flag"], arrs["init"], arrs["mon"]
         B = _lib.ACT_BITS
+        if units not in (1, 2):
+            raise ValueError("units must be 1 (English) or 2 (metric)")
+        st.units = int(units)
+        metric = units == 2
+        conv_raw, conv_init = {}, {}
+        if metric:
+            ok = B["ATEMP"] | B["SNOW"] | B["PWATER"] | B["IWATER"]
+            if act & ~ok:
+                raise NotImplementedError("metric units (siminfo['units'] = 2) are implemented for ATEMP, SNOW, PWATER and IWATER; "
+                                          "this batch also runs %s" % [a for a, b in B.items() if act & b & ~ok])
+            for sec in ("SNOW", "PWATER", "IWATER"):
+                if act & B[sec]:
+                    conv_raw.update(cls.METRIC_RAW[sec])
+                    conv_init.update(cls.METRIC_INIT[sec])
 
         def R(name):
-            return raw.get(name, np.full(n, RAW_DEFAULT[name]))
+            v = raw.get(name, np.full(n, RAW_DEFAULT[name]))
+            return conv_raw[name](v) if name in conv_raw else v
 
         def I(name):
-            return init.get(name, np.full(n, INIT_DEFAULT[name]))
+            v = init.get(name, np.full(n, INIT_DEFAULT[name]))
+            return conv_init[name](v) if name in conv_init else v
 
         # ---- plain parameter columns
         derived = {"MGMELT_IVL", "INFILT_IVL", "KGW", "ELEVGC"}
@@ -367,6 +403,9 @@ class SegmentStore:
                 st.par[row] = R(name)
         st.par[st.P["MGMELT_IVL"]] = R("MGMELT") * delt / 1440.0  # SNOW.py:146
         st.par[st.P["INFILT_IVL"]] = R("INFILT") * delt60  # PWATER.py:215
+        if metric:
+            st.par[st.P["MGMELT_IVL"]] = st.par[st.P["MGMELT_IVL"]] / 25.4  # SNOW.py:159
+            st.par[st.P["INFILT_IVL"]] = st.par[st.P["INFILT_IVL"]] * 0.0394  # PWATER.py:239
         if act & B["PWATER"]:
             st.par[st.P["KGW"]] = 1.0 - _vpow(R("AGWRC"), delt60 / 24.0)  # PWATER.py:247
         if act & (B["PWTGAS"] | B["IWTGAS"]):
@@ -395,7 +434,9 @@ class SegmentStore:
         s = st.state
         if act & B["SNOW"]:  # SNOW.py:102-232
             covinx, dull = I("COVINX").copy(), I("DULL").copy()
-            packf = I("PACKF") + I("PACKI")
+            packf = init.get("PACKF", np.full(n, INIT_DEFAULT["PACKF"])) + init.get("PACKI", np.full(n, INIT_DEFAULT["PACKI"]))
+            if metric:
+                packf = packf / 25.4  # SNOW.py:110,115: the ice is added in the user's units, then the sum is converted
             packi, packw, paktmp = I("PACKI").copy(), I("PACKW").copy(), I("PAKTMP").copy()
             rdenpf = I("RDENPF").copy()
             covind0 = R("COVIND")

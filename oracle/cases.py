@@ -109,7 +109,7 @@ def forcings(case):
 def siminfo_for(case):
     start = np.datetime64("%04d-01-01T00:00" % case.get("year", 1976)) + np.timedelta64(case.get("hour0", 0), "h")
     stop = start + np.timedelta64(case["steps"] * case["delt"], "m")
-    return {"start": start, "stop": stop, "delt": case["delt"], "units": 1, "steps": case["steps"]}
+    return {"start": start, "stop": stop, "delt": case["delt"], "units": case.get("units", 1), "steps": case["steps"]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -293,6 +293,27 @@ def build_cases():
     add("flowtest_pwater", "PERLND", fp, "flowtest", steps=8760, year=2018)
     fi = {"ACTIVITY": {"IWATER": 1}, "IWATER": copy.deepcopy(FLOWTEST_IMPLND)}
     add("flowtest_iwater", "IMPLND", fi, "flowtest", steps=8760, year=2018)
+
+    # -- metric units (siminfo['units'] == 2): entry / exit conversions of SNOW, PWATER, IWATER (SNOW.py:114-160,569-585;
+    #    PWATER.py:193-244,660-688; IWATER.py:86-131,276-283).  The numbers are the English tables read as metric values: what
+    #    matters for parity is that every conversion site is exercised (energy-balance snow with ice, monthly CEPSC / UZSN /
+    #    RETSC, frozen-ground factor, PWATER without SNOW) ------------------------------------------------------------
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    add("p001_metric", "PERLND", t, "perlnd", drop=("CLOUD",), units=2)
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    t["SNOW"]["STATES"].update({"PACKF": 40.0, "PACKI": 6.0, "PACKW": 2.0, "PAKTMP": -3.0, "COVINX": 20.0})
+    t["SNOW"]["PARAMETERS"].update({"TSNOW": 1.0, "TBASE": 0.0, "COVIND": 30.0, "MGMELT": 0.5, "MELEV": 300.0})
+    t["PWATER"]["PARAMETERS"].update({"PETMAX": 4.0, "PETMIN": 1.5, "KVARY": 0.02, "FZG": 0.04})
+    add("p_metric_pack", "PERLND", t, "perlnd", units=2, rain_mult=2.0)
+    ti = test10.implnd()
+    ti["ACTIVITY"].update({"SOLIDS": 0, "IWTGAS": 0})
+    ti["IWATER"]["PARAMETERS"].update({"VRSFG": 1})
+    ti["IWATER"]["MONTHLY_RETSC"] = monthly([.05, .05, .06, .07, .08, .1, .1, .1, .08, .07, .06, .05])
+    add("i001_metric", "IMPLND", ti, "implnd", units=2)
+    fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}
+    add("flowtest_pwater_metric", "PERLND", fp, "flowtest", steps=8760, year=2018, units=2)
     return C
 
 

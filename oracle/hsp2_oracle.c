@@ -78,16 +78,29 @@ void hsp2o_snow(const snow_ui *ui, const snow_in *in, const snow_out *out, int64
     const double delt = ui->delt;
     const double delt60 = delt / 60.0;
     const int cloudfg = (int)ui->cloudfg, icefg = (int)ui->ICEFG, snopfg = (int)ui->SNOPFG;
-    const double melev = ui->MELEV, rdcsn = ui->RDCSN, tbase = ui->TBASE, tsnow = ui->TSNOW;
+    double melev = ui->MELEV, tbase = ui->TBASE, tsnow = ui->TSNOW;
+    const double rdcsn = ui->RDCSN;
+    const int metric = ui->uunits == 2.0; /* SNOW.py:99 */
 
     /* SNOW.py:102-135 initial named states; PACKF includes the ice at load */
     double covinx = ui->COVINX, dull = ui->DULL;
     double packf = ui->PACKF + ui->PACKI, packi = ui->PACKI, packw = ui->PACKW, paktmp = ui->PAKTMP;
     double rdenpf = ui->RDENPF, skyclr = ui->SKYCLR, xlnmlt = ui->XLNMLT;
     double pdepth, snocov, neghts;
+    if (metric) { /* SNOW.py:114-120, 131-133: `x * 9./5.` is (x * 9.) / 5. */
+        packf = packf / 25.4;
+        packi = packi / 25.4;
+        packw = packw / 25.4;
+        covinx = covinx / 25.4;
+        paktmp = (paktmp * 9. / 5.) + 32.;
+        melev = melev * 3.28084;
+        tbase = (tbase * 9. / 5.) + 32.;
+        tsnow = (tsnow * 9. / 5.) + 32.;
+    }
+    const double covind0 = metric ? in->COVIND[0] / 25.4 : in->COVIND[0]; /* SNOW.py:157-159 before :185-206 */
 
     if (packf + packw <= 1.0e-5) { /* SNOW.py:185-200 no pack at start */
-        covinx = 0.1 * in->COVIND[0];
+        covinx = 0.1 * covind0;
         dull = 0.0;
         neghts = 0.0;
         packf = packi = packw = 0.0;
@@ -96,7 +109,7 @@ void hsp2o_snow(const snow_ui *ui, const snow_in *in, const snow_out *out, int64
         rdenpf = NAN;
         snocov = 0.0;
     } else { /* SNOW.py:201-206 */
-        if (covinx < 1.0e-5) covinx = 0.1 * in->COVIND[0];
+        if (covinx < 1.0e-5) covinx = 0.1 * covind0;
         pdepth = packf / rdenpf;
         snocov = packf < covinx ? packf / covinx : 1.0;
         neghts = (32.0 - paktmp) * 0.00695 * packf;
@@ -110,9 +123,13 @@ void hsp2o_snow(const snow_ui *ui, const snow_in *in, const snow_out *out, int64
 
     for (int64_t t = 0; t < nsteps; ++t) {
         const double oldprec = prec;
-        const double mgmelt = in->MGMELT[t] * delt / 1440.0; /* SNOW.py:146 */
+        double mgmelt = in->MGMELT[t] * delt / 1440.0; /* SNOW.py:146 */
         const double airtmp = in->AIRTMP[t];
-        const double covind = in->COVIND[t];
+        double covind = in->COVIND[t];
+        if (metric) { /* SNOW.py:157-159 */
+            covind = covind / 25.4;
+            mgmelt = mgmelt / 25.4;
+        }
         const double dtmpg = in->DTMPG[t];
         const int hr6ind = (int)(int64_t)in->HR6IND[t];
         const int hrfg = (int)(int64_t)in->HRFG[t];
@@ -408,6 +425,24 @@ void hsp2o_snow(const snow_ui *ui, const snow_in *in, const snow_out *out, int64
         out->SNOWF[t] = snowf;
         out->WYIELD[t] = wyield;
         out->XLNMLT[t] = xlnmlt;
+        if (metric) { /* SNOW.py:569-585: the stored series only; the state stays in English units */
+            out->PAKTMP[t] = (paktmp * 0.555) - 17.777;
+            out->DEWTMP[t] = (dewtmp * 0.555) - 17.777;
+            out->SNOTMP[t] = (snotmp * 0.555) - 17.777;
+            out->PACKF[t] = packf * 25.4;
+            out->PACKI[t] = packi * 25.4;
+            out->PACKW[t] = packw * 25.4;
+            out->PACK[t] = out->PACKF[t] + out->PACKW[t];
+            out->PDEPTH[t] = pdepth * 25.4;
+            out->NEGHTS[t] = neghts * 25.4;
+            out->COVINX[t] = covinx * 25.4;
+            out->SNOWE[t] = snowe * 25.4;
+            out->SNOWF[t] = snowf * 25.4;
+            out->WYIELD[t] = wyield * 25.4;
+            out->XLNMLT[t] = xlnmlt * 25.4;
+            out->MELT[t] = melt * 25.4;
+            out->PRAIN[t] = prain * 25.4;
+        }
     }
     (void)satvap;
 }
@@ -1550,7 +1585,7 @@ int hsp2o_perlnd_batch(int64_t nseg, int64_t nsteps, double delt, const double *
 
             snow_ui su = {delt, 0.0, p[BP_ICEFG], p[BP_SNOPFG], p[BP_MELEV], p[BP_PACKF], p[BP_PACKI], p[BP_PACKW],
                           p[BP_PAKTMP], p[BP_RDCSN], p[BP_RDENPF], p[BP_SKYCLR], p[BP_TBASE], p[BP_TSNOW],
-                          p[BP_COVINX], p[BP_DULL], p[BP_XLNMLT]};
+                          p[BP_COVINX], p[BP_DULL], p[BP_XLNMLT], 1.0};
             snow_in si;
             si.AIRTMP = f + 2 * nsteps; si.CCFACT = cst[0]; si.CLOUD = zeros; si.COVIND = cst[1];
             si.DTMPG = f + 5 * nsteps; si.HR6IND = cal + 2 * n1; si.HRFG = cal; si.KMELT = cst[7];

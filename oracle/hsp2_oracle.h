@@ -16,7 +16,8 @@
  * bit-for-bit (same glibc libm, no FMA contraction, same evaluation order), and against the HSPF known-answer
  * files the reference's own tests use (tests/ipwater/data/Flow_Test.plt, tests/test10/HSPFresults/test10I.hbn).
  *
- * Scope notes: English units only (uunits == 1); PWATER HWTFG=1 is unsupported in the reference itself
+ * Scope notes: English units, and metric (uunits == 2) for SNOW, PWATER and IWATER (SNOW.py:114-160,569-585 here; the array and
+ * scalar conversions of PWATER.py:193-244,660-688 / IWATER.py:86-131,276-283 are elementwise and live in oracle/wrappers.py); PWATER HWTFG=1 is unsupported in the reference itself
  * (PWATER.py:107-110) and is refused by the callers.
  *
  * Interface: every routine takes three homogeneous records whose members are listed by the X-macros below:
@@ -41,7 +42,7 @@ extern "C" {
 
 /* ---- SNOW ----------------------------------------------------------------------------------- */
 #define SNOW_UI(X) X(delt) X(cloudfg) X(ICEFG) X(SNOPFG) X(MELEV) X(PACKF) X(PACKI) X(PACKW) X(PAKTMP) \
-    X(RDCSN) X(RDENPF) X(SKYCLR) X(TBASE) X(TSNOW) X(COVINX) X(DULL) X(XLNMLT)
+    X(RDCSN) X(RDENPF) X(SKYCLR) X(TBASE) X(TSNOW) X(COVINX) X(DULL) X(XLNMLT) X(uunits)
 #define SNOW_IN(X) X(AIRTMP) X(CCFACT) X(CLOUD) X(COVIND) X(DTMPG) X(HR6IND) X(HRFG) X(KMELT) X(MGMELT) \
     X(MWATER) X(PREC) X(SEASONS) X(SHADE) X(SNOEVP) X(SNOWCF) X(SOLRAD) X(WINMOV)
 #define SNOW_OUT(X) X(ALBEDO) X(COVINX) X(DEWTMP) X(DULL) X(MELT) X(NEGHTS) X(PACKF) X(PACKI) X(PACKW) \

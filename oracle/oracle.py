@@ -100,7 +100,7 @@ def _atemp_(ui, ts):
 
 
 def _snow_(ui, ts):
-    return _run("snow", ui, ts, int(ui["steps"]), 1, ui_defaults={"ICEFG": 0, "SNOPFG": 0})
+    return _run("snow", ui, ts, int(ui["steps"]), 1, ui_defaults={"ICEFG": 0, "SNOPFG": 0, "uunits": 1})
 
 
 def _pwater_(ui, ts):

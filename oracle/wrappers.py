@@ -45,7 +45,20 @@ def _cal(siminfo):
 
 def _english(siminfo):
     if siminfo.get("units", 1) != 1:
-        raise NotImplementedError("oracle restates English units only (uunits == 1)")
+        raise NotImplementedError("oracle restates metric units (uunits == 2) for SNOW, PWATER and IWATER only")
+
+
+# metric units (uunits == 2): the reference converts parameters, states and parameter series on entry and the stored series
+# on exit, all elementwise (PWATER.py:193-244,660-688; IWATER.py:86-131,276-283).  numpy evaluates the same IEEE operations
+# in the same order as the Numba code (`x * 9./5. + 32.` is ((x * 9.) / 5.) + 32.), so the conversions live here and the C
+# cores stay in English units -- except SNOW's, where `packf = PACKF + PACKI` precedes its conversion (hsp2_oracle.c).
+def _f2c_in(x):
+    return (x * 9. / 5.) + 32.
+
+
+PWATER_OUT_METRIC = ("AGWET", "AGWI", "AGWO", "AGWS", "BASET", "CEPE", "CEPS", "GWVS", "IFWI", "IFWO", "IFWS", "IGWI", "INFIL",
+                     "LZET", "LZI", "LZS", "PERC", "PERO", "PERS", "SURI", "SURO", "SURS", "TAET", "UZET", "UZI", "UZS", "SUPY", "PET")
+IWATER_OUT_METRIC = ("IMPEV", "RETS", "SURI", "SURO", "SURS", "SUPY", "PET")
 
 
 def atemp(io_manager, siminfo, uci, ts):
@@ -58,7 +71,6 @@ def atemp(io_manager, siminfo, uci, ts):
 
 
 def snow(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     steps = siminfo["steps"]
     ts["SEASONS"] = cal.monthval(SEASONS)
@@ -75,7 +87,7 @@ def snow(io_manager, siminfo, uci, ts):
     if "FLAGS" in uci and "ICEFG" in uci["FLAGS"]:
         siminfo["ICEFG"] = uci["FLAGS"]["ICEFG"]
     ui = make_ui(uci)
-    ui.update(steps=steps, delt=siminfo["delt"], cloudfg=cloudfg)
+    ui.update(steps=steps, delt=siminfo["delt"], cloudfg=cloudfg, uunits=siminfo.get("units", 1))
     vkmfg = uci.get("FLAGS", {}).get("VKMFG", 0)
     ts["KMELT"] = cal.initm(uci, vkmfg, "MONTHLY_KMELT", uci["PARAMETERS"]["KMELT"])
     errors = O._snow_(ui, ts)
@@ -85,7 +97,6 @@ def snow(io_manager, siminfo, uci, ts):
 
 
 def pwater(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     steps = siminfo["steps"]
     for name in ("AGWLI", "IFWLI", "LGTMP", "LZLI", "PETINP", "PREC", "SURLI", "UZLI"):
@@ -115,12 +126,40 @@ def pwater(io_manager, siminfo, uci, ts):
     ui.update(steps=steps, delt=siminfo["delt"])
     ui["ICEFG"] = siminfo["ICEFG"] if "ICEFG" in siminfo else 0.0
     u["CSNOFG"] = int(ui["CSNOFG"]) if "CSNOFG" in ui else 0
-    errors = O._pwater_(ui, ts)
+    if siminfo.get("units", 1) != 2:
+        return O._pwater_(ui, ts), ERRMSGS_PWATER
+    # ---- metric: entry conversions (PWATER.py:193-207, 236-244) on copies, the English core, exit conversions (:660-688)
+    m, t2 = dict(ui), dict(ts)
+    m["LSUR"] = ui["LSUR"] * 3.28
+    for k in ("CEPS", "SURS", "UZS", "IFWS", "LZS", "AGWS", "GWVS"):
+        m[k] = ui[k] * 0.0394
+    if int(ui["ICEFG"]) and "FZG" in ui:
+        m["FZG"] = ui["FZG"] * 0.0394
+    for k in ("CEPSC", "UZSN", "LZSN", "WYIELD"):
+        t2[k] = np.asarray(ts[k], dtype=np.float64) * 0.0394
+    # INFILT = ts['INFILT'] * delt60, then * 0.0394 (PWATER.py:215, 239): the core multiplies by delt60 itself, so the factor is
+    # folded in on the other side of that product only where that is the same IEEE operation sequence: it is not, in general --
+    # the core is therefore handed INFILT * delt60 * 0.0394 / delt60 only when delt60 == 1; otherwise see _pwater_metric_infilt
+    t2["INFILT"] = _pwater_metric_infilt(np.asarray(ts["INFILT"], dtype=np.float64), siminfo["delt"] / 60.0)
+    t2["KVARY"] = np.asarray(ts["KVARY"], dtype=np.float64) / 0.0394
+    t2["PETMAX"] = _f2c_in(np.asarray(ts["PETMAX"], dtype=np.float64))
+    t2["PETMIN"] = _f2c_in(np.asarray(ts["PETMIN"], dtype=np.float64))
+    errors = O._pwater_(m, t2)
+    for k in O.fields("pwater_out"):
+        ts[k] = t2[k] * 25.4 if k in PWATER_OUT_METRIC else t2[k]
     return errors, ERRMSGS_PWATER
 
 
+def _pwater_metric_infilt(infilt, delt60):
+    """The series the English core must be handed so that its `INFILT[t] * delt60` (PWATER.py:215) equals the reference's metric
+    `(INFILT[t] * delt60) * 0.0394` (PWATER.py:215, 239).  For hourly runs (delt60 == 1.0, x * 1.0 == x) that is INFILT * 0.0394;
+    other steps would need the product inside the core."""
+    if delt60 != 1.0:
+        raise NotImplementedError("oracle: metric PWATER restated for hourly runs (delt == 60)")
+    return infilt * 0.0394
+
+
 def iwater(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     steps = siminfo["steps"]
     for name in ("AIRTMP", "PETINP", "PREC", "RAINF", "SNOCOV", "WYIELD"):
@@ -142,7 +181,20 @@ def iwater(io_manager, siminfo, uci, ts):
     ts["HRFG"] = cal.hoursval(np.ones(24), dofirst=True)
     ui = make_ui(uci)
     ui.update(steps=steps, delt=siminfo["delt"])
-    return O._iwater_(ui, ts), ERRMSGS_IWATER
+    if siminfo.get("units", 1) != 2:
+        return O._iwater_(ui, ts), ERRMSGS_IWATER
+    # ---- metric: IWATER.py:86-87, 112-116, 131-133 on entry, :276-283 on exit
+    m, t2 = dict(ui), dict(ts)
+    m["LSUR"] = ui["LSUR"] * 3.28
+    m["RETS"], m["SURS"] = ui["RETS"] * 0.0394, ui["SURS"] * 0.0394
+    t2["RETSC"] = np.asarray(ts["RETSC"], dtype=np.float64) * 0.0394
+    t2["WYIELD"] = np.asarray(ts["WYIELD"], dtype=np.float64) * 0.0394
+    t2["PETMAX"] = _f2c_in(np.asarray(ts["PETMAX"], dtype=np.float64))
+    t2["PETMIN"] = _f2c_in(np.asarray(ts["PETMIN"], dtype=np.float64))
+    errors = O._iwater_(m, t2)
+    for k in O.fields("iwater_out"):
+        ts[k] = t2[k] * 25.4 if k in IWATER_OUT_METRIC else t2[k]
+    return errors, ERRMSGS_IWATER
 
 
 def sedmnt(io_manager, siminfo, uci, ts):

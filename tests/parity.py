@@ -62,7 +62,7 @@ def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps
     if land_on:
         names = [n for n in forc if n in F and n not in ("SLIQSP", "ILIQC", "ALIQC")]
         tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
-        store = SegmentStore.from_tables(op, tables, cal)
+        store = SegmentStore.from_tables(op, tables, cal, units=si.get("units", 1))
         with LandBatch(store, cal, names, save, device=device) as b:
             if sub_steps is not None:
                 b.set_schedule(sub_steps)

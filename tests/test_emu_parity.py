@@ -28,7 +28,7 @@ def test_fused_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "cbp_delt15", "i001_test10", "p001_midyear", "cbp_pqual",
-                                  "i_iqual_variants"])
+                                  "i_iqual_variants", "p_metric_pack"])
 def test_chunked_equals_single_pass(name):
     """State (named + hidden) carried through the per-segment state record makes chunked runs bit-identical."""
     case = ALL[name]
@@ -57,7 +57,7 @@ def test_subchunk_tasks_equal_whole_chunk(name):
     assert not parity.compare(ref, b, exact=True, seg=69)
 
 
-@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10", "p_stress_wet"])
+@pytest.mark.parametrize("name", ["p001_test10", "cbp_fullchain", "i001_test10", "p_stress_wet", "p_metric_pack", "i001_metric"])
 def test_float32_outputs_are_the_reference_cast(name):
     """HSP2G_F32: the kernel's store rounds to float32 exactly like save_timeseries' astype(np.float32)
     (utilities.py:313) -- bit for bit on the CPU double, where the fp64 values are the oracle's."""
@@ -115,3 +115,17 @@ def test_option_word_kernels_equal_the_general_ones():
 
 def test_dispatcher_calls_are_served_from_fused_batches():
     parity.check_lazy_dispatch(n=12)
+
+
+def test_metric_units_refused_where_not_implemented():
+    """siminfo['units'] = 2 is implemented for ATEMP / SNOW / PWATER / IWATER (the reference's conversion sites SNOW.py:114-160,
+    569-585, PWATER.py:193-244,660-688, IWATER.py:86-131,276-283); the other sections refuse it loudly instead of computing in
+    the wrong units."""
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.segstore import SegmentStore
+    from oracle import cases as CASES
+
+    case = CASES.build_cases()["cbp_fullchain"]
+    cal = Calendar("1976-01-01", "1976-01-03", 60, "us")
+    with pytest.raises(NotImplementedError, match="metric"):
+        SegmentStore.from_tables("PERLND", [case["tables"]], cal, units=2)

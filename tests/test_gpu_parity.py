@@ -89,7 +89,8 @@ def test_chunked_equals_single_pass_bitwise(name):
 
 @pytest.mark.parametrize("name", ["p001_test10", "i001_test10", "cbp_fullchain", "p_nosnow_iffc2", "flowtest_pwater",
                                   "flowtest_iwater", "i_atemp_snow", "i001_iwtgas", "i_solids_m1_wtf_monthly",
-                                  "i_solids_iwtgas_alone", "i001_iqual", "i_iqual_variants", "cbp_pqual", "p_pqual_alone"])
+                                  "i_solids_iwtgas_alone", "i001_iqual", "i_iqual_variants", "cbp_pqual", "p_pqual_alone",
+                                  "p_metric_pack", "i001_metric", "flowtest_pwater_metric"])
 def test_dropin_vs_oracle(name):
     case = ALL[name]
     ref, ref_err = parity.run_oracle(case)
@@ -142,7 +143,7 @@ def test_subchunk_tasks_bitwise(name, save):
         assert np.array_equal(eb[k][:, :3], es[k])
 
 
-@pytest.mark.parametrize("name", ["p001_snow_pwater", "p001_test10", "i001_test10", "cbp_fullchain"])
+@pytest.mark.parametrize("name", ["p001_snow_pwater", "p001_test10", "i001_test10", "cbp_fullchain", "p_metric_pack"])
 def test_float32_outputs(name):
     """HSP2G_F32 (what save_timeseries stores, utilities.py:313): exactly the oracle's fp64 series cast to float32."""
     case = ALL[name]
