@@ -852,7 +852,7 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
     """One device-resident measurement of a named configuration (same rules as the headline: W >= 3 warm-up launches, CUDA events
     on the launching stream, inputs of every launch far larger than L2 and distinct from the previous launch's).
     order: None | "flags" (option word) | "climate" (option word, then the climate key LandBatch.climate_order derives from the
-    first chunk's forcings)."""
+    first chunk's forcings) | "groups" (one batch and kernel per option word, launched together: engine.GroupedLandBatch)."""
     from hspsquared_b200 import synth
     from hspsquared_b200.engine import LandBatch
 
@@ -860,23 +860,47 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
     Tc = Tc or Tc0
     store = ens.store(cal)
     perm = None
-    if order == "climate":
-        f0 = synth.forcing_chunk(ens, cal, first_chunk * Tc, min(Tc, 24 * 14), names=forcings)
-        perm = LandBatch.climate_order(store, forcings, f0)
+    grouped = order == "groups"
+    if order in ("climate", "groups"):
+        f0 = synth.forcing_chunk(ens, cal, first_chunk * Tc, min(Tc, 24 * 7), names=forcings)
+        if grouped:
+            keys = LandBatch.climate_keys(forcings, f0)
+        else:
+            perm = LandBatch.climate_order(store, forcings, f0)
+        del f0
     elif order == "flags":
         perm = store.divergence_order()
     if perm is not None and not np.array_equal(perm, np.arange(n)):
         ens = ens.take(perm)
         store = ens.store(cal)
-    batch = LandBatch(store, cal, forcings, save, device=dev.index or 0, layout=layout, jit=jit, order=None)
+    if grouped:
+        # one batch and one kernel per option word, launched together (engine.GroupedLandBatch); climate keys inside a group
+        from hspsquared_b200.engine import GroupedLandBatch
+
+        batch = GroupedLandBatch(store, cal, forcings, save, device=dev.index or 0, layout=layout, jit=jit, keys=keys)
+    else:
+        batch = LandBatch(store, cal, forcings, save, device=dev.index or 0, layout=layout, jit=jit, order=None)
     try:
         if sub is not None:
             batch.set_schedule(sub)
         if out_dtype is not None:
             batch.set_output_dtype(out_dtype)
-        npad, nf, ns = batch.npad, batch.nf, batch.ns
-        osz = batch.out_dtype.itemsize
-        forc = [device_forcing(torch, ens, cal, (first_chunk + c) * Tc, Tc, npad, dev, batch.forcing_rows, layout) for c in range(K + W)]
+        nf, ns = batch.nf, batch.ns
+        osz = 4 if out_dtype is not None and np.dtype(out_dtype).itemsize == 4 else 8
+        if grouped:
+            if layout != "plain":
+                raise ValueError("grouped runs of run_config use the plain layout")
+            npad = batch.width
+            parts = [(c0, b.npad, ens.take(idx)) for c0, idx, b in zip(batch.first_column, batch.members, batch.groups)]
+            forc = []
+            for c in range(K + W):
+                big = torch.empty((Tc, nf, npad), dtype=torch.float64, device=dev)
+                for c0, w_, e_ in parts:
+                    big[:, :, c0:c0 + w_] = device_forcing(torch, e_, cal, (first_chunk + c) * Tc, Tc, w_, dev, batch.forcing_rows, "plain")
+                forc.append(big)
+        else:
+            npad = batch.npad
+            forc = [device_forcing(torch, ens, cal, (first_chunk + c) * Tc, Tc, npad, dev, batch.forcing_rows, layout) for c in range(K + W)]
         outs = out_buffers(torch, npad, Tc, ns, dev, layout, torch.float32 if osz == 4 else None)
         torch.cuda.synchronize(dev)
         ms = time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0) if first_chunk == 0 else None
@@ -897,8 +921,11 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
         value = n * Tc * K / (ms * 1e-3)
         errs = {k: int((v != 0).sum()) for k, v in batch.errors().items() if (v != 0).any()}
         return {"config": name, "workload": note, "segments": n, "intervals_per_step": Tc, "steps": K, "warmup": W,
-                "series_layout": layout, "segment_order": order, "kernel": batch.kernel_name(),
-                "registers": (batch.jit_meta or {}).get("registers"), "forcing_rows": nf, "saved_rows": ns,
+                "series_layout": layout, "segment_order": order,
+                "kernel": batch.kernel_name() if not grouped else "%d kernels, one per option word, launched together; e.g. %s"
+                % (len(batch.groups), batch.kernel_names()[0]),
+                "registers": (batch.jit_meta or {}).get("registers") if not grouped else sorted({(b.jit_meta or {}).get("registers") for b in batch.groups}, key=str),
+                "forcing_rows": nf, "saved_rows": ns,
                 "bytes_per_segment_interval": B, "ms_per_step": ms / K, "value": value, "unit": "segment-timesteps/s",
                 "achieved_GBps": value * B / 1e9, "frac_of_measured_hbm": value * B / 1e9 / peak, "segments_with_error_counts": errs}
     finally:
@@ -976,19 +1003,92 @@ def run_sharded_ensemble(torch, dev, local_rank, rank, world, dist, cal, stream,
     return res
 
 
+def run_watershed_stream(device, cal, n=5000, stations=16, years=10, chunk=24 * 61, jit=True):
+    """BASELINE.json configs[4]: a testcbp-style watershed -- `n` full-chain PERLND land segments (the CBP segment's tables, option
+    flags drawn per segment) on `stations` met gages with per-segment MFACTORs (shared-met mode: no per-segment forcing exists
+    anywhere), `years` years hourly -- run END TO END through the product path: kernels in time chunks, the 10 series a CBP
+    land segment hands its river model leave the device as float32 and are streamed chunk by chunk into the results store
+    (hspsquared_b200.sink.NpyResults, a SupportsWriteTS / SupportsReadTS backend) while the next chunk computes.  Wall clock,
+    everything included."""
+    import shutil
+    import tempfile
+
+    import pandas as pd
+
+    from hspsquared_b200 import synth
+    from hspsquared_b200.engine import LandBatch
+    from hspsquared_b200.sink import NpyResults, stream_batch
+
+    steps = min(cal.steps, int(years * 8766))
+    ens = synth.Ensemble("PERLND", n, seed=4321, base="cbp", options=FULLCHAIN_OPTIONS)
+    forcings = list(synth.FULLCHAIN_FORCINGS)
+    store = ens.store(cal)
+    nf = len(forcings)
+    s0 = synth.shared_series("PERLND", cal, 0, steps)
+    series = np.empty((steps, nf, stations))
+    for k in range(stations):  # gages differ by a temperature offset
+        for r, nm in enumerate(forcings):
+            a = s0["AIRTMP" if nm == "GATMP" else nm]
+            if nm in ("AIRTMP", "GATMP"):
+                a = a + (k - stations / 2) * 0.4
+            elif nm == "DTMPG":
+                a = (s0["AIRTMP"] + (k - stations / 2) * 0.4) - 5.0
+            series[:, r, k] = a
+    station = np.minimum((np.argsort(np.argsort(ens.u_airt)) * stations // n), stations - 1).astype(np.int32)
+    mfac = np.ones((nf, n))
+    mfac[forcings.index("PREC")] = 1.0 + 0.2 * ens.u_prec
+    mfac[forcings.index("PETINP")] = 1.0 + 0.1 * ens.u_pet
+    root = tempfile.mkdtemp(prefix="hsp2g_results_", dir="/dev/shm" if os.path.isdir("/dev/shm") and
+                            shutil.disk_usage("/dev/shm").free > 3 * steps * n * 40 else None)
+    try:
+        tindex = pd.date_range(pd.Timestamp(str(cal.start)), periods=steps + 1, freq="60min")[1:]
+        save_tables = {}
+        for full in CBP10:
+            act, name = full.split("_", 1)
+            save_tables.setdefault(act, {})[name] = 1
+        segs = ["P%05d" % (i + 1) for i in range(n)]
+        t0 = time.perf_counter()
+        sink = NpyResults(root, mode="w")
+        with LandBatch(store, cal, forcings, list(CBP10), device=device, layout="plain", jit=jit, order="flags") as b:
+            b.set_shared_forcing(series, station, mfac)
+            t1 = time.perf_counter()
+            stream_batch(sink, b, {"tindex": tindex}, "PERLND", segs, save_tables, None, chunk)
+            kname = b.kernel_name()
+            launches, _ = b.kernel_stats()
+            errs = {k: int((v != 0).sum()) for k, v in b.errors().items() if (v != 0).any()}
+        sink.close()
+        t2 = time.perf_counter()
+        back = NpyResults(root).read_ts("RESULT", "PERLND", segs[n // 2], "PWATER")
+        nbytes = sum(os.path.getsize(os.path.join(root, f)) for f in os.listdir(root))
+        return {"workload": "%d full-chain PERLND segments (CBP land segment, option flags drawn per segment) on %d met gages x MFACTOR, "
+                            "%d hourly intervals (%.1f years), SAVE = the 10 CBP river-model series, streamed to the NpyResults store"
+                            % (n, stations, steps, steps / 8766.0),
+                "segments": n, "intervals": steps, "intervals_per_chunk": chunk, "kernel": kname, "gpu_launches": int(launches),
+                "wall_s": t2 - t0, "setup_s": t1 - t0, "value": n * steps / (t2 - t1), "unit": "segment-timesteps/s",
+                "stored_bytes": nbytes, "store_write_GBps": nbytes / (t2 - t1) / 1e9, "store": root.split("/")[1],
+                "read_back": {"frame": list(back.shape), "columns": list(back.columns), "dtype": str(back.to_numpy().dtype)},
+                "segments_with_error_counts": errs}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
     """The other BASELINE.json configurations, each a short device-resident measurement on this rank's GPU, so that the
     driver's record carries them beside the headline (rank 0 only)."""
     if rank != 0:
         return None
     out = {}
-    for key, name, kw in (("implnd_100k", "implnd", {}),
-                          ("fullchain_250k_all84", "fullchain_all", {"K": 12}),
-                          ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10})):
+    for key, name, kw in (("implnd_100k", "implnd", {"order": "climate"}),
+                          ("fullchain_250k_all84", "fullchain_all", {"K": 12, "order": "groups"}),
+                          ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10, "order": "groups"})):
         try:
             out[key] = run_config(torch, dev, name, cal, stream, peak, **kw)
         except Exception as ex:
             out[key] = {"error": repr(ex)}
+    try:
+        out["watershed_5k_10y_streamed"] = run_watershed_stream(local_rank, cal)
+    except Exception as ex:
+        out["watershed_5k_10y_streamed"] = {"error": repr(ex)}
     return out
 
 

@@ -55,6 +55,8 @@ _PROTOS = {
     "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "hsp2g_run_device_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "hsp2g_run_host_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "hsp2g_run_device_group": (C.c_int, [C.c_int32, C.POINTER(_h), C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         _i64p, C.c_void_p]),
     "hsp2g_set_series_layout": (C.c_int, [_h, C.c_int]),
     "hsp2g_set_forcing_dtype": (C.c_int, [_h, C.c_int]),
     "hsp2g_set_kernel_image": (C.c_int, [_h, C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p]),

@@ -93,6 +93,7 @@ struct hsp2g_batch {
     int forc_f32 = 0;  // forcing series are float32
     JitKernel jit;
     int *d_periods = nullptr;  // device copy of `periods`
+    cudaEvent_t group_fork = nullptr;   // hsp2g_run_device_group: the caller's stream at the time of the call
     cudaEvent_t last_launch = nullptr;  // recorded after every launch on the stream it used (state / error accessors wait for it)
     bool have_last = false;
     // shared-met mode
@@ -757,6 +758,7 @@ int hsp2g_batch_destroy(hsp2g_batch *b) {
     cudaFree(b->cal);
     cudaFree(b->d_periods);
     if (b->last_launch) cudaEventDestroy(b->last_launch);
+    if (b->group_fork) cudaEventDestroy(b->group_fork);
     drop_kernel_image(b);
     for (auto &s : b->slot) {
         cudaFree(s.forc);
@@ -976,6 +978,51 @@ int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d
 }
 
 void *hsp2g_batch_stream(hsp2g_batch *b) { return b ? (void *)b->comp : nullptr; }
+
+int hsp2g_run_device_group(int32_t n_batches, hsp2g_batch *const *batches, int64_t t0, int32_t nsteps, const void *d_forc,
+                           int64_t ldf, void *d_out, int64_t ldo, const int64_t *first_column, void *stream) {
+    if (n_batches <= 0 || !batches || !first_column) return fail("bad group arguments");
+    hsp2g_batch *b0 = batches[0];
+    if (!b0) return fail("null batch");
+    for (int k = 0; k < n_batches; ++k) {
+        hsp2g_batch *b = batches[k];
+        if (!b) return fail("null batch");
+        if (b->device != b0->device || b->plain != b0->plain || b->nf != b0->nf || b->ns != b0->ns || b->out_f32 != b0->out_f32 ||
+            b->forc_f32 != b0->forc_f32 || (b->met != nullptr) != (b0->met != nullptr))
+            return fail("the batches of a group share one series buffer: same device, layout, row sets and element types");
+        if (first_column[k] < 0 || (first_column[k] % LAND_TILE)) return fail("first_column must be a multiple of 32");
+        if (check_ready(b, t0, nsteps)) return 1;
+    }
+    if (b0->nf > 0 && !d_forc && !b0->met) return fail("null forcing pointer");
+    if (b0->ns > 0 && !d_out) return fail("null output pointer");
+    DeviceGuard g(b0->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : b0->comp;
+    const size_t fesz = b0->forc_f32 ? 4 : 8, osz = b0->out_f32 ? 4 : 8;
+    // fork: every batch's own stream waits for the caller's stream; join: the caller's stream waits for every batch's launch.
+    // The launches overlap on the device (each is too small to fill it: a group is the part of an ensemble that carries one
+    // option word and runs the kernel built for that word).
+    if (!b0->group_fork) CU(cudaEventCreateWithFlags(&b0->group_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(b0->group_fork, st));
+    for (int k = 0; k < n_batches; ++k) {
+        hsp2g_batch *b = batches[k];
+        const int64_t c0 = first_column[k];
+        const char *f = (const char *)d_forc;
+        char *o = (char *)d_out;
+        if (b->plain) {
+            if (c0 + b->n_pad > ldf && b->nf > 0 && !b->met) return fail("group %d: columns beyond ld_forcing", k);
+            if (c0 + b->n_pad > ldo && b->ns > 0) return fail("group %d: columns beyond ld_out", k);
+            if (f) f += (size_t)c0 * fesz;
+            if (o) o += (size_t)c0 * osz;
+        } else {  // TILED: the group's tiles are contiguous
+            if (f) f += (size_t)(c0 / LAND_TILE) * nsteps * b->nf * LAND_TILE * fesz;
+            if (o) o += (size_t)(c0 / LAND_TILE) * nsteps * b->ns * LAND_TILE * osz;
+        }
+        if (b->comp != st) CU(cudaStreamWaitEvent(b->comp, b0->group_fork, 0));
+        if (launch(b, t0, nsteps, f, ldf, o, ldo, b->comp)) return 1;
+        if (b->comp != st) CU(cudaStreamWaitEvent(st, b->last_launch, 0));
+    }
+    return 0;
+}
 
 int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_forc, int64_t ldf, void *h_out, int64_t ldo) {
     if (check_ready(b, t0, nsteps)) return 1;

@@ -117,6 +117,11 @@ class LandBatch:
         consecutive segments: lanes that see similar weather build, melt and lose their snowpack in the same intervals and
         get wet together, so they take the same branches.  Pass the result as LandBatch(order=...); run() and the state /
         error accessors keep speaking the caller's order."""
+        return store.divergence_order(keys=LandBatch.climate_keys(forcing_names, forcing_sample, bins))
+
+    @staticmethod
+    def climate_keys(forcing_names, forcing_sample, bins=16):
+        """The per-segment sort keys climate_order uses (most significant first): air-temperature class, mean precipitation."""
         names = list(forcing_names)
         f = np.asarray(forcing_sample)
         keys = []
@@ -127,7 +132,7 @@ class LandBatch:
             keys.append(np.floor((t - t.min()) / span * bins).clip(0, bins - 1) if span > 0 else np.zeros_like(t))
         if "PREC" in names:
             keys.append(f[:, names.index("PREC"), :].mean(axis=0))
-        return store.divergence_order(keys=tuple(keys))
+        return tuple(keys)
 
     # ------------------------------------------------------------------------------------------------
     def _upload(self, forcing_names, save, timing):
@@ -510,6 +515,114 @@ class LandBatch:
             self.close()
         except Exception:
             pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class GroupedLandBatch:
+    """An ensemble whose segments carry SEVERAL option words, run as one group per word: the segments are sorted by word
+    (divergence-aware sorting), every group is a LandBatch of its own -- so it gets the kernel built for ITS word, with every
+    option test folded away (jit.py) -- and the groups are launched together over column ranges of one series buffer
+    (hsp2g_run_device_group), sharing the GPU.  A mixed ensemble otherwise runs the one kernel that tests the options at run
+    time: larger code, more registers, fewer resident warps (profiles/README.md: 250k full-chain segments with 48 words).
+
+    Device columns: group g owns [first_column[g], first_column[g] + npad_g); `column_of[i]` is the device column of the caller's
+    segment i.  run() takes and returns arrays in the caller's order; run_device() works on a buffer of `width` columns."""
+
+    def __init__(self, store, calendar, forcing_names, save, device=0, layout="plain", jit=None, keys=(), min_group=1, **kw):
+        self.store, self.cal, self.n = store, calendar, store.n
+        words, inv = np.unique(store.flags, return_inverse=True)
+        keys = tuple(np.asarray(k) for k in keys)
+        self.groups, self.first_column, self.members = [], [], []
+        col = 0
+        try:
+            for w in range(len(words)):
+                idx = np.flatnonzero(inv == w)
+                if keys:  # climate / caller keys inside a group (most significant first)
+                    idx = idx[np.lexsort([k[idx] for k in reversed(keys)])]
+                b = LandBatch(store.subset(idx), calendar, forcing_names, save, device=device, layout=layout, jit=jit, order=None, **kw)
+                self.groups.append(b)
+                self.members.append(idx)
+                self.first_column.append(col)
+                col += b.npad
+        except Exception:
+            self.close()
+            raise
+        self.width = col
+        self.column_of = np.empty(self.n, dtype=np.int64)
+        for c0, idx in zip(self.first_column, self.members):
+            self.column_of[idx] = c0 + np.arange(len(idx))
+        g0 = self.groups[0]
+        self.lib, self.layout, self.device = g0.lib, layout, device
+        self.nf, self.ns, self.forcing_rows, self.save_rows, self.save = g0.nf, g0.ns, g0.forcing_rows, g0.save_rows, g0.save
+        self.forcing_names = g0.forcing_names
+        self._handles = (_lib._h * len(self.groups))(*[b.h for b in self.groups])
+        self._cols = np.ascontiguousarray(self.first_column, dtype=np.int64)
+        if any(b.jit for b in self.groups):  # build the groups' kernels side by side, not one after the other at first launch
+            from . import jit as _jit
+
+            try:
+                _jit.prebuild([_jit.spec_of(b) for b in self.groups], _lib.build_kind())
+            except Exception:
+                pass  # a group whose kernel cannot be built runs the library's general kernel (LandBatch._kernel records why)
+
+    def run_device(self, t0, nsteps, d_forcing, d_out, stream=0, ldf=None, ldo=None):
+        """d_forcing / d_out: device buffers of `width` columns -- PLAIN [nsteps][rows][ld] (ld default width) or TILED
+        [width/32][nsteps][rows][32] -- with group g's segments in columns first_column[g].. in `members[g]` order."""
+        for b in self.groups:
+            b._kernel()
+        _lib.check(self.lib.hsp2g_run_device_group(len(self.groups), self._handles, int(t0), int(nsteps), d_forcing or None,
+                                                   int(ldf or self.width), d_out, int(ldo or self.width),
+                                                   self._cols.ctypes.data_as(C.POINTER(C.c_int64)), stream or None))
+
+    def run(self, forcing, chunk=None):
+        """forcing [steps][nf][n] in the caller's segment order -> out [steps][ns][n]; host path, one group after the other."""
+        forcing = np.asarray(forcing)
+        out = np.empty((forcing.shape[0], self.ns, self.n), dtype=self.groups[0].out_dtype)
+        for b, idx in zip(self.groups, self.members):
+            out[:, :, idx] = b.run(np.ascontiguousarray(forcing[:, :, idx]), chunk=chunk)
+        return out
+
+    def _gather(self, fn, dtype):
+        parts = [fn(b) for b in self.groups]
+        out = np.empty(parts[0].shape[:-1] + (self.n,), dtype=dtype)
+        for p, idx in zip(parts, self.members):
+            out[..., idx] = p
+        return out
+
+    def get_state(self):
+        return self._gather(lambda b: b.get_state(), np.float64)
+
+    def errors(self):
+        per = [b.errors() for b in self.groups]
+        out = {k: np.empty(self.n, dtype=np.int64) for k in per[0]}
+        for e, idx in zip(per, self.members):
+            for k, v in e.items():
+                out[k][idx] = v
+        return out
+
+    def set_output_dtype(self, dtype):
+        for b in self.groups:
+            b.set_output_dtype(dtype)
+
+    def set_schedule(self, sub_steps):
+        for b in self.groups:
+            b.set_schedule(sub_steps)
+
+    def sync(self):
+        for b in self.groups:
+            b.sync()
+
+    def kernel_names(self):
+        return [b.kernel_name() for b in self.groups]
+
+    def close(self):
+        for b in getattr(self, "groups", ()):
+            b.close()
 
     def __enter__(self):
         return self

@@ -497,6 +497,19 @@ class SegmentStore:
         return st
 
     # ------------------------------------------------------------------------------------------------
+    def subset(self, idx):
+        """The segments `idx` (any order) as a store of their own."""
+        import copy as _copy
+
+        idx = np.asarray(idx, dtype=np.int64)
+        st = _copy.copy(self)
+        st.n = len(idx)
+        st.par = np.ascontiguousarray(self.par[:, idx])
+        st.state = np.ascontiguousarray(self.state[:, idx])
+        st.flags = np.ascontiguousarray(self.flags[idx])
+        st.monthly = {k: np.ascontiguousarray(v[:, idx]) for k, v in self.monthly.items()}
+        return st
+
     def permute(self, perm):
         """Reorder the segments in place: new position i holds old segment perm[i]."""
         perm = np.asarray(perm, dtype=np.int64)

@@ -160,6 +160,13 @@ int hsp2g_run_device_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *
                         int64_t ld_out, void *stream);
 int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_forcing, int64_t ld_forcing, void *h_out,
                       int64_t ld_out);
+/* Several batches over ONE series buffer, launched so that they overlap on the device: batch k owns the columns (segments)
+ * [first_column[k], first_column[k] + npad_k) of forcing / out (first_column a multiple of 32; PLAIN: ld >= the last column;
+ * TILED: its tiles are contiguous).  This is how an ensemble with several option words runs: its segments are grouped by word
+ * (divergence-aware sorting), each group is a batch with the kernel built for its word, and the groups -- each too small to
+ * fill the GPU -- share it.  Every batch runs on its own stream, forked from and joined to `stream` (NULL = batches[0]'s). */
+int hsp2g_run_device_group(int32_t n_batches, hsp2g_batch *const *batches, int64_t t0, int32_t nsteps, const void *d_forcing,
+                           int64_t ld_forcing, void *d_out, int64_t ld_out, const int64_t *first_column, void *stream);
 /* A kernel built for exactly this batch -- activity mask, forcing rows, SAVE set, element types, layout and, when every segment
  * carries the same option word, that word fixed at compile time (hspsquared_b200/jit.py generates the instantiation from
  * csrc/land_kernels.cuh and compiles it with `nvcc -cubin`).  image = the cubin (sm_100a), entry = its kernel, whose companion

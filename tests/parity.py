@@ -819,3 +819,76 @@ def check_streaming_sink(tmpdir, n=37, days=9, chunk=50, device=0, pinned=False)
         assert got.to_numpy().dtype == np.float32
         assert np.array_equal(got.to_numpy(), want.to_numpy(), equal_nan=True), (seg, act)
     assert "PET" not in store.read_ts("RESULT", "PERLND", segs[0], "PWATER").columns
+
+
+def check_grouped_batch(n=300, device=0, layout="plain", jit=None):
+    """engine.GroupedLandBatch (one batch and one kernel per option word, launched together over column ranges of one series
+    buffer, hsp2g_run_device_group) against the single mixed batch that tests the options at run time: every segment of a
+    full-chain ensemble with per-segment option flags comes out bit for bit the same -- through run() and through the
+    device-resident group launch --, state and error counts included."""
+    import ctypes as C
+
+    from hspsquared_b200.engine import GroupedLandBatch, tile_series, untile_series
+
+    cal = Calendar("1976-02-25", "1976-03-08", 60, "us")
+    steps = cal.steps
+    ens = synth.Ensemble("PERLND", n, seed=77, base="cbp", options=("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG"))
+    names = list(synth.FULLCHAIN_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, steps, names=names)
+    save = list(cbp10()) + ["SNOW_PACKF", "PSTEMP_SLTMP"]
+    store = ens.store(cal)
+    with LandBatch(store, cal, names, save, device=device, jit=False) as b:
+        ref = b.run(f, chunk=100)
+        ref_state, ref_err = b.get_state(), b.errors()
+    lib = _lib.load()
+    with GroupedLandBatch(store, cal, names, save, device=device, layout=layout, jit=jit, keys=(ens.u_airt,)) as g:
+        assert len(g.groups) == len(np.unique(store.flags)) > 8
+        got = g.run(f, chunk=100)
+        assert np.array_equal(got, ref, equal_nan=True)
+        assert np.array_equal(g.get_state(), ref_state, equal_nan=True)
+        e = g.errors()
+        assert all(np.array_equal(e[k], ref_err[k]) for k in ref_err)
+        if jit:
+            assert all(",jit>" in k and "options=0x" in k for k in g.kernel_names()), g.kernel_names()[:3]
+    # device-resident: one buffer of `width` columns, the groups launched together
+    with GroupedLandBatch(store, cal, names, save, device=device, layout=layout, jit=jit, keys=(ens.u_airt,)) as g:
+        W = g.width
+        fdev = np.zeros((steps, g.nf, W))
+        frows = [names.index(r) for r in g.forcing_rows]
+        for c0, idx, b in zip(g.first_column, g.members, g.groups):
+            cols = np.concatenate([idx, np.repeat(idx[-1:], b.npad - len(idx))])
+            fdev[:, :, c0:c0 + b.npad] = f[:, frows, :][:, :, cols]
+        if layout == "tiled":
+            fbuf = np.concatenate([tile_series(fdev[:, :, c0:c0 + b.npad]) for c0, b in zip(g.first_column, g.groups)], axis=0)
+        else:
+            fbuf = np.ascontiguousarray(fdev)
+        obytes = steps * g.ns * W * 8
+        d_f, d_o = lib.hsp2g_device_alloc(device, fbuf.nbytes), lib.hsp2g_device_alloc(device, obytes)
+        assert d_f and d_o
+        try:
+            _lib.check(lib.hsp2g_memcpy_h2d(device, d_f, fbuf.ctypes.data, fbuf.nbytes))
+            for t0 in range(0, steps, 96):  # chunked: the state is carried inside every group
+                m = min(96, steps - t0)
+                if layout == "plain":
+                    g.run_device(t0, m, d_f + t0 * g.nf * W * 8, d_o + t0 * g.ns * W * 8)
+                else:  # tile-major buffers hold one chunk: stage the chunk
+                    fb = np.concatenate([tile_series(fdev[t0:t0 + m, :, c0:c0 + b.npad]) for c0, b in zip(g.first_column, g.groups)], axis=0)
+                    _lib.check(lib.hsp2g_memcpy_h2d(device, d_f, fb.ctypes.data, fb.nbytes))
+                    g.run_device(t0, m, d_f, d_o + t0 * g.ns * W * 8)
+                g.sync()
+            raw = np.empty(steps * g.ns * W)
+            _lib.check(lib.hsp2g_memcpy_d2h(device, raw.ctypes.data, d_o, obytes))
+        finally:
+            lib.hsp2g_device_free(device, C.c_void_p(d_f))
+            lib.hsp2g_device_free(device, C.c_void_p(d_o))
+        if layout == "plain":
+            dev = raw.reshape(steps, g.ns, W)
+        else:
+            dev = np.empty((steps, g.ns, W))
+            for t0 in range(0, steps, 96):
+                m = min(96, steps - t0)
+                blk = raw[t0 * g.ns * W:(t0 + m) * g.ns * W].reshape(W // 32, m, g.ns, 32)
+                dev[t0:t0 + m] = untile_series(blk, W)
+        srows = [g.save_rows.index(s_) for s_ in g.save]
+        assert np.array_equal(dev[:, srows, :][:, :, g.column_of], ref, equal_nan=True)
+        assert np.array_equal(g.get_state(), ref_state, equal_nan=True)

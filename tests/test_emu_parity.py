@@ -129,3 +129,8 @@ def test_metric_units_refused_where_not_implemented():
     cal = Calendar("1976-01-01", "1976-01-03", 60, "us")
     with pytest.raises(NotImplementedError, match="metric"):
         SegmentStore.from_tables("PERLND", [case["tables"]], cal, units=2)
+
+
+@pytest.mark.parametrize("layout", ["plain", "tiled"])
+def test_groups_by_option_word_equal_the_mixed_batch(layout):
+    parity.check_grouped_batch(n=200, layout=layout)

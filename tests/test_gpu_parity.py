@@ -438,3 +438,10 @@ def test_handles_driven_from_threads_of_one_process():
     for (o, st, er), (o2, st2, er2) in zip(alone, got):
         assert np.array_equal(o, o2, equal_nan=True) and np.array_equal(st, st2, equal_nan=True)
         assert all(np.array_equal(er[k], er2[k]) for k in er)
+
+
+@pytest.mark.parametrize("layout", ["plain", "tiled"])
+def test_groups_by_option_word_equal_the_mixed_batch(layout):
+    """BASELINE configs[3] machinery: a full-chain ensemble with per-segment option flags as one batch (and one kernel built for
+    its word) per option word, launched together on the device, equals the single mixed batch bit for bit (3,000 segments)."""
+    parity.check_grouped_batch(n=3000, layout=layout, jit=True)
