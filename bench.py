@@ -27,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# before the first CUDA call of the process (hspsquared_b200/__init__.py does the same): one hardware queue per stream for the
+# ensembles that run one kernel per option word (engine.GroupedLandBatch)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 BYTES_PER_SEGSTEP = 8 * (6 + 24)  # 6 forcings read + 24 default-SAVE series written, fp64
 N_SEG_PER_GPU = 100_000

@@ -649,9 +649,30 @@ class QualBatch(LandBatch):
         from .qualstore import qual_store
 
         store = qual_store(operation, uci_list, calendar)
+        self.dep_keys = None
         if any(store.dep_series):
-            raise NotImplementedError("atmospheric deposition given as input series (PQADFG / IQADFG = -1): use the drop-in "
-                                      "activities, which feed every row its own column")
+            # Some constituent takes its atmospheric deposition from an input series (PQADFG / IQADFG = -1, PQUAL.py:94-103,
+            # IQUAL.py:88-94).  The deposition flux / concentration then are forcing rows of the batch (QADFX, QADCN), one column
+            # per (segment, constituent) row: gather() fills a row's column from the caller's series where the row's flag is
+            # -1 and, elsewhere, with the very series the reference's wrapper builds for it (its monthly table interpolated to
+            # the day, or zeros) -- what the kernel would have computed itself.
+            if land is not None:
+                raise NotImplementedError("deposition input series with the device-resident chain (land=...): feed the rows "
+                                          "through gather() / run()")
+            forcing_names = [n for n in forcing_names if n not in ("QADFX", "QADCN")] + ["QADFX", "QADCN"]
+            sec, ad = ("IQUAL", "IQAD") if operation == "IMPLND" else ("PQUAL", "PQAD")
+            self.dep_keys, self._dep_base = [], np.zeros((calendar.steps, 2, store.n))
+            for j, (i, k) in enumerate(store.rows):
+                uci = uci_list[i]
+                keys = {}
+                u = uci.get("FLAGS")
+                for c, nm in enumerate(("FX", "CN")):
+                    val = u[ad + "FG" + str(2 * k - 1 + c)] if u is not None else 0
+                    if val > 0:
+                        self._dep_base[:, c, j] = calendar.initm(uci, val, "%s%d_MONTHLY/%s%s" % (sec, k, ad, nm), 0.0)[:calendar.steps]
+                    elif val == -1:
+                        keys[nm] = "%s%s%d" % (ad, nm, k)  # the caller's series: deposition[(segment index, this key)]
+                self.dep_keys.append(keys)
         self.rows = store.rows
         self.row_segment = np.array([i for i, _k in store.rows], dtype=np.int64)
         if land is not None and isinstance(order, str) and order == "flags":
@@ -662,11 +683,23 @@ class QualBatch(LandBatch):
         if land is not None:
             self.attach(land)
 
-    def gather(self, series):
-        """{name: [steps][n_segments] or [steps]} -> forcing [steps][nf][rows] in `forcing_names` order."""
+    def gather(self, series, deposition=None):
+        """{name: [steps][n_segments] or [steps]} -> forcing [steps][nf][rows] in `forcing_names` order.
+        deposition: {(segment index, 'PQADFX<k>' | 'PQADCN<k>' | 'IQADFX<k>' | 'IQADCN<k>'): float64[steps]} for the constituents
+        whose deposition flag is -1 (`dep_keys[row]` names what each row needs)."""
         steps = len(next(iter(series.values())))
         out = np.empty((steps, len(self.forcing_names), self.n))
         for r, nme in enumerate(self.forcing_names):
+            if self.dep_keys is not None and nme in ("QADFX", "QADCN"):
+                c = 0 if nme == "QADFX" else 1
+                out[:, r, :] = self._dep_base[:steps, c, :]
+                for j, keys in enumerate(self.dep_keys):
+                    key = keys.get("FX" if c == 0 else "CN")
+                    if key is not None:
+                        if deposition is None or (self.rows[j][0], key) not in deposition:
+                            raise KeyError("deposition series %r of segment %d is an input (flag -1) and was not given" % (key, self.rows[j][0]))
+                        out[:, r, j] = np.asarray(deposition[(self.rows[j][0], key)], dtype=np.float64)[:steps]
+                continue
             a = np.asarray(series[nme], dtype=np.float64)
             out[:, r, :] = a[:steps, None] if a.ndim == 1 else a[:steps][:, self.row_segment]
         return out

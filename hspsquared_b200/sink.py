@@ -144,6 +144,10 @@ def stream_batch(sink, batch, siminfo, operation, segment_names, save_tables, fo
         raise ValueError("stream_batch needs LandBatch(layout='plain')")
     tindex = siminfo["tindex"]
     steps = len(tindex)
+    if batch.order is not None:
+        # the store keeps the batch's DEVICE order (divergence-aware sorting): a block names its segments, so nothing is
+        # permuted on the way out and read_ts finds a segment by name
+        segment_names = [segment_names[i] for i in batch.order]
     rows_of = {}
     for r, full in enumerate(batch.save_rows):
         act, name = full.split("_", 1)
@@ -157,7 +161,6 @@ def stream_batch(sink, batch, siminfo, operation, segment_names, save_tables, fo
         plan[act] = (cols, np.array([have[k] for k in cols]), sink.open_block(operation, act, segment_names, cols, tindex))
     if batch.out_dtype != np.float32:
         batch.set_output_dtype(np.float32)  # the cast save_timeseries applies (utilities.py:313), done by the kernel's store
-    seg_order = None if batch.order is None else np.asarray(batch._inv)
     alloc = (lambda shape: pinned_empty(shape, np.float32)) if pinned else (lambda shape: np.empty(shape, np.float32))
     nbuf = 3  # chunk c computes / copies out while c-1 is being written and c-2's write finishes
     bufs = [alloc((min(chunk, steps), batch.ns, batch.n)) for _ in range(nbuf)]
@@ -166,8 +169,12 @@ def stream_batch(sink, batch, siminfo, operation, segment_names, save_tables, fo
     def drain(t0, t1, k):
         o = bufs[k][: t1 - t0]
         for act, (cols, rows, block) in plan.items():
-            for j, r in enumerate(rows):  # one contiguous [chunk][n] slab per saved column (numpy releases the GIL while it copies)
-                block[t0:t1, j, :] = o[:, r, :] if seg_order is None else o[:, r, :][:, seg_order]
+            lo, hi = int(rows.min()), int(rows.max())
+            if hi - lo + 1 == len(rows) and np.array_equal(rows, np.arange(lo, hi + 1)):
+                block[t0:t1] = o[:, lo:hi + 1, :]  # the activity's columns are consecutive rows: one strided block copy
+            else:
+                for j, r in enumerate(rows):  # one [chunk][n] slab per saved column (numpy releases the GIL while it copies)
+                    block[t0:t1, j, :] = o[:, r, :]
 
     writes = [None] * nbuf
     chunks = [(t0, min(steps, t0 + chunk)) for t0 in range(0, steps, chunk)]

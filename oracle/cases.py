@@ -100,6 +100,8 @@ def forcings(case):
         out["PERO"] = out["SURO"] + out["IFWO"] + out["AGWO"]
         out["WSSD"] = np.where(out["SURO"] > 0.0, 0.05 * rng.random(steps), 0.0)
         out["SCRSD"] = np.where(out["SURO"] > 0.01, 0.01 * rng.random(steps), 0.0)
+    for key, scale in case.get("dep_series", {}).items():  # atmospheric deposition given as an input series (flag -1)
+        out[key] = scale * rng.random(steps) * (rng.random(steps) > 0.5)
     if case.get("runoff_inputs"):  # SURO / SURS given as external series (the sections that make them are off)
         out["SURO"] = np.where(out["PREC"] > 0.0, 0.8 * out["PREC"], 0.0) * rng.random(steps)
         out["SURS"] = 0.05 * rng.random(steps)
@@ -287,6 +289,12 @@ def build_cases():
     t["PQUAL"]["FLAGS"].update({"PQADFG3": 1})
     t["PQUAL"]["PQUAL2_MONTHLY/PQADFX"] = monthly([.001] * 12)
     add("p_pqual_alone", "PERLND", t, "perlnd", steps=24 * 150, qual_inputs=True)
+    # ... and atmospheric deposition as INPUT SERIES (PQADFG = -1, PQUAL.py:94-103): constituent 3 takes its dry flux from a
+    # series (its wet concentration stays monthly), constituent 2 its wet concentration
+    t = {"ACTIVITY": {"PQUAL": 1}, "PQUAL": test10.pqual_tables()}
+    t["PQUAL"]["FLAGS"].update({"PQADFG5": -1, "PQADFG6": 1, "PQADFG4": -1})
+    add("p_pqual_depseries", "PERLND", t, "perlnd", steps=24 * 120, qual_inputs=True,
+        dep_series={"PQADFX3 1": 0.004, "PQADCN2 1": 0.02})
 
     # -- the reference's own unit-test cases (tests/ipwater/test_ipwater.py:43-84) ----------------
     fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}

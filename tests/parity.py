@@ -87,7 +87,8 @@ def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps
         with QualBatch(op, ucis, cal, qn, "all", device=device) as q:
             if sub_steps is not None:
                 q.set_schedule(sub_steps)
-            qout = q.run(q.gather(series), chunk=chunk)
+            dep = {(i, key[:-2]): v for key, v in forc.items() if key.endswith(" 1") for i in range(replicate)}
+            qout = q.run(q.gather(series, dep), chunk=chunk)
             errs[qsec] = q.segment_errors(replicate)
             kname = kname or q.kernel_name()
             for j, (i, k) in enumerate(q.rows):
