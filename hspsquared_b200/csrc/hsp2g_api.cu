@@ -114,6 +114,7 @@ struct hsp2g_batch {
     std::vector<int> periods;  // hsp2g_set_output_periods: period of every interval of the run (empty = series out)
     int flags_uniform = 0;  // every segment carries flags_word (a replicated ensemble): kernels specialised on the word apply
     unsigned long long flags_word = 0;
+    unsigned long long flags_and = 0, flags_or = 0;
     cudaStream_t comp = nullptr, h2d = nullptr, d2h = nullptr;
     Slot slot[2];
     int next_slot = 0;
@@ -339,7 +340,9 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
     if (I[JI_HOURLY] && !(b->delt >= 60.0)) return false;
     if (((bits & JB_SHARED) != 0) != (L.met != nullptr)) return false;
     if (bits & JB_WORD) {
-        if (!L.flags_uniform || L.flags_word != I[JI_WORD]) return false;
+        // every bit fixed at compile time must be one all segments agree on, with the value the kernel was built for
+        const unsigned long long mask = I[JI_MASK];
+        if (((L.flags_and ^ L.flags_or) & mask) || ((L.flags_and ^ I[JI_WORD]) & mask)) return false;
     }
     if (bits & JB_LAYSTATIC) {
         if (((bits & JB_PLAIN) != 0) != (L.plain != 0)) return false;
@@ -419,6 +422,8 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
     L.opts = b->opts;
     L.flags_uniform = b->flags_uniform;
     L.flags_word = b->flags_word;
+    L.flags_and = b->flags_and;
+    L.flags_or = b->flags_or;
     L.delt = b->delt;
     L.delt60 = b->delt / 60.0;
     memcpy(L.frow, b->frow, sizeof L.frow);
@@ -798,7 +803,12 @@ int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags) {
     if (upload_rows(b->segblk, SB_ROWS, SB_FLAGS, flags, b->n_seg, b->n_seg, b->ntiles, 1)) return 1;
     b->flags_word = flags[0];
     b->flags_uniform = 1;
-    for (int64_t i = 1; i < b->n_seg && b->flags_uniform; ++i) b->flags_uniform = flags[i] == flags[0];
+    b->flags_and = b->flags_or = flags[0];
+    for (int64_t i = 1; i < b->n_seg; ++i) {
+        b->flags_and &= flags[i];
+        b->flags_or |= flags[i];
+    }
+    b->flags_uniform = b->flags_and == b->flags_or;
     b->have_flags = true;
     return 0;
 }

@@ -111,6 +111,7 @@ struct LandLaunch {
     unsigned opts;
     int flags_uniform;              // 1: every segment of the batch carries the option word flags_word
     unsigned long long flags_word;
+    unsigned long long flags_and, flags_or;  // AND / OR of all segments' option words: the bits they agree on are ~(and ^ or)
     double delt, delt60;
     short frow[HSP2G_NFORC];    // forcing id -> row in forc, or -1
     double ffill[HSP2G_NFORC];  // value read when the id is absent
@@ -568,17 +569,19 @@ __host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 
 
 // per-thread view of the batch
 
-// Option word of the batch: DynFlags reads each segment's 64-bit word from its segment block; StaticFlags<W> is for batches
-// whose segments all carry the word W (a replicated / calibration ensemble): every option test folds at compile time, the
-// sections a word switches off (degree-day snow, ARM routing, UZINF2, ...) vanish from the kernel.
+// Option words of the batch.  DynFlags reads each segment's 64-bit word from its segment block.  StaticFlags<W, MASK> fixes, at
+// compile time, the bits every segment of the batch agrees on (MASK; their common values in W): the tests of those bits fold
+// and the sections they switch off (degree-day snow, ARM routing, UZINF2, monthly-table paths ...) vanish from the kernel; only
+// the bits that really differ between segments are read from the segment's word.  MASK = all ones is the replicated /
+// calibration ensemble (one option word); an ensemble with a few options drawn per segment still agrees on most of the 62 bits.
 struct DynFlags {
     static constexpr bool KNOWN = false;
-    static constexpr unsigned long long W = 0;
+    static constexpr unsigned long long W = 0, MASK = 0;
 };
-template <unsigned long long W_>
+template <unsigned long long W_, unsigned long long MASK_ = ~0ull>
 struct StaticFlags {
     static constexpr bool KNOWN = true;
-    static constexpr unsigned long long W = W_;
+    static constexpr unsigned long long W = W_, MASK = MASK_;
 };
 
 template <class IO_, unsigned long long HOT_, bool SHARED_ = false, class FW_ = DynFlags, class LAY_ = TiledLay>
@@ -663,7 +666,7 @@ struct Seg {
         if (!SHARED && lay_f32in<LAY>(L)) return (double)reinterpret_cast<const float *>(stage)[r * LAND_TILE];
         return reinterpret_cast<const double *>(stage)[r * LAND_TILE];
     }
-    __device__ __forceinline__ bool flag(int bit) const { return ((FW::KNOWN ? FW::W : fl) >> bit) & 1ull; }
+    __device__ __forceinline__ bool flag(int bit) const { return ((((FW::MASK >> bit) & 1ull) ? FW::W : fl) >> bit) & 1ull; }
     __device__ __forceinline__ double par(int id) const {
         if (id < 64 && ((HOT >> (id & 63)) & 1ull)) return hot[hsp_popc(HOT & ((1ull << (id & 63)) - 1ull)) * LAND_TILE];
         return __ldg(sb + (SB_PAR + id) * LAND_TILE);

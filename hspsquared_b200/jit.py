@@ -90,13 +90,16 @@ def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="fl
     for nme in save:
         s[O[nme] // 64] |= 1 << (O[nme] % 64)
     qual = bool(act & (_lib.ACT_BITS["PQUAL"] | _lib.ACT_BITS["IQUAL"]))
-    uniform = len(store.flags) > 0 and bool((store.flags == store.flags[0]).all())
+    # the option bits every segment agrees on are fixed at compile time (all 64 for a replicated ensemble)
+    f_and = int(np.bitwise_and.reduce(store.flags)) if len(store.flags) else 0
+    f_or = int(np.bitwise_or.reduce(store.flags)) if len(store.flags) else 0
+    mask = ~(f_and ^ f_or) & 0xFFFFFFFFFFFFFFFF
     f32in = np.dtype(forcing_dtype).itemsize == 4 and not shared
     return {
         "op": 0 if store.operation == "PERLND" else 1, "qual": qual, "act": act, "hourly": bool(delt >= 60),
         "fmask": fmask, "s0": s[0], "s1": s[1], "s2": s[2], "f32out": bool(np.dtype(out_dtype).itemsize == 4),
         "plain": bool(layout == "plain"), "f32in": bool(f32in), "shared": bool(shared),
-        "word": int(store.flags[0]) if (word and uniform and not qual) else None,
+        "word": (f_and & mask) if (word and not qual and mask) else None, "mask": mask if (word and not qual and mask) else 0,
     }
 
 
@@ -132,7 +135,13 @@ def display_name(spec, maxreg):
              "plain" if spec["plain"] else "tiled"]
     if spec["shared"]:
         parts.append("met=shared")
-    parts.append("options=%#x" % spec["word"] if spec["word"] is not None else "options=per-segment")
+    if spec["word"] is None:
+        parts.append("options=per-segment")
+    elif spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF:
+        parts.append("options=%#x" % spec["word"])
+    else:
+        parts.append("options=%#x/fixed:%#x(%d bits per segment)" % (spec["word"], spec["mask"],
+                                                                      _popc(~spec["mask"] & ((1 << len(_lib.names("flags"))) - 1))))
     parts.append("regs<=%d" % maxreg)
     return "%s<%s,jit>" % (kern, ",".join(parts))
 
@@ -144,12 +153,13 @@ def source(spec, maxreg):
     act = spec["act"]
     lines = ["// generated by hspsquared_b200/jit.py for one batch configuration -- not a source file of the repository",
              "// %s" % display_name(spec, maxreg)]
-    if spec["word"] is not None and not (act & CHAIN_ACTS):
+    if spec["word"] is not None and spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF and not (act & CHAIN_ACTS):
         # small kernels (a known option word removes whole sections): the IEEE division sequence inline at every site
         lines.append("#define HSP_INLINE_DIV")
     lines += ['#include "jit_info.h"', '#include "land_kernels.cuh"', '#include "qual.cuh"',
               "typedef StaticIO<%s, %s, %s, %s, %s> IO;" % (u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), b(spec["f32out"]), u(spec["s2"])),
-              "typedef %s FW;" % ("StaticFlags<%s>" % u(spec["word"]) if spec["word"] is not None else "DynFlags"),
+              "typedef %s FW;" % ("StaticFlags<%s, %s>" % (u(spec["word"]), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF)))
+                                  if spec["word"] is not None else "DynFlags"),
               "typedef StaticLay<%s, %s> LAY;" % (b(spec["plain"]), b(spec["f32in"])),
               "constexpr int ACT = %d;" % act, "constexpr bool HOURLY = %s, SHARED = %s;" % (b(spec["hourly"]), b(spec["shared"])),
               "constexpr int FESZ = %d;" % (4 if spec["f32in"] else 8)]
@@ -165,9 +175,9 @@ def source(spec, maxreg):
     bits = " | ".join(n for n, on in (("JB_F32OUT", spec["f32out"]), ("JB_PLAIN", spec["plain"]), ("JB_F32IN", spec["f32in"]),
                                       ("JB_SHARED", spec["shared"]), ("JB_WORD", spec["word"] is not None), ("JB_IOSTATIC", True),
                                       ("JB_LAYSTATIC", True), ("JB_QUAL", spec["qual"])) if on)
-    info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, 0, 0}"
+    info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, %s, 0}"
             % (smem, spec["op"], u(act), int(spec["hourly"]), u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), u(spec["s2"]), bits,
-               u(spec["word"] or 0)))
+               u(spec["word"] or 0), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF) if spec["word"] is not None else 0)))
     lines += ["#ifdef HSP2G_HOST_EMU  /* the CPU test suite's double: a host function with the same body */",
               'extern "C" void %s(const LandLaunch &L) { %s }' % (ENTRY, body),
               'extern "C" const unsigned long long %s_info[JI_N] = %s;' % (ENTRY, info),

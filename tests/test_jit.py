@@ -32,7 +32,7 @@ def test_generated_source_names_what_it_fixes():
         spec = jit.spec_of(b)
     assert spec["word"] == int(ens.store(CAL).flags[0]) and spec["plain"] and not spec["f32in"] and spec["act"] == 6
     text = jit.source(spec, 128)
-    assert "StaticFlags<%#xull>" % spec["word"] in text and "StaticLay<true, false>" in text
+    assert "StaticFlags<%#xull, 0xffffffffffffffffull>" % spec["word"] in text and "StaticLay<true, false>" in text
     assert "perlnd_body<ACT, HOURLY, IO, SHARED, FW, LAY>" in text and "__launch_bounds__(LAND_BLOCK, 8)" in text
     assert "DynFlags" in jit.source(dict(spec, word=None), 168) and "__launch_bounds__(LAND_BLOCK, 6)" in jit.source(spec, 168)
 
