@@ -924,6 +924,8 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
         value = n * Tc * K / (ms * 1e-3)
         errs = {k: int((v != 0).sum()) for k, v in batch.errors().items() if (v != 0).any()}
         return {"config": name, "workload": note, "segments": n, "intervals_per_step": Tc, "steps": K, "warmup": W,
+                "window": "intervals %d..%d of the run (from 1976-01-01: the snow and melt season, the expensive regime)"
+                          % ((first_chunk + W) * Tc, (first_chunk + W + K) * Tc),
                 "series_layout": layout, "segment_order": order,
                 "kernel": batch.kernel_name() if not grouped else "%d kernels, one per option word, launched together; e.g. %s"
                 % (len(batch.groups), batch.kernel_names()[0]),
@@ -1082,8 +1084,10 @@ def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
         return None
     out = {}
     for key, name, kw in (("implnd_100k", "implnd", {"order": "climate"}),
-                          ("fullchain_250k_all84", "fullchain_all", {"K": 12, "order": "groups"}),
-                          ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10, "order": "groups"})):
+                          ("fullchain_250k_all84", "fullchain_all", {"K": 12, "order": "climate"}),
+                          ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10, "order": "climate"}),
+                          ("fullchain_250k_one_word_all84", "fullchain_uniform_all", {"K": 12, "order": "climate"}),
+                          ("fullchain_250k_one_word_cbp10", "fullchain_uniform_cbp10", {"K": 10, "order": "climate"})):
         try:
             out[key] = run_config(torch, dev, name, cal, stream, peak, **kw)
         except Exception as ex:
