@@ -412,6 +412,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations timed beside the headline")
+    ap.add_argument("--no-ensemble", action="store_true", help="N > 1: skip the sharded 1M-segment PERLND+IMPLND ensemble (configs[2])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
@@ -620,7 +621,7 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
     batch.close()
-    if world > 1 and not args.no_extras:
+    if world > 1 and not args.no_ensemble:
         try:
             r = run_sharded_ensemble(torch, dev, local_rank, rank, world, dist, cal, stream, peak, jit)
             if rank == 0:

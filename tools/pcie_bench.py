@@ -100,7 +100,7 @@ def worker(rank, nranks, nbytes, reps, barrier_dir, affinity):
                 raise TimeoutError("barrier " + tag)
 
     res = {"rank": rank, "cpus": (len(cpus) if cpus else None)}
-    for kind in ("default", "wc", "registered", "pageable"):
+    for kind in (("default", "wc", "registered", "pageable") if nranks == 1 else ("default", "wc")):
         h_src, free_src = alloc(kind)
         h_dst, free_dst = alloc("default" if kind == "wc" else kind)
         r = {}
@@ -163,7 +163,7 @@ def main():
             ok = [r for r in ranks if "error" not in r]
             if ok:
                 run["sum"] = {k: {m: round(sum(r[k][m] for r in ok), 1) for m in ("h2d", "d2h", "bidir")}
-                              for k in ("default", "wc", "registered", "pageable")}
+                              for k in ("default", "wc", "registered", "pageable") if all(k in r for r in ok)}
             report["runs"].append(run)
             print(json.dumps({"ranks": R, "affinity": bool(aff), "sum": run.get("sum")}), flush=True)
     if a.out:
