@@ -433,8 +433,8 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"  # keep stdout to the one JSON line (at VERSION and above NCCL prints a banner there)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -994,7 +994,9 @@ def run_sharded_ensemble(torch, dev, local_rank, rank, world, dist, cal, stream,
     gather_ms = 1e3 * (time.perf_counter() - g0)
     res = {"workload": "one %d-segment ensemble = %d PERLND (SNOW+PWATER) + %d IMPLND (SNOW+IWATER), default SAVE sets, split with "
                        "dist.shard_bounds over %d ranks" % (n_total, half, half, world),
-           "scaling": "strong", "segments_total": n_total, "segments_per_rank": [p[1].n for p in parts], "intervals_per_step": Tc,
+           "scaling": "strong", "segments_total": n_total,
+           "window": "intervals %d..%d of the run (1976-01-17 .. 03-21: snow and melt season, the expensive regime; the headline "
+                     "averages a whole year)" % (W * Tc, (W + K) * Tc), "segments_per_rank": [p[1].n for p in parts], "intervals_per_step": Tc,
            "steps": K, "warmup": W, "ms_per_step": ms / K, "value": n_total * Tc * K / (ms * 1e-3), "unit": "segment-timesteps/s",
            "kernels": [p[2].kernel_name() for p in parts],
            "bytes_per_segment_interval": {"PERLND": 240, "IMPLND": 176},
