@@ -41,6 +41,7 @@ _failed = {}
 
 # a batch below this size is not worth a 1-3 s build (the drop-in activities run one segment per call): LandBatch(jit=None)
 MIN_SEGMENTS = int(os.environ.get("HSP2G_JIT_MIN_SEGMENTS", "2048"))
+SPILL_OK = 32  # bytes of register spill tolerated before the register cap is raised
 
 
 def enabled(n_segments=None):
@@ -252,8 +253,9 @@ def ensure(spec, kind=None, maxreg=None):
                 json.dump(meta, f)
             os.replace(mtmp, meta_p)
         tried.append((mr, meta.get("spill_bytes", 0)))
-        # a spilling kernel loses more than the occupancy it keeps (profiles/README.md): give it registers
-        if maxreg is None and not os.environ.get("HSP2G_JIT_MAXREG") and meta.get("spill_bytes", 0) > 0 and mr < 232:
+        # a kernel that spills in earnest loses more than the occupancy it keeps (profiles/README.md: 280 B of spill cost 14 points):
+        # give it registers; a handful of bytes is cheaper than a quarter of the resident warps
+        if maxreg is None and not os.environ.get("HSP2G_JIT_MAXREG") and meta.get("spill_bytes", 0) > SPILL_OK and mr < 232:
             mr = 168 if mr < 168 else 232
             continue
         meta["tried"] = tried
