@@ -26,7 +26,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--years", type=float, default=10.0)
     ap.add_argument("--check", type=int, default=4, help="segments whose whole series is compared with the oracle")
-    ap.add_argument("--ordered", action="store_true", help="divergence-aware segment order")
+    ap.add_argument("--caller-order", action="store_true", help="keep the generator's segment order (default: the engine's "
+                    "automatic divergence-aware order, LandBatch.climate_order)")
+    ap.add_argument("--layout", default="plain", choices=("plain", "tiled"))
     args = ap.parse_args()
 
     import torch
@@ -45,14 +47,17 @@ def main():
     steps = cal.steps
     ens = synth.Ensemble("PERLND", n, seed=1234, sections=("SNOW", "PWATER"))
     store = ens.store(cal)
-    if args.ordered:
-        perm = store.divergence_order(keys=(np.floor(ens.u_airt * 16), ens.u_prec))
+    if not args.caller_order:
+        sample = synth.forcing_chunk(ens, cal, 0, 24 * 7)
+        perm = LandBatch.climate_order(store, list(synth.PERLND_FORCINGS), sample)
+        del sample
         ens = ens.take(perm)
         store = ens.store(cal)
     save = bench.default_save()
-    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=0, layout="tiled")
+    plain = args.layout == "plain"
+    batch = LandBatch(store, cal, list(synth.PERLND_FORCINGS), save, device=0, layout=args.layout, jit=True, order=None)
     npad, nf, ns = batch.npad, batch.nf, batch.ns
-    outs = [torch.empty((npad // 32, Tc, ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+    outs = bench.out_buffers(torch, npad, Tc, ns, dev, args.layout)
     stream = torch.cuda.Stream(dev)
     check = sorted(set(int(x) for x in np.linspace(0, n - 1, args.check))) if args.check else []
     got = {i: np.empty((steps, ns)) for i in check}
@@ -61,7 +66,7 @@ def main():
     ev = []
     l0, _ = batch.kernel_stats()
     for c, (t0, m) in enumerate(chunks):
-        f = bench.device_forcing(torch, ens, cal, t0, m, npad, dev, batch.forcing_rows, "tiled")
+        f = bench.device_forcing(torch, ens, cal, t0, m, npad, dev, batch.forcing_rows, args.layout)
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -69,9 +74,13 @@ def main():
         e1.record(stream)
         stream.synchronize()
         ev.append(e0.elapsed_time(e1))
-        o = outs[c % 2].view(-1)[:(npad // 32) * m * ns * 32].view(npad // 32, m, ns, 32)  # a ragged last chunk is [tile][m]...
-        for i in check:
-            got[i][t0:t0 + m] = o[i // 32, :m, :, i % 32].cpu().numpy()
+        if plain:
+            for i in check:
+                got[i][t0:t0 + m] = outs[c % 2][:m, :, i].cpu().numpy()
+        else:
+            o = outs[c % 2].view(-1)[:(npad // 32) * m * ns * 32].view(npad // 32, m, ns, 32)  # a ragged last chunk is [tile][m]...
+            for i in check:
+                got[i][t0:t0 + m] = o[i // 32, :m, :, i % 32].cpu().numpy()
         del f
     l1, _ = batch.kernel_stats()
     ms = float(np.sum(ev))
@@ -120,7 +129,7 @@ def main():
     errs = batch.errors()
     line = {"workload": "PERLND SNOW+PWATER, %d segments x %d hourly intervals (%.2f years), default SAVE, time-chunked by %d"
                         % (n, steps, steps / 8766.0, Tc),
-            "ordered": bool(args.ordered),
+            "segment_order": "caller's" if args.caller_order else "automatic (LandBatch.climate_order)", "series_layout": args.layout,
             "value": seg_steps / (ms * 1e-3), "unit": "segment-timesteps/s", "kernel_seconds": ms * 1e-3,
             "launches": int(l1 - l0), "kernel": batch.kernel_name(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
