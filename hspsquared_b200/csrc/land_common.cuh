@@ -247,6 +247,13 @@ __host__ __device__ constexpr bool io_saved(int oid) {
 #define HSP_PIN32(v) asm volatile("" : "+r"(v))
 #endif
 
+// Shared-met mode with few stations: the whole station table of an interval ([nf][n_stations] doubles, contiguous in the met
+// array) is fetched by ONE bulk copy per warp-interval and every lane picks its station's column out of shared memory, instead
+// of nf 8-byte gathers per lane (cp.async).  Needs the table to fit a stage (n_stations <= 32) and to be a multiple of 16 bytes.
+__host__ __device__ inline bool met_table_mode(const LandLaunch &L, int nf) {
+    return L.met != nullptr && L.n_stations <= LAND_TILE && ((nf * L.n_stations) & 1) == 0;
+}
+
 // ---- series layout policy: where interval t, row r of a tile lives (see the header of this file) and the element type
 // of the forcings.  StaticLay fixes both at compile time (kernels built for one batch, hspsquared_b200/jit.py);
 // DynLay reads them from the launch record (the general kernels of the library).
@@ -329,6 +336,8 @@ struct PipeT {
     int nf, nst;          // rows per interval; SHARED: stations
     int esz;              // forcing element size in bytes (8, or 4 for float32 forcings)
     int tile;             // PLAIN: current tile
+    int tbl;              // SHARED: 1 = one bulk copy of the interval's station table (met_table_mode), 0 = per-lane gathers
+    int my_station;       // SHARED table mode: this lane's station
     int t_end;            // end of the current task (no copies are issued past it)
     int st;               // stage of the current interval
     unsigned ph;          // its phase parity
@@ -361,7 +370,9 @@ struct PipeT {
         t_end = 0;
         tile = 0;
         src = nullptr;
-        if (!SHARED) {
+        tbl = SHARED && met_table_mode(L, nf);
+        my_station = 0;
+        if (!SHARED || tbl) {
             if (lane == 0) {
                 for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(bar_s + s * 8, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -370,8 +381,15 @@ struct PipeT {
             __syncwarp();
         }
     }
-    __device__ __forceinline__ void issue(int t, int s) {  // SHARED: every lane; else lane 0 only
-        if (SHARED) {
+    __device__ __forceinline__ void issue(int t, int s) {  // SHARED gathers: every lane; else lane 0 only
+        if (SHARED && tbl) {
+            if (t < t_end) {
+                const unsigned bytes = (unsigned)(nf * nst * 8);
+                const unsigned bar = bar_s + s * 8;
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(ring_s + (unsigned)s * (unsigned)stage_bytes, src + (size_t)t * bytes, bytes, bar);
+            }
+        } else if (SHARED) {
             if (t < t_end) {
                 double *dst = reinterpret_cast<double *>(ring + s * stage_bytes) + lane;
                 const double *g = reinterpret_cast<const double *>(src) + (size_t)t * nf * nst;
@@ -399,14 +417,17 @@ struct PipeT {
     __device__ __forceinline__ void begin_task(int tile_, int t0, int t1) {
         const LandLaunch &L = *Lp;
         tile = tile_;
-        if (SHARED)
+        if (SHARED && tbl) {
+            src = reinterpret_cast<const unsigned char *>(L.met);
+            my_station = L.station[tile * LAND_TILE + lane];
+        } else if (SHARED)
             src = reinterpret_cast<const unsigned char *>(L.met + L.station[tile * LAND_TILE + lane]);
         else if (lay_plain<LAY>(L))
             src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * LAND_TILE * esz;
         else
             src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * L.nsteps * stage_bytes;
         t_end = stage_bytes > 0 ? t1 : 0;
-        if (SHARED || lane == 0) {
+        if ((SHARED && !tbl) || lane == 0) {
             int s = st;
             for (int k = 0; k < PIPE_STAGES; ++k) {
                 issue(t0 + k, s);
@@ -416,6 +437,10 @@ struct PipeT {
     }
     // wait for the current interval's forcings; returns this lane's cell of row 0 of the stage
     __device__ __forceinline__ const unsigned char *acquire() {
+        if (SHARED && tbl) {
+            if (t_end > 0) mbar_wait(bar_s + st * 8, ph);
+            return ring + st * stage_bytes + my_station * 8;  // this lane's station's cell of row 0 of the table
+        }
         if (SHARED)
             asm volatile("cp.async.wait_group %0;\n" ::"n"(PIPE_STAGES - 1) : "memory");
         else if (t_end > 0)
@@ -425,7 +450,7 @@ struct PipeT {
     __device__ __forceinline__ double *hot_area() const { return reinterpret_cast<double *>(ring + PIPE_STAGES * stage_bytes); }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
     __device__ __forceinline__ void release(int t) {
-        if (SHARED) {
+        if (SHARED && !tbl) {
             issue(t + PIPE_STAGES, st);
         } else {
             __syncwarp();
@@ -437,7 +462,7 @@ struct PipeT {
         }
     }
     __device__ __forceinline__ void end_task() {
-        if (SHARED) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (SHARED && !tbl) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
 };
 
@@ -497,12 +522,14 @@ struct PipeT {
     unsigned char *ring;
     const LandLaunch *Lp;
     const unsigned char *src;
-    int stage_bytes, lane, t_cur, nf, nst, esz, tile;
+    int stage_bytes, lane, t_cur, nf, nst, esz, tile, tbl, my_station;
     void init(const LandLaunch &L, double *smem, int, int lane_, int nf_, int, int) {
         Lp = &L;
         ring = reinterpret_cast<unsigned char *>(smem);
         nf = nf_;
         nst = L.n_stations;
+        tbl = SHARED && met_table_mode(L, nf_);
+        my_station = 0;
         esz = (!SHARED && lay_f32in<LAY>(L)) ? 4 : 8;
         stage_bytes = nf * LAND_TILE * esz;
         lane = lane_;
@@ -510,7 +537,10 @@ struct PipeT {
     void begin_task(int tile_, int t0, int) {
         const LandLaunch &L = *Lp;
         tile = tile_;
-        if (SHARED)
+        if (SHARED && tbl) {
+            src = reinterpret_cast<const unsigned char *>(L.met);
+            my_station = L.station[tile * LAND_TILE + lane];
+        } else if (SHARED)
             src = reinterpret_cast<const unsigned char *>(L.met + L.station[tile * LAND_TILE + lane]);
         else if (lay_plain<LAY>(L))
             src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * LAND_TILE * esz;
@@ -519,6 +549,10 @@ struct PipeT {
         t_cur = t0;
     }
     const unsigned char *acquire() {
+        if (SHARED && tbl) {
+            memcpy(ring, src + (size_t)t_cur * nf * nst * 8, (size_t)nf * nst * 8);
+            return ring + my_station * 8;
+        }
         if (SHARED) {
             const double *g = reinterpret_cast<const double *>(src);
             for (int r = 0; r < nf; ++r) reinterpret_cast<double *>(ring)[r * LAND_TILE + lane] = g[((size_t)t_cur * nf + r) * nst];
@@ -605,6 +639,7 @@ struct Seg {
     unsigned calfl_next;   // ... of the next one, loaded an interval ahead (an L2 round trip off the critical path)
     long long out_step;    // bytes between consecutive intervals of out
     unsigned out_row;      // bytes between consecutive rows of out (PLAIN; TILED: 32 elements, a compile-time constant)
+    int met_stride;        // SHARED: elements between consecutive rows of a forcing stage (n_stations in table mode, else 32)
 
     // view of `tile` for the task that starts at interval t0 of the launch
     __device__ __forceinline__ Seg(const LandLaunch &l, int tile, int lane, int t0, double *hot_area) : L(l) {
@@ -638,6 +673,7 @@ struct Seg {
             for (int r = 0; r < nfr; ++r) h[(NHOT + r) * LAND_TILE] = __ldg(mg + r * LAND_TILE);
         }
         fl = *reinterpret_cast<const unsigned long long *>(sb + SB_FLAGS * LAND_TILE);
+        met_stride = (SHARED && met_table_mode(l, IO::STATIC ? IO::NF : l.nf)) ? l.n_stations : LAND_TILE;
         stage = nullptr;
         calfl = 0;
         calfl_next = calp->flags;
@@ -664,6 +700,7 @@ struct Seg {
     // forcing row r of the current interval (this lane's segment), widened when the series are float32
     __device__ __forceinline__ double stage_row(int r) const {
         if (!SHARED && lay_f32in<LAY>(L)) return (double)reinterpret_cast<const float *>(stage)[r * LAND_TILE];
+        if (SHARED) return reinterpret_cast<const double *>(stage)[r * met_stride];  // station table: rows n_stations apart
         return reinterpret_cast<const double *>(stage)[r * LAND_TILE];
     }
     __device__ __forceinline__ bool flag(int bit) const { return ((((FW::MASK >> bit) & 1ull) ? FW::W : fl) >> bit) & 1ull; }
