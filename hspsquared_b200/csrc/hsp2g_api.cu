@@ -344,9 +344,11 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
         const unsigned long long mask = I[JI_MASK];
         if (((L.flags_and ^ L.flags_or) & mask) || ((L.flags_and ^ I[JI_WORD]) & mask)) return false;
     }
+    if ((bits & JB_OPTS) && I[JI_OPTS] != (unsigned long long)b->opts) return false;  // HSP2G_OPT_* folded into the kernel
     if (bits & JB_LAYSTATIC) {
         if (((bits & JB_PLAIN) != 0) != (L.plain != 0)) return false;
         if (!(bits & JB_SHARED) && ((bits & JB_F32IN) != 0) != (L.forc_f32 != 0)) return false;
+        if ((bits & JB_SHARED) && ((bits & JB_METTBL) != 0) != (L.met_table != 0)) return false;
     }
     if (bits & JB_IOSTATIC) {
         if (((bits & JB_F32OUT) != 0) != (L.out_f32 != 0)) return false;
@@ -405,6 +407,8 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
         L.station = b->station;
         L.mfac = b->mfac;
         L.n_stations = b->n_stations;
+        static const bool no_table = getenv("HSP2G_NO_MET_TABLE") != nullptr;  // measurement switch: per-lane gathers always
+        L.met_table = !no_table && met_table_fits(b->n_stations, b->nf);
     }
     L.cal = b->cal + t0;
     L.ntiles = (int)b->ntiles;

@@ -91,6 +91,7 @@ struct LandLaunch {
     const int *station;  // [tile][32]
     const double *mfac;  // [tile][nf][32]
     int n_stations;
+    int met_table;       // shared-met: 1 = the interval's whole station table is fetched by one bulk copy (met_table_mode)
     int ntiles;
     int nsteps;
     int sub;          // intervals per task; a task = (tile, sub-chunk) (see Sched)
@@ -250,8 +251,9 @@ __host__ __device__ constexpr bool io_saved(int oid) {
 // Shared-met mode with few stations: the whole station table of an interval ([nf][n_stations] doubles, contiguous in the met
 // array) is fetched by ONE bulk copy per warp-interval and every lane picks its station's column out of shared memory, instead
 // of nf 8-byte gathers per lane (cp.async).  Needs the table to fit a stage (n_stations <= 32) and to be a multiple of 16 bytes.
-__host__ __device__ inline bool met_table_mode(const LandLaunch &L, int nf) {
-    return L.met != nullptr && L.n_stations <= LAND_TILE && ((nf * L.n_stations) & 1) == 0;
+// The host decides (hsp2g_api.cu launch(): L.met_table); kernels built for one batch have the answer at compile time (StaticLay).
+__host__ __device__ inline bool met_table_fits(int n_stations, int nf) {
+    return n_stations > 0 && n_stations <= LAND_TILE && ((nf * n_stations) & 1) == 0;
 }
 
 // ---- series layout policy: where interval t, row r of a tile lives (see the header of this file) and the element type
@@ -259,10 +261,12 @@ __host__ __device__ inline bool met_table_mode(const LandLaunch &L, int nf) {
 // DynLay reads them from the launch record (the general kernels of the library).
 struct DynLay {
     static constexpr bool STATIC = false, PLAIN = false, F32IN = false;
+    static constexpr int METTBL = -1;
 };
-template <bool PLAIN_, bool F32IN_>
+template <bool PLAIN_, bool F32IN_, int METTBL_ = -1>  // METTBL: shared-met table mode 0 / 1, -1 = read L.met_table
 struct StaticLay {
     static constexpr bool STATIC = true, PLAIN = PLAIN_, F32IN = F32IN_;
+    static constexpr int METTBL = METTBL_;
 };
 typedef StaticLay<false, false> TiledLay;
 template <class LAY>
@@ -272,6 +276,10 @@ __device__ __forceinline__ bool lay_plain(const LandLaunch &L) {
 template <class LAY>
 __device__ __forceinline__ bool lay_f32in(const LandLaunch &L) {
     return LAY::STATIC ? LAY::F32IN : (L.forc_f32 != 0);
+}
+template <class LAY>
+__device__ __forceinline__ bool lay_mettbl(const LandLaunch &L) {
+    return LAY::METTBL >= 0 ? LAY::METTBL != 0 : (L.met_table != 0);
 }
 
 #ifndef HSP2G_HOST_EMU
@@ -336,8 +344,9 @@ struct PipeT {
     int nf, nst;          // rows per interval; SHARED: stations
     int esz;              // forcing element size in bytes (8, or 4 for float32 forcings)
     int tile;             // PLAIN: current tile
-    int tbl;              // SHARED: 1 = one bulk copy of the interval's station table (met_table_mode), 0 = per-lane gathers
+    int tbl;              // SHARED: 1 = one bulk copy of the interval's station table (L.met_table), 0 = per-lane gathers
     int my_station;       // SHARED table mode: this lane's station
+    __device__ __forceinline__ bool table() const { return SHARED && (LAY::METTBL >= 0 ? LAY::METTBL != 0 : tbl != 0); }
     int t_end;            // end of the current task (no copies are issued past it)
     int st;               // stage of the current interval
     unsigned ph;          // its phase parity
@@ -370,7 +379,7 @@ struct PipeT {
         t_end = 0;
         tile = 0;
         src = nullptr;
-        tbl = SHARED && met_table_mode(L, nf);
+        tbl = SHARED && lay_mettbl<LAY>(L);
         my_station = 0;
         if (!SHARED || tbl) {
             if (lane == 0) {
@@ -382,7 +391,7 @@ struct PipeT {
         }
     }
     __device__ __forceinline__ void issue(int t, int s) {  // SHARED gathers: every lane; else lane 0 only
-        if (SHARED && tbl) {
+        if (table()) {
             if (t < t_end) {
                 const unsigned bytes = (unsigned)(nf * nst * 8);
                 const unsigned bar = bar_s + s * 8;
@@ -417,7 +426,7 @@ struct PipeT {
     __device__ __forceinline__ void begin_task(int tile_, int t0, int t1) {
         const LandLaunch &L = *Lp;
         tile = tile_;
-        if (SHARED && tbl) {
+        if (table()) {
             src = reinterpret_cast<const unsigned char *>(L.met);
             my_station = L.station[tile * LAND_TILE + lane];
         } else if (SHARED)
@@ -427,7 +436,7 @@ struct PipeT {
         else
             src = reinterpret_cast<const unsigned char *>(L.forc) + (size_t)tile * L.nsteps * stage_bytes;
         t_end = stage_bytes > 0 ? t1 : 0;
-        if ((SHARED && !tbl) || lane == 0) {
+        if ((SHARED && !table()) || lane == 0) {
             int s = st;
             for (int k = 0; k < PIPE_STAGES; ++k) {
                 issue(t0 + k, s);
@@ -437,7 +446,7 @@ struct PipeT {
     }
     // wait for the current interval's forcings; returns this lane's cell of row 0 of the stage
     __device__ __forceinline__ const unsigned char *acquire() {
-        if (SHARED && tbl) {
+        if (table()) {
             if (t_end > 0) mbar_wait(bar_s + st * 8, ph);
             return ring + st * stage_bytes + my_station * 8;  // this lane's station's cell of row 0 of the table
         }
@@ -450,7 +459,7 @@ struct PipeT {
     __device__ __forceinline__ double *hot_area() const { return reinterpret_cast<double *>(ring + PIPE_STAGES * stage_bytes); }
     // all lanes are done with interval t: refill its stage with interval t + PIPE_STAGES
     __device__ __forceinline__ void release(int t) {
-        if (SHARED && !tbl) {
+        if (SHARED && !table()) {
             issue(t + PIPE_STAGES, st);
         } else {
             __syncwarp();
@@ -462,7 +471,7 @@ struct PipeT {
         }
     }
     __device__ __forceinline__ void end_task() {
-        if (SHARED && !tbl) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        if (SHARED && !table()) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
 };
 
@@ -523,12 +532,13 @@ struct PipeT {
     const LandLaunch *Lp;
     const unsigned char *src;
     int stage_bytes, lane, t_cur, nf, nst, esz, tile, tbl, my_station;
+    bool table() const { return SHARED && (LAY::METTBL >= 0 ? LAY::METTBL != 0 : tbl != 0); }
     void init(const LandLaunch &L, double *smem, int, int lane_, int nf_, int, int) {
         Lp = &L;
         ring = reinterpret_cast<unsigned char *>(smem);
         nf = nf_;
         nst = L.n_stations;
-        tbl = SHARED && met_table_mode(L, nf_);
+        tbl = SHARED && lay_mettbl<LAY>(L);
         my_station = 0;
         esz = (!SHARED && lay_f32in<LAY>(L)) ? 4 : 8;
         stage_bytes = nf * LAND_TILE * esz;
@@ -537,7 +547,7 @@ struct PipeT {
     void begin_task(int tile_, int t0, int) {
         const LandLaunch &L = *Lp;
         tile = tile_;
-        if (SHARED && tbl) {
+        if (table()) {
             src = reinterpret_cast<const unsigned char *>(L.met);
             my_station = L.station[tile * LAND_TILE + lane];
         } else if (SHARED)
@@ -549,7 +559,7 @@ struct PipeT {
         t_cur = t0;
     }
     const unsigned char *acquire() {
-        if (SHARED && tbl) {
+        if (table()) {
             memcpy(ring, src + (size_t)t_cur * nf * nst * 8, (size_t)nf * nst * 8);
             return ring + my_station * 8;
         }
@@ -608,14 +618,17 @@ __host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 
 // and the sections they switch off (degree-day snow, ARM routing, UZINF2, monthly-table paths ...) vanish from the kernel; only
 // the bits that really differ between segments are read from the segment's word.  MASK = all ones is the replicated /
 // calibration ensemble (one option word); an ensemble with a few options drawn per segment still agrees on most of the 62 bits.
+// OPTS: the batch-wide HSP2G_OPT_* bits when they too are fixed at compile time (-1: read L.opts).
 struct DynFlags {
     static constexpr bool KNOWN = false;
     static constexpr unsigned long long W = 0, MASK = 0;
+    static constexpr int OPTS = -1;
 };
-template <unsigned long long W_, unsigned long long MASK_ = ~0ull>
+template <unsigned long long W_, unsigned long long MASK_ = ~0ull, int OPTS_ = -1>
 struct StaticFlags {
     static constexpr bool KNOWN = true;
     static constexpr unsigned long long W = W_, MASK = MASK_;
+    static constexpr int OPTS = OPTS_;
 };
 
 template <class IO_, unsigned long long HOT_, bool SHARED_ = false, class FW_ = DynFlags, class LAY_ = TiledLay>
@@ -673,7 +686,7 @@ struct Seg {
             for (int r = 0; r < nfr; ++r) h[(NHOT + r) * LAND_TILE] = __ldg(mg + r * LAND_TILE);
         }
         fl = *reinterpret_cast<const unsigned long long *>(sb + SB_FLAGS * LAND_TILE);
-        met_stride = (SHARED && met_table_mode(l, IO::STATIC ? IO::NF : l.nf)) ? l.n_stations : LAND_TILE;
+        met_stride = (SHARED && lay_mettbl<LAY>(l)) ? l.n_stations : LAND_TILE;
         stage = nullptr;
         calfl = 0;
         calfl_next = calp->flags;
@@ -764,7 +777,8 @@ struct Seg {
         if (IO::STATIC) return io_saved<IO>(oid);
         return L.srow[oid] >= 0;
     }
-    __device__ __forceinline__ bool metric() const { return (L.opts & OPT_METRIC) != 0; }
+    __device__ __forceinline__ unsigned opts() const { return FW::OPTS >= 0 ? (unsigned)FW::OPTS : L.opts; }
+    __device__ __forceinline__ bool metric() const { return (opts() & OPT_METRIC) != 0; }
     __device__ __forceinline__ void save(int oid, double v) const {
         if (metric()) {  // the stored series only (the state stays in English units); a warp-uniform branch
             const int c = metric_out_code(oid);

@@ -129,7 +129,7 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
                 fx.agwo = s.forcing(F_AGWO);
             }
             if (act & HSP2G_ACT_SEDMNT) {
-                const double rain = (L.opts & OPT_SED_RAIN_IS_PREC) ? prec : link.rainf;
+                const double rain = (s.opts() & OPT_SED_RAIN_IS_PREC) ? prec : link.rainf;
                 sedmnt_step(s, sd, rain, prec, link.snocov, fx.suro, fx.surs);
             }
             SoilTemps soil;

@@ -8,6 +8,7 @@ numpy and ctypes alone.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -88,6 +89,7 @@ class LandBatch:
         self.out_dtype = np.dtype(np.float64)
         self.forcing_dtype = np.dtype(np.float64)
         self.shared = False
+        self.met_table = False
         if layout not in ("plain", "tiled"):
             raise ValueError("layout must be 'plain' or 'tiled'")
         self.layout = layout
@@ -176,6 +178,7 @@ class LandBatch:
         ids = np.array([F[nme] for nme in self.forcing_rows], dtype=np.int32)
         if getattr(st, "units", 1) == 2:
             opts |= _lib.OPT_METRIC  # the store's parameters and states are already in English units (segstore.build)
+        self.opts = opts
         _lib.check(lib.hsp2g_set_forcing_layout(self.h, len(ids), _ptr(ids, C.POINTER(C.c_int32)), _ptr(fill), opts))
         self.nf = len(ids)
         # SAVE set
@@ -206,7 +209,7 @@ class LandBatch:
         forcing element types, layout and shared-met mode can change after construction)."""
         if not self.jit:
             return
-        key = (self.out_dtype.itemsize, self.forcing_dtype.itemsize, self.layout, self.shared, self.jit_word)
+        key = (self.out_dtype.itemsize, self.forcing_dtype.itemsize, self.layout, self.shared, self.met_table, self.jit_word)
         if key != self._kernel_for:
             self._kernel_for = key
             self._jit.specialize(self, word=self.jit_word)
@@ -306,6 +309,8 @@ class LandBatch:
                                                      _ptr(mf), self.n))
         self.shared_steps = steps
         self.shared = True
+        # few stations: the kernel fetches an interval's whole station table with one bulk copy (land_common.cuh met_table_fits)
+        self.met_table = 0 < nst <= 32 and (self.nf * nst) % 2 == 0 and "HSP2G_NO_MET_TABLE" not in os.environ
 
     def run_shared(self, t0=0, steps=None, chunk=None):
         """Advance over [t0, t0+steps) in shared-met mode -> out [steps][ns][n] (caller's row and segment order)."""

@@ -73,7 +73,7 @@ def _sources_hash():
 
 
 def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="float64", out_dtype="float64", shared=False,
-             word=True):
+             word=True, opts=None, met_table=False):
     """The compile-time description of a batch that does not exist yet (no GPU needed): store = SegmentStore, forcing_names /
     save = the names LandBatch would be given (save may be 'all')."""
     import numpy as np
@@ -96,18 +96,23 @@ def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="fl
     f_or = int(np.bitwise_or.reduce(store.flags)) if len(store.flags) else 0
     mask = ~(f_and ^ f_or) & 0xFFFFFFFFFFFFFFFF
     f32in = np.dtype(forcing_dtype).itemsize == 4 and not shared
+    if opts is None:  # the batch-wide option bits LandBatch would set (HSP2G_OPT_*)
+        from .engine import forcing_fill
+
+        opts = forcing_fill(store.operation, act, tuple(forcing_names))[1] | (_lib.OPT_METRIC if getattr(store, "units", 1) == 2 else 0)
     return {
         "op": 0 if store.operation == "PERLND" else 1, "qual": qual, "act": act, "hourly": bool(delt >= 60),
         "fmask": fmask, "s0": s[0], "s1": s[1], "s2": s[2], "f32out": bool(np.dtype(out_dtype).itemsize == 4),
         "plain": bool(layout == "plain"), "f32in": bool(f32in), "shared": bool(shared),
         "word": (f_and & mask) if (word and not qual and mask) else None, "mask": mask if (word and not qual and mask) else 0,
+        "opts": None if qual else int(opts), "mettbl": bool(shared and met_table),
     }
 
 
 def spec_of(batch, word=True):
     """Everything of `batch` (engine.LandBatch / QualBatch) that the kernel can fix at compile time."""
     return spec_for(batch.store, batch.cal.delt, batch.forcing_rows, batch.save_rows, batch.layout, batch.forcing_dtype,
-                    batch.out_dtype, batch.shared, word)
+                    batch.out_dtype, batch.shared, word, getattr(batch, "opts", None), getattr(batch, "met_table", False))
 
 
 def _popc(x):
@@ -135,7 +140,7 @@ def display_name(spec, maxreg):
                                          spec["s2"], ",f32" if spec["f32out"] else ""),
              "plain" if spec["plain"] else "tiled"]
     if spec["shared"]:
-        parts.append("met=shared")
+        parts.append("met=shared/table" if spec.get("mettbl") else "met=shared")
     if spec["word"] is None:
         parts.append("options=per-segment")
     elif spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF:
@@ -143,6 +148,8 @@ def display_name(spec, maxreg):
     else:
         parts.append("options=%#x/fixed:%#x(%d bits per segment)" % (spec["word"], spec["mask"],
                                                                       _popc(~spec["mask"] & ((1 << len(_lib.names("flags"))) - 1))))
+    if spec.get("opts"):
+        parts.append("batch-opts=%#x" % spec["opts"])
     parts.append("regs<=%d" % maxreg)
     return "%s<%s,jit>" % (kern, ",".join(parts))
 
@@ -159,9 +166,11 @@ def source(spec, maxreg):
         lines.append("#define HSP_INLINE_DIV")
     lines += ['#include "jit_info.h"', '#include "land_kernels.cuh"', '#include "qual.cuh"',
               "typedef StaticIO<%s, %s, %s, %s, %s> IO;" % (u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), b(spec["f32out"]), u(spec["s2"])),
-              "typedef %s FW;" % ("StaticFlags<%s, %s>" % (u(spec["word"]), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF)))
-                                  if spec["word"] is not None else "DynFlags"),
-              "typedef StaticLay<%s, %s> LAY;" % (b(spec["plain"]), b(spec["f32in"])),
+              "typedef %s FW;" % ("StaticFlags<%s, %s, %d>" % (u(spec["word"] or 0), u(spec.get("mask", 0) if spec["word"] is not None else 0),
+                                                                 spec["opts"])
+                                  if not spec["qual"] else "DynFlags"),
+              "typedef StaticLay<%s, %s, %d> LAY;" % (b(spec["plain"]), b(spec["f32in"]),
+                                                      int(bool(spec.get("mettbl"))) if spec["shared"] else -1),
               "constexpr int ACT = %d;" % act, "constexpr bool HOURLY = %s, SHARED = %s;" % (b(spec["hourly"]), b(spec["shared"])),
               "constexpr int FESZ = %d;" % (4 if spec["f32in"] else 8)]
     if spec["qual"]:
@@ -175,10 +184,11 @@ def source(spec, maxreg):
         smem = "land_smem_bytes(IO::NF, IMPLND_HOT, implnd_ncold<HOURLY, IO>(), SHARED, FESZ)"
     bits = " | ".join(n for n, on in (("JB_F32OUT", spec["f32out"]), ("JB_PLAIN", spec["plain"]), ("JB_F32IN", spec["f32in"]),
                                       ("JB_SHARED", spec["shared"]), ("JB_WORD", spec["word"] is not None), ("JB_IOSTATIC", True),
-                                      ("JB_LAYSTATIC", True), ("JB_QUAL", spec["qual"])) if on)
-    info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, %s, 0}"
+                                      ("JB_LAYSTATIC", True), ("JB_QUAL", spec["qual"]),
+                                      ("JB_OPTS", spec.get("opts") is not None), ("JB_METTBL", spec.get("mettbl"))) if on)
+    info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, %s, %d}"
             % (smem, spec["op"], u(act), int(spec["hourly"]), u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), u(spec["s2"]), bits,
-               u(spec["word"] or 0), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF) if spec["word"] is not None else 0)))
+               u(spec["word"] or 0), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF) if spec["word"] is not None else 0), spec.get("opts") or 0))
     lines += ["#ifdef HSP2G_HOST_EMU  /* the CPU test suite's double: a host function with the same body */",
               'extern "C" void %s(const LandLaunch &L) { %s }' % (ENTRY, body),
               'extern "C" const unsigned long long %s_info[JI_N] = %s;' % (ENTRY, info),
@@ -247,7 +257,7 @@ def ensure(spec, kind=None, maxreg=None):
             log, secs = _compile(text, out, kind, mr)
             regs, spill = _ptxas(log) if kind == _lib.CUDA_BUILD else (None, 0)
             meta = {"spec": spec, "name": display_name(spec, mr), "maxreg": mr, "registers": regs, "spill_bytes": spill,
-                    "compile_s": round(secs, 2), "kind": kind}
+                    "compile_s": round(secs, 2), "kind": kind, "sources": _sources_hash()}
             mtmp = meta_p + ".tmp%d_%d" % (os.getpid(), threading.get_ident())
             with open(mtmp, "w") as f:
                 json.dump(meta, f)
@@ -302,4 +312,28 @@ def prebuild(specs, kind=None):
 
     kind = kind or _lib.CUDA_BUILD
     with ThreadPoolExecutor(min(8, max(1, len(specs)))) as ex:
-        return [r[2] for r in ex.map(lambda sp: ensure(sp, kind), specs)]
+        names = [r[2] for r in ex.map(lambda sp: ensure(sp, kind), specs)]
+    prune()
+    return names
+
+
+def prune():
+    """Drop cached images built from other versions of the kernel headers (their keys can never be asked for again)."""
+    import glob
+    import json
+
+    n = 0
+    for meta_p in glob.glob(os.path.join(CACHE, "*.json")):
+        try:
+            with open(meta_p) as f:
+                stale = json.load(f).get("sources") != _sources_hash()
+        except (OSError, ValueError):
+            stale = True
+        if stale:
+            for ext in (".json", ".cubin", ".so"):
+                try:
+                    os.remove(meta_p[:-5] + ext)
+                    n += ext != ".json"
+                except OSError:
+                    pass
+    return n

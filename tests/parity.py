@@ -45,7 +45,7 @@ def run_oracle(case, time_unit="us"):
 
 
 def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps=None, save="all", max_steps=None,
-              out_dtype=None):
+              out_dtype=None, jit=None):
     """All active sections fused in one kernel; `replicate` copies of the segment (tests padding / multi-block).  A PQUAL /
     IQUAL section runs as a batch of (segment, constituent) rows fed by the land batch's outputs (engine.QualBatch)."""
     si = CASES.siminfo_for(case)
@@ -63,7 +63,7 @@ def run_fused(case, time_unit="us", chunk=None, replicate=1, device=0, sub_steps
         names = [n for n in forc if n in F and n not in ("SLIQSP", "ILIQC", "ALIQC")]
         tables = [copy.deepcopy(case["tables"]) for _ in range(replicate)]
         store = SegmentStore.from_tables(op, tables, cal, units=si.get("units", 1))
-        with LandBatch(store, cal, names, save, device=device) as b:
+        with LandBatch(store, cal, names, save, device=device, jit=jit) as b:
             if sub_steps is not None:
                 b.set_schedule(sub_steps)
             if out_dtype is not None:
@@ -176,12 +176,28 @@ def f32_ulp_diff(got32, ref64):
     return int(np.abs(a - b).max()) if a.size else 0
 
 
-def check_shared_met_mode(n=75, jit=None):
+def check_metric_batch_kernels(names=("p_metric_pack", "i001_metric"), replicate=3):
+    """siminfo['units'] == 2 folded into the kernel built for the batch (StaticFlags<.., OPTS>: the conversions of the stored
+    series are compiled in, the English-unit batches carry none of them) gives the bits of the general kernel, which reads the
+    option from the launch record."""
+    for name in names:
+        case = CASES.build_cases()[name]
+        a, ea, ka = run_fused(case, replicate=replicate, chunk=200, jit=False)
+        b, eb, kb = run_fused(case, replicate=replicate, chunk=200, jit=True)
+        assert ",jit>" in kb and "batch-opts=0x2" in kb and ",jit>" not in ka, (ka, kb)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), (name, k)
+        for k in ea:
+            assert np.array_equal(ea[k], eb[k]), (name, k)
+
+
+def check_shared_met_mode(n=75, jit=None, nst=5):
     """hsp2g_set_shared_forcing: a few met stations + per-segment station index and MFACTOR give bit-identical results to
     handing every segment its own series * MFACTOR arrays (what get_timeseries builds, utilities.py:274-290); generic and
     compile-time-specialised kernels, with and without divergence ordering."""
     cal = Calendar("1976-02-01", "1976-03-10", 60, "us")
-    steps, nst = cal.steps, 5
+    steps = cal.steps  # nst <= 32: one bulk copy of the station table per warp-interval; more: per-lane gathers
     rng = np.random.default_rng(3)
     ens = synth.Ensemble("PERLND", n, seed=21, sections=("SNOW", "PWATER"))
     names = list(synth.PERLND_FORCINGS)
@@ -191,11 +207,11 @@ def check_shared_met_mode(n=75, jit=None):
         for r, nm in enumerate(names):
             a = s0[nm].copy()
             if nm == "AIRTMP":
-                a = a + (k - 2) * 1.5
+                a = a + (k % 5 - 2) * 1.5
             elif nm == "DTMPG":
-                a = (s0["AIRTMP"] + (k - 2) * 1.5) - 5.0
+                a = (s0["AIRTMP"] + (k % 5 - 2) * 1.5) - 5.0
             elif nm == "PREC":
-                a = a * (1.0 + 0.05 * k)
+                a = a * (1.0 + 0.05 * (k % 7))
             series[:, r, k] = a
     station = rng.integers(0, nst, n).astype(np.int32)
     mfac = np.ones((len(names), n))
@@ -213,6 +229,7 @@ def check_shared_met_mode(n=75, jit=None):
                 b.set_shared_forcing(series, station, mfac)
                 got = b.run_shared(chunk=300)
                 assert "met=shared" in b.kernel_name()
+                assert not jit or ("met=shared/table" in b.kernel_name()) == (nst <= 32), b.kernel_name()
                 assert jit is None or (",jit>" in b.kernel_name()) == bool(jit), b.kernel_name()
                 assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
             assert np.array_equal(got, ref, equal_nan=True)

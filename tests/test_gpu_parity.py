@@ -269,6 +269,17 @@ def test_shared_met_mode_on_gpu():
     parity.check_shared_met_mode(n=2000)
 
 
+def test_shared_met_batch_kernels_table_and_gather_on_gpu():
+    """The kernels built for the batch in both shared-met modes: <= 32 stations (one bulk copy of the interval's station table per
+    warp) and more (per-lane cp.async gathers) == per-segment forcing arrays, bit for bit."""
+    parity.check_shared_met_mode(n=2500, jit=True)
+    parity.check_shared_met_mode(n=2500, jit=True, nst=37)
+
+
+def test_metric_units_compiled_into_batch_kernels_on_gpu():
+    parity.check_metric_batch_kernels(replicate=70)
+
+
 def test_hspf_known_answers(golden_dir):
     """The reference's own KATs through the GPU: Flow_Test.plt (test_ipwater.py tolerance) and test10I.hbn."""
     hspf = np.load(os.path.join(golden_dir, "hspf_flowtest.npz"))

@@ -32,9 +32,10 @@ def test_generated_source_names_what_it_fixes():
         spec = jit.spec_of(b)
     assert spec["word"] == int(ens.store(CAL).flags[0]) and spec["plain"] and not spec["f32in"] and spec["act"] == 6
     text = jit.source(spec, 128)
-    assert "StaticFlags<%#xull, 0xffffffffffffffffull>" % spec["word"] in text and "StaticLay<true, false>" in text
+    assert "StaticFlags<%#xull, 0xffffffffffffffffull, 0>" % spec["word"] in text and "StaticLay<true, false, -1>" in text
     assert "perlnd_body<ACT, HOURLY, IO, SHARED, FW, LAY>" in text and "__launch_bounds__(LAND_BLOCK, 8)" in text
-    assert "DynFlags" in jit.source(dict(spec, word=None), 168) and "__launch_bounds__(LAND_BLOCK, 6)" in jit.source(spec, 168)
+    # without a common option word the bits are read per segment (mask 0); the batch-wide HSP2G_OPT_* bits stay fixed
+    assert "StaticFlags<0x0ull, 0x0ull, 2>" in jit.source(dict(spec, word=None, opts=2), 168) and "__launch_bounds__(LAND_BLOCK, 6)" in jit.source(spec, 168)
 
 
 def test_dtype_and_layout_changes_rebuild_and_stale_images_are_refused():
@@ -76,6 +77,14 @@ def test_float32_forcings_are_widened_exactly(layout):
             got = b.run(f32, chunk=77)
             assert (",jit>" in b.kernel_name()) == use_jit
         assert np.array_equal(got, ref, equal_nan=True), (layout, use_jit)
+
+
+def test_metric_units_are_compiled_into_the_batch_kernel():
+    parity.check_metric_batch_kernels()
+
+
+def test_shared_met_gathers_with_many_stations():
+    parity.check_shared_met_mode(n=75, jit=True, nst=37)
 
 
 def test_shared_met_implnd_and_constituent_kernels():
