@@ -34,6 +34,13 @@ _i64p = C.POINTER(C.c_int64)
 _u64p = C.POINTER(C.c_uint64)
 _h = C.c_void_p
 
+
+
+class RowSource(C.Structure):
+    """hsp2g_row_source (include/hsp2g.h): where one linked forcing row lives, strides in bytes"""
+    _fields_ = [("base", C.c_void_p), ("interval_stride", C.c_int64), ("tile_stride", C.c_int64)]
+
+
 _PROTOS = {
     "hsp2g_abi_version": (C.c_int, []),
     "hsp2g_last_error": (C.c_char_p, []),
@@ -55,6 +62,8 @@ _PROTOS = {
     "hsp2g_run_host": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "hsp2g_run_device_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "hsp2g_run_host_ld": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "hsp2g_run_device_linked": (C.c_int, [_h, C.c_int64, C.c_int32, C.c_int32, C.POINTER(RowSource), C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_void_p]),
     "hsp2g_run_device_group": (C.c_int, [C.c_int32, C.POINTER(_h), C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          _i64p, C.c_void_p]),
     "hsp2g_set_series_layout": (C.c_int, [_h, C.c_int]),

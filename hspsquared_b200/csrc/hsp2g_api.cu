@@ -349,6 +349,7 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
         if (((bits & JB_PLAIN) != 0) != (L.plain != 0)) return false;
         if (!(bits & JB_SHARED) && ((bits & JB_F32IN) != 0) != (L.forc_f32 != 0)) return false;
         if ((bits & JB_SHARED) && ((bits & JB_METTBL) != 0) != (L.met_table != 0)) return false;
+        if (((bits & JB_LINKED) != 0) != (L.linked != 0)) return false;
     }
     if (bits & JB_IOSTATIC) {
         if (((bits & JB_F32OUT) != 0) != (L.out_f32 != 0)) return false;
@@ -392,9 +393,18 @@ int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid) {
 
 // One launch over intervals [t0, t0+nsteps).  Series layout: b->plain ? PLAIN with rows forc_ld / out_ld elements apart : TILED.
 int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long long forc_ld, void *d_out, long long out_ld,
-           cudaStream_t st) {
+           cudaStream_t st, const hsp2g_row_source *rows = nullptr, long long src_tiles = 0) {
     LandLaunch L;
     memset(&L, 0, sizeof L);
+    if (rows) {  // hsp2g_run_device_linked: every forcing row is read in place from another batch's device buffer
+        L.linked = 1;
+        L.src_tiles = (int)src_tiles;
+        for (int r = 0; r < b->nf; ++r) {
+            L.rowsrc[r].base = (const unsigned char *)rows[r].base;
+            L.rowsrc[r].t_stride = rows[r].interval_stride;
+            L.rowsrc[r].tile_stride = rows[r].tile_stride;
+        }
+    }
     L.segblk = b->segblk;
     L.mon = b->mon;
     L.forc = (const double *)d_forc;
@@ -407,8 +417,9 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
         L.station = b->station;
         L.mfac = b->mfac;
         L.n_stations = b->n_stations;
-        static const bool no_table = getenv("HSP2G_NO_MET_TABLE") != nullptr;  // measurement switch: per-lane gathers always
-        L.met_table = !no_table && met_table_fits(b->n_stations, b->nf);
+        // opt-in (HSP2G_MET_TABLE=1): measured 4.5 % SLOWER than the per-lane gathers on B200 (profiles/README.md, round 2)
+        const char *tbl = getenv("HSP2G_MET_TABLE");
+        L.met_table = tbl && tbl[0] == '1' && met_table_fits(b->n_stations, b->nf);
     }
     L.cal = b->cal + t0;
     L.ntiles = (int)b->ntiles;
@@ -435,7 +446,7 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
     memcpy(L.srow, b->srow, sizeof L.srow);
     memcpy(L.mslot, b->mslot, sizeof L.mslot);
 #ifndef HSP2G_HOST_EMU
-    if (b->plain && !b->met && b->nf > 0 && !getenv("HSP2G_NO_TMAP"))
+    if (b->plain && !b->met && !rows && b->nf > 0 && !getenv("HSP2G_NO_TMAP"))
         L.tmap_ok = make_tmap(L.tmap, d_forc, L.forc_f32 ? 4 : 8, forc_ld, b->nf, nsteps) ? 1 : 0;
 #endif
     const bool hourly = b->delt >= 60.0;
@@ -985,6 +996,25 @@ int hsp2g_run_device_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *
     }
     DeviceGuard g(b->device);
     return launch(b, t0, nsteps, d_forc, ldf, d_out, ldo, stream ? (cudaStream_t)stream : b->comp);
+}
+
+int hsp2g_run_device_linked(hsp2g_batch *b, int64_t t0, int32_t nsteps, int32_t n_rows, const hsp2g_row_source *rows,
+                            int64_t src_tiles, void *d_out, int64_t ldo, void *stream) {
+    if (check_ready(b, t0, nsteps)) return 1;
+    if (b->met) return fail("a batch in shared-met mode has no per-segment forcing rows to link");
+    if (b->forc_f32) return fail("linked forcing rows are float64 (the series another batch saved or was given)");
+    if (n_rows != b->nf || n_rows > LAND_MAX_LINKED || (n_rows > 0 && !rows))
+        return fail("%d row sources for a batch with %d forcing rows (at most %d can be linked)", n_rows, b->nf, LAND_MAX_LINKED);
+    if (src_tiles <= 0 || src_tiles > b->ntiles) return fail("src_tiles must be in [1, %lld]", (long long)b->ntiles);
+    for (int r = 0; r < n_rows; ++r)
+        if (!rows[r].base || (((uintptr_t)rows[r].base | (uintptr_t)rows[r].interval_stride | (uintptr_t)rows[r].tile_stride) & 15))
+            return fail("row source %d: base and strides must be non-null / multiples of 16 bytes (TMA bulk copies)", r);
+    if (b->ns > 0 && !d_out) return fail("null output pointer");
+    if ((uintptr_t)d_out & 15) return fail("device series must be 16-byte aligned (TMA bulk copies)");
+    if (b->plain && b->ns > 0 && (ldo < b->n_pad || (ldo & 3)))
+        return fail("PLAIN device series need rows of at least %lld elements, a multiple of 4", (long long)b->n_pad);
+    DeviceGuard g(b->device);
+    return launch(b, t0, nsteps, nullptr, b->n_pad, d_out, ldo, stream ? (cudaStream_t)stream : b->comp, rows, src_tiles);
 }
 
 int hsp2g_run_device(hsp2g_batch *b, int64_t t0, int32_t nsteps, const double *d_forc, double *d_out, void *stream) {

@@ -61,7 +61,7 @@ typedef StaticIO<FM_MET6_GATMP, SAVE_CBP10(olo), SAVE_CBP10(ohi)> IO_FullChainCb
 // does the launch record describe exactly this static configuration (rows in ascending id order)?
 template <class IO>
 static inline bool io_matches(const LandLaunch &L) {
-    if (L.plain || L.forc_f32) return false;  // the library's static kernels are built for the TILED float64 layout
+    if (L.plain || L.forc_f32 || L.linked) return false;  // the library's static kernels are built for the TILED float64 layout
     if (L.nf != IO::NF || L.ns != IO::NS || (L.out_f32 != 0) != IO::F32) return false;
     int r = 0;
     for (int id = 0; id < HSP2G_NFORC; ++id) {

@@ -79,6 +79,14 @@ struct __align__(32) CalStep {
     uint8_t pad[5];
 };
 
+// Linked forcing rows (hsp2g_run_device_linked): row r of interval t of this batch's tile q is the 256 bytes at
+// base + t * t_stride + (q % src_tiles) * tile_stride -- a row of ANOTHER batch's device buffer, read in place.
+#define LAND_MAX_LINKED 16
+struct RowSource {
+    const unsigned char *base;
+    long long t_stride, tile_stride;  // bytes
+};
+
 struct LandLaunch {
     double *segblk;
     const double *mon;
@@ -118,6 +126,9 @@ struct LandLaunch {
     double ffill[HSP2G_NFORC];  // value read when the id is absent
     short srow[HSP2G_NOUT];     // output id -> row in out, or -1 (not saved)
     short mslot[HSP2G_NMON];    // monthly table id -> slot in mon, or -1
+    int linked;       // 1: the forcing rows come from rowsrc (forc, forc_ld, tmap are unused)
+    int src_tiles;    // linked: tiles of the source batch; this batch's tile q reads source tile q % src_tiles
+    RowSource rowsrc[LAND_MAX_LINKED];
     // PLAIN: CUtensorMap of forc as a 3-D tensor (segment, row, interval), box = 32 x nf x 1 (hsp2g_api.cu make_tmap)
     alignas(64) unsigned long long tmap[16];
 };
@@ -260,12 +271,13 @@ __host__ __device__ inline bool met_table_fits(int n_stations, int nf) {
 // of the forcings.  StaticLay fixes both at compile time (kernels built for one batch, hspsquared_b200/jit.py);
 // DynLay reads them from the launch record (the general kernels of the library).
 struct DynLay {
-    static constexpr bool STATIC = false, PLAIN = false, F32IN = false;
+    static constexpr bool STATIC = false, PLAIN = false, F32IN = false, LINKED = false;
     static constexpr int METTBL = -1;
 };
-template <bool PLAIN_, bool F32IN_, int METTBL_ = -1>  // METTBL: shared-met table mode 0 / 1, -1 = read L.met_table
+// METTBL: shared-met table mode 0 / 1, -1 = read L.met_table; LINKED: forcing rows read in place from another batch's buffers
+template <bool PLAIN_, bool F32IN_, int METTBL_ = -1, bool LINKED_ = false>
 struct StaticLay {
-    static constexpr bool STATIC = true, PLAIN = PLAIN_, F32IN = F32IN_;
+    static constexpr bool STATIC = true, PLAIN = PLAIN_, F32IN = F32IN_, LINKED = LINKED_;
     static constexpr int METTBL = METTBL_;
 };
 typedef StaticLay<false, false> TiledLay;
@@ -276,6 +288,10 @@ __device__ __forceinline__ bool lay_plain(const LandLaunch &L) {
 template <class LAY>
 __device__ __forceinline__ bool lay_f32in(const LandLaunch &L) {
     return LAY::STATIC ? LAY::F32IN : (L.forc_f32 != 0);
+}
+template <class LAY>
+__device__ __forceinline__ bool lay_linked(const LandLaunch &L) {
+    return LAY::STATIC ? LAY::LINKED : (L.linked != 0);
 }
 template <class LAY>
 __device__ __forceinline__ bool lay_mettbl(const LandLaunch &L) {
@@ -344,6 +360,7 @@ struct PipeT {
     int nf, nst;          // rows per interval; SHARED: stations
     int esz;              // forcing element size in bytes (8, or 4 for float32 forcings)
     int tile;             // PLAIN: current tile
+    int src_tile;         // linked rows: the source batch's tile this tile reads
     int tbl;              // SHARED: 1 = one bulk copy of the interval's station table (L.met_table), 0 = per-lane gathers
     int my_station;       // SHARED table mode: this lane's station
     __device__ __forceinline__ bool table() const { return SHARED && (LAY::METTBL >= 0 ? LAY::METTBL != 0 : tbl != 0); }
@@ -409,7 +426,14 @@ struct PipeT {
             const unsigned bytes = (unsigned)stage_bytes;
             const unsigned bar = bar_s + s * 8, dst = ring_s + (unsigned)s * bytes;
             mbar_expect_tx(bar, bytes);
-            if (!lay_plain<LAY>(*Lp))
+            if (lay_linked<LAY>(*Lp)) {  // row by row, each from its own source buffer (src_tile: the source's tile)
+                const unsigned rowb = (unsigned)(LAND_TILE * 8);
+#pragma unroll 1
+                for (int r = 0; r < nf; ++r) {
+                    const RowSource &rs = Lp->rowsrc[r];
+                    bulk_g2s(dst + r * rowb, rs.base + (long long)t * rs.t_stride + (long long)src_tile * rs.tile_stride, rowb, bar);
+                }
+            } else if (!lay_plain<LAY>(*Lp))
                 bulk_g2s(dst, src + (size_t)t * bytes, bytes, bar);
             else if (Lp->tmap_ok)
                 tensor_g2s(dst, Lp->tmap, tile * LAND_TILE, t, bar);
@@ -426,6 +450,7 @@ struct PipeT {
     __device__ __forceinline__ void begin_task(int tile_, int t0, int t1) {
         const LandLaunch &L = *Lp;
         tile = tile_;
+        if (!SHARED && lay_linked<LAY>(L)) src_tile = tile % L.src_tiles;
         if (table()) {
             src = reinterpret_cast<const unsigned char *>(L.met);
             my_station = L.station[tile * LAND_TILE + lane];
@@ -531,7 +556,7 @@ struct PipeT {
     unsigned char *ring;
     const LandLaunch *Lp;
     const unsigned char *src;
-    int stage_bytes, lane, t_cur, nf, nst, esz, tile, tbl, my_station;
+    int stage_bytes, lane, t_cur, nf, nst, esz, tile, src_tile, tbl, my_station;
     bool table() const { return SHARED && (LAY::METTBL >= 0 ? LAY::METTBL != 0 : tbl != 0); }
     void init(const LandLaunch &L, double *smem, int, int lane_, int nf_, int, int) {
         Lp = &L;
@@ -547,6 +572,7 @@ struct PipeT {
     void begin_task(int tile_, int t0, int) {
         const LandLaunch &L = *Lp;
         tile = tile_;
+        if (!SHARED && lay_linked<LAY>(L)) src_tile = tile % L.src_tiles;
         if (table()) {
             src = reinterpret_cast<const unsigned char *>(L.met);
             my_station = L.station[tile * LAND_TILE + lane];
@@ -566,6 +592,12 @@ struct PipeT {
         if (SHARED) {
             const double *g = reinterpret_cast<const double *>(src);
             for (int r = 0; r < nf; ++r) reinterpret_cast<double *>(ring)[r * LAND_TILE + lane] = g[((size_t)t_cur * nf + r) * nst];
+        } else if (lay_linked<LAY>(*Lp)) {
+            for (int r = 0; r < nf; ++r) {
+                const RowSource &rs = Lp->rowsrc[r];
+                memcpy(ring + (size_t)r * LAND_TILE * 8, rs.base + (long long)t_cur * rs.t_stride + (long long)src_tile * rs.tile_stride,
+                       (size_t)LAND_TILE * 8);
+            }
         } else if (lay_plain<LAY>(*Lp)) {
             const size_t ldb = (size_t)Lp->forc_ld * esz;
             for (int r = 0; r < nf; ++r)

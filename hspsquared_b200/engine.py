@@ -90,6 +90,7 @@ class LandBatch:
         self.forcing_dtype = np.dtype(np.float64)
         self.shared = False
         self.met_table = False
+        self.linked = False  # the last launch read its forcing rows in place from another batch's buffers (run_device_linked)
         if layout not in ("plain", "tiled"):
             raise ValueError("layout must be 'plain' or 'tiled'")
         self.layout = layout
@@ -204,12 +205,14 @@ class LandBatch:
     def ntiles(self):
         return self.npad // _lib.TILE
 
-    def _kernel(self):
+    def _kernel(self, linked=False):
         """Before every launch: make sure the kernel built for this batch matches its current configuration (output and
-        forcing element types, layout and shared-met mode can change after construction)."""
+        forcing element types, layout, shared-met mode and linked forcing rows can change after construction)."""
+        self.linked = bool(linked)
         if not self.jit:
             return
-        key = (self.out_dtype.itemsize, self.forcing_dtype.itemsize, self.layout, self.shared, self.met_table, self.jit_word)
+        key = (self.out_dtype.itemsize, self.forcing_dtype.itemsize, self.layout, self.shared, self.met_table, self.jit_word,
+               self.linked)
         if key != self._kernel_for:
             self._kernel_for = key
             self._jit.specialize(self, word=self.jit_word)
@@ -289,6 +292,15 @@ class LandBatch:
         _lib.check(self.lib.hsp2g_run_device_ld(self.h, int(t0), int(nsteps), d_forcing or None, int(ldf or self.npad), d_out,
                                                 int(ldo or self.npad), stream or None))
 
+    def run_device_linked(self, t0, nsteps, sources, src_tiles, d_out, stream=0, ldo=None):
+        """Device-resident pass whose forcing rows are read in place from other device buffers (include/hsp2g.h
+        hsp2g_run_device_linked).  sources: one (base pointer, interval stride, tile stride) in bytes per forcing row, in
+        `self.forcing_rows` order; tile q of this batch reads tile q % src_tiles of the sources."""
+        self._kernel(linked=True)
+        arr = (_lib.RowSource * max(1, len(sources)))(*[_lib.RowSource(int(b), int(ts), int(tl)) for b, ts, tl in sources])
+        _lib.check(self.lib.hsp2g_run_device_linked(self.h, int(t0), int(nsteps), len(sources), arr, int(src_tiles), d_out,
+                                                    int(ldo or self.npad), stream or None))
+
     def set_shared_forcing(self, series, station, mfactor=None):
         """Shared-met mode (include/hsp2g.h hsp2g_set_shared_forcing): `series` [steps][rows][stations] float64 with rows
         in the order of the `forcing_names` given to the constructor, `station` int[n] (which station each segment draws
@@ -309,8 +321,9 @@ class LandBatch:
                                                      _ptr(mf), self.n))
         self.shared_steps = steps
         self.shared = True
-        # few stations: the kernel fetches an interval's whole station table with one bulk copy (land_common.cuh met_table_fits)
-        self.met_table = 0 < nst <= 32 and (self.nf * nst) % 2 == 0 and "HSP2G_NO_MET_TABLE" not in os.environ
+        # HSP2G_MET_TABLE=1 and few stations: the kernel fetches an interval's whole station table with one bulk copy instead of
+        # per-lane gathers (land_common.cuh met_table_fits; slower on B200, kept as a measured alternative)
+        self.met_table = 0 < nst <= 32 and (self.nf * nst) % 2 == 0 and os.environ.get("HSP2G_MET_TABLE", "0")[:1] == "1"
 
     def run_shared(self, t0=0, steps=None, chunk=None):
         """Advance over [t0, t0+steps) in shared-met mode -> out [steps][ns][n] (caller's row and segment order)."""
@@ -645,15 +658,44 @@ class QualBatch(LandBatch):
     (segment index, constituent number); in the reference's ts that series is '<P|I>QUAL<k>_<NAME>'."""
 
     def __init__(self, operation, uci_list, calendar, forcing_names, save="all", device=0, timing=False, order="flags",
-                 land=None, layout="plain", jit=None):
-        """order="flags" (default) puts rows with equal option words next to each other on the device: the constituents of a
+                 land=None, layout="plain", jit=None, chain=None):
+        """chain (with land=...): "linked" -- the rows read the land batch's device buffers IN PLACE (run_device_linked_from; no
+        scratch buffer, no gather launch).  The device rows are constituent-major over the land batch's tiles: device row
+        k*land.npad + p is constituent slot k of the land batch's device segment p (`self.rows[j]` = (caller's segment, constituent
+        number), segment -1 for the lanes that pad the land batch's last tile), so a tile of 32 rows reads exactly one tile of
+        every land series.  Needs the same number of constituents in every segment and no deposition input series.  "gather" --
+        the rows keep an order of their own and a device gather fills a scratch buffer (run_device_from).  None = "linked" where
+        possible.
+        order="flags" (default) puts rows with equal option words next to each other on the device: the constituents of a
         segment differ in kind (sediment-associated, overland-flow-associated, subsurface concentrations ...), segment-major rows
         would make every warp execute every kind.  Invisible to run() / gather(); run_device buffers are in device order.
         land: the LandBatch whose device buffers will feed this batch (attach() is called): within equal option words the rows
         then follow the land batch's device order, so that 32 consecutive rows gather 32 consecutive cells of a land tile."""
-        from .qualstore import qual_store
+        from .qualstore import nquals, qual_store
 
-        store = qual_store(operation, uci_list, calendar)
+        self.chain = None
+        if land is not None and chain != "gather":
+            counts = {nquals(u) for u in uci_list}
+            if len(counts) == 1 and len(uci_list) == land.n:
+                # the land batch's device order, its last tile padded with copies of its last segment (as its own lanes are)
+                pos = np.arange(land.npad)
+                pos[land.n:] = land.n - 1
+                seg = pos if land.order is None else np.asarray(land.order)[pos]
+                nq = counts.pop()
+                ext = qual_store(operation, [uci_list[i] for i in seg], calendar)
+                if not any(ext.dep_series) and nq > 0:
+                    self.chain = "linked"
+                    store = ext
+                    store.rows = [(int(seg[p]) if p < land.n else -1, k) for p, k in store.rows]
+                    # qual_store's rows are segment-major (p, k): device row k*npad + p holds its row p*nq + k
+                    order = (np.arange(land.npad)[None, :] * nq + np.arange(nq)[:, None]).reshape(-1)
+            if self.chain is None and chain == "linked":
+                raise NotImplementedError("chain='linked' needs one constituent count for all segments, one table set per land "
+                                          "segment and no deposition input series")
+        if self.chain is None:
+            store = qual_store(operation, uci_list, calendar)
+            if land is not None:
+                self.chain = "gather"
         self.dep_keys = None
         if any(store.dep_series):
             # Some constituent takes its atmospheric deposition from an input series (PQADFG / IQADFG = -1, PQUAL.py:94-103,
@@ -680,11 +722,11 @@ class QualBatch(LandBatch):
                 self.dep_keys.append(keys)
         self.rows = store.rows
         self.row_segment = np.array([i for i, _k in store.rows], dtype=np.int64)
-        if land is not None and isinstance(order, str) and order == "flags":
+        if self.chain == "gather" and isinstance(order, str) and order == "flags":
             pos = self.row_segment if land._inv is None else np.asarray(land._inv)[self.row_segment]
             order = store.divergence_order(keys=(pos,))
         super().__init__(store, calendar, forcing_names, save, device=device, timing=timing, order=order,
-                         layout="tiled" if land is not None else layout, jit=jit)
+                         layout="tiled" if self.chain == "gather" else layout, jit=jit)
         if land is not None:
             self.attach(land)
 
@@ -719,8 +761,20 @@ class QualBatch(LandBatch):
         land's output rows (it must be in land's SAVE set, float64), anything else from land's forcing rows."""
         if land.out_dtype != np.float64:
             raise ValueError("the land batch must write float64 outputs to feed constituents")
+        if self.chain == "linked":
+            self._link = []  # per forcing row of this batch: ('out' | 'forc', the land batch's row)
+            for nme in self.forcing_rows:
+                full = self.OUTPUT_OF[self.store.operation].get(nme)
+                if full is not None and full in land.save_rows:
+                    self._link.append(("out", land.save_rows.index(full)))
+                elif nme in land.forcing_rows and full is None:
+                    self._link.append(("forc", land.forcing_rows.index(nme)))
+                else:
+                    raise KeyError("%s: neither saved by the land batch (%s) nor one of its forcing rows" % (nme, full))
+            self._land = land
+            return self
         if land.layout != "tiled" or self.layout != "tiled":
-            raise ValueError("the device-resident chain gathers between tile-major buffers: LandBatch(layout='tiled')")
+            raise ValueError("the gathering chain works between tile-major buffers: LandBatch(layout='tiled')")
         rows = self.row_segment if self.order is None else self.row_segment[self.order]  # device row -> caller's segment
         seg = rows if land._inv is None else np.asarray(land._inv)[rows]  # -> the land batch's device position
         seg = np.ascontiguousarray(seg, dtype=np.int64)
@@ -759,6 +813,27 @@ class QualBatch(LandBatch):
                                                  _ptr(b, i32), int(nsteps), stream or None))
         self.run_device(t0, nsteps, d_scratch, d_out, stream)
 
+    def run_device_linked_from(self, t0, nsteps, d_land_forcing, d_land_out, d_out, stream=0, land_ldf=None, land_ldo=None,
+                               ldo=None):
+        """chain="linked": run the constituents of intervals [t0, t0+nsteps) straight from the land batch's device buffers of the
+        same chunk (its forcing buffer, float64, and the output buffer it wrote; the land batch's layout, row lengths land_ldf /
+        land_ldo when plain) into d_out (this batch's layout).  Stream ordering as for run_device_from."""
+        land = self._land
+        if land.forcing_dtype != np.float64 and any(kind == "forc" for kind, _r in self._link):
+            raise ValueError("linked rows are float64: the land batch's forcings must be float64")
+        if not stream:
+            land.sync()
+            stream = self.lib.hsp2g_batch_stream(self.h)
+        src = []
+        for kind, row in self._link:
+            buf, rows, ld = (d_land_out, land.ns, land_ldo) if kind == "out" else (d_land_forcing, land.nf, land_ldf)
+            if land.layout == "tiled":
+                src.append((buf + row * 256, rows * 256, int(nsteps) * rows * 256))
+            else:
+                ld = int(ld or land.npad)
+                src.append((buf + row * ld * 8, rows * ld * 8, 256))
+        self.run_device_linked(t0, nsteps, src, land.ntiles, d_out, stream, ldo)
+
     def close(self):
         g = getattr(self, "_gather", None)
         if g is not None and g.value:
@@ -770,7 +845,8 @@ class QualBatch(LandBatch):
         """int64[2][n_segments]: the reference's error vector of each segment (errors[0] = constituents that take
         atmospheric deposition without being associated with overland flow, PQUAL.py:171-174)."""
         e = np.zeros((2, n_segments), dtype=np.int64)
-        np.add.at(e[0], self.row_segment, self.store.dep_without_qsofg)
+        real = self.row_segment >= 0  # chain="linked": the rows of the land batch's padding lanes belong to no segment
+        np.add.at(e[0], self.row_segment[real], self.store.dep_without_qsofg[real])
         return e
 
 

@@ -73,7 +73,7 @@ def _sources_hash():
 
 
 def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="float64", out_dtype="float64", shared=False,
-             word=True, opts=None, met_table=False):
+             word=True, opts=None, met_table=False, linked=False):
     """The compile-time description of a batch that does not exist yet (no GPU needed): store = SegmentStore, forcing_names /
     save = the names LandBatch would be given (save may be 'all')."""
     import numpy as np
@@ -105,14 +105,15 @@ def spec_for(store, delt, forcing_names, save, layout="plain", forcing_dtype="fl
         "fmask": fmask, "s0": s[0], "s1": s[1], "s2": s[2], "f32out": bool(np.dtype(out_dtype).itemsize == 4),
         "plain": bool(layout == "plain"), "f32in": bool(f32in), "shared": bool(shared),
         "word": (f_and & mask) if (word and not qual and mask) else None, "mask": mask if (word and not qual and mask) else 0,
-        "opts": None if qual else int(opts), "mettbl": bool(shared and met_table),
+        "opts": None if qual else int(opts), "mettbl": bool(shared and met_table), "linked": bool(linked and not shared),
     }
 
 
 def spec_of(batch, word=True):
     """Everything of `batch` (engine.LandBatch / QualBatch) that the kernel can fix at compile time."""
     return spec_for(batch.store, batch.cal.delt, batch.forcing_rows, batch.save_rows, batch.layout, batch.forcing_dtype,
-                    batch.out_dtype, batch.shared, word, getattr(batch, "opts", None), getattr(batch, "met_table", False))
+                    batch.out_dtype, batch.shared, word, getattr(batch, "opts", None), getattr(batch, "met_table", False),
+                    getattr(batch, "linked", False))
 
 
 def _popc(x):
@@ -139,6 +140,8 @@ def display_name(spec, maxreg):
              "save=%d:%#x.%#x.%#x%s" % (_popc(spec["s0"]) + _popc(spec["s1"]) + _popc(spec["s2"]), spec["s0"], spec["s1"],
                                          spec["s2"], ",f32" if spec["f32out"] else ""),
              "plain" if spec["plain"] else "tiled"]
+    if spec.get("linked"):
+        parts.append("in=linked-rows")
     if spec["shared"]:
         parts.append("met=shared/table" if spec.get("mettbl") else "met=shared")
     if spec["word"] is None:
@@ -161,7 +164,10 @@ def source(spec, maxreg):
     act = spec["act"]
     lines = ["// generated by hspsquared_b200/jit.py for one batch configuration -- not a source file of the repository",
              "// %s" % display_name(spec, maxreg)]
-    if spec["word"] is not None and spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF and not (act & CHAIN_ACTS):
+    inline_div = spec["word"] is not None and spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF and not (act & CHAIN_ACTS)
+    if os.environ.get("HSP2G_JIT_INLINE_DIV"):  # measurement switch
+        inline_div = os.environ["HSP2G_JIT_INLINE_DIV"] == "1"
+    if inline_div:
         # small kernels (a known option word removes whole sections): the IEEE division sequence inline at every site
         lines.append("#define HSP_INLINE_DIV")
     lines += ['#include "jit_info.h"', '#include "land_kernels.cuh"', '#include "qual.cuh"',
@@ -169,8 +175,9 @@ def source(spec, maxreg):
               "typedef %s FW;" % ("StaticFlags<%s, %s, %d>" % (u(spec["word"] or 0), u(spec.get("mask", 0) if spec["word"] is not None else 0),
                                                                  spec["opts"])
                                   if not spec["qual"] else "DynFlags"),
-              "typedef StaticLay<%s, %s, %d> LAY;" % (b(spec["plain"]), b(spec["f32in"]),
-                                                      int(bool(spec.get("mettbl"))) if spec["shared"] else -1),
+              "typedef StaticLay<%s, %s, %d, %s> LAY;" % (b(spec["plain"]), b(spec["f32in"]),
+                                                          int(bool(spec.get("mettbl"))) if spec["shared"] else -1,
+                                                          b(spec.get("linked"))),
               "constexpr int ACT = %d;" % act, "constexpr bool HOURLY = %s, SHARED = %s;" % (b(spec["hourly"]), b(spec["shared"])),
               "constexpr int FESZ = %d;" % (4 if spec["f32in"] else 8)]
     if spec["qual"]:
@@ -185,7 +192,8 @@ def source(spec, maxreg):
     bits = " | ".join(n for n, on in (("JB_F32OUT", spec["f32out"]), ("JB_PLAIN", spec["plain"]), ("JB_F32IN", spec["f32in"]),
                                       ("JB_SHARED", spec["shared"]), ("JB_WORD", spec["word"] is not None), ("JB_IOSTATIC", True),
                                       ("JB_LAYSTATIC", True), ("JB_QUAL", spec["qual"]),
-                                      ("JB_OPTS", spec.get("opts") is not None), ("JB_METTBL", spec.get("mettbl"))) if on)
+                                      ("JB_OPTS", spec.get("opts") is not None), ("JB_METTBL", spec.get("mettbl")),
+                                      ("JB_LINKED", spec.get("linked"))) if on)
     info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, %s, %d}"
             % (smem, spec["op"], u(act), int(spec["hourly"]), u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), u(spec["s2"]), bits,
                u(spec["word"] or 0), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF) if spec["word"] is not None else 0), spec.get("opts") or 0))

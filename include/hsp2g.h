@@ -160,6 +160,21 @@ int hsp2g_run_device_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *
                         int64_t ld_out, void *stream);
 int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_forcing, int64_t ld_forcing, void *h_out,
                       int64_t ld_out);
+/* Forcing rows read IN PLACE from other device buffers -- how the PQUAL / IQUAL rows take SURO, IFWO, AGWO, PERO, WSSD, SCRSD and
+ * PREC from the buffers the land batch of the same chunk wrote and read (the reference's constituents read the segment's ts
+ * arrays in place too, PQUAL.py:119-126, IQUAL.py:104-109): no copy, no scratch buffer.  Forcing row r (ascending-id order, as for
+ * hsp2g_run_device) of interval t of this batch's tile q is the 32 float64 at
+ *     rows[r].base + t * interval_stride + (q % src_tiles) * tile_stride          (bytes; all multiples of 16)
+ * -- for a source row `row` of a TILED buffer with R rows: base = buf + row*256, interval_stride = R*256, tile_stride =
+ * nsteps*R*256; of a PLAIN buffer with row length ld: base = buf + row*ld*8, interval_stride = R*ld*8, tile_stride = 256.  A batch
+ * of (segment, constituent) rows laid out constituent-major over the source's tiles (entity k*src_tiles*32 + p = constituent k of
+ * the source's device segment p) reads every source row once per constituent.  n_rows = the batch's forcing rows (<= 16). */
+typedef struct hsp2g_row_source {
+    const void *base;
+    int64_t interval_stride, tile_stride;
+} hsp2g_row_source;
+int hsp2g_run_device_linked(hsp2g_batch *b, int64_t t0, int32_t nsteps, int32_t n_rows, const hsp2g_row_source *rows,
+                            int64_t src_tiles, void *d_out, int64_t ld_out, void *stream);
 /* Several batches over ONE series buffer, launched so that they overlap on the device: batch k owns the columns (segments)
  * [first_column[k], first_column[k] + npad_k) of forcing / out (first_column a multiple of 32; PLAIN: ld >= the last column;
  * TILED: its tiles are contiguous).  This is how an ensemble with several option words runs: its segments are grouped by word

@@ -192,12 +192,25 @@ def check_metric_batch_kernels(names=("p_metric_pack", "i001_metric"), replicate
             assert np.array_equal(ea[k], eb[k]), (name, k)
 
 
-def check_shared_met_mode(n=75, jit=None, nst=5):
+def check_shared_met_mode(n=75, jit=None, nst=5, table=False):
     """hsp2g_set_shared_forcing: a few met stations + per-segment station index and MFACTOR give bit-identical results to
     handing every segment its own series * MFACTOR arrays (what get_timeseries builds, utilities.py:274-290); generic and
     compile-time-specialised kernels, with and without divergence ordering."""
     cal = Calendar("1976-02-01", "1976-03-10", 60, "us")
-    steps = cal.steps  # nst <= 32: one bulk copy of the station table per warp-interval; more: per-lane gathers
+    steps = cal.steps
+    # per-lane gathers from the station table; HSP2G_MET_TABLE=1 and nst <= 32: one bulk copy of the table per warp-interval
+    old = os.environ.get("HSP2G_MET_TABLE")
+    os.environ["HSP2G_MET_TABLE"] = "1" if table else "0"
+    try:
+        _check_shared_met_mode(n, jit, nst, table, cal, steps)
+    finally:
+        if old is None:
+            del os.environ["HSP2G_MET_TABLE"]
+        else:
+            os.environ["HSP2G_MET_TABLE"] = old
+
+
+def _check_shared_met_mode(n, jit, nst, table, cal, steps):
     rng = np.random.default_rng(3)
     ens = synth.Ensemble("PERLND", n, seed=21, sections=("SNOW", "PWATER"))
     names = list(synth.PERLND_FORCINGS)
@@ -229,7 +242,7 @@ def check_shared_met_mode(n=75, jit=None, nst=5):
                 b.set_shared_forcing(series, station, mfac)
                 got = b.run_shared(chunk=300)
                 assert "met=shared" in b.kernel_name()
-                assert not jit or ("met=shared/table" in b.kernel_name()) == (nst <= 32), b.kernel_name()
+                assert not jit or ("met=shared/table" in b.kernel_name()) == (table and nst <= 32), b.kernel_name()
                 assert jit is None or (",jit>" in b.kernel_name()) == bool(jit), b.kernel_name()
                 assert np.array_equal(b.get_state(), ref_state, equal_nan=True)
             assert np.array_equal(got, ref, equal_nan=True)
@@ -433,10 +446,11 @@ def check_watershed(tmpdir, n=48, gages=4, days=40, sample=(0, 7, 21), chunk=480
     return sink
 
 
-def check_qual_chain_on_device(n=70, chunk=300, order=None):
-    """Land batch -> hsp2g_gather_* -> PQUAL rows with every buffer device-resident (hsp2g_run_device on both batches) gives the
-    same bits as feeding the constituents from the land batch's host-side outputs (QualBatch.gather), with and without a
-    divergence-aware device order of the land segments."""
+def check_qual_chain_on_device(n=70, chunk=300, order=None, chain="gather", layout="tiled", jit=None):
+    """Land batch -> PQUAL rows with every buffer device-resident gives the same bits as feeding the constituents from the land
+    batch's host-side outputs (QualBatch.gather), with and without a divergence-aware device order of the land segments.
+    chain="gather": hsp2g_gather_* fills a scratch buffer (tile-major); chain="linked": the rows read the land batch's buffers in
+    place (hsp2g_run_device_linked), in either series layout."""
     import ctypes as C
 
     from hspsquared_b200.engine import QualBatch, tile_series, untile_series
@@ -458,10 +472,14 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
     series["PREC"] = f[:, names.index("PREC"), :]
     with QualBatch("PERLND", ucis, cal, qn, "all") as q:
         want = q.run(q.gather(series), chunk=chunk)
+        want_rows = list(q.rows)
     # device-resident chain
-    with LandBatch(ens.store(cal), cal, names, need, order=order, layout="tiled") as land, \
-            QualBatch("PERLND", ucis, cal, qn, "all", land=land) as q:
-        got = np.empty_like(want)
+    if chain == "gather":
+        layout = "tiled"
+    with LandBatch(ens.store(cal), cal, names, need, order=order, layout=layout, jit=jit) as land, \
+            QualBatch("PERLND", ucis, cal, qn, "all", land=land, chain=chain, layout=layout, jit=jit) as q:
+        assert q.chain == chain
+        got = np.empty((steps, q.ns, q.n))
         dev = []
 
         def dalloc(nbytes):
@@ -475,21 +493,40 @@ def check_qual_chain_on_device(n=70, chunk=300, order=None):
             fc = f[t0:t0 + m][:, land._fperm, :]
             if land.order is not None:
                 fc = fc[:, :, land.order]
-            ft = tile_series(fc)
-            d_f, d_lo = dalloc(ft.nbytes), dalloc(land.ntiles * m * land.ns * 32 * 8)
-            d_qf, d_qo = dalloc(q.ntiles * m * q.nf * 32 * 8), dalloc(q.ntiles * m * q.ns * 32 * 8)
+            if layout == "tiled":
+                ft = tile_series(fc)
+            else:
+                ft = np.zeros((m, land.nf, land.npad))
+                ft[:, :, :land.n] = fc
+            d_f, d_lo = dalloc(ft.nbytes), dalloc(land.npad * m * land.ns * 8)
+            d_qo = dalloc(q.npad * m * q.ns * 8)
             _lib.check(lib.hsp2g_memcpy_h2d(0, d_f, ft.ctypes.data, ft.nbytes))
             land.run_device(t0, m, d_f, d_lo)
-            q.run_device_from(t0, m, d_f, d_lo, d_qf, d_qo)
+            if chain == "gather":
+                q.run_device_from(t0, m, d_f, d_lo, dalloc(q.npad * m * q.nf * 8), d_qo)
+            else:
+                q.run_device_linked_from(t0, m, d_f, d_lo, d_qo)
+                assert "in=linked-rows" in q.kernel_name() or not q.jit, q.kernel_name()
             land.sync()
             q.sync()
-            ho = np.empty((q.ntiles, m, q.ns, 32))
-            _lib.check(lib.hsp2g_memcpy_d2h(0, ho.ctypes.data, d_qo, ho.nbytes))
-            u = untile_series(ho, q.n)[:, q._sinv, :]  # device row order -> the caller's
+            if layout == "tiled":
+                ho = np.empty((q.ntiles, m, q.ns, 32))
+                _lib.check(lib.hsp2g_memcpy_d2h(0, ho.ctypes.data, d_qo, ho.nbytes))
+                u = untile_series(ho, q.n)
+            else:
+                ho = np.empty((m, q.ns, q.npad))
+                _lib.check(lib.hsp2g_memcpy_d2h(0, ho.ctypes.data, d_qo, ho.nbytes))
+                u = ho[:, :, :q.n]
+            u = u[:, q._sinv, :]  # device row order -> the caller's
             got[t0:t0 + m] = u if q._inv is None else u[:, :, q._inv]
         for p in dev:
             lib.hsp2g_device_free(0, C.c_void_p(p))
-    assert np.array_equal(got, want, equal_nan=True)
+        rows = list(q.rows)
+    if chain == "linked":  # one row per (land device segment incl. the padding lanes, constituent): pick the real ones
+        assert len(rows) == land.npad * 3 and sum(1 for sgm, _k in rows if sgm < 0) == (land.npad - n) * 3
+        at = {r: j for j, r in enumerate(rows) if r[0] >= 0}
+        got = got[:, :, [at[r] for r in want_rows]]
+    assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True)
     assert np.nanmax(want[:, q.save.index("PQUAL_SOQUAL"), :]) > 0
 
 

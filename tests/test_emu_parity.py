@@ -105,6 +105,14 @@ def test_constituents_fed_on_the_device(order):
     parity.check_qual_chain_on_device(order=order)
 
 
+@pytest.mark.parametrize("layout,order,jit", [("tiled", None, False), ("plain", "flags", False), ("tiled", "flags", True),
+                                               ("plain", None, True)])
+def test_constituents_read_the_land_buffers_in_place(layout, order, jit):
+    """hsp2g_run_device_linked: the PQUAL rows, constituent-major over the land batch's tiles, read its output and forcing buffers
+    in place (no gather, no scratch) == the host-side chain, bit for bit; general kernels and the ones built for the batch."""
+    parity.check_qual_chain_on_device(order=order, chain="linked", layout=layout, jit=jit)
+
+
 def test_abi_error_behaviour_and_smallest_shapes():
     parity.check_abi_errors_and_edges()
 

@@ -270,10 +270,13 @@ def test_shared_met_mode_on_gpu():
 
 
 def test_shared_met_batch_kernels_table_and_gather_on_gpu():
-    """The kernels built for the batch in both shared-met modes: <= 32 stations (one bulk copy of the interval's station table per
-    warp) and more (per-lane cp.async gathers) == per-segment forcing arrays, bit for bit."""
+    """The kernels built for the batch in both shared-met modes: per-lane cp.async gathers (the default) and, with
+    HSP2G_MET_TABLE=1 and <= 32 stations, one bulk copy of the interval's station table per warp == per-segment forcing
+    arrays, bit for bit."""
     parity.check_shared_met_mode(n=2500, jit=True)
     parity.check_shared_met_mode(n=2500, jit=True, nst=37)
+    parity.check_shared_met_mode(n=2500, jit=True, table=True)
+    parity.check_shared_met_mode(n=2500, jit=None, table=True)
 
 
 def test_metric_units_compiled_into_batch_kernels_on_gpu():
@@ -373,6 +376,13 @@ def test_constituents_fed_on_the_device():
     """Land kernel -> gather kernel -> qual kernel with every buffer in HBM: same bits as the host-side chain (3,000 segments,
     divergence-ordered land batch)."""
     parity.check_qual_chain_on_device(n=3000, chunk=256, order="flags")
+
+
+@pytest.mark.parametrize("layout,jit", [("tiled", True), ("plain", True), ("plain", False)])
+def test_constituents_read_the_land_buffers_in_place(layout, jit):
+    """hsp2g_run_device_linked on the GPU: the PQUAL rows fetch their seven input rows with one 256-byte bulk copy each straight
+    from the land batch's output / forcing buffers (3,000 segments -> 9,024 rows incl. the padding lanes)."""
+    parity.check_qual_chain_on_device(n=3000, chunk=256, order="flags", chain="linked", layout=layout, jit=jit)
 
 
 def test_metstore_feeds_shared_met_kernels():

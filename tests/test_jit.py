@@ -32,7 +32,7 @@ def test_generated_source_names_what_it_fixes():
         spec = jit.spec_of(b)
     assert spec["word"] == int(ens.store(CAL).flags[0]) and spec["plain"] and not spec["f32in"] and spec["act"] == 6
     text = jit.source(spec, 128)
-    assert "StaticFlags<%#xull, 0xffffffffffffffffull, 0>" % spec["word"] in text and "StaticLay<true, false, -1>" in text
+    assert "StaticFlags<%#xull, 0xffffffffffffffffull, 0>" % spec["word"] in text and "StaticLay<true, false, -1, false>" in text
     assert "perlnd_body<ACT, HOURLY, IO, SHARED, FW, LAY>" in text and "__launch_bounds__(LAND_BLOCK, 8)" in text
     # without a common option word the bits are read per segment (mask 0); the batch-wide HSP2G_OPT_* bits stay fixed
     assert "StaticFlags<0x0ull, 0x0ull, 2>" in jit.source(dict(spec, word=None, opts=2), 168) and "__launch_bounds__(LAND_BLOCK, 6)" in jit.source(spec, 168)
@@ -83,8 +83,10 @@ def test_metric_units_are_compiled_into_the_batch_kernel():
     parity.check_metric_batch_kernels()
 
 
-def test_shared_met_gathers_with_many_stations():
-    parity.check_shared_met_mode(n=75, jit=True, nst=37)
+def test_shared_met_station_table_mode():
+    """HSP2G_MET_TABLE=1: the interval's station table by one bulk copy (<= 32 stations; more fall back to the gathers)."""
+    parity.check_shared_met_mode(n=75, jit=True, table=True)
+    parity.check_shared_met_mode(n=75, jit=True, nst=37, table=True)
 
 
 def test_shared_met_implnd_and_constituent_kernels():

@@ -80,8 +80,10 @@ def run_qual(name, torch, dev):
 
 
 def run_chain(name, torch, dev):
-    """configs[3] with its quality constituents: 250 k full-chain segments (6 flow / sediment series saved), the device gather and
-    3 PQUAL constituents per segment (750 k rows, all 20 outputs each), everything resident in HBM; timed end to end per chunk."""
+    """configs[3] with its quality constituents: 250 k full-chain segments (6 flow / sediment series saved) and 3 PQUAL constituents
+    per segment (750 k rows, all 20 outputs each), everything resident in HBM; timed end to end per chunk.
+    fullchain_pqual[_plain]: the constituents read the land batch's buffers in place (hsp2g_run_device_linked);
+    fullchain_pqual_gather: round 1's chain, a device gather into a scratch buffer between the two kernels."""
     from hspsquared_b200 import synth, test10
     from hspsquared_b200.calendar import Calendar
     from hspsquared_b200.engine import LandBatch, QualBatch
@@ -89,23 +91,29 @@ def run_chain(name, torch, dev):
 
     cal = Calendar(bench.RUN_START, bench.RUN_STOP, 60, "ns")
     K, W, Tc, n = 8, 3, 128, 250_000
+    gather = name.endswith("_gather")
+    layout = "plain" if name.endswith("_plain") else "tiled"
     ens = synth.Ensemble("PERLND", n, seed=1234, base="cbp", options=("RTOPFG", "UZFG", "SNOPFG", "ICEFG", "TSOPFG"))
     forcings = list(synth.FULLCHAIN_FORCINGS)
     need = ["PWATER_SURO", "PWATER_IFWO", "PWATER_AGWO", "PWATER_PERO", "SEDMNT_WSSD", "SEDMNT_SCRSD"]
     qt = test10.pqual_tables()
-    with LandBatch(ens.store(cal), cal, forcings, need, device=dev.index or 0, order="flags", layout="tiled") as land, \
-            QualBatch("PERLND", [qt] * n, cal, list(PQUAL_INPUTS[:7]), "all", device=dev.index or 0, land=land) as q:
+    with LandBatch(ens.store(cal), cal, forcings, need, device=dev.index or 0, order="flags", layout=layout) as land, \
+            QualBatch("PERLND", [qt] * n, cal, list(PQUAL_INPUTS[:7]), "all", device=dev.index or 0, land=land, layout=layout,
+                      chain="gather" if gather else "linked") as q:
         ens2 = ens.take(land.order)  # forcings generated in the land batch's device order
-        forc = [bench.device_forcing(torch, ens2, cal, c * Tc, Tc, land.npad, dev, land.forcing_rows, "tiled") for c in range(K + W)]
-        lo = torch.empty((land.npad // 32, Tc, land.ns, 32), dtype=torch.float64, device=dev)
-        qf = torch.empty((q.npad // 32, Tc, q.nf, 32), dtype=torch.float64, device=dev)
-        qo = [torch.empty((q.npad // 32, Tc, q.ns, 32), dtype=torch.float64, device=dev) for _ in range(2)]
+        forc = [bench.device_forcing(torch, ens2, cal, c * Tc, Tc, land.npad, dev, land.forcing_rows, layout) for c in range(K + W)]
+        lo = torch.empty(land.npad * Tc * land.ns, dtype=torch.float64, device=dev)
+        qf = torch.empty(q.npad * Tc * q.nf if gather else 1, dtype=torch.float64, device=dev)
+        qo = [torch.empty(q.npad * Tc * q.ns, dtype=torch.float64, device=dev) for _ in range(2)]
         stream = torch.cuda.Stream(dev)
         torch.cuda.synchronize(dev)
 
         def step(c):
             land.run_device(c * Tc, Tc, forc[c].data_ptr(), lo.data_ptr(), stream.cuda_stream)
-            q.run_device_from(c * Tc, Tc, forc[c].data_ptr(), lo.data_ptr(), qf.data_ptr(), qo[c % 2].data_ptr(), stream.cuda_stream)
+            if gather:
+                q.run_device_from(c * Tc, Tc, forc[c].data_ptr(), lo.data_ptr(), qf.data_ptr(), qo[c % 2].data_ptr(), stream.cuda_stream)
+            else:
+                q.run_device_linked_from(c * Tc, Tc, forc[c].data_ptr(), lo.data_ptr(), qo[c % 2].data_ptr(), stream.cuda_stream)
 
         for c in range(W):
             step(c)
@@ -118,15 +126,25 @@ def run_chain(name, torch, dev):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
         peak, _src = bench.measured_peak()
-        # algorithmic bytes per segment-interval: land 6 forcings in + 6 series out, gather 7 in + 7 out per row, constituents 7 + 20
-        B = 8 * (6 + 6) + 3 * 8 * (7 + 7) + 3 * 8 * (7 + 20)
+        # algorithmic bytes per segment-interval: land 6 forcings in + 6 series out, constituents 7 in + 20 out per row (+ the
+        # gather's 7 in + 7 out per row where there is one)
+        B = 8 * (6 + 6) + 3 * 8 * (7 + 20) + (3 * 8 * (7 + 7) if gather else 0)
         value = n * Tc * K / (ms * 1e-3)
-        sq = float(qo[(W + K - 1) % 2][:, :, q.save_rows.index("PQUAL_SOQUAL")].sum().item())
-        line = {"config": name, "kernels": [land.kernel_name(), "gather_kernel", q.kernel_name()], "segments": n,
-                "constituent_rows": q.n, "intervals_per_step": Tc, "steps": K, "ms_per_step": ms / K,
-                "segment_timesteps_per_s": value, "bytes_per_segment_interval": B, "algorithmic_GBps": value * B / 1e9,
-                "frac_of_measured_hbm": value * B / 1e9 / peak, "checksum_soqual_last_chunk": sq,
-                "note": "full chain + 3 PQUAL constituents per segment, three launches per chunk on one stream, no host round trip"}
+        last = qo[(W + K - 1) % 2]
+        r = q.save_rows.index("PQUAL_SOQUAL")
+        sq = last.view(q.npad // 32, Tc, q.ns, 32)[:, :, r].permute(1, 0, 2).reshape(Tc, -1) if layout == "tiled" \
+            else last.view(Tc, q.ns, q.npad)[:, r]
+        sq = sq[:, :q.n]  # [interval][device row]
+        if not gather:  # the rows of the land batch's padding lanes (copies of its last segment) are not part of the result
+            real = torch.tensor([sgm >= 0 for sgm, _k in q.rows], device=dev)[torch.as_tensor(q.order, device=dev)]
+            sq = sq[:, real]
+        line = {"config": name, "kernels": [land.kernel_name()] + (["gather_kernel"] if gather else []) + [q.kernel_name()],
+                "segments": n, "constituent_rows": int(sum(1 for sgm, _k in q.rows if sgm >= 0)), "intervals_per_step": Tc, "steps": K,
+                "ms_per_step": ms / K, "segment_timesteps_per_s": value, "bytes_per_segment_interval": B,
+                "algorithmic_GBps": value * B / 1e9, "frac_of_measured_hbm": value * B / 1e9 / peak,
+                "checksum_soqual_last_chunk": float(sq.sum().item()),
+                "note": "full chain + 3 PQUAL constituents per segment, %s launches per chunk on one stream, no host round trip"
+                        % ("three" if gather else "two")}
     del forc, lo, qf, qo
     torch.cuda.empty_cache()
     return line
@@ -233,7 +251,7 @@ def run(name, torch, dev):
         return run_daily_e2e(name, torch, dev)
     if name in ("pqual", "iqual"):
         return run_qual(name, torch, dev)
-    if name == "fullchain_pqual":
+    if name.startswith("fullchain_pqual"):
         return run_chain(name, torch, dev)
     from hspsquared_b200 import synth, test10
     from hspsquared_b200.calendar import Calendar
