@@ -1531,11 +1531,21 @@ void *hsp2g_host_alloc_flags(size_t bytes, unsigned flags) {
 void *hsp2g_host_alloc(size_t bytes) { return hsp2g_host_alloc_flags(bytes, 0); }
 int hsp2g_host_register(void *p, size_t bytes) {
     if (!p || !bytes) return fail("null argument");
-    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();  // e.g. already page-locked: not an error of any later launch
+        return fail("cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
     return 0;
 }
 int hsp2g_host_unregister(void *p) {
-    if (p) CU(cudaHostUnregister(p));
+    if (p) {
+        cudaError_t e = cudaHostUnregister(p);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail("cudaHostUnregister: %s", cudaGetErrorString(e));
+        }
+    }
     return 0;
 }
 int hsp2g_host_free(void *p) {

@@ -51,6 +51,26 @@ def pinned_empty(shape, dtype=np.float64, write_combined=False):
     return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
+class _PageLocked:
+    """Page-lock ordinary numpy arrays in place for the duration of a run (cudaHostRegister).  Measured on the B200 hosts
+    (tools/exp_pin.py): registering costs 0.02 s per GB, against 0.4-1.0 s per GB for a fresh cudaHostAlloc, and the copies of
+    a registered array run asynchronously at PCIe speed, where the driver stages a pageable one through a bounce buffer at a
+    tenth of it.  Arrays that already are page-locked (pinned_empty, a caller's own registration) are left alone."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self, lib, arrays):
+        self.lib, self.ptrs = lib, []
+        for a in arrays:
+            if a is not None and a.nbytes >= self.MIN_BYTES and lib.hsp2g_host_register(a.ctypes.data, a.nbytes) == 0:
+                self.ptrs.append(a.ctypes.data)
+
+    def release(self):
+        for ptr in self.ptrs:
+            self.lib.hsp2g_host_unregister(ptr)
+        self.ptrs = []
+
+
 class LandBatch:
     def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False, order="flags",
                  layout="plain", jit=None):
@@ -379,9 +399,11 @@ class LandBatch:
         """Wait until the older of the (at most two) chunks in flight through run_chunk / run_host has arrived on the host."""
         _lib.check(self.lib.hsp2g_sync_oldest(self.h))
 
-    def run(self, forcing, chunk=None):
+    def run(self, forcing, chunk=None, out=None):
         """Whole series through host buffers in chunks of `chunk` intervals: forcing [steps][nf][n] -> out
-        [steps][ns][n] (plain layouts; re-tiled per chunk on the way in and out)."""
+        [steps][ns][n] (plain layouts; re-tiled per chunk on the way in and out).
+        out: an array of that shape and the batch's output dtype to fill instead of a new one (saves the first-touch page faults
+        of a fresh array, 0.2 s per GB; used as it is when the device's row and segment order are the caller's)."""
         forcing = np.asarray(forcing)
         steps = forcing.shape[0]
         if forcing.shape != (steps, self.nf, self.n):
@@ -389,16 +411,31 @@ class LandBatch:
         chunk = chunk or steps
         if self.layout == "plain":
             # the arrays go to the device as they are: one strided copy per chunk each way, no host re-tiling (a host copy is
-            # made only when the caller's row order or a segment permutation differs from the device's)
+            # made only when the caller's row order or a segment permutation differs from the device's); ordinary numpy arrays
+            # are page-locked in place for the duration of the call
             f = self._to_device_order(forcing)
-            dev = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
+            same_order = self._inv is None and list(self._sinv) == list(range(self.ns))
+            if out is not None and (out.shape != (steps, self.ns, self.n) or out.dtype != self.out_dtype):
+                raise ValueError("out must be [%d][%d][%d] %s" % (steps, self.ns, self.n, self.out_dtype))
+            direct = out is not None and same_order and out.flags.c_contiguous
+            dev = out if direct else np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
             self._keep.append((f, dev))
             self._kernel()
-            for t0 in range(0, steps, chunk):
-                t1 = min(steps, t0 + chunk)
-                _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(t1 - t0), f[t0:t1].ctypes.data if self.nf else None,
-                                                      self.n, dev[t0:t1].ctypes.data, self.n))
-            self.sync()
+            locked = _PageLocked(self.lib, (f if self.nf else None, dev if self.ns else None))
+            try:
+                for t0 in range(0, steps, chunk):
+                    t1 = min(steps, t0 + chunk)
+                    _lib.check(self.lib.hsp2g_run_host_ld(self.h, int(t0), int(t1 - t0), f[t0:t1].ctypes.data if self.nf else None,
+                                                          self.n, dev[t0:t1].ctypes.data, self.n))
+                self.sync()
+            finally:
+                try:
+                    self.sync()  # nothing may still be copying when the pages are unlocked
+                finally:
+                    locked.release()
+            if out is not None and not direct:
+                out[...] = self._to_caller(dev)
+                return out
             return self._to_caller(dev)
         forcing = np.asarray(forcing, dtype=self.forcing_dtype)
         out = np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
@@ -436,6 +473,7 @@ class LandBatch:
             f = self._to_device_order(forcing)
             dev = np.empty((nper, self.ns, 3, self.n), dtype=np.float32)
             self._keep.append((f, dev))
+            locked = _PageLocked(self.lib, (f if self.nf else None, dev if self.ns else None))
             try:
                 self._kernel()
                 for a, b in zip(cuts[:-1], cuts[1:]):
@@ -443,7 +481,10 @@ class LandBatch:
                                                           dev[int(P[a]):].ctypes.data, self.n))
                 self.sync()
             finally:
-                self.sync()
+                try:
+                    self.sync()
+                finally:
+                    locked.release()
                 _lib.check(self.lib.hsp2g_set_output_periods(self.h, 0, None))
                 self.set_output_dtype(previous)
             u = dev

@@ -263,6 +263,37 @@ def test_water_balance_at_full_size():
     assert np.abs(lhs - rhs).max() / scale.max() < 1e-12, np.abs(lhs - rhs).max()
 
 
+def test_run_page_locks_ordinary_numpy_arrays():
+    """LandBatch.run() registers ordinary numpy arrays in place for the call (cudaHostRegister) and leaves arrays that already
+    are page-locked alone; results do not depend on where the buffers live, `out=` is filled in place, and a refused
+    registration leaves no error behind for the next launch."""
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch, pinned_empty
+
+    cal = Calendar("1976-02-01", "1976-02-15", 60, "us")
+    ens = synth.Ensemble("PERLND", 3000, seed=5, sections=("SNOW", "PWATER"))
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps)
+    assert f.nbytes > (1 << 20)
+    save = ["SNOW_PACKF", "PWATER_SURO", "PWATER_AGWO", "PWATER_UZS"]
+    with LandBatch(ens.store(cal), cal, list(synth.PERLND_FORCINGS), save, order=None) as b:
+        first = b.run(f, chunk=100)
+        state = b.get_state()
+        fp = pinned_empty(f.shape)
+        fp[...] = f
+        op = pinned_empty(first.shape)
+        for fin, out in ((fp, None), (f, np.empty_like(first)), (fp, op), (f[:, :, :], None)):
+            b.set_state(ens.store(cal).state)
+            got = b.run(fin, chunk=100, out=out)
+            assert out is None or got is out
+            assert np.array_equal(got, first, equal_nan=True)
+            assert np.array_equal(b.get_state(), state, equal_nan=True)
+        lib = b.lib
+        assert lib.hsp2g_host_register(fp.ctypes.data, fp.nbytes) != 0 and b"cudaHostRegister" in lib.hsp2g_last_error()
+        b.set_state(ens.store(cal).state)
+        assert np.array_equal(b.run(f, chunk=100), first, equal_nan=True)  # no stale CUDA error after the refusal
+
+
 def test_shared_met_mode_on_gpu():
     """Shared-met mode (cp.async gathers from the station table + MFACTOR at the point of use) == per-segment forcing
     arrays through the TMA ring, bit for bit, on 2,000 segments."""
