@@ -755,10 +755,15 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrie
 
     def pageable(steps, base):
         """ordinary numpy arrays through LandBatch.run(): what a caller who knows nothing about pinned memory pays"""
-        batch.set_forcing_dtype(np.float64)
+        from hspsquared_b200.engine import LandBatch
+
+        f = synth.forcing_chunk(ens0, cal, base, Te, names=list(synth.PERLND_FORCINGS))
+        with LandBatch(store0, cal, list(synth.PERLND_FORCINGS), default_save(), device=dev.index or 0) as plain_batch:
+            return pageable_run(plain_batch, f, steps)
+
+    def pageable_run(batch, f, steps):
+        """a batch built with the defaults (the caller's segment order), ordinary arrays in, a float32 array out"""
         batch.set_output_dtype(np.float32)
-        f = synth.forcing_chunk(ens, cal, base, Te, names=batch.forcing_rows)
-        batch.set_state(store.state)
         batch.run(f, chunk=Te)  # warm-up
         barrier()
         t0 = time.perf_counter()

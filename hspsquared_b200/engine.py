@@ -71,6 +71,21 @@ class _PageLocked:
         self.ptrs = []
 
 
+def _prefault(a, threads=None):
+    """Touch the pages of a freshly allocated array from several threads: the kernel zeroes a page in the thread that first
+    touches it (1.5-5 GB/s from one thread, several times that from eight), and cudaHostRegister would do it alone."""
+    v = a.reshape(-1).view(np.uint8)
+    if v.size < (64 << 20):
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    threads = threads or min(8, os.cpu_count() or 1)
+    cuts = np.linspace(0, v.size, threads * 4 + 1).astype(np.int64) // 4096 * 4096
+    cuts[-1] = v.size
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: v[cuts[i]:cuts[i + 1]:4096].fill(0), range(len(cuts) - 1)))
+
+
 class LandBatch:
     def __init__(self, store: SegmentStore, calendar: Calendar, forcing_names, save, device=0, timing=False, order="flags",
                  layout="plain", jit=None):
@@ -419,6 +434,8 @@ class LandBatch:
                 raise ValueError("out must be [%d][%d][%d] %s" % (steps, self.ns, self.n, self.out_dtype))
             direct = out is not None and same_order and out.flags.c_contiguous
             dev = out if direct else np.empty((steps, self.ns, self.n), dtype=self.out_dtype)
+            if not direct:
+                _prefault(dev)
             self._keep.append((f, dev))
             self._kernel()
             locked = _PageLocked(self.lib, (f if self.nf else None, dev if self.ns else None))
