@@ -372,18 +372,19 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
 }
 
 int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid) {
-    hsp2g_plan_tasks(L, b->sub_steps, b->jit.resident, LAND_WARPS, grid);
+    const unsigned block = (unsigned)b->jit.info[JI_BLOCK];  // the image's own block size (jit.py `block`)
+    hsp2g_plan_tasks(L, b->sub_steps, b->jit.resident, (int)block / LAND_TILE, grid);
 #ifdef HSP2G_HOST_EMU
     (void)st;
     for (unsigned blk = 0; blk < (unsigned)*grid; ++blk)
-        for (unsigned t = 0; t < LAND_BLOCK; ++t) {
+        for (unsigned t = 0; t < block; ++t) {
             blockIdx.x = blk;
             threadIdx.x = t;
             b->jit.fn(L);
         }
 #else
     void *params[1] = {&L};
-    CUresult r = driver().LaunchKernel(b->jit.fn, (unsigned)*grid, 1, 1, LAND_BLOCK, 1, 1, (unsigned)b->jit.info[JI_SMEM], (CUstream)st,
+    CUresult r = driver().LaunchKernel(b->jit.fn, (unsigned)*grid, 1, 1, block, 1, 1, (unsigned)b->jit.info[JI_SMEM], (CUstream)st,
                                        params, nullptr);
     if (r != CUDA_SUCCESS) return fail("launch of the batch's own kernel failed: %s", cu_str(r));
 #endif
@@ -465,9 +466,13 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
     int grid = 0;
     const bool qual = (b->act & (HSP2G_ACT_PQUAL | HSP2G_ACT_IQUAL)) != 0;
     int rc = 0;
-    if (b->jit.on && jit_matches(b, L))
+    long long warps_per_block = LAND_WARPS;
+    bool lockstep = false;
+    if (b->jit.on && jit_matches(b, L)) {
         rc = launch_jit(b, L, st, &grid);
-    else {
+        warps_per_block = (long long)b->jit.info[JI_BLOCK] / LAND_TILE;
+        lockstep = (b->jit.info[JI_BITS] & JB_LOCKSTEP) != 0;
+    } else {
         cudaError_t e = qual                    ? hsp2g_launch_qual(L, b->op == HSP2G_IMPLND, b->sub_steps, st, &b->kname, &grid)
                         : b->op == HSP2G_PERLND ? hsp2g_launch_perlnd(L, hourly, b->sub_steps, st, &b->kname, &grid)
                                                 : hsp2g_launch_implnd(L, hourly, b->sub_steps, st, &b->kname, &grid);
@@ -479,7 +484,10 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
         return rc;
     }
     // every task draws one ticket and every warp one more (the draw that tells it to stop)
-    b->task_base += (unsigned long long)L.ntiles * L.nsub + (unsigned long long)grid * LAND_WARPS;
+    // (lock-step kernels draw a block's tickets together: whole rounds of warps_per_block, and one last round per block)
+    const unsigned long long tasks = (unsigned long long)L.ntiles * L.nsub;
+    b->task_base += (lockstep ? (tasks + warps_per_block - 1) / warps_per_block * warps_per_block : tasks) +
+                    (unsigned long long)grid * warps_per_block;
     b->prog_base += (unsigned)L.nsub;
     if (b->timing) {
         CU(cudaEventRecord(e1, st));
@@ -1459,7 +1467,7 @@ int hsp2g_set_kernel_image(hsp2g_batch *b, const void *image, size_t nbytes, con
     CU(cudaMemcpy(info, (const void *)ip, sizeof info, cudaMemcpyDeviceToHost));
 #endif
     if (info[JI_MAGIC] != HSP2G_JIT_MAGIC || info[JI_LAUNCH_BYTES] != sizeof(LandLaunch) || info[JI_SBROWS] != SB_ROWS ||
-        info[JI_BLOCK] != LAND_BLOCK) {
+        info[JI_BLOCK] < LAND_TILE || info[JI_BLOCK] > 1024 || info[JI_BLOCK] % LAND_TILE) {
         drop_kernel_image(b);
         return fail("kernel image was built against other kernel sources than this library (launch record %llu vs %zu bytes)",
                     info[JI_LAUNCH_BYTES], sizeof(LandLaunch));
@@ -1471,7 +1479,7 @@ int hsp2g_set_kernel_image(hsp2g_batch *b, const void *image, size_t nbytes, con
         return fail("cuFuncSetAttribute(max dynamic shared memory = %llu): %s", info[JI_SMEM], cu_str(r));
     }
     int per_sm = 0, sms = 0;
-    r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->jit.fn, LAND_BLOCK, (size_t)info[JI_SMEM]);
+    r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->jit.fn, (int)info[JI_BLOCK], (size_t)info[JI_SMEM]);
     if (r != CUDA_SUCCESS || per_sm <= 0) {
         drop_kernel_image(b);
         return fail("the batch's kernel does not fit an SM (%llu bytes of shared memory): %s", info[JI_SMEM], cu_str(r));

@@ -515,15 +515,44 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
+// HSP_LOCKSTEP (kernels built per batch only, hspsquared_b200/jit.py `lockstep`): the warps of a block draw LAND_WARPS
+// consecutive tickets at once (adjacent tiles of one sub-chunk, i.e. neighbours in the batch's climate order) and meet at a
+// block barrier before every interval, so that the resident warps of an SM run the SAME stretch of the loop at about the same
+// time and share its instruction-cache lines instead of sitting at 16 unrelated points of a 38 KB loop (profiles/README.md,
+// the melt-season launch).  Every warp of a block passes exactly L.sub barriers per round, whether its own task is shorter
+// (the last sub-chunk) or absent (tickets past the end): `idle`.  Dependencies (progress[tile]) point at tickets ntiles
+// earlier, i.e. at earlier rounds, so the lowest unfinished round can always run: no deadlock.
 struct Sched {
     const LandLaunch &L;
     int lane, c;
+#ifdef HSP_LOCKSTEP
+    int wib;
+    bool idle;
+    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int wib_) : L(l), lane(lane_), c(0), wib(wib_), idle(false) {}
+#else
     __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int) : L(l), lane(lane_), c(0) {}
+#endif
     __device__ __forceinline__ bool next(int &tile, int &t0, int &t1) {
+#ifdef HSP_LOCKSTEP
+        __shared__ unsigned long long s_base;
+        __syncthreads();  // the previous round's readers are done with s_base
+        if (threadIdx.x == 0) s_base = atomicAdd(L.task_counter, (unsigned long long)LAND_WARPS) - L.task_base;
+        __syncthreads();
+        const unsigned long long base = s_base;
+        if (base >= (unsigned long long)L.ntiles * (unsigned)L.nsub) return false;  // block-uniform
+        const unsigned long long k = base + (unsigned)wib;
+        idle = k >= (unsigned long long)L.ntiles * (unsigned)L.nsub;
+        if (idle) {
+            tile = 0;
+            t0 = t1 = 0;
+            return true;
+        }
+#else
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(L.task_counter, 1ull) - L.task_base;
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= (unsigned long long)L.ntiles * (unsigned)L.nsub) return false;
+#endif
         c = (int)(k / (unsigned)L.ntiles);
         tile = (int)(k - (unsigned long long)c * (unsigned)L.ntiles);
         t0 = c * L.sub;
@@ -547,6 +576,28 @@ struct Sched {
     }
 };
 #define HSP_SYNCWARP() __syncwarp()
+#ifdef HSP_LOCKSTEP
+// a warp without a task keeps its block's barrier count; the time loop runs L.sub rounds for every warp of the block
+#define HSP_TASK_IDLE(sched, L)                                   \
+    if ((sched).idle) {                                           \
+        for (int i_ = 0; i_ < (L).sub; ++i_) __syncthreads();     \
+        continue;                                                 \
+    }
+#define HSP_T_LIM(L, t0, t1) ((t0) + (L).sub)
+#define HSP_STEP_SYNC(t, t1) \
+    __syncthreads();         \
+    if ((t) >= (t1)) continue;
+#if HSP_LOCKSTEP >= 2
+#define HSP_SECTION_SYNC() __syncthreads()
+#else
+#define HSP_SECTION_SYNC()
+#endif
+#else
+#define HSP_TASK_IDLE(sched, L)
+#define HSP_T_LIM(L, t0, t1) (t1)
+#define HSP_STEP_SYNC(t, t1)
+#define HSP_SECTION_SYNC()
+#endif
 
 #else
 // test double: same interface, synchronous copies (no TMA on the host); one "thread" at a time, which walks the
@@ -624,6 +675,10 @@ struct Sched {
     void done(int) {}
 };
 #define HSP_SYNCWARP()
+#define HSP_TASK_IDLE(sched, L)
+#define HSP_T_LIM(L, t0, t1) (t1)
+#define HSP_STEP_SYNC(t, t1)
+#define HSP_SECTION_SYNC()
 #endif
 
 // ---- metric units (siminfo['units'] == 2; HSP2G_OPT_METRIC in L.opts).  The reference keeps every state in English units and

@@ -72,6 +72,7 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {  // one task = intervals [t0, t1) of one tile (land_common.cuh Sched)
+        HSP_TASK_IDLE(sched, L)
         pipe.begin_task(tile, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
@@ -92,7 +93,9 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
         if (act & HSP2G_ACT_SEDMNT) sd.load(s);
         if (act & HSP2G_ACT_PSTEMP) ps.load(s);
 
-        for (int t = t0; t < t1; ++t) {
+        const int t_lim = HSP_T_LIM(L, t0, t1);
+        for (int t = t0; t < t_lim; ++t) {
+            HSP_STEP_SYNC(t, t1)
             s.begin_step(pipe.acquire());
             const double prec = s.forcing(F_PREC);
             const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);
@@ -119,6 +122,7 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
             link.airtmp = airtmp;
 
             PwaterFlux fx;
+            HSP_SECTION_SYNC();
             if (act & HSP2G_ACT_PWATER) {
                 if (t == t0 || (s.calfl & HSP2G_CAL_NEWDAY)) pw.refresh_daily(s);
                 pwater_step<HOURLY>(s, pw, link, prec, fx);
@@ -179,6 +183,7 @@ __device__ __forceinline__ void implnd_body(const LandLaunch &L) {
     Sched sched(L, lane, wib);
     int tile, t0, t1;
     while (sched.next(tile, t0, t1)) {
+        HSP_TASK_IDLE(sched, L)
         pipe.begin_task(tile, t0, t1);
         SegT s(L, tile, lane, t0, pipe.hot_area());
 
@@ -192,7 +197,9 @@ __device__ __forceinline__ void implnd_body(const LandLaunch &L) {
         if (act & HSP2G_ACT_SOLIDS) sl.load(s);
         if (act & HSP2G_ACT_IWTGAS) ig.load(s);
 
-        for (int t = t0; t < t1; ++t) {
+        const int t_lim = HSP_T_LIM(L, t0, t1);
+        for (int t = t0; t < t_lim; ++t) {
+            HSP_STEP_SYNC(t, t1)
             s.begin_step(pipe.acquire());
             const double prec = s.forcing(F_PREC);
             const double airtmp = (act & HSP2G_ACT_ATEMP) ? atemp_step(s, prec) : s.forcing(F_AIRTMP);

@@ -132,7 +132,17 @@ def default_maxreg(spec):
     return 168 if (spec["act"] & CHAIN_ACTS) or ns > 32 else 128
 
 
-def display_name(spec, maxreg):
+def geometry(spec, kind=None):
+    """(threads per block, lock-step level) of the kernel built for `spec`.  Lock-step blocks (csrc/land_common.cuh
+    HSP_LOCKSTEP): the warps of a block take adjacent tiles and meet at a block barrier before every interval."""
+    if spec["qual"] or (kind or _lib.build_kind()) != _lib.CUDA_BUILD:
+        return 64, 0
+    block = int(os.environ.get("HSP2G_JIT_BLOCK", spec.get("block") or 64))
+    lockstep = int(os.environ.get("HSP2G_JIT_LOCKSTEP", spec.get("lockstep") or 0))
+    return block, lockstep
+
+
+def display_name(spec, maxreg, kind=None):
     acts = "|".join(n for i, n in enumerate(ACT_NAMES) if spec["act"] >> i & 1)
     kern = "qual_kernel" if spec["qual"] else ("perlnd_kernel" if spec["op"] == 0 else "implnd_kernel")
     parts = [acts, "hourly" if spec["hourly"] else "subhourly",
@@ -153,23 +163,31 @@ def display_name(spec, maxreg):
                                                                       _popc(~spec["mask"] & ((1 << len(_lib.names("flags"))) - 1))))
     if spec.get("opts"):
         parts.append("batch-opts=%#x" % spec["opts"])
+    block, lockstep = geometry(spec, kind)
+    if block != 64 or lockstep:
+        parts.append("block=%d%s" % (block, ",lockstep=%d" % lockstep if lockstep else ""))
     parts.append("regs<=%d" % maxreg)
     return "%s<%s,jit>" % (kern, ",".join(parts))
 
 
-def source(spec, maxreg):
+def source(spec, maxreg, kind=None):
     """The translation unit: one instantiation of the body template + the info words hsp2g_set_kernel_image checks."""
     u = lambda v: "%#xull" % v
     b = lambda v: "true" if v else "false"
     act = spec["act"]
     lines = ["// generated by hspsquared_b200/jit.py for one batch configuration -- not a source file of the repository",
-             "// %s" % display_name(spec, maxreg)]
+             "// %s" % display_name(spec, maxreg, kind)]
     inline_div = spec["word"] is not None and spec.get("mask", 0xFFFFFFFFFFFFFFFF) == 0xFFFFFFFFFFFFFFFF and not (act & CHAIN_ACTS)
     if os.environ.get("HSP2G_JIT_INLINE_DIV"):  # measurement switch
         inline_div = os.environ["HSP2G_JIT_INLINE_DIV"] == "1"
     if inline_div:
         # small kernels (a known option word removes whole sections): the IEEE division sequence inline at every site
         lines.append("#define HSP_INLINE_DIV")
+    block, lockstep = geometry(spec, kind)
+    if block != 64:
+        lines.append("#define LAND_BLOCK %d" % block)
+    if lockstep:
+        lines.append("#define HSP_LOCKSTEP %d" % lockstep)
     lines += ['#include "jit_info.h"', '#include "land_kernels.cuh"', '#include "qual.cuh"',
               "typedef StaticIO<%s, %s, %s, %s, %s> IO;" % (u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), b(spec["f32out"]), u(spec["s2"])),
               "typedef %s FW;" % ("StaticFlags<%s, %s, %d>" % (u(spec["word"] or 0), u(spec.get("mask", 0) if spec["word"] is not None else 0),
@@ -193,7 +211,7 @@ def source(spec, maxreg):
                                       ("JB_SHARED", spec["shared"]), ("JB_WORD", spec["word"] is not None), ("JB_IOSTATIC", True),
                                       ("JB_LAYSTATIC", True), ("JB_QUAL", spec["qual"]),
                                       ("JB_OPTS", spec.get("opts") is not None), ("JB_METTBL", spec.get("mettbl")),
-                                      ("JB_LINKED", spec.get("linked"))) if on)
+                                      ("JB_LINKED", spec.get("linked")), ("JB_LOCKSTEP", lockstep)) if on)
     info = ("{HSP2G_JIT_MAGIC, sizeof(LandLaunch), %s, %d, %s, %d, %s, %s, %s, %s, %s, %s, LAND_BLOCK, SB_ROWS, %s, %d}"
             % (smem, spec["op"], u(act), int(spec["hourly"]), u(spec["fmask"]), u(spec["s0"]), u(spec["s1"]), u(spec["s2"]), bits,
                u(spec["word"] or 0), u(spec.get("mask", 0xFFFFFFFFFFFFFFFF) if spec["word"] is not None else 0), spec.get("opts") or 0))
@@ -204,7 +222,7 @@ def source(spec, maxreg):
               "// register cap %d through the resident-blocks bound (__maxnreg__ cannot be combined with __launch_bounds__ on a"
               " non-template kernel)" % maxreg,
               'extern "C" __global__ void __launch_bounds__(LAND_BLOCK, %d) %s(const __grid_constant__ LandLaunch L) { %s }'
-              % (65536 // (64 * maxreg), ENTRY, body),
+              % (max(1, 65536 // (block * maxreg)), ENTRY, body),
               'extern "C" __device__ const unsigned long long %s_info[JI_N] = %s;' % (ENTRY, info),
               "#endif", ""]
     return "\n".join(lines)
@@ -253,7 +271,7 @@ def ensure(spec, kind=None, maxreg=None):
     tried = []
     mr = maxreg or default_maxreg(spec)
     while True:
-        text = source(spec, mr)
+        text = source(spec, mr, kind)
         key = hashlib.sha1((text + "\0" + _sources_hash() + "\0" + kind + "\0" + " ".join(NVCC_FLAGS) +
                             os.environ.get("HSP2G_JIT_FLAGS", "")).encode()).hexdigest()[:20]
         out = os.path.join(CACHE, key + (".cubin" if kind == _lib.CUDA_BUILD else ".so"))
@@ -264,7 +282,7 @@ def ensure(spec, kind=None, maxreg=None):
         else:
             log, secs = _compile(text, out, kind, mr)
             regs, spill = _ptxas(log) if kind == _lib.CUDA_BUILD else (None, 0)
-            meta = {"spec": spec, "name": display_name(spec, mr), "maxreg": mr, "registers": regs, "spill_bytes": spill,
+            meta = {"spec": spec, "name": display_name(spec, mr, kind), "maxreg": mr, "registers": regs, "spill_bytes": spill,
                     "compile_s": round(secs, 2), "kind": kind, "sources": _sources_hash()}
             mtmp = meta_p + ".tmp%d_%d" % (os.getpid(), threading.get_ident())
             with open(mtmp, "w") as f:
