@@ -364,6 +364,9 @@ def out_column(got, i, layout):
     return got[:, :, i] if layout == "plain" else got[i // 32, :, :, i % 32]
 
 
+OVERLAP = os.environ.get("HSP2G_OVERLAP", "1") != "0"  # measurement switch: 0 = every launch waits for the previous one to end
+
+
 def time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0):
     """W untimed + K timed launches of `batch` over consecutive chunks (state carried), CUDA events on the launching stream,
     barrier + synchronize on both sides, max over ranks.  -> ms for the K launches"""
@@ -373,6 +376,11 @@ def time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # consecutive launches overlap at their tails (hsp2g_set_launch_overlap): every chunk's forcings are resident before the
+    # loop starts and the two output buffers alternate, which is the caller's side of that contract
+    overlap = OVERLAP and hasattr(batch, "set_launch_overlap")
+    if overlap:
+        batch.set_launch_overlap(True)
     for c in range(first, first + W):
         batch.run_device(c * Tc, Tc, forc[c % len(forc)].data_ptr(), outs[c % 2].data_ptr(), stream.cuda_stream)
     barrier()
@@ -383,6 +391,8 @@ def time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    if overlap:
+        batch.set_launch_overlap(False)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -83,6 +83,8 @@ _PROTOS = {
     "hsp2g_reset_errors": (C.c_int, [_h]),
     "hsp2g_set_output_dtype": (C.c_int, [_h, C.c_int]),
     "hsp2g_set_schedule": (C.c_int, [_h, C.c_int32]),
+    "hsp2g_set_launch_overlap": (C.c_int, [_h, C.c_int]),
+    "hsp2g_chained_launches": (C.c_int64, [_h]),
     "hsp2g_set_timing": (C.c_int, [_h, C.c_int]),
     "hsp2g_kernel_stats": (C.c_int, [_h, _i64p, _dp]),
     "hsp2g_kernel_name": (C.c_char_p, [_h]),

@@ -84,10 +84,18 @@ struct hsp2g_batch {
     double *mon = nullptr;     // [tile][slot*12 + month][32]
     std::vector<double> h_mon; // host copy [slot][12][n_seg] (tables arrive one at a time)
     CalStep *cal = nullptr;
-    unsigned long long *d_counter = nullptr;  // task tickets (land_common.cuh Sched)
+    unsigned long long *d_counter = nullptr;  // [2] task tickets (land_common.cuh Sched); launches alternate between the two
     unsigned *d_progress = nullptr;           // [ntiles] sub-chunks completed
-    unsigned long long task_base = 0;
+    unsigned long long task_base[2] = {0, 0};
+    int ticket_slot = 0;
     unsigned prog_base = 0;
+    // hsp2g_set_launch_overlap: a launch may start while the previous launch of this batch (same stream, nothing enqueued in
+    // between) is still draining its last tasks
+    int overlap = 0;
+    cudaStream_t last_stream = nullptr;  // stream of the last launch
+    bool last_recorded = false;          // last_launch has been recorded for it (overlap mode records lazily)
+    bool last_full_grid = false;         // the last launch ran the batch's own kernel on a grid that fills the device
+    int64_t chained_launches = 0;
     int sub_steps = 64;
     int out_f32 = 0;
     int plain = 0;     // series layout of run_device / run_host: 0 = TILED [tile][t][row][32], 1 = PLAIN [t][row][ld]
@@ -211,8 +219,16 @@ int check_ready(const hsp2g_batch *b, int64_t t0, int32_t nsteps) {
 
 // the batch's kernels may run on a caller's stream (hsp2g_run_device): state and error rows are read / written only after the
 // last launch has finished, whatever stream it used
+int ensure_last_recorded(hsp2g_batch *b) {
+    if (b->have_last && !b->last_recorded) {
+        CU(cudaEventRecord(b->last_launch, b->last_stream));
+        b->last_recorded = true;
+    }
+    return 0;
+}
 int wait_last_launch(hsp2g_batch *b) {
     CU(cudaStreamSynchronize(b->comp));
+    if (ensure_last_recorded(b)) return 1;
     if (b->have_last) CU(cudaEventSynchronize(b->last_launch));
     return 0;
 }
@@ -257,6 +273,7 @@ struct Driver {
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **,
                              void **) = nullptr;
+    CUresult (*LaunchKernelEx)(const CUlaunchConfig *, CUfunction, void **, void **) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
     CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -276,6 +293,7 @@ const Driver &driver() {
                     {"cuFuncSetAttribute", (void **)&d.FuncSetAttribute},
                     {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void **)&d.OccupancyMaxActiveBlocksPerMultiprocessor},
                     {"cuLaunchKernel", (void **)&d.LaunchKernel},
+                    {"cuLaunchKernelEx", (void **)&d.LaunchKernelEx},
                     {"cuGetErrorString", (void **)&d.GetErrorString},
                     {"cuTensorMapEncodeTiled", (void **)&d.TensorMapEncodeTiled}};
         for (auto &w : want) {
@@ -371,9 +389,15 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
     return true;
 }
 
-int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid) {
+// may_chain: the previous launch of this batch went to the same stream on a full grid, and the caller allows overlap.
+// *full_grid: this launch fills the device (grid = resident blocks), so a chained successor can only become resident as this
+// launch's blocks exit: at most two launches of the batch are ever in flight, one per ticket counter.
+int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid, bool may_chain, bool *full_grid, bool *chained) {
     const unsigned block = (unsigned)b->jit.info[JI_BLOCK];  // the image's own block size (jit.py `block`)
     hsp2g_plan_tasks(L, b->sub_steps, b->jit.resident, (int)block / LAND_TILE, grid);
+    *full_grid = *grid == b->jit.resident;
+    *chained = may_chain && *full_grid;
+    L.chained = b->overlap ? 1 : 0;  // sub-chunk 0 of a tile also waits for the tile's previous launch (progress[tile])
 #ifdef HSP2G_HOST_EMU
     (void)st;
     for (unsigned blk = 0; blk < (unsigned)*grid; ++blk)
@@ -384,8 +408,29 @@ int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid) {
         }
 #else
     void *params[1] = {&L};
-    CUresult r = driver().LaunchKernel(b->jit.fn, (unsigned)*grid, 1, 1, block, 1, 1, (unsigned)b->jit.info[JI_SMEM], (CUstream)st,
-                                       params, nullptr);
+    CUresult r;
+    if (*chained) {
+        // programmatic dependent launch: the blocks of this grid may become resident as soon as every block of the previous
+        // kernel in the stream has started (ours call griddepcontrol.launch_dependents first thing), i.e. while that kernel's last
+        // tasks are still running.  Ordering between the two launches is per tile, through progress[tile] (land_common.cuh Sched).
+        CUlaunchAttribute attr[1];
+        memset(attr, 0, sizeof attr);
+        attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+        attr[0].value.programmaticStreamSerializationAllowed = 1;
+        CUlaunchConfig cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDimX = (unsigned)*grid;
+        cfg.gridDimY = cfg.gridDimZ = 1;
+        cfg.blockDimX = block;
+        cfg.blockDimY = cfg.blockDimZ = 1;
+        cfg.sharedMemBytes = (unsigned)b->jit.info[JI_SMEM];
+        cfg.hStream = (CUstream)st;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        r = driver().LaunchKernelEx(&cfg, b->jit.fn, params, nullptr);
+    } else
+        r = driver().LaunchKernel(b->jit.fn, (unsigned)*grid, 1, 1, block, 1, 1, (unsigned)b->jit.info[JI_SMEM], (CUstream)st, params,
+                                  nullptr);
     if (r != CUDA_SUCCESS) return fail("launch of the batch's own kernel failed: %s", cu_str(r));
 #endif
     b->kname = b->jit.name.c_str();
@@ -451,16 +496,22 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
         L.tmap_ok = make_tmap(L.tmap, d_forc, L.forc_f32 ? 4 : 8, forc_ld, b->nf, nsteps) ? 1 : 0;
 #endif
     const bool hourly = b->delt >= 60.0;
-    // launches of one batch share its ticket counter and state rows: each waits for the previous one, whatever its stream
-    if (b->have_last) CU(cudaStreamWaitEvent(st, b->last_launch, 0));
+    // launches of one batch share its state rows: each waits for the previous one, whatever its stream (stream order does it when
+    // the stream is the same; in overlap mode the event is recorded only when somebody needs it)
+    if (b->have_last && !(b->overlap && b->last_stream == st)) {
+        if (ensure_last_recorded(b)) return 1;
+        CU(cudaStreamWaitEvent(st, b->last_launch, 0));
+    }
+    const bool may_chain = b->overlap && b->have_last && b->last_stream == st && b->last_full_grid && !b->last_recorded && !b->timing;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (b->timing) {
         e0 = get_event(b);
         e1 = get_event(b);
         CU(cudaEventRecord(e0, st));
     }
-    L.task_counter = b->d_counter;
-    L.task_base = b->task_base;
+    const int slot = b->ticket_slot;
+    L.task_counter = b->d_counter + slot;
+    L.task_base = b->task_base[slot];
     L.progress = b->d_progress;
     L.prog_base = b->prog_base;
     int grid = 0;
@@ -468,8 +519,9 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
     int rc = 0;
     long long warps_per_block = LAND_WARPS;
     bool lockstep = false;
+    bool full_grid = false, chained = false;
     if (b->jit.on && jit_matches(b, L)) {
-        rc = launch_jit(b, L, st, &grid);
+        rc = launch_jit(b, L, st, &grid, may_chain, &full_grid, &chained);
         warps_per_block = (long long)b->jit.info[JI_BLOCK] / LAND_TILE;
         lockstep = (b->jit.info[JI_BITS] & JB_LOCKSTEP) != 0;
     } else {
@@ -486,16 +538,21 @@ int launch(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *d_forc, long 
     // every task draws one ticket and every warp one more (the draw that tells it to stop)
     // (lock-step kernels draw a block's tickets together: whole rounds of warps_per_block, and one last round per block)
     const unsigned long long tasks = (unsigned long long)L.ntiles * L.nsub;
-    b->task_base += (lockstep ? (tasks + warps_per_block - 1) / warps_per_block * warps_per_block : tasks) +
-                    (unsigned long long)grid * warps_per_block;
+    b->task_base[slot] += (lockstep ? (tasks + warps_per_block - 1) / warps_per_block * warps_per_block : tasks) +
+                          (unsigned long long)grid * warps_per_block;
+    b->ticket_slot ^= 1;
     b->prog_base += (unsigned)L.nsub;
     if (b->timing) {
         CU(cudaEventRecord(e1, st));
         b->pending.emplace_back(e0, e1);
     }
     // the state / error accessors and the next launch of this batch order themselves after this one, whatever stream it is on
-    CU(cudaEventRecord(b->last_launch, st));
+    b->last_stream = st;
+    b->last_full_grid = full_grid;
+    b->chained_launches += chained ? 1 : 0;
+    b->last_recorded = false;
     b->have_last = true;
+    if (!b->overlap && ensure_last_recorded(b)) return 1;
     b->launches += 1;
     return 0;
 }
@@ -753,7 +810,7 @@ int hsp2g_batch_create(int device, int operation, int64_t n_seg, uint32_t act, d
     }                                                                              \
     cudaMemset((ptr), 0, (bytes));
     ALLOC(b->segblk, np * SB_ROWS * sizeof(double));
-    ALLOC(b->d_counter, sizeof(unsigned long long));
+    ALLOC(b->d_counter, 2 * sizeof(unsigned long long));
     ALLOC(b->d_progress, (size_t)b->ntiles * sizeof(unsigned));
 #undef ALLOC
     ce = cudaStreamCreateWithFlags(&b->comp, cudaStreamNonBlocking);
@@ -1085,7 +1142,10 @@ int hsp2g_run_device_group(int32_t n_batches, hsp2g_batch *const *batches, int64
         last_on[(size_t)(i % ns_used)] = b;
     }
     for (int i = 0; i < ns_used; ++i)
-        if (last_on[(size_t)i] && batches[order[(size_t)i]]->comp != st) CU(cudaStreamWaitEvent(st, last_on[(size_t)i]->last_launch, 0));
+        if (last_on[(size_t)i] && batches[order[(size_t)i]]->comp != st) {
+            if (ensure_last_recorded(last_on[(size_t)i])) return 1;
+            CU(cudaStreamWaitEvent(st, last_on[(size_t)i]->last_launch, 0));
+        }
     return 0;
 }
 
@@ -1229,6 +1289,7 @@ int hsp2g_sync(hsp2g_batch *b) {
     CU(cudaStreamSynchronize(b->h2d));
     CU(cudaStreamSynchronize(b->comp));
     CU(cudaStreamSynchronize(b->d2h));
+    if (ensure_last_recorded(b)) return 1;
     if (b->have_last) CU(cudaEventSynchronize(b->last_launch));
     return drain_timing(b);
 }
@@ -1506,6 +1567,16 @@ int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps) {
     b->sub_steps = sub_steps;
     return 0;
 }
+
+int hsp2g_set_launch_overlap(hsp2g_batch *b, int on) {
+    if (!b) return fail("null batch");
+    DeviceGuard g(b->device);
+    if (wait_last_launch(b)) return 1;  // the switch is thrown between launches, never under one
+    b->overlap = on ? 1 : 0;
+    return 0;
+}
+
+int64_t hsp2g_chained_launches(const hsp2g_batch *b) { return b ? b->chained_launches : 0; }
 
 int hsp2g_set_timing(hsp2g_batch *b, int on) {
     if (!b) return fail("null batch");

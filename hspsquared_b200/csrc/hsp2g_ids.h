@@ -32,10 +32,13 @@
 /* ---- per-segment scalar parameters: par[P_x][segment], fp64 -------------------------------------- */
 /* derived columns (computed by the host with the reference's own expression order):
  *   MGMELT_IVL = MGMELT*delt/1440 (SNOW.py:146)   INFILT_IVL = INFILT*delt60 (PWATER.py:215)
- *   KGW = 1 - AGWRC**(delt60/24) (PWATER.py:247)   ELEVGC = ((288-0.00198*ELEV)/288)**5.256 (PWTGAS.py:95) */
+ *   KGW = 1 - AGWRC**(delt60/24) (PWATER.py:247)   ELEVGC = ((288-0.00198*ELEV)/288)**5.256 (PWTGAS.py:95)
+ *   the per-segment constant heads of three SNOW expressions, each the FIRST operation(s) of the reference's left-to-right
+ *   evaluation, so that hoisting them changes no bit:  MELEV_FAC = 1.0 - 0.3*MELEV/10000.0 (SNOW.py:360, one fp64 division per
+ *   interval with a pack otherwise),  SNOEVP_K = SNOEVP*0.0002 (SNOW.py:336),  CCFACT_K = CCFACT*0.00026 (SNOW.py:354) */
 #define HSP2G_PARAMS(X)                                                                                   \
     X(ELDAT)                                                                                              \
-    X(MELEV) X(SHADE) X(SNOWCF) X(COVIND) X(KMELT) X(TBASE) X(RDCSN) X(TSNOW) X(SNOEVP) X(CCFACT)         \
+    X(MELEV_FAC) X(SHADE) X(SNOWCF) X(COVIND) X(KMELT) X(TBASE) X(RDCSN) X(TSNOW) X(SNOEVP_K) X(CCFACT_K) \
     X(MWATER) X(MGMELT_IVL)                                                                               \
     X(FOREST) X(LZSN) X(INFILT_IVL) X(LSUR) X(SLSUR) X(KVARY) X(KGW) X(PETMAX) X(PETMIN) X(INFEXP)        \
     X(INFILD) X(DEEPFR) X(BASETP) X(AGWETP) X(CEPSC) X(UZSN) X(NSUR) X(INTFW) X(IRC) X(LZETP) X(FZG)      \

@@ -58,7 +58,7 @@
 // = 13.5 KB; 8 two-warp blocks (+1 KB system reservation each) fit the 228 KB of an SM = 16 resident warps at <= 128
 // registers (RDCSN, read only while it snows, stays in global memory: a 55th row would cost two warps).
 #define HOT_SNOW                                                                                                   \
-    (PBIT(TSNOW) | PBIT(SNOWCF) | PBIT(COVIND) | PBIT(SNOEVP) | PBIT(CCFACT) | PBIT(MELEV) |          \
+    (PBIT(TSNOW) | PBIT(SNOWCF) | PBIT(COVIND) | PBIT(SNOEVP_K) | PBIT(CCFACT_K) | PBIT(MELEV_FAC) |  \
      PBIT(SHADE) | PBIT(MWATER) | PBIT(MGMELT_IVL))
 #define HOT_PWATER                                                                                                 \
     (PBIT(INFILT_IVL) | PBIT(KVARY) | PBIT(LZSN) | PBIT(FOREST) | PBIT(PETMAX) | PBIT(PETMIN) | PBIT(FZG) |         \
@@ -126,6 +126,8 @@ struct LandLaunch {
     double ffill[HSP2G_NFORC];  // value read when the id is absent
     short srow[HSP2G_NOUT];     // output id -> row in out, or -1 (not saved)
     short mslot[HSP2G_NMON];    // monthly table id -> slot in mon, or -1
+    int chained;      // 1: the previous launch of this batch may still be running (hsp2g_set_launch_overlap): sub-chunk 0 of a tile
+                      // waits for progress[tile] like every other sub-chunk does
     int linked;       // 1: the forcing rows come from rowsrc (forc, forc_ld, tmap are unused)
     int src_tiles;    // linked: tiles of the source batch; this batch's tile q reads source tile q % src_tiles
     RowSource rowsrc[LAND_MAX_LINKED];
@@ -206,6 +208,24 @@ static __device__ __noinline__ double hsp_div(double a, double b) { return a / b
 #else
 #define HDIV(a, b) hsp_div((a), (b))
 #endif
+
+// a / C for the constants whose odd part is a small integer: three operations, same bits (const_div.h has the proof and the pin)
+#ifdef HSP2G_HOST_EMU
+static inline unsigned hsp_hi32(double x) {
+    unsigned long long u;
+    memcpy(&u, &x, 8);
+    return (unsigned)(u >> 32);
+}
+#define HSP_CDIV_DECL static inline
+#define HSP_CDIV_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#define HSP_CDIV_HI(x) hsp_hi32(x)
+#else
+#define HSP_CDIV_DECL static __device__ __forceinline__
+#define HSP_CDIV_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define HSP_CDIV_HI(x) __double2hiint(x)
+#endif
+#define HSP_CDIV_SLOW(a, c) hsp_div((a), (c))
+#include "const_div.h"
 
 // Python semantics: max(a,b) = b if b>a else a ; min(a,b) = b if b<a else a  
 __device__ __forceinline__ double py_max(double a, double b) { return b > a ? b : a; }
@@ -525,12 +545,18 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 struct Sched {
     const LandLaunch &L;
     int lane, c;
+    // first thing a block does: let the next kernel of the stream be scheduled as soon as every block of this one has started.  It
+    // matters only to a launch made with programmatic stream serialization (hsp2g_api.cu launch_jit, overlap mode): that launch's
+    // blocks then take the places this grid's blocks free as they run out of tickets, instead of waiting for its last task.
+    static __device__ __forceinline__ void release_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 #ifdef HSP_LOCKSTEP
     int wib;
     bool idle;
-    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int wib_) : L(l), lane(lane_), c(0), wib(wib_), idle(false) {}
+    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int wib_) : L(l), lane(lane_), c(0), wib(wib_), idle(false) {
+        release_dependents();
+    }
 #else
-    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int) : L(l), lane(lane_), c(0) {}
+    __device__ __forceinline__ Sched(const LandLaunch &l, int lane_, int) : L(l), lane(lane_), c(0) { release_dependents(); }
 #endif
     __device__ __forceinline__ bool next(int &tile, int &t0, int &t1) {
 #ifdef HSP_LOCKSTEP
@@ -557,7 +583,7 @@ struct Sched {
         tile = (int)(k - (unsigned long long)c * (unsigned)L.ntiles);
         t0 = c * L.sub;
         t1 = t0 + L.sub < L.nsteps ? t0 + L.sub : L.nsteps;
-        if (c > 0) {
+        if (c > 0 || L.chained) {
             if (lane == 0)
                 while ((int)(ld_acquire_u32(L.progress + tile) - (L.prog_base + (unsigned)c)) < 0) __nanosleep(256);
             __syncwarp();

@@ -117,7 +117,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
             rainf = 0.0;
             if (hrfg || fprfg) {
                 const double rdcsn = s.par(P_RDCSN);
-                const double a = HDIV(airtmp, 100.0);
+                const double a = hsp_div100(airtmp);
                 w.rdnsn = airtmp > 0.0 ? rdcsn + a * a : rdcsn;
             }
         } else {
@@ -132,7 +132,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
             if (w.skyclr > 1.0) w.skyclr = 1.0;
         }
     }
-    if (!snop && s.has_forcing(F_CLOUD)) w.skyclr = py_max(0.15, 1.0 - (s.forcing(F_CLOUD) / 10.0));
+    if (!snop && s.has_forcing(F_CLOUD)) w.skyclr = py_max(0.15, 1.0 - hsp_div10(s.forcing(F_CLOUD)));
 
     double prain, snowe, melt, wyield;
     if (w.packf > 0.0 || snowf > 0.0) {
@@ -174,7 +174,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
             if (iregfg) {
                 w.vap = svp_at(w.dewtmp);
                 const double satvap = svp_at(airtmp);
-                const double d = s.par(P_SNOEVP) * 0.0002 * winmov * (satvap - w.vap) * w.snocov;
+                const double d = s.par(P_SNOEVP_K) * winmov * (satvap - w.vap) * w.snocov;  // SNOEVP_K = SNOEVP * 0.0002
                 w.snowep = w.vap >= 6.108 ? 0.0 : d;
             }
             if (w.snowep >= w.packf) {
@@ -193,12 +193,12 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
 
         if (iregfg) {
             if (!snop) {  // ---- HEXCHR + ALBEDO (SNOW.py:353-377)
-                const double factr = s.par(P_CCFACT) * 0.00026 * winmov;
+                const double factr = s.par(P_CCFACT_K) * winmov;  // CCFACT_K = CCFACT * 0.00026
                 double d = 8.59 * (w.vap - 6.108);
                 const double condht = w.vap > 6.108 ? d * factr : 0.0;
-                d = reltmp * (1.0 - HDIV(0.3 * s.par(P_MELEV), 10000.0)) * factr;
+                d = reltmp * s.par(P_MELEV_FAC) * factr;  // MELEV_FAC = 1.0 - 0.3 * MELEV / 10000.0 (host, segstore.py)
                 const double convht = airtmp > 32.0 ? d : 0.0;
-                d = sqrt(HDIV(w.dull, 24.0));
+                d = sqrt(hsp_div24(w.dull));
                 const double summer = py_max(0.45, 0.80 - 0.10 * d);
                 const double winter = py_max(0.60, 0.85 - 0.07 * d);
                 w.albedo = (s.calfl & HSP2G_CAL_SEASON) ? summer : winter;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void snow_step(const SEG &s, SNOWSTATE &w, SnowFlux &
             } else  // ---- DEGDAY (SNOW.py:380); KMELT*delt/1440 as in SNOW.py:145
                 w.mostht = (s.daily(FB_M_KMELT, M_KMELT, P_KMELT) * delt / 1440.0) * (airtmp - s.par(P_TBASE));
         }
-        const double rnsht = rainf > 0.0 ? HDIV(reltmp * rainf, 144.0) : 0.0;
+        const double rnsht = rainf > 0.0 ? hsp_div144(reltmp * rainf) : 0.0;
         double sumht = w.mostht + rnsht;
         if (w.snocov < 1.0) sumht = sumht * w.snocov;
         w.paktmp = w.neghts <= 0.0 ? 32.0 : 32.0 - HDIV(w.neghts, 0.00695 * w.packf);

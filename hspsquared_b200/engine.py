@@ -572,6 +572,14 @@ class LandBatch:
         """Intervals per (tile, sub-chunk) task of one launch (include/hsp2g.h hsp2g_set_schedule); 0 = whole chunk."""
         _lib.check(self.lib.hsp2g_set_schedule(self.h, int(sub_steps)))
 
+    def set_launch_overlap(self, on=True):
+        """Let consecutive run_device calls on one stream overlap at their tails (include/hsp2g.h hsp2g_set_launch_overlap: the
+        buffers of a call must be ready when the previous call is enqueued, outputs distinct from the previous call's)."""
+        _lib.check(self.lib.hsp2g_set_launch_overlap(self.h, 1 if on else 0))
+
+    def chained_launches(self):
+        return int(self.lib.hsp2g_chained_launches(self.h))
+
     def kernel_stats(self):
         n = C.c_int64(0)
         ms = C.c_double(0.0)

@@ -397,12 +397,16 @@ class SegmentStore:
             return conv_init[name](v) if name in conv_init else v
 
         # ---- plain parameter columns
-        derived = {"MGMELT_IVL", "INFILT_IVL", "KGW", "ELEVGC"}
+        derived = {"MGMELT_IVL", "INFILT_IVL", "KGW", "ELEVGC", "MELEV_FAC", "SNOEVP_K", "CCFACT_K"}
         for name, row in st.P.items():
             if name not in derived:
                 st.par[row] = R(name)
         st.par[st.P["MGMELT_IVL"]] = R("MGMELT") * delt / 1440.0  # SNOW.py:146
         st.par[st.P["INFILT_IVL"]] = R("INFILT") * delt60  # PWATER.py:215
+        # per-segment constant heads of SNOW expressions (the first operations of the reference's left-to-right evaluation)
+        st.par[st.P["MELEV_FAC"]] = 1.0 - 0.3 * R("MELEV") / 10000.0  # SNOW.py:360  reltmp * (1.0 - 0.3 * melev / 10000.0) * factr
+        st.par[st.P["SNOEVP_K"]] = R("SNOEVP") * 0.0002  # SNOW.py:336  snoevp * 0.0002 * winmov * ...
+        st.par[st.P["CCFACT_K"]] = R("CCFACT") * 0.00026  # SNOW.py:354  ccfact * 0.00026 * winmov
         if metric:
             st.par[st.P["MGMELT_IVL"]] = st.par[st.P["MGMELT_IVL"]] / 25.4  # SNOW.py:159
             st.par[st.P["INFILT_IVL"]] = st.par[st.P["INFILT_IVL"]] * 0.0394  # PWATER.py:239

@@ -497,3 +497,45 @@ def test_groups_by_option_word_equal_the_mixed_batch(layout):
     """BASELINE configs[3] machinery: a full-chain ensemble with per-segment option flags as one batch (and one kernel built for
     its word) per option word, launched together on the device, equals the single mixed batch bit for bit (3,000 segments)."""
     parity.check_grouped_batch(n=3000, layout=layout, jit=True)
+
+
+@pytest.mark.parametrize("layout", ["plain", "tiled"])
+def test_overlapped_launches_are_bit_identical(layout):
+    """hsp2g_set_launch_overlap: consecutive launches of one batch overlap at their tails (programmatic dependent launch, per-tile
+    hand-over through progress[tile]).  100,000 segments = 3,125 tiles > resident warps, so the grid fills the device and the
+    launches really are chained; every saved value, the final state and the error counts equal the serialised run's."""
+    import torch
+
+    import bench
+    from hspsquared_b200 import synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    dev = torch.device("cuda", 0)
+    cal = Calendar("1976-02-10", "1976-03-05", 60, "ns")
+    n, Tc, chunks = 100_000, 96, 6
+    assert Tc * chunks <= cal.steps
+    ens = synth.Ensemble("PERLND", n, seed=21, sections=("SNOW", "PWATER"))
+    names = list(synth.PERLND_FORCINGS)
+    save = ["SNOW_PACKF", "SNOW_WYIELD", "PWATER_SURO", "PWATER_AGWS", "PWATER_UZS", "PWATER_PERO"]
+    stream = torch.cuda.Stream(dev)
+    results = []
+    for overlap in (True, False):
+        with LandBatch(ens.store(cal), cal, names, save, layout=layout, order=None) as b:
+            forc = [bench.device_forcing(torch, ens, cal, c * Tc, Tc, b.npad, dev, b.forcing_rows, layout) for c in range(chunks)]
+            outs = bench.out_buffers(torch, b.npad, Tc, b.ns, dev, layout, count=chunks)
+            b.set_schedule(32)
+            b.set_launch_overlap(overlap)
+            torch.cuda.synchronize(dev)
+            for c in range(chunks):
+                b.run_device(c * Tc, Tc, forc[c].data_ptr(), outs[c].data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize(dev)
+            assert ",jit>" in b.kernel_name()
+            assert b.chained_launches() == (chunks - 1 if overlap else 0)
+            results.append(([o.cpu().numpy() for o in outs], b.get_state(), b.errors()))
+            del forc, outs
+    (oa, sa, ea), (ob, sb, eb) = results
+    for a, b_ in zip(oa, ob):
+        assert np.array_equal(a, b_, equal_nan=True)
+    assert np.array_equal(sa, sb, equal_nan=True)
+    assert all(np.array_equal(ea[k], eb[k]) for k in ea)
