@@ -418,6 +418,8 @@ def main():
     ap.add_argument("--caller-order", action="store_true", help="keep the ensemble generator's segment order on the device "
                     "instead of the engine's automatic divergence-aware order")
     ap.add_argument("--no-ordered", action="store_true", help="skip the extra measurement in the other segment order")
+    ap.add_argument("--no-overlap", action="store_true", help="every launch waits for the previous one to end (default: consecutive "
+                    "launches of a batch overlap at their tails, hsp2g_set_launch_overlap)")
     ap.add_argument("--no-alt-layout", action="store_true", help="skip the extra measurement in the other series layout")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -426,6 +428,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
+    if args.no_overlap:
+        global OVERLAP
+        OVERLAP = False
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -617,6 +622,8 @@ def main():
                                     "week of the batch's forcings (LandBatch.climate_order)",
                    "cache": "inputs of every step (%.2f GB) and outputs (%.2f GB) are far larger than L2; %d distinct "
                             "forcing chunks resident" % (per_f / 1e9, Tc * ns * npad * 8 / 1e9, n_forcing_chunks),
+                   "launches": ("consecutive launches overlap at their tails (programmatic dependent launch, per-tile hand-over; "
+                                "hsp2g_set_launch_overlap)" if OVERLAP else "each launch waits for the previous one to end"),
                    "kernel": kname, "parallelism": "segments sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

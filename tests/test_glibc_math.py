@@ -47,3 +47,14 @@ def test_generated_tables_match_the_library(tmp_path):
     out = str(tmp_path / "glibc_tables.h")
     mod.main(out)
     assert open(out).read() == open(mod.OUT).read()
+
+
+def test_division_by_small_odd_part_constants_equals_ieee_division(tmp_path):
+    """csrc/const_div.h: a / 24, a / 100, a / 144 ... in three operations (the header carries the proof); pinned here against the
+    host's own division on 12 M arguments per constant -- any bit pattern, exact multiples and their neighbours, short decimals."""
+    exe = str(tmp_path / "const_div_check")
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-I", CSRC, os.path.join(ROOT, "tests", "const_div_check.c"),
+                    "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe, "12000000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert all(line.split()[1].startswith("0/") for line in r.stdout.strip().splitlines())
