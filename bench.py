@@ -879,7 +879,7 @@ def config_workload(name, n=None, seed=1234):
 
 
 def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=True, order="flags", K=20, W=3, Tc=None, sub=None,
-               dist=None, out_dtype=None, first_chunk=0, seed=1234):
+               dist=None, out_dtype=None, first_chunk=0, seed=1234, forcing_dtype=None):
     """One device-resident measurement of a named configuration (same rules as the headline: W >= 3 warm-up launches, CUDA events
     on the launching stream, inputs of every launch far larger than L2 and distinct from the previous launch's).
     order: None | "flags" (option word) | "climate" (option word, then the climate key LandBatch.climate_order derives from the
@@ -916,6 +916,9 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
             batch.set_schedule(sub)
         if out_dtype is not None:
             batch.set_output_dtype(out_dtype)
+        f32in = forcing_dtype is not None and np.dtype(forcing_dtype).itemsize == 4 and not grouped
+        if f32in:
+            batch.set_forcing_dtype(np.float32)
         nf, ns = batch.nf, batch.ns
         osz = 4 if out_dtype is not None and np.dtype(out_dtype).itemsize == 4 else 8
         if grouped:
@@ -931,7 +934,8 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
                 forc.append(big)
         else:
             npad = batch.npad
-            forc = [device_forcing(torch, ens, cal, (first_chunk + c) * Tc, Tc, npad, dev, batch.forcing_rows, layout) for c in range(K + W)]
+            forc = [device_forcing(torch, ens, cal, (first_chunk + c) * Tc, Tc, npad, dev, batch.forcing_rows, layout,
+                                   torch.float32 if f32in else None) for c in range(K + W)]
         outs = out_buffers(torch, npad, Tc, ns, dev, layout, torch.float32 if osz == 4 else None)
         torch.cuda.synchronize(dev)
         ms = time_device(torch, batch, forc, outs, Tc, K, W, stream, dev, dist, first=0) if first_chunk == 0 else None
@@ -948,7 +952,7 @@ def run_config(torch, dev, name, cal, stream, peak, n=None, layout="plain", jit=
             e1.record(stream)
             torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1)
-        B = 8 * nf + osz * ns
+        B = (4 if f32in else 8) * nf + osz * ns
         value = n * Tc * K / (ms * 1e-3)
         errs = {k: int((v != 0).sum()) for k, v in batch.errors().items() if (v != 0).any()}
         return {"config": name, "workload": note, "segments": n, "intervals_per_step": Tc, "steps": K, "warmup": W,

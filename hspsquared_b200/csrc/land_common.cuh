@@ -79,6 +79,18 @@ struct __align__(32) CalStep {
     uint8_t pad[5];
 };
 
+// cache policy of the saved-series stores: streaming (evict-first) by default; HSP_STORE_POLICY is a measurement switch
+// (1 = ordinary write-back, 2 = .cg, 3 = write-through), profiles/README.md
+#if !defined(HSP_STORE_POLICY) || HSP_STORE_POLICY == 0 || defined(HSP2G_HOST_EMU)
+#define HSP_STORE(p, v) __stcs((p), (v))
+#elif HSP_STORE_POLICY == 1
+#define HSP_STORE(p, v) (*(p) = (v))
+#elif HSP_STORE_POLICY == 2
+#define HSP_STORE(p, v) __stcg((p), (v))
+#else
+#define HSP_STORE(p, v) __stwt((p), (v))
+#endif
+
 // Linked forcing rows (hsp2g_run_device_linked): row r of interval t of this batch's tile q is the 256 bytes at
 // base + t * t_stride + (q % src_tiles) * tile_stride -- a row of ANOTHER batch's device buffer, read in place.
 #define LAND_MAX_LINKED 16
@@ -819,9 +831,9 @@ struct Seg {
         unsigned char *q = outp + ((LAY::STATIC && !LAY::PLAIN) ? (unsigned long long)(r * LAND_TILE * (out_is_f32() ? 4 : 8))
                                                                  : (unsigned long long)(unsigned)r * (unsigned long long)out_row);
         if (out_is_f32())
-            __stcs(reinterpret_cast<float *>(q), (float)v);
+            HSP_STORE(reinterpret_cast<float *>(q), (float)v);
         else
-            __stcs(reinterpret_cast<double *>(q), v);
+            HSP_STORE(reinterpret_cast<double *>(q), v);
     }
     // forcing row r of the current interval (this lane's segment), widened when the series are float32
     __device__ __forceinline__ double stage_row(int r) const {

@@ -221,8 +221,11 @@ def source(spec, maxreg, kind=None):
               "#else",
               "// register cap %d through the resident-blocks bound (__maxnreg__ cannot be combined with __launch_bounds__ on a"
               " non-template kernel)" % maxreg,
-              'extern "C" __global__ void __launch_bounds__(LAND_BLOCK, %d) %s(const __grid_constant__ LandLaunch L) { %s }'
-              % (max(1, 65536 // (block * maxreg)), ENTRY, body),
+              ('extern "C" __global__ void __launch_bounds__(LAND_BLOCK, %d) %s(const __grid_constant__ LandLaunch L) { %s }'
+               % (max(1, 65536 // (block * maxreg)), ENTRY, body)) if not os.environ.get("HSP2G_JIT_MAXNREG") else
+              ('extern "C" __global__ void %s(const __grid_constant__ LandLaunch L) { %s } // cap %d'
+               % (ENTRY, body, maxreg)),  # measurement switch: an exact cap through -maxrregcount (_compile) -- the resident-blocks
+                                          # bound only reaches 128, 96, 80 ...
               'extern "C" __device__ const unsigned long long %s_info[JI_N] = %s;' % (ENTRY, info),
               "#endif", ""]
     return "\n".join(lines)
@@ -239,6 +242,8 @@ def _compile(text, out, kind, maxreg=128):
         if not nvcc:
             raise RuntimeError("nvcc not found")
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("HSP2G_JIT_FLAGS", "").split() + ["-I", CSRC, "-cubin", src, "-o", tmp]
+        if os.environ.get("HSP2G_JIT_MAXNREG"):
+            cmd += ["-maxrregcount", str(maxreg)]
     else:  # host double (tests/emu): same text, g++, linked against the double for its thread-index globals
         from tests.emu import build_emu
 

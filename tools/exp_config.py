@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--segments", type=int, default=None)
     ap.add_argument("--first-chunk", type=int, default=0)
     ap.add_argument("--f32out", action="store_true")
+    ap.add_argument("--f32in", action="store_true")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -45,7 +46,8 @@ def main():
                 try:
                     r = B.run_config(torch, dev, name, cal, stream, peak, n=a.segments, layout=layout, jit=not a.no_jit,
                                      order=None if order == "none" else order, K=a.steps, W=a.warmup, Tc=a.chunk, sub=a.sub,
-                                     out_dtype=np.float32 if a.f32out else None, first_chunk=a.first_chunk)
+                                     out_dtype=np.float32 if a.f32out else None, first_chunk=a.first_chunk,
+                                     forcing_dtype=np.float32 if a.f32in else None)
                 except Exception as ex:
                     r = {"config": name, "layout": layout, "order": order, "error": repr(ex)}
                 print(json.dumps(r), flush=True)
