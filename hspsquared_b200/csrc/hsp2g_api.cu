@@ -1169,7 +1169,10 @@ int hsp2g_run_host_ld(hsp2g_batch *b, int64_t t0, int32_t nsteps, const void *h_
             s.forc = nullptr;
             s.cap_f = 0;
             CU(cudaMalloc((void **)&s.forc, need_f));
-            CU(cudaMemset(s.forc, 0, need_f));  // PLAIN: columns past n_seg of the last tile are never copied in; they read 0
+            // PLAIN: columns past n_seg of the last tile are never copied in; they read 0.  On the copy-in stream: the batch's
+            // streams do not synchronise with the default stream, where a plain cudaMemset of device memory runs asynchronously
+            // and could land AFTER the chunk's copy-in (seen on small batches: a group's forcings zeroed under its kernel)
+            CU(cudaMemsetAsync(s.forc, 0, need_f, b->h2d));
             s.cap_f = need_f;
         }
         if (need_o > s.cap_o) {
@@ -1314,8 +1317,10 @@ int hsp2g_reset_errors(hsp2g_batch *b) {
     if (!b) return fail("null batch");
     DeviceGuard g(b->device);
     if (wait_last_launch(b)) return 1;
-    CU(cudaMemset2D(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
-                    (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles));
+    // on the compute stream, where the next launch goes (the default stream does not order itself with the batch's streams)
+    CU(cudaMemset2DAsync(b->segblk + (size_t)SB_ERR * LAND_TILE, (size_t)SB_ROWS * LAND_TILE * 8, 0,
+                         (size_t)HSP2G_NERR * LAND_TILE * 8, (size_t)b->ntiles, b->comp));
+    CU(cudaStreamSynchronize(b->comp));
     return 0;
 }
 

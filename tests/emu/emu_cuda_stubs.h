@@ -67,6 +67,10 @@ inline cudaError_t cudaMemset2D(void *p, size_t pitch, int v, size_t w, size_t h
     for (size_t r = 0; r < h; ++r) memset((char *)p + r * pitch, v, w);
     return cudaSuccess;
 }
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { return cudaMemset(p, v, n); }
+inline cudaError_t cudaMemset2DAsync(void *p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
+    return cudaMemset2D(p, pitch, v, w, h);
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
