@@ -322,6 +322,45 @@ def build_cases():
     add("i001_metric", "IMPLND", ti, "implnd", units=2)
     fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}
     add("flowtest_pwater_metric", "PERLND", fp, "flowtest", steps=8760, year=2018, units=2)
+
+    # -- metric units in the other sections (SEDMNT.py:113-117,258-262; PSTEMP.py:80-126,136-149,205-215; PWTGAS.py:90-94,167-174,
+    #    310-350; SOLIDS.py:84-88,143-145; IWTGAS.py:80-82,111-114,160-163,179-182): again the English tables read as metric
+    #    values.  The full CBP chain (TSOPFG=1 tables, method-1 washoff, lateral inflows with concentrations); the TSOPFG=0 /
+    #    VSIVFG=2 / method-2 variant WITHOUT a PSTEMP initial-state table (the 16 deg C defaults of PSTEMP.py:80-88); the IMPLND
+    #    chain with monthly accumulation and regression tables; SOLIDS / IWTGAS on external runoff series ----------------
+    t = _cbp_tables()
+    t["PWTGAS"]["PARAMETERS"].update({"SLIFAC": 0.5, "ILIFAC": 0.3, "ALIFAC": 0.2})
+    t["PSTEMP"]["STATES"] = {"AIRTC": 5.0, "SLTMP": 4.0, "ULTMP": 6.0, "LGTMP": 8.0}
+    add("cbp_fullchain_metric", "PERLND", t, "perlnd", gatmp=2.0, units=2,
+        lateral=("SURLI", "UZLI", "IFWLI", "LZLI", "AGWLI", "SLSED"),
+        lateral_conc={"SLITMP": (2., 20.), "SLIDOX": (4., 12.), "SLICO2": (0., .2), "ILITMP": (2., 20.),
+                      "ILIDOX": (4., 12.), "ILICO2": (0., .2), "ALITMP": (4., 15.), "ALIDOX": (3., 9.),
+                      "ALICO2": (0., .2)})
+    t = _cbp_tables()
+    t["PWATER"]["PARAMETERS"].update({"RTOPFG": 0, "UZFG": 1, "VLEFG": 2, "KVARY": 0.0, "BASETP": 0.15})
+    t["SEDMNT"]["PARAMETERS"].update({"SDOPFG": 0, "VSIVFG": 2, "KGER": 0.3, "JGER": 1.5})
+    t["PSTEMP"]["PARAMETERS"].update({"TSOPFG": 0, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5,
+                                      "BSLT": 0.365, "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0})
+    t["PWTGAS"]["PARAMETERS"].update({"IDVFG": 0, "GDVFG": 0, "ICVFG": 1, "GCVFG": 1, "IDOXP": 6.0, "ADOXP": 5.0})
+    t["PWTGAS"]["MONTHLY_ICO2P"] = monthly([.05, .05, .06, .07, .08, .1, .12, .12, .1, .08, .06, .05])
+    t["PWTGAS"]["MONTHLY_ACO2P"] = monthly([.04, .04, .05, .05, .06, .07, .08, .08, .07, .06, .05, .04])
+    add("chain_uzfg_newton_metric", "PERLND", t, "perlnd", drop=("CLOUD",), gatmp=-1.5, rain_mult=3.0, units=2)
+    t = test10.implnd()
+    t["ACTIVITY"].update({"ATEMP": 1, "IWTGAS": 1})
+    t["ATEMP"] = {"PARAMETERS": {"ELDAT": 120.0, "AIRTMP": 30.0}}
+    t["SOLIDS"]["PARAMETERS"].update({"SDOPFG": 1, "VASDFG": 1, "VRSDFG": 1, "KEIM": 0.3, "JEIM": 1.4})
+    t["SOLIDS"]["MONTHLY_ACCSDP"] = monthly([.004, .004, .006, .01, .012, .014, .014, .012, .01, .008, .006, .004])
+    t["SOLIDS"]["MONTHLY_REMSDP"] = monthly([.03, .03, .04, .05, .06, .07, .07, .06, .05, .04, .03, .03])
+    t["IWTGAS"]["PARAMETERS"].update({"WTFVFG": 1, "SLIFAC": 0.4, "ELEV": 380.0})
+    t["IWTGAS"]["STATES"] = {"SOTMP": 15.0, "SODOX": 0.0, "SOCO2": 0.0}
+    t["IWTGAS"]["MONTHLY_AWTF"] = monthly([1., 2., 3., 7., 11., 16., 19., 18., 14., 9., 4., 2.])
+    t["IWTGAS"]["MONTHLY_BWTF"] = monthly([.3, .3, .35, .4, .45, .5, .5, .5, .45, .4, .35, .3])
+    add("i_chain_metric", "IMPLND", t, "implnd", gatmp=1.0, drop=("CLOUD",), rain_mult=2.5, lateral=("SURLI",),
+        lateral_conc={"SLITMP": (2., 20.), "SLIDOX": (4., 12.)}, units=2)
+    t = test10.implnd()
+    t["ACTIVITY"].update({"SNOW": 0, "IWATER": 0, "IWTGAS": 1})
+    t["IWTGAS"]["STATES"] = {"SOTMP": 15.0, "SODOX": 0.0, "SOCO2": 0.0}
+    add("i_solids_iwtgas_alone_metric", "IMPLND", t, "implnd", steps=24 * 120, runoff_inputs=True, units=2)
     return C
 
 

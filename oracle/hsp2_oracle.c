@@ -1011,9 +1011,11 @@ void hsp2o_sedmnt(const sedmnt_ui *ui, const sedmnt_in *in, const sedmnt_out *ou
     const int SDOPFG = ui->SDOPFG != 0.0, CSNOFG = (int)ui->CSNOFG;
     const double smpf = ui->SMPF, krer = ui->KRER, jrer = ui->JRER, affix = ui->AFFIX, kser = ui->KSER,
                  jser = ui->JSER, kger = ui->KGER, jger = ui->JGER;
+    const int metric = ui->uunits == 2.0; /* SEDMNT.py:60,113-117: NVSI series, SURO / SURS (the wrapper) and DETS on entry */
     double nvsi = ui->NVSI * delt / 1440.;
     double cover = in->COVERI[0];
     double dets = ui->DETS;
+    if (metric) dets = dets * 1.10231 / 2.471;
     int drydfg = 1;
     double wssd = 0.0, scrsd = 0.0, sosed = 0.0;
 
@@ -1035,6 +1037,7 @@ void hsp2o_sedmnt(const sedmnt_ui *ui, const sedmnt_in *in, const sedmnt_out *ou
         }
         if (dayfg) { /* SEDMNT.py:175-179 */
             nvsi = in->NVSI[t] * delt / 1440.;
+            if (metric) nvsi = nvsi * 2.205 / 2.471; /* SEDMNT.py:79,114: NVSI = ts['NVSI'] * delt / 1440., then * 2.205 / 2.471 */
             if (VSIVFG == 2 && drydfg) {
                 double d = nvsi * (1440. / delt);
                 dets = dets + d;
@@ -1090,48 +1093,57 @@ void hsp2o_sedmnt(const sedmnt_ui *ui, const sedmnt_in *in, const sedmnt_out *ou
         out->SCRSD[t] = scrsd;
         out->SOSED[t] = sosed;
         out->COVER[t] = cover;
+        if (metric) { /* SEDMNT.py:258-262: the stored series only */
+            out->DETS[t] = dets / 1.10231 * 2.471;
+            out->WSSD[t] = wssd / 1.10231 * 2.471;
+            out->SCRSD[t] = scrsd / 1.10231 * 2.471;
+            out->SOSED[t] = sosed / 1.10231 * 2.471;
+        }
     }
 }
 
 /* ============================================================================================== */
-/* PSTEMP  (PSTEMP.py:62-217), English units                                                       */
+/* PSTEMP  (PSTEMP.py:62-217); metric (uunits == 2): states and tables are deg C already, AIRTMP is  */
+/* taken to Celsius as an array on entry (:110-111), nothing is converted back on exit (:205-215)     */
 /* ============================================================================================== */
 void hsp2o_pstemp(const pstemp_ui *ui, const pstemp_in *in, const pstemp_out *out, int64_t nsteps,
                   int64_t *errors) {
     for (int i = 0; i < HSP2O_NERR_PSTEMP; ++i) errors[i] = 0;
     const double TSOPFG = ui->TSOPFG; /* float compare in the reference */
     const int AIRTFG = (int)ui->AIRTFG;
-    double airtc = (ui->AIRTC - 32.0) * 0.555;
-    double sltmp = (ui->SLTMP - 32.0) * 0.555;
-    double ultmp = (ui->ULTMP - 32.0) * 0.555;
-    double lgtmp = (ui->LGTMP - 32.0) * 0.555;
-    double airts = in->AIRTMP[0];
+    const int metric = ui->uunits == 2.0; /* PSTEMP.py:70 */
+    double airtc = metric ? ui->AIRTC : (ui->AIRTC - 32.0) * 0.555; /* PSTEMP.py:97-101 */
+    double sltmp = metric ? ui->SLTMP : (ui->SLTMP - 32.0) * 0.555;
+    double ultmp = metric ? ui->ULTMP : (ui->ULTMP - 32.0) * 0.555;
+    double lgtmp = metric ? ui->LGTMP : (ui->LGTMP - 32.0) * 0.555;
+    /* metric: AIRTMP = (AIRTMP - 32.0) * 0.555 as an array (:110-111), airts = AIRTMP[0] of THAT array (:128) */
+    double airts = metric ? (in->AIRTMP[0] - 32.0) * 0.555 : in->AIRTMP[0];
     (void)airtc;
 
     for (int64_t t = 0; t < nsteps; ++t) {
         const int hrfg = (int)(int64_t)in->HRFG[t];
-        const double airtmp = in->AIRTMP[t];
-        const double airtcs = (airts - 32.0) * 0.555;
-        airtc = (airtmp - 32.0) * 0.555;
+        const double airtmp = metric ? (in->AIRTMP[t] - 32.0) * 0.555 : in->AIRTMP[t];
+        const double airtcs = metric ? airts : (airts - 32.0) * 0.555; /* PSTEMP.py:136-142 */
+        airtc = metric ? airtmp : (airtmp - 32.0) * 0.555;
         if (hrfg) {
-            double aslt = (in->ASLT[t] - 32.0) * 0.555;
+            double aslt = metric ? in->ASLT[t] : (in->ASLT[t] - 32.0) * 0.555; /* PSTEMP.py:146-149 */
             double bslt = in->BSLT[t];
             sltmp = aslt + bslt * airtc;
         }
         if (TSOPFG == 1) {
             if (hrfg) {
-                double ault = (in->ULTP1[t] - 32.0) * 0.5555; /* PSTEMP.py:122 */
+                double ault = metric ? in->ULTP1[t] : (in->ULTP1[t] - 32.0) * 0.5555; /* PSTEMP.py:120-122 */
                 double bult = in->ULTP2[t];
                 ultmp = ault + bult * airtc;
-                lgtmp = (in->LGTP1[t] - 32.0) * 0.5555; /* PSTEMP.py:123 */
+                lgtmp = metric ? in->LGTP1[t] : (in->LGTP1[t] - 32.0) * 0.5555; /* PSTEMP.py:123 */
             }
         } else {
             double ulsmo = in->ULTP1[t];
-            double ultdif = 0.555 * in->ULTP2[t]; /* PSTEMP.py:125 */
+            double ultdif = metric ? in->ULTP2[t] : 0.555 * in->ULTP2[t]; /* PSTEMP.py:125 */
             double ultmps = ultmp;
             ultmp = ultmps + ulsmo * (airtcs + ultdif - ultmps);
             double lgsmo = in->LGTP1[t];
-            double lgtdif = 0.555 * in->LGTP2[t]; /* PSTEMP.py:126 */
+            double lgtdif = metric ? in->LGTP2[t] : 0.555 * in->LGTP2[t]; /* PSTEMP.py:126 */
             double lgtmps = lgtmp;
             if (TSOPFG == 0)
                 lgtmp = lgtmps + lgsmo * (airtcs + lgtdif - lgtmps);
@@ -1146,20 +1158,22 @@ void hsp2o_pstemp(const pstemp_ui *ui, const pstemp_in *in, const pstemp_out *ou
         if (lgtmp > 100) { lgtmp = 100; errors[5] += 1; }
         if (AIRTFG == 0) airts = airtmp;
 
-        out->AIRTC[t] = (airtc * 9.0 / 5.0) + 32.0;
-        out->SLTMP[t] = (sltmp * 9.0 / 5.0) + 32.0;
-        out->ULTMP[t] = (ultmp * 9.0 / 5.0) + 32.0;
-        out->LGTMP[t] = (lgtmp * 9.0 / 5.0) + 32.0;
+        out->AIRTC[t] = metric ? airtc : (airtc * 9.0 / 5.0) + 32.0; /* PSTEMP.py:205-215 */
+        out->SLTMP[t] = metric ? sltmp : (sltmp * 9.0 / 5.0) + 32.0;
+        out->ULTMP[t] = metric ? ultmp : (ultmp * 9.0 / 5.0) + 32.0;
+        out->LGTMP[t] = metric ? lgtmp : (lgtmp * 9.0 / 5.0) + 32.0;
     }
 }
 
 /* ============================================================================================== */
-/* PWTGAS  (PWTGAS.py:65-352), English units                                                       */
+/* PWTGAS  (PWTGAS.py:65-352); metric (uunits == 2): ELEV, the soil temperatures and the flows are    */
+/* converted on entry by the wrapper (:90-95,167-174), the stored series here (:310-350)              */
 /* ============================================================================================== */
 void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *out, int64_t nsteps) {
     const int CSNOFG = (int)ui->CSNOFG;
     const double slifac = ui->SLIFAC, ilifac = ui->ILIFAC, alifac = ui->ALIFAC;
     const double gdvfg = ui->GDVFG;
+    const int metric = ui->uunits == 2.0;
     const double elevgc = pow((288.0 - 0.00198 * ui->ELEV) / 288.0, 5.256);
     const double EFACTA = 407960., MFACTA = 0.2266;
 
@@ -1242,9 +1256,9 @@ void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *ou
         double soco2m = soco2 * suro * MFACTA, ioco2m = ioco2 * ifwo * MFACTA, aoco2m = aoco2 * agwo * MFACTA;
         out->POCO2M[t] = soco2m + ioco2m + aoco2m;
 
-        out->SOTMP[t] = sotmp > -1e28 ? (sotmp * 9.0 / 5.0) + 32.0 : sotmp;
-        out->IOTMP[t] = iotmp > -1e28 ? (iotmp * 9.0 / 5.0) + 32.0 : iotmp;
-        out->AOTMP[t] = aotmp > -1e28 ? (aotmp * 9.0 / 5.0) + 32.0 : aotmp;
+        out->SOTMP[t] = (sotmp > -1e28 && !metric) ? (sotmp * 9.0 / 5.0) + 32.0 : sotmp;
+        out->IOTMP[t] = (iotmp > -1e28 && !metric) ? (iotmp * 9.0 / 5.0) + 32.0 : iotmp;
+        out->AOTMP[t] = (aotmp > -1e28 && !metric) ? (aotmp * 9.0 / 5.0) + 32.0 : aotmp;
         out->SODOX[t] = sodox;
         out->SOCO2[t] = soco2;
         out->IODOX[t] = iodox;
@@ -1260,11 +1274,26 @@ void hsp2o_pwtgas(const pwtgas_ui *ui, const pwtgas_in *in, const pwtgas_out *ou
         out->IOCO2M[t] = ioco2m;
         out->AODOXM[t] = aodoxm;
         out->AOCO2M[t] = aoco2m;
+        if (metric) { /* PWTGAS.py:338-350 */
+            out->SOHT[t] = out->SOHT[t] / 3.96567 * 2.471;
+            out->IOHT[t] = out->IOHT[t] / 3.96567 * 2.471;
+            out->AOHT[t] = out->AOHT[t] / 3.96567 * 2.471;
+            out->POHT[t] = out->POHT[t] / 3.96567 * 2.471;
+            out->SODOXM[t] = out->SODOXM[t] / 2.205 * 2.471;
+            out->SOCO2M[t] = out->SOCO2M[t] / 2.205 * 2.471;
+            out->IODOXM[t] = out->IODOXM[t] / 2.205 * 2.471;
+            out->IOCO2M[t] = out->IOCO2M[t] / 2.205 * 2.471;
+            out->AODOXM[t] = out->AODOXM[t] / 2.205 * 2.471;
+            out->AOCO2M[t] = out->AOCO2M[t] / 2.205 * 2.471;
+            out->PODOXM[t] = out->PODOXM[t] / 2.205 * 2.471;
+            out->POCO2M[t] = out->POCO2M[t] / 2.205 * 2.471;
+        }
     }
 }
 
 /* ============================================================================================== */
-/* SOLIDS  (SOLIDS.py:52-146), IMPLND, English units.  SLSLD is read by the reference but unused.   */
+/* SOLIDS  (SOLIDS.py:52-146), IMPLND.  SLSLD is read by the reference but unused.  Metric: every    */
+/* conversion is elementwise on entry / exit (:84-88,143-145) and lives in oracle/wrappers.py          */
 /* ============================================================================================== */
 void hsp2o_solids(const solids_ui *ui, const solids_in *in, const solids_out *out, int64_t nsteps) {
     const double delt60 = ui->delt60, keim = ui->KEIM, jeim = ui->JEIM;
@@ -1312,13 +1341,14 @@ void hsp2o_solids(const solids_ui *ui, const solids_in *in, const solids_out *ou
 }
 
 /* ============================================================================================== */
-/* IWTGAS  (IWTGAS.py:65-183), IMPLND, English units                                               */
+/* IWTGAS  (IWTGAS.py:65-183), IMPLND; metric: entry conversions in the wrapper, SOTMP stays deg C   */
 /* ============================================================================================== */
 void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *out, int64_t nsteps) {
     const double EFACTA = 407960., MFACTA = 0.2266;
     const double slifac = ui->SLIFAC;
     double sotmp = ui->SOTMP, sodox = ui->SODOX, soco2 = ui->SOCO2;
     const double elevgc = pow((288.0 - 0.00198 * ui->ELEV) / 288.0, 5.256);
+    const int metric = ui->uunits == 2.0;
     double awtf = in->AWTF[0], bwtf = in->BWTF[0]; /* raw until the first DAYFG interval (IWTGAS.py:119-120) */
     for (int64_t t = 0; t < nsteps; ++t) {
         const double airtc = (in->AIRTMP[t] - 32.0) * 0.555;
@@ -1345,7 +1375,7 @@ void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *ou
             out->SOHT[t] = sotmp * suro * EFACTA;
             out->SODOXM[t] = sodox * suro * MFACTA;
             out->SOCO2M[t] = soco2 * suro * MFACTA;
-            out->SOTMP[t] = (sotmp * 9.0 / 5.0) + 32.0;
+            out->SOTMP[t] = metric ? sotmp : (sotmp * 9.0 / 5.0) + 32.0; /* IWTGAS.py:160-163 */
             out->SODOX[t] = sodox;
             out->SOCO2[t] = soco2;
         } else {
@@ -1358,6 +1388,11 @@ void hsp2o_iwtgas(const iwtgas_ui *ui, const iwtgas_in *in, const iwtgas_out *ou
             out->SOTMP[t] = sotmp;
             out->SODOX[t] = sodox;
             out->SOCO2[t] = soco2;
+        }
+        if (metric) { /* IWTGAS.py:179-182 */
+            out->SOHT[t] = out->SOHT[t] / 3.96567 * 2.471;
+            out->SODOXM[t] = out->SODOXM[t] / 2.205 * 2.471;
+            out->SOCO2M[t] = out->SOCO2M[t] / 2.205 * 2.471;
         }
     }
 }

@@ -68,17 +68,17 @@ extern "C" {
 
 /* ---- SEDMNT --------------------------------------------------------------------------------- */
 #define SEDMNT_UI(X) X(delt) X(VSIVFG) X(SDOPFG) X(CSNOFG) X(SMPF) X(KRER) X(JRER) X(AFFIX) X(NVSI) \
-    X(KSER) X(JSER) X(KGER) X(JGER) X(DETS)
+    X(KSER) X(JSER) X(KGER) X(JGER) X(DETS) X(uunits)
 #define SEDMNT_IN(X) X(COVERI) X(NVSI) X(RAIN) X(PREC) X(SLSED) X(SNOCOV) X(SURO) X(SURS) X(DAYFG)
 #define SEDMNT_OUT(X) X(DETS) X(WSSD) X(SCRSD) X(SOSED) X(COVER)
 
 /* ---- PSTEMP --------------------------------------------------------------------------------- */
-#define PSTEMP_UI(X) X(TSOPFG) X(AIRTFG) X(AIRTC) X(SLTMP) X(ULTMP) X(LGTMP)
+#define PSTEMP_UI(X) X(TSOPFG) X(AIRTFG) X(AIRTC) X(SLTMP) X(ULTMP) X(LGTMP) X(uunits)
 #define PSTEMP_IN(X) X(AIRTMP) X(ASLT) X(BSLT) X(ULTP1) X(ULTP2) X(LGTP1) X(LGTP2) X(HRFG)
 #define PSTEMP_OUT(X) X(AIRTC) X(SLTMP) X(ULTMP) X(LGTMP)
 
 /* ---- PWTGAS --------------------------------------------------------------------------------- */
-#define PWTGAS_UI(X) X(CSNOFG) X(SLIFAC) X(ILIFAC) X(ALIFAC) X(ELEV) X(GDVFG)
+#define PWTGAS_UI(X) X(CSNOFG) X(SLIFAC) X(ILIFAC) X(ALIFAC) X(ELEV) X(GDVFG) X(uunits)
 #define PWTGAS_IN(X) X(IDOXP) X(ICO2P) X(ADOXP) X(ACO2P) X(WYIELD) X(SURO) X(IFWO) X(AGWO) X(SURLI) \
     X(IFWLI) X(AGWLI) X(SLTMP) X(ULTMP) X(LGTMP) X(SLITMP) X(SLIDOX) X(SLICO2) X(ILITMP) X(ILIDOX) \
     X(ILICO2) X(ALITMP) X(ALIDOX) X(ALICO2) X(DAYFG)
@@ -92,7 +92,7 @@ extern "C" {
 #define SOLIDS_OUT(X) X(SOSLD) X(SLDS)
 
 /* ---- IWTGAS (IMPLND) ------------------------------------------------------------------------- */
-#define IWTGAS_UI(X) X(SLIFAC) X(SOTMP) X(SODOX) X(SOCO2) X(ELEV)
+#define IWTGAS_UI(X) X(SLIFAC) X(SOTMP) X(SODOX) X(SOCO2) X(ELEV) X(uunits)
 #define IWTGAS_IN(X) X(AIRTMP) X(WYIELD) X(SURO) X(SURLI) X(SLITMP) X(SLIDOX) X(SLICO2) X(AWTF) X(BWTF) X(DAYFG)
 #define IWTGAS_OUT(X) X(SOTMP) X(SODOX) X(SOCO2) X(SOHT) X(SODOXM) X(SOCO2M)
 

@@ -125,14 +125,15 @@ def _sedmnt_(ui, ts):
             ts[n] = np.zeros(int(ui["simlen"]))
     ts["_RAIN"] = ts["RAINF"] if "RAINF" in ts else ts["PREC"]  # SEDMNT.py:86-89
     e = _run("sedmnt", ui, ts, int(ui["simlen"]), None, in_alias={"RAIN": "_RAIN"},
-             ui_defaults={"VSIVFG": 0, "SDOPFG": 0})
+             ui_defaults={"VSIVFG": 0, "SDOPFG": 0, "uunits": 1})
     del ts["_RAIN"]
     return e
 
 
 def _pstemp_(ui, ts):
+    t0 = 16.0 if ui.get("uunits", 1) == 2 else 60.0  # PSTEMP.py:80-88
     return _run("pstemp", ui, ts, int(ui["simlen"]), 6,
-                ui_defaults={"TSOPFG": 0, "AIRTC": 60.0, "SLTMP": 60.0, "ULTMP": 60.0, "LGTMP": 60.0})
+                ui_defaults={"TSOPFG": 0, "AIRTC": t0, "SLTMP": t0, "ULTMP": t0, "LGTMP": t0, "uunits": 1})
 
 
 def _pwtgas_(ui, ts):
@@ -144,7 +145,7 @@ def _pwtgas_(ui, ts):
                  "ALITMP", "ALIDOX", "ALICO2"):  # PWTGAS.py:117-140
         if name not in ts:
             ts[name] = np.full(n, -1.0e30)
-    return _run("pwtgas", ui, ts, n, None, ui_defaults={"GDVFG": 0})
+    return _run("pwtgas", ui, ts, n, None, ui_defaults={"GDVFG": 0, "uunits": 1})
 
 
 def _solids_(ui, ts):
@@ -160,7 +161,7 @@ def _iwtgas_(ui, ts):
     for nm in ("SLITMP", "SLIDOX", "SLICO2"):  # IWTGAS.py:92-94
         if nm not in ts:
             ts[nm] = np.full(n, -1.0e30)
-    return _run("iwtgas", ui, ts, n, None)
+    return _run("iwtgas", ui, ts, n, None, ui_defaults={"uunits": 1})
 
 
 def _pqual_(ui, ts):

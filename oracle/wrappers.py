@@ -43,9 +43,12 @@ def _cal(siminfo):
     return siminfo["_calendar"]
 
 
-def _english(siminfo):
-    if siminfo.get("units", 1) != 1:
-        raise NotImplementedError("oracle restates metric units (uunits == 2) for SNOW, PWATER and IWATER only")
+def _metric(siminfo):
+    return siminfo.get("units", 1) == 2
+
+
+def _arr(ts, name):
+    return np.asarray(ts[name], dtype=np.float64)
 
 
 # metric units (uunits == 2): the reference converts parameters, states and parameter series on entry and the stored series
@@ -198,21 +201,30 @@ def iwater(io_manager, siminfo, uci, ts):
 
 
 def sedmnt(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     n = siminfo["steps"]
     ui = make_ui(uci)
-    ui.update(simlen=n, delt=siminfo["delt"])
+    ui.update(simlen=n, delt=siminfo["delt"], uunits=siminfo.get("units", 1))
     u = uci["PARAMETERS"]
     ts["COVERI"] = cal.initm(uci, u["CRVFG"], "MONTHLY_COVER", u["COVER"]) if "CRVFG" in u else np.full(n, u["COVER"])
     ts["NVSI"] = cal.initm(uci, u["VSIVFG"], "MONTHLY_NVSI", u["NVSI"]) if "VSIVFG" in u else np.full(n, u["NVSI"])
     ts["DAYFG"] = cal.hourflag(0, dofirst=True)
-    return O._sedmnt_(ui, ts), []
+    if not _metric(siminfo):
+        return O._sedmnt_(ui, ts), []
+    # ---- metric (SEDMNT.py:113-117): SURO / SURS back to inches on local copies; NVSI, DETS and the stored series in the core
+    for k in ("PREC", "SLSED", "SNOCOV", "SURO", "SURS"):  # SEDMNT.py:94-96: the zero fills stay in ts
+        if k not in ts:
+            ts[k] = np.zeros(n)
+    t2 = dict(ts)
+    t2["SURO"], t2["SURS"] = _arr(ts, "SURO") * 0.0394, _arr(ts, "SURS") * 0.0394
+    errors = O._sedmnt_(ui, t2)
+    for k in O.fields("sedmnt_out"):
+        ts[k] = t2[k]
+    return errors, []
 
 
 def solids(io_manager, siminfo, uci, ts):
     """SOLIDS.py:16-49"""
-    _english(siminfo)
     cal = _cal(siminfo)
     n = siminfo["steps"]
     for nm in ("SURO", "SURS", "PREC", "SLSLD"):
@@ -224,16 +236,25 @@ def solids(io_manager, siminfo, uci, ts):
     ui = make_ui(uci)
     ui.update(simlen=n, delt60=siminfo["delt"] / 60)
     ts["DAYFG"] = cal.hourflag(0, dofirst=True)
-    return O._solids_(ui, ts), []
+    if not _metric(siminfo):
+        return O._solids_(ui, ts), []
+    # ---- metric: SOLIDS.py:84-88 on entry (local copies), :143-145 on exit
+    m, t2 = dict(ui), dict(ts)
+    t2["ACCSDP"] = _arr(ts, "ACCSDP") * 1.10231 / 2.471
+    t2["SURO"], t2["SURS"] = _arr(ts, "SURO") * 0.0394, _arr(ts, "SURS") * 0.0394
+    m["SLDS"] = ui["SLDS"] * 1.10231 / 2.471
+    errors = O._solids_(m, t2)
+    for k in O.fields("solids_out"):
+        ts[k] = t2[k] / 1.10231 * 2.471
+    return errors, []
 
 
 def iwtgas(io_manager, siminfo, uci, ts):
     """IWTGAS.py:33-63"""
-    _english(siminfo)
     cal = _cal(siminfo)
     n = siminfo["steps"]
     ui = make_ui(uci)
-    ui.update(simlen=n)
+    ui.update(simlen=n, uunits=siminfo.get("units", 1))
     u = uci["PARAMETERS"]
     for nm in ("AWTF", "BWTF"):
         ts[nm] = cal.initm(uci, u["WTFVFG"], "MONTHLY_" + nm, u[nm]) if "WTFVFG" in u else np.full(n, u[nm])
@@ -241,15 +262,24 @@ def iwtgas(io_manager, siminfo, uci, ts):
         if nm not in ts:
             ts[nm] = np.zeros(n)
     ts["DAYFG"] = cal.hourflag(0, dofirst=True)
-    return O._iwtgas_(ui, ts), []
+    if not _metric(siminfo):
+        return O._iwtgas_(ui, ts), []
+    # ---- metric: IWTGAS.py:80-82 (ELEV; SOTMP is overwritten before it is read), :111-114 on local copies; the stored series in the core
+    m, t2 = dict(ui), dict(ts)
+    m["ELEV"] = ui["ELEV"] * 3.281
+    t2["AWTF"] = _f2c_in(_arr(ts, "AWTF"))
+    t2["WYIELD"], t2["SURO"] = _arr(ts, "WYIELD") * 0.0394, _arr(ts, "SURO") * 0.0394
+    errors = O._iwtgas_(m, t2)
+    for k in list(O.fields("iwtgas_out")) + ["SLITMP", "SLIDOX", "SLICO2"]:
+        ts[k] = t2[k]
+    return errors, []
 
 
 def pstemp(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     n = siminfo["steps"]
     ui = make_ui(uci)
-    ui.update(simlen=n, delt=siminfo["delt"])
+    ui.update(simlen=n, delt=siminfo["delt"], uunits=siminfo.get("units", 1))  # metric: inside the core (hsp2_oracle.c)
     u = uci["PARAMETERS"]
     for flag, names in (("SLTVFG", ("ASLT", "BSLT")), ("ULTVFG", ("ULTP1", "ULTP2")), ("LGTVFG", ("LGTP1", "LGTP2"))):
         for nm in names:
@@ -259,16 +289,37 @@ def pstemp(io_manager, siminfo, uci, ts):
 
 
 def pwtgas(io_manager, siminfo, uci, ts):
-    _english(siminfo)
     cal = _cal(siminfo)
     n = siminfo["steps"]
     ui = make_ui(uci)
-    ui.update(simlen=n)
+    ui.update(simlen=n, uunits=siminfo.get("units", 1))
     u = uci["PARAMETERS"]
     for flag, nm in (("IDVFG", "IDOXP"), ("ICVFG", "ICO2P"), ("GDVFG", "ADOXP"), ("GCVFG", "ACO2P")):
         ts[nm] = cal.initm(uci, u[flag], "MONTHLY_" + nm, u[nm]) if flag in u else np.full(n, u[nm])
     ts["DAYFG"] = cal.hourflag(0, dofirst=True)
-    return O._pwtgas_(ui, ts), []
+    if not _metric(siminfo):
+        return O._pwtgas_(ui, ts), []
+    # ---- metric: PWTGAS.py:90-94 (ELEV; SOTMP / IOTMP / AOTMP are overwritten before they are read), :167-174 on local copies
+    # -- the -1e30 fills of absent soil temperatures are converted like any other value --; the stored series in the core
+    m, t2 = dict(ui), dict(ts)
+    m["ELEV"] = ui["ELEV"] * 3.281
+    fills = {}
+    for k in ("WYIELD", "SURO", "IFWO", "AGWO", "SURLI", "IFWLI", "AGWLI"):  # PWTGAS.py:106-108
+        if k not in ts:
+            fills[k] = np.zeros(n)
+    for k in ("SLTMP", "ULTMP", "LGTMP", "SLITMP", "SLIDOX", "SLICO2", "ILITMP", "ILIDOX", "ILICO2", "ALITMP", "ALIDOX", "ALICO2"):
+        if k not in ts:
+            fills[k] = np.full(n, -1.0e30)
+    ts.update(fills)
+    t2.update(fills)
+    for k in ("SLTMP", "ULTMP", "LGTMP"):
+        t2[k] = _f2c_in(_arr(ts, k))
+    for k in ("WYIELD", "SURO", "IFWO", "AGWO"):
+        t2[k] = _arr(ts, k) * 0.0394
+    errors = O._pwtgas_(m, t2)
+    for k in O.fields("pwtgas_out"):
+        ts[k] = t2[k]
+    return errors, []
 
 
 ERRMSGS_PQUAL = ("PQUAL: A constituent must be associated with overland flow in order to receive atmospheric deposition inputs", "")
@@ -324,8 +375,7 @@ def _qual_common(pre, siminfo, uci, ts, monthly_names, adname):
 
 
 def pqual(io_manager, siminfo, uci, ts):
-    """PQUAL.py:26-113"""
-    _english(siminfo)
+    """PQUAL.py:26-113 -- no unit handling in the reference: a metric run reads the flows in the units they were stored in"""
     ui, nquals, n = _qual_common(
         "PQUAL", siminfo, uci, ts,
         (("POTFW", "VPFWFG"), ("POTFS", "VPFSFG"), ("ACQOP", "VQOFG"), ("SQOLIM", "VQOFG"), ("IOQCP", "VIQCFG"), ("AOQCP", "VAQCFG")),
@@ -343,8 +393,7 @@ def pqual(io_manager, siminfo, uci, ts):
 
 
 def iqual(io_manager, siminfo, uci, ts):
-    """IQUAL.py:24-107"""
-    _english(siminfo)
+    """IQUAL.py:24-107 -- no unit handling in the reference (see pqual)"""
     ui, nquals, n = _qual_common("IQUAL", siminfo, uci, ts, (("POTFW", "VPFWFG"), ("ACQOP", "VQOFG"), ("SQOLIM", "VQOFG")),
                                  "IQAD")
     for k in range(1, nquals + 1):
