@@ -69,9 +69,7 @@ def _calendar(siminfo):
 
 
 def _run_section(section, operation, siminfo, uci, ts, **eff_kw):
-    units = int(siminfo.get("units", 1))
-    if units != 1 and section not in ("ATEMP", "SNOW", "PWATER", "IWATER"):
-        raise NotImplementedError("libhsp2g: metric units (siminfo['units'] = 2) are implemented for ATEMP, SNOW, PWATER, IWATER")
+    units = int(siminfo.get("units", 1))  # 2: metric, every section converts where the reference does (segstore.py, csrc/)
     cal = _calendar(siminfo)
     steps = int(siminfo["steps"])
     if steps != cal.steps:
@@ -264,8 +262,7 @@ def _qual(operation, siminfo, uci, ts):
     """PQUAL.py:26-113 / IQUAL.py:24-107: all constituents of the segment in one launch, one row each."""
     from .qualstore import IQUAL_INPUTS, PQUAL_INPUTS, nquals, qual_store
 
-    if siminfo.get("units", 1) != 1:
-        raise NotImplementedError("libhsp2g implements English units (uunits=1) only")
+    # no unit handling in the reference's PQUAL / IQUAL: a metric run reads the flows in the units they were stored in
     imp = operation == "IMPLND"
     sec, adname = ("IQUAL", "IQAD") if imp else ("PQUAL", "PQAD")
     cal = _calendar(siminfo)

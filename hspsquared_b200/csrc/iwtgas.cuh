@@ -1,6 +1,7 @@
 // iwtgas.cuh -- one IWTGAS interval (temperature, dissolved oxygen and CO2 of impervious-land runoff) for one segment.
 //
-// Behaviour: HSPF HIMPGAS as HSP2 runs it, src/hsp2/hsp2/IWTGAS.py:122-183 (_iwtgas_ loop body), English units.
+// Behaviour: HSPF HIMPGAS as HSP2 runs it, src/hsp2/hsp2/IWTGAS.py:122-183 (_iwtgas_ loop body).  Metric runs: AWTF goes to deg F
+// first (:112), wyield / suro arrive as `x * 0.0394` of the stored series, SOTMP is stored in deg C (:160-163), fluxes by save().
 // Differences from PWTGAS' surface branch that matter for parity: the runoff temperature is a regression on air
 // temperature (AWTF + BWTF * airtc, coefficients refreshed on DAYFG intervals), the literal 0.555, and the lateral
 // inflow block: DO and CO2 are only mixed when the lateral TEMPERATURE is present (they nest under it, :151-158).
@@ -26,7 +27,9 @@ __device__ __forceinline__ void iwtgas_step(const SEG &s, IwtgasState &w, double
     const double EFACTA = 407960., MFACTA = 0.2266;
     const double airtc = (airtmp - 32.0) * 0.555;
     if (s.calfl & HSP2G_CAL_DAYFG) {  // IWTGAS.py:132-134
-        w.awtf = (s.daily(FB_M_AWTF, M_AWTF, P_AWTF) - 32.0) * 0.555;
+        double awtf = s.daily(FB_M_AWTF, M_AWTF, P_AWTF);
+        if (s.metric()) awtf = (awtf * 9. / 5.) + 32.;  // IWTGAS.py:112
+        w.awtf = (awtf - 32.0) * 0.555;
         w.bwtf = s.daily(FB_M_BWTF, M_BWTF, P_BWTF);
     }
     double sotmp_out = -1.0e30, sodox = -1.0e30, soco2 = -1.0e30, soht = 0.0, sodoxm = 0.0, soco2m = 0.0;
@@ -51,7 +54,7 @@ __device__ __forceinline__ void iwtgas_step(const SEG &s, IwtgasState &w, double
         soht = sotmp * suro * EFACTA;
         sodoxm = sodox * suro * MFACTA;
         soco2m = soco2 * suro * MFACTA;
-        sotmp_out = (sotmp * 9.0 / 5.0) + 32.0;
+        sotmp_out = s.metric() ? sotmp : (sotmp * 9.0 / 5.0) + 32.0;
     }
     s.save(O_IWTGAS_SOTMP, sotmp_out);
     s.save(O_IWTGAS_SODOX, sodox);

@@ -722,10 +722,15 @@ struct Sched {
 // ---- metric units (siminfo['units'] == 2; HSP2G_OPT_METRIC in L.opts).  The reference keeps every state in English units and
 // converts (a) parameters and initial states on entry -- done by the host in the reference's expression order
 // (hspsquared_b200/segstore.py) --, (b) some parameter SERIES on entry, elementwise after any monthly interpolation (CEPSC, UZSN,
-// RETSC * 0.0394: refresh_daily) and the series one section hands the next (WYIELD), and (c) the STORED series on exit
-// (SNOW.py:569-585, PWATER.py:660-688, IWATER.py:276-283): `x * 25.4`, or `x * 0.555 - 17.777` for the three snow temperatures.
+// RETSC * 0.0394; NVSI * 2.205 / 2.471; ACCSDP * 1.10231 / 2.471; AWTF * 9 / 5 + 32: at the point of use) and the series one
+// section hands the next (WYIELD, SURO, SURS, IFWO, AGWO: stored * 25.4 by the water section, read back * 0.0394 by SEDMNT /
+// PWTGAS / SOLIDS / IWTGAS; the soil temperatures PSTEMP stores in deg C, land_kernels.cuh), and (c) the STORED series on exit
+// (SNOW.py:569-585, PWATER.py:660-688, IWATER.py:276-283, SEDMNT.py:258-262, PWTGAS.py:338-350, SOLIDS.py:143-145,
+// IWTGAS.py:179-182): `x * 25.4`, `x * 0.555 - 17.777` for the three snow temperatures, `x / 1.10231 * 2.471` (tons/ac ->
+// tonnes/ha), `x / 3.96567 * 2.471` (heat), `x / 2.205 * 2.471` (mass).  PSTEMP / PWTGAS / IWTGAS temperatures: the sections
+// themselves store deg C instead of converting to deg F.
 #define OPT_METRIC 2u
-__host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 25.4, 2 x * 0.555 - 17.777
+__host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 25.4, 2 x * 0.555 - 17.777, 3 / 4 / 5 see above
     return (oid == O_SNOW_PAKTMP || oid == O_SNOW_DEWTMP || oid == O_SNOW_SNOTMP) ? 2
            : (oid == O_SNOW_PACKF || oid == O_SNOW_PACKI || oid == O_SNOW_PACKW || oid == O_SNOW_PDEPTH || oid == O_SNOW_NEGHTS ||
               oid == O_SNOW_COVINX || oid == O_SNOW_SNOWE || oid == O_SNOW_SNOWF || oid == O_SNOW_WYIELD || oid == O_SNOW_XLNMLT ||
@@ -733,7 +738,15 @@ __host__ __device__ constexpr int metric_out_code(int oid) {  // 0 as is, 1 x * 
                ? 1
            : (oid >= O_PWATER_AGWET && oid <= O_PWATER_UZS && oid != O_PWATER_PETADJ && oid != O_PWATER_TGWS)                     ? 1
            : (oid >= O_IWATER_IMPEV && oid <= O_IWATER_SURS && oid != O_IWATER_PETADJ)                                             ? 1
-                                                                                                                                   : 0;
+           : (oid == O_SEDMNT_DETS || oid == O_SEDMNT_WSSD || oid == O_SEDMNT_SCRSD || oid == O_SEDMNT_SOSED ||
+              oid == O_SOLIDS_SOSLD || oid == O_SOLIDS_SLDS)
+               ? 3
+           : (oid == O_PWTGAS_SOHT || oid == O_PWTGAS_IOHT || oid == O_PWTGAS_AOHT || oid == O_PWTGAS_POHT || oid == O_IWTGAS_SOHT) ? 4
+           : (oid == O_PWTGAS_SODOXM || oid == O_PWTGAS_SOCO2M || oid == O_PWTGAS_IODOXM || oid == O_PWTGAS_IOCO2M ||
+              oid == O_PWTGAS_AODOXM || oid == O_PWTGAS_AOCO2M || oid == O_PWTGAS_PODOXM || oid == O_PWTGAS_POCO2M ||
+              oid == O_IWTGAS_SODOXM || oid == O_IWTGAS_SOCO2M)
+               ? 5
+               : 0;
 }
 
 // per-thread view of the batch
@@ -911,6 +924,12 @@ struct Seg {
                 v = v * 25.4;
             else if (c == 2)
                 v = (v * 0.555) - 17.777;
+            else if (c == 3)
+                v = HDIV(v, 1.10231) * 2.471;
+            else if (c == 4)
+                v = HDIV(v, 3.96567) * 2.471;
+            else if (c == 5)
+                v = HDIV(v, 2.205) * 2.471;
         }
         if (IO::STATIC) {
             if (io_saved<IO>(oid)) store_out(io_row<IO>(oid), v);

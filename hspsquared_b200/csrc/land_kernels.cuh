@@ -132,6 +132,20 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
                 fx.ifwo = s.forcing(F_IFWO);
                 fx.agwo = s.forcing(F_AGWO);
             }
+            if (perlnd_has_chain(ACT_CT) && s.metric()) {
+                // the later sections read the series the water section STORED, i.e. x * 25.4 (PWATER.py:667-682), and take them
+                // back to inches with * 0.0394 (SEDMNT.py:115-116, PWTGAS.py:172-174); external series are in mm already
+                if (act & HSP2G_ACT_PWATER) {
+                    fx.suro = fx.suro * 25.4;
+                    fx.surs = fx.surs * 25.4;
+                    fx.ifwo = fx.ifwo * 25.4;
+                    fx.agwo = fx.agwo * 25.4;
+                }
+                fx.suro = fx.suro * 0.0394;
+                fx.surs = fx.surs * 0.0394;
+                fx.ifwo = fx.ifwo * 0.0394;
+                fx.agwo = fx.agwo * 0.0394;
+            }
             if (act & HSP2G_ACT_SEDMNT) {
                 const double rain = (s.opts() & OPT_SED_RAIN_IS_PREC) ? prec : link.rainf;
                 sedmnt_step(s, sd, rain, prec, link.snocov, fx.suro, fx.surs);
@@ -146,6 +160,11 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
                 soil.sltmp = s.forcing(F_SLTMP);
                 soil.ultmp = s.forcing(F_ULTMP);
                 soil.lgtmp = s.forcing(F_LGTMP);
+                if (s.metric()) {  // external soil temperatures are deg C (PWTGAS.py:168-170)
+                    soil.sltmp = (soil.sltmp * 9. / 5.) + 32.;
+                    soil.ultmp = (soil.ultmp * 9. / 5.) + 32.;
+                    soil.lgtmp = (soil.lgtmp * 9. / 5.) + 32.;
+                }
             }
             if (act & HSP2G_ACT_PWTGAS) {
                 if (newday) pg.refresh_daily(s);
@@ -230,6 +249,16 @@ __device__ __forceinline__ void implnd_body(const LandLaunch &L) {
             } else {
                 suro = s.forcing(F_SURO);
                 surs = s.forcing(F_SURS);
+            }
+            if ((act & (HSP2G_ACT_SOLIDS | HSP2G_ACT_IWTGAS)) && s.metric()) {
+                // SOLIDS / IWTGAS read the series IWATER stored (x * 25.4, IWATER.py:281-282) back with * 0.0394 (SOLIDS.py:86-87,
+                // IWTGAS.py:114); external series are in mm already
+                if (act & HSP2G_ACT_IWATER) {
+                    suro = suro * 25.4;
+                    surs = surs * 25.4;
+                }
+                suro = suro * 0.0394;
+                surs = surs * 0.0394;
             }
             if (act & HSP2G_ACT_SOLIDS) solids_step(s, sl, suro, surs, prec);
             if (act & HSP2G_ACT_IWTGAS) iwtgas_step(s, ig, airtmp, link.wyield, suro);

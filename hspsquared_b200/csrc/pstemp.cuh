@@ -1,9 +1,11 @@
-// pstemp.cuh -- one PSTEMP interval (soil-layer temperatures) for one segment, English units.
+// pstemp.cuh -- one PSTEMP interval (soil-layer temperatures) for one segment.
 //
 // Behaviour: HSPF HPERTMP as HSP2 runs it, src/hsp2/hsp2/PSTEMP.py:130-215 (_pstemp_ loop body) with the array
 // pre-scalings of :120-126 applied per interval.  From the behavioural spec: the literal 0.555
 // (and 0.5555 for the TSOPFG=1 tables), `airts` frozen at AIRTMP[0] when ATEMP is active, TSOPFG compared as a
-// number, clamps at +-100 C with error counts.
+// number, clamps at +-100 C with error counts.  Metric runs (uunits == 2): the tables and states are deg C already -- no
+// conversion of ASLT / ULTP1 / LGTP1 / ULTP2 / LGTP2 (PSTEMP.py:120-126,146-149) and none of the stored series (:205-215); AIRTMP
+// is still taken from deg F to deg C, as an array on entry there (:110-111), i.e. the same operations on the same values.
 #pragma once
 #include "land_common.cuh"
 
@@ -43,27 +45,28 @@ struct SoilTemps {  // deg F, what PWTGAS reads from ts
 template <bool HOURLY, class SEG>
 __device__ __forceinline__ void pstemp_step(const SEG &s, PstempState &w, double airtmp, SoilTemps &o) {
     const bool hrfg = HOURLY ? true : (s.calfl & HSP2G_CAL_HRFG);
+    const bool metric = s.metric();
     const double airtcs = (w.airts - 32.0) * 0.555;
     const double airtc = (airtmp - 32.0) * 0.555;
     if (hrfg) {
-        const double aslt = (w.aslt - 32.0) * 0.555;
+        const double aslt = metric ? (double)w.aslt : (w.aslt - 32.0) * 0.555;
         const double bslt = w.bslt;
         w.sltmp = aslt + bslt * airtc;
     }
     if (s.flag(FB_TSOP1)) {
         if (hrfg) {
-            const double ault = (w.ultp1 - 32.0) * 0.5555;
+            const double ault = metric ? (double)w.ultp1 : (w.ultp1 - 32.0) * 0.5555;
             const double bult = w.ultp2;
             w.ultmp = ault + bult * airtc;
-            w.lgtmp = (w.lgtp1 - 32.0) * 0.5555;
+            w.lgtmp = metric ? (double)w.lgtp1 : (w.lgtp1 - 32.0) * 0.5555;
         }
     } else {
         const double ulsmo = w.ultp1;
-        const double ultdif = 0.555 * w.ultp2;
+        const double ultdif = metric ? (double)w.ultp2 : 0.555 * w.ultp2;
         const double ultmps = w.ultmp;
         w.ultmp = ultmps + ulsmo * (airtcs + ultdif - ultmps);
         const double lgsmo = w.lgtp1;
-        const double lgtdif = 0.555 * w.lgtp2;
+        const double lgtdif = metric ? (double)w.lgtp2 : 0.555 * w.lgtp2;
         const double lgtmps = w.lgtmp;
         if (s.flag(FB_TSOP0))
             w.lgtmp = lgtmps + lgsmo * (airtcs + lgtdif - lgtmps);
@@ -90,8 +93,10 @@ __device__ __forceinline__ void pstemp_step(const SEG &s, PstempState &w, double
         s.count(E_PSTEMP4, e4);
         s.count(E_PSTEMP5, e5);
     }
-    s.save(O_PSTEMP_AIRTC, (airtc * 9.0 / 5.0) + 32.0);
-    s.save(O_PSTEMP_SLTMP, o.sltmp);
-    s.save(O_PSTEMP_ULTMP, o.ultmp);
-    s.save(O_PSTEMP_LGTMP, o.lgtmp);
+    // metric: the series are stored in deg C; PWTGAS converts what it reads `(x * 9. / 5.) + 32.` (PWTGAS.py:168-170) -- the very
+    // expression above, so `o` is what PWTGAS works on in both unit systems
+    s.save(O_PSTEMP_AIRTC, metric ? airtc : (airtc * 9.0 / 5.0) + 32.0);
+    s.save(O_PSTEMP_SLTMP, metric ? w.sltmp : o.sltmp);
+    s.save(O_PSTEMP_ULTMP, metric ? w.ultmp : o.ultmp);
+    s.save(O_PSTEMP_LGTMP, metric ? w.lgtmp : o.lgtmp);
 }

@@ -1,6 +1,8 @@
 // pwtgas.cuh -- one PWTGAS interval (outflow water temperature, dissolved oxygen, CO2) for one segment.
 //
-// Behaviour: HSPF HPERGAS as HSP2 runs it, src/hsp2/hsp2/PWTGAS.py:172-334 (_pwtgas_ loop body), English units.
+// Behaviour: HSPF HPERGAS as HSP2 runs it, src/hsp2/hsp2/PWTGAS.py:172-334 (_pwtgas_ loop body).  Metric runs: the caller hands
+// the soil temperatures in deg F and the flows in inches as the reference's entry conversions make them (:167-174,
+// land_kernels.cuh); the three outflow temperatures are stored in deg C (:310-320), heat and mass fluxes converted by save().
 // Stateless: every quantity is rebuilt each interval; -1e30 marks "no flow" and is multiplied by the zero flow in
 // the flux terms exactly as the reference does.
 #pragma once
@@ -82,9 +84,10 @@ __device__ __forceinline__ void pwtgas_step(const SEG &s, const PwtgasDaily &g, 
     s.save(O_PWTGAS_POHT, soht + ioht + aoht);
     s.save(O_PWTGAS_PODOXM, sodoxm + iodoxm + aodoxm);
     s.save(O_PWTGAS_POCO2M, soco2m + ioco2m + aoco2m);
-    s.save(O_PWTGAS_SOTMP, sotmp > -1e28 ? (sotmp * 9.0 / 5.0) + 32.0 : sotmp);
-    s.save(O_PWTGAS_IOTMP, iotmp > -1e28 ? (iotmp * 9.0 / 5.0) + 32.0 : iotmp);
-    s.save(O_PWTGAS_AOTMP, aotmp > -1e28 ? (aotmp * 9.0 / 5.0) + 32.0 : aotmp);
+    const bool degf = !s.metric();
+    s.save(O_PWTGAS_SOTMP, (sotmp > -1e28 && degf) ? (sotmp * 9.0 / 5.0) + 32.0 : sotmp);
+    s.save(O_PWTGAS_IOTMP, (iotmp > -1e28 && degf) ? (iotmp * 9.0 / 5.0) + 32.0 : iotmp);
+    s.save(O_PWTGAS_AOTMP, (aotmp > -1e28 && degf) ? (aotmp * 9.0 / 5.0) + 32.0 : aotmp);
     s.save(O_PWTGAS_SODOX, sodox);
     s.save(O_PWTGAS_SOCO2, soco2);
     s.save(O_PWTGAS_IODOX, iodox);

@@ -20,6 +20,8 @@ struct SedmntState {
 };
 
 // rain: RAINF when SNOW (or the PWATER wrapper's NaN fill) put it in ts, else PREC (SEDMNT.py:86-89)
+// metric runs: suro / surs arrive as the reference's `SURO * 0.0394` of the STORED series (land_kernels.cuh); rain is not
+// converted by the reference; the stored series are converted by save() (land_common.cuh metric_out_code)
 template <class SEG>
 __device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double rain, double prec, double snocov,
                                             double suro, double surs) {
@@ -40,6 +42,7 @@ __device__ __forceinline__ void sedmnt_step(const SEG &s, SedmntState &w, double
     }
     if (dayfg) {  // SEDMNT.py:175-179
         w.nvsi = s.daily(FB_M_NVSI, M_NVSI, P_NVSI) * delt / 1440.;
+        if (s.metric()) w.nvsi = HDIV(w.nvsi * 2.205, 2.471);  // SEDMNT.py:79,114: kg/ha to lbs/ac, after the time conversion
         if (s.flag(FB_VSIV_EQ2) && w.drydfg) {
             const double d = w.nvsi * (1440. / delt);
             w.dets = w.dets + d;

@@ -1,6 +1,7 @@
 // solids.cuh -- one SOLIDS interval (accumulation and washoff of solids on impervious land) for one segment.
 //
-// Behaviour: HSPF HIMPSLD as HSP2 runs it, src/hsp2/hsp2/SOLIDS.py:88-140 (_solids_ loop body), English units.
+// Behaviour: HSPF HIMPSLD as HSP2 runs it, src/hsp2/hsp2/SOLIDS.py:88-140 (_solids_ loop body).  Metric runs: suro / surs arrive
+// as the reference's `SURO * 0.0394` of the stored series, ACCSDP is converted where it is used (:84-87), the stored series by save().
 // Same transport-capacity washoff as SEDMNT's (method 1 on SURS+SURO when SDOPFG == 1, else on SURO), then the
 // once-a-day accumulation / removal that only happens after a dry day (DRYDFG latch).  The lateral solids inflow
 // SLSLD is read by the reference but never used (SOLIDS.py:93), so it is not an input here.
@@ -48,8 +49,11 @@ __device__ __forceinline__ void solids_step(const SEG &s, SolidsState &w, double
     if (!dayfg) {  // SOLIDS.py:129-142
         if (prec > 0.0) w.drydfg = 0;
     } else {
-        if (w.drydfg)
-            w.slds = s.daily(FB_M_ACCSDP, M_ACCSDP, P_ACCSDP) + w.slds * (1.0 - s.daily(FB_M_REMSDP, M_REMSDP, P_REMSDP));
+        if (w.drydfg) {
+            double accsdp = s.daily(FB_M_ACCSDP, M_ACCSDP, P_ACCSDP);
+            if (s.metric()) accsdp = HDIV(accsdp * 1.10231, 2.471);  // SOLIDS.py:85: tonnes/ha to tons/ac
+            w.slds = accsdp + w.slds * (1.0 - s.daily(FB_M_REMSDP, M_REMSDP, P_REMSDP));
+        }
         w.drydfg = prec > 0.0 ? 0 : 1;
     }
     s.save(O_SOLIDS_SOSLD, sosld);

@@ -13,7 +13,7 @@ IWATER.py:128-143, SEDMNT.py:63-145, PSTEMP.py:76-128, PWTGAS.py:73-95):
   forcing_fill(...)              replays the wrappers' NaN / zero / -1e30 fills for absent input series.
 
 Unsupported (refused loudly, like the reference or because the reference itself cannot run them):
-metric units (uunits=2), PWATER HWTFG=1 (PWATER.py:107-110), IFRDFG outside {0,1}, a broadcast parameter supplied as an
+PWATER HWTFG=1 (PWATER.py:107-110), IFRDFG outside {0,1}, a broadcast parameter supplied as an
 external time series (SNOW.py:49-51, PWATER.py:51-53).
 """
 from __future__ import annotations
@@ -53,7 +53,7 @@ INIT_DEFAULT = {
     "CEPS": 0.0, "SURS": 0.0, "UZS": 0.001, "IFWS": 0.0, "LZS": 0.001, "AGWS": 0.0, "GWVS": 0.0,
     "RETS": 0.001,
     "SLDS": 0.0,
-    "DETS": 0.0, "PST_SLTMP": 60.0, "PST_ULTMP": 60.0, "PST_LGTMP": 60.0,
+    "DETS": 0.0, "PST_SLTMP": NAN, "PST_ULTMP": NAN, "PST_LGTMP": NAN,  # NaN = absent: 60 deg F / 16 deg C (PSTEMP.py:80-88)
 }
 
 
@@ -263,9 +263,9 @@ def effective(operation, tables, pw_icefg=None, airtfg=None, ext_names=()):
                 if fl in u and _initm(uci, u[fl], "MONTHLY_" + n):
                     flag["M_" + n] = 1
                     mon[n] = _table(uci, "MONTHLY_" + n)
-        init["PST_SLTMP"] = ui.get("SLTMP", 60.0)
-        init["PST_ULTMP"] = ui.get("ULTMP", 60.0)
-        init["PST_LGTMP"] = ui.get("LGTMP", 60.0)
+        init["PST_SLTMP"] = ui.get("SLTMP", NAN)  # absent: the unit system's default, SegmentStore.build
+        init["PST_ULTMP"] = ui.get("ULTMP", NAN)
+        init["PST_LGTMP"] = ui.get("LGTMP", NAN)
 
     if act & _lib.ACT_BITS["PWTGAS"]:
         uci = tables["PWTGAS"]
@@ -357,12 +357,16 @@ class SegmentStore:
                    "PETMAX": lambda x: (x * 9. / 5.) + 32., "PETMIN": lambda x: (x * 9. / 5.) + 32.,
                    "FZG": lambda x: x * 0.0394},  # PWATER.py:194,206-207,240-243; INFILT below; CEPSC / UZSN on the device
         "IWATER": {"LSUR": lambda x: x * 3.28, "PETMAX": lambda x: (x * 9. / 5.) + 32., "PETMIN": lambda x: (x * 9. / 5.) + 32.},
+        "PWTGAS": {"ELEV": lambda x: x * 3.281},  # PWTGAS.py:94 (before ELEVGC); SOTMP / IOTMP / AOTMP are overwritten before use
+        "IWTGAS": {"ELEV": lambda x: x * 3.281},  # IWTGAS.py:82
     }
     METRIC_INIT = {
         "SNOW": {"PACKI": lambda x: x / 25.4, "PACKW": lambda x: x / 25.4, "COVINX": lambda x: x / 25.4,
                  "PAKTMP": lambda x: (x * 9. / 5.) + 32.},  # SNOW.py:114-119; PACKF below (the ice is added first)
         "PWATER": {k: (lambda x: x * 0.0394) for k in ("CEPS", "SURS", "UZS", "IFWS", "LZS", "AGWS", "GWVS")},  # PWATER.py:195-201
         "IWATER": {"RETS": lambda x: x * 0.0394, "SURS": lambda x: x * 0.0394},  # IWATER.py:131-133
+        "SEDMNT": {"DETS": lambda x: x * 1.10231 / 2.471},  # SEDMNT.py:117; the NVSI series on the device
+        "SOLIDS": {"SLDS": lambda x: x * 1.10231 / 2.471},  # SOLIDS.py:88; the ACCSDP series on the device
     }
 
     @classmethod
@@ -379,14 +383,12 @@ class SegmentStore:
         metric = units == 2
         conv_raw, conv_init = {}, {}
         if metric:
-            ok = B["ATEMP"] | B["SNOW"] | B["PWATER"] | B["IWATER"]
-            if act & ~ok:
-                raise NotImplementedError("metric units (siminfo['units'] = 2) are implemented for ATEMP, SNOW, PWATER and IWATER; "
-                                          "this batch also runs %s" % [a for a, b in B.items() if act & b & ~ok])
-            for sec in ("SNOW", "PWATER", "IWATER"):
+            # every section of the path (ATEMP and the quality constituents have no unit handling in the reference); PSTEMP's
+            # tables and states are deg C as they are, below
+            for sec in ("SNOW", "PWATER", "IWATER", "SEDMNT", "PWTGAS", "SOLIDS", "IWTGAS"):
                 if act & B[sec]:
-                    conv_raw.update(cls.METRIC_RAW[sec])
-                    conv_init.update(cls.METRIC_INIT[sec])
+                    conv_raw.update(cls.METRIC_RAW.get(sec, {}))
+                    conv_init.update(cls.METRIC_INIT.get(sec, {}))
 
         def R(name):
             v = raw.get(name, np.full(n, RAW_DEFAULT[name]))
@@ -493,10 +495,11 @@ class SegmentStore:
             s[S["SED_NVSI"]] = R("NVSI") * delt / 1440.0
             s[S["SED_COVER"]] = daily0("COVER")
             s[S["DRYDFG"]] = 1.0
-        if act & B["PSTEMP"]:  # PSTEMP.py:78-101 (English units)
-            s[S["SLTMP"]] = (I("PST_SLTMP") - 32.0) * 0.555
-            s[S["ULTMP"]] = (I("PST_ULTMP") - 32.0) * 0.555
-            s[S["LGTMP"]] = (I("PST_LGTMP") - 32.0) * 0.555
+        if act & B["PSTEMP"]:  # PSTEMP.py:78-101: deg F (default 60) to deg C; a metric run's values are deg C (default 16)
+            for nme in ("SLTMP", "ULTMP", "LGTMP"):
+                v = I("PST_" + nme)
+                v = np.where(np.isnan(v), 16.0 if metric else 60.0, v)
+                s[S[nme]] = v if metric else (v - 32.0) * 0.555
             s[S["AIRTS"]] = NAN  # set from AIRTMP[0] on the device at the first interval (PSTEMP.py:128)
         return st
 

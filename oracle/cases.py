@@ -341,6 +341,9 @@ def build_cases():
     t["SEDMNT"]["PARAMETERS"].update({"SDOPFG": 0, "VSIVFG": 2, "KGER": 0.3, "JGER": 1.5})
     t["PSTEMP"]["PARAMETERS"].update({"TSOPFG": 0, "SLTVFG": 0, "ULTVFG": 0, "LGTVFG": 0, "ASLT": 14.5,
                                       "BSLT": 0.365, "ULTP1": 0.1, "ULTP2": 4.0, "LGTP1": 0.05, "LGTP2": 6.0})
+    for grp in ("PARAMETERS", "STATES"):  # no initial soil temperatures: 16 deg C (PSTEMP.py:80-88)
+        for k in ("AIRTC", "SLTMP", "ULTMP", "LGTMP"):
+            t["PSTEMP"].get(grp, {}).pop(k, None)
     t["PWTGAS"]["PARAMETERS"].update({"IDVFG": 0, "GDVFG": 0, "ICVFG": 1, "GCVFG": 1, "IDOXP": 6.0, "ADOXP": 5.0})
     t["PWTGAS"]["MONTHLY_ICO2P"] = monthly([.05, .05, .06, .07, .08, .1, .12, .12, .1, .08, .06, .05])
     t["PWTGAS"]["MONTHLY_ACO2P"] = monthly([.04, .04, .05, .05, .06, .07, .08, .08, .07, .06, .05, .04])

@@ -176,7 +176,7 @@ def f32_ulp_diff(got32, ref64):
     return int(np.abs(a - b).max()) if a.size else 0
 
 
-def check_metric_batch_kernels(names=("p_metric_pack", "i001_metric"), replicate=3):
+def check_metric_batch_kernels(names=("p_metric_pack", "i001_metric", "cbp_fullchain_metric", "i_chain_metric"), replicate=3):
     """siminfo['units'] == 2 folded into the kernel built for the batch (StaticFlags<.., OPTS>: the conversions of the stored
     series are compiled in, the English-unit batches carry none of them) gives the bits of the general kernel, which reads the
     option from the launch record."""

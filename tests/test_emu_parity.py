@@ -2,6 +2,8 @@
 control flow, executed through the host-compiled TEST DOUBLE of libhsp2g (tests/emu/README.md) and compared with the
 CPU oracle BIT FOR BIT (same glibc libm, no FMA contraction).  The CUDA library itself is exercised by the `-m gpu`
 suite (tests/test_gpu_parity.py) through the same harness."""
+import math
+
 import numpy as np
 import pytest
 
@@ -125,18 +127,31 @@ def test_dispatcher_calls_are_served_from_fused_batches():
     parity.check_lazy_dispatch(n=12)
 
 
-def test_metric_units_refused_where_not_implemented():
-    """siminfo['units'] = 2 is implemented for ATEMP / SNOW / PWATER / IWATER (the reference's conversion sites SNOW.py:114-160,
-    569-585, PWATER.py:193-244,660-688, IWATER.py:86-131,276-283); the other sections refuse it loudly instead of computing in
-    the wrong units."""
+def test_metric_units_entry_conversions_of_the_chain_sections():
+    """siminfo['units'] = 2 in the sections behind the water budget: what the reference converts on entry of each core is
+    converted when the store is built, in its expression order (SEDMNT.py:117, PWTGAS.py:94-95, PSTEMP.py:80-101: a metric run's
+    soil temperatures are deg C as they are, 16 deg C when the table is absent); the per-interval conversions are the kernels'
+    (the *_metric cases of test_fused_bit_exact / test_dropin_bit_exact)."""
     from hspsquared_b200.calendar import Calendar
     from hspsquared_b200.segstore import SegmentStore
     from oracle import cases as CASES
 
     case = CASES.build_cases()["cbp_fullchain"]
+    for grp in ("PARAMETERS", "STATES"):  # no initial soil temperatures: the unit system's defaults
+        for k in ("AIRTC", "SLTMP", "ULTMP", "LGTMP"):
+            case["tables"]["PSTEMP"].get(grp, {}).pop(k, None)
     cal = Calendar("1976-01-01", "1976-01-03", 60, "us")
-    with pytest.raises(NotImplementedError, match="metric"):
-        SegmentStore.from_tables("PERLND", [case["tables"]], cal, units=2)
+    en = SegmentStore.from_tables("PERLND", [case["tables"]], cal, units=1)
+    me = SegmentStore.from_tables("PERLND", [case["tables"]], cal, units=2)
+    P, S = en.P, en.S
+    from hspsquared_b200.segstore import make_ui
+
+    dets = make_ui(case["tables"]["SEDMNT"])["DETS"]
+    assert me.state[S["DETS"], 0] == dets * 1.10231 / 2.471 and en.state[S["DETS"], 0] == dets
+    elev = make_ui(case["tables"]["PWTGAS"])["ELEV"]
+    assert me.par[P["ELEVGC"], 0] == math.pow((288.0 - 0.00198 * (elev * 3.281)) / 288.0, 5.256)
+    assert en.par[P["ELEVGC"], 0] == math.pow((288.0 - 0.00198 * elev) / 288.0, 5.256)
+    assert me.state[S["SLTMP"], 0] == 16.0 and en.state[S["SLTMP"], 0] == (60.0 - 32.0) * 0.555
 
 
 @pytest.mark.parametrize("layout", ["plain", "tiled"])

@@ -90,7 +90,8 @@ def test_chunked_equals_single_pass_bitwise(name):
 @pytest.mark.parametrize("name", ["p001_test10", "i001_test10", "cbp_fullchain", "p_nosnow_iffc2", "flowtest_pwater",
                                   "flowtest_iwater", "i_atemp_snow", "i001_iwtgas", "i_solids_m1_wtf_monthly",
                                   "i_solids_iwtgas_alone", "i001_iqual", "i_iqual_variants", "cbp_pqual", "p_pqual_alone",
-                                  "p_metric_pack", "i001_metric", "flowtest_pwater_metric"])
+                                  "p_metric_pack", "i001_metric", "flowtest_pwater_metric", "cbp_fullchain_metric",
+                                  "i_chain_metric", "i_solids_iwtgas_alone_metric"])
 def test_dropin_vs_oracle(name):
     case = ALL[name]
     ref, ref_err = parity.run_oracle(case)
