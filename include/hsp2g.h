@@ -65,11 +65,13 @@ extern "C" {
 
 /* hsp2g_set_forcing_layout opts */
 #define HSP2G_OPT_SED_RAIN_IS_PREC 1u /* SEDMNT.py:86-89: no RAINF in ts -> RAIN = PREC */
-/* siminfo['units'] == 2 (SNOW.py:114-160,569-585, PWATER.py:193-244,660-688, IWATER.py:86-131,276-283): the parameters and
+/* siminfo['units'] == 2 (SNOW.py:114-160,569-585, PWATER.py:193-244,660-688, IWATER.py:86-131,276-283, SEDMNT.py:113-117,258-262,
+ * PSTEMP.py:80-126,136-149,205-215, PWTGAS.py:90-94,167-174,310-350, SOLIDS.py:84-88,143-145, IWTGAS.py:80-82,111-114,160-182): the parameters and
  * states handed to hsp2g_set_params / hsp2g_set_state are ALREADY converted to the kernels' English units in the reference's
  * expression order (hspsquared_b200/segstore.py does it); with this bit the kernels apply the conversions that happen per
- * interval -- parameter series after monthly interpolation, the series SNOW hands the water section, every stored series.
- * SNOW, PWATER, IWATER and ATEMP only. */
+ * interval -- parameter series after monthly interpolation, the series one section hands the next (stored in metric units,
+ * read back in English ones), every stored series.  All land sections; PQUAL / IQUAL have no unit handling in the reference
+ * and none here (their inputs are read in the units they were stored in). */
 #define HSP2G_OPT_METRIC 2u
 
 typedef struct hsp2g_batch hsp2g_batch;
