@@ -605,7 +605,7 @@ def main():
     # ---- end to end through the public API with plain HOST buffers (H2D and D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier)
+        e2e = run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier, ens0=ens0)
 
     traffic, traffic_src = measured_traffic(kname, n, Tc)
     avg_launch_s = ms * 1e-3 / K
@@ -698,7 +698,7 @@ def pin_to_gpu_numa_node(local_rank):
     return None
 
 
-def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier):
+def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrier, ens0=None):
     """Same metric through the public API a host program calls -- LandBatch.run_chunk -> hsp2g_run_host_ld -- with PLAIN host
     buffers, [interval][row][segment] exactly as the reference's ts arrays stack: nothing is re-tiled on the host, each chunk
     is one (strided) copy each way, H2D, kernel and D2H pipelined over 3 streams / 2 device slots, all inside the timed region.
@@ -774,8 +774,9 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrie
         """ordinary numpy arrays through LandBatch.run(): what a caller who knows nothing about pinned memory pays"""
         from hspsquared_b200.engine import LandBatch
 
-        f = synth.forcing_chunk(ens0, cal, base, Te, names=list(synth.PERLND_FORCINGS))
-        with LandBatch(store0, cal, list(synth.PERLND_FORCINGS), default_save(), device=dev.index or 0) as plain_batch:
+        e0 = ens0 if ens0 is not None else ens  # the ensemble in the generator's own order: no ordering done for the caller
+        f = synth.forcing_chunk(e0, cal, base, Te, names=list(synth.PERLND_FORCINGS))
+        with LandBatch(e0.store(cal), cal, list(synth.PERLND_FORCINGS), default_save(), device=dev.index or 0) as plain_batch:
             return pageable_run(plain_batch, f, steps)
 
     def pageable_run(batch, f, steps):
