@@ -872,6 +872,7 @@ int hsp2g_set_params(hsp2g_batch *b, const double *par, int64_t ld) {
     if (!b || !par) return fail("null argument");
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
+    if (wait_last_launch(b)) return 1;  // a calibration loop re-parameterises between runs: never under a running kernel
     if (upload_rows(b->segblk, SB_ROWS, SB_PAR, par, ld, b->n_seg, b->ntiles, HSP2G_NPAR)) return 1;
     b->have_par = true;
     return 0;
@@ -880,6 +881,7 @@ int hsp2g_set_params(hsp2g_batch *b, const double *par, int64_t ld) {
 int hsp2g_set_flags(hsp2g_batch *b, const uint64_t *flags) {
     if (!b || !flags) return fail("null argument");
     DeviceGuard g(b->device);
+    if (wait_last_launch(b)) return 1;
     if (upload_rows(b->segblk, SB_ROWS, SB_FLAGS, flags, b->n_seg, b->n_seg, b->ntiles, 1)) return 1;
     b->flags_word = flags[0];
     b->flags_uniform = 1;
@@ -898,6 +900,7 @@ int hsp2g_set_monthly(hsp2g_batch *b, int id, const double *tab, int64_t ld) {
     if (id < 0 || id >= HSP2G_NMON) return fail("monthly table id %d out of range", id);
     if (ld < b->n_seg) return fail("ld < n_seg");
     DeviceGuard g(b->device);
+    if (wait_last_launch(b)) return 1;
     const size_t one = (size_t)12 * b->n_seg;
     int slot = b->mslot[id];
     if (slot < 0) {  // a new table: grow the host copy and the tile-major device block by one slot

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
+import weakref
 
 import numpy as np
 
@@ -52,18 +54,42 @@ def pinned_empty(shape, dtype=np.float64, write_combined=False):
 
 
 class _PageLocked:
-    """Page-lock ordinary numpy arrays in place for the duration of a run (cudaHostRegister).  Measured on the B200 hosts
-    (tools/exp_pin.py): registering costs 0.02 s per GB, against 0.4-1.0 s per GB for a fresh cudaHostAlloc, and the copies of
-    a registered array run asynchronously at PCIe speed, where the driver stages a pageable one through a bounce buffer at a
-    tenth of it.  Arrays that already are page-locked (pinned_empty, a caller's own registration) are left alone."""
+    """Page-lock ordinary numpy arrays in place (cudaHostRegister) so that their copies run asynchronously at PCIe speed, where
+    the driver stages a pageable array through a bounce buffer at a tenth of it.  Measured on the B200 hosts
+    (profiles/r2t_run_phases_ordinary_arrays.json): registering the 2.1 + 4.2 GB of one headline chunk costs 0.45-0.8 s, four
+    to seven times the copies and the kernel it serves -- so a registration is KEPT for as long as the array lives (a caller who
+    hands run() the same forcing array or the same out= array again pays it once) and undone by a finalizer when the array is
+    collected, before its memory is returned.  Arrays that already are page-locked (pinned_empty, a caller's own registration)
+    are left alone.  HSP2G_KEEP_REGISTERED=0: register for the duration of the call only."""
 
     MIN_BYTES = 1 << 20
+    KEEP = os.environ.get("HSP2G_KEEP_REGISTERED", "1") != "0"
+    _kept = {}  # (address, bytes) -> weakref.finalize of the array that owns the registration
+    _lock = threading.Lock()
 
     def __init__(self, lib, arrays):
         self.lib, self.ptrs = lib, []
         for a in arrays:
-            if a is not None and a.nbytes >= self.MIN_BYTES and lib.hsp2g_host_register(a.ctypes.data, a.nbytes) == 0:
-                self.ptrs.append(a.ctypes.data)
+            if a is None or a.nbytes < self.MIN_BYTES:
+                continue
+            key = (a.ctypes.data, a.nbytes)
+            with self._lock:
+                fin = self._kept.get(key)
+                if fin is not None and fin.alive:
+                    continue  # still registered from an earlier call
+                if lib.hsp2g_host_register(a.ctypes.data, a.nbytes) != 0:
+                    continue  # refused (already page-locked by somebody else, or not lockable): the copies are staged
+                if self.KEEP:
+                    fin = self._kept[key] = weakref.finalize(a, self._forget, lib, key)
+                    fin.atexit = False  # at interpreter exit the driver unpins everything itself
+                else:
+                    self.ptrs.append(a.ctypes.data)
+
+    @classmethod
+    def _forget(cls, lib, key):
+        with cls._lock:
+            cls._kept.pop(key, None)
+        lib.hsp2g_host_unregister(key[0])
 
     def release(self):
         for ptr in self.ptrs:

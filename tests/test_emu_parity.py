@@ -157,3 +157,37 @@ def test_metric_units_entry_conversions_of_the_chain_sections():
 @pytest.mark.parametrize("layout", ["plain", "tiled"])
 def test_groups_by_option_word_equal_the_mixed_batch(layout):
     parity.check_grouped_batch(n=200, layout=layout)
+
+
+def test_run_keeps_host_registrations_for_the_life_of_the_array():
+    """LandBatch.run() page-locks ordinary numpy arrays in place; the registration is kept while the array lives (a second call
+    with the same forcing / out= arrays registers nothing) and undone when the array is collected (engine._PageLocked)."""
+    import gc
+
+    from hspsquared_b200 import engine, synth
+    from hspsquared_b200.calendar import Calendar
+    from hspsquared_b200.engine import LandBatch
+
+    cal = Calendar("1976-01-01", "1976-01-20", 60, "us")
+    ens = synth.Ensemble("PERLND", 64, seed=5, sections=("SNOW", "PWATER"))
+    names = list(synth.PERLND_FORCINGS)
+    f = synth.forcing_chunk(ens, cal, 0, cal.steps, names=names)
+    assert f.nbytes >= engine._PageLocked.MIN_BYTES
+    with LandBatch(ens.store(cal), cal, names, "all", device=0, order=None) as b:
+        lib, calls = b.lib, []
+        reg, unreg = lib.hsp2g_host_register, lib.hsp2g_host_unregister
+        lib.hsp2g_host_register = lambda p, n: (calls.append(("reg", p)), reg(p, n))[1]
+        lib.hsp2g_host_unregister = lambda p: (calls.append(("unreg", p)), unreg(p))[1]
+        try:
+            out = b.run(f, chunk=200)
+            first = out.copy()
+            assert [c for c in calls if c[0] == "reg"] == [("reg", f.ctypes.data), ("reg", out.ctypes.data)] and len(calls) == 2
+            b.set_state(ens.store(cal).state)
+            b.run(f, chunk=200, out=out)  # same arrays: nothing is registered again
+            assert len(calls) == 2 and np.array_equal(out, first, equal_nan=True)
+            fptr, optr = f.ctypes.data, out.ctypes.data
+            del f, out
+            gc.collect()
+            assert sorted(calls[2:]) == sorted([("unreg", fptr), ("unreg", optr)])
+        finally:
+            lib.hsp2g_host_register, lib.hsp2g_host_unregister = reg, unreg  # the bound functions, with their argtypes
