@@ -782,17 +782,19 @@ def run_e2e(torch, batch, ens, cal, store, n, Tc, K, W, dev, dist, world, barrie
     def pageable_run(batch, f, steps):
         """a batch built with the defaults (the caller's segment order), ordinary arrays in, a float32 array out"""
         batch.set_output_dtype(np.float32)
-        batch.run(f, chunk=Te)  # warm-up
+        ck = (Te + 2) // 3  # three chunks per call: copy-in, kernel and copy-out of neighbouring chunks overlap
+        batch.run(f, chunk=ck)  # warm-up
         barrier()
         t0 = time.perf_counter()
         chk = 0.0
         for _ in range(steps):
-            o = batch.run(f, chunk=Te)
+            o = batch.run(f, chunk=ck)
             chk = float(np.nansum(o[-1, 13:], dtype=np.float64))
         dt = time.perf_counter() - t0
+        batch.run(f, chunk=ck, out=o)  # registers o
         t0 = time.perf_counter()
         for _ in range(steps):
-            batch.run(f, chunk=Te, out=o)
+            batch.run(f, chunk=ck, out=o)
         dt2 = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([dt, dt2], dtype=torch.float64, device=dev)
