@@ -1618,7 +1618,7 @@ void *hsp2g_host_alloc_flags(size_t bytes, unsigned flags) {
 void *hsp2g_host_alloc(size_t bytes) { return hsp2g_host_alloc_flags(bytes, 0); }
 int hsp2g_host_register(void *p, size_t bytes) {
     if (!p || !bytes) return fail("null argument");
-    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);  // one registration serves every device of the process
     if (e != cudaSuccess) {
         (void)cudaGetLastError();  // e.g. already page-locked: not an error of any later launch
         return fail("cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));

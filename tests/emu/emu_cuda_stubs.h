@@ -25,7 +25,7 @@ typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaHostAllocPortable = 1,
-       cudaHostAllocWriteCombined = 4, cudaHostRegisterDefault = 0 };
+       cudaHostAllocWriteCombined = 4, cudaHostRegisterDefault = 0, cudaHostRegisterPortable = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 struct cudaDeviceProp {
     int major, minor;
