@@ -171,6 +171,11 @@ const char *k_outputs = HSP2G_OUT_ATEMP(OA) HSP2G_OUT_SNOW(OS) HSP2G_OUT_PWATER(
 
 // host [rows][ld] (segment-minor) <-> device tile-major rows [tile][row0 + r][32] of a block with `blk_rows` rows per
 // tile.  Padded lanes of the last tile receive copies of the last real segment (land_common.cuh).
+// A synchronous cudaMemcpy FROM PAGEABLE host memory returns once the source is staged; the DMA into device memory may still be
+// in flight (CUDA "API synchronization behavior").  The batch's streams are non-blocking -- they do not order themselves with the
+// default stream -- so every such upload is followed by a wait on the default stream before anything can be launched on them.
+#define H2D_DONE() CU(cudaStreamSynchronize(0))
+
 int upload_rows(double *blk, int blk_rows, int row0, const void *src, int64_t ld, int64_t n_seg, int64_t ntiles,
                 int rows) {
     std::vector<uint64_t> pk((size_t)ntiles * rows * LAND_TILE);
@@ -185,6 +190,7 @@ int upload_rows(double *blk, int blk_rows, int row0, const void *src, int64_t ld
     const size_t w = (size_t)rows * LAND_TILE * 8;
     CU(cudaMemcpy2D(blk + (size_t)row0 * LAND_TILE, (size_t)blk_rows * LAND_TILE * 8, pk.data(), w, w, (size_t)ntiles,
                     cudaMemcpyHostToDevice));
+    H2D_DONE();
     return 0;
 }
 int download_rows(void *dst, int64_t ld, const double *blk, int blk_rows, int row0, int64_t n_seg, int64_t ntiles,
@@ -963,6 +969,7 @@ int hsp2g_set_calendar(hsp2g_batch *b, int64_t n, const uint8_t *flags, const ui
     CU(cudaMalloc((void **)&b->cal, (size_t)(n + 1) * sizeof(CalStep)));
     CU(cudaMemset(b->cal, 0, (size_t)(n + 1) * sizeof(CalStep)));
     CU(cudaMemcpy(b->cal, h.data(), (size_t)n * sizeof(CalStep), cudaMemcpyHostToDevice));
+    H2D_DONE();
     b->ncal = n;
     return 0;
 }
@@ -1015,6 +1022,7 @@ int hsp2g_set_shared_forcing(hsp2g_batch *b, int32_t n_stations, int64_t n_steps
     CU(cudaMemcpy(b->met, series, met_bytes, cudaMemcpyHostToDevice));
     CU(cudaMalloc((void **)&b->station, st.size() * sizeof(int)));
     CU(cudaMemcpy(b->station, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    H2D_DONE();
     CU(cudaMalloc((void **)&b->mfac, (size_t)b->ntiles * b->nf * LAND_TILE * sizeof(double)));
     if (upload_rows(b->mfac, b->nf, 0, mfactor, ld, b->n_seg, b->ntiles, b->nf)) return 1;
     b->n_stations = n_stations;
@@ -1381,6 +1389,7 @@ int hsp2g_gather_create(int device, int64_t n_src_seg, int64_t n_dst, const int6
         return fail("out of device memory");
     }
     cudaMemcpy(h->seg_of, v.data(), v.size() * sizeof(long long), cudaMemcpyHostToDevice);
+    cudaStreamSynchronize(0);  // see H2D_DONE
     *out = h;
     return 0;
 }
@@ -1492,6 +1501,7 @@ int hsp2g_set_output_periods(hsp2g_batch *b, int64_t n, const int32_t *period_of
     b->d_periods = nullptr;
     CU(cudaMalloc((void **)&b->d_periods, (size_t)n * sizeof(int)));
     CU(cudaMemcpy(b->d_periods, period_of_step, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    H2D_DONE();
     b->periods.assign(period_of_step, period_of_step + n);
     return 0;
 }
@@ -1657,6 +1667,7 @@ int hsp2g_device_free(int device, void *p) {
 int hsp2g_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
     DeviceGuard g(device);
     CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    H2D_DONE();
     return 0;
 }
 int hsp2g_memcpy_d2h(int device, void *dst, const void *src, size_t bytes) {
