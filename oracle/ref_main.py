@@ -56,7 +56,17 @@ class MemoryBackend:
             pass
 
 
-def test10_land_model(start="1976-01-01", stop="1976-04-01", clones=1):
+CHAIN_SAVE = {
+    "PSTEMP": ("AIRTC", "SLTMP", "ULTMP", "LGTMP"),
+    "PWTGAS": ("SOTMP", "IOTMP", "AOTMP", "SODOX", "SOCO2", "IODOX", "IOCO2", "AODOX", "AOCO2", "SOHT", "IOHT", "AOHT", "POHT",
+               "SODOXM", "SOCO2M", "IODOXM", "IOCO2M", "AODOXM", "AOCO2M", "PODOXM", "POCO2M"),
+    "SEDMNT": ("DETS", "WSSD", "SCRSD", "SOSED", "COVER"),
+    "SOLIDS": ("SOSLD", "SLDS"),
+    "IWTGAS": ("SOTMP", "SODOX", "SOCO2", "SOHT", "SODOXM", "SOCO2M"),
+}
+
+
+def test10_land_model(start="1976-01-01", stop="1976-04-01", clones=1, units=1):
     """UCI object + input series for test10's PERLND P001 and IMPLND I001 (tables of hspsquared_b200/test10.py, EXT SOURCES
     of test10.uci:891-914 as in ref_harness.TEST10_EXT), SAVE tables = the SaveTable.csv defaults.
     clones > 1: P001..Pnnn and I001..Innn interleaved in the operation sequence, each with its own parameters and MFACTORs;
@@ -72,7 +82,7 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01", clones=1):
     imp["IQUAL"] = test10.iqual_tables()
     tables = {"PERLND": ("P001", test10.perlnd(), PERLND_ACTS), "IMPLND": ("I001", imp, IMPLND_ACTS)}
     if clones > 1:
-        return _cloned_model(u, tables, clones, start, stop)
+        return _cloned_model(u, tables, clones, start, stop, units)
     rows = []
     for op, (seg, t, acts) in tables.items():
         u.uci[(op, "GENERAL", seg)] = {"ACTIVITY": {a: int(t["ACTIVITY"].get(a, 0)) for a in acts}}
@@ -81,18 +91,20 @@ def test10_land_model(start="1976-01-01", stop="1976-04-01", clones=1):
                 continue
             ui = copy.deepcopy(tab)
             ui["SAVE"] = {k: 1 for k in test10.SAVE_DEFAULT.get(act, ())}
+            if units == 2 and act in CHAIN_SAVE:  # the metric run also writes the sections behind the water budget
+                ui["SAVE"] = {k: 1 for k in CHAIN_SAVE[act]}
             if act == "IQUAL":  # SaveTable.csv:264-273 (all 0: written only under saveall)
                 ui["SAVE"] = {k: 0 for k in ("SQO", "SOQSP", "SOQS", "SOQO", "SOQOC", "SOQUAL", "SOQC", "IQADDR", "IQADWT", "IQADEP")}
             u.uci[(op, act, seg)] = ui
         rows.append((op, seg, 60))
         u.ddext_sources[(op, seg)] = [Row(dsn, mf, name, tran, "") for dsn, mf, tran, name in H.TEST10_EXT[op]]
     u.opseq = pd.DataFrame(rows, columns=["OPERATION", "SEGMENT", "INDELT_minutes"])
-    u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": 1}
+    u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": units}  # 2: the tables read as metric values
     wdm = H.read_wdm(H.TEST10_WDM)
     return u, wdm
 
 
-def _cloned_model(u, tables, clones, start, stop):
+def _cloned_model(u, tables, clones, start, stop, units=1):
     import pandas as pd
 
     rows = []
@@ -125,7 +137,7 @@ def _cloned_model(u, tables, clones, start, stop):
             u.ddext_sources[(op, seg)] = [Row(dsn, mf * (1.0 + 0.01 * k) if name == "PREC" else mf, name, tran, "")
                                           for dsn, mf, tran, name in H.TEST10_EXT[op]]
     u.opseq = pd.DataFrame(rows, columns=["OPERATION", "SEGMENT", "INDELT_minutes"])
-    u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": 1}
+    u.siminfo = {"start": pd.Timestamp(start), "stop": pd.Timestamp(stop), "units": units}
     return u, H.read_wdm(H.TEST10_WDM)
 
 

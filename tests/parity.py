@@ -778,7 +778,7 @@ def _dispatch_like_main(io_manager, uci_obj, registry):
     return results, errors_of
 
 
-def check_lazy_dispatch(n=24, device=0):
+def check_lazy_dispatch(n=24, device=0, pairs=(("PERLND", "cbp_fullchain"), ("IMPLND", "i001_test10"))):
     """The drop-in activities called one (segment, activity) at a time by a dispatcher shaped like hsp2.main, over n clones of
     the CBP full-chain PERLND and n of test10's IMPLND 1 with per-segment parameters and forcings: every series left in ts and
     every error vector equals the oracle's run of that segment, while the work was done in one fused batch per operation."""
@@ -790,7 +790,7 @@ def check_lazy_dispatch(n=24, device=0):
     uci, rows, ddext = {}, [], {}
     _DISPATCH_SERIES.clear()
     si = None
-    for op, cname in (("PERLND", "cbp_fullchain"), ("IMPLND", "i001_test10")):
+    for op, cname in pairs:  # the unit system is the first case's (siminfo['units'])
         case = cases[cname]
         s = CASES.siminfo_for(case)
         steps = min(24 * 45, s["steps"])

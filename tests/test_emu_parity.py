@@ -127,6 +127,12 @@ def test_dispatcher_calls_are_served_from_fused_batches():
     parity.check_lazy_dispatch(n=12)
 
 
+def test_dispatcher_calls_are_served_from_fused_batches_in_a_metric_run():
+    """siminfo['units'] = 2 through the dispatcher: the sections behind the water budget find the converted series of the
+    earlier ones in ts, exactly as the reference's wrappers leave them."""
+    parity.check_lazy_dispatch(n=6, pairs=(("PERLND", "cbp_fullchain_metric"), ("IMPLND", "i_chain_metric")))
+
+
 def test_metric_units_entry_conversions_of_the_chain_sections():
     """siminfo['units'] = 2 in the sections behind the water budget: what the reference converts on entry of each core is
     converted when the store is built, in its expression order (SEDMNT.py:117, PWTGAS.py:94-95, PSTEMP.py:80-101: a metric run's

@@ -50,6 +50,34 @@ def test_main_with_dropin_activities_writes_the_same_frames(saveall):
                                                             if not np.array_equal(a[:, i], b[:, i], equal_nan=True)])
 
 
+def test_main_in_a_metric_run_writes_the_same_frames():
+    """siminfo['units'] = 2 through the unmodified main(): every section of test10's PERLND 1 (SNOW, PWATER, PSTEMP, PWTGAS ...)
+    and IMPLND 1 (SNOW, IWATER, SOLIDS, IQUAL) converts where the reference does -- frames identical to the stock Numba run."""
+    from hspsquared_b200 import activities, lazybatch
+    from oracle import ref_main as R
+
+    uci, wdm = R.test10_land_model("1976-01-01", "1976-03-01", units=2)
+    ref = R.run_main(uci, wdm, saveall=True)
+    cfg = H.load()["configuration"]
+    saved = activities.install(cfg)
+    lazybatch.reset()
+    try:
+        got = R.run_main(uci, wdm, saveall=True)
+        stats = dict(lazybatch.STATS)
+    finally:
+        activities.uninstall(saved, cfg)
+    assert set(got) == set(ref)
+    for key in (("PERLND", "P001", "PSTEMP"), ("PERLND", "P001", "PWTGAS"), ("IMPLND", "I001", "SOLIDS")):
+        assert key in ref and ref[key].shape[1] >= 2, key  # the chain sections' frames are there to be compared
+    for key, df in ref.items():
+        g = got[key]
+        assert list(g.columns) == list(df.columns) and g.index.equals(df.index), key
+        assert np.array_equal(g.to_numpy(), df.to_numpy(), equal_nan=True), key
+    # one segment per operation: below the lazy-batching threshold, so every call ran the one-section path, each section finding
+    # the converted series of the earlier ones in ts (the fused metric chain is test_emu_parity's metric dispatcher test)
+    assert stats["fallback"] > 0 and stats["windows"] == 0 and stats["served"] == 0, stats
+
+
 def test_main_over_many_segments_is_served_from_one_fused_batch():
     """SURVEY 8b "granularity mismatch": the unmodified main() walks 70 PERLND + 70 IMPLND clones (parameters and met
     factors varied per segment) one (segment, activity) at a time; the drop-ins advance each operation's segments in ONE fused
