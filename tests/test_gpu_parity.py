@@ -442,6 +442,11 @@ def test_dispatcher_calls_are_served_from_fused_batches():
     parity.check_lazy_dispatch(n=40)
 
 
+def test_dispatcher_calls_are_served_from_fused_batches_in_a_metric_run():
+    """... and with siminfo['units'] = 2: the fused chain hands SEDMNT / PSTEMP / PWTGAS / SOLIDS / IWTGAS the converted series."""
+    parity.check_lazy_dispatch(n=20, pairs=(("PERLND", "cbp_fullchain_metric"), ("IMPLND", "i_chain_metric")))
+
+
 def test_results_stream_into_the_product_store(tmp_path):
     """north_star subsystem 4 on the GPU: SAVEd series leave the device chunk by chunk into pinned buffers and a writer thread
     puts them into the NpyResults store (a SupportsWriteTS / SupportsReadTS backend) while the next chunk computes; every frame
