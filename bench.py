@@ -1123,6 +1123,7 @@ def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
     out = {}
     for key, name, kw in (("implnd_100k", "implnd", {"order": "climate"}),
                           ("fullchain_250k_all84", "fullchain_all", {"K": 12, "order": "climate"}),
+                          ("fullchain_250k_all84_tiled", "fullchain_all", {"K": 12, "order": "climate", "layout": "tiled"}),
                           ("fullchain_250k_cbp10", "fullchain_cbp10", {"K": 10, "order": "climate"}),
                           ("fullchain_250k_one_word_all84", "fullchain_uniform_all", {"K": 12, "order": "climate"}),
                           ("fullchain_250k_one_word_cbp10", "fullchain_uniform_cbp10", {"K": 10, "order": "climate"})):

@@ -142,6 +142,12 @@ def geometry(spec, kind=None):
     return block, lockstep
 
 
+def write_back_stores(spec):
+    """Ordinary write-back stores instead of streaming ones for the saved series (csrc/land_common.cuh HSP_STORE_POLICY)?"""
+    ns = _popc(spec["s0"]) + _popc(spec["s1"]) + _popc(spec["s2"])
+    return bool(spec["plain"]) and ns > 48 and "HSP_STORE_POLICY" not in os.environ.get("HSP2G_JIT_FLAGS", "")
+
+
 def display_name(spec, maxreg, kind=None):
     acts = "|".join(n for i, n in enumerate(ACT_NAMES) if spec["act"] >> i & 1)
     kern = "qual_kernel" if spec["qual"] else ("perlnd_kernel" if spec["op"] == 0 else "implnd_kernel")
@@ -163,6 +169,8 @@ def display_name(spec, maxreg, kind=None):
                                                                       _popc(~spec["mask"] & ((1 << len(_lib.names("flags"))) - 1))))
     if spec.get("opts"):
         parts.append("batch-opts=%#x" % spec["opts"])
+    if write_back_stores(spec):
+        parts.append("stores=write-back")
     block, lockstep = geometry(spec, kind)
     if block != 64 or lockstep:
         parts.append("block=%d%s" % (block, ",lockstep=%d" % lockstep if lockstep else ""))
@@ -183,6 +191,11 @@ def source(spec, maxreg, kind=None):
     if inline_div:
         # small kernels (a known option word removes whole sections): the IEEE division sequence inline at every site
         lines.append("#define HSP_INLINE_DIV")
+    if write_back_stores(spec):
+        # many saved rows in the plain layout: a warp-interval scatters ns pieces of 256 bytes, each in another DRAM page; ordinary
+        # write-back stores let the L2 gather neighbouring tiles' pieces before they leave (all 84 outputs of the full chain: +5.5 %,
+        # profiles/r3d_fullchain_layout_policy.jsonl; no effect on the 24-row headline, profiles/r2z_store_policy.jsonl)
+        lines.append("#define HSP_STORE_POLICY 1")
     block, lockstep = geometry(spec, kind)
     if block != 64:
         lines.append("#define LAND_BLOCK %d" % block)
