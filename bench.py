@@ -1131,6 +1131,19 @@ def run_extras(torch, dev, local_rank, rank, world, dist, cal, stream, peak):
             out[key] = run_config(torch, dev, name, cal, stream, peak, **kw)
         except Exception as ex:
             out[key] = {"error": repr(ex)}
+    # configs[3] over one whole simulated year (the headline's measure; the entries above time the winter window)
+    try:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import bench_config_year
+
+        for key, layout in (("fullchain_250k_all84_year", "plain"), ("fullchain_250k_all84_year_tiled", "tiled")):
+            try:
+                out[key] = bench_config_year.one(torch, dev, "fullchain_all", layout, 128, 8784)
+            except Exception as ex:
+                out[key] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
+    except Exception as ex:
+        out["fullchain_250k_all84_year"] = {"error": repr(ex)}
     try:
         out["watershed_5k_10y_streamed"] = run_watershed_stream(local_rank, cal)
     except Exception as ex:
