@@ -30,6 +30,21 @@
 // sections beyond SNOW+PWATER can run (ACT_CT < 0: any mask)
 __host__ __device__ constexpr bool perlnd_has_chain(int act_ct) { return act_ct < 0 || (act_ct & (int)CHAIN_ACTS) != 0; }
 __host__ __device__ constexpr unsigned long long perlnd_hot(int act_ct) { return HOT_SNOW | HOT_PWATER | (perlnd_has_chain(act_ct) ? HOT_CHAIN : 0ull); }
+// ... as a kernel with compile-time row sets stages them: a batch without lateral inflow series never reads the lateral factors,
+// and the scour coefficients are read on intervals with surface runoff only (from global memory then, like RDCSN while it
+// snows).  71 instead of 76 shared-memory rows per warp: SIX two-warp blocks of the full chain fit an SM (12 resident warps, what
+// its 168 registers allow) instead of five (profiles/r3f_fullchain_all_plain_ncu_summary.md: shared memory was the limiter).
+template <class IO>
+__host__ __device__ constexpr unsigned long long perlnd_hot_io(int act_ct) {
+    unsigned long long h = perlnd_hot(act_ct);
+    if (IO::STATIC && perlnd_has_chain(act_ct)) {
+        if (!((IO::FMASK >> F_SURLI) & 1ull)) h &= ~PBIT(SLIFAC);
+        if (!((IO::FMASK >> F_IFWLI) & 1ull)) h &= ~PBIT(ILIFAC);
+        if (!((IO::FMASK >> F_AGWLI) & 1ull)) h &= ~PBIT(ALIFAC);
+        h &= ~(PBIT(KGER) | PBIT(JGER));
+    }
+    return h;
+}
 #define OPT_SED_RAIN_IS_PREC 1u  // SEDMNT: no RAINF in ts -> RAIN = PREC (SEDMNT.py:86-89)
 
 
@@ -64,7 +79,7 @@ __device__ __forceinline__ void perlnd_body(const LandLaunch &L) {
     HSP_PIN32(lane);  // kept in a register: rematerialising it costs an S2R per use
     const unsigned act = ACT_CT >= 0 ? (unsigned)ACT_CT : L.act;
     const int nf = IO::STATIC ? IO::NF : L.nf;
-    typedef Seg<IO, perlnd_hot(ACT_CT), SHARED, FW, LAY> SegT;
+    typedef Seg<IO, perlnd_hot_io<IO>(ACT_CT), SHARED, FW, LAY> SegT;
     typedef typename ColdPick<HOURLY && IO::STATIC>::type SNOWCOLD;
     constexpr int NCOLD = SnowStateT<SNOWCOLD>::SMEM_ROWS + NCOLD_PWATER + (perlnd_has_chain(ACT_CT) ? NCOLD_CHAIN : 0);
     PipeT<SHARED, LAY> pipe;

@@ -15,7 +15,7 @@
 template <int ACT_CT, bool HOURLY, class IO, int MAXREG, bool SHARED = false>
 static cudaError_t launch_one(LandLaunch &L, int sub_pref, cudaStream_t st, const char **name, const char *nm, int *grid_out) {
     typedef typename LayFor<IO>::type LAY;
-    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>(), SHARED,
+    const size_t smem = land_smem_bytes(IO::STATIC ? IO::NF : L.nf, perlnd_hot_io<IO>(ACT_CT), perlnd_ncold<HOURLY, IO, ACT_CT>(), SHARED,
                                         L.forc_f32 ? 4 : 8);
     auto k = perlnd_kernel<ACT_CT, HOURLY, IO, MAXREG, SHARED, DynFlags, LAY>;
     int cap = 0;

@@ -216,7 +216,7 @@ def source(spec, maxreg, kind=None):
         smem = "land_smem_bytes(IO::NF, 0ull, 0, false, FESZ)"
     elif spec["op"] == 0:
         body = "perlnd_body<ACT, HOURLY, IO, SHARED, FW, LAY>(L);"
-        smem = "land_smem_bytes(IO::NF, perlnd_hot(ACT), perlnd_ncold<HOURLY, IO, ACT>(), SHARED, FESZ)"
+        smem = "land_smem_bytes(IO::NF, perlnd_hot_io<IO>(ACT), perlnd_ncold<HOURLY, IO, ACT>(), SHARED, FESZ)"
     else:
         body = "implnd_body<ACT, HOURLY, IO, SHARED, FW, LAY>(L);"
         smem = "land_smem_bytes(IO::NF, IMPLND_HOT, implnd_ncold<HOURLY, IO>(), SHARED, FESZ)"
