@@ -322,6 +322,10 @@ def build_cases():
     add("i001_metric", "IMPLND", ti, "implnd", units=2)
     fp = {"ACTIVITY": {"PWATER": 1}, "PWATER": copy.deepcopy(FLOWTEST_PERLND)}
     add("flowtest_pwater_metric", "PERLND", fp, "flowtest", steps=8760, year=2018, units=2)
+    # sub-hourly metric run: the time conversions (MGMELT, KMELT, INFILT * delt60) come before the unit conversions
+    t = test10.perlnd()
+    t["ACTIVITY"].update({"PSTEMP": 0, "PWTGAS": 0})
+    add("p001_metric_delt30", "PERLND", t, "perlnd", steps=2 * 24 * 100, delt=30, units=2)
 
     # -- metric units in the other sections (SEDMNT.py:113-117,258-262; PSTEMP.py:80-126,136-149,205-215; PWTGAS.py:90-94,167-174,
     #    310-350; SOLIDS.py:84-88,143-145; IWTGAS.py:80-82,111-114,160-163,179-182): again the English tables read as metric

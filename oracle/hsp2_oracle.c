@@ -555,7 +555,8 @@ void hsp2o_pwater(const pwater_ui *ui, const pwater_in *in, const pwater_out *ou
         double inffac = 1.0;
         const double kgw = 1.0 - pow(in->AGWRC[t], delt60 / 24.0); /* PWATER.py:247 */
         const double lzetp = in->LZETP[t], cepsc = in->CEPSC[t], uzsn = in->UZSN[t];
-        const double infilt = in->INFILT[t] * delt60; /* PWATER.py:215 */
+        /* PWATER.py:215; a metric run multiplies the product by 0.0394 (:239): INFILT_MFAC, 1.0 otherwise (x * 1.0 == x) */
+        const double infilt = (in->INFILT[t] * delt60) * ui->INFILT_MFAC;
         const double kvary = in->KVARY[t], lzsn = in->LZSN[t];
         const double petinp = in->PETINP[t];
         double supy, pet, petadj_out = 0.0;
@@ -1637,7 +1638,7 @@ int hsp2o_perlnd_batch(int64_t nseg, int64_t nsteps, double delt, const double *
             pwater_ui pu = {delt, p[BP_ICEFG], 1.0, p[BP_IFFCFG], p[BP_IFRDFG], p[BP_RTOPFG], p[BP_UZFG], p[BP_VLEFG],
                             p[BP_AGWETP], p[BP_AGWS], p[BP_BASETP], p[BP_CEPS], p[BP_GWVS], p[BP_IFWS], p[BP_INFEXP],
                             p[BP_INFILD], p[BP_LSUR], p[BP_LZS], p[BP_SLSUR], p[BP_SURS], p[BP_UZS], p[BP_FOREST],
-                            p[BP_FZG], p[BP_FZGL]};
+                            p[BP_FZG], p[BP_FZGL], 1.0};
             pwater_in pi;
             pi.AGWLI = zeros; pi.AGWRC = cst[8]; pi.AIRTMP = f + 2 * nsteps; pi.CEPSC = m; pi.DEEPFR = cst[9];
             pi.IFWLI = zeros; pi.INFILT = cst[10]; pi.INTFW = cst[15]; pi.IRC = irc; pi.KVARY = cst[11];

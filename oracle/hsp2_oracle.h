@@ -52,7 +52,7 @@ extern "C" {
 /* ---- PWATER --------------------------------------------------------------------------------- */
 #define PWATER_UI(X) X(delt) X(ICEFG) X(CSNOFG) X(IFFCFG) X(IFRDFG) X(RTOPFG) X(UZFG) X(VLEFG) \
     X(AGWETP) X(AGWS) X(BASETP) X(CEPS) X(GWVS) X(IFWS) X(INFEXP) X(INFILD) X(LSUR) X(LZS) X(SLSUR) \
-    X(SURS) X(UZS) X(FOREST) X(FZG) X(FZGL)
+    X(SURS) X(UZS) X(FOREST) X(FZG) X(FZGL) X(INFILT_MFAC)
 #define PWATER_IN(X) X(AGWLI) X(AGWRC) X(AIRTMP) X(CEPSC) X(DEEPFR) X(IFWLI) X(INFILT) X(INTFW) X(IRC) \
     X(KVARY) X(LGTMP) X(LZETP) X(LZLI) X(LZSN) X(NSUR) X(PACKI) X(PETINP) X(PETMAX) X(PETMIN) X(PREC) \
     X(RAINF) X(SNOCOV) X(SURLI) X(UZLI) X(UZSN) X(WYIELD) X(DAYFG) X(HRFG)

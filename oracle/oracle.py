@@ -106,7 +106,7 @@ def _snow_(ui, ts):
 def _pwater_(ui, ts):
     if int(ui.get("HWTFG", 0)):
         raise NotImplementedError("HWTFG=1 is not implemented in the reference (PWATER.py:107-110)")
-    d = {"ICEFG": 0, "FZG": 1.0, "FZGL": 0.1}
+    d = {"ICEFG": 0, "FZG": 1.0, "FZGL": 0.1, "INFILT_MFAC": 1.0}
     if "CSNOFG" not in ui:  # PWATER.py:159-176 defaults when the PWAT-PARM1 flags are absent
         d.update({"CSNOFG": 0, "IFFCFG": 1, "IFRDFG": 0, "RTOPFG": 0, "UZFG": 0, "VLEFG": 0})
     return _run("pwater", ui, ts, int(ui["steps"]), 10, ui_defaults=d)

@@ -140,10 +140,7 @@ def pwater(io_manager, siminfo, uci, ts):
         m["FZG"] = ui["FZG"] * 0.0394
     for k in ("CEPSC", "UZSN", "LZSN", "WYIELD"):
         t2[k] = np.asarray(ts[k], dtype=np.float64) * 0.0394
-    # INFILT = ts['INFILT'] * delt60, then * 0.0394 (PWATER.py:215, 239): the core multiplies by delt60 itself, so the factor is
-    # folded in on the other side of that product only where that is the same IEEE operation sequence: it is not, in general --
-    # the core is therefore handed INFILT * delt60 * 0.0394 / delt60 only when delt60 == 1; otherwise see _pwater_metric_infilt
-    t2["INFILT"] = _pwater_metric_infilt(np.asarray(ts["INFILT"], dtype=np.float64), siminfo["delt"] / 60.0)
+    m["INFILT_MFAC"] = 0.0394  # INFILT = ts['INFILT'] * delt60, then * 0.0394 (PWATER.py:215, 239): the second product is the core's
     t2["KVARY"] = np.asarray(ts["KVARY"], dtype=np.float64) / 0.0394
     t2["PETMAX"] = _f2c_in(np.asarray(ts["PETMAX"], dtype=np.float64))
     t2["PETMIN"] = _f2c_in(np.asarray(ts["PETMIN"], dtype=np.float64))
@@ -151,15 +148,6 @@ def pwater(io_manager, siminfo, uci, ts):
     for k in O.fields("pwater_out"):
         ts[k] = t2[k] * 25.4 if k in PWATER_OUT_METRIC else t2[k]
     return errors, ERRMSGS_PWATER
-
-
-def _pwater_metric_infilt(infilt, delt60):
-    """The series the English core must be handed so that its `INFILT[t] * delt60` (PWATER.py:215) equals the reference's metric
-    `(INFILT[t] * delt60) * 0.0394` (PWATER.py:215, 239).  For hourly runs (delt60 == 1.0, x * 1.0 == x) that is INFILT * 0.0394;
-    other steps would need the product inside the core."""
-    if delt60 != 1.0:
-        raise NotImplementedError("oracle: metric PWATER restated for hourly runs (delt == 60)")
-    return infilt * 0.0394
 
 
 def iwater(io_manager, siminfo, uci, ts):
