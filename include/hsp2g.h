@@ -237,7 +237,7 @@ int hsp2g_reset_errors(hsp2g_batch *b);
 /* Scheduling of one launch.  When a batch has more 32-segment tiles than the GPU holds warps, a launch is cut into
  * tasks of `sub_steps` intervals of one tile, drawn in order by the resident warps, so the device stays full to the
  * end of the chunk; a tile's state passes from task to task through the segment store, results are bit-identical.
- * Default 64; 0 = one task per tile (whole chunk). */
+ * Default 64 (with overlapping launches, below: half a launch when that is longer); 0 = one task per tile (whole chunk). */
 int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps);
 /* Overlap of consecutive launches (off by default).  A launch ends with a tail: the last tasks finish one by one while the rest
  * of the device idles (4 % of a 438-interval launch over 100,000 segments).  With overlap on, an hsp2g_run_device /
@@ -247,7 +247,8 @@ int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps);
  * The caller's side of the contract: the forcing buffer of a call is complete, and its output buffer free and distinct from the
  * previous call's, when the PREVIOUS call is enqueued -- anything enqueued on the stream between two calls (a copy, an event, a
  * kernel of another batch) orders the second call after it in the ordinary way and simply switches the overlap off for that pair.
- * Applies to batches that run their own kernel (hsp2g_set_kernel_image) on a grid that fills the device. */
+ * Applies to batches that run their own kernel (hsp2g_set_kernel_image) on a grid that fills the device, to launches cut into
+ * at least two tasks per tile. */
 int hsp2g_set_launch_overlap(hsp2g_batch *b, int on);
 /* launches made that way so far (instrumentation: tests check that the overlap really happened) */
 int64_t hsp2g_chained_launches(const hsp2g_batch *b);
