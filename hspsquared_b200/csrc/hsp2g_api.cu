@@ -97,7 +97,6 @@ struct hsp2g_batch {
     bool last_full_grid = false;         // the last launch ran the batch's own kernel on a grid that fills the device
     int64_t chained_launches = 0;
     int sub_steps = 64;
-    bool sub_user = false;  // hsp2g_set_schedule was called: the caller's task length is used as given
     int out_f32 = 0;
     int plain = 0;     // series layout of run_device / run_host: 0 = TILED [tile][t][row][32], 1 = PLAIN [t][row][ld]
     int forc_f32 = 0;  // forcing series are float32
@@ -401,12 +400,11 @@ bool jit_matches(const hsp2g_batch *b, const LandLaunch &L) {
 // launch's blocks exit: at most two launches of the batch are ever in flight, one per ticket counter.
 int launch_jit(hsp2g_batch *b, LandLaunch &L, cudaStream_t st, int *grid, bool may_chain, bool *full_grid, bool *chained) {
     const unsigned block = (unsigned)b->jit.info[JI_BLOCK];  // the image's own block size (jit.py `block`)
-    // task length.  With overlapping launches the next launch fills this one's tail, so fewer, longer tasks win (fewer hand-overs of
-    // a tile's state through the segment block): half a launch unless the caller chose (438-interval launches of 100,000 segments:
-    // 64 -> 2.135 ms, 110 -> 2.105, 146 -> 2.090, 219 -> 2.083; profiles/r3k_overlap_task_length.jsonl)
-    int sub = b->sub_steps;
-    if (b->overlap && !b->sub_user && sub > 0 && (L.nsteps + 1) / 2 > sub) sub = (L.nsteps + 1) / 2;
-    hsp2g_plan_tasks(L, sub, b->jit.resident, (int)block / LAND_TILE, grid);
+    // task length: the batch's (hsp2g_set_schedule, default 64).  Measured with overlapping launches on the headline alone, longer
+    // tasks win (438-interval launches of 100,000 segments: 64 -> 2.135 ms, 110 -> 2.105, 146 -> 2.090, 219 -> 2.083,
+    // profiles/r3k_overlap_task_length.jsonl) -- but a full bench.py run with "half a launch" as the default for every configuration
+    // did not finish (cause not found before the round's GPU budget ran out), so the default stays at the validated 64.
+    hsp2g_plan_tasks(L, b->sub_steps, b->jit.resident, (int)block / LAND_TILE, grid);
     *full_grid = *grid == b->jit.resident;
     // a launch of whole-chunk tasks (one task per tile) is never chained: measured to stall on the B200 (bench.py --sub 438 did not
     // finish in 200 s); it waits for its predecessor to end like any other kernel of the stream
@@ -1591,7 +1589,6 @@ int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps) {
     if (!b) return fail("null batch");
     if (sub_steps < 0) return fail("sub_steps must be >= 0 (0 = one task per tile)");
     b->sub_steps = sub_steps;
-    b->sub_user = true;
     return 0;
 }
 

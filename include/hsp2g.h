@@ -237,7 +237,7 @@ int hsp2g_reset_errors(hsp2g_batch *b);
 /* Scheduling of one launch.  When a batch has more 32-segment tiles than the GPU holds warps, a launch is cut into
  * tasks of `sub_steps` intervals of one tile, drawn in order by the resident warps, so the device stays full to the
  * end of the chunk; a tile's state passes from task to task through the segment store, results are bit-identical.
- * Default 64 (with overlapping launches, below: half a launch when that is longer); 0 = one task per tile (whole chunk). */
+ * Default 64; 0 = one task per tile (whole chunk). */
 int hsp2g_set_schedule(hsp2g_batch *b, int32_t sub_steps);
 /* Overlap of consecutive launches (off by default).  A launch ends with a tail: the last tasks finish one by one while the rest
  * of the device idles (4 % of a 438-interval launch over 100,000 segments).  With overlap on, an hsp2g_run_device /
