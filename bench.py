@@ -635,7 +635,7 @@ def main():
     finished = threading.Event()
 
     def watchdog():
-        limit = float(os.environ.get("HSP2G_BENCH_LEGS_S", "1200"))
+        limit = float(os.environ.get("HSP2G_BENCH_LEGS_S", "600"))
         if finished.wait(limit):
             return
         if rank == 0:
